@@ -1,0 +1,156 @@
+"""TF-1.15 op semantics restated with torch CPU fp32 ops.  TEST INFRASTRUCTURE ONLY.
+
+Every function cites the reference call site it follows (paths relative to the upstream
+repo root).  Layouts are the reference's: activations NHWC, conv filters HWIO
+(`[kh,kw,Cin,Cout]`), transposed-conv filters `[kh,kw,Cout,Cin]`.
+
+PARITY UNPINNED (see oracle/__init__.py).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def _same_pad(in_size: int, k: int, s: int):
+    """TF 'SAME' padding split: out=ceil(in/s); extra pad goes to bottom/right."""
+    out = -(-in_size // s)
+    total = max((out - 1) * s + k - in_size, 0)
+    before = total // 2
+    return out, before, total - before
+
+
+def conv2d_same(x: torch.Tensor, w: torch.Tensor, stride: int = 1) -> torch.Tensor:
+    """tf.nn.conv2d(x, W, strides=[1,s,s,1], padding='SAME')  (FCN.py:130).
+
+    x: [N,H,W,Cin]; w: [kh,kw,Cin,Cout] -> [N,ceil(H/s),ceil(W/s),Cout]. Cross-correlation.
+    """
+    kh, kw = w.shape[0], w.shape[1]
+    _, pt, pb = _same_pad(x.shape[1], kh, stride)
+    _, pl, pr = _same_pad(x.shape[2], kw, stride)
+    xn = x.permute(0, 3, 1, 2)
+    xn = F.pad(xn, (pl, pr, pt, pb))
+    y = F.conv2d(xn, w.permute(3, 2, 0, 1), stride=stride)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def conv2d_transpose_same(x: torch.Tensor, w: torch.Tensor, out_hw, stride: int) -> torch.Tensor:
+    """tf.nn.conv2d_transpose(x, W[kh,kw,Cout,Cin], output_shape, [1,s,s,1], 'SAME')
+    (FCN.py:106,155).  Defined as the input-gradient of the SAME conv2d whose input has
+    `output_shape`:  y[n, i*s - p + ky, j*s - p + kx, co] += x[n,i,j,ci] * W[ky,kx,co,ci].
+    """
+    kh, kw = w.shape[0], w.shape[1]
+    oh, ow = out_hw
+    _, pt, _ = _same_pad(oh, kh, stride)
+    _, pl, _ = _same_pad(ow, kw, stride)
+    xn = x.permute(0, 3, 1, 2)
+    # torch conv_transpose2d weight: [Cin, Cout, kh, kw]
+    wt = w.permute(3, 2, 0, 1)
+    full = F.conv_transpose2d(xn, wt, stride=stride)  # no padding: size (in-1)*s + k
+    y = full[:, :, pt:pt + oh, pl:pl + ow]
+    # when (in-1)*s+k-pt < oh the tail would be short; the hot-path layers (k=2s) never hit it
+    assert y.shape[2] == oh and y.shape[3] == ow, (y.shape, oh, ow)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def bias_add(x: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """tf.nn.bias_add (FCN.py:107,132,157)."""
+    return x + b
+
+
+def relu(x: torch.Tensor) -> torch.Tensor:
+    """tf.nn.relu (FCN.py:134)."""
+    return torch.relu(x)
+
+
+def max_pool_2x2(x: torch.Tensor) -> torch.Tensor:
+    """tf.nn.max_pool(ksize 2x2, stride 2, 'VALID') (FCN.py:163). Autograd routes the
+    gradient to the first maximal element in row-major window order, as TF's MaxPoolGrad."""
+    y = F.max_pool2d(x.permute(0, 3, 1, 2), 2, 2)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def max_pool_2x2_with_argmax(x: np.ndarray):
+    """NumPy restatement of the 2x2/s2 VALID max-pool with the in-window index (0..3,
+    row-major (dy,dx)) of the FIRST maximal element (strict '>' scan), i.e. the element
+    TF's MaxPoolGrad routes the gradient to."""
+    n, h, w, c = x.shape
+    oh, ow = h // 2, w // 2
+    win = np.stack([x[:, 0:2 * oh:2, 0:2 * ow:2], x[:, 0:2 * oh:2, 1:2 * ow:2],
+                    x[:, 1:2 * oh:2, 0:2 * ow:2], x[:, 1:2 * oh:2, 1:2 * ow:2]], axis=0)
+    best = win[0].copy()
+    idx = np.zeros(best.shape, np.uint8)
+    for k in range(1, 4):
+        gt = win[k] > best
+        best = np.where(gt, win[k], best)
+        idx = np.where(gt, np.uint8(k), idx)
+    return best, idx
+
+
+def max_pool_2x2_grad(dy: np.ndarray, idx: np.ndarray, in_hw) -> np.ndarray:
+    """MaxPoolGrad from the stored in-window index."""
+    n, oh, ow, c = dy.shape
+    h, w = in_hw
+    dx = np.zeros((n, h, w, c), dy.dtype)
+    for k in range(4):
+        ky, kx = divmod(k, 2)
+        dx[:, ky:2 * oh:2, kx:2 * ow:2] = np.where(idx == k, dy, 0)
+    return dx
+
+
+def dropout(x: torch.Tensor, keep_prob: float, mask: torch.Tensor | None) -> torch.Tensor:
+    """tf.nn.dropout(x, keep_prob) = x * floor(keep_prob + U[0,1)) / keep_prob (FCN.py:167).
+    TF's RNG stream is not reproducible, so the keep-mask (0/1) is injected."""
+    if keep_prob >= 1.0 or mask is None:
+        return x
+    return x * mask / keep_prob
+
+
+def softmax_cross_entropy_with_logits(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """tf.nn.softmax_cross_entropy_with_logits(logits=, labels=) over the last axis
+    (FCN.py:334): loss = sum_c labels_c * (log sum exp z - z_c), z = logits - max."""
+    z = logits - logits.max(dim=-1, keepdim=True).values
+    lse = torch.log(torch.exp(z).sum(dim=-1, keepdim=True))
+    return (labels * (lse - z)).sum(dim=-1)
+
+
+def argmax_last(logits: torch.Tensor) -> torch.Tensor:
+    """tf.argmax(logits, 3): int64, first index on ties (FCN.py:111)."""
+    return torch.argmax(logits, dim=-1)
+
+
+def confusion_matrix(gt: np.ndarray, pred: np.ndarray, ncls: int = 2) -> np.ndarray:
+    """cm[gt,pred] int64 (new functionality)."""
+    return np.bincount((gt.astype(np.int64) * ncls + pred.astype(np.int64)).ravel(),
+                       minlength=ncls * ncls).reshape(ncls, ncls).astype(np.int64)
+
+
+def iou_road(cm: np.ndarray) -> float:
+    d = cm[1, 1] + cm[0, 1] + cm[1, 0]
+    return float(cm[1, 1]) / float(d) if d else 0.0
+
+
+def adam_tf_step(p, m, v, g, t: int, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
+    """tf.train.AdamOptimizer ApplyAdam (FCN.py:338-340), TF formula (epsilon outside the
+    bias correction): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps).
+    Operates in-place on fp32 torch tensors; t starts at 1."""
+    lr_t = np.float32(lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t))
+    m.mul_(b1).add_(g, alpha=1.0 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1.0 - b2)
+    p.sub_(lr_t * m / (v.sqrt() + eps))
+    return float(lr_t)
+
+
+def momentum_tf_step(p, a, g, lr, mu):
+    """tf.train.MomentumOptimizer: a = mu*a + g; p -= lr*a."""
+    a.mul_(mu).add_(g)
+    p.sub_(lr * a)
+
+
+def to_bf16_grid(x: torch.Tensor) -> torch.Tensor:
+    """Round an fp32 tensor to the nearest bf16 value (kept as fp32).  Used to build the
+    'bf16-storage' variant of the oracle that mirrors where the CUDA path rounds."""
+    return x.to(torch.bfloat16).to(torch.float32)

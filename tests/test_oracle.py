@@ -1,0 +1,134 @@
+"""Oracle self-checks (CPU): the torch restatement vs naive NumPy loops, fp64 finite
+differences, TF-Adam closed form, and the ln2 initial loss (SURVEY §4 tier 1)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import naive, tf_ops as T
+from oracle.fcn_oracle import FCN8sOracle, init_variables, synthetic_batch, variable_shapes
+
+
+@pytest.mark.parametrize("k,s,h,w", [(3, 1, 5, 7), (7, 1, 5, 6), (1, 1, 4, 4), (3, 2, 7, 8), (4, 2, 6, 6)])
+def test_conv2d_same_vs_naive(k, s, h, w):
+    rng = np.random.default_rng(k * 10 + s)
+    x = rng.standard_normal((2, h, w, 3)).astype(np.float32)
+    wt = rng.standard_normal((k, k, 3, 4)).astype(np.float32)
+    got = T.conv2d_same(torch.tensor(x), torch.tensor(wt), s).numpy()
+    ref = naive.conv2d_same_naive(x, wt, s)
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("k,s", [(4, 2), (16, 8)])
+def test_conv2d_transpose_vs_naive_and_grad_definition(k, s):
+    rng = np.random.default_rng(k)
+    x = rng.standard_normal((1, 3, 4, 2)).astype(np.float32)
+    wt = rng.standard_normal((k, k, 3, 2)).astype(np.float32)   # [kh,kw,Cout,Cin]
+    oh, ow = 3 * s, 4 * s
+    got = T.conv2d_transpose_same(torch.tensor(x), torch.tensor(wt), (oh, ow), s).numpy()
+    ref = naive.conv2d_transpose_same_naive(x, wt, (oh, ow), s)
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-5)
+    # definition: input-gradient of the SAME conv2d whose input has output_shape
+    inp = torch.zeros((1, oh, ow, 3), dtype=torch.float64, requires_grad=True)
+    out = T.conv2d_same(inp, torch.tensor(wt, dtype=torch.float64), s)
+    out.backward(torch.tensor(x, dtype=torch.float64))
+    np.testing.assert_allclose(inp.grad.numpy(), ref, rtol=1e-9, atol=1e-9)
+
+
+def test_max_pool_argmax_first_max_and_grad():
+    rng = np.random.default_rng(0)
+    x = rng.integers(0, 3, (2, 6, 8, 5)).astype(np.float32)    # many ties
+    y, idx = T.max_pool_2x2_with_argmax(x)
+    yn, idxn = naive.max_pool_2x2_naive(x)
+    assert np.array_equal(y, yn) and np.array_equal(idx, idxn)
+    yt = T.max_pool_2x2(torch.tensor(x)).numpy()
+    assert np.array_equal(y, yt)
+    # gradient routing equals torch autograd (== TF MaxPoolGrad first-max rule)
+    xt = torch.tensor(x, requires_grad=True)
+    dy = rng.standard_normal(y.shape).astype(np.float32)
+    T.max_pool_2x2(xt).backward(torch.tensor(dy))
+    assert np.array_equal(T.max_pool_2x2_grad(dy, idx, (6, 8)), xt.grad.numpy())
+
+
+def test_softmax_xent_and_grad():
+    rng = np.random.default_rng(1)
+    lg = rng.standard_normal((2, 3, 4, 2)).astype(np.float32) * 5
+    lab = rng.integers(0, 2, (2, 3, 4))
+    onehot = np.eye(2, dtype=np.float32)[lab]
+    lt = torch.tensor(lg, requires_grad=True)
+    loss = T.softmax_cross_entropy_with_logits(lt, torch.tensor(onehot))
+    ref_loss, ref_grad = naive.softmax_xent_naive(lg, onehot)
+    np.testing.assert_allclose(loss.detach().numpy(), ref_loss, rtol=1e-5, atol=1e-6)
+    loss.sum().backward()
+    np.testing.assert_allclose(lt.grad.numpy(), ref_grad, rtol=1e-5, atol=1e-6)
+
+
+def test_adam_tf_formula_closed_form_and_differs_from_torch():
+    g = 1e-10
+    p, m, v = torch.zeros(1), torch.zeros(1), torch.zeros(1)
+    T.adam_tf_step(p, m, v, torch.full((1,), g), 1)
+    lr_t = 1e-4 * math.sqrt(1 - 0.999) / (1 - 0.9)
+    exp = -lr_t * (0.1 * g) / (math.sqrt(0.001 * g * g) + 1e-8)
+    assert abs(float(p) - exp) <= 1e-6 * abs(exp)
+    assert abs(float(p)) == pytest.approx(3.16e-8, rel=2e-2)
+    # three steps vs explicit recurrence in fp64
+    p, m, v = torch.zeros(3), torch.zeros(3), torch.zeros(3)
+    gs = [torch.tensor([1e-3, -2e-9, 5.0]), torch.tensor([2e-3, 1e-9, -1.0]), torch.tensor([0.0, 3e-9, 2.0])]
+    pe, me, ve = np.zeros(3), np.zeros(3), np.zeros(3)
+    for t, gt in enumerate(gs, 1):
+        T.adam_tf_step(p, m, v, gt, t)
+        gn = gt.numpy().astype(np.float64)
+        me = 0.9 * me + 0.1 * gn
+        ve = 0.999 * ve + 0.001 * gn * gn
+        pe -= 1e-4 * math.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t) * me / (np.sqrt(ve) + 1e-8)
+    np.testing.assert_allclose(p.numpy(), pe, rtol=1e-4)
+
+
+def test_confusion_matrix_and_iou():
+    gt = np.array([[0, 0, 1, 1, 1]])
+    pr = np.array([[0, 1, 1, 1, 0]])
+    cm = T.confusion_matrix(gt, pr)
+    assert cm.tolist() == [[1, 1], [1, 2]] and cm.dtype == np.int64
+    assert T.iou_road(cm) == pytest.approx(2 / 4)
+
+
+def test_variable_inventory():
+    shapes = variable_shapes(3, 2)
+    assert len(shapes) == 40   # 20 layers x (weights, biases); SURVEY says 38, miscounted
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 138_873_924
+    assert list(shapes)[-1] == "conv_t3/bias"
+
+
+@pytest.fixture(scope="module")
+def small_model():
+    variables = init_variables(cin=3, ncls=2, fc=128, seed=1234, init="ref")
+    return variables
+
+
+def test_initial_loss_is_ln2_and_logit_scale(small_model):
+    x, lab = synthetic_batch(1, 32, 64, seed=0)
+    o = FCN8sOracle(small_model)
+    pred, logits = o.forward(x)
+    assert pred.shape == (1, 32, 64, 1) and pred.dtype == torch.int64
+    assert logits.shape == (1, 32, 64, 2)
+    loss = float(o.loss(logits, lab))
+    assert abs(loss - math.log(2.0)) < 1e-4
+
+
+def test_fd_gradient_check_small_graph():
+    """fp64 finite differences through conv->relu->pool->deconv->xent built from tf_ops."""
+    torch.manual_seed(0)
+    x = torch.randn(1, 4, 4, 2, dtype=torch.float64)
+    w1 = torch.randn(3, 3, 2, 3, dtype=torch.float64, requires_grad=True)
+    wt = torch.randn(4, 4, 2, 3, dtype=torch.float64, requires_grad=True)
+    lab = torch.nn.functional.one_hot(torch.randint(0, 2, (1, 4, 4)), 2).double()
+
+    def f(w1_, wt_):
+        a = T.relu(T.conv2d_same(x, w1_))
+        p = T.max_pool_2x2(a)
+        lg = T.conv2d_transpose_same(p, wt_, (4, 4), 2)
+        return T.softmax_cross_entropy_with_logits(lg, lab).mean()
+
+    assert torch.autograd.gradcheck(f, (w1, wt), eps=1e-6, atol=1e-5)
