@@ -1,0 +1,198 @@
+/*
+ * segk.h — C ABI of libsegk.so: the B200 (sm_100a) segmentation hot path.
+ *
+ * The reference (SeunghwanByun/SemanticSegmentation_Tensorflow) has no FFI of its own:
+ * its boundary is a set of Python helpers that each wrap one TensorFlow op.  Every entry
+ * point below names the reference call site it replaces (paths relative to the upstream
+ * repo root).  All tensors are caller-owned DEVICE pointers; every call enqueues work on
+ * the caller's `stream` (a cudaStream_t passed as void*) and returns without
+ * synchronising.  No torch types, no hidden allocation on the hot path.
+ *
+ * Layouts: activations NHWC bf16 (channel pitch = `ld*` elements where given), images
+ * u8/f32 NHWC, logits f32 NHWC, master weights fp32 in the reference's HWIO order
+ * (`[kh,kw,Cin,Cout]`; transposed conv `[kh,kw,Cout,Cin]`, FCN.py:125,143).
+ *
+ * Return value: 0 = OK, negative = error (see enum); text via segk_last_error().
+ * There is NO CPU fallback: an unsupported shape returns SEGK_EINVAL.
+ */
+#ifndef SEGK_H
+#define SEGK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEGK_ABI_VERSION 1
+
+enum {
+  SEGK_OK = 0,
+  SEGK_EINVAL = -1,  /* unsupported shape / dtype / null pointer */
+  SEGK_ECUDA = -2,   /* CUDA runtime or driver error */
+  SEGK_ENOMEM = -3
+};
+
+typedef struct segk_ctx segk_ctx;
+
+/* ---- context ---------------------------------------------------------------------- */
+int segk_abi_version(void);
+int segk_create(int device, segk_ctx** out);
+int segk_destroy(segk_ctx* ctx);
+const char* segk_last_error(segk_ctx* ctx);
+/* number of kernels launched through this ctx since creation (bench.py gpu_launches) */
+int64_t segk_launch_count(segk_ctx* ctx);
+int segk_sm_count(segk_ctx* ctx);
+
+/* ---- epilogue flags for the conv family ------------------------------------------------ */
+#define SEGK_EPI_RELU 1u      /* y = max(y,0) after bias (+residual)            */
+#define SEGK_EPI_OUT_F32 2u   /* y stored as fp32 instead of bf16               */
+
+/*
+ * conv_layer forward: relu(conv2d(x, W, stride 1, SAME) + b)        (FCN.py:117-136)
+ *   x [N,H,W,Cin] bf16; wk = kernel-layout weights [kh*kw][Cout][Cin] bf16 produced by
+ *   segk_pack_conv_weights; bias fp32 [Cout] or NULL; residual (same shape as y, bf16) is
+ *   added before the ReLU when non-NULL (the `fuse` skip-add, FCN.py:169-171).
+ *   tcgen05 path: requires Cin % 64 == 0 and Cout % 64 == 0, odd kh,kw, kh*kw <= 64.
+ */
+int segk_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* bias,
+                    const void* residual, void* y, int N, int H, int W, int Cin, int Cout,
+                    int kh, int kw, unsigned flags, void* stream);
+
+/*
+ * Conv2DBackpropInput of the above (part of what `optimizer.minimize` emits, FCN.py:340):
+ *   dx = dy (*) rot180(W);  wd = dgrad-layout weights [kh*kw (taps reversed)][Cin][Cout] bf16.
+ *   dx = ((acc + residual) masked by relu_mask > 0) * scale, where
+ *   relu_mask (shape of dx, bf16, or NULL) is the forward activation whose ReluGrad is
+ *   fused here, residual (or NULL) a second gradient path into the same tensor (AddN at
+ *   pool3/pool4), and scale = 1/keep_prob folds the dropout backward (FCN.py:165-167).
+ */
+int segk_conv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask,
+                      const void* residual, void* dx, float scale, int N, int H, int W,
+                      int Cin, int Cout, int kh, int kw, void* stream);
+
+/*
+ * Conv2DBackpropFilter of conv_layer (FCN.py:340): dw[kh,kw,Cin,Cout] fp32 HWIO
+ * (+= when accumulate != 0, else overwritten).  Split-K over pixels with fp32 atomics.
+ * BiasAddGrad is segk_bias_grad.  Requires N*H*W tileable into 64-pixel boxes.
+ */
+int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H,
+                      int W, int Cin, int Cout, int kh, int kw, int accumulate, void* stream);
+
+/*
+ * deconv_layer forward: conv2d_transpose(x, W[k,k,Cout,Cin], stride s, SAME) + b, k = 2s
+ * (FCN.py:138-159).  x [N,H,W,Cin] bf16 -> y [N,sH,sW,Cout]; wk = phase-packed weights
+ * from segk_pack_deconv_weights; residual = skip tensor added in the epilogue (fuse_1 /
+ * fuse_2, FCN.py:92,96).  tcgen05 path: Cin % 64 == 0 and Cout % 64 == 0.
+ */
+int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* bias,
+                      const void* residual, void* y, int N, int H, int W, int Cin, int Cout,
+                      int k, int s, unsigned flags, void* stream);
+
+/* gradient of deconv_layer wrt its input = conv2d(dy, W, stride s);
+ * dy [N,sH,sW,Cout] bf16, wd [k*k][Cin][Cout] bf16, dx [N,H,W,Cin] bf16. k=4, s=2. */
+int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask,
+                        void* dx, int N, int H, int W, int Cin, int Cout, int k, int s,
+                        void* stream);
+
+/* gradient of deconv_layer wrt W[k,k,Cout,Cin] (fp32). k=4, s=2. */
+int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H,
+                        int W, int Cin, int Cout, int k, int s, int accumulate, void* stream);
+
+/* ---- small-channel layers on CUDA cores (conv1_1 Cin=3/4, conv8 Cout=2, conv_t1 Cin=2,
+ *      conv_t3 Cout=2) ----------------------------------------------------------------- */
+/* conv_layer forward for ragged channel counts.  x_dtype: 0 = bf16, 2 = u8 (raw image,
+ * FCN.py:312).  w fp32 HWIO, output bf16.  Supported: K = kh*kw*Cin <= 64 (any Cout), or
+ * 1x1 with Cout in {2,4,8} and Cin % 8 == 0. */
+int segk_conv2d_small_fwd(segk_ctx* ctx, const void* x, int x_dtype, const float* w,
+                          const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                          int kh, int kw, unsigned flags, void* stream);
+/* 1x1, Cout in {2,4,8}: dx = ((dy W^T) masked by relu_mask > 0) * scale */
+int segk_conv2d_small_dgrad(segk_ctx* ctx, const void* dy, const float* w, const void* relu_mask,
+                            void* dx, float scale, int N, int H, int W, int Cin, int Cout,
+                            int kh, int kw, void* stream);
+int segk_conv2d_small_wgrad(segk_ctx* ctx, const void* x, int x_dtype, const void* dy, float* dw,
+                            int N, int H, int W, int Cin, int Cout, int kh, int kw,
+                            void* stream);
+/* deconv_layer (any Cin/Cout, k = 2s) on CUDA cores: fwd / dgrad / wgrad; w fp32
+ * [k,k,Cout,Cin]; dy may be fp32 (the logits gradient) or bf16. */
+int segk_deconv2d_small_fwd(segk_ctx* ctx, const void* x, const float* w, const float* bias,
+                            const void* residual, void* y, int N, int H, int W, int Cin,
+                            int Cout, int k, int s, unsigned flags, void* stream);
+int segk_deconv2d_small_dgrad(segk_ctx* ctx, const void* dy, int dy_is_f32, const float* w,
+                              const void* relu_mask, void* dx, int N, int H, int W, int Cin,
+                              int Cout, int k, int s, void* stream);
+int segk_deconv2d_small_wgrad(segk_ctx* ctx, const void* x, const void* dy, int dy_is_f32,
+                              float* dw, int N, int H, int W, int Cin, int Cout, int k, int s,
+                              void* stream);
+
+/* ---- weight layout packing (fp32 master -> bf16 kernel layouts) ------------------------ */
+/* w[kh,kw,Cin,Cout] fp32 (HWIO, FCN.py:125) -> wk[tap][Cout][Cin] bf16 (fwd) and
+ * wd[ntaps-1-tap][Cin][Cout] bf16 (dgrad: taps reversed = rot180).  Either may be NULL. */
+int segk_pack_conv_weights(segk_ctx* ctx, const float* w, void* wk, void* wd, int kh, int kw,
+                           int Cin, int Cout, void* stream);
+/* w[k,k,Cout,Cin] fp32 (k = 2s, FCN.py:143) ->
+ *   wk[ay*s+ax][uy*2+ux][Cout][Cin] bf16 = w[ay+s*(1-uy)][ax+s*(1-ux)]  (deconv fwd phases)
+ *   wd[ky*k+kx][Cin][Cout] bf16                                           (deconv dgrad)   */
+int segk_pack_deconv_weights(segk_ctx* ctx, const float* w, void* wk, void* wd, int k, int s,
+                             int Cin, int Cout, void* stream);
+
+/* ---- HBM-bound kernels --------------------------------------------------------------- */
+/* max_pool 2x2/s2 VALID (FCN.py:161-163): y [N,H/2,W/2,C] bf16 and the in-window index of
+ * the first maximal element (0..3, row-major) as u8 — bit-exact vs the oracle. */
+int segk_maxpool2x2_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int N, int H, int W,
+                        int C, void* stream);
+/* MaxPoolGrad from the stored index, fused with the ReluGrad of the pooled activation:
+ * dx[n,y,x,c] = (idx==k ? dy : 0) * [act > 0]  (act may be NULL: no mask). */
+int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const void* act,
+                        void* dx, int N, int H, int W, int C, void* stream);
+
+/* tf.nn.dropout (FCN.py:165-167): y = x * keep_mask / keep_prob.  mask (u8 0/1) is used
+ * when non-NULL (parity runs); otherwise Philox4x32-10(seed, element index). Same call is
+ * the backward (pass dy as x). */
+int segk_dropout(segk_ctx* ctx, const void* x, void* y, const uint8_t* mask, int64_t n,
+                 float keep_prob, uint64_t seed, void* stream);
+
+/* reduce_mean(softmax_cross_entropy_with_logits) + its gradient + argmax (FCN.py:334,111):
+ *   logits f32 [npix,C] (C = 2), labels u8 class ids [npix];
+ *   dlogits (f32, may be NULL) = (softmax - onehot) * grad_scale   (grad_scale =
+ *   1/(world*N*H*W)); pred (u8, may be NULL) = argmax, ties -> 0;
+ *   loss_sum (f32[1]) = sum over pixels of the per-pixel loss (deterministic two-stage);
+ *   cm (int64[4], may be NULL) += confusion counts cm[gt*2+pred].
+ *   workspace: >= segk_xent_workspace_bytes(npix) bytes. */
+size_t segk_xent_workspace_bytes(int64_t npix);
+int segk_softmax_xent_fwd_bwd(segk_ctx* ctx, const float* logits, const uint8_t* labels,
+                              float* dlogits, uint8_t* pred, float* loss_sum, int64_t* cm,
+                              void* workspace, int64_t npix, int C, float grad_scale,
+                              void* stream);
+/* tf.nn.softmax + road mask (FCN.py:229,204-206): prob f32 [npix,C] (may be NULL),
+ * mask u8 [npix] = prob[...,1] > 0.5 (may be NULL) */
+int segk_softmax_infer(segk_ctx* ctx, const float* logits, float* prob, uint8_t* mask,
+                       int64_t npix, int C, void* stream);
+/* road / non-road confusion matrix (new): cm[gt*2+pred] += counts */
+int segk_confusion_matrix(segk_ctx* ctx, const uint8_t* gt, const uint8_t* pred, int64_t* cm,
+                          int64_t npix, void* stream);
+
+/* tf.train.AdamOptimizer ApplyAdam over a flat fp32 arena (FCN.py:338-340), TF formula:
+ *   m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t m / (sqrt(v) + eps),
+ *   lr_t = lr sqrt(1-b2^t)/(1-b1^t) computed by the caller.  g is multiplied by
+ *   grad_scale first (1.0, or 1/world when the allreduce was a plain sum of means). */
+int segk_adam_step(segk_ctx* ctx, float* p, float* m, float* v, const float* g, int64_t n,
+                   float lr_t, float beta1, float beta2, float eps, float grad_scale,
+                   void* stream);
+/* tf.train.MomentumOptimizer: a = mu a + g; p -= lr a (new) */
+int segk_momentum_step(segk_ctx* ctx, float* p, float* a, const float* g, int64_t n, float lr,
+                       float mu, float grad_scale, void* stream);
+
+/* ---- misc device utilities ------------------------------------------------------------ */
+/* u8/f32 NHWC image -> bf16 NHWC (the feed_dict cast of FCN.py:312,395) */
+int segk_cast_to_bf16(segk_ctx* ctx, const void* x, int x_dtype, void* y, int64_t n, void* stream);
+/* db[c] = sum over rows of dy[rows, C] (BiasAddGrad); dy bf16 or f32 */
+int segk_bias_grad(segk_ctx* ctx, const void* dy, int dy_is_f32, float* db, int64_t rows, int C,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGK_H */

@@ -1,0 +1,51 @@
+// Context management for libsegk.so.
+#include "common.cuh"
+
+extern "C" {
+
+int segk_abi_version(void) { return SEGK_ABI_VERSION; }
+
+int segk_create(int device, segk_ctx** out) {
+  if (!out) return SEGK_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || device < 0 || device >= ndev) return SEGK_ECUDA;
+  segk_ctx* ctx = new (std::nothrow) segk_ctx();
+  if (!ctx) return SEGK_ENOMEM;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete ctx;
+    return SEGK_ECUDA;
+  }
+  if (prop.major != 10) {  // sm_100a only: no fallback code path exists
+    delete ctx;
+    return SEGK_EINVAL;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  cudaSetDevice(device);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    delete ctx;
+    return SEGK_ECUDA;
+  }
+  ctx->encode_tiled = reinterpret_cast<decltype(ctx->encode_tiled)>(fn);
+  *out = ctx;
+  return SEGK_OK;
+}
+
+int segk_destroy(segk_ctx* ctx) {
+  delete ctx;
+  return SEGK_OK;
+}
+
+const char* segk_last_error(segk_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+int64_t segk_launch_count(segk_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int segk_sm_count(segk_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+}  // extern "C"

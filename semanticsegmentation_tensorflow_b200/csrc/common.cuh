@@ -1,0 +1,67 @@
+// Shared helpers for libsegk.so (sm_100a only).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/segk.h"
+
+struct segk_ctx {
+  int device = 0;
+  int sm_count = 148;
+  std::atomic<int64_t> launches{0};
+  char err[512] = {0};
+  // driver entry point resolved at segk_create (no link-time libcuda dependency)
+  CUresult (*encode_tiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                           const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                           CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                           CUtensorMapFloatOOBfill) = nullptr;
+};
+
+inline int segk_fail(segk_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define SEGK_REQUIRE(ctx, cond, ...)                                   \
+  do {                                                                 \
+    if (!(cond)) return segk_fail((ctx), SEGK_EINVAL, __VA_ARGS__);    \
+  } while (0)
+
+// call after a kernel launch: counts it and converts launch errors into a status
+#define SEGK_LAUNCHED(ctx, what)                                                        \
+  do {                                                                                  \
+    (ctx)->launches.fetch_add(1, std::memory_order_relaxed);                            \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess)                                                             \
+      return segk_fail((ctx), SEGK_ECUDA, "%s: %s", (what), cudaGetErrorString(e__));   \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float bf2f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ bf16 f2bf(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
+  return __bfloat1622float2(t);
+}

@@ -1,0 +1,599 @@
+// HBM-bound kernels of the segmentation hot path: max-pool fwd/bwd (bit-exact argmax
+// routing), dropout, fused softmax-xent + gradient + argmax + confusion counts, Adam /
+// momentum, casts, bias-grad and weight-layout packing.  All are pure streaming kernels:
+// 16-byte vector accesses, grid = multiple of the SM count, grid-stride loops.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int stream_grid(segk_ctx* ctx, int64_t work_items, int per_sm = 8) {
+  int64_t blocks = ceil_div64(work_items, kThreads);
+  int64_t cap = (int64_t)ctx->sm_count * per_sm;
+  return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+// ------------------------------------------------------------------------------------
+// max-pool 2x2 / stride 2 / VALID  (FCN.py:161-163).  One thread = 8 channels (16 B) of one
+// pooled pixel.  idx = first maximal element under a strict '>' scan in (dy,dx) row-major
+// order: exactly the element TF's MaxPoolGrad (and torch) route the gradient to.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const uint4* __restrict__ x,
+                                                               uint4* __restrict__ y,
+                                                               uint2* __restrict__ idx, int N, int H,
+                                                               int W, int C8) {
+  const int OH = H >> 1, OW = W >> 1;
+  const int64_t total = (int64_t)N * OH * OW * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % C8);
+    int64_t p = i / C8;
+    int ox = (int)(p % OW);
+    p /= OW;
+    int oy = (int)(p % OH);
+    int n = (int)(p / OH);
+    const int64_t row0 = ((int64_t)(n * H + 2 * oy) * W + 2 * ox) * C8 + c8;
+    uint4 v[4];
+    v[0] = __ldg(x + row0);
+    v[1] = __ldg(x + row0 + C8);
+    v[2] = __ldg(x + row0 + (int64_t)W * C8);
+    v[3] = __ldg(x + row0 + (int64_t)W * C8 + C8);
+    uint32_t outw[4];
+    uint32_t idxw[2] = {0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w0 = (&v[0].x)[j];
+      float2 best = unpack_bf16x2(w0);
+      uint32_t bits_lo = w0 & 0xffffu, bits_hi = w0 >> 16;
+      uint32_t k_lo = 0, k_hi = 0;
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        const uint32_t wk = (&v[k].x)[j];
+        float2 f = unpack_bf16x2(wk);
+        if (f.x > best.x) { best.x = f.x; bits_lo = wk & 0xffffu; k_lo = k; }
+        if (f.y > best.y) { best.y = f.y; bits_hi = wk >> 16; k_hi = k; }
+      }
+      outw[j] = bits_lo | (bits_hi << 16);
+      const int e = 2 * j;  // element index within the 8-channel group
+      idxw[e >> 2] |= (k_lo << (8 * (e & 3))) | (k_hi << (8 * ((e + 1) & 3)));
+    }
+    y[i] = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+    idx[i] = make_uint2(idxw[0], idxw[1]);
+  }
+}
+
+// MaxPoolGrad from the stored index fused with ReluGrad of the pooled activation.
+__global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const uint4* __restrict__ dy,
+                                                               const uint2* __restrict__ idx,
+                                                               const uint4* __restrict__ act,
+                                                               uint4* __restrict__ dx, int N, int H,
+                                                               int W, int C8) {
+  const int OH = H >> 1, OW = W >> 1;
+  const int64_t total = (int64_t)N * OH * OW * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % C8);
+    int64_t p = i / C8;
+    int ox = (int)(p % OW);
+    p /= OW;
+    int oy = (int)(p % OH);
+    int n = (int)(p / OH);
+    const int64_t row0 = ((int64_t)(n * H + 2 * oy) * W + 2 * ox) * C8 + c8;
+    const int64_t offs[4] = {row0, row0 + C8, row0 + (int64_t)W * C8, row0 + (int64_t)W * C8 + C8};
+    const uint4 g = __ldg(dy + i);
+    const uint2 id = __ldg(idx + i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint4 a = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // +1.0 pairs
+      if (act) a = __ldg(act + offs[k]);
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int e = 2 * j;
+        const uint32_t k_lo = ((&id.x)[e >> 2] >> (8 * (e & 3))) & 0xffu;
+        const uint32_t k_hi = ((&id.x)[e >> 2] >> (8 * ((e + 1) & 3))) & 0xffu;
+        const float2 af = unpack_bf16x2((&a.x)[j]);
+        const uint32_t gw = (&g.x)[j];
+        uint32_t lo = (k_lo == (uint32_t)k && af.x > 0.f) ? (gw & 0xffffu) : 0u;
+        uint32_t hi = (k_hi == (uint32_t)k && af.y > 0.f) ? (gw & 0xffff0000u) : 0u;
+        o[j] = lo | hi;
+      }
+      dx[offs[k]] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// dropout (FCN.py:165-167).  Philox4x32-10 keyed by (seed), counter = element index / 4.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+__global__ void __launch_bounds__(kThreads) dropout_kernel(const bf16* __restrict__ x,
+                                                           bf16* __restrict__ y,
+                                                           const uint8_t* __restrict__ mask, int64_t n,
+                                                           float keep, float inv_keep, uint64_t seed) {
+  const int64_t n4 = (n + 3) >> 2;
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n4;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (!mask)
+      r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), 0u, 0u),
+                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t e = q * 4 + j;
+      if (e >= n) break;
+      bool kp;
+      if (mask) kp = mask[e] != 0;
+      else kp = ((&r.x)[j] >> 8) * (1.0f / 16777216.0f) < keep;
+      y[e] = kp ? f2bf(bf2f(x[e]) * inv_keep) : f2bf(0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// fused softmax-xent + dlogits + argmax + confusion counts (FCN.py:334,111), C == 2 fast
+// path (float2 / pixel) and a generic small-C path.  Loss: per-block partial sums written to
+// the workspace, then summed in a fixed order by a single block => deterministic.
+// ------------------------------------------------------------------------------------
+constexpr int kXentBlocks = 148 * 8;
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (w == 0) {
+    t = (l < (int)(blockDim.x >> 5)) ? sh[l] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  __syncthreads();
+  return t;  // valid in warp 0
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreads) xent_kernel(const float* __restrict__ logits,
+                                                        const uint8_t* __restrict__ labels,
+                                                        float* __restrict__ dlogits,
+                                                        uint8_t* __restrict__ pred,
+                                                        float* __restrict__ partial,
+                                                        unsigned long long* __restrict__ cm,
+                                                        int64_t npix, int Crt, float scale) {
+  __shared__ float sh[32];
+  __shared__ unsigned int cm_sh[4];
+  if (threadIdx.x < 4) cm_sh[threadIdx.x] = 0;
+  __syncthreads();
+  float loss = 0.f;
+  unsigned int cnt[4] = {0, 0, 0, 0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int lab = labels[i];
+    int am = 0;
+    if (C == 2) {
+      const float2 l = __ldg(reinterpret_cast<const float2*>(logits) + i);
+      const float mx = fmaxf(l.x, l.y);
+      const float z0 = l.x - mx, z1 = l.y - mx;
+      const float e0 = expf(z0), e1 = expf(z1);
+      const float s = e0 + e1;
+      loss += logf(s) - (lab ? z1 : z0);
+      am = l.y > l.x ? 1 : 0;
+      if (dlogits) {
+        const float inv = 1.f / s;
+        float2 d;
+        d.x = (e0 * inv - (lab == 0 ? 1.f : 0.f)) * scale;
+        d.y = (e1 * inv - (lab == 1 ? 1.f : 0.f)) * scale;
+        reinterpret_cast<float2*>(dlogits)[i] = d;
+      }
+    } else {
+      const float* l = logits + i * Crt;
+      float mx = l[0];
+      for (int c = 1; c < Crt; ++c) {
+        if (l[c] > mx) { mx = l[c]; am = c; }
+      }
+      float s = 0.f;
+      for (int c = 0; c < Crt; ++c) s += expf(l[c] - mx);
+      loss += logf(s) - (l[lab] - mx);
+      if (dlogits) {
+        const float inv = 1.f / s;
+        for (int c = 0; c < Crt; ++c)
+          dlogits[i * Crt + c] = (expf(l[c] - mx) * inv - (c == lab ? 1.f : 0.f)) * scale;
+      }
+    }
+    if (pred) pred[i] = (uint8_t)am;
+    if (C == 2) cnt[(lab & 1) * 2 + am]++;
+  }
+  if (cm && C == 2) {
+    // warp-aggregated: one shared-memory atomic per warp per bin, one global per block
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      unsigned int w = __reduce_add_sync(0xffffffffu, cnt[b]);
+      if ((threadIdx.x & 31) == 0 && w) atomicAdd(&cm_sh[b], w);
+    }
+  }
+  const float tot = block_sum(loss, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+  if (cm && C == 2 && threadIdx.x < 4 && cm_sh[threadIdx.x])
+    atomicAdd(&cm[threadIdx.x], (unsigned long long)cm_sh[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(kThreads) sum_partials_kernel(const float* __restrict__ partial,
+                                                                int n, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float v = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += partial[i];
+  const float t = block_sum(v, sh);
+  if (threadIdx.x == 0) *out = t;
+}
+
+__global__ void __launch_bounds__(kThreads) softmax_infer_kernel(const float* __restrict__ logits,
+                                                                 float* __restrict__ prob,
+                                                                 uint8_t* __restrict__ mask,
+                                                                 int64_t npix, int C) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float* l = logits + i * C;
+    float mx = l[0];
+    for (int c = 1; c < C; ++c) mx = fmaxf(mx, l[c]);
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += expf(l[c] - mx);
+    const float inv = 1.f / s;
+    float p1 = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float p = expf(l[c] - mx) * inv;
+      if (prob) prob[i * C + c] = p;
+      if (c == 1) p1 = p;
+    }
+    if (mask) mask[i] = p1 > 0.5f ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) confusion_kernel(const uint8_t* __restrict__ gt,
+                                                             const uint8_t* __restrict__ pred,
+                                                             unsigned long long* __restrict__ cm,
+                                                             int64_t npix) {
+  __shared__ unsigned int cm_sh[4];
+  if (threadIdx.x < 4) cm_sh[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned int cnt[4] = {0, 0, 0, 0};
+  // 16 pixels per thread per iteration (uint4 of u8) where aligned
+  const int64_t n16 = npix >> 4;
+  const uint4* g4 = reinterpret_cast<const uint4*>(gt);
+  const uint4* p4 = reinterpret_cast<const uint4*>(pred);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 g = __ldg(g4 + i), p = __ldg(p4 + i);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t gw = (&g.x)[j] & 0x01010101u, pw = (&p.x)[j] & 0x01010101u;
+      const uint32_t both = gw & pw, gonly = gw & ~pw, ponly = pw & ~gw;
+      const unsigned c11 = __popc(both), c10 = __popc(gonly), c01 = __popc(ponly);
+      cnt[3] += c11; cnt[2] += c10; cnt[1] += c01; cnt[0] += 4 - c11 - c10 - c01;
+    }
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t i = (n16 << 4) + threadIdx.x; i < npix; i += blockDim.x)
+      cnt[(gt[i] & 1) * 2 + (pred[i] & 1)]++;
+  }
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    unsigned int w = __reduce_add_sync(0xffffffffu, cnt[b]);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(&cm_sh[b], w);
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 && cm_sh[threadIdx.x])
+    atomicAdd(&cm[threadIdx.x], (unsigned long long)cm_sh[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------
+// optimizers (FCN.py:338-340).  28 B/param: p,m,v read+write (24) + g read (4).
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, float* __restrict__ m,
+                                                        float* __restrict__ v,
+                                                        const float* __restrict__ g, int64_t n,
+                                                        float lr_t, float b1, float b2, float eps,
+                                                        float gs) {
+  const int64_t n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const float c1 = 1.f - b1, c2 = 1.f - b2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = __ldg(g4 + i);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gj = (&gg.x)[j] * gs;
+      float mj = b1 * (&mm.x)[j] + c1 * gj;
+      float vj = b2 * (&vv.x)[j] + c2 * gj * gj;
+      (&mm.x)[j] = mj;
+      (&vv.x)[j] = vj;
+      (&pp.x)[j] -= lr_t * mj / (sqrtf(vj) + eps);
+    }
+    p4[i] = pp; m4[i] = mm; v4[i] = vv;
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      const float gj = g[i] * gs;
+      const float mj = b1 * m[i] + c1 * gj;
+      const float vj = b2 * v[i] + c2 * gj * gj;
+      m[i] = mj; v[i] = vj;
+      p[i] -= lr_t * mj / (sqrtf(vj) + eps);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) momentum_kernel(float* __restrict__ p,
+                                                            float* __restrict__ a,
+                                                            const float* __restrict__ g, int64_t n,
+                                                            float lr, float mu, float gs) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float aj = mu * a[i] + g[i] * gs;
+    a[i] = aj;
+    p[i] -= lr * aj;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// casts, bias-grad, weight packing
+// ------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) cast_bf16_kernel(const T* __restrict__ x,
+                                                             bf16* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = f2bf((float)x[i]);
+}
+
+// db[c] += sum_r dy[r][c].  Block = 256 threads = (256/CT channel-threads) ... generic:
+// thread t handles channel (blockIdx.y*blockDim.x + t), block x handles a row chunk.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) bias_grad_kernel(const T* __restrict__ dy,
+                                                             float* __restrict__ db, int64_t rows,
+                                                             int C, int64_t rows_per_block) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int64_t r0 = blockIdx.x * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc = 0.f;
+  for (int64_t r = r0; r < r1; ++r) acc += (float)dy[r * C + c];
+  atomicAdd(db + c, acc);
+}
+
+// w fp32 [T][A][B] -> cp bf16 [T'][A][B] (cast) and/or tr bf16 [T][B][A] (per-tap transpose);
+// T' = T-1-t when rev_cp (rot180 of the filter for dgrad).
+__global__ void __launch_bounds__(kThreads) pack_weights_kernel(const float* __restrict__ w,
+                                                                bf16* __restrict__ cp,
+                                                                bf16* __restrict__ tr, int A, int B,
+                                                                int rev_cp) {
+  __shared__ float tile[32][33];
+  const int t = blockIdx.z;
+  const int tc = rev_cp ? (int)gridDim.z - 1 - t : t;
+  const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const float* wt = w + (int64_t)t * A * B;
+  for (int r = ty; r < 32; r += 8) {
+    const int a = a0 + r, b = b0 + tx;
+    float v = 0.f;
+    if (a < A && b < B) {
+      v = wt[(int64_t)a * B + b];
+      if (cp) cp[(int64_t)tc * A * B + (int64_t)a * B + b] = f2bf(v);
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  if (tr) {
+    for (int r = ty; r < 32; r += 8) {
+      const int b = b0 + r, a = a0 + tx;
+      if (a < A && b < B) tr[(int64_t)t * A * B + (int64_t)b * A + a] = f2bf(tile[tx][r]);
+    }
+  }
+}
+
+// deconv forward phase packing: wk[ay*s+ax][uy*2+ux][co][ci] = w[ay+s*(1-uy)][ax+s*(1-ux)][co][ci]
+__global__ void __launch_bounds__(kThreads) pack_deconv_phase_kernel(const float* __restrict__ w,
+                                                                     bf16* __restrict__ wk, int k, int s,
+                                                                     int Cin, int Cout) {
+  const int64_t per = (int64_t)Cout * Cin;
+  const int64_t total = (int64_t)s * s * 4 * per;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e = i % per;
+    const int pu = (int)(i / per);
+    const int u = pu & 3, ph = pu >> 2;
+    const int uy = u >> 1, ux = u & 1, ay = ph / s, ax = ph % s;
+    const int ky = ay + s * (1 - uy), kx = ax + s * (1 - ux);
+    wk[i] = f2bf(w[(int64_t)(ky * k + kx) * per + e]);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int segk_maxpool2x2_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int N, int H, int W,
+                        int C, void* stream) {
+  SEGK_REQUIRE(ctx, x && y && idx, "maxpool_fwd: null pointer");
+  SEGK_REQUIRE(ctx, N > 0 && H >= 2 && W >= 2 && (H % 2 == 0) && (W % 2 == 0) && C % 8 == 0,
+               "maxpool_fwd: need even H,W and C%%8==0 (got %dx%dx%dx%d)", N, H, W, C);
+  const int64_t items = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  maxpool_fwd_kernel<<<stream_grid(ctx, items), kThreads, 0, (cudaStream_t)stream>>>(
+      (const uint4*)x, (uint4*)y, (uint2*)idx, N, H, W, C / 8);
+  SEGK_LAUNCHED(ctx, "maxpool_fwd");
+  return SEGK_OK;
+}
+
+int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const void* act, void* dx,
+                        int N, int H, int W, int C, void* stream) {
+  SEGK_REQUIRE(ctx, dy && idx && dx, "maxpool_bwd: null pointer");
+  SEGK_REQUIRE(ctx, N > 0 && H >= 2 && W >= 2 && (H % 2 == 0) && (W % 2 == 0) && C % 8 == 0,
+               "maxpool_bwd: need even H,W and C%%8==0 (got %dx%dx%dx%d)", N, H, W, C);
+  const int64_t items = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  maxpool_bwd_kernel<<<stream_grid(ctx, items), kThreads, 0, (cudaStream_t)stream>>>(
+      (const uint4*)dy, (const uint2*)idx, (const uint4*)act, (uint4*)dx, N, H, W, C / 8);
+  SEGK_LAUNCHED(ctx, "maxpool_bwd");
+  return SEGK_OK;
+}
+
+int segk_dropout(segk_ctx* ctx, const void* x, void* y, const uint8_t* mask, int64_t n,
+                 float keep_prob, uint64_t seed, void* stream) {
+  SEGK_REQUIRE(ctx, x && y && n > 0, "dropout: null pointer / empty");
+  SEGK_REQUIRE(ctx, keep_prob > 0.f && keep_prob <= 1.f, "dropout: keep_prob %f out of (0,1]",
+               keep_prob);
+  dropout_kernel<<<stream_grid(ctx, (n + 3) / 4), kThreads, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (bf16*)y, mask, n, keep_prob, 1.0f / keep_prob, seed);
+  SEGK_LAUNCHED(ctx, "dropout");
+  return SEGK_OK;
+}
+
+size_t segk_xent_workspace_bytes(int64_t npix) {
+  (void)npix;
+  return (size_t)kXentBlocks * sizeof(float) + 64;
+}
+
+int segk_softmax_xent_fwd_bwd(segk_ctx* ctx, const float* logits, const uint8_t* labels,
+                              float* dlogits, uint8_t* pred, float* loss_sum, int64_t* cm,
+                              void* workspace, int64_t npix, int C, float grad_scale, void* stream) {
+  SEGK_REQUIRE(ctx, logits && labels && loss_sum && workspace, "xent: null pointer");
+  SEGK_REQUIRE(ctx, npix > 0 && C >= 2 && C <= 64, "xent: bad npix/C (%lld, %d)", (long long)npix, C);
+  SEGK_REQUIRE(ctx, cm == nullptr || C == 2, "xent: confusion counts need C == 2");
+  int blocks = (int)ceil_div64(npix, kThreads);
+  if (blocks > kXentBlocks) blocks = kXentBlocks;
+  float* partial = (float*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 2)
+    xent_kernel<2><<<blocks, kThreads, 0, st>>>(logits, labels, dlogits, pred, partial,
+                                               (unsigned long long*)cm, npix, C, grad_scale);
+  else
+    xent_kernel<0><<<blocks, kThreads, 0, st>>>(logits, labels, dlogits, pred, partial,
+                                               (unsigned long long*)cm, npix, C, grad_scale);
+  SEGK_LAUNCHED(ctx, "xent");
+  sum_partials_kernel<<<1, kThreads, 0, st>>>(partial, blocks, loss_sum);
+  SEGK_LAUNCHED(ctx, "xent_sum");
+  return SEGK_OK;
+}
+
+int segk_softmax_infer(segk_ctx* ctx, const float* logits, float* prob, uint8_t* mask, int64_t npix,
+                       int C, void* stream) {
+  SEGK_REQUIRE(ctx, logits && (prob || mask) && npix > 0 && C >= 2, "softmax_infer: bad args");
+  softmax_infer_kernel<<<stream_grid(ctx, npix), kThreads, 0, (cudaStream_t)stream>>>(
+      logits, prob, mask, npix, C);
+  SEGK_LAUNCHED(ctx, "softmax_infer");
+  return SEGK_OK;
+}
+
+int segk_confusion_matrix(segk_ctx* ctx, const uint8_t* gt, const uint8_t* pred, int64_t* cm,
+                          int64_t npix, void* stream) {
+  SEGK_REQUIRE(ctx, gt && pred && cm && npix > 0, "confusion: bad args");
+  SEGK_REQUIRE(ctx, (((uintptr_t)gt | (uintptr_t)pred) & 15) == 0, "confusion: 16-byte alignment");
+  confusion_kernel<<<stream_grid(ctx, (npix + 15) / 16), kThreads, 0, (cudaStream_t)stream>>>(
+      gt, pred, (unsigned long long*)cm, npix);
+  SEGK_LAUNCHED(ctx, "confusion");
+  return SEGK_OK;
+}
+
+int segk_adam_step(segk_ctx* ctx, float* p, float* m, float* v, const float* g, int64_t n, float lr_t,
+                   float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  SEGK_REQUIRE(ctx, p && m && v && g && n > 0, "adam: bad args");
+  SEGK_REQUIRE(ctx, (((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)g) & 15) == 0,
+               "adam: arenas must be 16-byte aligned");
+  adam_kernel<<<stream_grid(ctx, n / 4 + 1), kThreads, 0, (cudaStream_t)stream>>>(
+      p, m, v, g, n, lr_t, beta1, beta2, eps, grad_scale);
+  SEGK_LAUNCHED(ctx, "adam");
+  return SEGK_OK;
+}
+
+int segk_momentum_step(segk_ctx* ctx, float* p, float* a, const float* g, int64_t n, float lr,
+                       float mu, float grad_scale, void* stream) {
+  SEGK_REQUIRE(ctx, p && a && g && n > 0, "momentum: bad args");
+  momentum_kernel<<<stream_grid(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(p, a, g, n, lr, mu,
+                                                                             grad_scale);
+  SEGK_LAUNCHED(ctx, "momentum");
+  return SEGK_OK;
+}
+
+int segk_cast_to_bf16(segk_ctx* ctx, const void* x, int x_dtype, void* y, int64_t n, void* stream) {
+  SEGK_REQUIRE(ctx, x && y && n > 0, "cast: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == 1)
+    cast_bf16_kernel<float><<<stream_grid(ctx, n), kThreads, 0, st>>>((const float*)x, (bf16*)y, n);
+  else if (x_dtype == 2)
+    cast_bf16_kernel<uint8_t><<<stream_grid(ctx, n), kThreads, 0, st>>>((const uint8_t*)x, (bf16*)y, n);
+  else
+    return segk_fail(ctx, SEGK_EINVAL, "cast: x_dtype must be 1 (f32) or 2 (u8)");
+  SEGK_LAUNCHED(ctx, "cast");
+  return SEGK_OK;
+}
+
+int segk_bias_grad(segk_ctx* ctx, const void* dy, int dy_is_f32, float* db, int64_t rows, int C,
+                   void* stream) {
+  SEGK_REQUIRE(ctx, dy && db && rows > 0 && C > 0, "bias_grad: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * C, st);
+  if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "bias_grad memset: %s", cudaGetErrorString(e));
+  const int tx = C < kThreads ? ((C + 31) / 32) * 32 : kThreads;
+  const int gy = ceil_div(C, tx);
+  int64_t want = (int64_t)ctx->sm_count * 8 / gy;
+  if (want < 1) want = 1;
+  int64_t rpb = ceil_div64(rows, want);
+  if (rpb < 16) rpb = 16;
+  dim3 grid((unsigned)ceil_div64(rows, rpb), gy);
+  if (dy_is_f32)
+    bias_grad_kernel<float><<<grid, tx, 0, st>>>((const float*)dy, db, rows, C, rpb);
+  else
+    bias_grad_kernel<bf16><<<grid, tx, 0, st>>>((const bf16*)dy, db, rows, C, rpb);
+  SEGK_LAUNCHED(ctx, "bias_grad");
+  return SEGK_OK;
+}
+
+int segk_pack_conv_weights(segk_ctx* ctx, const float* w, void* wk, void* wd, int kh, int kw, int Cin,
+                           int Cout, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, w && (wk || wd) && kh > 0 && kw > 0 && Cin > 0 && Cout > 0, "pack_conv: bad args");
+  const int T = kh * kw;
+  dim3 grid(ceil_div(Cout, 32), ceil_div(Cin, 32), T);
+  SEGK_REQUIRE(ctx, grid.y <= 65535 && grid.z <= 65535, "pack_conv: dims too large");
+  // w[t][Cin][Cout]: wd = cast copy with taps reversed, wk = per-tap transpose [Cout][Cin]
+  pack_weights_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(w, (bf16*)wd, (bf16*)wk, Cin, Cout, 1);
+  SEGK_LAUNCHED(ctx, "pack_conv_weights");
+  return SEGK_OK;
+}
+
+int segk_pack_deconv_weights(segk_ctx* ctx, const float* w, void* wk, void* wd, int k, int s, int Cin,
+                             int Cout, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, w && (wk || wd) && k == 2 * s && s > 0 && Cin > 0 && Cout > 0, "pack_deconv: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (wd) {
+    // w[t][Cout][Cin] -> wd[t][Cin][Cout]
+    dim3 grid(ceil_div(Cin, 32), ceil_div(Cout, 32), k * k);
+    SEGK_REQUIRE(ctx, grid.y <= 65535 && grid.z <= 65535, "pack_deconv: dims too large");
+    pack_weights_kernel<<<grid, kThreads, 0, st>>>(w, nullptr, (bf16*)wd, Cout, Cin, 0);
+    SEGK_LAUNCHED(ctx, "pack_deconv_wd");
+  }
+  if (wk) {
+    const int64_t n = (int64_t)s * s * 4 * Cout * Cin;
+    pack_deconv_phase_kernel<<<stream_grid(ctx, n), kThreads, 0, st>>>(w, (bf16*)wk, k, s, Cin, Cout);
+    SEGK_LAUNCHED(ctx, "pack_deconv_wk");
+  }
+  return SEGK_OK;
+}
+
+}  // extern "C"

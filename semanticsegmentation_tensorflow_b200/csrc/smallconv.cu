@@ -1,0 +1,510 @@
+// CUDA-core kernels for the layers whose channel counts cannot feed a tensor-core tile:
+//   conv1_1 (Cin = 3/4, K = 27/36)            -> "tiny-K" direct conv fwd / wgrad
+//   conv8   (1x1, Cout = num_classes = 2)      -> "skinny" 1x1 fwd / dgrad / wgrad
+//   conv_t1 (Cin = 2) and, for now, conv_t3    -> gather-form transposed conv fwd/dgrad/wgrad
+// They are bandwidth / latency bound and tiny next to the 3x3 stack.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------------------
+// tiny-K conv forward: thread = (pixel, block of 32 output channels). Weights (fp32 HWIO
+// [K][Cout]) staged in shared memory and read as broadcast float4.
+// ---------------------------------------------------------------------------------------
+constexpr int kTinyKMax = 64;
+
+__device__ __forceinline__ float ld_in(const bf16* p) { return bf2f(*p); }
+__device__ __forceinline__ float ld_in(const uint8_t* p) { return (float)*p; }
+
+template <typename XT>
+__global__ void __launch_bounds__(kThreads) conv_tinyk_fwd_kernel(
+    const XT* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+    bf16* __restrict__ y, int N, int H, int W, int Cin, int Cout, int kh, int kw, int relu) {
+  extern __shared__ float wsm[];  // [K][32] for this block's channel block
+  const int K = kh * kw * Cin;
+  const int cb = blockIdx.y * 32;
+  for (int i = threadIdx.x; i < K * 32; i += blockDim.x) {
+    const int k = i >> 5, c = i & 31;
+    wsm[i] = (cb + c < Cout) ? w[(int64_t)k * Cout + cb + c] : 0.f;
+  }
+  __syncthreads();
+  const int64_t npix = (int64_t)N * H * W;
+  const int ph = kh / 2, pw = kw / 2;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const int xw = (int)(p % W);
+    const int yh = (int)((p / W) % H);
+    const int n = (int)(p / ((int64_t)W * H));
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = bias ? ((cb + c < Cout) ? bias[cb + c] : 0.f) : 0.f;
+    int k = 0;
+    for (int ky = 0; ky < kh; ++ky) {
+      const int yy = yh + ky - ph;
+      for (int kx = 0; kx < kw; ++kx) {
+        const int xx = xw + kx - pw;
+        const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+        const XT* xp = x + (((int64_t)n * H + yy) * W + xx) * Cin;
+        for (int ci = 0; ci < Cin; ++ci, ++k) {
+          const float xv = in ? ld_in(xp + ci) : 0.f;
+          const float4* wr = reinterpret_cast<const float4*>(wsm + k * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 wv = wr[q];
+            acc[4 * q + 0] += xv * wv.x;
+            acc[4 * q + 1] += xv * wv.y;
+            acc[4 * q + 2] += xv * wv.z;
+            acc[4 * q + 3] += xv * wv.w;
+          }
+        }
+      }
+    }
+    bf16* yp = y + p * Cout + cb;
+    if (cb + 32 <= Cout) {
+      uint4* y4 = reinterpret_cast<uint4*>(yp);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a = acc[8 * q + 2 * j], b = acc[8 * q + 2 * j + 1];
+          if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+          o[j] = pack_bf16x2(a, b);
+        }
+        y4[q] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    } else {
+      for (int c = 0; c < 32 && cb + c < Cout; ++c) yp[c] = f2bf(relu ? fmaxf(acc[c], 0.f) : acc[c]);
+    }
+  }
+}
+
+// tiny-K wgrad: dW[k][co] = sum_p x[p + tap(k)][ci(k)] * dy[p][co].  Block = 256 threads =
+// 64 channels x 4 k-groups; each block reduces a contiguous pixel chunk, then atomicAdd.
+template <typename XT>
+__global__ void __launch_bounds__(kThreads) conv_tinyk_wgrad_kernel(
+    const XT* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw, int N, int H,
+    int W, int Cin, int Cout, int kh, int kw, int64_t pix_per_block) {
+  constexpr int PT = 32;  // pixels staged per tile
+  __shared__ float xs[PT][kTinyKMax];
+  const int K = kh * kw * Cin;
+  const int co = blockIdx.y * 64 + (threadIdx.x & 63);
+  const int kg = threadIdx.x >> 6;              // 0..3
+  const int kper = (K + 3) / 4;                 // <= 16
+  const int k0 = kg * kper;
+  const int64_t npix = (int64_t)N * H * W;
+  const int64_t p0 = blockIdx.x * pix_per_block;
+  const int64_t p1 = p0 + pix_per_block < npix ? p0 + pix_per_block : npix;
+  const int ph = kh / 2, pw = kw / 2;
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int64_t pt = p0; pt < p1; pt += PT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < PT * K; i += blockDim.x) {
+      const int pp = i / K, k = i % K;
+      const int64_t p = pt + pp;
+      float v = 0.f;
+      if (p < p1) {
+        const int ci = k % Cin, t = k / Cin;
+        const int ky = t / kw, kx = t % kw;
+        const int xw = (int)(p % W), yh = (int)((p / W) % H);
+        const int n = (int)(p / ((int64_t)W * H));
+        const int yy = yh + ky - ph, xx = xw + kx - pw;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+          v = ld_in(x + (((int64_t)n * H + yy) * W + xx) * Cin + ci);
+      }
+      xs[pp][k] = v;
+    }
+    __syncthreads();
+    if (co < Cout) {
+      const int lim = (int)((p1 - pt) < PT ? (p1 - pt) : PT);
+      for (int pp = 0; pp < lim; ++pp) {
+        const float g = bf2f(dy[(pt + pp) * Cout + co]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < kper && k0 + i < K) acc[i] += xs[pp][k0 + i] * g;
+      }
+    }
+  }
+  if (co < Cout) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < kper && k0 + i < K) atomicAdd(dw + (int64_t)(k0 + i) * Cout + co, acc[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// skinny 1x1 conv (Cout <= 8): one warp per pixel.
+// ---------------------------------------------------------------------------------------
+template <int CO>
+__global__ void __launch_bounds__(kThreads) conv_skinny_fwd_kernel(
+    const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+    bf16* __restrict__ y, int64_t npix, int Cin, int relu) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < npix; p += nwarps) {
+    float acc[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+    const bf16* xp = x + p * Cin;
+    for (int ci = lane * 8; ci < Cin; ci += 256) {
+      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xp + ci));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&xv.x)[j]);
+        const float* w0 = w + (int64_t)(ci + 2 * j) * CO;
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[c] += f.x * __ldg(w0 + c) + f.y * __ldg(w0 + CO + c);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CO; ++c)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        float v = acc[c] + (bias ? bias[c] : 0.f);
+        y[p * CO + c] = f2bf(relu ? fmaxf(v, 0.f) : v);
+      }
+    }
+  }
+}
+
+// dx[p][ci] = sum_co dy[p][co] * w[ci][co], masked by relu_mask[p][ci] > 0
+template <int CO>
+__global__ void __launch_bounds__(kThreads) conv_skinny_dgrad_kernel(
+    const bf16* __restrict__ dy, const float* __restrict__ w, const bf16* __restrict__ mask,
+    bf16* __restrict__ dx, int64_t npix, int Cin, float scale) {
+  const int64_t total = npix * Cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / Cin;
+    const int ci = (int)(i % Cin);
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < CO; ++c) a += bf2f(dy[p * CO + c]) * __ldg(w + (int64_t)ci * CO + c);
+    if (mask && !(bf2f(mask[i]) > 0.f)) a = 0.f;
+    dx[i] = f2bf(a * scale);
+  }
+}
+
+// dW[ci][co] += sum_p x[p][ci] dy[p][co]
+template <int CO>
+__global__ void __launch_bounds__(kThreads) conv_skinny_wgrad_kernel(
+    const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw, int64_t npix,
+    int Cin, int64_t pix_per_block) {
+  const int ci = blockIdx.y * blockDim.x + threadIdx.x;
+  if (ci >= Cin) return;
+  const int64_t p0 = blockIdx.x * pix_per_block;
+  const int64_t p1 = p0 + pix_per_block < npix ? p0 + pix_per_block : npix;
+  float acc[CO];
+#pragma unroll
+  for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+  for (int64_t p = p0; p < p1; ++p) {
+    const float xv = bf2f(x[p * Cin + ci]);
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[c] += xv * bf2f(dy[p * CO + c]);
+  }
+#pragma unroll
+  for (int c = 0; c < CO; ++c) atomicAdd(dw + (int64_t)ci * CO + c, acc[c]);
+}
+
+// ---------------------------------------------------------------------------------------
+// transposed conv, k = 2s, SAME (FCN.py:138-159) on CUDA cores, gather form:
+//   y[n,oy,ox,co] = b[co] + sum_{ty,tx in {0,1}} sum_ci x[n, qy-ty, qx-tx, ci] * W[ay+s*ty, ax+s*tx, co, ci]
+//   with qy = (oy+p)/s, ay = (oy+p)%s, p = s/2  (SURVEY Appendix B.2).
+// ---------------------------------------------------------------------------------------
+template <typename OT>
+__global__ void __launch_bounds__(kThreads) deconv_fwd_kernel(
+    const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+    const bf16* __restrict__ res, OT* __restrict__ y, int N, int H, int W, int Cin, int Cout, int k,
+    int s, int relu) {
+  const int OH = H * s, OW = W * s, p = s / 2;
+  const int64_t total = (int64_t)N * OH * OW * Cout;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    int64_t r = i / Cout;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int n = (int)(r / OH);
+    const int qy = (oy + p) / s, ay = (oy + p) % s;
+    const int qx = (ox + p) / s, ax = (ox + p) % s;
+    float acc = bias ? bias[co] : 0.f;
+#pragma unroll
+    for (int ty = 0; ty < 2; ++ty) {
+      const int iy = qy - ty;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int tx = 0; tx < 2; ++tx) {
+        const int ix = qx - tx;
+        if (ix < 0 || ix >= W) continue;
+        const bf16* xp = x + (((int64_t)n * H + iy) * W + ix) * Cin;
+        const float* wp = w + (((int64_t)(ay + s * ty) * k + (ax + s * tx)) * Cout + co) * Cin;
+        if ((Cin & 7) == 0) {
+          for (int ci = 0; ci < Cin; ci += 8) {
+            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(xp + ci));
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp + ci));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wp + ci + 4));
+            float2 f;
+            f = unpack_bf16x2(xv.x); acc += f.x * w0.x + f.y * w0.y;
+            f = unpack_bf16x2(xv.y); acc += f.x * w0.z + f.y * w0.w;
+            f = unpack_bf16x2(xv.z); acc += f.x * w1.x + f.y * w1.y;
+            f = unpack_bf16x2(xv.w); acc += f.x * w1.z + f.y * w1.w;
+          }
+        } else {
+          for (int ci = 0; ci < Cin; ++ci) acc += bf2f(xp[ci]) * __ldg(wp + ci);
+        }
+      }
+    }
+    if (res) acc += bf2f(res[i]);
+    if (relu) acc = fmaxf(acc, 0.f);
+    y[i] = (OT)acc;
+  }
+}
+
+// dx[n,i,j,ci] = sum_{ky,kx,co} dy[n, i*s-p+ky, j*s-p+kx, co] * W[ky,kx,co,ci]; thread = (pixel, ci)
+template <typename GT>
+__global__ void __launch_bounds__(kThreads) deconv_dgrad_kernel(
+    const GT* __restrict__ dy, const float* __restrict__ w, const bf16* __restrict__ mask,
+    bf16* __restrict__ dx, int N, int H, int W, int Cin, int Cout, int k, int s) {
+  const int OH = H * s, OW = W * s, p = s / 2;
+  const int64_t total = (int64_t)N * H * W * Cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    int64_t r = i / Cin;
+    const int ix = (int)(r % W);
+    r /= W;
+    const int iy = (int)(r % H);
+    const int n = (int)(r / H);
+    float acc = 0.f;
+    for (int ky = 0; ky < k; ++ky) {
+      const int oy = iy * s - p + ky;
+      if (oy < 0 || oy >= OH) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ox = ix * s - p + kx;
+        if (ox < 0 || ox >= OW) continue;
+        const GT* gp = dy + (((int64_t)n * OH + oy) * OW + ox) * Cout;
+        const float* wp = w + ((int64_t)(ky * k + kx) * Cout) * Cin + ci;
+        for (int co = 0; co < Cout; ++co) acc += (float)gp[co] * __ldg(wp + (int64_t)co * Cin);
+      }
+    }
+    if (mask && !(bf2f(mask[i]) > 0.f)) acc = 0.f;
+    dx[i] = f2bf(acc);
+  }
+}
+
+// dW[ky,kx,co,ci] += sum_{n,i,j} x[n,i,j,ci] * dy[n, i*s-p+ky, j*s-p+kx, co]
+// thread = one weight element (ci fastest); blockIdx.y = slice of the (n,i) rows.
+template <typename GT>
+__global__ void __launch_bounds__(kThreads) deconv_wgrad_kernel(
+    const bf16* __restrict__ x, const GT* __restrict__ dy, float* __restrict__ dw, int N, int H,
+    int W, int Cin, int Cout, int k, int s, int rows_per_slice) {
+  const int OH = H * s, OW = W * s, p = s / 2;
+  const int64_t nw = (int64_t)k * k * Cout * Cin;
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= nw) return;
+  const int ci = (int)(e % Cin);
+  int64_t r = e / Cin;
+  const int co = (int)(r % Cout);
+  r /= Cout;
+  const int kx = (int)(r % k), ky = (int)(r / k);
+  const int row0 = blockIdx.y * rows_per_slice;
+  const int row1 = min(row0 + rows_per_slice, N * H);
+  float acc = 0.f;
+  for (int row = row0; row < row1; ++row) {
+    const int n = row / H, iy = row % H;
+    const int oy = iy * s - p + ky;
+    if (oy < 0 || oy >= OH) continue;
+    const bf16* xp = x + ((int64_t)row * W) * Cin + ci;
+    const GT* gp = dy + (((int64_t)n * OH + oy) * OW) * Cout + co;
+    for (int ix = 0; ix < W; ++ix) {
+      const int ox = ix * s - p + kx;
+      if (ox < 0 || ox >= OW) continue;
+      acc += bf2f(xp[(int64_t)ix * Cin]) * (float)gp[(int64_t)ox * Cout];
+    }
+  }
+  atomicAdd(dw + e, acc);
+}
+
+inline int sgrid(segk_ctx* ctx, int64_t items, int per_sm = 8) {
+  int64_t b = ceil_div64(items, kThreads), cap = (int64_t)ctx->sm_count * per_sm;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int segk_conv2d_small_fwd(segk_ctx* ctx, const void* x, int x_dtype, const float* w, const float* bias,
+                          void* y, int N, int H, int W, int Cin, int Cout, int kh, int kw, unsigned flags,
+                          void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && w && y && N > 0 && H > 0 && W > 0, "conv_small_fwd: bad args");
+  SEGK_REQUIRE(ctx, x_dtype == 0 || x_dtype == 2, "conv_small_fwd: x_dtype must be 0 (bf16) or 2 (u8)");
+  const int relu = (flags & SEGK_EPI_RELU) ? 1 : 0;
+  const int K = kh * kw * Cin;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t npix = (int64_t)N * H * W;
+  if (K <= kTinyKMax && (kh & 1) && (kw & 1)) {
+    dim3 grid(sgrid(ctx, npix, 4), ceil_div(Cout, 32));
+    if (x_dtype == 2)
+      conv_tinyk_fwd_kernel<uint8_t><<<grid, kThreads, K * 32 * sizeof(float), st>>>(
+          (const uint8_t*)x, w, bias, (bf16*)y, N, H, W, Cin, Cout, kh, kw, relu);
+    else
+      conv_tinyk_fwd_kernel<bf16><<<grid, kThreads, K * 32 * sizeof(float), st>>>(
+          (const bf16*)x, w, bias, (bf16*)y, N, H, W, Cin, Cout, kh, kw, relu);
+    SEGK_LAUNCHED(ctx, "conv_tinyk_fwd");
+    return SEGK_OK;
+  }
+  if (x_dtype == 0 && kh == 1 && kw == 1 && Cin % 8 == 0 && (Cout == 2 || Cout == 4 || Cout == 8)) {
+    const int grid = sgrid(ctx, npix * 32, 8);
+    if (Cout == 2)
+      conv_skinny_fwd_kernel<2><<<grid, kThreads, 0, st>>>((const bf16*)x, w, bias, (bf16*)y, npix, Cin, relu);
+    else if (Cout == 4)
+      conv_skinny_fwd_kernel<4><<<grid, kThreads, 0, st>>>((const bf16*)x, w, bias, (bf16*)y, npix, Cin, relu);
+    else
+      conv_skinny_fwd_kernel<8><<<grid, kThreads, 0, st>>>((const bf16*)x, w, bias, (bf16*)y, npix, Cin, relu);
+    SEGK_LAUNCHED(ctx, "conv_skinny_fwd");
+    return SEGK_OK;
+  }
+  return segk_fail(ctx, SEGK_EINVAL,
+                   "conv_small_fwd: unsupported shape k=%dx%d Cin=%d Cout=%d dtype=%d (no fallback)", kh, kw,
+                   Cin, Cout, x_dtype);
+}
+
+int segk_conv2d_small_dgrad(segk_ctx* ctx, const void* dy, const float* w, const void* relu_mask, void* dx,
+                            float scale, int N, int H, int W, int Cin, int Cout, int kh, int kw,
+                            void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, dy && w && dx && N > 0, "conv_small_dgrad: bad args");
+  SEGK_REQUIRE(ctx, kh == 1 && kw == 1 && (Cout == 2 || Cout == 4 || Cout == 8),
+               "conv_small_dgrad: only 1x1 with Cout in {2,4,8} (got %dx%d Cout=%d)", kh, kw, Cout);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t npix = (int64_t)N * H * W;
+  const int grid = sgrid(ctx, npix * Cin);
+  if (Cout == 2)
+    conv_skinny_dgrad_kernel<2><<<grid, kThreads, 0, st>>>((const bf16*)dy, w, (const bf16*)relu_mask, (bf16*)dx, npix, Cin, scale);
+  else if (Cout == 4)
+    conv_skinny_dgrad_kernel<4><<<grid, kThreads, 0, st>>>((const bf16*)dy, w, (const bf16*)relu_mask, (bf16*)dx, npix, Cin, scale);
+  else
+    conv_skinny_dgrad_kernel<8><<<grid, kThreads, 0, st>>>((const bf16*)dy, w, (const bf16*)relu_mask, (bf16*)dx, npix, Cin, scale);
+  SEGK_LAUNCHED(ctx, "conv_skinny_dgrad");
+  return SEGK_OK;
+}
+
+int segk_conv2d_small_wgrad(segk_ctx* ctx, const void* x, int x_dtype, const void* dy, float* dw, int N,
+                            int H, int W, int Cin, int Cout, int kh, int kw, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && dy && dw && N > 0, "conv_small_wgrad: bad args");
+  SEGK_REQUIRE(ctx, x_dtype == 0 || x_dtype == 2, "conv_small_wgrad: x_dtype must be 0 (bf16) or 2 (u8)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t npix = (int64_t)N * H * W;
+  const int K = kh * kw * Cin;
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)K * Cout, st);
+  if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "wgrad memset: %s", cudaGetErrorString(e));
+  if (K <= kTinyKMax && (kh & 1) && (kw & 1)) {
+    const int gy = ceil_div(Cout, 64);
+    int64_t blocks = (int64_t)ctx->sm_count * 4 / gy;
+    if (blocks < 1) blocks = 1;
+    int64_t ppb = ceil_div64(npix, blocks);
+    ppb = ceil_div64(ppb, 32) * 32;
+    dim3 grid((unsigned)ceil_div64(npix, ppb), gy);
+    if (x_dtype == 2)
+      conv_tinyk_wgrad_kernel<uint8_t><<<grid, kThreads, 0, st>>>((const uint8_t*)x, (const bf16*)dy, dw, N, H,
+                                                                  W, Cin, Cout, kh, kw, ppb);
+    else
+      conv_tinyk_wgrad_kernel<bf16><<<grid, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, dw, N, H, W,
+                                                               Cin, Cout, kh, kw, ppb);
+    SEGK_LAUNCHED(ctx, "conv_tinyk_wgrad");
+  } else if (x_dtype == 0 && kh == 1 && kw == 1 && (Cout == 2 || Cout == 4 || Cout == 8)) {
+    const int tx = 128;
+    const int gy = ceil_div(Cin, tx);
+    int64_t blocks = (int64_t)ctx->sm_count * 8 / gy;
+    if (blocks < 1) blocks = 1;
+    int64_t ppb = ceil_div64(npix, blocks);
+    if (ppb < 8) ppb = 8;
+    dim3 grid((unsigned)ceil_div64(npix, ppb), gy);
+    if (Cout == 2)
+      conv_skinny_wgrad_kernel<2><<<grid, tx, 0, st>>>((const bf16*)x, (const bf16*)dy, dw, npix, Cin, ppb);
+    else if (Cout == 4)
+      conv_skinny_wgrad_kernel<4><<<grid, tx, 0, st>>>((const bf16*)x, (const bf16*)dy, dw, npix, Cin, ppb);
+    else
+      conv_skinny_wgrad_kernel<8><<<grid, tx, 0, st>>>((const bf16*)x, (const bf16*)dy, dw, npix, Cin, ppb);
+    SEGK_LAUNCHED(ctx, "conv_skinny_wgrad");
+  } else {
+    return segk_fail(ctx, SEGK_EINVAL,
+                     "conv_small_wgrad: unsupported shape k=%dx%d Cin=%d Cout=%d (no fallback)", kh, kw,
+                     Cin, Cout);
+  }
+  return SEGK_OK;
+}
+
+int segk_deconv2d_small_fwd(segk_ctx* ctx, const void* x, const float* w, const float* bias,
+                            const void* residual, void* y, int N, int H, int W, int Cin, int Cout,
+                            int k, int s, unsigned flags, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && w && y && N > 0, "deconv_small_fwd: bad args");
+  SEGK_REQUIRE(ctx, k == 2 * s && (s % 2 == 0), "deconv: need k == 2*stride, even stride (k=%d s=%d)", k, s);
+  const int relu = (flags & SEGK_EPI_RELU) ? 1 : 0;
+  const int64_t total = (int64_t)N * H * s * W * s * Cout;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (flags & SEGK_EPI_OUT_F32)
+    deconv_fwd_kernel<float><<<sgrid(ctx, total, 16), kThreads, 0, st>>>(
+        (const bf16*)x, w, bias, (const bf16*)residual, (float*)y, N, H, W, Cin, Cout, k, s, relu);
+  else
+    deconv_fwd_kernel<bf16><<<sgrid(ctx, total, 16), kThreads, 0, st>>>(
+        (const bf16*)x, w, bias, (const bf16*)residual, (bf16*)y, N, H, W, Cin, Cout, k, s, relu);
+  SEGK_LAUNCHED(ctx, "deconv_small_fwd");
+  return SEGK_OK;
+}
+
+int segk_deconv2d_small_dgrad(segk_ctx* ctx, const void* dy, int dy_is_f32, const float* w,
+                              const void* relu_mask, void* dx, int N, int H, int W, int Cin, int Cout,
+                              int k, int s, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, dy && w && dx && N > 0, "deconv_small_dgrad: bad args");
+  SEGK_REQUIRE(ctx, k == 2 * s && (s % 2 == 0), "deconv: need k == 2*stride, even stride (k=%d s=%d)", k, s);
+  const int64_t total = (int64_t)N * H * W * Cin;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dy_is_f32)
+    deconv_dgrad_kernel<float><<<sgrid(ctx, total, 16), kThreads, 0, st>>>(
+        (const float*)dy, w, (const bf16*)relu_mask, (bf16*)dx, N, H, W, Cin, Cout, k, s);
+  else
+    deconv_dgrad_kernel<bf16><<<sgrid(ctx, total, 16), kThreads, 0, st>>>(
+        (const bf16*)dy, w, (const bf16*)relu_mask, (bf16*)dx, N, H, W, Cin, Cout, k, s);
+  SEGK_LAUNCHED(ctx, "deconv_small_dgrad");
+  return SEGK_OK;
+}
+
+int segk_deconv2d_small_wgrad(segk_ctx* ctx, const void* x, const void* dy, int dy_is_f32, float* dw, int N,
+                              int H, int W, int Cin, int Cout, int k, int s, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && dy && dw && N > 0, "deconv_small_wgrad: bad args");
+  SEGK_REQUIRE(ctx, k == 2 * s && (s % 2 == 0), "deconv: need k == 2*stride, even stride (k=%d s=%d)", k, s);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nw = (int64_t)k * k * Cout * Cin;
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)nw, st);
+  if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "wgrad memset: %s", cudaGetErrorString(e));
+  const int gx = (int)ceil_div64(nw, kThreads);
+  int slices = ceil_div(ctx->sm_count * 8, gx);
+  if (slices < 1) slices = 1;
+  if (slices > N * H) slices = N * H;
+  const int rps = ceil_div(N * H, slices);
+  dim3 grid(gx, ceil_div(N * H, rps));
+  if (dy_is_f32)
+    deconv_wgrad_kernel<float><<<grid, kThreads, 0, st>>>((const bf16*)x, (const float*)dy, dw, N, H, W, Cin, Cout, k, s, rps);
+  else
+    deconv_wgrad_kernel<bf16><<<grid, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, dw, N, H, W, Cin, Cout, k, s, rps);
+  SEGK_LAUNCHED(ctx, "deconv_small_wgrad");
+  return SEGK_OK;
+}
+
+}  // extern "C"

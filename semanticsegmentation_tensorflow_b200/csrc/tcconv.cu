@@ -1,0 +1,855 @@
+// Tensor-core convolution family for sm_100a: implicit GEMM on tcgen05.mma with TMEM
+// accumulators and TMA-staged operand tiles.
+//
+//   igemm_kernel  (K-major operands)  : conv_layer forward, its Conv2DBackpropInput (dgrad), the
+//                                       phase-decomposed transposed conv and the strided conv that is
+//                                       the transposed conv's input gradient.
+//   wgrad_kernel  (MN-major operands) : Conv2DBackpropFilter, reduction over pixels, split-K.
+//
+// GEMM view:  rows = 128 output pixels (a TMA box bw x bh x bn of the NHWC
+// tensor), cols = BLOCK_N output channels, K = taps x Cin walked in 64-channel steps.  SAME
+// padding is the TMA unit's out-of-bounds zero fill: a tap (dy,dx) simply shifts the box
+// start coordinate, which may be negative.  Nothing is im2col'ed in memory.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0    TMA producer (one elected lane)        smem ring of kStages {A 16 KB, B BLOCK_N*128 B}
+//   warp 1    tcgen05.mma issuer (one lane) + TMEM allocator; 2 accumulators of BLOCK_N columns
+//   warps 2-5 epilogue: tcgen05.ld -> bias / residual / ReLU / ReLU-mask / scale -> global stores
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 192;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;             // bf16 elements = one 128-byte swizzle row
+constexpr int kABytes = kBlockM * 128;  // 16 KB
+constexpr int kMaxTaps = 64;
+constexpr int kSmemBudget = 200 * 1024;
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = kSmemBudget / kStageBytes;  // 256:4  128:6  64:8
+  static constexpr int kTmemCols = 2 * BLOCK_N;              // double-buffered accumulator
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct alignas(64) TensorMaps {
+  CUtensorMap a[4];
+  CUtensorMap b;
+};
+
+struct TapTable {
+  int8_t dy[kMaxTaps];
+  int8_t dx[kMaxTaps];
+  int8_t map[kMaxTaps];
+};
+
+struct IgemmParams {
+  // row space: boxes of the q-grid [N, H, W] (for a plain conv the output pixel grid)
+  int N, H, W;
+  int bw, bh, bn, rows;
+  int tiles_w, tiles_h, tiles_n;
+  int n_tiles;   // GEMM-N tiles = Cout / BLOCK_N
+  int phases;    // s*s output phases of a transposed conv (1 otherwise)
+  int s;         // phases per dim
+  int ntaps, kchunks;
+  int in_H, in_W;  // extent of the tensor view the taps index (tile-level tap skipping)
+  // output mapping: out pixel = (qy*os + ay - opad, qx*os + ax - opad), phase = ay*s + ax
+  int out_H, out_W, ldo, os, opad;
+  void* out;
+  int out_f32;
+  const float* bias;
+  const bf16* residual;
+  const bf16* mask;
+  float scale;
+  int relu;
+};
+
+struct PipeState {
+  int stage = 0;
+  uint32_t phase = 0;
+  template <int STAGES>
+  __device__ __forceinline__ void advance() {
+    if (++stage == STAGES) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+struct TileCoord {
+  int nt, x0, y0, n0, phase;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
+  TileCoord t;
+  t.nt = tile % p.n_tiles;
+  int r = tile / p.n_tiles;
+  t.x0 = (r % p.tiles_w) * p.bw;
+  r /= p.tiles_w;
+  t.y0 = (r % p.tiles_h) * p.bh;
+  r /= p.tiles_h;
+  t.n0 = (r % p.tiles_n) * p.bn;
+  t.phase = r / p.tiles_n;
+  return t;
+}
+
+// A tap whose shifted box lies entirely outside the input contributes only zeros.
+__device__ __forceinline__ bool tap_active(const IgemmParams& p, const TileCoord& t, int dy, int dx) {
+  const int ya = t.y0 + dy, xa = t.x0 + dx;
+  return !(ya + p.bh <= 0 || ya >= p.in_H || xa + p.bw <= 0 || xa >= p.in_W);
+}
+
+__device__ __forceinline__ uint64_t tap_mask(const IgemmParams& p, const TapTable& taps, const TileCoord& t) {
+  uint64_t m = 0;
+  for (int i = 0; i < p.ntaps; ++i)
+    if (tap_active(p, t, taps.dy[i], taps.dx[i])) m |= (1ull << i);
+  if (m == 0) m = (p.ntaps >= 64) ? ~0ull : ((1ull << p.ntaps) - 1);  // all-zero tile: still produce zeros
+  return m;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const TapTable taps) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps;
+      const uint32_t tx_bytes = (uint32_t)p.rows * 128u + (uint32_t)C::kBBytes;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const uint64_t tm = tap_mask(p, taps, t);
+        for (int i = 0; i < p.ntaps; ++i) {
+          if (!((tm >> i) & 1)) continue;
+          const int dy = taps.dy[i], dx = taps.dx[i], mi = taps.map[i];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+            uint8_t* sa = smem + ps.stage * C::kStageBytes;
+            mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
+            tma_load_4d(&maps.a[mi], &full_bar[ps.stage], sa, kc * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
+            tma_load_3d(&maps.b, &full_bar[ps.stage], sa + kABytes, kc * kBlockK, t.nt * BLOCK_N,
+                        t.phase * p.ntaps + i);
+            ps.advance<C::kStages>();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      PipeState ps;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 0, 0);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const uint64_t tm = tap_mask(p, taps, t);
+        const int nsteps = __popcll(tm) * p.kchunks;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int ks = 0; ks < nsteps; ++ks) {
+          mbar_wait(&full_bar[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + ps.stage * C::kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_f16(d_addr, ad, bd, idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[ps.stage]);
+          if (ks == nsteps - 1) umma_commit(&tfull_bar[acc]);
+          ps.advance<C::kStages>();
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ---- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int iw = row % p.bw;
+    const int ih = (row / p.bw) % p.bh;
+    const int in = row / (p.bw * p.bh);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int ay = t.phase / p.s, ax = t.phase % p.s;
+      const int qx = t.x0 + iw, qy = t.y0 + ih, n = t.n0 + in;
+      const int ox = qx * p.os + ax - p.opad, oy = qy * p.os + ay - p.opad;
+      const bool valid = row < p.rows && qx < p.W && qy < p.H && n < p.N && ox >= 0 && ox < p.out_W &&
+                         oy >= 0 && oy < p.out_H;
+      const int64_t opix = ((int64_t)n * p.out_H + oy) * p.out_W + ox;
+      const int64_t obase = opix * p.ldo + (int64_t)t.nt * BLOCK_N;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + t.nt * BLOCK_N + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(b4 + i);
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+          }
+          if (p.residual) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = __ldg(r4 + i);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2((&u.x)[j]);
+                v[8 * i + 2 * j] += f.x;
+                v[8 * i + 2 * j + 1] += f.y;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.mask) {
+            const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = __ldg(m4 + i);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2((&u.x)[j]);
+                if (!(f.x > 0.f)) v[8 * i + 2 * j] = 0.f;
+                if (!(f.y > 0.f)) v[8 * i + 2 * j + 1] = 0.f;
+              }
+            }
+          }
+          if (p.scale != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+          }
+          if (p.out_f32) {
+            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                 pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad: dW[rb*64 + i][co] = sum over pixels  X[pixel + shift(rb)][ci(rb)*64 + i] * dY[pixel][co]
+// A row block rb = (tap, 64-channel chunk of Cin).  One work item = (k-split, pair of row blocks,
+// N tile); it walks its range of 64-pixel boxes.  Both operands are MN-major in shared memory
+// (a TMA box [64 pixels][64 channels] is exactly one MN-major SWIZZLE_128B block).
+// ------------------------------------------------------------------------------------------
+struct WgradParams {
+  int N, H, W;
+  int bw, bh, bn;  // 64-pixel box
+  int tiles_w, tiles_h, tiles_n;
+  int splits, n_rb, n_rbp, kchunks_in, n_tiles;
+  int Cin_total, Cout_total;  // leading dims of dW rows / cols
+  int dw_tap_stride;          // elements between taps in dW (= Cin*Cout for HWIO)
+  int dw_row_stride;          // elements between consecutive ci rows (= Cout for HWIO)
+  int dw_col_stride;          // elements between consecutive co (1 for HWIO)
+  float* dw;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const TapTable taps) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + C::kStages;
+  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_items = p.splits * p.n_rbp * p.n_tiles;
+  const int per_split = (n_ptiles + p.splits - 1) / p.splits;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState ps;
+      constexpr uint32_t tx_bytes = (uint32_t)C::kStageBytes;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int nt = item % p.n_tiles;
+        const int rbp = (item / p.n_tiles) % p.n_rbp;
+        const int split = item / (p.n_tiles * p.n_rbp);
+        const int rb0 = 2 * rbp, rb1 = (2 * rbp + 1 < p.n_rb) ? 2 * rbp + 1 : 2 * rbp;
+        const int tap0 = rb0 / p.kchunks_in, c0 = (rb0 % p.kchunks_in) * 64;
+        const int tap1 = rb1 / p.kchunks_in, c1 = (rb1 % p.kchunks_in) * 64;
+        const int dy0 = taps.dy[tap0], dx0 = taps.dx[tap0], dy1 = taps.dy[tap1], dx1 = taps.dx[tap1];
+        const int m0 = taps.map[tap0], m1 = taps.map[tap1];
+        const int pt0 = split * per_split;
+        const int pt1 = min(pt0 + per_split, n_ptiles);
+        for (int pt = pt0; pt < pt1; ++pt) {
+          const int x0 = (pt % p.tiles_w) * p.bw;
+          const int y0 = ((pt / p.tiles_w) % p.tiles_h) * p.bh;
+          const int n0 = (pt / (p.tiles_w * p.tiles_h)) * p.bn;
+          mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+          uint8_t* sa = smem + ps.stage * C::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
+          tma_load_4d(&maps.a[m0], &full_bar[ps.stage], sa, c0, x0 + dx0, y0 + dy0, n0);
+          tma_load_4d(&maps.a[m1], &full_bar[ps.stage], sa + 8192, c1, x0 + dx1, y0 + dy1, n0);
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_4d(&maps.b, &full_bar[ps.stage], sa + kABytes + j * 8192, nt * BLOCK_N + j * 64, x0, y0, n0);
+          ps.advance<C::kStages>();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      PipeState ps;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 1, 1);
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int split = item / (p.n_tiles * p.n_rbp);
+        const int pt0 = split * per_split;
+        const int pt1 = min(pt0 + per_split, n_ptiles);
+        const int nsteps = pt1 - pt0;
+        if (nsteps <= 0) continue;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int ks = 0; ks < nsteps; ++ks) {
+          mbar_wait(&full_bar[ps.stage], ps.phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + ps.stage * C::kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 16 pixels per MMA
+            const uint64_t ad = make_smem_desc(a_addr + k * 2048, 8192, 1024);
+            const uint64_t bd = make_smem_desc(b_addr + k * 2048, 8192, 1024);
+            umma_f16(d_addr, ad, bd, idesc, (ks | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[ps.stage]);
+          if (ks == nsteps - 1) umma_commit(&tfull_bar[acc]);
+          ps.advance<C::kStages>();
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int nt = item % p.n_tiles;
+      const int rbp = (item / p.n_tiles) % p.n_rbp;
+      const int split = item / (p.n_tiles * p.n_rbp);
+      const int pt0 = split * per_split;
+      const int pt1 = min(pt0 + per_split, n_ptiles);
+      if (pt1 - pt0 <= 0) continue;
+      const int rb = 2 * rbp + (row >> 6);
+      const bool valid = rb < p.n_rb;
+      const int tap = rb / p.kchunks_in;
+      const int ci = (rb % p.kchunks_in) * 64 + (row & 63);
+      float* dst = p.dw + (int64_t)tap * p.dw_tap_stride + (int64_t)ci * p.dw_row_stride +
+                   (int64_t)(nt * BLOCK_N) * p.dw_col_stride;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(dst + (int64_t)(c0 + i) * p.dw_col_stride, __uint_as_float(r[i]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct Box {
+  int bw, bh, bn, rows, tiles;
+};
+
+// Pick a pixel box bw x bh x bn with at most `max_rows` rows (exactly, when `exact`) that
+// covers [N,H,W] with the fewest tiles; ties -> wider bw (longer contiguous runs for TMA).
+Box choose_box(int N, int H, int W, int max_rows, bool exact, int lim_h = 0, int lim_w = 0) {
+  Box best{0, 0, 0, 0, 0};
+  int64_t best_cost = -1;
+  if (lim_h <= 0) lim_h = H;
+  if (lim_w <= 0) lim_w = W;
+  for (int bw = 1; bw <= lim_w && bw <= max_rows; ++bw) {
+    for (int bh = 1; bh <= lim_h && bw * bh <= max_rows; ++bh) {
+      int bn = max_rows / (bw * bh);
+      if (bn > N) bn = N;
+      if (bn > 256 || bw > 256 || bh > 256) continue;
+      const int rows = bw * bh * bn;
+      if (exact && rows != max_rows) continue;
+      if (!exact && rows % 8 != 0) continue;
+      const int tiles = ceil_div(W, bw) * ceil_div(H, bh) * ceil_div(N, bn);
+      const int64_t cost = (int64_t)tiles * 1024 - bw;
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best = Box{bw, bh, bn, rows, tiles};
+      }
+    }
+  }
+  return best;
+}
+
+int encode_act_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int N, int H, int W, int C, int64_t pix_stride_w,
+                   int64_t pix_stride_h, int64_t pix_stride_n, int bw, int bh, int bn) {
+  // dims innermost first: (C, W, H, N); strides in bytes for dims 1..3
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)pix_stride_w * 2, (cuuint64_t)pix_stride_h * 2, (cuuint64_t)pix_stride_n * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = ctx->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return segk_fail(ctx, SEGK_ECUDA, "cuTensorMapEncodeTiled(act %dx%dx%dx%d box %dx%dx%d) failed: %d", N, H, W, C,
+                     bw, bh, bn, (int)r);
+  return SEGK_OK;
+}
+
+int encode_weight_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int K, int Nrows, int T, int block_n) {
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Nrows, (cuuint64_t)T};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * Nrows * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)block_n, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = ctx->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return segk_fail(ctx, SEGK_ECUDA, "cuTensorMapEncodeTiled(weights K=%d N=%d T=%d) failed: %d", K, Nrows, T, (int)r);
+  return SEGK_OK;
+}
+
+int pick_block_n(int Cout) {
+  if (Cout % 256 == 0) return 256;
+  if (Cout % 128 == 0) return 128;
+  return 64;
+}
+
+template <int BLOCK_N>
+int launch_igemm_t(segk_ctx* ctx, const TensorMaps& maps, const IgemmParams& p, const TapTable& taps, int grid,
+                   cudaStream_t st) {
+  using C = Cfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "igemm smem attr: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  igemm_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(maps, p, taps);
+  SEGK_LAUNCHED(ctx, "igemm");
+  return SEGK_OK;
+}
+
+int launch_igemm(segk_ctx* ctx, int block_n, const TensorMaps& maps, const IgemmParams& p, const TapTable& taps,
+                 cudaStream_t st) {
+  const int total = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  switch (block_n) {
+    case 256: return launch_igemm_t<256>(ctx, maps, p, taps, grid, st);
+    case 128: return launch_igemm_t<128>(ctx, maps, p, taps, grid, st);
+    default: return launch_igemm_t<64>(ctx, maps, p, taps, grid, st);
+  }
+}
+
+template <int BLOCK_N>
+int launch_wgrad_t(segk_ctx* ctx, const TensorMaps& maps, const WgradParams& p, const TapTable& taps, int grid,
+                   cudaStream_t st) {
+  using C = Cfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "wgrad smem attr: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  wgrad_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(maps, p, taps);
+  SEGK_LAUNCHED(ctx, "wgrad");
+  return SEGK_OK;
+}
+
+void conv_taps(TapTable& t, int kh, int kw) {
+  memset(&t, 0, sizeof(t));
+  for (int i = 0; i < kh * kw; ++i) {
+    t.dy[i] = (int8_t)(i / kw - kh / 2);
+    t.dx[i] = (int8_t)(i % kw - kw / 2);
+    t.map[i] = 0;
+  }
+}
+
+// shared body of conv fwd and dgrad: y[N,H,W,Cn] = epilogue( sum_taps x[.. + tap][Ck] * wt[tap][Cn][Ck] )
+int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, const float* bias, const void* residual,
+               const void* mask, float scale, int relu, int out_f32, void* y, int N, int H, int W, int Ck, int Cn,
+               int kh, int kw, void* stream) {
+  SEGK_REQUIRE(ctx, x && wt && y, "%s: null pointer", what);
+  SEGK_REQUIRE(ctx, N > 0 && H > 0 && W > 0, "%s: empty tensor", what);
+  SEGK_REQUIRE(ctx, Ck % 64 == 0 && Cn % 64 == 0 && Ck > 0 && Cn > 0,
+               "%s: tensor-core path needs channel counts that are multiples of 64 (got %d -> %d); no fallback", what,
+               Ck, Cn);
+  SEGK_REQUIRE(ctx, (kh & 1) && (kw & 1) && kh * kw <= kMaxTaps, "%s: odd kernel sizes up to %d taps (got %dx%d)", what,
+               kMaxTaps, kh, kw);
+  SEGK_REQUIRE(ctx, (((uintptr_t)x | (uintptr_t)wt | (uintptr_t)y | (uintptr_t)residual | (uintptr_t)mask) & 15) == 0,
+               "%s: pointers must be 16-byte aligned", what);
+  const Box b = choose_box(N, H, W, kBlockM, false);
+  SEGK_REQUIRE(ctx, b.rows > 0, "%s: no pixel box for %dx%dx%d", what, N, H, W);
+  const int block_n = pick_block_n(Cn);
+  TensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Ck, Ck, (int64_t)W * Ck, (int64_t)H * W * Ck, b.bw, b.bh, b.bn);
+  if (rc) return rc;
+  maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
+  rc = encode_weight_map(ctx, &maps.b, wt, Ck, Cn, kh * kw, block_n);
+  if (rc) return rc;
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W;
+  p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.rows;
+  p.tiles_w = ceil_div(W, b.bw); p.tiles_h = ceil_div(H, b.bh); p.tiles_n = ceil_div(N, b.bn);
+  p.n_tiles = Cn / block_n;
+  p.phases = 1; p.s = 1;
+  p.ntaps = kh * kw; p.kchunks = Ck / 64;
+  p.in_H = H; p.in_W = W;
+  p.out_H = H; p.out_W = W; p.ldo = Cn; p.os = 1; p.opad = 0;
+  p.out = y; p.out_f32 = out_f32;
+  p.bias = bias; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask;
+  p.scale = scale; p.relu = relu;
+  TapTable taps;
+  conv_taps(taps, kh, kw);
+  return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+}
+
+
+// decimated views of a [N, s*H, s*W, C] tensor: view (py,px) holds pixels (s*i+py, s*j+px)
+int encode_decimated_maps(segk_ctx* ctx, TensorMaps& maps, const void* base, int N, int H, int W, int C, int s,
+                          const Box& b) {
+  const int OH = H * s, OW = W * s;
+  for (int py = 0; py < s; ++py)
+    for (int px = 0; px < s; ++px) {
+      const bf16* v = (const bf16*)base + ((int64_t)py * OW + px) * C;
+      int rc = encode_act_map(ctx, &maps.a[py * s + px], v, N, H, W, C, (int64_t)s * C, (int64_t)s * OW * C,
+                              (int64_t)OH * OW * C, b.bw, b.bh, b.bn);
+      if (rc) return rc;
+    }
+  return SEGK_OK;
+}
+
+// taps of the stride-s conv that is the transposed conv's gradient: dY row s*i - p + ky
+void strided_taps(TapTable& t, int k, int s) {
+  memset(&t, 0, sizeof(t));
+  const int p = s / 2;
+  for (int ky = 0; ky < k; ++ky)
+    for (int kx = 0; kx < k; ++kx) {
+      const int ry = ky - p, rx = kx - p;
+      const int py = ((ry % s) + s) % s, px = ((rx % s) + s) % s;
+      const int i = ky * k + kx;
+      t.dy[i] = (int8_t)((ry - py) / s);
+      t.dx[i] = (int8_t)((rx - px) / s);
+      t.map[i] = (int8_t)(py * s + px);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* bias, const void* residual, void* y,
+                      int N, int H, int W, int Cin, int Cout, int k, int s, unsigned flags, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && wk && y && N > 0 && H > 0 && W > 0, "deconv2d_fwd: bad args");
+  SEGK_REQUIRE(ctx, k == 2 * s && s >= 2 && s % 2 == 0 && s * s * 4 <= 32767, "deconv2d_fwd: need k == 2*stride, even stride");
+  SEGK_REQUIRE(ctx, Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0,
+               "deconv2d_fwd: tensor-core path needs channels %% 64 == 0 (got %d -> %d); use segk_deconv2d_small_fwd", Cin,
+               Cout);
+  const Box b = choose_box(N, H + 1, W + 1, kBlockM, false, H, W);
+  SEGK_REQUIRE(ctx, b.rows > 0, "deconv2d_fwd: no pixel box");
+  const int block_n = pick_block_n(Cout);
+  TensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Cin, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin, b.bw, b.bh, b.bn);
+  if (rc) return rc;
+  maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
+  rc = encode_weight_map(ctx, &maps.b, wk, Cin, Cout, s * s * 4, block_n);
+  if (rc) return rc;
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H + 1; p.W = W + 1;
+  p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.rows;
+  p.tiles_w = ceil_div(W + 1, b.bw); p.tiles_h = ceil_div(H + 1, b.bh); p.tiles_n = ceil_div(N, b.bn);
+  p.n_tiles = Cout / block_n;
+  p.phases = s * s; p.s = s;
+  p.ntaps = 4; p.kchunks = Cin / 64;
+  p.in_H = H; p.in_W = W;
+  p.out_H = H * s; p.out_W = W * s; p.ldo = Cout; p.os = s; p.opad = s / 2;
+  p.out = y; p.out_f32 = (flags & SEGK_EPI_OUT_F32) ? 1 : 0;
+  p.bias = bias; p.residual = (const bf16*)residual; p.mask = nullptr;
+  p.scale = 1.f; p.relu = (flags & SEGK_EPI_RELU) ? 1 : 0;
+  TapTable taps;
+  memset(&taps, 0, sizeof(taps));
+  for (int u = 0; u < 4; ++u) {
+    taps.dy[u] = (int8_t)(u / 2 - 1);
+    taps.dx[u] = (int8_t)(u % 2 - 1);
+  }
+  return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+}
+
+int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, void* dx, int N, int H,
+                        int W, int Cin, int Cout, int k, int s, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, dy && wd && dx && N > 0 && H > 0 && W > 0, "deconv2d_dgrad: bad args");
+  SEGK_REQUIRE(ctx, k == 4 && s == 2, "deconv2d_dgrad: tensor-core path supports k=4, stride 2 (got k=%d s=%d)", k, s);
+  SEGK_REQUIRE(ctx, Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0,
+               "deconv2d_dgrad: tensor-core path needs channels %% 64 == 0 (got %d -> %d)", Cin, Cout);
+  const Box b = choose_box(N, H, W, kBlockM, false);
+  SEGK_REQUIRE(ctx, b.rows > 0, "deconv2d_dgrad: no pixel box");
+  const int block_n = pick_block_n(Cin);
+  TensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc = encode_decimated_maps(ctx, maps, dy, N, H, W, Cout, s, b);
+  if (rc) return rc;
+  rc = encode_weight_map(ctx, &maps.b, wd, Cout, Cin, k * k, block_n);
+  if (rc) return rc;
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W;
+  p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.rows;
+  p.tiles_w = ceil_div(W, b.bw); p.tiles_h = ceil_div(H, b.bh); p.tiles_n = ceil_div(N, b.bn);
+  p.n_tiles = Cin / block_n;
+  p.phases = 1; p.s = 1;
+  p.ntaps = k * k; p.kchunks = Cout / 64;
+  p.in_H = H; p.in_W = W;
+  p.out_H = H; p.out_W = W; p.ldo = Cin; p.os = 1; p.opad = 0;
+  p.out = dx; p.out_f32 = 0;
+  p.mask = (const bf16*)relu_mask;
+  p.scale = 1.f;
+  TapTable taps;
+  strided_taps(taps, k, s);
+  return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+}
+
+int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                        int k, int s, int accumulate, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && dy && dw && N > 0 && H > 0 && W > 0, "deconv2d_wgrad: bad args");
+  SEGK_REQUIRE(ctx, k == 4 && s == 2, "deconv2d_wgrad: tensor-core path supports k=4, stride 2 (got k=%d s=%d)", k, s);
+  SEGK_REQUIRE(ctx, Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0,
+               "deconv2d_wgrad: tensor-core path needs channels %% 64 == 0 (got %d -> %d)", Cin, Cout);
+  cudaStream_t st = (cudaStream_t)stream;
+  const Box b = choose_box(N, H, W, 64, true);
+  SEGK_REQUIRE(ctx, b.rows == 64, "deconv2d_wgrad: cannot tile %dx%dx%d into 64-pixel boxes", N, H, W);
+  const int block_n = pick_block_n(Cin);
+  TensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc = encode_decimated_maps(ctx, maps, dy, N, H, W, Cout, s, b);  // A side: dY (rows = (tap, co))
+  if (rc) return rc;
+  rc = encode_act_map(ctx, &maps.b, x, N, H, W, Cin, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin, b.bw, b.bh, b.bn);
+  if (rc) return rc;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W;
+  p.bw = b.bw; p.bh = b.bh; p.bn = b.bn;
+  p.tiles_w = ceil_div(W, b.bw); p.tiles_h = ceil_div(H, b.bh); p.tiles_n = ceil_div(N, b.bn);
+  const int n_ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.kchunks_in = Cout / 64;
+  p.n_rb = k * k * p.kchunks_in;
+  p.n_rbp = (p.n_rb + 1) / 2;
+  p.n_tiles = Cin / block_n;
+  int splits = ceil_div(2 * ctx->sm_count, p.n_rbp * p.n_tiles);
+  const int max_splits = ceil_div(n_ptiles, 8);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const int per_split = ceil_div(n_ptiles, splits);
+  p.splits = ceil_div(n_ptiles, per_split);
+  p.Cin_total = Cout; p.Cout_total = Cin;
+  p.dw_tap_stride = Cout * Cin; p.dw_row_stride = Cin; p.dw_col_stride = 1;
+  p.dw = dw;
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * k * Cin * Cout, st);
+    if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "deconv2d_wgrad memset: %s", cudaGetErrorString(e));
+  }
+  TapTable taps;
+  strided_taps(taps, k, s);
+  const int total = p.splits * p.n_rbp * p.n_tiles;
+  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  switch (block_n) {
+    case 256: return launch_wgrad_t<256>(ctx, maps, p, taps, grid, st);
+    case 128: return launch_wgrad_t<128>(ctx, maps, p, taps, grid, st);
+    default: return launch_wgrad_t<64>(ctx, maps, p, taps, grid, st);
+  }
+}
+
+int segk_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* bias, const void* residual, void* y,
+                    int N, int H, int W, int Cin, int Cout, int kh, int kw, unsigned flags, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  return conv_igemm(ctx, "conv2d_fwd", x, wk, bias, residual, nullptr, 1.f, (flags & SEGK_EPI_RELU) ? 1 : 0,
+                    (flags & SEGK_EPI_OUT_F32) ? 1 : 0, y, N, H, W, Cin, Cout, kh, kw, stream);
+}
+
+int segk_conv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, const void* residual,
+                      void* dx, float scale, int N, int H, int W, int Cin, int Cout, int kh, int kw, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  // GEMM-K = Cout (channels of dy), GEMM-N = Cin (channels of dx); wd holds the taps reversed.
+  return conv_igemm(ctx, "conv2d_dgrad", dy, wd, nullptr, residual, relu_mask, scale, 0, 0, dx, N, H, W, Cout, Cin, kh,
+                    kw, stream);
+}
+
+int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                      int kh, int kw, int accumulate, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && dy && dw, "conv2d_wgrad: null pointer");
+  SEGK_REQUIRE(ctx, N > 0 && H > 0 && W > 0, "conv2d_wgrad: empty tensor");
+  SEGK_REQUIRE(ctx, Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0,
+               "conv2d_wgrad: tensor-core path needs channel counts that are multiples of 64 (got %d -> %d); no fallback",
+               Cin, Cout);
+  SEGK_REQUIRE(ctx, (kh & 1) && (kw & 1) && kh * kw <= kMaxTaps, "conv2d_wgrad: odd kernel sizes up to %d taps", kMaxTaps);
+  SEGK_REQUIRE(ctx, (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) == 0, "conv2d_wgrad: 16-byte alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const Box b = choose_box(N, H, W, 64, true);
+  SEGK_REQUIRE(ctx, b.rows == 64, "conv2d_wgrad: cannot tile %dx%dx%d into 64-pixel boxes (need N*H*W >= 64)", N, H, W);
+  const int block_n = pick_block_n(Cout);
+  TensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Cin, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin, b.bw, b.bh, b.bn);
+  if (rc) return rc;
+  maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
+  rc = encode_act_map(ctx, &maps.b, dy, N, H, W, Cout, Cout, (int64_t)W * Cout, (int64_t)H * W * Cout, b.bw, b.bh, b.bn);
+  if (rc) return rc;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W;
+  p.bw = b.bw; p.bh = b.bh; p.bn = b.bn;
+  p.tiles_w = ceil_div(W, b.bw); p.tiles_h = ceil_div(H, b.bh); p.tiles_n = ceil_div(N, b.bn);
+  const int n_ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.kchunks_in = Cin / 64;
+  p.n_rb = kh * kw * p.kchunks_in;
+  p.n_rbp = (p.n_rb + 1) / 2;
+  p.n_tiles = Cout / block_n;
+  const int base_items = p.n_rbp * p.n_tiles;
+  int splits = ceil_div(2 * ctx->sm_count, base_items);
+  const int max_splits = ceil_div(n_ptiles, 8);  // at least 8 k-steps per item
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  // make every split non-empty
+  const int per_split = ceil_div(n_ptiles, splits);
+  splits = ceil_div(n_ptiles, per_split);
+  p.splits = splits;
+  p.Cin_total = Cin; p.Cout_total = Cout;
+  p.dw_tap_stride = Cin * Cout; p.dw_row_stride = Cout; p.dw_col_stride = 1;
+  p.dw = dw;
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)kh * kw * Cin * Cout, st);
+    if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "conv2d_wgrad memset: %s", cudaGetErrorString(e));
+  }
+  TapTable taps;
+  conv_taps(taps, kh, kw);
+  const int total = p.splits * p.n_rbp * p.n_tiles;
+  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  switch (block_n) {
+    case 256: return launch_wgrad_t<256>(ctx, maps, p, taps, grid, st);
+    case 128: return launch_wgrad_t<128>(ctx, maps, p, taps, grid, st);
+    default: return launch_wgrad_t<64>(ctx, maps, p, taps, grid, st);
+  }
+}
+
+}  // extern "C"

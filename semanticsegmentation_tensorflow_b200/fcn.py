@@ -1,0 +1,435 @@
+"""FCN-8s on the B200 kernels behind the reference's builder API (`Network/model/FCN.py`).
+
+    net = FCN(image, keep_prob, num_classess)      # FCN.py:31-47  (image: NHWC u8/float CUDA tensor)
+    pred, logits = net.create()                    # FCN.py:49-114 (runs the forward pass)
+    loss = net.loss(annotation)                    # FCN.py:334
+    train_step = AdamOptimizer(1e-4).minimize(net) # FCN.py:338-340
+    train_step({net.image: x, net.annotation: y, net.keep_probability: 0.8})   # FCN.py:395-398
+
+The TF-1.x graph/session split collapses: `create()` executes eagerly on the current CUDA
+stream.  Every FLOP runs in libsegk.so (tcgen05 implicit-GEMM convs, HBM-bound pool / loss /
+optimizer kernels); torch only owns the buffers."""
+from __future__ import annotations
+
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import plan as P
+from .ops import Ops
+
+
+def reference_init(shapes, seed: int = 1234, init: str = "ref"):
+    """Variables as the reference creates them: weights N(0, 0.01^2) (FCN.py:125,143,102),
+    biases 0 (FCN.py:127,145,103); one numpy default_rng(seed) stream consumed in creation
+    order.  init='he' gives every layer a visible scale for parity tests."""
+    rng = np.random.default_rng(seed)
+    out = OrderedDict()
+    for name, shape in shapes.items():
+        if name.endswith("weights"):
+            z = rng.standard_normal(shape, dtype=np.float32)
+            if init == "ref":
+                std = 0.01
+            else:
+                if name.startswith("conv_t"):
+                    kh, kw, _, ci = shape
+                    s = {4: 2, 16: 8}[kh]
+                    fan_in = (kh // s) * (kw // s) * ci
+                else:
+                    kh, kw, ci, _ = shape
+                    fan_in = kh * kw * ci
+                std = float(np.sqrt(2.0 / fan_in))
+            out[name] = (z * np.float32(std)).astype(np.float32)
+        else:
+            out[name] = np.zeros(shape, np.float32)
+    return out
+
+
+class Variables:
+    """Flat fp32 arenas (params, Adam m/v, gradients) + bf16 kernel-layout weight shadows."""
+
+    def __init__(self, layers, device, values=None, init="ref", seed=1234):
+        self.layers = [l for l in layers if l.kind != "pool"]
+        shapes = OrderedDict()
+        for l in self.layers:
+            shapes[f"{l.name}/weights"] = l.weight_shape
+            shapes[f"{l.name}/{l.bias_name}"] = (l.cout,)
+        self.shapes = shapes
+        self.slots, self.total = P.arena_layout(shapes)
+        self.device = device
+        self.p = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.g = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.m = None   # optimizer slots are created by the optimizer (as TF does)
+        self.v = None
+        if values is None:
+            if init == "device":
+                gen = torch.Generator(device=device)
+                gen.manual_seed(seed)
+                for name, s in self.slots.items():
+                    if name.endswith("weights"):
+                        self.view(self.p, name).copy_(
+                            torch.randn(s.shape, generator=gen, device=device, dtype=torch.float32) * 0.01)
+            else:
+                values = reference_init(shapes, seed, init)
+        if values is not None:
+            self.assign(values)
+        self.wk = {}
+        self.wd = {}
+
+    def view(self, arena, name):
+        s = self.slots[name]
+        return arena[s.offset:s.offset + s.size].view(s.shape)
+
+    def assign(self, values):
+        for name, arr in values.items():
+            self.view(self.p, name).copy_(torch.as_tensor(np.asarray(arr), dtype=torch.float32))
+
+    def param(self, name):
+        return self.view(self.p, name)
+
+    def grad(self, name):
+        return self.view(self.g, name)
+
+    def export(self):
+        """{reference variable name: numpy array} in reference layouts (checkpoint interchange)."""
+        return OrderedDict((n, self.view(self.p, n).detach().cpu().numpy().copy()) for n in self.slots)
+
+    def repack(self, ops: Ops):
+        """fp32 masters -> bf16 kernel layouts for the tensor-core layers (after each update)."""
+        for l in self.layers:
+            if not l.tensor_core:
+                continue
+            w = self.param(f"{l.name}/weights")
+            if l.kind == "conv":
+                self.wk[l.name], self.wd[l.name] = ops.pack_conv_weights(w, self.wk.get(l.name), self.wd.get(l.name))
+            else:
+                self.wk[l.name], self.wd[l.name] = ops.pack_deconv_weights(w, l.stride, self.wk.get(l.name),
+                                                                           self.wd.get(l.name))
+
+
+class _Feed:
+    """Placeholder handle (tf.placeholder analogue, FCN.py:311-313) used as feed_dict key."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __repr__(self):
+        return f"<placeholder {self.name}>"
+
+
+class FCN:
+    """FCN-8s builder with the reference's constructor signature (FCN.py:31-47)."""
+
+    def __init__(self, x, keep_prob=1.0, num_classess=2, variables=None, init="ref", seed=1234, fc=4096,
+                 dropout_seed=42, world_size=1):
+        if not torch.cuda.is_available():
+            raise RuntimeError("FCN needs a CUDA (sm_100a) device: the segmentation ops have no CPU fallback")
+        x = self._as_image(x)
+        self.device = x.device
+        self.ops = Ops(self.device)
+        self.num_classes = int(num_classess)
+        self.keep_prob = float(keep_prob)
+        self.N, self.H, self.W, self.Cin = x.shape
+        if self.H % 32 or self.W % 32:
+            raise ValueError(f"image size {self.H}x{self.W} must be a multiple of 32 (five 2x2 pools)")
+        self.layers = P.fcn8s_layers(self.Cin, self.num_classes, fc)
+        self.vars = variables if isinstance(variables, Variables) else Variables(
+            self.layers, self.device, values=variables, init=init, seed=seed)
+        self.vars.repack(self.ops)
+        self.world_size = world_size
+        self.dropout_seed = dropout_seed
+        self.step_count = 0
+        self.injected_masks = None     # {"dropout6": u8 tensor, "dropout7": ...} for parity runs
+        # placeholders (FCN.py:311-313)
+        self.image = _Feed("input_image")
+        self.annotation = _Feed("annotation")
+        self.keep_probability = _Feed("keep_probability")
+        self.x = x
+        self._alloc()
+        self._ran_forward = False
+
+    # -- buffers ------------------------------------------------------------------------
+    @staticmethod
+    def _as_image(x):
+        x = torch.as_tensor(x)
+        if x.dim() != 4:
+            raise ValueError("image must be NHWC")
+        if x.dtype != torch.uint8:
+            # raw 0..255 pixels fed as float (FCN.py:312,395): exact in u8
+            x = x.round().clamp(0, 255).to(torch.uint8)
+        return x.contiguous()
+
+    def _alloc(self):
+        dev, N = self.device, self.N
+        bf = torch.bfloat16
+        self.act = OrderedDict()
+        self.idx = {}
+        h, w = self.H, self.W
+        for l in self.layers:
+            if l.kind == "pool":
+                h, w = h // 2, w // 2
+                self.act[l.name] = torch.empty((N, h, w, l.cout), dtype=bf, device=dev)
+                self.idx[l.name] = torch.empty((N, h, w, l.cout), dtype=torch.uint8, device=dev)
+            elif l.kind == "conv":
+                self.act[l.name] = torch.empty((N, h, w, l.cout), dtype=bf, device=dev)
+            else:
+                h, w = h * l.stride, w * l.stride
+                if l.name == "conv_t3":
+                    self.act[l.name] = torch.empty((N, h, w, l.cout), dtype=torch.float32, device=dev)
+                else:
+                    self.act[l.name] = torch.empty((N, h, w, l.cout), dtype=bf, device=dev)
+        self.logits = self.act["conv_t3"]
+        npix = N * self.H * self.W
+        self.dlogits = torch.empty_like(self.logits)
+        self.pred_u8 = torch.empty((N, self.H, self.W), dtype=torch.uint8, device=dev)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.cm = torch.zeros(4, dtype=torch.int64, device=dev)
+        self.xent_ws = self.ops.xent_workspace(npix, dev)
+        self.labels = torch.zeros((N, self.H, self.W), dtype=torch.uint8, device=dev)
+        # gradient ping-pong buffers (largest activation: N*H*W*64 bf16) + the two skip gradients
+        big = N * self.H * self.W * 64
+        self._gbuf = [torch.empty(big, dtype=bf, device=dev) for _ in range(2)]
+        self.dfuse_1 = torch.empty_like(self.act["conv_t1"])
+        self.dfuse_2 = torch.empty_like(self.act["conv_t2"])
+
+    def _g(self, i, like):
+        return self._gbuf[i][:like.numel()].view(like.shape)
+
+    # -- feeds --------------------------------------------------------------------------
+    def feed(self, feed_dict):
+        for k, v in feed_dict.items():
+            name = k.name if isinstance(k, _Feed) else str(k)
+            if name == "input_image":
+                x = self._as_image(v)
+                if tuple(x.shape) != (self.N, self.H, self.W, self.Cin):
+                    raise ValueError(f"image shape {tuple(x.shape)} != planned {(self.N, self.H, self.W, self.Cin)}")
+                self.x = x.to(self.device, non_blocking=True)
+            elif name == "annotation":
+                self.labels = self._as_labels(v)
+            elif name == "keep_probability":
+                self.keep_prob = float(v)
+            else:
+                raise KeyError(name)
+
+    def _as_labels(self, y):
+        """Class-id map u8 [N,H,W]; also accepts the reference's one-hot [N,H,W,2] bool/float
+        (channel 1 = road, FCN.py:195-201)."""
+        y = torch.as_tensor(y)
+        if y.dim() == 4:
+            y = y.to(self.device).argmax(dim=3)
+        y = y.to(device=self.device, dtype=torch.uint8, non_blocking=True).contiguous()
+        if tuple(y.shape) != (self.N, self.H, self.W):
+            raise ValueError(f"annotation shape {tuple(y.shape)} != {(self.N, self.H, self.W)}")
+        return y
+
+    # -- forward (FCN.py:49-114) ------------------------------------------------------
+    def _dropout_fwd(self, l, t):
+        if self.keep_prob >= 1.0:
+            return
+        mask = None if self.injected_masks is None else self.injected_masks.get("dropout" + l.name[-1])
+        seed = (self.dropout_seed * 1000003 + self.step_count) * 16 + int(l.name[-1])
+        self.ops.dropout(t, t, self.keep_prob, seed, mask)
+
+    def create(self):
+        """Run the forward pass; returns (pred [N,H,W,1] int64, logits [N,H,W,C] f32)."""
+        self.forward()
+        pred = (self.logits[..., 1] > self.logits[..., 0]).to(torch.int64).unsqueeze(3) if self.num_classes == 2 \
+            else torch.argmax(self.logits, dim=3, keepdim=True)
+        return pred, self.logits
+
+    def forward(self):
+        ops, V, act = self.ops, self.vars, self.act
+        cur = self.x
+        for l in self.layers:
+            out = act[l.name]
+            if l.kind == "pool":
+                ops.maxpool_fwd(cur, out, self.idx[l.name])
+            elif l.kind == "conv":
+                b = V.param(f"{l.name}/{l.bias_name}")
+                if l.tensor_core:
+                    ops.conv2d_fwd(cur, V.wk[l.name], b, out, l.k, l.k, relu=l.relu)
+                else:
+                    ops.conv2d_small_fwd(cur, V.param(f"{l.name}/weights"), b, out, relu=l.relu)
+                if l.dropout:
+                    self._dropout_fwd(l, out)
+            else:
+                b = V.param(f"{l.name}/{l.bias_name}")
+                res = {"conv_t1": act["pool4"], "conv_t2": act["pool3"]}.get(l.name)   # fuse, FCN.py:92,96
+                if l.tensor_core:
+                    ops.deconv2d_fwd(cur, V.wk[l.name], b, out, l.k, l.stride, residual=res)
+                else:
+                    ops.deconv2d_small_fwd(cur, V.param(f"{l.name}/weights"), b, out, l.stride, residual=res)
+            cur = out
+        self._ran_forward = True
+        return self.logits
+
+    # -- loss (FCN.py:334) ----------------------------------------------------------------
+    def loss(self, annotation=None, with_grad=False):
+        """reduce_mean(softmax_cross_entropy_with_logits); returns a 0-dim device tensor."""
+        if annotation is not None:
+            self.labels = self._as_labels(annotation)
+        if not self._ran_forward:
+            self.forward()
+        npix = self.N * self.H * self.W
+        self.ops.softmax_xent(self.logits, self.labels, self.dlogits if with_grad else None, self.pred_u8,
+                              self.loss_sum, None, self.xent_ws, 1.0 / (npix * self.world_size))
+        return self.loss_sum[0] / npix
+
+    def confusion_matrix(self):
+        """Road / non-road confusion counts cm[gt, pred] of the last forward (int64 2x2)."""
+        cm = torch.zeros(4, dtype=torch.int64, device=self.device)
+        self.ops.confusion_matrix(self.labels, self.pred_u8, cm)
+        return cm.view(2, 2)
+
+    # -- backward (what optimizer.minimize emits, FCN.py:340; schedule = SURVEY App. E) ---------
+    def backward(self, after_layer=None):
+        """Fills vars.g with d(mean loss)/d(variable).  Needs forward() + loss(with_grad=True).
+        `after_layer(name)` is called once a layer's weight and bias gradients are enqueued
+        (the data-parallel path uses it to launch bucket all-reduces)."""
+        ops, V, act = self.ops, self.vars, self.act
+        L = self.layers
+        inv_keep = 1.0 / self.keep_prob if self.keep_prob < 1.0 else 1.0
+        names = [l.name for l in L]
+        def prev_act(i):
+            return self.x if i == 0 else act[names[i - 1]]
+        dcur = self.dlogits          # gradient wrt the current layer's output (pre-activation-grad applied)
+        flip = 0
+        for i in range(len(L) - 1, -1, -1):
+            l = L[i]
+            xin = prev_act(i)
+            if l.kind == "pool":
+                # MaxPoolGrad fused with the ReluGrad of the pre-pool conv output
+                dx = self._g(flip, xin)
+                ops.maxpool_bwd(dcur, self.idx[l.name], dx, act=xin)
+                dcur = dx
+                flip ^= 1
+                continue
+            gw = V.grad(f"{l.name}/weights")
+            gb = V.grad(f"{l.name}/{l.bias_name}")
+            ops.bias_grad(dcur, gb)
+            prev = L[i - 1] if i > 0 else None
+            if l.kind == "deconv":
+                if l.tensor_core:
+                    ops.deconv2d_wgrad(xin, dcur, gw, l.k, l.stride)
+                else:
+                    ops.deconv2d_small_wgrad(xin, dcur, gw, l.stride)
+                # gradient wrt the deconv input
+                if l.name == "conv_t3":
+                    dx = self.dfuse_2
+                elif l.name == "conv_t2":
+                    dx = self.dfuse_1
+                else:
+                    dx = self._g(flip, xin)
+                    flip ^= 1
+                mask = xin if (prev is not None and prev.kind == "conv" and prev.relu) else None
+                if l.tensor_core:
+                    ops.deconv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.stride, relu_mask=mask)
+                else:
+                    ops.deconv2d_small_dgrad(dcur, V.param(f"{l.name}/weights"), dx, l.stride, relu_mask=mask)
+                dcur = dx
+            else:
+                if l.tensor_core:
+                    ops.conv2d_wgrad(xin, dcur, gw, l.k, l.k)
+                else:
+                    ops.conv2d_small_wgrad(xin, dcur, gw)
+                if i > 0:
+                    # ReluGrad of the producer (mask = its output) and dropout backward (scale) fused
+                    mask = xin if (prev.kind == "conv" and prev.relu) else None
+                    scale = inv_keep if (prev.kind == "conv" and prev.dropout) else 1.0
+                    # AddN of the skip gradients into pool4 / pool3 (FCN.py:92,96)
+                    res = {"pool4": self.dfuse_1, "pool3": self.dfuse_2}.get(prev.name)
+                    dx = self._g(flip, xin)
+                    flip ^= 1
+                    if l.tensor_core:
+                        ops.conv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.k, relu_mask=mask, residual=res, scale=scale)
+                    else:
+                        assert res is None
+                        ops.conv2d_small_dgrad(dcur, V.param(f"{l.name}/weights"), dx, relu_mask=mask, scale=scale)
+                    dcur = dx
+            if after_layer is not None:
+                after_layer(l.name)
+
+    # -- inference (FCN.py:229,204-206) -----------------------------------------------------
+    def infer(self, image=None):
+        """softmax at keep_prob 1.0 and the road mask softmax[...,1] > 0.5."""
+        if image is not None:
+            self.feed({self.image: image})
+        kp, self.keep_prob = self.keep_prob, 1.0
+        try:
+            self.forward()
+        finally:
+            self.keep_prob = kp
+        prob = torch.empty_like(self.logits)
+        mask = torch.empty((self.N, self.H, self.W), dtype=torch.uint8, device=self.device)
+        self.ops.softmax_infer(self.logits, prob, mask)
+        return prob, mask
+
+
+class AdamOptimizer:
+    """tf.train.AdamOptimizer(learning_rate) with TF's update formula (FCN.py:338)."""
+
+    def __init__(self, learning_rate=1e-4, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        self.lr, self.beta1, self.beta2, self.eps = learning_rate, beta1, beta2, epsilon
+        self.t = 0
+
+    def minimize(self, net: FCN, allreduce=None):
+        V = net.vars
+        if V.m is None:
+            V.m = torch.zeros_like(V.p)
+            V.v = torch.zeros_like(V.p)
+        return TrainStep(net, self, allreduce)
+
+    def apply(self, net: FCN, lo=0, hi=None, grad_scale=1.0):
+        V = net.vars
+        hi = V.total if hi is None else hi
+        lr_t = P.adam_lr_t(self.lr, self.t, self.beta1, self.beta2)
+        net.ops.adam_step(V.p[lo:hi], V.m[lo:hi], V.v[lo:hi], V.g[lo:hi], lr_t, self.beta1, self.beta2, self.eps,
+                          grad_scale)
+
+
+class MomentumOptimizer:
+    """tf.train.MomentumOptimizer: a = mu*a + g; p -= lr*a (new functionality)."""
+
+    def __init__(self, learning_rate, momentum=0.9):
+        self.lr, self.mu = learning_rate, momentum
+        self.t = 0
+
+    def minimize(self, net: FCN, allreduce=None):
+        if net.vars.m is None:
+            net.vars.m = torch.zeros_like(net.vars.p)
+        return TrainStep(net, self, allreduce)
+
+    def apply(self, net: FCN, lo=0, hi=None, grad_scale=1.0):
+        V = net.vars
+        hi = V.total if hi is None else hi
+        net.ops.momentum_step(V.p[lo:hi], V.m[lo:hi], V.g[lo:hi], self.lr, self.mu, grad_scale)
+
+
+class TrainStep:
+    """`train_step` of FCN.py:340; calling it is one `sess.run(train_step, feed_dict)` (FCN.py:398):
+    forward, loss, backward, (bucketed gradient all-reduce), optimizer update, weight repack.
+    Returns the mean loss as a 0-dim device tensor (no host sync)."""
+
+    def __init__(self, net: FCN, opt, allreduce=None):
+        self.net, self.opt, self.allreduce = net, opt, allreduce
+
+    def __call__(self, feed_dict=None):
+        net, opt = self.net, self.opt
+        if feed_dict:
+            net.feed(feed_dict)
+        net.forward()
+        loss = net.loss(with_grad=True)
+        opt.t += 1
+        if self.allreduce is None:
+            net.backward()
+            opt.apply(net)
+        else:
+            self.allreduce.begin_step()
+            net.backward(after_layer=self.allreduce.layer_done)
+            for lo, hi in self.allreduce.finish():
+                opt.apply(net, lo, hi)
+        net.vars.repack(net.ops)
+        net.step_count += 1
+        net._ran_forward = False
+        return loss

@@ -1,0 +1,204 @@
+"""Per-op Python wrappers over the C ABI (`include/segk.h`).  Tensors are torch CUDA tensors
+used purely as device buffers; every call enqueues on torch's current stream.
+
+Layouts: activations NHWC bf16, logits NHWC fp32, images NHWC u8, master weights fp32 in
+the reference's HWIO / [k,k,Cout,Cin] order."""
+from __future__ import annotations
+
+import torch
+
+from ._lib import Context, EPI_OUT_F32, EPI_RELU, DT_BF16, DT_U8, DT_F32
+
+_CTX = {}
+
+
+def context(device=None) -> Context:
+    if device is None:
+        device = torch.cuda.current_device()
+    if isinstance(device, torch.device):
+        device = device.index or 0
+    if device not in _CTX:
+        _CTX[device] = Context(device)
+    return _CTX[device]
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dt(x):
+    if x.dtype == torch.bfloat16:
+        return DT_BF16
+    if x.dtype == torch.uint8:
+        return DT_U8
+    if x.dtype == torch.float32:
+        return DT_F32
+    raise TypeError(f"unsupported dtype {x.dtype}")
+
+
+class Ops:
+    """Bound to one device context."""
+
+    def __init__(self, device=None):
+        self.ctx = context(device)
+        self.call = self.ctx.call
+
+    # ---- weight packing -------------------------------------------------------------
+    def pack_conv_weights(self, w, wk=None, wd=None):
+        kh, kw, cin, cout = w.shape
+        dev = w.device
+        if wk is None:
+            wk = torch.empty((kh * kw, cout, cin), dtype=torch.bfloat16, device=dev)
+        if wd is None:
+            wd = torch.empty((kh * kw, cin, cout), dtype=torch.bfloat16, device=dev)
+        self.call("segk_pack_conv_weights", _p(w), _p(wk), _p(wd), kh, kw, cin, cout, _stream())
+        return wk, wd
+
+    def pack_deconv_weights(self, w, s, wk=None, wd=None):
+        k, _, cout, cin = w.shape
+        dev = w.device
+        if wk is None:
+            wk = torch.empty((s * s, 4, cout, cin), dtype=torch.bfloat16, device=dev)
+        if wd is None:
+            wd = torch.empty((k * k, cin, cout), dtype=torch.bfloat16, device=dev)
+        self.call("segk_pack_deconv_weights", _p(w), _p(wk), _p(wd), k, s, cin, cout, _stream())
+        return wk, wd
+
+    # ---- tensor-core conv family ------------------------------------------------------
+    def conv2d_fwd(self, x, wk, bias, y, kh, kw, relu=True, residual=None):
+        n, h, w, cin = x.shape
+        cout = y.shape[3]
+        flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if y.dtype == torch.float32 else 0)
+        self.call("segk_conv2d_fwd", _p(x), _p(wk), _p(bias), _p(residual), _p(y), n, h, w, cin, cout, kh, kw,
+                  flags, _stream())
+        return y
+
+    def conv2d_dgrad(self, dy, wd, dx, kh, kw, relu_mask=None, residual=None, scale=1.0):
+        n, h, w, cout = dy.shape
+        cin = dx.shape[3]
+        self.call("segk_conv2d_dgrad", _p(dy), _p(wd), _p(relu_mask), _p(residual), _p(dx), float(scale), n, h, w,
+                  cin, cout, kh, kw, _stream())
+        return dx
+
+    def conv2d_wgrad(self, x, dy, dw, kh, kw, accumulate=False):
+        n, h, w, cin = x.shape
+        cout = dy.shape[3]
+        self.call("segk_conv2d_wgrad", _p(x), _p(dy), _p(dw), n, h, w, cin, cout, kh, kw, int(accumulate), _stream())
+        return dw
+
+    def deconv2d_fwd(self, x, wk, bias, y, k, s, residual=None, relu=False):
+        n, h, w, cin = x.shape
+        cout = y.shape[3]
+        flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if y.dtype == torch.float32 else 0)
+        self.call("segk_deconv2d_fwd", _p(x), _p(wk), _p(bias), _p(residual), _p(y), n, h, w, cin, cout, k, s, flags,
+                  _stream())
+        return y
+
+    def deconv2d_dgrad(self, dy, wd, dx, k, s, relu_mask=None):
+        n, h, w, cin = dx.shape
+        cout = dy.shape[3]
+        self.call("segk_deconv2d_dgrad", _p(dy), _p(wd), _p(relu_mask), _p(dx), n, h, w, cin, cout, k, s, _stream())
+        return dx
+
+    def deconv2d_wgrad(self, x, dy, dw, k, s, accumulate=False):
+        n, h, w, cin = x.shape
+        cout = dy.shape[3]
+        self.call("segk_deconv2d_wgrad", _p(x), _p(dy), _p(dw), n, h, w, cin, cout, k, s, int(accumulate), _stream())
+        return dw
+
+    # ---- CUDA-core layers for ragged channel counts -------------------------------------
+    def conv2d_small_fwd(self, x, w, bias, y, relu=True):
+        n, h, wd_, cin = x.shape
+        kh, kw, _, cout = w.shape
+        self.call("segk_conv2d_small_fwd", _p(x), _dt(x), _p(w), _p(bias), _p(y), n, h, wd_, cin, cout, kh, kw,
+                  EPI_RELU if relu else 0, _stream())
+        return y
+
+    def conv2d_small_dgrad(self, dy, w, dx, relu_mask=None, scale=1.0):
+        n, h, wd_, cout = dy.shape
+        kh, kw, cin, _ = w.shape
+        self.call("segk_conv2d_small_dgrad", _p(dy), _p(w), _p(relu_mask), _p(dx), float(scale), n, h, wd_, cin, cout,
+                  kh, kw, _stream())
+        return dx
+
+    def conv2d_small_wgrad(self, x, dy, dw):
+        n, h, wd_, cin = x.shape
+        kh, kw, _, cout = dw.shape
+        self.call("segk_conv2d_small_wgrad", _p(x), _dt(x), _p(dy), _p(dw), n, h, wd_, cin, cout, kh, kw, _stream())
+        return dw
+
+    def deconv2d_small_fwd(self, x, w, bias, y, s, residual=None, relu=False):
+        n, h, wd_, cin = x.shape
+        k, _, cout, _ = w.shape
+        flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if y.dtype == torch.float32 else 0)
+        self.call("segk_deconv2d_small_fwd", _p(x), _p(w), _p(bias), _p(residual), _p(y), n, h, wd_, cin, cout, k, s,
+                  flags, _stream())
+        return y
+
+    def deconv2d_small_dgrad(self, dy, w, dx, s, relu_mask=None):
+        n, h, wd_, cin = dx.shape
+        k, _, cout, _ = w.shape
+        self.call("segk_deconv2d_small_dgrad", _p(dy), int(dy.dtype == torch.float32), _p(w), _p(relu_mask), _p(dx), n,
+                  h, wd_, cin, cout, k, s, _stream())
+        return dx
+
+    def deconv2d_small_wgrad(self, x, dy, dw, s):
+        n, h, wd_, cin = x.shape
+        k, _, cout, _ = dw.shape
+        self.call("segk_deconv2d_small_wgrad", _p(x), _p(dy), int(dy.dtype == torch.float32), _p(dw), n, h, wd_, cin,
+                  cout, k, s, _stream())
+        return dw
+
+    # ---- HBM-bound kernels ----------------------------------------------------------------
+    def maxpool_fwd(self, x, y, idx):
+        n, h, w, c = x.shape
+        self.call("segk_maxpool2x2_fwd", _p(x), _p(y), _p(idx), n, h, w, c, _stream())
+        return y, idx
+
+    def maxpool_bwd(self, dy, idx, dx, act=None):
+        n, h, w, c = dx.shape
+        self.call("segk_maxpool2x2_bwd", _p(dy), _p(idx), _p(act), _p(dx), n, h, w, c, _stream())
+        return dx
+
+    def dropout(self, x, y, keep_prob, seed, mask=None):
+        self.call("segk_dropout", _p(x), _p(y), _p(mask), x.numel(), float(keep_prob), int(seed), _stream())
+        return y
+
+    def xent_workspace(self, npix, device):
+        nbytes = int(self.ctx.c.segk_xent_workspace_bytes(int(npix)))
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+    def softmax_xent(self, logits, labels, dlogits, pred, loss_sum, cm, workspace, grad_scale):
+        c = logits.shape[-1]
+        npix = logits.numel() // c
+        self.call("segk_softmax_xent_fwd_bwd", _p(logits), _p(labels), _p(dlogits), _p(pred), _p(loss_sum), _p(cm),
+                  _p(workspace), npix, c, float(grad_scale), _stream())
+
+    def softmax_infer(self, logits, prob=None, mask=None):
+        c = logits.shape[-1]
+        self.call("segk_softmax_infer", _p(logits), _p(prob), _p(mask), logits.numel() // c, c, _stream())
+
+    def confusion_matrix(self, gt, pred, cm):
+        self.call("segk_confusion_matrix", _p(gt), _p(pred), _p(cm), gt.numel(), _stream())
+        return cm
+
+    def adam_step(self, p, m, v, g, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+        self.call("segk_adam_step", _p(p), _p(m), _p(v), _p(g), p.numel(), float(lr_t), float(beta1), float(beta2),
+                  float(eps), float(grad_scale), _stream())
+
+    def momentum_step(self, p, a, g, lr, mu, grad_scale=1.0):
+        self.call("segk_momentum_step", _p(p), _p(a), _p(g), p.numel(), float(lr), float(mu), float(grad_scale),
+                  _stream())
+
+    def cast_to_bf16(self, x, y):
+        self.call("segk_cast_to_bf16", _p(x), _dt(x), _p(y), x.numel(), _stream())
+        return y
+
+    def bias_grad(self, dy, db):
+        c = dy.shape[-1]
+        self.call("segk_bias_grad", _p(dy), int(dy.dtype == torch.float32), _p(db), dy.numel() // c, c, _stream())
+        return db

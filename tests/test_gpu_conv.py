@@ -1,0 +1,157 @@
+"""GPU parity: tensor-core conv family (through the C ABI) vs the CPU oracle (oracle/tf_ops.py).
+
+Inputs are drawn on the bf16 grid so the only differences are accumulation order (fp32 in
+both) and the final bf16 store: tolerance 1e-2 of the tensor max for bf16 outputs
+(bf16 ulp = 2^-8 relative), 2e-3 for fp32 outputs (north_star: rtol 2e-2 under bf16)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tf_ops as T
+from tests.gpu_util import assert_close, bf16_grid, dev_bf16, dev_f32, host
+
+pytestmark = pytest.mark.gpu
+
+TOL_BF16 = 1e-2
+TOL_F32 = 2e-3
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_device):
+    from semanticsegmentation_tensorflow_b200.ops import Ops
+    return Ops(cuda_device)
+
+
+CONV_SHAPES = [
+    # N, H, W, Cin, Cout, k
+    (2, 16, 24, 64, 64, 3),
+    (1, 8, 8, 128, 256, 3),
+    (3, 10, 12, 128, 64, 1),
+    (2, 5, 18, 64, 128, 7),
+    (1, 20, 72, 256, 512, 3),
+    (4, 10, 36, 512, 512, 3),
+    (2, 40, 144, 128, 256, 3),
+    (1, 7, 9, 64, 192, 3),       # ragged box, Cout = 3 x 64
+]
+
+
+def _conv_case(shape, seed=0):
+    n, h, w, ci, co, k = shape
+    rng = np.random.default_rng(seed)
+    x = bf16_grid(rng.standard_normal((n, h, w, ci)))
+    wt = bf16_grid(rng.standard_normal((k, k, ci, co)) / np.sqrt(k * k * ci))
+    b = rng.standard_normal(co).astype(np.float32) * 0.1
+    return x, wt, b
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv2d_fwd_bias_relu(ops, cuda_device, shape):
+    n, h, w, ci, co, k = shape
+    x, wt, b = _conv_case(shape)
+    ref = T.relu(T.bias_add(T.conv2d_same(torch.tensor(x), torch.tensor(wt)), torch.tensor(b))).numpy()
+    wk, _ = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    y = torch.empty((n, h, w, co), dtype=torch.bfloat16, device=cuda_device)
+    ops.conv2d_fwd(dev_bf16(x, cuda_device), wk, dev_f32(b, cuda_device), y, k, k, relu=True)
+    torch.cuda.synchronize()
+    assert_close(host(y), ref, TOL_BF16, f"conv fwd {shape}")
+
+
+def test_conv2d_fwd_residual_f32_no_relu(ops, cuda_device):
+    shape = (2, 12, 20, 128, 128, 3)
+    n, h, w, ci, co, k = shape
+    x, wt, b = _conv_case(shape, 1)
+    res = bf16_grid(np.random.default_rng(2).standard_normal((n, h, w, co)))
+    ref = (T.bias_add(T.conv2d_same(torch.tensor(x), torch.tensor(wt)), torch.tensor(b)) + torch.tensor(res)).numpy()
+    wk, _ = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    y = torch.empty((n, h, w, co), dtype=torch.float32, device=cuda_device)
+    ops.conv2d_fwd(dev_bf16(x, cuda_device), wk, dev_f32(b, cuda_device), y, k, k, relu=False,
+                   residual=dev_bf16(res, cuda_device))
+    torch.cuda.synchronize()
+    assert_close(host(y), ref, TOL_F32, "conv fwd residual f32")
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv2d_dgrad(ops, cuda_device, shape):
+    n, h, w, ci, co, k = shape
+    x, wt, _ = _conv_case(shape, 3)
+    rng = np.random.default_rng(4)
+    dy = bf16_grid(rng.standard_normal((n, h, w, co)))
+    act = bf16_grid(rng.standard_normal((n, h, w, ci)))          # forward activation -> ReLU mask
+    res = bf16_grid(rng.standard_normal((n, h, w, ci)))
+    xt = torch.tensor(x, requires_grad=True)
+    T.conv2d_same(xt, torch.tensor(wt)).backward(torch.tensor(dy))
+    ref = ((xt.grad.numpy() + res) * (act > 0)) * 1.25
+    _, wd = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=cuda_device)
+    ops.conv2d_dgrad(dev_bf16(dy, cuda_device), wd, dx, k, k, relu_mask=dev_bf16(act, cuda_device),
+                     residual=dev_bf16(res, cuda_device), scale=1.25)
+    torch.cuda.synchronize()
+    assert_close(host(dx), ref, TOL_BF16, f"conv dgrad {shape}")
+
+
+@pytest.mark.parametrize("shape", CONV_SHAPES)
+def test_conv2d_wgrad(ops, cuda_device, shape):
+    n, h, w, ci, co, k = shape
+    if n * h * w < 64:
+        pytest.skip("needs >= 64 pixels")
+    x, wt, _ = _conv_case(shape, 5)
+    dy = bf16_grid(np.random.default_rng(6).standard_normal((n, h, w, co)))
+    wtt = torch.tensor(wt, requires_grad=True)
+    T.conv2d_same(torch.tensor(x), wtt).backward(torch.tensor(dy))
+    ref = wtt.grad.numpy()
+    dw = torch.full((k, k, ci, co), 7.0, dtype=torch.float32, device=cuda_device)   # must be overwritten
+    ops.conv2d_wgrad(dev_bf16(x, cuda_device), dev_bf16(dy, cuda_device), dw, k, k)
+    torch.cuda.synchronize()
+    assert_close(host(dw), ref, TOL_F32, f"conv wgrad {shape}")
+    # accumulate=1 adds on top
+    ops.conv2d_wgrad(dev_bf16(x, cuda_device), dev_bf16(dy, cuda_device), dw, k, k, accumulate=True)
+    torch.cuda.synchronize()
+    assert_close(host(dw), 2 * ref, TOL_F32, f"conv wgrad accumulate {shape}")
+
+
+DECONV_SHAPES = [
+    # N, H, W, Cin, Cout  (k=4, s=2)
+    (2, 5, 9, 64, 64),
+    (2, 10, 36, 512, 256),
+    (1, 8, 8, 128, 192),
+]
+
+
+@pytest.mark.parametrize("shape", DECONV_SHAPES)
+def test_deconv2d_tc_fwd_dgrad_wgrad(ops, cuda_device, shape):
+    n, h, w, ci, co = shape
+    k, s = 4, 2
+    rng = np.random.default_rng(7)
+    x = bf16_grid(rng.standard_normal((n, h, w, ci)))
+    wt = bf16_grid(rng.standard_normal((k, k, co, ci)) / np.sqrt(4 * ci))
+    b = rng.standard_normal(co).astype(np.float32) * 0.1
+    res = bf16_grid(rng.standard_normal((n, h * s, w * s, co)))
+    dy = bf16_grid(rng.standard_normal((n, h * s, w * s, co)))
+    xt = torch.tensor(x, requires_grad=True)
+    wtt = torch.tensor(wt, requires_grad=True)
+    y_ref = T.bias_add(T.conv2d_transpose_same(xt, wtt, (h * s, w * s), s), torch.tensor(b)) + torch.tensor(res)
+    y_ref.backward(torch.tensor(dy))
+    wk, wd = ops.pack_deconv_weights(dev_f32(wt, cuda_device), s)
+    y = torch.empty((n, h * s, w * s, co), dtype=torch.bfloat16, device=cuda_device)
+    ops.deconv2d_fwd(dev_bf16(x, cuda_device), wk, dev_f32(b, cuda_device), y, k, s, residual=dev_bf16(res, cuda_device))
+    torch.cuda.synchronize()
+    assert_close(host(y), y_ref.detach().numpy(), TOL_BF16, f"deconv fwd {shape}")
+    dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=cuda_device)
+    ops.deconv2d_dgrad(dev_bf16(dy, cuda_device), wd, dx, k, s)
+    torch.cuda.synchronize()
+    assert_close(host(dx), xt.grad.numpy(), TOL_BF16, f"deconv dgrad {shape}")
+    if n * h * w >= 64:
+        dw = torch.empty((k, k, co, ci), dtype=torch.float32, device=cuda_device)
+        ops.deconv2d_wgrad(dev_bf16(x, cuda_device), dev_bf16(dy, cuda_device), dw, k, s)
+        torch.cuda.synchronize()
+        assert_close(host(dw), wtt.grad.numpy(), TOL_F32, f"deconv wgrad {shape}")
+
+
+def test_unsupported_shape_is_an_error_not_a_fallback(ops, cuda_device):
+    from semanticsegmentation_tensorflow_b200._lib import SegkError, SEGK_EINVAL
+    x = torch.zeros((1, 8, 8, 48), dtype=torch.bfloat16, device=cuda_device)
+    wk = torch.zeros((9, 64, 48), dtype=torch.bfloat16, device=cuda_device)
+    y = torch.zeros((1, 8, 8, 64), dtype=torch.bfloat16, device=cuda_device)
+    with pytest.raises(SegkError) as ei:
+        ops.conv2d_fwd(x, wk, None, y, 3, 3)
+    assert ei.value.code == SEGK_EINVAL and "no fallback" in str(ei.value)
