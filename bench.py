@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the FCN-8s training hot path (BASELINE.json: train images/sec, FCN-8s 160x576).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle restatement)
+
+A "step" is one pass of the hot path over one synthetic batch: forward + mean softmax-xent loss +
+backward + TF-Adam update (+ gradient all-reduce when N > 1), FCN.py:398.  Workload at every N:
+BASELINE.json configs[1], batch 32 per GPU, 160x576x3 u8 images, bf16 storage / fp32 accumulate.
+Prints ONE JSON line on rank 0."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train images/sec FCN-8s 160x576"
+UNIT = "images/s"
+H, W, CIN, NCLS = 160, 576, 3, 2
+BATCH_PER_GPU = 32
+TRAIN_GFLOP_PER_IMAGE = 230.78      # valid-tap fwd+dgrad+wgrad, BASELINE.md §4 / SURVEY §8d
+KEEP_PROB = 0.8                     # FCN.py:395
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # samples under load = upper half (the sampler also sees the idle edges)
+        load = sorted(sm)[len(sm) // 2:]
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_images_per_s(steps, warmup, max_seconds=240.0):
+    """The reference's CPU path: fp32 FCN-8s fwd + bwd + TF-Adam at batch 1 (a bounded sample of the
+    batch-32 workload) on all host cores.  TensorFlow is not installable here, so this
+    is the oracle restatement ("port")."""
+    import torch
+    from oracle.fcn_oracle import FCN8sOracle, default_threads, init_variables, synthetic_batch
+    cores = default_threads()
+    torch.set_num_threads(cores)
+    orc = FCN8sOracle(init_variables(CIN, NCLS, 4096, seed=1234, init="ref"), threads=cores)
+    x, lab = synthetic_batch(1, H, W, CIN, seed=0)
+    for _ in range(warmup):
+        orc.train_step(x, lab, keep_prob=1.0)
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        orc.train_step(x, lab, keep_prob=1.0)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > max_seconds:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    return 1e3 / ms, ms, cores, len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    # each step is ~seconds of CPU work: bound the run to a few minutes
+    steps, warmup = min(steps, 5), min(warmup, 1)
+    ips, ms, cores, done = cpu_reference_images_per_s(steps, warmup)
+    sample = f"batch 1 of the 32-image step, fp32, {done} step(s) after {warmup} warm-up"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "FCN-8s 2-class training (fwd+loss+bwd+Adam), 160x576x3, CPU sample = 1 image/step",
+                   "global_batch": 1, "keep_prob": 1.0},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "restated reference (torch-CPU fp32 with TF-1.15 op semantics), not TensorFlow: TF is not installable in this image",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from semanticsegmentation_tensorflow_b200 import build_library
+    from semanticsegmentation_tensorflow_b200.dp import BucketedAllReduce, init_distributed
+    from semanticsegmentation_tensorflow_b200.fcn import FCN, AdamOptimizer
+    from semanticsegmentation_tensorflow_b200.ops import Profile
+
+    rank, world, local = init_distributed("nccl")
+    if rank == 0:
+        build_library()
+    if world > 1:
+        dist.barrier()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    B = args.batch
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    # synthetic KITTI-road-shaped batch (raw 0..255 u8 pixels, class-id labels), per rank
+    gen = torch.Generator().manual_seed(1000 + rank)
+    host_x = torch.randint(0, 256, (B, H, W, CIN), dtype=torch.uint8, generator=gen).pin_memory()
+    host_y = torch.randint(0, 2, (B, H, W), dtype=torch.uint8, generator=gen).pin_memory()
+    dev_x, dev_y = host_x.to(dev), host_y.to(dev)
+
+    net = FCN(dev_x, KEEP_PROB, NCLS, init="device", seed=1234, world_size=world, dropout_seed=42 + rank)
+    allreduce = BucketedAllReduce.for_net(net) if world > 1 else None
+    train_step = AdamOptimizer(1e-4).minimize(net, allreduce=allreduce)
+    feed_dev = {net.image: dev_x, net.annotation: dev_y, net.keep_probability: KEEP_PROB}
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        loss = train_step(feed_dev)
+    sync()
+
+    # ---- timed region 1: device-resident inputs (value) + per-launch events (roofline) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    net.ops.profile = Profile()
+    launches0 = net.ops.ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for _ in range(steps):
+        loss = train_step(feed_dev)
+    e1.record()
+    sync()
+    ms_total = e0.elapsed_time(e1)
+    launches = net.ops.ctx.launches - launches0
+    prof = net.ops.profile.summary()
+    net.ops.profile = None
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t[0])
+    ms_step = ms_total / steps
+    value = world * B * steps / (ms_total / 1e3)
+    final_loss = float(loss)
+
+    # ---- timed region 2: end to end through the public API with HOST buffers -------------
+    feed_host = {net.image: host_x, net.annotation: host_y, net.keep_probability: KEEP_PROB}
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    for _ in range(2):
+        loss_host.copy_(train_step(feed_host).reshape(1), non_blocking=True)
+    sync()
+    e0.record()
+    for _ in range(steps):
+        l = train_step(feed_host)                       # H2D of images + labels inside
+        loss_host.copy_(l.reshape(1), non_blocking=True)     # D2H of the step's loss
+    e1.record()
+    sync()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t[0])
+    e2e_value = world * B * steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    # dominant kernel family by device time
+    fam_ms = {k: v["ms"] for k, v in prof.items()}
+    total_prof_ms = sum(fam_ms.values())
+    dom = max(fam_ms, key=fam_ms.get)
+    d = prof[dom]
+    if d["unit"] == "flop":
+        achieved = d["work"] / (d["ms"] / 1e3) / 1e12
+        peak, unit, bound = peaks["bf16_tflops_sustained"], "TFLOP/s", "tensor"
+    else:
+        achieved = d["work"] / (d["ms"] / 1e3) / 1e9
+        peak, unit, bound = peaks["hbm_gbs"], "GB/s", "hbm"
+    roofline = {"bound": bound, "kernel": dom, "achieved": achieved, "peak": peak, "unit": unit,
+                "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + (" sustained" if bound == "tensor" else ""),
+                "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
+                "share_of_step": d["ms"] / total_prof_ms if total_prof_ms else None}
+    families = {k: {"ms_per_step": v["ms"] / steps, "launches_per_step": v["launches"] / steps,
+                    ("tflops" if v["unit"] == "flop" else "gbs"):
+                        (v["work"] / (v["ms"] / 1e3) / (1e12 if v["unit"] == "flop" else 1e9)) if v["ms"] > 0 else None}
+                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+    step_tflops = TRAIN_GFLOP_PER_IMAGE * 1e9 * value / world / 1e12
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        ips, ms, cores, done = cpu_reference_images_per_s(2, 1, max_seconds=60.0)
+        cpu_baseline = {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"batch 1 of the 32-image step, fp32 oracle, {done} step(s) after 1 warm-up, {ms:.0f} ms/step"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "FCN-8s 2-class bf16 training (fwd+loss+bwd+Adam), batch 32 per GPU, 160x576x3 (BASELINE configs[1])",
+                   "global_batch": world * B, "batch_per_gpu": B, "keep_prob": KEEP_PROB,
+                   "parallelism": f"dp{world}", "init": "random N(0,0.01^2) (FCN.py:125)",
+                   "l2": "working set (1.8 GiB activations + 2.2 GiB weights/optimizer state) >> 126 MB L2; no flush needed"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": int(host_x.numel() + host_y.numel()), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "tensor_util_step": {"train_tflops_per_gpu": step_tflops, "frac_of_peak": step_tflops / peaks["bf16_tflops_sustained"],
+                             "flops_per_image": TRAIN_GFLOP_PER_IMAGE * 1e9, "convention": "valid-tap fwd+dgrad+wgrad"},
+        "kernel_families": families,
+        "cpu_baseline": cpu_baseline,
+        "final_loss": final_loss,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

@@ -138,8 +138,12 @@ def adam_tf_step(p, m, v, g, t: int, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
     bias correction): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps).
     Operates in-place on fp32 torch tensors; t starts at 1."""
     lr_t = np.float32(lr * math.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t))
-    m.mul_(b1).add_(g, alpha=1.0 - b1)
-    v.mul_(b2).addcmul_(g, g, value=1.0 - b2)
+    # TF's ApplyAdam kernel evaluates the same recurrences in this form, in the variable dtype:
+    #   m += (g - m) * (1 - b1);  v += (g*g - v) * (1 - b2);  var -= (m * lr_t) / (sqrt(v) + eps)
+    c1 = float(np.float32(1.0) - np.float32(b1))
+    c2 = float(np.float32(1.0) - np.float32(b2))
+    m.add_((g - m) * c1)
+    v.add_((g * g - v) * c2)
     p.sub_(lr_t * m / (v.sqrt() + eps))
     return float(lr_t)
 

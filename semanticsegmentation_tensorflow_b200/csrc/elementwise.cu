@@ -319,9 +319,10 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, f
     const float4 gg = __ldg(g4 + i);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+      // TF's ApplyAdam form: m += (g - m)(1 - b1); v += (g^2 - v)(1 - b2)
       const float gj = (&gg.x)[j] * gs;
-      float mj = b1 * (&mm.x)[j] + c1 * gj;
-      float vj = b2 * (&vv.x)[j] + c2 * gj * gj;
+      float mj = (&mm.x)[j] + (gj - (&mm.x)[j]) * c1;
+      float vj = (&vv.x)[j] + (gj * gj - (&vv.x)[j]) * c2;
       (&mm.x)[j] = mj;
       (&vv.x)[j] = vj;
       (&pp.x)[j] -= lr_t * mj / (sqrtf(vj) + eps);
@@ -331,8 +332,8 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, f
   if (blockIdx.x == 0) {
     for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
       const float gj = g[i] * gs;
-      const float mj = b1 * m[i] + c1 * gj;
-      const float vj = b2 * v[i] + c2 * gj * gj;
+      const float mj = m[i] + (gj - m[i]) * c1;
+      const float vj = v[i] + (gj * gj - v[i]) * c2;
       m[i] = mj; v[i] = vj;
       p[i] -= lr_t * mj / (sqrtf(vj) + eps);
     }

@@ -1,0 +1,78 @@
+"""Batch-sharded data parallelism: one process per GPU, weights replicated, gradients summed
+with a bucketed all-reduce that overlaps the rest of backward.
+
+The reference is single-process / single-GPU (`SegNet.py:92-95`); this is new functionality.
+The loss gradient is scaled 1/(world * N*H*W) in the xent kernel, so the collective is a
+plain SUM over ranks.  Buckets are contiguous slices of the flat gradient arena in backward
+completion order; a bucket's all-reduce is issued (async, on the process group's own stream)
+as soon as its last layer's weight gradient has been enqueued, and the optimizer update for
+that slice waits only on that bucket."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import plan as P
+
+
+class BucketedAllReduce:
+    def __init__(self, flat_grad: torch.Tensor, buckets: List[Tuple[int, int, str]], group=None):
+        """flat_grad: the gradient arena (any device); buckets: (start, end, last_layer) in
+        backward completion order, e.g. from plan.gradient_buckets()."""
+        self.g = flat_grad
+        self.buckets = list(buckets)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._next = 0
+        self._works = []
+
+    @classmethod
+    def for_net(cls, net, group=None, layer_groups=None):
+        return cls(net.vars.g, P.gradient_buckets(net.vars.slots, layer_groups), group)
+
+    def begin_step(self):
+        self._next = 0
+        self._works = []
+
+    def _launch(self, b):
+        lo, hi, _ = self.buckets[b]
+        if self.world > 1:
+            w = dist.all_reduce(self.g[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            w = None
+        self._works.append((lo, hi, w))
+
+    def layer_done(self, name: str):
+        """Called by FCN.backward after each layer's dW/db kernels are enqueued."""
+        while self._next < len(self.buckets) and self.buckets[self._next][2] == name:
+            self._launch(self._next)
+            self._next += 1
+
+    def finish(self):
+        """Yields (lo, hi) arena slices as their reductions complete (stream-ordered wait)."""
+        while self._next < len(self.buckets):        # layers never reported (defensive)
+            self._launch(self._next)
+            self._next += 1
+        for lo, hi, w in self._works:
+            if w is not None:
+                w.wait()
+            yield lo, hi
+
+
+def init_distributed(backend: str = "nccl"):
+    """torchrun-style rendezvous (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the env)."""
+    import os
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local

@@ -234,8 +234,12 @@ class FCN:
     def create(self):
         """Run the forward pass; returns (pred [N,H,W,1] int64, logits [N,H,W,C] f32)."""
         self.forward()
-        pred = (self.logits[..., 1] > self.logits[..., 0]).to(torch.int64).unsqueeze(3) if self.num_classes == 2 \
-            else torch.argmax(self.logits, dim=3, keepdim=True)
+        if self.num_classes == 2:
+            # tf.argmax over 2 classes, ties -> 0 (FCN.py:111): computed by the softmax/mask kernel
+            self.ops.softmax_infer(self.logits, None, self.pred_u8)
+            pred = self.pred_u8.to(torch.int64).unsqueeze(3)
+        else:
+            pred = torch.argmax(self.logits, dim=3, keepdim=True)
         return pred, self.logits
 
     def forward(self):

@@ -40,12 +40,68 @@ def _dt(x):
     raise TypeError(f"unsupported dtype {x.dtype}")
 
 
+def _valid_frac(n, k):
+    """Average fraction of a k-tap SAME window that lies inside [0, n) (1-D)."""
+    p = k // 2
+    return sum(min(o + k - 1 - p, n - 1) - max(o - p, 0) + 1 for o in range(n)) / float(n * k)
+
+
+_VF = {}
+
+
+def conv_flops(n, h, w, cin, cout, kh, kw):
+    """Algorithmic (valid-tap) FLOPs of one conv pass: multiplies against SAME padding excluded."""
+    key = (h, w, kh, kw)
+    if key not in _VF:
+        _VF[key] = _valid_frac(h, kh) * _valid_frac(w, kw)
+    return 2.0 * n * h * w * kh * kw * cin * cout * _VF[key]
+
+
+def deconv_flops(n, h, w, cin, cout, k, s):
+    vf = (s * h) / float((h - 1) * s + k) * (s * w) / float((w - 1) * s + k)
+    return 2.0 * n * h * w * k * k * cin * cout * vf
+
+
+class Profile:
+    """Per-launch CUDA-event timing of the C-ABI calls, recorded on the launching stream."""
+
+    def __init__(self):
+        self.records = []     # (family, work, unit, start_event, end_event)
+
+    def summary(self):
+        out = {}
+        for fam, work, unit, e0, e1 in self.records:
+            d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "work": 0.0, "unit": unit})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["work"] += work
+        return out
+
+
 class Ops:
     """Bound to one device context."""
 
     def __init__(self, device=None):
         self.ctx = context(device)
-        self.call = self.ctx.call
+        self._call = self.ctx.call
+        self.profile = None
+        self._work = None
+
+    def call(self, name, *args):
+        if self.profile is None:
+            return self._call(name, *args)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self._call(name, *args)
+        e1.record()
+        work, unit = self._work if self._work is not None else (0.0, "")
+        self._work = None
+        self.profile.records.append((name, work, unit, e0, e1))
+
+    def _w(self, work, unit):
+        if self.profile is not None:
+            self._work = (work, unit)
 
     # ---- weight packing -------------------------------------------------------------
     def pack_conv_weights(self, w, wk=None, wd=None):
@@ -55,6 +111,7 @@ class Ops:
             wk = torch.empty((kh * kw, cout, cin), dtype=torch.bfloat16, device=dev)
         if wd is None:
             wd = torch.empty((kh * kw, cin, cout), dtype=torch.bfloat16, device=dev)
+        self._w(8.0 * w.numel(), "byte")
         self.call("segk_pack_conv_weights", _p(w), _p(wk), _p(wd), kh, kw, cin, cout, _stream())
         return wk, wd
 
@@ -65,6 +122,7 @@ class Ops:
             wk = torch.empty((s * s, 4, cout, cin), dtype=torch.bfloat16, device=dev)
         if wd is None:
             wd = torch.empty((k * k, cin, cout), dtype=torch.bfloat16, device=dev)
+        self._w(8.0 * w.numel(), "byte")
         self.call("segk_pack_deconv_weights", _p(w), _p(wk), _p(wd), k, s, cin, cout, _stream())
         return wk, wd
 
@@ -73,6 +131,7 @@ class Ops:
         n, h, w, cin = x.shape
         cout = y.shape[3]
         flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if y.dtype == torch.float32 else 0)
+        self._w(conv_flops(n, h, w, cin, cout, kh, kw), "flop")
         self.call("segk_conv2d_fwd", _p(x), _p(wk), _p(bias), _p(residual), _p(y), n, h, w, cin, cout, kh, kw,
                   flags, _stream())
         return y
@@ -80,6 +139,7 @@ class Ops:
     def conv2d_dgrad(self, dy, wd, dx, kh, kw, relu_mask=None, residual=None, scale=1.0):
         n, h, w, cout = dy.shape
         cin = dx.shape[3]
+        self._w(conv_flops(n, h, w, cin, cout, kh, kw), "flop")
         self.call("segk_conv2d_dgrad", _p(dy), _p(wd), _p(relu_mask), _p(residual), _p(dx), float(scale), n, h, w,
                   cin, cout, kh, kw, _stream())
         return dx
@@ -87,6 +147,7 @@ class Ops:
     def conv2d_wgrad(self, x, dy, dw, kh, kw, accumulate=False):
         n, h, w, cin = x.shape
         cout = dy.shape[3]
+        self._w(conv_flops(n, h, w, cin, cout, kh, kw), "flop")
         self.call("segk_conv2d_wgrad", _p(x), _p(dy), _p(dw), n, h, w, cin, cout, kh, kw, int(accumulate), _stream())
         return dw
 
@@ -94,6 +155,7 @@ class Ops:
         n, h, w, cin = x.shape
         cout = y.shape[3]
         flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if y.dtype == torch.float32 else 0)
+        self._w(deconv_flops(n, h, w, cin, cout, k, s), "flop")
         self.call("segk_deconv2d_fwd", _p(x), _p(wk), _p(bias), _p(residual), _p(y), n, h, w, cin, cout, k, s, flags,
                   _stream())
         return y
@@ -101,12 +163,14 @@ class Ops:
     def deconv2d_dgrad(self, dy, wd, dx, k, s, relu_mask=None):
         n, h, w, cin = dx.shape
         cout = dy.shape[3]
+        self._w(deconv_flops(n, h, w, cin, cout, k, s), "flop")
         self.call("segk_deconv2d_dgrad", _p(dy), _p(wd), _p(relu_mask), _p(dx), n, h, w, cin, cout, k, s, _stream())
         return dx
 
     def deconv2d_wgrad(self, x, dy, dw, k, s, accumulate=False):
         n, h, w, cin = x.shape
         cout = dy.shape[3]
+        self._w(deconv_flops(n, h, w, cin, cout, k, s), "flop")
         self.call("segk_deconv2d_wgrad", _p(x), _p(dy), _p(dw), n, h, w, cin, cout, k, s, int(accumulate), _stream())
         return dw
 
@@ -114,6 +178,7 @@ class Ops:
     def conv2d_small_fwd(self, x, w, bias, y, relu=True):
         n, h, wd_, cin = x.shape
         kh, kw, _, cout = w.shape
+        self._w(conv_flops(n, h, wd_, cin, cout, kh, kw), "flop")
         self.call("segk_conv2d_small_fwd", _p(x), _dt(x), _p(w), _p(bias), _p(y), n, h, wd_, cin, cout, kh, kw,
                   EPI_RELU if relu else 0, _stream())
         return y
@@ -121,6 +186,7 @@ class Ops:
     def conv2d_small_dgrad(self, dy, w, dx, relu_mask=None, scale=1.0):
         n, h, wd_, cout = dy.shape
         kh, kw, cin, _ = w.shape
+        self._w(conv_flops(n, h, wd_, cin, cout, kh, kw), "flop")
         self.call("segk_conv2d_small_dgrad", _p(dy), _p(w), _p(relu_mask), _p(dx), float(scale), n, h, wd_, cin, cout,
                   kh, kw, _stream())
         return dx
@@ -128,6 +194,7 @@ class Ops:
     def conv2d_small_wgrad(self, x, dy, dw):
         n, h, wd_, cin = x.shape
         kh, kw, _, cout = dw.shape
+        self._w(conv_flops(n, h, wd_, cin, cout, kh, kw), "flop")
         self.call("segk_conv2d_small_wgrad", _p(x), _dt(x), _p(dy), _p(dw), n, h, wd_, cin, cout, kh, kw, _stream())
         return dw
 
@@ -135,6 +202,7 @@ class Ops:
         n, h, wd_, cin = x.shape
         k, _, cout, _ = w.shape
         flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if y.dtype == torch.float32 else 0)
+        self._w(deconv_flops(n, h, wd_, cin, cout, k, s), "flop")
         self.call("segk_deconv2d_small_fwd", _p(x), _p(w), _p(bias), _p(residual), _p(y), n, h, wd_, cin, cout, k, s,
                   flags, _stream())
         return y
@@ -142,6 +210,7 @@ class Ops:
     def deconv2d_small_dgrad(self, dy, w, dx, s, relu_mask=None):
         n, h, wd_, cin = dx.shape
         k, _, cout, _ = w.shape
+        self._w(deconv_flops(n, h, wd_, cin, cout, k, s), "flop")
         self.call("segk_deconv2d_small_dgrad", _p(dy), int(dy.dtype == torch.float32), _p(w), _p(relu_mask), _p(dx), n,
                   h, wd_, cin, cout, k, s, _stream())
         return dx
@@ -149,6 +218,7 @@ class Ops:
     def deconv2d_small_wgrad(self, x, dy, dw, s):
         n, h, wd_, cin = x.shape
         k, _, cout, _ = dw.shape
+        self._w(deconv_flops(n, h, wd_, cin, cout, k, s), "flop")
         self.call("segk_deconv2d_small_wgrad", _p(x), _p(dy), int(dy.dtype == torch.float32), _p(dw), n, h, wd_, cin,
                   cout, k, s, _stream())
         return dw
@@ -156,11 +226,13 @@ class Ops:
     # ---- HBM-bound kernels ----------------------------------------------------------------
     def maxpool_fwd(self, x, y, idx):
         n, h, w, c = x.shape
+        self._w(2.0 * x.numel() + 3.0 * y.numel(), "byte")
         self.call("segk_maxpool2x2_fwd", _p(x), _p(y), _p(idx), n, h, w, c, _stream())
         return y, idx
 
     def maxpool_bwd(self, dy, idx, dx, act=None):
         n, h, w, c = dx.shape
+        self._w(2.0 * dx.numel() + 3.0 * dy.numel() + (2.0 * dx.numel() if act is not None else 0.0), "byte")
         self.call("segk_maxpool2x2_bwd", _p(dy), _p(idx), _p(act), _p(dx), n, h, w, c, _stream())
         return dx
 
@@ -175,6 +247,7 @@ class Ops:
     def softmax_xent(self, logits, labels, dlogits, pred, loss_sum, cm, workspace, grad_scale):
         c = logits.shape[-1]
         npix = logits.numel() // c
+        self._w(npix * (4.0 * c + 1.0 + (4.0 * c if dlogits is not None else 0.0)), "byte")
         self.call("segk_softmax_xent_fwd_bwd", _p(logits), _p(labels), _p(dlogits), _p(pred), _p(loss_sum), _p(cm),
                   _p(workspace), npix, c, float(grad_scale), _stream())
 
@@ -187,6 +260,7 @@ class Ops:
         return cm
 
     def adam_step(self, p, m, v, g, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+        self._w(28.0 * p.numel(), "byte")
         self.call("segk_adam_step", _p(p), _p(m), _p(v), _p(g), p.numel(), float(lr_t), float(beta1), float(beta2),
                   float(eps), float(grad_scale), _stream())
 
@@ -200,5 +274,6 @@ class Ops:
 
     def bias_grad(self, dy, db):
         c = dy.shape[-1]
+        self._w(float(dy.numel() * dy.element_size()), "byte")
         self.call("segk_bias_grad", _p(dy), int(dy.dtype == torch.float32), _p(db), dy.numel() // c, c, _stream())
         return db

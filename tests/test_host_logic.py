@@ -1,0 +1,148 @@
+"""CPU tests: host-side planning logic, the C-ABI library (loads, exports every symbol the
+header declares), and the data-parallel bucket logic over gloo with world_size 2."""
+import ctypes
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from semanticsegmentation_tensorflow_b200 import plan as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_layer_table_matches_reference_graph():
+    L = P.fcn8s_layers(3, 2)
+    convs = [l for l in L if l.kind == "conv"]
+    assert len(convs) == 17 and sum(l.kind == "pool" for l in L) == 5 and sum(l.kind == "deconv" for l in L) == 3
+    assert [l.k for l in convs].count(3) == 14                       # FCN.py:52-73
+    assert convs[-3].k == 7 and convs[-3].cout == 4096 and convs[-3].dropout      # conv6, FCN.py:78-79
+    assert convs[-1].cout == 2 and convs[-1].relu                    # conv8 ReLU'd, FCN.py:86
+    t = [l for l in L if l.kind == "deconv"]
+    assert [(l.k, l.stride, l.cin, l.cout) for l in t] == [(4, 2, 2, 512), (4, 2, 512, 256), (16, 8, 256, 2)]
+    assert t[2].bias_name == "bias"                                  # FCN.py:103
+
+
+def test_variable_shapes_match_oracle():
+    from oracle.fcn_oracle import variable_shapes
+    for cin in (3, 4):
+        assert list(P.variable_shapes(cin, 2).items()) == list(variable_shapes(cin, 2).items())
+    assert sum(int(np.prod(s)) for s in P.variable_shapes().values()) == 138_873_924
+
+
+def test_reference_init_matches_oracle_stream():
+    from oracle.fcn_oracle import init_variables
+    from semanticsegmentation_tensorflow_b200.fcn import reference_init
+    for init in ("ref", "he"):
+        a = reference_init(P.variable_shapes(3, 2, 64), 1234, init)
+        b = init_variables(3, 2, 64, 1234, init)
+        assert list(a) == list(b)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+
+
+def test_arena_layout_alignment_and_buckets():
+    slots, total = P.arena_layout(P.variable_shapes())
+    off = 0
+    for s in slots.values():
+        assert s.offset % P.ALIGN == 0 and s.offset >= off
+        off = s.offset + s.size
+    assert total >= off and total % P.ALIGN == 0
+    b = P.gradient_buckets(slots)
+    # backward completion order; contiguous, disjoint, covering
+    assert [x[2] for x in b] == ["conv7", "conv6", "conv4_1", "conv1_1"]
+    assert b[0][1] == total and b[-1][0] == 0
+    for (lo, hi, _), (lo2, hi2, _) in zip(b, b[1:]):
+        assert lo == hi2 and lo2 < hi2
+    conv6 = slots["conv6/weights"]
+    assert b[1][0] == conv6.offset and b[1][1] - b[1][0] >= conv6.size
+
+
+def test_adam_lr_t_and_sharding():
+    assert P.adam_lr_t(1e-4, 1) == pytest.approx(1e-4 * math.sqrt(1 - 0.999) / (1 - 0.9))
+    assert P.shard_batch(64, 8, 3) == (24, 32)
+    with pytest.raises(ValueError):
+        P.shard_batch(10, 4, 0)
+
+
+def test_flop_model_matches_survey():
+    fwd_d, train_d = P.train_flops_per_image(160, 576, valid_taps=False)
+    assert fwd_d / 1e9 == pytest.approx(86.58, abs=0.01)
+    assert train_d / 1e9 == pytest.approx(259.42, abs=0.01)
+    fwd_v, _ = P.train_flops_per_image(160, 576, valid_taps=True)
+    assert fwd_v / 1e9 == pytest.approx(77.0, abs=0.2)
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from semanticsegmentation_tensorflow_b200 import build_library
+    from semanticsegmentation_tensorflow_b200 import _lib
+    path = build_library()
+    decls = _lib.parse_header()
+    assert len(decls) >= 30
+    cdll = ctypes.CDLL(path)
+    for name in decls:
+        assert hasattr(cdll, name), f"libsegk.so does not export {name}"
+    assert cdll.segk_abi_version() == 1
+    # no GPU here: creating a context must fail with a status, not crash, and nothing falls back
+    if not torch.cuda.is_available():
+        h = ctypes.c_void_p()
+        cdll.segk_create.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+        assert cdll.segk_create(0, ctypes.byref(h)) != 0 and not h.value
+        from semanticsegmentation_tensorflow_b200.fcn import FCN
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            FCN(torch.zeros((1, 32, 32, 3), dtype=torch.uint8), 1.0, 2)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "semanticsegmentation_tensorflow_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from semanticsegmentation_tensorflow_b200 import plan as P
+from semanticsegmentation_tensorflow_b200.dp import BucketedAllReduce
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+slots, total = P.arena_layout(P.variable_shapes(3, 2, 64))
+torch.manual_seed(0)
+full = torch.randn(world, total)                      # per-rank gradient contributions
+g = full[rank].clone()
+ar = BucketedAllReduce(g, P.gradient_buckets(slots))
+order = []
+ar.begin_step()
+layers = [l for l in P.fcn8s_layers(3, 2, 64) if l.kind != "pool"]
+for l in reversed(layers):                           # backward visits layers in reverse
+    before = len(ar._works)
+    ar.layer_done(l.name)
+    if len(ar._works) > before:
+        order.append(l.name)
+done = list(ar.finish())
+assert order == ["conv7", "conv6", "conv4_1", "conv1_1"], order
+assert sorted(done) == sorted((lo, hi) for lo, hi, _ in ar.buckets)
+assert torch.allclose(g, full.sum(0), atol=1e-5), "all-reduce result != sum over ranks"
+lo, hi = P.shard_batch(8, world, rank)
+assert hi - lo == 8 // world
+dist.barrier()
+print("rank", rank, "ok")
+'''
+
+
+def test_bucketed_allreduce_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o}"
+        assert f"rank {r} ok" in o
