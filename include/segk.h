@@ -127,6 +127,29 @@ int segk_deconv2d_small_wgrad(segk_ctx* ctx, const void* x, const void* dy, int 
                               float* dw, int N, int H, int W, int Cin, int Cout, int k, int s,
                               void* stream);
 
+/* ---- ragged-channel layers as tensor-core GEMMs via a patch tensor ---------------------- */
+/* conv1_1 (Cin 3/4, FCN.py:52): P[n,y,x,kk] bf16, kk = (ky*kw+kx)*Cin+ci zero-padded to 64, so
+ * the layer becomes a 1x1 conv over P (segk_conv2d_fwd / segk_conv2d_wgrad with Cin = 64).
+ * x_dtype 2 = u8 image, 0 = bf16. */
+int segk_im2col_k64(segk_ctx* ctx, const void* x, int x_dtype, void* P, int N, int H, int W,
+                    int Cin, int kh, int kw, void* stream);
+/* w[K][Cout] fp32 (HWIO flattened) -> wk[Cout][64] bf16, zero-padded, for the 1x1 conv above */
+int segk_pack_im2col_weights(segk_ctx* ctx, const float* w, void* wk, int K, int Cout,
+                             void* stream);
+/* conv_t3 (16x16 s8, Cout = 2, FCN.py:98-107) backward: P[n,i,j,(ky,kx,co)] bf16 =
+ * dy[n, s*i-p+ky, s*j-p+kx, co] (0 outside), so that dx = P . W^T and dW = P^T . x are 1x1
+ * GEMMs (segk_conv2d_fwd / segk_conv2d_wgrad with Cin = k*k*Cout). */
+int segk_deconv_patch_gather(segk_ctx* ctx, const void* dy, int dy_is_f32, void* P, int N, int H,
+                             int W, int Cout, int k, int s, void* stream);
+/* conv_t3 forward: yp[n,i,j,(ky,kx,co)] fp32 = x . W (a 1x1 GEMM) -> y[n,oy,ox,co] = b[co] + the
+ * 4 overlapping patch entries (+ residual).  y fp32 (logits) or bf16. */
+int segk_deconv_col2im(segk_ctx* ctx, const float* yp, const float* bias, const void* residual,
+                       void* y, int out_f32, int N, int H, int W, int Cout, int k, int s,
+                       void* stream);
+/* generic matrix pack: w fp32 [T][A][B] -> cp bf16 [T][A][B] and/or tr bf16 [T][B][A] */
+int segk_pack_matrix(segk_ctx* ctx, const float* w, void* cp, void* tr, int T, int A, int B,
+                     void* stream);
+
 /* ---- weight layout packing (fp32 master -> bf16 kernel layouts) ------------------------ */
 /* w[kh,kw,Cin,Cout] fp32 (HWIO, FCN.py:125) -> wk[tap][Cout][Cin] bf16 (fwd) and
  * wd[ntaps-1-tap][Cin][Cout] bf16 (dgrad: taps reversed = rot180).  Either may be NULL. */

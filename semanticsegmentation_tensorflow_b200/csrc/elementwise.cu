@@ -577,6 +577,16 @@ int segk_pack_conv_weights(segk_ctx* ctx, const float* w, void* wk, void* wd, in
   return SEGK_OK;
 }
 
+int segk_pack_matrix(segk_ctx* ctx, const float* w, void* cp, void* tr, int T, int A, int B, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, w && (cp || tr) && T > 0 && A > 0 && B > 0, "pack_matrix: bad args");
+  dim3 grid(ceil_div(B, 32), ceil_div(A, 32), T);
+  SEGK_REQUIRE(ctx, grid.y <= 65535 && grid.z <= 65535, "pack_matrix: dims too large");
+  pack_weights_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(w, (bf16*)cp, (bf16*)tr, A, B, 0);
+  SEGK_LAUNCHED(ctx, "pack_matrix");
+  return SEGK_OK;
+}
+
 int segk_pack_deconv_weights(segk_ctx* ctx, const float* w, void* wk, void* wd, int k, int s, int Cin,
                              int Cout, void* stream) {
   if (!ctx) return SEGK_EINVAL;

@@ -1,0 +1,189 @@
+// Layout-changing helper kernels that turn the ragged-channel layers into tensor-core GEMMs:
+//   conv1_1 (Cin = 3/4, K = 27/36)  : im2col of the u8 image into a [N,H,W,64] bf16 patch tensor
+//                                     (K zero-padded to one 64-wide k-step) -> 1x1 igemm / wgrad
+//   conv_t3 (16x16 s8, Cout = 2)    : forward  = 1x1 GEMM into patch space [N,H,W,k*k*Cout] fp32
+//                                                + col2im gather (4 overlapping patches / pixel);
+//                                     backward = gather dlogits into the same patch space (bf16)
+//                                                -> dgrad and wgrad are plain 1x1 GEMMs.
+// All HBM-bound streaming kernels: 16-byte stores, grid-stride, grid = multiple of the SM count.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int sgrid(segk_ctx* ctx, int64_t items, int per_sm = 8) {
+  int64_t b = ceil_div64(items, kThreads), cap = (int64_t)ctx->sm_count * per_sm;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+__device__ __forceinline__ float ld_f(const bf16* p) { return bf2f(*p); }
+__device__ __forceinline__ float ld_f(const uint8_t* p) { return (float)*p; }
+__device__ __forceinline__ float ld_f(const float* p) { return *p; }
+
+// P[n,y,x,kk] = kk < K ? x[n, y+ky-ph, x+kx-pw, ci] : 0,  kk = (ky*kw+kx)*Cin+ci ; thread = 8 kk
+template <typename XT>
+__global__ void __launch_bounds__(kThreads) im2col_k64_kernel(const XT* __restrict__ x, uint4* __restrict__ P,
+                                                              int N, int H, int W, int Cin, int kh, int kw) {
+  const int K = kh * kw * Cin;
+  const int ph = kh / 2, pw = kw / 2;
+  const int64_t total = (int64_t)N * H * W * 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 7);
+    const int64_t p = i >> 3;
+    const int xw = (int)(p % W);
+    const int yh = (int)((p / W) % H);
+    const int n = (int)(p / ((int64_t)W * H));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int kk = g * 8 + j;
+      float f = 0.f;
+      if (kk < K) {
+        const int ci = kk % Cin, t = kk / Cin;
+        const int yy = yh + t / kw - ph, xx = xw + t % kw - pw;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) f = ld_f(x + (((int64_t)n * H + yy) * W + xx) * Cin + ci);
+      }
+      v[j] = f;
+    }
+    P[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                      pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// wk[co][kk] (bf16, 64 wide) = kk < K ? w[kk][co] : 0
+__global__ void __launch_bounds__(kThreads) pack_im2col_weights_kernel(const float* __restrict__ w,
+                                                                       bf16* __restrict__ wk, int K, int Cout) {
+  const int total = Cout * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int kk = i & 63, co = i >> 6;
+    wk[i] = f2bf(kk < K ? w[(int64_t)kk * Cout + co] : 0.f);
+  }
+}
+
+// P[n,i,j,(ky,kx,co)] = dy[n, s*i-p+ky, s*j-p+kx, co] (0 outside) ; thread = 8 consecutive elements
+template <typename GT>
+__global__ void __launch_bounds__(kThreads) patch_gather_kernel(const GT* __restrict__ dy, uint4* __restrict__ P,
+                                                                int N, int H, int W, int Co, int k, int s) {
+  const int OH = H * s, OW = W * s, p = s / 2;
+  const int E = k * k * Co;       // multiple of 8
+  const int E8 = E >> 3;
+  const int64_t total = (int64_t)N * H * W * E8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % E8);
+    int64_t r = i / E8;
+    const int j = (int)(r % W);
+    r /= W;
+    const int ii = (int)(r % H);
+    const int n = (int)(r / H);
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int e = g * 8 + q;
+      const int co = e % Co, t = e / Co;
+      const int oy = ii * s - p + t / k, ox = j * s - p + t % k;
+      v[q] = (oy >= 0 && oy < OH && ox >= 0 && ox < OW) ? ld_f(dy + (((int64_t)n * OH + oy) * OW + ox) * Co + co) : 0.f;
+    }
+    P[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                      pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// y[n,oy,ox,co] = b[co] + sum_{ty,tx in {0,1}} Yp[n, qy-ty, qx-tx, ((ay+s*ty)*k + ax+s*tx)*Co + co]
+//   qy = (oy+p)/s, ay = (oy+p)%s  (k = 2s, SAME: SURVEY Appendix B.2)
+template <typename OT>
+__global__ void __launch_bounds__(kThreads) col2im_kernel(const float* __restrict__ yp, const float* __restrict__ bias,
+                                                          const bf16* __restrict__ res, OT* __restrict__ y, int N,
+                                                          int H, int W, int Co, int k, int s) {
+  const int OH = H * s, OW = W * s, p = s / 2;
+  const int E = k * k * Co;
+  const int64_t total = (int64_t)N * OH * OW * Co;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Co);
+    int64_t r = i / Co;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int n = (int)(r / OH);
+    const int qy = (oy + p) / s, ay = (oy + p) % s;
+    const int qx = (ox + p) / s, ax = (ox + p) % s;
+    float acc = bias ? bias[co] : 0.f;
+#pragma unroll
+    for (int ty = 0; ty < 2; ++ty) {
+      const int iy = qy - ty;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int tx = 0; tx < 2; ++tx) {
+        const int ix = qx - tx;
+        if (ix < 0 || ix >= W) continue;
+        acc += __ldg(yp + (((int64_t)n * H + iy) * W + ix) * E + ((ay + s * ty) * k + ax + s * tx) * Co + co);
+      }
+    }
+    if (res) acc += bf2f(res[i]);
+    y[i] = (OT)acc;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int segk_im2col_k64(segk_ctx* ctx, const void* x, int x_dtype, void* P, int N, int H, int W, int Cin, int kh,
+                    int kw, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && P && N > 0 && H > 0 && W > 0, "im2col_k64: bad args");
+  SEGK_REQUIRE(ctx, kh * kw * Cin <= 64 && (kh & 1) && (kw & 1), "im2col_k64: need kh*kw*Cin <= 64, odd kernel");
+  const int64_t items = (int64_t)N * H * W * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == 2)
+    im2col_k64_kernel<uint8_t><<<sgrid(ctx, items, 16), kThreads, 0, st>>>((const uint8_t*)x, (uint4*)P, N, H, W, Cin, kh, kw);
+  else if (x_dtype == 0)
+    im2col_k64_kernel<bf16><<<sgrid(ctx, items, 16), kThreads, 0, st>>>((const bf16*)x, (uint4*)P, N, H, W, Cin, kh, kw);
+  else
+    return segk_fail(ctx, SEGK_EINVAL, "im2col_k64: x_dtype must be 0 (bf16) or 2 (u8)");
+  SEGK_LAUNCHED(ctx, "im2col_k64");
+  return SEGK_OK;
+}
+
+int segk_pack_im2col_weights(segk_ctx* ctx, const float* w, void* wk, int K, int Cout, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, w && wk && K > 0 && K <= 64 && Cout > 0, "pack_im2col_weights: bad args");
+  pack_im2col_weights_kernel<<<ceil_div(Cout * 64, kThreads), kThreads, 0, (cudaStream_t)stream>>>(w, (bf16*)wk, K, Cout);
+  SEGK_LAUNCHED(ctx, "pack_im2col_weights");
+  return SEGK_OK;
+}
+
+int segk_deconv_patch_gather(segk_ctx* ctx, const void* dy, int dy_is_f32, void* P, int N, int H, int W, int Cout,
+                             int k, int s, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, dy && P && N > 0 && H > 0 && W > 0, "patch_gather: bad args");
+  SEGK_REQUIRE(ctx, k == 2 * s && s % 2 == 0 && (k * k * Cout) % 8 == 0, "patch_gather: need k == 2*stride, k*k*Cout %% 8 == 0");
+  const int64_t items = (int64_t)N * H * W * (k * k * Cout / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dy_is_f32)
+    patch_gather_kernel<float><<<sgrid(ctx, items, 16), kThreads, 0, st>>>((const float*)dy, (uint4*)P, N, H, W, Cout, k, s);
+  else
+    patch_gather_kernel<bf16><<<sgrid(ctx, items, 16), kThreads, 0, st>>>((const bf16*)dy, (uint4*)P, N, H, W, Cout, k, s);
+  SEGK_LAUNCHED(ctx, "patch_gather");
+  return SEGK_OK;
+}
+
+int segk_deconv_col2im(segk_ctx* ctx, const float* yp, const float* bias, const void* residual, void* y, int out_f32,
+                       int N, int H, int W, int Cout, int k, int s, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, yp && y && N > 0 && H > 0 && W > 0, "col2im: bad args");
+  SEGK_REQUIRE(ctx, k == 2 * s && s % 2 == 0, "col2im: need k == 2*stride, even stride");
+  const int64_t items = (int64_t)N * H * s * W * s * Cout;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_f32)
+    col2im_kernel<float><<<sgrid(ctx, items, 16), kThreads, 0, st>>>(yp, bias, (const bf16*)residual, (float*)y, N, H, W, Cout, k, s);
+  else
+    col2im_kernel<bf16><<<sgrid(ctx, items, 16), kThreads, 0, st>>>(yp, bias, (const bf16*)residual, (bf16*)y, N, H, W, Cout, k, s);
+  SEGK_LAUNCHED(ctx, "col2im");
+  return SEGK_OK;
+}
+
+}  // extern "C"

@@ -475,14 +475,14 @@ Box choose_box(int N, int H, int W, int max_rows, bool exact, int lim_h = 0, int
   int64_t best_cost = -1;
   if (lim_h <= 0) lim_h = H;
   if (lim_w <= 0) lim_w = W;
-  for (int bw = 1; bw <= lim_w && bw <= max_rows; ++bw) {
-    for (int bh = 1; bh <= lim_h && bw * bh <= max_rows; ++bh) {
+  for (int bw = 1; bw <= lim_w && bw <= max_rows && bw <= 256; ++bw) {
+    for (int bh = 1; bh <= lim_h && bw * bh <= max_rows && bh <= 256; ++bh) {
       int bn = max_rows / (bw * bh);
-      if (bn > N) bn = N;
-      if (bn > 256 || bw > 256 || bh > 256) continue;
+      // exact boxes may run past the batch (TMA zero-fills the out-of-bounds images)
+      if (!exact && bn > N) bn = N;
+      if (bn > 256) continue;
       const int rows = bw * bh * bn;
       if (exact && rows != max_rows) continue;
-      if (!exact && rows % 8 != 0) continue;
       const int tiles = ceil_div(W, bw) * ceil_div(H, bh) * ceil_div(N, bn);
       const int64_t cost = (int64_t)tiles * 1024 - bw;
       if (best_cost < 0 || cost < best_cost) {

@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from . import plan as P
-from .ops import Ops
+from .ops import Ops, conv_flops, deconv_flops
 
 
 def reference_init(shapes, seed: int = 1234, init: str = "ref"):
@@ -98,14 +98,19 @@ class Variables:
     def repack(self, ops: Ops):
         """fp32 masters -> bf16 kernel layouts for the tensor-core layers (after each update)."""
         for l in self.layers:
-            if not l.tensor_core:
-                continue
             w = self.param(f"{l.name}/weights")
-            if l.kind == "conv":
+            if l.path == "tc" and l.kind == "conv":
                 self.wk[l.name], self.wd[l.name] = ops.pack_conv_weights(w, self.wk.get(l.name), self.wd.get(l.name))
-            else:
+            elif l.path == "tc":
                 self.wk[l.name], self.wd[l.name] = ops.pack_deconv_weights(w, l.stride, self.wk.get(l.name),
                                                                            self.wd.get(l.name))
+            elif l.path == "im2col":
+                self.wk[l.name] = ops.pack_im2col_weights(w, self.wk.get(l.name))
+            elif l.path == "patch":
+                # W[k,k,Cout,Cin] as the matrix [(ky,kx,co)][ci]: wk = fwd B operand, wd = its transpose
+                e = l.k * l.k * l.cout
+                self.wk[l.name], self.wd[l.name] = ops.pack_matrix(w.view(1, e, l.cin), self.wk.get(l.name),
+                                                                   self.wd.get(l.name))
 
 
 class _Feed:
@@ -179,6 +184,21 @@ class FCN:
                     self.act[l.name] = torch.empty((N, h, w, l.cout), dtype=torch.float32, device=dev)
                 else:
                     self.act[l.name] = torch.empty((N, h, w, l.cout), dtype=bf, device=dev)
+        self.patch = {}     # layer -> bf16 patch tensor saved for backward; fp32 patch-space scratch
+        self.patch_f32 = {}
+        h, w = self.H, self.W
+        for l in self.layers:
+            if l.kind == "pool":
+                h, w = h // 2, w // 2
+            elif l.path == "im2col":
+                self.patch[l.name] = torch.empty((N, h, w, 64), dtype=bf, device=dev)
+                self.patch_f32[l.name] = torch.empty((1, 1, 64, l.cout), dtype=torch.float32, device=dev)
+            elif l.kind == "deconv":
+                if l.path == "patch":
+                    e = l.k * l.k * l.cout
+                    self.patch[l.name] = torch.empty((N, h, w, e), dtype=bf, device=dev)
+                    self.patch_f32[l.name] = torch.empty((N, h, w, e), dtype=torch.float32, device=dev)
+                h, w = h * l.stride, w * l.stride
         self.logits = self.act["conv_t3"]
         npix = N * self.H * self.W
         self.dlogits = torch.empty_like(self.logits)
@@ -251,8 +271,12 @@ class FCN:
                 ops.maxpool_fwd(cur, out, self.idx[l.name])
             elif l.kind == "conv":
                 b = V.param(f"{l.name}/{l.bias_name}")
-                if l.tensor_core:
+                if l.path == "tc":
                     ops.conv2d_fwd(cur, V.wk[l.name], b, out, l.k, l.k, relu=l.relu)
+                elif l.path == "im2col":
+                    P1 = ops.im2col_k64(cur, self.patch[l.name], l.k, l.k)
+                    ops.conv2d_fwd(P1, V.wk[l.name], b, out, 1, 1, relu=l.relu,
+                                   flops=conv_flops(self.N, out.shape[1], out.shape[2], l.cin, l.cout, l.k, l.k))
                 else:
                     ops.conv2d_small_fwd(cur, V.param(f"{l.name}/weights"), b, out, relu=l.relu)
                 if l.dropout:
@@ -260,8 +284,12 @@ class FCN:
             else:
                 b = V.param(f"{l.name}/{l.bias_name}")
                 res = {"conv_t1": act["pool4"], "conv_t2": act["pool3"]}.get(l.name)   # fuse, FCN.py:92,96
-                if l.tensor_core:
+                if l.path == "tc":
                     ops.deconv2d_fwd(cur, V.wk[l.name], b, out, l.k, l.stride, residual=res)
+                elif l.path == "patch":
+                    yp = ops.conv2d_fwd(cur, V.wk[l.name], None, self.patch_f32[l.name], 1, 1, relu=False,
+                                        flops=deconv_flops(self.N, cur.shape[1], cur.shape[2], l.cin, l.cout, l.k, l.stride))
+                    ops.deconv_col2im(yp, b, out, l.k, l.stride, residual=res)
                 else:
                     ops.deconv2d_small_fwd(cur, V.param(f"{l.name}/weights"), b, out, l.stride, residual=res)
             cur = out
@@ -314,8 +342,12 @@ class FCN:
             ops.bias_grad(dcur, gb)
             prev = L[i - 1] if i > 0 else None
             if l.kind == "deconv":
-                if l.tensor_core:
+                if l.path == "tc":
                     ops.deconv2d_wgrad(xin, dcur, gw, l.k, l.stride)
+                elif l.path == "patch":
+                    Pg = ops.deconv_patch_gather(dcur, self.patch[l.name], l.k, l.stride)
+                    dfl = deconv_flops(self.N, xin.shape[1], xin.shape[2], l.cin, l.cout, l.k, l.stride)
+                    ops.conv2d_wgrad(Pg, xin, gw.view(1, 1, l.k * l.k * l.cout, l.cin), 1, 1, flops=dfl)
                 else:
                     ops.deconv2d_small_wgrad(xin, dcur, gw, l.stride)
                 # gradient wrt the deconv input
@@ -327,14 +359,22 @@ class FCN:
                     dx = self._g(flip, xin)
                     flip ^= 1
                 mask = xin if (prev is not None and prev.kind == "conv" and prev.relu) else None
-                if l.tensor_core:
+                if l.path == "tc":
                     ops.deconv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.stride, relu_mask=mask)
+                elif l.path == "patch":
+                    ops.conv2d_dgrad(Pg, V.wd[l.name], dx, 1, 1, relu_mask=mask, flops=dfl)
                 else:
                     ops.deconv2d_small_dgrad(dcur, V.param(f"{l.name}/weights"), dx, l.stride, relu_mask=mask)
                 dcur = dx
             else:
-                if l.tensor_core:
+                if l.path == "tc":
                     ops.conv2d_wgrad(xin, dcur, gw, l.k, l.k)
+                elif l.path == "im2col":
+                    if i != 0:
+                        raise NotImplementedError("im2col route is for the first layer only (no input gradient)")
+                    tmp = ops.conv2d_wgrad(self.patch[l.name], dcur, self.patch_f32[l.name], 1, 1,
+                                           flops=conv_flops(self.N, dcur.shape[1], dcur.shape[2], l.cin, l.cout, l.k, l.k))
+                    gw.view(-1).copy_(tmp.view(-1)[:gw.numel()])      # rows >= K are the zero padding
                 else:
                     ops.conv2d_small_wgrad(xin, dcur, gw)
                 if i > 0:
@@ -345,7 +385,7 @@ class FCN:
                     res = {"pool4": self.dfuse_1, "pool3": self.dfuse_2}.get(prev.name)
                     dx = self._g(flip, xin)
                     flip ^= 1
-                    if l.tensor_core:
+                    if l.path == "tc":
                         ops.conv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.k, relu_mask=mask, residual=res, scale=scale)
                     else:
                         assert res is None

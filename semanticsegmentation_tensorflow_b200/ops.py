@@ -126,28 +126,69 @@ class Ops:
         self.call("segk_pack_deconv_weights", _p(w), _p(wk), _p(wd), k, s, cin, cout, _stream())
         return wk, wd
 
+    def pack_matrix(self, w3, cp=None, tr=None):
+        """w3 fp32 [T][A][B] -> cp bf16 [T][A][B], tr bf16 [T][B][A]."""
+        t, a, b = w3.shape
+        if cp is None:
+            cp = torch.empty((t, a, b), dtype=torch.bfloat16, device=w3.device)
+        if tr is None:
+            tr = torch.empty((t, b, a), dtype=torch.bfloat16, device=w3.device)
+        self._w(8.0 * w3.numel(), "byte")
+        self.call("segk_pack_matrix", _p(w3), _p(cp), _p(tr), t, a, b, _stream())
+        return cp, tr
+
+    def pack_im2col_weights(self, w, wk=None):
+        kh, kw, cin, cout = w.shape
+        if wk is None:
+            wk = torch.empty((1, cout, 64), dtype=torch.bfloat16, device=w.device)
+        self.call("segk_pack_im2col_weights", _p(w), _p(wk), kh * kw * cin, cout, _stream())
+        return wk
+
+    # ---- patch-space helpers (conv1_1 / conv_t3 as tensor-core GEMMs) --------------------------
+    def im2col_k64(self, x, P, kh, kw):
+        n, h, w, cin = x.shape
+        self._w(float(x.numel() * x.element_size() + 2 * P.numel()), "byte")
+        self.call("segk_im2col_k64", _p(x), _dt(x), _p(P), n, h, w, cin, kh, kw, _stream())
+        return P
+
+    def deconv_patch_gather(self, dy, P, k, s):
+        n, h, w, _ = P.shape
+        cout = dy.shape[3]
+        self._w(float(dy.numel() * dy.element_size() + 2 * P.numel()), "byte")
+        self.call("segk_deconv_patch_gather", _p(dy), int(dy.dtype == torch.float32), _p(P), n, h, w, cout, k, s,
+                  _stream())
+        return P
+
+    def deconv_col2im(self, yp, bias, y, k, s, residual=None):
+        n, h, w, _ = yp.shape
+        cout = y.shape[3]
+        self._w(float(4 * yp.numel() + y.numel() * y.element_size()), "byte")
+        self.call("segk_deconv_col2im", _p(yp), _p(bias), _p(residual), _p(y), int(y.dtype == torch.float32), n, h, w,
+                  cout, k, s, _stream())
+        return y
+
     # ---- tensor-core conv family ------------------------------------------------------
-    def conv2d_fwd(self, x, wk, bias, y, kh, kw, relu=True, residual=None):
+    def conv2d_fwd(self, x, wk, bias, y, kh, kw, relu=True, residual=None, flops=None):
         n, h, w, cin = x.shape
         cout = y.shape[3]
         flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if y.dtype == torch.float32 else 0)
-        self._w(conv_flops(n, h, w, cin, cout, kh, kw), "flop")
+        self._w(conv_flops(n, h, w, cin, cout, kh, kw) if flops is None else flops, "flop")
         self.call("segk_conv2d_fwd", _p(x), _p(wk), _p(bias), _p(residual), _p(y), n, h, w, cin, cout, kh, kw,
                   flags, _stream())
         return y
 
-    def conv2d_dgrad(self, dy, wd, dx, kh, kw, relu_mask=None, residual=None, scale=1.0):
+    def conv2d_dgrad(self, dy, wd, dx, kh, kw, relu_mask=None, residual=None, scale=1.0, flops=None):
         n, h, w, cout = dy.shape
         cin = dx.shape[3]
-        self._w(conv_flops(n, h, w, cin, cout, kh, kw), "flop")
+        self._w(conv_flops(n, h, w, cin, cout, kh, kw) if flops is None else flops, "flop")
         self.call("segk_conv2d_dgrad", _p(dy), _p(wd), _p(relu_mask), _p(residual), _p(dx), float(scale), n, h, w,
                   cin, cout, kh, kw, _stream())
         return dx
 
-    def conv2d_wgrad(self, x, dy, dw, kh, kw, accumulate=False):
+    def conv2d_wgrad(self, x, dy, dw, kh, kw, accumulate=False, flops=None):
         n, h, w, cin = x.shape
         cout = dy.shape[3]
-        self._w(conv_flops(n, h, w, cin, cout, kh, kw), "flop")
+        self._w(conv_flops(n, h, w, cin, cout, kh, kw) if flops is None else flops, "flop")
         self.call("segk_conv2d_wgrad", _p(x), _p(dy), _p(dw), n, h, w, cin, cout, kh, kw, int(accumulate), _stream())
         return dw
 

@@ -31,13 +31,27 @@ class Layer:
 
     @property
     def tensor_core(self) -> bool:
-        """Layers whose channel counts feed a tcgen05 tile (both multiples of 64)."""
+        """Layers whose channel counts feed a tcgen05 tile directly (both multiples of 64)."""
+        return self.path == "tc"
+
+    @property
+    def path(self) -> str:
+        """Kernel route: 'tc' implicit GEMM; 'im2col' = first layer with kh*kw*Cin <= 64 turned into
+        a 1x1 GEMM over a 64-wide patch tensor; 'patch' = transposed conv with tiny Cout run as
+        GEMMs in patch space [N,H,W,k*k*Cout]; 'small' = CUDA-core kernels."""
         if self.kind == "pool":
-            return False
-        ok = self.cin % 64 == 0 and self.cout % 64 == 0
-        if self.kind == "deconv":
-            ok = ok and self.k == 4 and self.stride == 2
-        return ok
+            return "none"
+        if self.kind == "conv":
+            if self.cin % 64 == 0 and self.cout % 64 == 0:
+                return "tc"
+            if self.k * self.k * self.cin <= 64 and self.cout % 64 == 0:
+                return "im2col"
+            return "small"
+        if self.cin % 64 == 0 and self.cout % 64 == 0 and self.k == 4 and self.stride == 2:
+            return "tc"
+        if self.cin % 64 == 0 and (self.k * self.k * self.cout) % 64 == 0 and self.k == 2 * self.stride:
+            return "patch"
+        return "small"
 
 
 def fcn8s_layers(cin: int = 3, ncls: int = 2, fc: int = 4096) -> List[Layer]:

@@ -108,6 +108,7 @@ def test_adam_tf_formula_three_steps(ops, cuda_device):
     rng = np.random.default_rng(4)
     n = 100003                                                          # odd tail
     p0 = rng.standard_normal(n).astype(np.float32)
+    p0[::2] = 0.0                                                       # makes the update itself visible
     scales = 10.0 ** rng.uniform(-13, 0, n)                             # deep layers: |g| << eps
     p, m, v = torch.tensor(p0), torch.zeros(n), torch.zeros(n)
     pd = torch.zeros(n + 1, dtype=torch.float32, device=cuda_device)[:n]
@@ -124,9 +125,9 @@ def test_adam_tf_formula_three_steps(ops, cuda_device):
     # m can cancel (alternating gradient signs): tolerance relative to the gradient scale seen
     assert np.all(np.abs(host(md) - m.numpy()) <= 1e-6 * gmax + 1e-45)
     np.testing.assert_allclose(host(vd), v.numpy(), rtol=1e-5, atol=0)
-    upd, upd_ref = host(pd) - p0, p.numpy() - p0
     np.testing.assert_allclose(host(pd), p.numpy(), rtol=2e-7, atol=1e-9)
-    assert np.abs(upd - upd_ref).max() <= 1e-5 * np.abs(upd_ref).max()
+    # where p started at 0 the parameter IS the accumulated update: |g| << eps elements included
+    np.testing.assert_allclose(host(pd)[::2], p.numpy()[::2], rtol=2e-5, atol=1e-12)
 
 
 def test_momentum_step(ops, cuda_device):

@@ -103,3 +103,70 @@ def test_deconv_small_fwd_dgrad_wgrad(ops, cuda_device, case):
     ops.deconv2d_small_wgrad(xd, dyd, dw, s)
     torch.cuda.synchronize()
     assert_close(host(dw), wtt.grad.numpy(), 1e-4, f"deconv small wgrad {case}")
+
+
+@pytest.mark.parametrize("cin", [3, 4])
+def test_conv1_1_as_im2col_gemm(ops, cuda_device, cin):
+    """conv1_1 routed through the 64-wide patch tensor + 1x1 tensor-core GEMM (fwd and wgrad)."""
+    n, h, w, co = 2, 16, 24, 64
+    rng = np.random.default_rng(10)
+    img = rng.integers(0, 256, (n, h, w, cin), dtype=np.uint8)
+    wt = bf16_grid(rng.standard_normal((3, 3, cin, co)) * 0.01)
+    b = (rng.standard_normal(co) * 0.1).astype(np.float32)
+    wtt = torch.tensor(wt, requires_grad=True)
+    z = T.bias_add(T.conv2d_same(torch.tensor(img.astype(np.float32)), wtt), torch.tensor(b))
+    P = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=cuda_device)
+    ops.im2col_k64(torch.as_tensor(img).to(cuda_device), P, 3, 3)
+    wk = ops.pack_im2col_weights(dev_f32(wt, cuda_device))
+    y = torch.empty((n, h, w, co), dtype=torch.bfloat16, device=cuda_device)
+    ops.conv2d_fwd(P, wk, dev_f32(b, cuda_device), y, 1, 1, relu=True)
+    torch.cuda.synchronize()
+    # patch tensor is exact: compare with a host im2col
+    Pn = host(P)
+    assert np.all(Pn[..., 9 * cin:] == 0)
+    pad = np.pad(img.astype(np.float32), ((0, 0), (1, 1), (1, 1), (0, 0)))
+    for t in range(9):
+        ky, kx = divmod(t, 3)
+        assert np.array_equal(Pn[..., t * cin:(t + 1) * cin], pad[:, ky:ky + h, kx:kx + w, :])
+    assert_close(host(y), T.relu(z).detach().numpy(), 1e-2, "conv1_1 im2col fwd")
+    dy = bf16_grid(rng.standard_normal((n, h, w, co)))
+    z.backward(torch.tensor(dy))
+    dw = torch.empty((1, 1, 64, co), dtype=torch.float32, device=cuda_device)
+    ops.conv2d_wgrad(P, dev_bf16(dy, cuda_device), dw, 1, 1)
+    torch.cuda.synchronize()
+    got = host(dw).reshape(64, co)
+    assert np.all(got[9 * cin:] == 0)
+    assert_close(got[:9 * cin].reshape(3, 3, cin, co), wtt.grad.numpy(), 2e-3, "conv1_1 im2col wgrad")
+
+
+def test_conv_t3_in_patch_space(ops, cuda_device):
+    """conv_t3 (16x16 s8, Cout=2): fwd = 1x1 GEMM + col2im, bwd = patch gather + 1x1 GEMMs."""
+    n, h, w, ci, co, k, s = 2, 5, 9, 256, 2, 16, 8
+    rng = np.random.default_rng(11)
+    x = bf16_grid(rng.standard_normal((n, h, w, ci)))
+    wt = bf16_grid(rng.standard_normal((k, k, co, ci)) / np.sqrt(4 * ci))
+    b = (rng.standard_normal(co) * 0.1).astype(np.float32)
+    xt = torch.tensor(x, requires_grad=True)
+    wtt = torch.tensor(wt, requires_grad=True)
+    y_ref = T.bias_add(T.conv2d_transpose_same(xt, wtt, (h * s, w * s), s), torch.tensor(b))
+    e = k * k * co
+    wk, wd = ops.pack_matrix(dev_f32(wt, cuda_device).view(1, e, ci))
+    xd = dev_bf16(x, cuda_device)
+    yp = torch.empty((n, h, w, e), dtype=torch.float32, device=cuda_device)
+    ops.conv2d_fwd(xd, wk, None, yp, 1, 1, relu=False)
+    y = torch.empty((n, h * s, w * s, co), dtype=torch.float32, device=cuda_device)
+    ops.deconv_col2im(yp, dev_f32(b, cuda_device), y, k, s)
+    torch.cuda.synchronize()
+    assert_close(host(y), y_ref.detach().numpy(), 1e-4, "conv_t3 patch fwd")
+    dy = rng.standard_normal((n, h * s, w * s, co)).astype(np.float32)
+    y_ref.backward(torch.tensor(dy))
+    P = torch.empty((n, h, w, e), dtype=torch.bfloat16, device=cuda_device)
+    ops.deconv_patch_gather(dev_f32(dy, cuda_device), P, k, s)
+    dw = torch.empty((1, 1, e, ci), dtype=torch.float32, device=cuda_device)
+    ops.conv2d_wgrad(P, xd, dw, 1, 1)
+    dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=cuda_device)
+    ops.conv2d_dgrad(P, wd, dx, 1, 1)
+    torch.cuda.synchronize()
+    # dy is rounded to bf16 inside the patch tensor: 2^-9 relative per element
+    assert_close(host(dw).reshape(k, k, co, ci), wtt.grad.numpy(), 5e-3, "conv_t3 patch wgrad")
+    assert_close(host(dx), xt.grad.numpy(), 1e-2, "conv_t3 patch dgrad")
