@@ -189,6 +189,7 @@ def run_gpu(args):
     ms_total = e0.elapsed_time(e1)
     launches = net.ops.ctx.launches - launches0
     prof = net.ops.profile.summary()
+    prof_detail = net.ops.profile.summary(detail=True)
     net.ops.profile = None
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
@@ -220,6 +221,15 @@ def run_gpu(args):
 
     if rank != 0:
         return
+    if args.layers_out:
+        rows = []
+        for k, v in sorted(prof_detail.items(), key=lambda kv: -kv[1]["ms"]):
+            rate = v["work"] / (v["ms"] / 1e3) / (1e12 if v["unit"] == "flop" else 1e9) if v["ms"] > 0 else 0.0
+            rows.append({"call": k, "ms_per_step": v["ms"] / steps, "launches_per_step": v["launches"] / steps,
+                         "rate": rate, "rate_unit": "TFLOP/s" if v["unit"] == "flop" else "GB/s"})
+        os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
+        with open(args.layers_out, "w") as f:
+            json.dump(rows, f, indent=1)
     peaks = measured_peaks()
     # dominant kernel family by device time
     fam_ms = {k: v["ms"] for k, v in prof.items()}
@@ -278,6 +288,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers-out", default=None, help="write the per-call (per-layer) timing table here")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -93,6 +93,19 @@ def synthetic_batch(n, h, w, cin=3, seed=0, road_shaped=False):
     return x, lab
 
 
+class _RoundBoth(torch.autograd.Function):
+    """bf16 storage point: value rounded in forward, gradient rounded in backward (the CUDA path
+    stores both activations and activation gradients as bf16)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return T.to_bf16_grid(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return T.to_bf16_grid(g)
+
+
 class FCN8sOracle:
     """Forward/backward/Adam of the FCN.py graph on CPU.
 
@@ -100,11 +113,12 @@ class FCN8sOracle:
     arithmetic in between), mirroring where the CUDA path stores bf16; logits stay fp32.
     """
 
-    def __init__(self, variables, ncls=2, bf16_storage=False, threads=None):
+    def __init__(self, variables, ncls=2, bf16_storage=False, threads=None, bf16_grads=False):
         if threads:
             torch.set_num_threads(threads)
         self.ncls = ncls
         self.bf16 = bf16_storage
+        self.bf16_grads = bf16_grads      # also round activation gradients at the storage points
         self.vars = OrderedDict((k, torch.tensor(v, dtype=torch.float32, requires_grad=True))
                                 for k, v in variables.items())
         self.m = OrderedDict((k, torch.zeros_like(v)) for k, v in self.vars.items())
@@ -112,14 +126,16 @@ class FCN8sOracle:
         self.t = 0
         self.acts = OrderedDict()
 
-    def _q(self, x):
+    def _q(self, x, weight=False):
         if not self.bf16:
             return x
+        if self.bf16_grads and not weight:
+            return _RoundBoth.apply(x)
         # straight-through rounding so autograd matches "store bf16, compute fp32"
         return x + (T.to_bf16_grid(x.detach()) - x.detach())
 
     def _w(self, name):
-        return self._q(self.vars[name])
+        return self._q(self.vars[name], weight=True)
 
     def _conv(self, x, name, keep=True):
         # conv_layer, FCN.py:117-136

@@ -38,6 +38,7 @@ int segk_create(int device, segk_ctx** out) {
 }
 
 int segk_destroy(segk_ctx* ctx) {
+  if (ctx && ctx->ws) cudaFree(ctx->ws);
   delete ctx;
   return SEGK_OK;
 }

@@ -378,6 +378,60 @@ __global__ void __launch_bounds__(kThreads) bias_grad_kernel(const T* __restrict
   atomicAdd(db + c, acc);
 }
 
+// Vectorised BiasAddGrad for bf16 [rows][C], C % 8 == 0: thread = 8 channels of one row per
+// iteration (16-byte loads), block-level reduce over the row lanes, one atomicAdd per channel/block.
+__global__ void __launch_bounds__(kThreads) bias_grad_bf16x8_kernel(const uint4* __restrict__ dy,
+                                                                     float* __restrict__ db, int64_t rows,
+                                                                     int C8) {
+  __shared__ float sh[kThreads][9];
+  const int cpb = C8 < kThreads ? C8 : kThreads;       // column groups handled by this block
+  const int R = kThreads / cpb;                         // row lanes
+  const int cg = blockIdx.y * cpb + (threadIdx.x % cpb);
+  const int rl = threadIdx.x / cpb;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (cg < C8 && rl < R) {
+    for (int64_t r = (int64_t)blockIdx.x * R + rl; r < rows; r += (int64_t)gridDim.x * R) {
+      const uint4 u = __ldg(dy + r * C8 + cg);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&u.x)[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (rl == 0 && cg < C8) {
+    for (int k = 1; k < R; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += sh[threadIdx.x + k * cpb][j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(db + cg * 8 + j, acc[j]);
+  }
+}
+
+// BiasAddGrad for fp32 [rows][C] with C in {1,2,4} (the logits gradient): float4 loads.
+__global__ void __launch_bounds__(kThreads) bias_grad_f32_small_kernel(const float4* __restrict__ dy,
+                                                                        float* __restrict__ db, int64_t n4, int C) {
+  __shared__ float sh[32];
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(dy + i);
+    a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+  }
+  // element j of every float4 belongs to channel j % C
+  if (C == 1) { a[0] += a[1] + a[2] + a[3]; }
+  else if (C == 2) { a[0] += a[2]; a[1] += a[3]; }
+  for (int c = 0; c < C; ++c) {
+    const float t = block_sum(a[c], sh);
+    if (threadIdx.x == 0) atomicAdd(db + c, t);
+  }
+}
+
 // w fp32 [T][A][B] -> cp bf16 [T'][A][B] (cast) and/or tr bf16 [T][B][A] (per-tap transpose);
 // T' = T-1-t when rev_cp (rot180 of the filter for dgrad).
 __global__ void __launch_bounds__(kThreads) pack_weights_kernel(const float* __restrict__ w,
@@ -549,6 +603,27 @@ int segk_bias_grad(segk_ctx* ctx, const void* dy, int dy_is_f32, float* db, int6
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * C, st);
   if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "bias_grad memset: %s", cudaGetErrorString(e));
+  if (!dy_is_f32 && C % 8 == 0 && (((uintptr_t)dy) & 15) == 0) {
+    const int C8 = C / 8;
+    const int cpb = C8 < kThreads ? C8 : kThreads;
+    if (kThreads % cpb == 0 && C8 % cpb == 0) {
+      const int R = kThreads / cpb;
+      const int gy = C8 / cpb;
+      int64_t gx = ceil_div64(rows, (int64_t)R * 4);
+      const int64_t cap = (int64_t)ctx->sm_count * 8 / gy;
+      if (gx > cap) gx = cap;
+      if (gx < 1) gx = 1;
+      bias_grad_bf16x8_kernel<<<dim3((unsigned)gx, gy), kThreads, 0, st>>>((const uint4*)dy, db, rows, C8);
+      SEGK_LAUNCHED(ctx, "bias_grad_bf16x8");
+      return SEGK_OK;
+    }
+  }
+  if (dy_is_f32 && (C == 1 || C == 2 || C == 4) && (rows * C) % 4 == 0 && (((uintptr_t)dy) & 15) == 0) {
+    const int64_t n4 = rows * C / 4;
+    bias_grad_f32_small_kernel<<<stream_grid(ctx, n4, 4), kThreads, 0, st>>>((const float4*)dy, db, n4, C);
+    SEGK_LAUNCHED(ctx, "bias_grad_f32_small");
+    return SEGK_OK;
+  }
   const int tx = C < kThreads ? ((C + 31) / 32) * 32 : kThreads;
   const int gy = ceil_div(C, tx);
   int64_t want = (int64_t)ctx->sm_count * 8 / gy;

@@ -21,34 +21,43 @@ __device__ __forceinline__ float ld_f(const bf16* p) { return bf2f(*p); }
 __device__ __forceinline__ float ld_f(const uint8_t* p) { return (float)*p; }
 __device__ __forceinline__ float ld_f(const float* p) { return *p; }
 
-// P[n,y,x,kk] = kk < K ? x[n, y+ky-ph, x+kx-pw, ci] : 0,  kk = (ky*kw+kx)*Cin+ci ; thread = 8 kk
+// P[n,y,x,kk] = kk < K ? x[n, y+ky-ph, x+kx-pw, ci] : 0,  kk = (ky*kw+kx)*Cin+ci ; thread = 8 kk of one
+// pixel (8 lanes write one 128-byte patch row).  The (ky,kx,ci) decode of a thread's 8 kk is hoisted
+// out of the grid-stride loop (the stride is a multiple of 8, so a thread keeps its kk group).
 template <typename XT>
 __global__ void __launch_bounds__(kThreads) im2col_k64_kernel(const XT* __restrict__ x, uint4* __restrict__ P,
                                                               int N, int H, int W, int Cin, int kh, int kw) {
   const int K = kh * kw * Cin;
   const int ph = kh / 2, pw = kw / 2;
-  const int64_t total = (int64_t)N * H * W * 8;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i & 7);
-    const int64_t p = i >> 3;
+  const int g = threadIdx.x & 7;
+  int ody[8], odx[8], oci[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int kk = g * 8 + j;
+    if (kk < K) {
+      const int t = kk / Cin;
+      oci[j] = kk % Cin;
+      ody[j] = t / kw - ph;
+      odx[j] = t % kw - pw;
+    } else {
+      oci[j] = -1; ody[j] = 0; odx[j] = 0;
+    }
+  }
+  const int64_t npix = (int64_t)N * H * W;
+  for (int64_t p = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 3; p < npix;
+       p += ((int64_t)gridDim.x * blockDim.x) >> 3) {
     const int xw = (int)(p % W);
     const int yh = (int)((p / W) % H);
-    const int n = (int)(p / ((int64_t)W * H));
+    const XT* base = x + p * Cin;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int kk = g * 8 + j;
-      float f = 0.f;
-      if (kk < K) {
-        const int ci = kk % Cin, t = kk / Cin;
-        const int yy = yh + t / kw - ph, xx = xw + t % kw - pw;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) f = ld_f(x + (((int64_t)n * H + yy) * W + xx) * Cin + ci);
-      }
-      v[j] = f;
+      const int yy = yh + ody[j], xx = xw + odx[j];
+      v[j] = (oci[j] >= 0 && yy >= 0 && yy < H && xx >= 0 && xx < W)
+                 ? ld_f(base + ((int64_t)ody[j] * W + odx[j]) * Cin + oci[j]) : 0.f;
     }
-    P[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                      pack_bf16x2(v[6], v[7]));
+    P[p * 8 + g] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                              pack_bf16x2(v[6], v[7]));
   }
 }
 

@@ -301,6 +301,44 @@ __global__ void __launch_bounds__(kThreads) deconv_dgrad_kernel(
   }
 }
 
+// Same gradient for tiny Cin (conv_t1: Cin = 2, Cout = 512): one WARP per (pixel, ci); lanes stride
+// over co so the dy reads are coalesced, then a shuffle reduction.
+template <typename GT>
+__global__ void __launch_bounds__(kThreads) deconv_dgrad_warp_kernel(
+    const GT* __restrict__ dy, const float* __restrict__ w, const bf16* __restrict__ mask,
+    bf16* __restrict__ dx, int N, int H, int W, int Cin, int Cout, int k, int s) {
+  const int OH = H * s, OW = W * s, p = s / 2;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = (int64_t)N * H * W * Cin;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; i < total; i += nwarps) {
+    const int ci = (int)(i % Cin);
+    int64_t r = i / Cin;
+    const int ix = (int)(r % W);
+    r /= W;
+    const int iy = (int)(r % H);
+    const int n = (int)(r / H);
+    float acc = 0.f;
+    for (int ky = 0; ky < k; ++ky) {
+      const int oy = iy * s - p + ky;
+      if (oy < 0 || oy >= OH) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ox = ix * s - p + kx;
+        if (ox < 0 || ox >= OW) continue;
+        const GT* gp = dy + (((int64_t)n * OH + oy) * OW + ox) * Cout;
+        const float* wp = w + ((int64_t)(ky * k + kx) * Cout) * Cin + ci;
+        for (int co = lane; co < Cout; co += 32) acc += (float)gp[co] * __ldg(wp + (int64_t)co * Cin);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      if (mask && !(bf2f(mask[i]) > 0.f)) acc = 0.f;
+      dx[i] = f2bf(acc);
+    }
+  }
+}
+
 // dW[ky,kx,co,ci] += sum_{n,i,j} x[n,i,j,ci] * dy[n, i*s-p+ky, j*s-p+kx, co]
 // thread = one weight element (ci fastest); blockIdx.y = slice of the (n,i) rows.
 template <typename GT>
@@ -474,6 +512,16 @@ int segk_deconv2d_small_dgrad(segk_ctx* ctx, const void* dy, int dy_is_f32, cons
   SEGK_REQUIRE(ctx, k == 2 * s && (s % 2 == 0), "deconv: need k == 2*stride, even stride (k=%d s=%d)", k, s);
   const int64_t total = (int64_t)N * H * W * Cin;
   cudaStream_t st = (cudaStream_t)stream;
+  if (Cin <= 8 && Cout >= 64) {
+    if (dy_is_f32)
+      deconv_dgrad_warp_kernel<float><<<sgrid(ctx, total * 32, 16), kThreads, 0, st>>>(
+          (const float*)dy, w, (const bf16*)relu_mask, (bf16*)dx, N, H, W, Cin, Cout, k, s);
+    else
+      deconv_dgrad_warp_kernel<bf16><<<sgrid(ctx, total * 32, 16), kThreads, 0, st>>>(
+          (const bf16*)dy, w, (const bf16*)relu_mask, (bf16*)dx, N, H, W, Cin, Cout, k, s);
+    SEGK_LAUNCHED(ctx, "deconv_small_dgrad_warp");
+    return SEGK_OK;
+  }
   if (dy_is_f32)
     deconv_dgrad_kernel<float><<<sgrid(ctx, total, 16), kThreads, 0, st>>>(
         (const float*)dy, w, (const bf16*)relu_mask, (bf16*)dx, N, H, W, Cin, Cout, k, s);

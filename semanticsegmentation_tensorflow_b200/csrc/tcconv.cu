@@ -67,6 +67,10 @@ struct IgemmParams {
   const bf16* mask;
   float scale;
   int relu;
+  // split-K over the (tap, k-chunk) walk: unit = tile * ksplits + split; partial sums are
+  // atomically added into the fp32 workspace `ws` [pixels][ldo] and finished by epilogue_finish_kernel
+  int ksplits;
+  float* ws;
 };
 
 struct PipeState {
@@ -82,11 +86,13 @@ struct PipeState {
 };
 
 struct TileCoord {
-  int nt, x0, y0, n0, phase;
+  int nt, x0, y0, n0, phase, split;
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
   TileCoord t;
+  t.split = tile % p.ksplits;
+  tile /= p.ksplits;
   t.nt = tile % p.n_tiles;
   int r = tile / p.n_tiles;
   t.x0 = (r % p.tiles_w) * p.bw;
@@ -125,7 +131,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+  const int total_tiles = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.ksplits;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.a[i]);
@@ -153,10 +159,15 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
         const uint64_t tm = tap_mask(p, taps, t);
+        const int nall = __popcll(tm) * p.kchunks;
+        const int per = (nall + p.ksplits - 1) / p.ksplits;
+        const int lo = t.split * per, hi = min(lo + per, nall);
+        int step = 0;
         for (int i = 0; i < p.ntaps; ++i) {
           if (!((tm >> i) & 1)) continue;
           const int dy = taps.dy[i], dx = taps.dx[i], mi = taps.map[i];
-          for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int kc = 0; kc < p.kchunks; ++kc, ++step) {
+            if (step < lo || step >= hi) continue;
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
             uint8_t* sa = smem + ps.stage * C::kStageBytes;
             mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
@@ -177,7 +188,9 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
         const uint64_t tm = tap_mask(p, taps, t);
-        const int nsteps = __popcll(tm) * p.kchunks;
+        const int nall = __popcll(tm) * p.kchunks;
+        const int per = (nall + p.ksplits - 1) / p.ksplits;
+        const int nsteps = min(t.split * per + per, nall) - t.split * per;   // host guarantees > 0
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -226,7 +239,11 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
-        if (valid) {
+        if (valid && p.ksplits > 1) {
+          float* w = p.ws + obase + c0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(w + i, __uint_as_float(r[i]));
+        } else if (valid) {
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -313,6 +330,7 @@ struct WgradParams {
   int dw_tap_stride;          // elements between taps in dW (= Cin*Cout for HWIO)
   int dw_row_stride;          // elements between consecutive ci rows (= Cout for HWIO)
   int dw_col_stride;          // elements between consecutive co (1 for HWIO)
+  int direct;                 // 1: single split, overwrite -> plain 16-byte stores instead of atomics
   float* dw;
 };
 
@@ -444,8 +462,16 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
         if (valid) {
+          if (p.direct) {
+            float4* d4 = reinterpret_cast<float4*>(dst + c0);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(dst + (int64_t)(c0 + i) * p.dw_col_stride, __uint_as_float(r[i]));
+            for (int i = 0; i < 8; ++i)
+              d4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                  __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(dst + (int64_t)(c0 + i) * p.dw_col_stride, __uint_as_float(r[i]));
+          }
         }
       }
       tc_fence_before();
@@ -459,6 +485,69 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+// Finishes a split-K igemm: out = epilogue(ws) over [rows][C], 8 channels per thread.
+__global__ void __launch_bounds__(256) epilogue_finish_kernel(const float* __restrict__ ws, const float* __restrict__ bias,
+                                                              const bf16* __restrict__ residual,
+                                                              const bf16* __restrict__ mask, void* __restrict__ out,
+                                                              int out_f32, int relu, float scale, int64_t rows, int C) {
+  const int C8 = C >> 3;
+  const int64_t total = rows * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    const int64_t base = (i / C8) * C + c;
+    float v[8];
+    const float4 a = *reinterpret_cast<const float4*>(ws + base), b = *reinterpret_cast<const float4*>(ws + base + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += __ldg(bias + c + j);
+    }
+    if (residual) {
+      const uint4 u = *reinterpret_cast<const uint4*>(residual + base);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&u.x)[j]);
+        v[2 * j] += f.x; v[2 * j + 1] += f.y;
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (mask) {
+      const uint4 u = *reinterpret_cast<const uint4*>(mask + base);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&u.x)[j]);
+        if (!(f.x > 0.f)) v[2 * j] = 0.f;
+        if (!(f.y > 0.f)) v[2 * j + 1] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= scale;
+    if (out_f32) {
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + base);
+      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out) + base) =
+          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+  }
+}
+
+// grow-only device scratch owned by the context (first use allocates; never on the steady-state path)
+int ensure_workspace(segk_ctx* ctx, size_t bytes) {
+  if (ctx->ws_bytes >= bytes) return SEGK_OK;
+  if (ctx->ws) cudaFree(ctx->ws);
+  ctx->ws = nullptr;
+  ctx->ws_bytes = 0;
+  cudaError_t e = cudaMalloc(&ctx->ws, bytes);
+  if (e != cudaSuccess) return segk_fail(ctx, SEGK_ENOMEM, "workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
+  ctx->ws_bytes = bytes;
+  return SEGK_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -546,7 +635,7 @@ int launch_igemm_t(segk_ctx* ctx, const TensorMaps& maps, const IgemmParams& p, 
 
 int launch_igemm(segk_ctx* ctx, int block_n, const TensorMaps& maps, const IgemmParams& p, const TapTable& taps,
                  cudaStream_t st) {
-  const int total = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+  const int total = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.ksplits;
   const int grid = total < ctx->sm_count ? total : ctx->sm_count;
   switch (block_n) {
     case 256: return launch_igemm_t<256>(ctx, maps, p, taps, grid, st);
@@ -615,8 +704,34 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   p.out = y; p.out_f32 = out_f32;
   p.bias = bias; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask;
   p.scale = scale; p.relu = relu;
+  p.ksplits = 1; p.ws = nullptr;
   TapTable taps;
   conv_taps(taps, kh, kw);
+  // few output tiles but a long K walk (conv6 dgrad: 48 tiles x 3136 k-steps): split K across SMs
+  const int tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+  if (tiles * 2 <= ctx->sm_count && p.ntaps * p.kchunks >= 32 && p.kchunks >= 2) {
+    int ks = ctx->sm_count / tiles;
+    if (ks > p.kchunks) ks = p.kchunks;   // every split keeps >= 1 step even if a single tap is active
+    if (ks > 16) ks = 16;
+    if (ks > 1) {
+      const size_t bytes = sizeof(float) * (size_t)N * H * W * Cn;
+      rc = ensure_workspace(ctx, bytes);
+      if (rc) return rc;
+      cudaError_t e = cudaMemsetAsync(ctx->ws, 0, bytes, (cudaStream_t)stream);
+      if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "%s: workspace memset: %s", what, cudaGetErrorString(e));
+      p.ksplits = ks;
+      p.ws = (float*)ctx->ws;
+      rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+      if (rc) return rc;
+      const int64_t rows = (int64_t)N * H * W;
+      int64_t blocks = ceil_div64(rows * (Cn / 8), 256);
+      if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
+      epilogue_finish_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+          (const float*)ctx->ws, bias, (const bf16*)residual, (const bf16*)mask, y, out_f32, relu, scale, rows, Cn);
+      SEGK_LAUNCHED(ctx, "igemm split-K finish");
+      return SEGK_OK;
+    }
+  }
   return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
 }
 
@@ -685,6 +800,7 @@ int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float*
   p.out = y; p.out_f32 = (flags & SEGK_EPI_OUT_F32) ? 1 : 0;
   p.bias = bias; p.residual = (const bf16*)residual; p.mask = nullptr;
   p.scale = 1.f; p.relu = (flags & SEGK_EPI_RELU) ? 1 : 0;
+  p.ksplits = 1; p.ws = nullptr;
   TapTable taps;
   memset(&taps, 0, sizeof(taps));
   for (int u = 0; u < 4; ++u) {
@@ -723,6 +839,7 @@ int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const voi
   p.out = dx; p.out_f32 = 0;
   p.mask = (const bf16*)relu_mask;
   p.scale = 1.f;
+  p.ksplits = 1; p.ws = nullptr;
   TapTable taps;
   strided_taps(taps, k, s);
   return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
@@ -764,7 +881,8 @@ int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw,
   p.Cin_total = Cout; p.Cout_total = Cin;
   p.dw_tap_stride = Cout * Cin; p.dw_row_stride = Cin; p.dw_col_stride = 1;
   p.dw = dw;
-  if (!accumulate) {
+  p.direct = (!accumulate && p.splits == 1 && p.n_rb % 2 == 0) ? 1 : 0;
+  if (!accumulate && !p.direct) {
     cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * k * Cin * Cout, st);
     if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "deconv2d_wgrad memset: %s", cudaGetErrorString(e));
   }
@@ -837,7 +955,8 @@ int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, i
   p.Cin_total = Cin; p.Cout_total = Cout;
   p.dw_tap_stride = Cin * Cout; p.dw_row_stride = Cout; p.dw_col_stride = 1;
   p.dw = dw;
-  if (!accumulate) {
+  p.direct = (!accumulate && p.splits == 1) ? 1 : 0;
+  if (!accumulate && !p.direct) {
     cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)kh * kw * Cin * Cout, st);
     if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "conv2d_wgrad memset: %s", cudaGetErrorString(e));
   }

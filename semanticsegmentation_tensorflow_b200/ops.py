@@ -68,10 +68,12 @@ class Profile:
     def __init__(self):
         self.records = []     # (family, work, unit, start_event, end_event)
 
-    def summary(self):
+    def summary(self, detail=False):
+        """Aggregate by C entry point (or by entry point + integer arguments when detail)."""
         out = {}
-        for fam, work, unit, e0, e1 in self.records:
-            d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "work": 0.0, "unit": unit})
+        for fam, work, unit, e0, e1, dims in self.records:
+            key = fam + str(list(dims)) if detail else fam
+            d = out.setdefault(key, {"launches": 0, "ms": 0.0, "work": 0.0, "unit": unit})
             d["launches"] += 1
             d["ms"] += e0.elapsed_time(e1)
             d["work"] += work
@@ -97,7 +99,8 @@ class Ops:
         e1.record()
         work, unit = self._work if self._work is not None else (0.0, "")
         self._work = None
-        self.profile.records.append((name, work, unit, e0, e1))
+        dims = tuple(a for a in args[:-1] if isinstance(a, int) and not isinstance(a, bool) and 0 <= a < (1 << 20))
+        self.profile.records.append((name, work, unit, e0, e1, dims))
 
     def _w(self, work, unit):
         if self.profile is not None:

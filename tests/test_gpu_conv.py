@@ -32,6 +32,7 @@ CONV_SHAPES = [
     (4, 10, 36, 512, 512, 3),
     (2, 40, 144, 128, 256, 3),
     (1, 7, 9, 64, 192, 3),       # ragged box, Cout = 3 x 64
+    (1, 5, 18, 256, 128, 7),     # few tiles, long K walk -> split-K path (fwd and dgrad)
 ]
 
 

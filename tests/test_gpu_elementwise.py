@@ -116,18 +116,22 @@ def test_adam_tf_formula_three_steps(ops, cuda_device):
     md, vd = torch.zeros_like(pd), torch.zeros_like(pd)
     from semanticsegmentation_tensorflow_b200.plan import adam_lr_t
     gmax = np.zeros(n, np.float32)
+    updmax = np.zeros(n, np.float32)
     for t in range(1, 4):
         g = (rng.standard_normal(n) * scales).astype(np.float32)
         gmax = np.maximum(gmax, np.abs(g))
+        before = p.numpy().copy()
         T.adam_tf_step(p, m, v, torch.tensor(g), t)
+        updmax = np.maximum(updmax, np.abs(p.numpy() - before))
         ops.adam_step(pd, md, vd, dev_f32(g, cuda_device), adam_lr_t(1e-4, t))
     torch.cuda.synchronize()
     # m can cancel (alternating gradient signs): tolerance relative to the gradient scale seen
     assert np.all(np.abs(host(md) - m.numpy()) <= 1e-6 * gmax + 1e-45)
     np.testing.assert_allclose(host(vd), v.numpy(), rtol=1e-5, atol=0)
     np.testing.assert_allclose(host(pd), p.numpy(), rtol=2e-7, atol=1e-9)
-    # where p started at 0 the parameter IS the accumulated update: |g| << eps elements included
-    np.testing.assert_allclose(host(pd)[::2], p.numpy()[::2], rtol=2e-5, atol=1e-12)
+    # where p started at 0 the parameter IS the accumulated update (|g| << eps elements included):
+    # error bounded relative to the largest single-step update of that element (m may cancel)
+    assert np.all(np.abs(host(pd) - p.numpy())[::2] <= 1e-4 * updmax[::2] + 1e-30)
 
 
 def test_momentum_step(ops, cuda_device):
