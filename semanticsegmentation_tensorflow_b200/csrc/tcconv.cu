@@ -17,6 +17,8 @@
 //   warps 2-5 epilogue: tcgen05.ld -> bias / residual / ReLU / ReLU-mask / scale -> global stores
 #include "tc_common.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 using namespace tc;
@@ -559,12 +561,27 @@ struct Box {
 
 // Pick a pixel box bw x bh x bn with at most `max_rows` rows (exactly, when `exact`) that
 // covers [N,H,W] with the fewest tiles; ties -> wider bw (longer contiguous runs for TMA).
-Box choose_box(int N, int H, int W, int max_rows, bool exact, int lim_h = 0, int lim_w = 0) {
+// Number of (tile, tap) pairs that survive tile-level tap skipping for a kh x kw SAME conv when
+// [H, W] is tiled by bh x bw boxes (1-D factorises: rows and columns are independent).
+int64_t active_taps_1d(int n, int b, int k) {
+  const int p = k / 2;
+  int64_t tot = 0;
+  for (int t0 = 0; t0 < n; t0 += b)
+    for (int d = -p; d <= k - 1 - p; ++d)
+      if (!(t0 + d + b <= 0 || t0 + d >= n)) ++tot;
+  return tot;
+}
+
+// Pick a pixel box bw x bh x bn with at most `max_rows` rows (exactly, when `exact`) that covers
+// [N,H,W] with the least work = sum over tiles of active taps (kh = kw = 1: the tile count);
+// ties -> wider bw (longer contiguous runs for TMA).
+Box choose_box(int N, int H, int W, int max_rows, bool exact, int lim_h = 0, int lim_w = 0, int kh = 1, int kw = 1) {
   Box best{0, 0, 0, 0, 0};
   int64_t best_cost = -1;
   if (lim_h <= 0) lim_h = H;
   if (lim_w <= 0) lim_w = W;
   for (int bw = 1; bw <= lim_w && bw <= max_rows && bw <= 256; ++bw) {
+    const int64_t ax = active_taps_1d(W, bw, kw);
     for (int bh = 1; bh <= lim_h && bw * bh <= max_rows && bh <= 256; ++bh) {
       int bn = max_rows / (bw * bh);
       // exact boxes may run past the batch (TMA zero-fills the out-of-bounds images)
@@ -573,7 +590,8 @@ Box choose_box(int N, int H, int W, int max_rows, bool exact, int lim_h = 0, int
       const int rows = bw * bh * bn;
       if (exact && rows != max_rows) continue;
       const int tiles = ceil_div(W, bw) * ceil_div(H, bh) * ceil_div(N, bn);
-      const int64_t cost = (int64_t)tiles * 1024 - bw;
+      const int64_t work = ax * active_taps_1d(H, bh, kh) * ceil_div(N, bn);
+      const int64_t cost = work * 1024 - bw;
       if (best_cost < 0 || cost < best_cost) {
         best_cost = cost;
         best = Box{bw, bh, bn, rows, tiles};
@@ -612,7 +630,15 @@ int encode_weight_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int K, in
   return SEGK_OK;
 }
 
+// tuning overrides for sweeps (tools/sweep_tiles.py); 0 / unset = use the heuristics
+int env_int(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
+}
+
 int pick_block_n(int Cout) {
+  const int f = env_int("SEGK_FORCE_BN");
+  if ((f == 64 || f == 128 || f == 256) && Cout % f == 0) return f;
   if (Cout % 256 == 0) return 256;
   if (Cout % 128 == 0) return 128;
   return 64;
@@ -681,7 +707,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
                kMaxTaps, kh, kw);
   SEGK_REQUIRE(ctx, (((uintptr_t)x | (uintptr_t)wt | (uintptr_t)y | (uintptr_t)residual | (uintptr_t)mask) & 15) == 0,
                "%s: pointers must be 16-byte aligned", what);
-  const Box b = choose_box(N, H, W, kBlockM, false);
+  const Box b = choose_box(N, H, W, kBlockM, false, 0, 0, kh, kw);
   SEGK_REQUIRE(ctx, b.rows > 0, "%s: no pixel box for %dx%dx%d", what, N, H, W);
   const int block_n = pick_block_n(Cn);
   TensorMaps maps;
@@ -709,8 +735,10 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   conv_taps(taps, kh, kw);
   // few output tiles but a long K walk (conv6 dgrad: 48 tiles x 3136 k-steps): split K across SMs
   const int tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
-  if (tiles * 2 <= ctx->sm_count && p.ntaps * p.kchunks >= 32 && p.kchunks >= 2) {
+  const int force_ks = env_int("SEGK_FORCE_KSPLIT");
+  if ((tiles * 2 <= ctx->sm_count && p.ntaps * p.kchunks >= 32 && p.kchunks >= 2) || force_ks > 0) {
     int ks = ctx->sm_count / tiles;
+    if (force_ks > 0) ks = force_ks;
     if (ks > p.kchunks) ks = p.kchunks;   // every split keeps >= 1 step even if a single tap is active
     if (ks > 16) ks = 16;
     if (ks > 1) {
@@ -872,7 +900,8 @@ int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw,
   p.n_rb = k * k * p.kchunks_in;
   p.n_rbp = (p.n_rb + 1) / 2;
   p.n_tiles = Cin / block_n;
-  int splits = ceil_div(2 * ctx->sm_count, p.n_rbp * p.n_tiles);
+  const int base_items = p.n_rbp * p.n_tiles;
+  int splits = base_items >= 16 ? ctx->sm_count / base_items : ceil_div(2 * ctx->sm_count, base_items);
   const int max_splits = ceil_div(n_ptiles, 8);
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -944,7 +973,10 @@ int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, i
   p.n_rbp = (p.n_rb + 1) / 2;
   p.n_tiles = Cout / block_n;
   const int base_items = p.n_rbp * p.n_tiles;
-  int splits = ceil_div(2 * ctx->sm_count, base_items);
+  // measured (profiles/, sweep): one wave of items is best once there are >= 16 base items (the
+  // atomics of extra splits cost more than the tail); tiny item counts want two waves
+  int splits = base_items >= 16 ? ctx->sm_count / base_items : ceil_div(2 * ctx->sm_count, base_items);
+  if (env_int("SEGK_FORCE_WSPLIT") > 0) splits = env_int("SEGK_FORCE_WSPLIT");
   const int max_splits = ceil_div(n_ptiles, 8);  // at least 8 k-steps per item
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
