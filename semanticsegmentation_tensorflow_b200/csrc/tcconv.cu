@@ -318,6 +318,244 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
 }
 
 // ------------------------------------------------------------------------------------------
+// slab_kernel: 3x3 stride-1 conv (fwd / dgrad) for large maps with few output channels, where the
+// tap-wise igemm is bound by re-reading the activations 9x from L2 (measured: conv1_2 at 0.36 PF/s).
+// One TMA loads a haloed slab (kSlabH+2 image rows x 32 columns x 64 channels) per 64-channel step;
+// all 9 taps are UMMA descriptors into that SAME slab: output "row" o = i*32 + j (i < 4 image rows,
+// j < 32 slab columns, the last two are discarded halo columns) reads slab row o + ty*32 + tx, so a
+// tap is just a start-row offset.  Offsets that are not multiples of 8 rows are expressed with the
+// descriptor's matrix-base-offset field (start >> 7) & 7.  Activation traffic drops from 9x to
+// (6/4)*(32/30) = 1.6x.  Separate rings for slabs and weight tiles.
+// ------------------------------------------------------------------------------------------
+constexpr int kSlabP = 32;        // slab pitch in pixels
+constexpr int kSlabH = 4;         // output image rows per tile
+constexpr int kSlabWV = 30;       // valid output columns per tile
+constexpr int kSlabRows = (kSlabH + 2) * kSlabP;          // 192 rows written by TMA (+2 spill rows read)
+constexpr int kSlabBytes = 25600;                          // 194 rows * 128 B rounded up to 1024
+
+template <int BLOCK_N>
+struct SlabCfg {
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kAStages = BLOCK_N == 256 ? 2 : 3;
+  static constexpr int kBStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 7 : 12);
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kAStages * kSlabBytes + kBStages * kBBytes + 1024 + 512;
+};
+
+struct SlabParams {
+  int N, H, W;
+  int tiles_w, tiles_h;   // ceil(W/30), H/4
+  int n_tiles;            // Cn / BLOCK_N
+  int kchunks;            // Ck / 64
+  int ldo;
+  int base_offset_mode;   // 1: descriptor base offset = (addr >> 7) & 7 ; 0: always 0
+  void* out;
+  int out_f32;
+  const float* bias;
+  const bf16* residual;
+  const bf16* mask;
+  float scale;
+  int relu;
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t sbo_bytes, int mode) {
+  uint64_t d = make_smem_desc(saddr, 16, sbo_bytes);
+  if (mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  return d;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
+  using C = SlabCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kAStages * kSlabBytes;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(smem_b + C::kBStages * C::kBBytes);
+  uint64_t* emptyA = fullA + C::kAStages;
+  uint64_t* fullB = emptyA + C::kAStages;
+  uint64_t* emptyB = fullB + C::kBStages;
+  uint64_t* tfull_bar = emptyB + C::kBStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < C::kAStages; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < C::kBStages; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+    fence_barrier_init();
+  }
+  // the two spill rows past each slab are read (for discarded outputs only) but never written by
+  // TMA: zero the slab ring once so they can never hold NaN patterns that matter to no one
+  for (int i = threadIdx.x; i < C::kAStages * kSlabBytes / 16; i += kThreads)
+    reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      PipeState pa, pb;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        int r = tile / p.n_tiles;
+        const int x0 = (r % p.tiles_w) * kSlabWV;
+        r /= p.tiles_w;
+        const int y0 = (r % p.tiles_h) * kSlabH;
+        const int n = r / p.tiles_h;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&emptyA[pa.stage], pa.phase ^ 1);
+          mbar_arrive_expect_tx(&fullA[pa.stage], (uint32_t)kSlabRows * 128u);
+          tma_load_4d(&maps.a[0], &fullA[pa.stage], smem_a + pa.stage * kSlabBytes, kc * kBlockK, x0 - 1, y0 - 1, n);
+          pa.advance<C::kAStages>();
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&emptyB[pb.stage], pb.phase ^ 1);
+            mbar_arrive_expect_tx(&fullB[pb.stage], (uint32_t)C::kBBytes);
+            tma_load_3d(&maps.b, &fullB[pb.stage], smem_b + pb.stage * C::kBBytes, kc * kBlockK, nt * BLOCK_N, tap);
+            pb.advance<C::kBStages>();
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      PipeState pa, pb;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 0, 0);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&fullA[pa.stage], pa.phase);
+          const uint32_t slab = smem_u32(smem_a + pa.stage * kSlabBytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&fullB[pb.stage], pb.phase);
+            tc_fence_after();
+            const uint32_t a_addr = slab + (uint32_t)((tap / 3) * kSlabP + (tap % 3)) * 128u;
+            const uint32_t b_addr = smem_u32(smem_b + pb.stage * C::kBBytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint64_t ad = make_smem_desc_bo(a_addr + k * 32, 1024, p.base_offset_mode);
+              const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
+              umma_f16(d_addr, ad, bd, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&emptyB[pb.stage]);
+            pb.advance<C::kBStages>();
+          }
+          umma_commit(&emptyA[pa.stage]);
+          pa.advance<C::kAStages>();
+        }
+        umma_commit(&tfull_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;       // TMEM lane quarter == image row of the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      int r = tile / p.n_tiles;
+      const int x0 = (r % p.tiles_w) * kSlabWV;
+      r /= p.tiles_w;
+      const int y0 = (r % p.tiles_h) * kSlabH;
+      const int n = r / p.tiles_h;
+      const int ox = x0 + lane, oy = y0 + q;
+      const bool valid = lane < kSlabWV && ox < p.W && oy < p.H;
+      const int64_t obase = (((int64_t)n * p.H + oy) * p.W + ox) * p.ldo + (int64_t)nt * BLOCK_N;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(taddr + c0, rr);
+        tmem_ld_wait();
+        if (valid) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+          if (p.bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = __ldg(b4 + i);
+              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+          }
+          if (p.residual) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = __ldg(r4 + i);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2((&u.x)[j]);
+                v[8 * i + 2 * j] += f.x;
+                v[8 * i + 2 * j + 1] += f.y;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.mask) {
+            const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = __ldg(m4 + i);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2((&u.x)[j]);
+                if (!(f.x > 0.f)) v[8 * i + 2 * j] = 0.f;
+                if (!(f.y > 0.f)) v[8 * i + 2 * j + 1] = 0.f;
+              }
+            }
+          }
+          if (p.scale != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+          }
+          if (p.out_f32) {
+            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                 pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
 // wgrad: dW[rb*64 + i][co] = sum over pixels  X[pixel + shift(rb)][ci(rb)*64 + i] * dY[pixel][co]
 // A row block rb = (tap, 64-channel chunk of Cin).  One work item = (k-split, pair of row blocks,
 // N tile); it walks its range of 64-pixel boxes.  Both operands are MN-major in shared memory
@@ -685,6 +923,59 @@ int launch_wgrad_t(segk_ctx* ctx, const TensorMaps& maps, const WgradParams& p, 
   return SEGK_OK;
 }
 
+template <int BLOCK_N>
+int launch_slab_t(segk_ctx* ctx, const TensorMaps& maps, const SlabParams& p, int grid, cudaStream_t st) {
+  using C = SlabCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(slab_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "slab smem attr: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  slab_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(maps, p);
+  SEGK_LAUNCHED(ctx, "slab");
+  return SEGK_OK;
+}
+
+// 3x3 layers on large maps whose GEMM-N is small are activation-traffic bound in the tap-wise igemm
+bool slab_applicable(int N, int H, int W, int Ck, int Cn, int kh, int kw) {
+  const int mode = getenv("SEGK_SLAB") ? atoi(getenv("SEGK_SLAB")) : 1;   // 0 off, 1 auto, 2 whenever legal
+  if (mode == 0) return false;
+  const bool legal = kh == 3 && kw == 3 && H % kSlabH == 0 && W >= kSlabWV && Ck % 64 == 0 && Cn % 64 == 0;
+  if (!legal) return false;
+  if (mode == 2) return true;
+  return Cn <= 128 && (int64_t)H * W >= 4096;
+}
+
+int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, const float* bias, const void* residual,
+              const void* mask, float scale, int relu, int out_f32, void* y, int N, int H, int W, int Ck, int Cn,
+              void* stream) {
+  const int block_n = pick_block_n(Cn);
+  TensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  int rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Ck, Ck, (int64_t)W * Ck, (int64_t)H * W * Ck, kSlabP, kSlabH + 2, 1);
+  if (rc) return rc;
+  maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
+  rc = encode_weight_map(ctx, &maps.b, wt, Ck, Cn, 9, block_n);
+  if (rc) return rc;
+  SlabParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W;
+  p.tiles_w = ceil_div(W, kSlabWV); p.tiles_h = H / kSlabH;
+  p.n_tiles = Cn / block_n; p.kchunks = Ck / 64; p.ldo = Cn;
+  p.base_offset_mode = getenv("SEGK_SLAB_BO") ? atoi(getenv("SEGK_SLAB_BO")) : 1;
+  p.out = y; p.out_f32 = out_f32; p.bias = bias; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask;
+  p.scale = scale; p.relu = relu;
+  const int total = N * p.tiles_h * p.tiles_w * p.n_tiles;
+  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  (void)what;
+  switch (block_n) {
+    case 256: return launch_slab_t<256>(ctx, maps, p, grid, (cudaStream_t)stream);
+    case 128: return launch_slab_t<128>(ctx, maps, p, grid, (cudaStream_t)stream);
+    default: return launch_slab_t<64>(ctx, maps, p, grid, (cudaStream_t)stream);
+  }
+}
+
 void conv_taps(TapTable& t, int kh, int kw) {
   memset(&t, 0, sizeof(t));
   for (int i = 0; i < kh * kw; ++i) {
@@ -707,6 +998,8 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
                kMaxTaps, kh, kw);
   SEGK_REQUIRE(ctx, (((uintptr_t)x | (uintptr_t)wt | (uintptr_t)y | (uintptr_t)residual | (uintptr_t)mask) & 15) == 0,
                "%s: pointers must be 16-byte aligned", what);
+  if (slab_applicable(N, H, W, Ck, Cn, kh, kw))
+    return conv_slab(ctx, what, x, wt, bias, residual, mask, scale, relu, out_f32, y, N, H, W, Ck, Cn, stream);
   const Box b = choose_box(N, H, W, kBlockM, false, 0, 0, kh, kw);
   SEGK_REQUIRE(ctx, b.rows > 0, "%s: no pixel box for %dx%dx%d", what, N, H, W);
   const int block_n = pick_block_n(Cn);

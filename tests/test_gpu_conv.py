@@ -156,3 +156,51 @@ def test_unsupported_shape_is_an_error_not_a_fallback(ops, cuda_device):
     with pytest.raises(SegkError) as ei:
         ops.conv2d_fwd(x, wk, None, y, 3, 3)
     assert ei.value.code == SEGK_EINVAL and "no fallback" in str(ei.value)
+
+
+SLAB_SHAPES = [
+    # N, H, W, Cin, Cout  (3x3; routed to the haloed-slab kernel: Cout <= 128 and H*W >= 4096)
+    (2, 64, 96, 64, 64),
+    (1, 80, 288, 64, 128),
+    (1, 160, 576, 64, 64),
+    (2, 40, 144, 128, 128),
+    (1, 64, 70, 128, 64),        # W not a multiple of 30: ragged last column tile
+]
+
+
+@pytest.mark.parametrize("shape", SLAB_SHAPES)
+def test_slab_conv_fwd_and_dgrad(ops, cuda_device, shape):
+    n, h, w, ci, co = shape
+    k = 3
+    x, wt, b = _conv_case((n, h, w, ci, co, k), 20)
+    rng = np.random.default_rng(21)
+    res = bf16_grid(rng.standard_normal((n, h, w, co)))
+    xt = torch.tensor(x, requires_grad=True)
+    z = T.bias_add(T.conv2d_same(xt, torch.tensor(wt)), torch.tensor(b)) + torch.tensor(res)
+    ref = T.relu(z).detach().numpy()
+    wk, wd = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    y = torch.empty((n, h, w, co), dtype=torch.bfloat16, device=cuda_device)
+    ops.conv2d_fwd(dev_bf16(x, cuda_device), wk, dev_f32(b, cuda_device), y, k, k, relu=True,
+                   residual=dev_bf16(res, cuda_device))
+    torch.cuda.synchronize()
+    assert_close(host(y), ref, TOL_BF16, f"slab fwd {shape}")
+    dy = bf16_grid(rng.standard_normal((n, h, w, co)))
+    z.backward(torch.tensor(dy))
+    dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=cuda_device)
+    ops.conv2d_dgrad(dev_bf16(dy, cuda_device), wd, dx, k, k, relu_mask=dev_bf16(x, cuda_device), scale=0.5)
+    torch.cuda.synchronize()
+    assert_close(host(dx), xt.grad.numpy() * (x > 0) * 0.5, TOL_BF16, f"slab dgrad {shape}")
+
+
+def test_slab_forced_for_wide_layers(ops, cuda_device, monkeypatch):
+    """SEGK_SLAB=2 forces the slab kernel wherever it is legal (BLOCK_N = 256 instance)."""
+    monkeypatch.setenv("SEGK_SLAB", "2")
+    shape = (1, 40, 144, 128, 256, 3)
+    n, h, w, ci, co, k = shape
+    x, wt, b = _conv_case(shape, 22)
+    ref = T.relu(T.bias_add(T.conv2d_same(torch.tensor(x), torch.tensor(wt)), torch.tensor(b))).numpy()
+    wk, _ = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    y = torch.empty((n, h, w, co), dtype=torch.bfloat16, device=cuda_device)
+    ops.conv2d_fwd(dev_bf16(x, cuda_device), wk, dev_f32(b, cuda_device), y, k, k, relu=True)
+    torch.cuda.synchronize()
+    assert_close(host(y), ref, TOL_BF16, "slab forced BN=256")

@@ -1,0 +1,138 @@
+"""GPU checks at BASELINE.json's full sizes (batch 32, 160x576), where the CPU oracle would take
+minutes: size-independent properties (spot checks against the oracle on random output pixels,
+additivity over the batch, mass conservation, per-pixel gradient sums) instead of full tensors."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tf_ops as T
+from tests.gpu_util import assert_close, host
+
+pytestmark = pytest.mark.gpu
+
+B, H, W = 32, 160, 576
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_device):
+    from semanticsegmentation_tensorflow_b200.ops import Ops
+    return Ops(cuda_device)
+
+
+def _spot_check_conv(x, wt, b, y, k, npts=96, seed=0):
+    """Compare npts random output pixels with the oracle applied to their k x k input patches."""
+    n, h, w, ci = x.shape
+    rng = np.random.default_rng(seed)
+    p = k // 2
+    pts = [(rng.integers(n), rng.integers(h), rng.integers(w)) for _ in range(npts)]
+    pts += [(0, 0, 0), (n - 1, h - 1, w - 1), (0, h - 1, 0), (n - 1, 0, w - 1)]       # corners (SAME padding)
+    xp = torch.nn.functional.pad(x.float(), (0, 0, p, p, p, p))
+    got, ref = [], []
+    wt_c, b_c = wt.float().cpu(), b.float().cpu()
+    for (ni, yi, xi) in pts:
+        patch = xp[ni, yi:yi + k, xi:xi + k, :].cpu()                                  # [k,k,Cin]
+        ref.append(torch.relu(torch.einsum("abc,abcd->d", patch, wt_c) + b_c).numpy())
+        got.append(y[ni, yi, xi].float().cpu().numpy())
+    return np.stack(got), np.stack(ref)
+
+
+@pytest.mark.parametrize("layer", [(64, 64, 160, 576), (128, 128, 80, 288), (256, 256, 40, 144), (512, 512, 20, 72)])
+def test_conv_fwd_full_batch_spot_check(ops, cuda_device, layer):
+    ci, co, h, w = layer
+    g = torch.Generator(device=cuda_device).manual_seed(1)
+    x = torch.randn((B, h, w, ci), generator=g, device=cuda_device).to(torch.bfloat16)
+    wt = (torch.randn((3, 3, ci, co), generator=g, device=cuda_device) / math.sqrt(9 * ci)).to(torch.bfloat16).float()
+    b = torch.randn(co, generator=g, device=cuda_device) * 0.1
+    wk, _ = ops.pack_conv_weights(wt)
+    y = torch.empty((B, h, w, co), dtype=torch.bfloat16, device=cuda_device)
+    ops.conv2d_fwd(x, wk, b, y, 3, 3, relu=True)
+    torch.cuda.synchronize()
+    got, ref = _spot_check_conv(x, wt, b, y, 3)
+    assert_close(got, ref, 1e-2, f"full-size conv fwd {layer}")
+
+
+def test_wgrad_full_batch_is_additive_over_images(ops, cuda_device):
+    """dW(batch of 32) == dW(first 16) + dW(last 16): exercises split-K / atomics at full size."""
+    ci, co, h, w = 64, 64, H, W
+    g = torch.Generator(device=cuda_device).manual_seed(2)
+    x = torch.randn((B, h, w, ci), generator=g, device=cuda_device).to(torch.bfloat16)
+    dy = torch.randn((B, h, w, co), generator=g, device=cuda_device).to(torch.bfloat16)
+    dw = torch.empty((3, 3, ci, co), dtype=torch.float32, device=cuda_device)
+    dwa = torch.empty_like(dw)
+    ops.conv2d_wgrad(x, dy, dw, 3, 3)
+    ops.conv2d_wgrad(x[:16].contiguous(), dy[:16].contiguous(), dwa, 3, 3)
+    ops.conv2d_wgrad(x[16:].contiguous(), dy[16:].contiguous(), dwa, 3, 3, accumulate=True)
+    torch.cuda.synchronize()
+    assert_close(host(dw), host(dwa), 1e-4, "wgrad additivity")
+    # and the centre tap equals the plain matrix product X^T dY (fp32 on the GPU, chunked)
+    ref = torch.zeros((ci, co), dtype=torch.float32, device=cuda_device)
+    xf, df = x.view(-1, ci), dy.view(-1, co)
+    for s in range(0, xf.shape[0], 1 << 18):
+        ref += xf[s:s + (1 << 18)].float().t() @ df[s:s + (1 << 18)].float()
+    assert_close(host(dw[1, 1]), host(ref), 1e-3, "wgrad centre tap")
+
+
+def test_pool_full_size_properties(ops, cuda_device):
+    c = 64
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    x = torch.relu(torch.randn((B, H, W, c), generator=g, device=cuda_device)).to(torch.bfloat16)
+    y = torch.empty((B, H // 2, W // 2, c), dtype=torch.bfloat16, device=cuda_device)
+    idx = torch.empty((B, H // 2, W // 2, c), dtype=torch.uint8, device=cuda_device)
+    ops.maxpool_fwd(x, y, idx)
+    dy = torch.randn(y.shape, generator=g, device=cuda_device).to(torch.bfloat16)
+    dx = torch.empty_like(x)
+    ops.maxpool_bwd(dy, idx, dx)
+    torch.cuda.synchronize()
+    assert int(idx.max()) <= 3
+    win = x.view(B, H // 2, 2, W // 2, 2, c)
+    assert torch.equal(y, win.amax(dim=(2, 4)))                                          # bit-exact max
+    # first-max routing: gather by idx reproduces y exactly
+    flat = win.permute(0, 1, 3, 5, 2, 4).reshape(B, H // 2, W // 2, c, 4)
+    assert torch.equal(torch.gather(flat, 4, idx.long().unsqueeze(-1)).squeeze(-1), y)
+    # and no earlier window element equals the max (strict '>' scan => first maximal element)
+    pos = torch.arange(4, device=cuda_device).view(1, 1, 1, 1, 4)
+    earlier_equal = ((flat == y.unsqueeze(-1)) & (pos < idx.long().unsqueeze(-1))).any()
+    assert not bool(earlier_equal)
+    # mass conservation: every dy lands on exactly one input element
+    assert torch.equal(dx.view(B, H // 2, 2, W // 2, 2, c).double().sum(dim=(2, 4)), dy.double())
+
+
+def test_xent_and_confusion_full_size_properties(ops, cuda_device):
+    npix = B * H * W
+    g = torch.Generator(device=cuda_device).manual_seed(4)
+    lg = torch.randn((npix, 2), generator=g, device=cuda_device) * 3
+    lab = torch.randint(0, 2, (npix,), generator=g, device=cuda_device, dtype=torch.uint8)
+    dl = torch.empty_like(lg)
+    pred = torch.empty(npix, dtype=torch.uint8, device=cuda_device)
+    loss_sum = torch.zeros(1, device=cuda_device)
+    cm = torch.zeros(4, dtype=torch.int64, device=cuda_device)
+    ops.softmax_xent(lg, lab, dl, pred, loss_sum, cm, ops.xent_workspace(npix, cuda_device), 1.0 / npix)
+    torch.cuda.synchronize()
+    assert float(dl.sum(dim=1).abs().max()) <= 1e-6 / npix * 4                          # softmax - onehot sums to 0
+    assert int(cm.sum()) == npix
+    assert torch.equal(pred, (lg[:, 1] > lg[:, 0]).to(torch.uint8))
+    ref_cm = torch.bincount(lab.long() * 2 + pred.long(), minlength=4)
+    assert torch.equal(cm, ref_cm)                                                       # bit-exact histogram
+    ref_loss = torch.nn.functional.cross_entropy(lg.double(), lab.long(), reduction="sum")
+    assert abs(float(loss_sum[0]) - float(ref_loss)) <= 1e-5 * float(ref_loss)
+
+
+def test_full_size_training_step_reference_init(cuda_device):
+    """BASELINE configs[1] for real: batch 32, 160x576, reference init -> loss == ln 2, finite grads,
+    a second step runs, and the loss stays within 1e-3 of ln 2 (SURVEY §0 finding 5)."""
+    from semanticsegmentation_tensorflow_b200.fcn import FCN, AdamOptimizer
+    g = torch.Generator().manual_seed(5)
+    x = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=g).to(cuda_device)
+    y = torch.randint(0, 2, (B, H, W), dtype=torch.uint8, generator=g).to(cuda_device)
+    net = FCN(x, 1.0, 2, init="device")
+    step = AdamOptimizer(1e-4).minimize(net)
+    l0 = float(step({net.image: x, net.annotation: y, net.keep_probability: 1.0}))
+    assert abs(l0 - math.log(2.0)) < 1e-3
+    assert bool(torch.isfinite(net.vars.g).all())
+    assert float(net.vars.g.abs().max()) > 0
+    l1 = float(step({net.image: x, net.annotation: y, net.keep_probability: 0.8}))
+    assert math.isfinite(l1) and abs(l1 - math.log(2.0)) < 1e-2
+    cm = net.confusion_matrix()
+    assert int(cm.sum()) == B * H * W

@@ -71,3 +71,31 @@ if __name__ == "__main__":
     run_wgrad(2, 16, 16, 64, 256)
     run_wgrad(2, 16, 16, 192, 64)
     print("diag done")
+
+
+def run_slab(bo_mode, n=1, h=8, w=64, ci=64, co=64):
+    """3x3 conv through the slab kernel with integer data; prints the error under a base-offset mode."""
+    os.environ["SEGK_SLAB"] = "2"
+    os.environ["SEGK_SLAB_BO"] = str(bo_mode)
+    rng = np.random.default_rng(1)
+    x = torch.tensor(rng.integers(-2, 3, (n, h, w, ci)).astype(np.float32))
+    wt = torch.tensor(rng.integers(-1, 2, (3, 3, ci, co)).astype(np.float32))
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), wt.permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
+    wk, _ = ops.pack_conv_weights(wt.to(dev))
+    y = torch.full((n, h, w, co), -77.0, dtype=torch.float32, device=dev)
+    ops.conv2d_fwd(x.to(torch.bfloat16).to(dev), wk, None, y, 3, 3, relu=False)
+    torch.cuda.synchronize()
+    err = (y.cpu() - ref).abs()
+    print(f"slab bo_mode={bo_mode} n{n} h{h} w{w} ci{ci} co{co}: max err {err.max():.3f} mismatches {(err > 0.01).sum().item()} / {err.numel()}")
+    if err.max() > 0.01:
+        bad = (err > 0.01).any(-1)
+        print("  bad pixel map (n=0), rows = y:")
+        for yy in range(min(h, 8)):
+            print("   ", "".join("X" if bad[0, yy, xx] else "." for xx in range(w)))
+    os.environ["SEGK_SLAB"] = "1"
+
+
+if __name__ == "__main__":
+    run_slab(1)
+    run_slab(0)
+    run_slab(1, 2, 16, 96, 128, 128)
