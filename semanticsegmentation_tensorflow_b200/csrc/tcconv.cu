@@ -39,6 +39,11 @@ struct Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// UMMA shared-memory descriptor minus the start address (tc_common.cuh make_smem_desc): SWIZZLE_128B,
+// version 1, SBO = 1024 B; K-major: LBO field 1 (ignored); MN-major: LBO = 8192 B between 64-wide blocks.
+constexpr uint64_t kDescKMajor = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+constexpr uint64_t kDescMNMajor = (512ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+
 struct alignas(64) TensorMaps {
   CUtensorMap a[4];
   CUtensorMap b;
@@ -154,66 +159,70 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA warps run warp-converged and elect one lane only around the issue itself: the
+  // single-lane (divergent) form made ptxas marshal every descriptor through ELECT / R2UR loops,
+  // ~125 SASS instructions per k-step, which left the BLOCK_N = 64 layers MMA-issue-bound (ncu r1).
   if (warp == 0) {
-    if (lane == 0) {
-      PipeState ps;
-      const uint32_t tx_bytes = (uint32_t)p.rows * 128u + (uint32_t)C::kBBytes;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        const uint64_t tm = tap_mask(p, taps, t);
-        const int nall = __popcll(tm) * p.kchunks;
-        const int per = (nall + p.ksplits - 1) / p.ksplits;
-        const int lo = t.split * per, hi = min(lo + per, nall);
-        int step = 0;
-        for (int i = 0; i < p.ntaps; ++i) {
-          if (!((tm >> i) & 1)) continue;
-          const int dy = taps.dy[i], dx = taps.dx[i], mi = taps.map[i];
-          for (int kc = 0; kc < p.kchunks; ++kc, ++step) {
-            if (step < lo || step >= hi) continue;
-            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+    PipeState ps;
+    const uint32_t tx_bytes = (uint32_t)p.rows * 128u + (uint32_t)C::kBBytes;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const uint64_t tm = tap_mask(p, taps, t);
+      const int nall = __popcll(tm) * p.kchunks;
+      const int per = (nall + p.ksplits - 1) / p.ksplits;
+      const int lo = t.split * per, hi = min(lo + per, nall);
+      int step = 0;
+      for (int i = 0; i < p.ntaps; ++i) {
+        if (!((tm >> i) & 1)) continue;
+        const int dy = taps.dy[i], dx = taps.dx[i], mi = taps.map[i];
+        for (int kc = 0; kc < p.kchunks; ++kc, ++step) {
+          if (step < lo || step >= hi) continue;
+          mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+          if (elect_one()) {
             uint8_t* sa = smem + ps.stage * C::kStageBytes;
             mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
             tma_load_4d(&maps.a[mi], &full_bar[ps.stage], sa, kc * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
             tma_load_3d(&maps.b, &full_bar[ps.stage], sa + kABytes, kc * kBlockK, t.nt * BLOCK_N,
                         t.phase * p.ntaps + i);
-            ps.advance<C::kStages>();
           }
+          __syncwarp();
+          ps.advance<C::kStages>();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      PipeState ps;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 0, 0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
-        const uint64_t tm = tap_mask(p, taps, t);
-        const int nall = __popcll(tm) * p.kchunks;
-        const int per = (nall + p.ksplits - 1) / p.ksplits;
-        const int nsteps = min(t.split * per + per, nall) - t.split * per;   // host guarantees > 0
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    PipeState ps;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 0, 0);
+    const uint32_t smem_lo = smem_u32(smem) >> 4;          // descriptor start-address units (16 B)
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const uint64_t tm = tap_mask(p, taps, t);
+      const int nall = __popcll(tm) * p.kchunks;
+      const int per = (nall + p.ksplits - 1) / p.ksplits;
+      const int nsteps = min(t.split * per + per, nall) - t.split * per;   // host guarantees > 0
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int ks = 0; ks < nsteps; ++ks) {
+        mbar_wait(&full_bar[ps.stage], ps.phase);
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int ks = 0; ks < nsteps; ++ks) {
-          mbar_wait(&full_bar[ps.stage], ps.phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + ps.stage * C::kStageBytes);
-          const uint32_t b_addr = a_addr + kABytes;
+        if (elect_one()) {
+          const uint32_t a_lo = smem_lo + (uint32_t)ps.stage * (uint32_t)(C::kStageBytes >> 4);
+          const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t ad = make_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_f16(d_addr, ad, bd, idesc, (ks | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16(d_addr, kDescKMajor | (uint64_t)(a_lo + 2 * k), kDescKMajor | (uint64_t)(b_lo + 2 * k), idesc,
+                     (ks | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[ps.stage]);
           if (ks == nsteps - 1) umma_commit(&tfull_bar[acc]);
-          ps.advance<C::kStages>();
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        ps.advance<C::kStages>();
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     // ---- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----
@@ -323,8 +332,10 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
 // One TMA loads a haloed slab (kSlabH+2 image rows x 32 columns x 64 channels) per 64-channel step;
 // all 9 taps are UMMA descriptors into that SAME slab: output "row" o = i*32 + j (i < 4 image rows,
 // j < 32 slab columns, the last two are discarded halo columns) reads slab row o + ty*32 + tx, so a
-// tap is just a start-row offset.  Offsets that are not multiples of 8 rows are expressed with the
-// descriptor's matrix-base-offset field (start >> 7) & 7.  Activation traffic drops from 9x to
+// tap is just a start-row offset, including offsets that are not multiples of the 8-row swizzle atom:
+// measured on B200, the 128B swizzle is a function of the absolute shared-memory address on both the
+// TMA write and the UMMA read side, so the descriptor's base-offset field stays 0 (setting it to
+// (start >> 7) & 7 gave wrong results in the round-1 diagnostic run).  Activation traffic drops from 9x to
 // (6/4)*(32/30) = 1.6x.  Separate rings for slabs and weight tiles.
 // ------------------------------------------------------------------------------------------
 constexpr int kSlabP = 32;        // slab pitch in pixels
@@ -348,7 +359,6 @@ struct SlabParams {
   int n_tiles;            // Cn / BLOCK_N
   int kchunks;            // Ck / 64
   int ldo;
-  int base_offset_mode;   // 1: descriptor base offset = (addr >> 7) & 7 ; 0: always 0
   void* out;
   int out_f32;
   const float* bias;
@@ -357,12 +367,6 @@ struct SlabParams {
   float scale;
   int relu;
 };
-
-__device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, uint32_t sbo_bytes, int mode) {
-  uint64_t d = make_smem_desc(saddr, 16, sbo_bytes);
-  if (mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
-  return d;
-}
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -403,63 +407,71 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      PipeState pa, pb;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
-        int r = tile / p.n_tiles;
-        const int x0 = (r % p.tiles_w) * kSlabWV;
-        r /= p.tiles_w;
-        const int y0 = (r % p.tiles_h) * kSlabH;
-        const int n = r / p.tiles_h;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&emptyA[pa.stage], pa.phase ^ 1);
+    PipeState pa, pb;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      int r = tile / p.n_tiles;
+      const int x0 = (r % p.tiles_w) * kSlabWV;
+      r /= p.tiles_w;
+      const int y0 = (r % p.tiles_h) * kSlabH;
+      const int n = r / p.tiles_h;
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&emptyA[pa.stage], pa.phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&fullA[pa.stage], (uint32_t)kSlabRows * 128u);
           tma_load_4d(&maps.a[0], &fullA[pa.stage], smem_a + pa.stage * kSlabBytes, kc * kBlockK, x0 - 1, y0 - 1, n);
-          pa.advance<C::kAStages>();
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&emptyB[pb.stage], pb.phase ^ 1);
+        }
+        __syncwarp();
+        pa.advance<C::kAStages>();
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&emptyB[pb.stage], pb.phase ^ 1);
+          if (elect_one()) {
             mbar_arrive_expect_tx(&fullB[pb.stage], (uint32_t)C::kBBytes);
             tma_load_3d(&maps.b, &fullB[pb.stage], smem_b + pb.stage * C::kBBytes, kc * kBlockK, nt * BLOCK_N, tap);
-            pb.advance<C::kBStages>();
           }
+          __syncwarp();
+          pb.advance<C::kBStages>();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      PipeState pa, pb;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 0, 0);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&fullA[pa.stage], pa.phase);
-          const uint32_t slab = smem_u32(smem_a + pa.stage * kSlabBytes);
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(&fullB[pb.stage], pb.phase);
-            tc_fence_after();
-            const uint32_t a_addr = slab + (uint32_t)((tap / 3) * kSlabP + (tap % 3)) * 128u;
-            const uint32_t b_addr = smem_u32(smem_b + pb.stage * C::kBBytes);
+    PipeState pa, pb;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 0, 0);
+    const uint32_t a_lo0 = smem_u32(smem_a) >> 4, b_lo0 = smem_u32(smem_b) >> 4;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        mbar_wait(&fullA[pa.stage], pa.phase);
+        const uint32_t slab_lo = a_lo0 + (uint32_t)pa.stage * (uint32_t)(kSlabBytes >> 4);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&fullB[pb.stage], pb.phase);
+          tc_fence_after();
+          if (elect_one()) {
+            // tap (ty,tx) = slab row offset ty*32 + tx; one row = 128 B = 8 descriptor units
+            const uint32_t a_lo = slab_lo + (uint32_t)((tap / 3) * kSlabP + (tap % 3)) * 8u;
+            const uint32_t b_lo = b_lo0 + (uint32_t)pb.stage * (uint32_t)(C::kBBytes >> 4);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              const uint64_t ad = make_smem_desc_bo(a_addr + k * 32, 1024, p.base_offset_mode);
-              const uint64_t bd = make_smem_desc(b_addr + k * 32, 16, 1024);
-              umma_f16(d_addr, ad, bd, idesc, (kc | tap | k) != 0 ? 1u : 0u);
-            }
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16(d_addr, kDescKMajor | (uint64_t)(a_lo + 2 * k), kDescKMajor | (uint64_t)(b_lo + 2 * k), idesc,
+                       (kc | tap | k) != 0 ? 1u : 0u);
             umma_commit(&emptyB[pb.stage]);
-            pb.advance<C::kBStages>();
+            if (tap == 8) {
+              umma_commit(&emptyA[pa.stage]);
+              if (kc == p.kchunks - 1) umma_commit(&tfull_bar[acc]);
+            }
           }
-          umma_commit(&emptyA[pa.stage]);
-          pa.advance<C::kAStages>();
+          __syncwarp();
+          pb.advance<C::kBStages>();
         }
-        umma_commit(&tfull_bar[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        pa.advance<C::kAStages>();
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     const int q = warp & 3;       // TMEM lane quarter == image row of the tile
@@ -611,25 +623,25 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      PipeState ps;
-      constexpr uint32_t tx_bytes = (uint32_t)C::kStageBytes;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int nt = item % p.n_tiles;
-        const int rbp = (item / p.n_tiles) % p.n_rbp;
-        const int split = item / (p.n_tiles * p.n_rbp);
-        const int rb0 = 2 * rbp, rb1 = (2 * rbp + 1 < p.n_rb) ? 2 * rbp + 1 : 2 * rbp;
-        const int tap0 = rb0 / p.kchunks_in, c0 = (rb0 % p.kchunks_in) * 64;
-        const int tap1 = rb1 / p.kchunks_in, c1 = (rb1 % p.kchunks_in) * 64;
-        const int dy0 = taps.dy[tap0], dx0 = taps.dx[tap0], dy1 = taps.dy[tap1], dx1 = taps.dx[tap1];
-        const int m0 = taps.map[tap0], m1 = taps.map[tap1];
-        const int pt0 = split * per_split;
-        const int pt1 = min(pt0 + per_split, n_ptiles);
-        for (int pt = pt0; pt < pt1; ++pt) {
-          const int x0 = (pt % p.tiles_w) * p.bw;
-          const int y0 = ((pt / p.tiles_w) % p.tiles_h) * p.bh;
-          const int n0 = (pt / (p.tiles_w * p.tiles_h)) * p.bn;
-          mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+    PipeState ps;
+    constexpr uint32_t tx_bytes = (uint32_t)C::kStageBytes;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int nt = item % p.n_tiles;
+      const int rbp = (item / p.n_tiles) % p.n_rbp;
+      const int split = item / (p.n_tiles * p.n_rbp);
+      const int rb0 = 2 * rbp, rb1 = (2 * rbp + 1 < p.n_rb) ? 2 * rbp + 1 : 2 * rbp;
+      const int tap0 = rb0 / p.kchunks_in, c0 = (rb0 % p.kchunks_in) * 64;
+      const int tap1 = rb1 / p.kchunks_in, c1 = (rb1 % p.kchunks_in) * 64;
+      const int dy0 = taps.dy[tap0], dx0 = taps.dx[tap0], dy1 = taps.dy[tap1], dx1 = taps.dx[tap1];
+      const int m0 = taps.map[tap0], m1 = taps.map[tap1];
+      const int pt0 = split * per_split;
+      const int pt1 = min(pt0 + per_split, n_ptiles);
+      int x0 = (pt0 % p.tiles_w) * p.bw;
+      int y0 = ((pt0 / p.tiles_w) % p.tiles_h) * p.bh;
+      int n0 = (pt0 / (p.tiles_w * p.tiles_h)) * p.bn;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + ps.stage * C::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
           tma_load_4d(&maps.a[m0], &full_bar[ps.stage], sa, c0, x0 + dx0, y0 + dy0, n0);
@@ -637,43 +649,51 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
             tma_load_4d(&maps.b, &full_bar[ps.stage], sa + kABytes + j * 8192, nt * BLOCK_N + j * 64, x0, y0, n0);
-          ps.advance<C::kStages>();
+        }
+        __syncwarp();
+        ps.advance<C::kStages>();
+        // next pixel box (w fastest, then h, then n) without divisions
+        x0 += p.bw;
+        if (x0 >= p.tiles_w * p.bw) {
+          x0 = 0;
+          y0 += p.bh;
+          if (y0 >= p.tiles_h * p.bh) { y0 = 0; n0 += p.bn; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      PipeState ps;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 1, 1);
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int split = item / (p.n_tiles * p.n_rbp);
-        const int pt0 = split * per_split;
-        const int pt1 = min(pt0 + per_split, n_ptiles);
-        const int nsteps = pt1 - pt0;
-        if (nsteps <= 0) continue;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    PipeState ps;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 1, 1);
+    const uint32_t smem_lo = smem_u32(smem) >> 4;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int split = item / (p.n_tiles * p.n_rbp);
+      const int pt0 = split * per_split;
+      const int pt1 = min(pt0 + per_split, n_ptiles);
+      const int nsteps = pt1 - pt0;
+      if (nsteps <= 0) continue;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int ks = 0; ks < nsteps; ++ks) {
+        mbar_wait(&full_bar[ps.stage], ps.phase);
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int ks = 0; ks < nsteps; ++ks) {
-          mbar_wait(&full_bar[ps.stage], ps.phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + ps.stage * C::kStageBytes);
-          const uint32_t b_addr = a_addr + kABytes;
+        if (elect_one()) {
+          const uint32_t a_lo = smem_lo + (uint32_t)ps.stage * (uint32_t)(C::kStageBytes >> 4);
+          const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // 16 pixels per MMA
-            const uint64_t ad = make_smem_desc(a_addr + k * 2048, 8192, 1024);
-            const uint64_t bd = make_smem_desc(b_addr + k * 2048, 8192, 1024);
-            umma_f16(d_addr, ad, bd, idesc, (ks | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)   // 16 pixels (2048 B = 128 units) per MMA
+            umma_f16(d_addr, kDescMNMajor | (uint64_t)(a_lo + 128 * k), kDescMNMajor | (uint64_t)(b_lo + 128 * k), idesc,
+                     (ks | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[ps.stage]);
           if (ks == nsteps - 1) umma_commit(&tfull_bar[acc]);
-          ps.advance<C::kStages>();
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        ps.advance<C::kStages>();
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else {
     const int q = warp & 3;
@@ -963,7 +983,6 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
   p.N = N; p.H = H; p.W = W;
   p.tiles_w = ceil_div(W, kSlabWV); p.tiles_h = H / kSlabH;
   p.n_tiles = Cn / block_n; p.kchunks = Ck / 64; p.ldo = Cn;
-  p.base_offset_mode = getenv("SEGK_SLAB_BO") ? atoi(getenv("SEGK_SLAB_BO")) : 1;
   p.out = y; p.out_f32 = out_f32; p.bias = bias; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask;
   p.scale = scale; p.relu = relu;
   const int total = N * p.tiles_h * p.tiles_w * p.n_tiles;

@@ -96,6 +96,5 @@ def run_slab(bo_mode, n=1, h=8, w=64, ci=64, co=64):
 
 
 if __name__ == "__main__":
-    run_slab(1)
     run_slab(0)
-    run_slab(1, 2, 16, 96, 128, 128)
+    run_slab(0, 2, 16, 96, 128, 128)
