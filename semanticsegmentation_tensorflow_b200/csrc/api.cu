@@ -39,6 +39,7 @@ int segk_create(int device, segk_ctx** out) {
 
 int segk_destroy(segk_ctx* ctx) {
   if (ctx && ctx->ws) cudaFree(ctx->ws);
+  if (ctx && ctx->ws2) cudaFree(ctx->ws2);
   delete ctx;
   return SEGK_OK;
 }

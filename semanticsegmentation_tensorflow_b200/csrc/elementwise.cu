@@ -409,26 +409,39 @@ __global__ void __launch_bounds__(kThreads) bias_grad_bf16x8_kernel(const uint4*
     for (int k = 1; k < R; ++k)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += sh[threadIdx.x + k * cpb][j];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(db + cg * 8 + j, acc[j]);
+    // per-block partial row: db is [gridDim.x][C] here (summed in fixed order by reduce_rows_kernel).
+    // Atomics onto C addresses from hundreds of blocks serialise in L2 (~0.5 us per link of the chain).
+    float* out = db + (int64_t)blockIdx.x * (C8 * 8) + cg * 8;
+    *reinterpret_cast<float4*>(out) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(out + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
   }
 }
 
-// BiasAddGrad for fp32 [rows][C] with C in {1,2,4} (the logits gradient): float4 loads.
-__global__ void __launch_bounds__(kThreads) bias_grad_f32_small_kernel(const float4* __restrict__ dy,
-                                                                        float* __restrict__ db, int64_t n4, int C) {
-  __shared__ float sh[32];
-  float a[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 v = __ldg(dy + i);
-    a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+// out[c] = sum_r part[r][c] in a fixed order: block = 32 channels x 8 row lanes (independent
+// accumulators keep 4 loads in flight per thread), then a shared-memory tree over the row lanes.
+__global__ void __launch_bounds__(kThreads) reduce_rows_kernel(const float* __restrict__ part,
+                                                                float* __restrict__ out, int rows, int C) {
+  __shared__ float sh[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < C) {
+    int r = rl;
+    for (; r + 24 < rows; r += 32) {
+      a0 += part[(int64_t)r * C + c];
+      a1 += part[(int64_t)(r + 8) * C + c];
+      a2 += part[(int64_t)(r + 16) * C + c];
+      a3 += part[(int64_t)(r + 24) * C + c];
+    }
+    for (; r < rows; r += 8) a0 += part[(int64_t)r * C + c];
   }
-  // element j of every float4 belongs to channel j % C
-  if (C == 1) { a[0] += a[1] + a[2] + a[3]; }
-  else if (C == 2) { a[0] += a[2]; a[1] += a[3]; }
-  for (int c = 0; c < C; ++c) {
-    const float t = block_sum(a[c], sh);
-    if (threadIdx.x == 0) atomicAdd(db + c, t);
+  sh[rl][cl] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][cl];
+    out[c] = t;
   }
 }
 
@@ -558,7 +571,8 @@ int segk_confusion_matrix(segk_ctx* ctx, const uint8_t* gt, const uint8_t* pred,
                           int64_t npix, void* stream) {
   SEGK_REQUIRE(ctx, gt && pred && cm && npix > 0, "confusion: bad args");
   SEGK_REQUIRE(ctx, (((uintptr_t)gt | (uintptr_t)pred) & 15) == 0, "confusion: 16-byte alignment");
-  confusion_kernel<<<stream_grid(ctx, (npix + 15) / 16), kThreads, 0, (cudaStream_t)stream>>>(
+  // 2 blocks / SM: each block ends with 4 global atomics on the same 4 counters (serialised in L2)
+  confusion_kernel<<<stream_grid(ctx, (npix + 15) / 16, 2), kThreads, 0, (cudaStream_t)stream>>>(
       gt, pred, (unsigned long long*)cm, npix);
   SEGK_LAUNCHED(ctx, "confusion");
   return SEGK_OK;
@@ -601,25 +615,34 @@ int segk_bias_grad(segk_ctx* ctx, const void* dy, int dy_is_f32, float* db, int6
                    void* stream) {
   SEGK_REQUIRE(ctx, dy && db && rows > 0 && C > 0, "bias_grad: bad args");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * C, st);
-  if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "bias_grad memset: %s", cudaGetErrorString(e));
   if (!dy_is_f32 && C % 8 == 0 && (((uintptr_t)dy) & 15) == 0) {
     const int C8 = C / 8;
     const int cpb = C8 < kThreads ? C8 : kThreads;
     if (kThreads % cpb == 0 && C8 % cpb == 0) {
       const int R = kThreads / cpb;
       const int gy = C8 / cpb;
-      // ~2 blocks per SM in total: every block ends with one atomicAdd per channel, and atomics on
-      // the same few addresses serialise in L2 (1184 blocks x 512 channels ran at 0.46 TB/s)
       int64_t gx = ceil_div64(rows, (int64_t)R * 4);
-      const int64_t cap = ceil_div64((int64_t)ctx->sm_count * 2, gy);
+      const int64_t cap = ceil_div64((int64_t)ctx->sm_count * 4, gy);
       if (gx > cap) gx = cap;
       if (gx < 1) gx = 1;
-      bias_grad_bf16x8_kernel<<<dim3((unsigned)gx, gy), kThreads, 0, st>>>((const uint4*)dy, db, rows, C8);
+      const size_t need = sizeof(float) * (size_t)gx * C;
+      if (ctx->ws2_bytes < need) {
+        if (ctx->ws2) cudaFree(ctx->ws2);
+        ctx->ws2 = nullptr;
+        ctx->ws2_bytes = 0;
+        const size_t want = need < (size_t)(8 << 20) ? (size_t)(8 << 20) : need;
+        if (cudaMalloc(&ctx->ws2, want) != cudaSuccess) return segk_fail(ctx, SEGK_ENOMEM, "bias_grad workspace");
+        ctx->ws2_bytes = want;
+      }
+      bias_grad_bf16x8_kernel<<<dim3((unsigned)gx, gy), kThreads, 0, st>>>((const uint4*)dy, (float*)ctx->ws2, rows, C8);
       SEGK_LAUNCHED(ctx, "bias_grad_bf16x8");
+      reduce_rows_kernel<<<ceil_div(C, 32), kThreads, 0, st>>>((const float*)ctx->ws2, db, (int)gx, C);
+      SEGK_LAUNCHED(ctx, "bias_grad_reduce");
       return SEGK_OK;
     }
   }
+  cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * C, st);
+  if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "bias_grad memset: %s", cudaGetErrorString(e));
   if (dy_is_f32 && (C == 1 || C == 2 || C == 4) && (rows * C) % 4 == 0 && (((uintptr_t)dy) & 15) == 0) {
     const int64_t n4 = rows * C / 4;
     bias_grad_f32_small_kernel<<<stream_grid(ctx, n4, 4), kThreads, 0, st>>>((const float4*)dy, db, n4, C);

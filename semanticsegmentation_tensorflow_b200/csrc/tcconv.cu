@@ -39,6 +39,17 @@ struct Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// wgrad ring: a stage holds kPB 64-pixel boxes, so one barrier round-trip feeds 4*kPB MMAs
+template <int BLOCK_N>
+struct WCfg {
+  static constexpr int kPB = BLOCK_N == 256 ? 1 : 2;
+  static constexpr int kBoxBytes = kABytes + BLOCK_N * 128;      // one pixel box: A 2x8 KB + B BLOCK_N/64 x 8 KB
+  static constexpr int kStageBytes = kPB * kBoxBytes;
+  static constexpr int kStages = kSmemBudget / kStageBytes;      // 256:4  128:3  64:4
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
 // UMMA shared-memory descriptor minus the start address (tc_common.cuh make_smem_desc): SWIZZLE_128B,
 // version 1, SBO = 1024 B; K-major: LBO field 1 (ignored); MN-major: LBO = 8192 B between 64-wide blocks.
 constexpr uint64_t kDescKMajor = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
@@ -346,9 +357,13 @@ constexpr int kSlabBytes = 25600;                          // 194 rows * 128 B r
 
 template <int BLOCK_N>
 struct SlabCfg {
-  static constexpr int kBBytes = BLOCK_N * 128;
+  // weight tiles travel in groups of kGroup taps per ring stage: one barrier round-trip then feeds
+  // 4*kGroup MMAs (with BLOCK_N = 64 a single tap is only 128 tensor cycles, less than the wait costs)
+  static constexpr int kGroup = BLOCK_N == 256 ? 1 : 3;
+  static constexpr int kTapBytes = BLOCK_N * 128;
+  static constexpr int kBBytes = kGroup * kTapBytes;
   static constexpr int kAStages = BLOCK_N == 256 ? 2 : 3;
-  static constexpr int kBStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 7 : 12);
+  static constexpr int kBStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 3 : 4);
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kSmemBytes = kAStages * kSlabBytes + kBStages * kBBytes + 1024 + 512;
 };
@@ -423,11 +438,14 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
         }
         __syncwarp();
         pa.advance<C::kAStages>();
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tg = 0; tg < 9; tg += C::kGroup) {
           mbar_wait(&emptyB[pb.stage], pb.phase ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(&fullB[pb.stage], (uint32_t)C::kBBytes);
-            tma_load_3d(&maps.b, &fullB[pb.stage], smem_b + pb.stage * C::kBBytes, kc * kBlockK, nt * BLOCK_N, tap);
+#pragma unroll
+            for (int j = 0; j < C::kGroup; ++j)
+              tma_load_3d(&maps.b, &fullB[pb.stage], smem_b + pb.stage * C::kBBytes + j * C::kTapBytes, kc * kBlockK,
+                          nt * BLOCK_N, tg + j);
           }
           __syncwarp();
           pb.advance<C::kBStages>();
@@ -448,19 +466,24 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
         mbar_wait(&fullA[pa.stage], pa.phase);
         const uint32_t slab_lo = a_lo0 + (uint32_t)pa.stage * (uint32_t)(kSlabBytes >> 4);
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
+        for (int tg = 0; tg < 9; tg += C::kGroup) {
           mbar_wait(&fullB[pb.stage], pb.phase);
           tc_fence_after();
           if (elect_one()) {
-            // tap (ty,tx) = slab row offset ty*32 + tx; one row = 128 B = 8 descriptor units
-            const uint32_t a_lo = slab_lo + (uint32_t)((tap / 3) * kSlabP + (tap % 3)) * 8u;
             const uint32_t b_lo = b_lo0 + (uint32_t)pb.stage * (uint32_t)(C::kBBytes >> 4);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_f16(d_addr, kDescKMajor | (uint64_t)(a_lo + 2 * k), kDescKMajor | (uint64_t)(b_lo + 2 * k), idesc,
-                       (kc | tap | k) != 0 ? 1u : 0u);
+            for (int j = 0; j < C::kGroup; ++j) {
+              const int tap = tg + j;
+              // tap (ty,tx) = slab row offset ty*32 + tx; one row = 128 B = 8 descriptor units
+              const uint32_t a_lo = slab_lo + (uint32_t)((tap / 3) * kSlabP + (tap % 3)) * 8u;
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_f16(d_addr, kDescKMajor | (uint64_t)(a_lo + 2 * k),
+                         kDescKMajor | (uint64_t)(b_lo + j * (C::kTapBytes >> 4) + 2 * k), idesc,
+                         (kc | tap | k) != 0 ? 1u : 0u);
+            }
             umma_commit(&emptyB[pb.stage]);
-            if (tap == 8) {
+            if (tg + C::kGroup >= 9) {
               umma_commit(&emptyA[pa.stage]);
               if (kc == p.kchunks - 1) umma_commit(&tfull_bar[acc]);
             }
@@ -589,7 +612,7 @@ struct WgradParams {
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const TapTable taps) {
-  using C = Cfg<BLOCK_N>;
+  using C = WCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
@@ -624,7 +647,6 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
 
   if (warp == 0) {
     PipeState ps;
-    constexpr uint32_t tx_bytes = (uint32_t)C::kStageBytes;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int nt = item % p.n_tiles;
       const int rbp = (item / p.n_tiles) % p.n_rbp;
@@ -639,26 +661,30 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
       int x0 = (pt0 % p.tiles_w) * p.bw;
       int y0 = ((pt0 / p.tiles_w) % p.tiles_h) * p.bh;
       int n0 = (pt0 / (p.tiles_w * p.tiles_h)) * p.bn;
-      for (int pt = pt0; pt < pt1; ++pt) {
+      for (int pt = pt0; pt < pt1; pt += C::kPB) {
+        const int nb = min(C::kPB, pt1 - pt);
         mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
-        if (elect_one()) {
-          uint8_t* sa = smem + ps.stage * C::kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
-          tma_load_4d(&maps.a[m0], &full_bar[ps.stage], sa, c0, x0 + dx0, y0 + dy0, n0);
-          tma_load_4d(&maps.a[m1], &full_bar[ps.stage], sa + 8192, c1, x0 + dx1, y0 + dy1, n0);
+        const bool leader = elect_one();
+        if (leader) mbar_arrive_expect_tx(&full_bar[ps.stage], (uint32_t)(nb * C::kBoxBytes));
+        for (int bi = 0; bi < nb; ++bi) {
+          if (leader) {
+            uint8_t* sa = smem + ps.stage * C::kStageBytes + bi * C::kBoxBytes;
+            tma_load_4d(&maps.a[m0], &full_bar[ps.stage], sa, c0, x0 + dx0, y0 + dy0, n0);
+            tma_load_4d(&maps.a[m1], &full_bar[ps.stage], sa + 8192, c1, x0 + dx1, y0 + dy1, n0);
 #pragma unroll
-          for (int j = 0; j < BLOCK_N / 64; ++j)
-            tma_load_4d(&maps.b, &full_bar[ps.stage], sa + kABytes + j * 8192, nt * BLOCK_N + j * 64, x0, y0, n0);
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_4d(&maps.b, &full_bar[ps.stage], sa + kABytes + j * 8192, nt * BLOCK_N + j * 64, x0, y0, n0);
+          }
+          // next pixel box (w fastest, then h, then n) without divisions
+          x0 += p.bw;
+          if (x0 >= p.tiles_w * p.bw) {
+            x0 = 0;
+            y0 += p.bh;
+            if (y0 >= p.tiles_h * p.bh) { y0 = 0; n0 += p.bn; }
+          }
         }
         __syncwarp();
         ps.advance<C::kStages>();
-        // next pixel box (w fastest, then h, then n) without divisions
-        x0 += p.bw;
-        if (x0 >= p.tiles_w * p.bw) {
-          x0 = 0;
-          y0 += p.bh;
-          if (y0 >= p.tiles_h * p.bh) { y0 = 0; n0 += p.bn; }
-        }
       }
     }
   } else if (warp == 1) {
@@ -671,23 +697,26 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
       const int split = item / (p.n_tiles * p.n_rbp);
       const int pt0 = split * per_split;
       const int pt1 = min(pt0 + per_split, n_ptiles);
-      const int nsteps = pt1 - pt0;
-      if (nsteps <= 0) continue;
+      const int nboxes = pt1 - pt0;
+      if (nboxes <= 0) continue;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
-      for (int ks = 0; ks < nsteps; ++ks) {
+      for (int b0 = 0; b0 < nboxes; b0 += C::kPB) {
+        const int nb = min(C::kPB, nboxes - b0);
         mbar_wait(&full_bar[ps.stage], ps.phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a_lo = smem_lo + (uint32_t)ps.stage * (uint32_t)(C::kStageBytes >> 4);
-          const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
+          for (int bi = 0; bi < nb; ++bi) {
+            const uint32_t a_lo = smem_lo + (uint32_t)(ps.stage * C::kStageBytes + bi * C::kBoxBytes) / 16u;
+            const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // 16 pixels (2048 B = 128 units) per MMA
-            umma_f16(d_addr, kDescMNMajor | (uint64_t)(a_lo + 128 * k), kDescMNMajor | (uint64_t)(b_lo + 128 * k), idesc,
-                     (ks | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)   // 16 pixels (2048 B = 128 units) per MMA
+              umma_f16(d_addr, kDescMNMajor | (uint64_t)(a_lo + 128 * k), kDescMNMajor | (uint64_t)(b_lo + 128 * k),
+                       idesc, (b0 | bi | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&empty_bar[ps.stage]);
-          if (ks == nsteps - 1) umma_commit(&tfull_bar[acc]);
+          if (b0 + C::kPB >= nboxes) umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
         ps.advance<C::kStages>();
@@ -931,7 +960,7 @@ int launch_igemm(segk_ctx* ctx, int block_n, const TensorMaps& maps, const Igemm
 template <int BLOCK_N>
 int launch_wgrad_t(segk_ctx* ctx, const TensorMaps& maps, const WgradParams& p, const TapTable& taps, int grid,
                    cudaStream_t st) {
-  using C = Cfg<BLOCK_N>;
+  using C = WCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);

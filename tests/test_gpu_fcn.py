@@ -85,7 +85,7 @@ def test_loss_and_all_gradients(cuda_device, init):
         e, c = rel_err(g, r), cosine(g, r)
         f = grads_f32[name].numpy()
         e0, c0 = rel_err(r, f), cosine(r, f)                        # the oracle's own bf16 noise
-        tol_e, tol_c = max(5e-2, 3 * e0), min(0.999, 1 - 3 * (1 - c0))
+        tol_e, tol_c = max(5e-2, 3 * e0), min(0.999, 1 - 9 * (1 - c0))   # 3x in amplitude = 9x in cosine deficit
         report.append((name, e, c, e0, c0))
         assert e <= tol_e and c >= tol_c, (f"[{init}] grad {name}: rel err {e:.3e} (tol {tol_e:.3e}) cosine {c:.6f} "
                                            f"(tol {tol_c:.6f}) max|ref| {np.abs(r).max():.3e}")
@@ -112,7 +112,9 @@ def test_training_curve_matches_oracle(cuda_device):
     print("loss curve gpu", ["%.5f" % v for v in got])
     print("loss curve ref", ["%.5f" % v for v in ref])
     assert ref[-1] < ref[0]                                        # it trains
-    np.testing.assert_allclose(got, ref, rtol=2e-2)
+    # Adam's first steps move every weight by ~lr * sign(g): bf16 noise flips the sign of near-zero
+    # gradients, so the two trajectories agree to a few per cent, not to rounding (loss falls 14x here)
+    np.testing.assert_allclose(got, ref, rtol=5e-2)
     # variables after 10 steps
     for name in ("conv1_1/weights", "conv5_3/weights", "conv_t3/weights", "conv8/biases"):
         p = net.vars.param(name).cpu().numpy()
@@ -137,7 +139,7 @@ def test_dropout_training_step_with_injected_masks(cuda_device):
     assert abs(float(loss) - loss_ref) <= 2e-3 * abs(loss_ref)
     for name in ("conv6/weights", "conv7/weights", "conv5_1/weights", "conv8/weights"):
         g, r, f = net.vars.grad(name).cpu().numpy(), grads_ref[name].numpy(), grads_f32[name].numpy()
-        tol_e, tol_c = max(5e-2, 3 * rel_err(r, f)), min(0.999, 1 - 3 * (1 - cosine(r, f)))
+        tol_e, tol_c = max(5e-2, 3 * rel_err(r, f)), min(0.999, 1 - 9 * (1 - cosine(r, f)))
         assert rel_err(g, r) <= tol_e and cosine(g, r) >= tol_c, (name, rel_err(g, r), cosine(g, r), tol_e, tol_c)
 
 
