@@ -445,6 +445,24 @@ __global__ void __launch_bounds__(kThreads) reduce_rows_kernel(const float* __re
   }
 }
 
+// BiasAddGrad for fp32 [rows][C] with C in {1,2,4} (the logits gradient): float4 loads.
+__global__ void __launch_bounds__(kThreads) bias_grad_f32_small_kernel(const float4* __restrict__ dy,
+                                                                        float* __restrict__ db, int64_t n4, int C) {
+  __shared__ float sh[32];
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(dy + i);
+    a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+  }
+  // element j of every float4 belongs to channel j % C
+  if (C == 1) { a[0] += a[1] + a[2] + a[3]; }
+  else if (C == 2) { a[0] += a[2]; a[1] += a[3]; }
+  for (int c = 0; c < C; ++c) {
+    const float t = block_sum(a[c], sh);
+    if (threadIdx.x == 0) atomicAdd(db + c, t);
+  }
+}
+
 // w fp32 [T][A][B] -> cp bf16 [T'][A][B] (cast) and/or tr bf16 [T][B][A] (per-tap transpose);
 // T' = T-1-t when rev_cp (rot180 of the filter for dgrad).
 __global__ void __launch_bounds__(kThreads) pack_weights_kernel(const float* __restrict__ w,
