@@ -131,7 +131,7 @@ def run_reference(args):
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "restated reference (torch-CPU fp32 with TF-1.15 op semantics), not TensorFlow: TF is not installable in this image",
     }
-    print(json.dumps(line), flush=True)
+    args.emit(json.dumps(line))
 
 
 def run_gpu(args):
@@ -277,23 +277,99 @@ def run_gpu(args):
         "cpu_baseline": cpu_baseline,
         "final_loss": final_loss,
     }
-    print(json.dumps(line), flush=True)
+    args.emit(json.dumps(line))
+
+
+def run_infer(args):
+    """BASELINE configs[3]: full-resolution inference, batch 16, one GPU; host images in, road mask out."""
+    import torch
+    from semanticsegmentation_tensorflow_b200 import build_library
+    from semanticsegmentation_tensorflow_b200.fcn import FCN
+    build_library()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    h, w, B = 384, 1248, 16
+    gen = torch.Generator().manual_seed(7)
+    host_x = torch.randint(0, 256, (B, h, w, CIN), dtype=torch.uint8, generator=gen).pin_memory()
+    net = FCN(host_x.to(dev), 1.0, NCLS, init="device", seed=1234)
+    mask_host = torch.empty((B, h, w), dtype=torch.uint8).pin_memory()
+    for _ in range(max(args.warmup, 3)):
+        net.infer(host_x)
+    torch.cuda.synchronize()
+    lat = []
+    launches0 = net.ops.ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    for _ in range(args.steps):
+        e0.record()
+        prob, mask = net.infer(host_x)              # H2D of 16 images inside
+        mask_host.copy_(mask, non_blocking=True)    # D2H of the road masks
+        e1.record()
+        e1.synchronize()
+        lat.append(e0.elapsed_time(e1))
+    t_all1.record()
+    torch.cuda.synchronize()
+    total_ms = t_all0.elapsed_time(t_all1)
+    lat.sort()
+    fwd_gflop = 428.29
+    line = {
+        "metric": "inference images/sec FCN-8s 384x1248", "value": B * args.steps / (total_ms / 1e3), "unit": UNIT,
+        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "FCN-8s 2-class forward + softmax + road mask, batch 16, 384x1248x3 (BASELINE configs[3])",
+                   "global_batch": B, "keep_prob": 1.0},
+        "latency_ms": {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(0.99 * len(lat)))], "min": lat[0]},
+        "e2e": {"value": B * args.steps / (total_ms / 1e3), "unit": UNIT,
+                "h2d_bytes_per_step": int(host_x.numel()), "d2h_bytes_per_step": int(mask_host.numel())},
+        "gpu_launches": int(net.ops.ctx.launches - launches0),
+        "tensor_util_step": {"fwd_tflops": fwd_gflop * 1e9 * B * args.steps / (total_ms / 1e3) / 1e12,
+                             "flops_per_image": fwd_gflop * 1e9, "convention": "valid-tap forward"},
+    }
+    args.emit(json.dumps(line))
+
+
+class _StdoutGuard:
+    """Everything except the final JSON line goes to stderr (NCCL / torchrun print banners on fd 1)."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers-out", default=None, help="write the per-call (per-layer) timing table here")
+    ap.add_argument("--workload", default="train", choices=["train", "infer"],
+                    help="train = BASELINE configs[1] (default, the driver's metric); infer = configs[3]: "
+                         "FCN-8s forward + softmax + road mask at 384x1248, batch 16 (throughput and latency)")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_gpu(args)
+    with _StdoutGuard() as out:
+        args.emit = out.emit
+        if args.impl == "reference":
+            run_reference(args)
+        elif args.workload == "infer":
+            run_infer(args)
+        else:
+            run_gpu(args)
     try:
         import torch.distributed as dist
         if dist.is_initialized():

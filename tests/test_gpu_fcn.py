@@ -157,3 +157,26 @@ def test_inference_softmax_and_road_mask(cuda_device):
     assert np.abs(prob.cpu().numpy() - p_ref).max() <= 1e-6
     assert np.array_equal(mask.cpu().numpy(), (lg[..., 1] > lg[..., 0]).numpy().astype(np.uint8))
     assert mask.shape == (N, H, W)
+
+
+def test_full_resolution_inference_384x1248(cuda_device):
+    """BASELINE configs[3] shape: FCN-8s forward at 384x1248 with the real fc=4096 head, batch 1,
+    vs the fp32-arithmetic oracle mirroring bf16 storage (logits rtol 2e-2, margin-conditioned argmax
+    agreement >= 99.9 %), plus the softmax / road-mask epilogue (FCN.py:229,204-206)."""
+    from semanticsegmentation_tensorflow_b200.fcn import FCN
+    n, h, w = 1, 384, 1248
+    variables = init_variables(cin=3, ncls=2, fc=4096, seed=1234, init="ref")
+    x, _ = synthetic_batch(n, h, w, seed=7)
+    net = FCN(torch.as_tensor(x).to(cuda_device), 1.0, 2, variables=variables)
+    prob, mask = net.infer()
+    torch.cuda.synchronize()
+    orc = FCN8sOracle(variables, bf16_storage=True)
+    pred_ref, logits_ref = orc.forward(x)
+    lr = logits_ref.detach().numpy()
+    lg = net.logits.cpu().numpy()
+    assert rel_err(lg, lr) <= 2e-2
+    margin = np.abs(lr[..., 1] - lr[..., 0])
+    sel = margin >= 0.01 * np.abs(lr).mean()
+    agree = mask.cpu().numpy() == pred_ref.numpy()[..., 0]
+    assert agree[sel].mean() >= 0.999, agree[sel].mean()
+    assert abs(float(prob.sum()) - n * h * w) <= 1e-3 * n * h * w        # softmax rows sum to 1
