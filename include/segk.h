@@ -104,7 +104,7 @@ int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw,
  *      conv_t3 Cout=2) ----------------------------------------------------------------- */
 /* conv_layer forward for ragged channel counts.  x_dtype: 0 = bf16, 2 = u8 (raw image,
  * FCN.py:312).  w fp32 HWIO, output bf16.  Supported: K = kh*kw*Cin <= 64 (any Cout), or
- * 1x1 with Cout in {2,4,8} and Cin % 8 == 0. */
+ * 1x1 with Cout in {2,4,8} and Cin % 8 == 0 (this one also with SEGK_EPI_OUT_F32: fp32 logits). */
 int segk_conv2d_small_fwd(segk_ctx* ctx, const void* x, int x_dtype, const float* w,
                           const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
                           int kh, int kw, unsigned flags, void* stream);
@@ -150,6 +150,26 @@ int segk_deconv_col2im(segk_ctx* ctx, const float* yp, const float* bias, const 
 int segk_pack_matrix(segk_ctx* ctx, const float* w, void* cp, void* tr, int T, int A, int B,
                      void* stream);
 
+/* ---- shared-helper layers of the secondary builders (Network/utils/utils.py) -------------- */
+/* Batch_Normalization (utils.py:300-301) is tf.layers.batch_normalization with training=False and
+ * never-updated moving stats: y = gamma * x / sqrt(1 + 1e-3) + beta.  The scale is folded into the
+ * packed conv weights (out = in * scale[c] * mult, e.g. W * gamma / sqrt(1+eps)) and back out of the
+ * weight gradient; beta is the conv epilogue's bias.  in/out fp32 [rows][C], out may alias in. */
+int segk_scale_columns(segk_ctx* ctx, const float* in, const float* scale, float mult, float* out,
+                       int64_t rows, int C, void* stream);
+/* dgamma[c] = sum_r dz[r][c] * (y[r][c] - beta[c]) / gamma[c]  (dz, y bf16 [rows][C]; dz already
+ * carries the ReLU mask, so (y - beta)/gamma' is the raw conv output wherever dz != 0).
+ * workspace: >= 4 * C * min(rows/4+1, 4*SMs) bytes (8 MB always suffices for C <= 4096). */
+int segk_bn_gamma_grad(segk_ctx* ctx, const void* dz, const void* y, const float* beta,
+                       const float* gamma, float* dgamma, void* workspace, size_t workspace_bytes,
+                       int64_t rows, int C, void* stream);
+/* Concat (utils.py:332) and its gradient: dst[r][coff_dst + c] (=, or += when accumulate)
+ * src[r][coff_src + c] for c < C, zeroed where mask[r][c] <= 0 (mask dense [rows][C] or NULL =
+ * the fused ReluGrad of the producer).  bf16, all channel counts multiples of 8. */
+int segk_channel_copy(segk_ctx* ctx, const void* src, int ld_src, int coff_src, void* dst,
+                      int ld_dst, int coff_dst, const void* mask, int accumulate, int64_t rows, int C,
+                      void* stream);
+
 /* ---- weight layout packing (fp32 master -> bf16 kernel layouts) ------------------------ */
 /* w[kh,kw,Cin,Cout] fp32 (HWIO, FCN.py:125) -> wk[tap][Cout][Cin] bf16 (fwd) and
  * wd[ntaps-1-tap][Cin][Cout] bf16 (dgrad: taps reversed = rot180).  Either may be NULL. */
@@ -167,9 +187,10 @@ int segk_pack_deconv_weights(segk_ctx* ctx, const float* w, void* wk, void* wd, 
 int segk_maxpool2x2_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int N, int H, int W,
                         int C, void* stream);
 /* MaxPoolGrad from the stored index, fused with the ReluGrad of the pooled activation:
- * dx[n,y,x,c] = (idx==k ? dy : 0) * [act > 0]  (act may be NULL: no mask). */
+ * dx[n,y,x,c] = ((idx==k ? dy : 0) + residual) * [act > 0]  (act may be NULL: no mask; residual,
+ * shape of dx or NULL, is a second gradient path into the same tensor, e.g. a skip connection). */
 int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const void* act,
-                        void* dx, int N, int H, int W, int C, void* stream);
+                        const void* residual, void* dx, int N, int H, int W, int C, void* stream);
 
 /* tf.nn.dropout (FCN.py:165-167): y = x * keep_mask / keep_prob.  mask (u8 0/1) is used
  * when non-NULL (parity runs); otherwise Philox4x32-10(seed, element index). Same call is

@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const uint4* __re
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const uint4* __restrict__ dy,
                                                                const uint2* __restrict__ idx,
                                                                const uint4* __restrict__ act,
+                                                               const uint4* __restrict__ res,
                                                                uint4* __restrict__ dx, int N, int H,
                                                                int W, int C8) {
   const int OH = H >> 1, OW = W >> 1;
@@ -98,6 +99,16 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const uint4* __re
         uint32_t lo = (k_lo == (uint32_t)k && af.x > 0.f) ? (gw & 0xffffu) : 0u;
         uint32_t hi = (k_hi == (uint32_t)k && af.y > 0.f) ? (gw & 0xffff0000u) : 0u;
         o[j] = lo | hi;
+      }
+      if (res) {   // second gradient path into the same tensor (added before the mask)
+        const uint4 rv = __ldg(res + offs[k]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 af = unpack_bf16x2((&a.x)[j]);
+          const float2 rf = unpack_bf16x2((&rv.x)[j]);
+          const float2 of = unpack_bf16x2(o[j]);
+          o[j] = pack_bf16x2(af.x > 0.f ? of.x + rf.x : 0.f, af.y > 0.f ? of.y + rf.y : 0.f);
+        }
       }
       dx[offs[k]] = make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -526,14 +537,14 @@ int segk_maxpool2x2_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int
   return SEGK_OK;
 }
 
-int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const void* act, void* dx,
-                        int N, int H, int W, int C, void* stream) {
+int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const void* act,
+                        const void* residual, void* dx, int N, int H, int W, int C, void* stream) {
   SEGK_REQUIRE(ctx, dy && idx && dx, "maxpool_bwd: null pointer");
   SEGK_REQUIRE(ctx, N > 0 && H >= 2 && W >= 2 && (H % 2 == 0) && (W % 2 == 0) && C % 8 == 0,
                "maxpool_bwd: need even H,W and C%%8==0 (got %dx%dx%dx%d)", N, H, W, C);
   const int64_t items = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
   maxpool_bwd_kernel<<<stream_grid(ctx, items), kThreads, 0, (cudaStream_t)stream>>>(
-      (const uint4*)dy, (const uint2*)idx, (const uint4*)act, (uint4*)dx, N, H, W, C / 8);
+      (const uint4*)dy, (const uint2*)idx, (const uint4*)act, (const uint4*)residual, (uint4*)dx, N, H, W, C / 8);
   SEGK_LAUNCHED(ctx, "maxpool_bwd");
   return SEGK_OK;
 }

@@ -136,6 +136,102 @@ __global__ void __launch_bounds__(kThreads) col2im_kernel(const float* __restric
   }
 }
 
+
+// out[r][c] = in[r][c] * scale[c] * mult   (BN-affine gamma/sqrt(1+eps) folded into conv weights and
+// back out of their gradients, utils.py:300-301)
+__global__ void __launch_bounds__(kThreads) scale_columns_kernel(const float* __restrict__ in,
+                                                                 const float* __restrict__ scale, float mult,
+                                                                 float* __restrict__ out, int64_t n, int C) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = in[i] * __ldg(scale + (int)(i % C)) * mult;
+}
+
+// partial[b][c]      = sum over the block's rows of dz[r][c] * (y[r][c] - beta[c])
+// (fixed-order second stage: bn_gamma_finish_kernel divides by gamma)
+__global__ void __launch_bounds__(kThreads) bn_gamma_partial_kernel(const uint4* __restrict__ dz,
+                                                                    const uint4* __restrict__ y,
+                                                                    const float* __restrict__ beta,
+                                                                    float* __restrict__ partial, int64_t rows, int C8) {
+  __shared__ float sh[kThreads][9];
+  const int cpb = C8 < kThreads ? C8 : kThreads;
+  const int R = kThreads / cpb;
+  const int cg = blockIdx.y * cpb + (threadIdx.x % cpb);
+  const int rl = threadIdx.x / cpb;
+  float acc[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { acc[j] = 0.f; b[j] = (cg < C8) ? __ldg(beta + cg * 8 + j) : 0.f; }
+  if (cg < C8 && rl < R) {
+    for (int64_t r = (int64_t)blockIdx.x * R + rl; r < rows; r += (int64_t)gridDim.x * R) {
+      const uint4 g = __ldg(dz + r * C8 + cg), v = __ldg(y + r * C8 + cg);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 gf = unpack_bf16x2((&g.x)[j]), vf = unpack_bf16x2((&v.x)[j]);
+        acc[2 * j] += gf.x * (vf.x - b[2 * j]);
+        acc[2 * j + 1] += gf.y * (vf.y - b[2 * j + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (rl == 0 && cg < C8) {
+    for (int k = 1; k < R; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += sh[threadIdx.x + k * cpb][j];
+    float* out = partial + (int64_t)blockIdx.x * (C8 * 8) + cg * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[j] = acc[j];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) bn_gamma_finish_kernel(const float* __restrict__ partial,
+                                                                   const float* __restrict__ gamma,
+                                                                   float* __restrict__ dgamma, int nparts, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f;
+  for (int r = 0; r < nparts; ++r) a += partial[(int64_t)r * C + c];
+  dgamma[c] = a / gamma[c];
+}
+
+// dst[r][coff_dst + c] (= or +=) src[r][coff_src + c], optionally zeroed where mask[r][c] <= 0; 8 channels/thread
+__global__ void __launch_bounds__(kThreads) channel_copy_kernel(const bf16* __restrict__ src, int ld_src, int coff_src,
+                                                                bf16* __restrict__ dst, int ld_dst, int coff_dst,
+                                                                const bf16* __restrict__ mask, int accumulate,
+                                                                int64_t rows, int C8) {
+  const int64_t total = rows * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    const int64_t r = i / C8;
+    uint4 v = *reinterpret_cast<const uint4*>(src + r * ld_src + coff_src + c);
+    uint4* d = reinterpret_cast<uint4*>(dst + r * ld_dst + coff_dst + c);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = unpack_bf16x2((&v.x)[j]);
+      f[2 * j] = t.x; f[2 * j + 1] = t.y;
+    }
+    if (accumulate) {
+      const uint4 o = *d;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16x2((&o.x)[j]);
+        f[2 * j] += t.x; f[2 * j + 1] += t.y;
+      }
+    }
+    if (mask) {
+      const uint4 m = *reinterpret_cast<const uint4*>(mask + r * (int64_t)(C8 * 8) + c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16x2((&m.x)[j]);
+        if (!(t.x > 0.f)) f[2 * j] = 0.f;
+        if (!(t.y > 0.f)) f[2 * j + 1] = 0.f;
+      }
+    }
+    *d = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -192,6 +288,53 @@ int segk_deconv_col2im(segk_ctx* ctx, const float* yp, const float* bias, const 
   else
     col2im_kernel<bf16><<<sgrid(ctx, items, 16), kThreads, 0, st>>>(yp, bias, (const bf16*)residual, (bf16*)y, N, H, W, Cout, k, s);
   SEGK_LAUNCHED(ctx, "col2im");
+  return SEGK_OK;
+}
+
+int segk_scale_columns(segk_ctx* ctx, const float* in, const float* scale, float mult, float* out, int64_t rows,
+                       int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, in && scale && out && rows > 0 && C > 0, "scale_columns: bad args");
+  const int64_t n = rows * C;
+  scale_columns_kernel<<<sgrid(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(in, scale, mult, out, n, C);
+  SEGK_LAUNCHED(ctx, "scale_columns");
+  return SEGK_OK;
+}
+
+int segk_bn_gamma_grad(segk_ctx* ctx, const void* dz, const void* y, const float* beta, const float* gamma,
+                       float* dgamma, void* workspace, size_t workspace_bytes, int64_t rows, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, dz && y && beta && gamma && dgamma && workspace && rows > 0, "bn_gamma_grad: bad args");
+  SEGK_REQUIRE(ctx, C % 8 == 0 && (C / 8 <= kThreads ? kThreads % (C / 8) == 0 : (C / 8) % kThreads == 0),
+               "bn_gamma_grad: C must be a multiple of 8 with C/8 dividing 256 (got %d)", C);
+  const int C8 = C / 8;
+  const int cpb = C8 < kThreads ? C8 : kThreads;
+  const int R = kThreads / cpb, gy = C8 / cpb;
+  int64_t gx = ceil_div64(rows, (int64_t)R * 4);
+  const int64_t cap = ceil_div64((int64_t)ctx->sm_count * 4, gy);
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  SEGK_REQUIRE(ctx, workspace_bytes >= sizeof(float) * (size_t)gx * C, "bn_gamma_grad: workspace too small (%zu < %zu)",
+               workspace_bytes, sizeof(float) * (size_t)gx * C);
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_gamma_partial_kernel<<<dim3((unsigned)gx, gy), kThreads, 0, st>>>((const uint4*)dz, (const uint4*)y, beta,
+                                                                    (float*)workspace, rows, C8);
+  SEGK_LAUNCHED(ctx, "bn_gamma_partial");
+  bn_gamma_finish_kernel<<<ceil_div(C, kThreads), kThreads, 0, st>>>((const float*)workspace, gamma, dgamma, (int)gx, C);
+  SEGK_LAUNCHED(ctx, "bn_gamma_finish");
+  return SEGK_OK;
+}
+
+int segk_channel_copy(segk_ctx* ctx, const void* src, int ld_src, int coff_src, void* dst, int ld_dst, int coff_dst,
+                      const void* mask, int accumulate, int64_t rows, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, src && dst && rows > 0 && C > 0, "channel_copy: bad args");
+  SEGK_REQUIRE(ctx, C % 8 == 0 && ld_src % 8 == 0 && ld_dst % 8 == 0 && coff_src % 8 == 0 && coff_dst % 8 == 0,
+               "channel_copy: channel counts / offsets must be multiples of 8");
+  const int64_t items = rows * (C / 8);
+  channel_copy_kernel<<<sgrid(ctx, items, 16), kThreads, 0, (cudaStream_t)stream>>>(
+      (const bf16*)src, ld_src, coff_src, (bf16*)dst, ld_dst, coff_dst, (const bf16*)mask, accumulate, rows, C / 8);
+  SEGK_LAUNCHED(ctx, "channel_copy");
   return SEGK_OK;
 }
 

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kThreads) conv_tinyk_wgrad_kernel(
 template <int CO>
 __global__ void __launch_bounds__(kThreads) conv_skinny_fwd_kernel(
     const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-    bf16* __restrict__ y, int64_t npix, int Cin, int relu) {
+    void* __restrict__ y, int64_t npix, int Cin, int relu, int out_f32) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -169,7 +169,9 @@ __global__ void __launch_bounds__(kThreads) conv_skinny_fwd_kernel(
 #pragma unroll
       for (int c = 0; c < CO; ++c) {
         float v = acc[c] + (bias ? bias[c] : 0.f);
-        y[p * CO + c] = f2bf(relu ? fmaxf(v, 0.f) : v);
+        v = relu ? fmaxf(v, 0.f) : v;
+        if (out_f32) reinterpret_cast<float*>(y)[p * CO + c] = v;
+        else reinterpret_cast<bf16*>(y)[p * CO + c] = f2bf(v);
       }
     }
   }
@@ -388,10 +390,11 @@ int segk_conv2d_small_fwd(segk_ctx* ctx, const void* x, int x_dtype, const float
   SEGK_REQUIRE(ctx, x && w && y && N > 0 && H > 0 && W > 0, "conv_small_fwd: bad args");
   SEGK_REQUIRE(ctx, x_dtype == 0 || x_dtype == 2, "conv_small_fwd: x_dtype must be 0 (bf16) or 2 (u8)");
   const int relu = (flags & SEGK_EPI_RELU) ? 1 : 0;
+  const int out_f32 = (flags & SEGK_EPI_OUT_F32) ? 1 : 0;
   const int K = kh * kw * Cin;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t npix = (int64_t)N * H * W;
-  if (K <= kTinyKMax && (kh & 1) && (kw & 1)) {
+  if (K <= kTinyKMax && (kh & 1) && (kw & 1) && !out_f32) {
     dim3 grid(sgrid(ctx, npix, 4), ceil_div(Cout, 32));
     if (x_dtype == 2)
       conv_tinyk_fwd_kernel<uint8_t><<<grid, kThreads, K * 32 * sizeof(float), st>>>(
@@ -405,11 +408,11 @@ int segk_conv2d_small_fwd(segk_ctx* ctx, const void* x, int x_dtype, const float
   if (x_dtype == 0 && kh == 1 && kw == 1 && Cin % 8 == 0 && (Cout == 2 || Cout == 4 || Cout == 8)) {
     const int grid = sgrid(ctx, npix * 32, 8);
     if (Cout == 2)
-      conv_skinny_fwd_kernel<2><<<grid, kThreads, 0, st>>>((const bf16*)x, w, bias, (bf16*)y, npix, Cin, relu);
+      conv_skinny_fwd_kernel<2><<<grid, kThreads, 0, st>>>((const bf16*)x, w, bias, y, npix, Cin, relu, out_f32);
     else if (Cout == 4)
-      conv_skinny_fwd_kernel<4><<<grid, kThreads, 0, st>>>((const bf16*)x, w, bias, (bf16*)y, npix, Cin, relu);
+      conv_skinny_fwd_kernel<4><<<grid, kThreads, 0, st>>>((const bf16*)x, w, bias, y, npix, Cin, relu, out_f32);
     else
-      conv_skinny_fwd_kernel<8><<<grid, kThreads, 0, st>>>((const bf16*)x, w, bias, (bf16*)y, npix, Cin, relu);
+      conv_skinny_fwd_kernel<8><<<grid, kThreads, 0, st>>>((const bf16*)x, w, bias, y, npix, Cin, relu, out_f32);
     SEGK_LAUNCHED(ctx, "conv_skinny_fwd");
     return SEGK_OK;
   }

@@ -30,6 +30,9 @@ class BucketedAllReduce:
 
     @classmethod
     def for_net(cls, net, group=None, layer_groups=None):
+        if hasattr(net, "nodes"):      # GraphNet: generic even-size buckets over its conv/deconv nodes
+            names = [n.name for n in net.nodes if n.kind in ("conv", "deconv")]
+            return cls(net.vars.g, P.gradient_buckets_even(net.vars.slots, names), group)
         return cls(net.vars.g, P.gradient_buckets(net.vars.slots, layer_groups), group)
 
     def begin_step(self):

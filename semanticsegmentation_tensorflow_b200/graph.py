@@ -1,0 +1,453 @@
+"""Encoder-decoder builders on the shared layer helpers of the reference (`Network/utils/utils.py`),
+executed on the same B200 kernels as FCN-8s.
+
+Helpers mirrored (same names / argument meaning, graph-building style):
+    Conv2D_Block(x, num_filters, 3, 3, batch_normalization=, relu=, name=)     utils.py:185-208 (no bias, :180)
+    Deconv2D_Block(x, shape, num_filters, output_shape, 4, 4, 2, name=)         utils.py:255-298 (no bias)
+    Batch_Normalization  -> inference-mode affine, gamma/beta trainable           utils.py:300-301
+    Max_Pooling(x, name) / Concat([a, b], axis=-1, name)                         utils.py:306,332
+
+Builders:
+    UNet(x, num_classes)   BASELINE configs[2].  The reference has no U-Net file; per SURVEY §8a row 12
+                           it is SegNet's VGG16-BN encoder (SegNet.py:30-51) with the skip-concat decoder
+                           idiom of FCDenseNet (FCDenseNet.py:141-160): Deconv2D_Block(4x4, s2) ->
+                           Concat(skip) -> Conv2D_Block..., ReLU on, 1x1 `final_conv` head.
+
+A builder returns a GraphNet with the FCN-compatible training interface (forward / loss / backward /
+vars / feed), so AdamOptimizer.minimize(net) and the data-parallel all-reduce work unchanged."""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import List
+
+import numpy as np
+import torch
+
+from . import plan as P
+from .fcn import _Feed
+from .ops import Ops, conv_flops
+
+BN_EPS = 1e-3          # tf.layers.batch_normalization default epsilon
+BN_SCALE = 1.0 / math.sqrt(1.0 + BN_EPS)   # moving_variance stays 1, moving_mean 0 (never updated)
+
+
+@dataclass
+class Node:
+    name: str
+    kind: str                       # "conv" | "deconv" | "pool" | "concat"
+    inputs: List[str] = field(default_factory=list)
+    k: int = 3
+    cout: int = 0
+    stride: int = 1
+    bias: bool = False
+    bn: bool = False
+    relu: bool = False
+    bn_scope: str = ""              # TF variable scope of the BN layer ("batch_normalization_7")
+
+
+class GraphBuilder:
+    """Collects helper calls (utils.py signatures) into a node list."""
+
+    def __init__(self):
+        self.nodes: List[Node] = []
+        self._bn = 0
+
+    def _bn_scope(self):
+        s = "batch_normalization" if self._bn == 0 else f"batch_normalization_{self._bn}"
+        self._bn += 1
+        return s
+
+    def Conv2D_Block(self, x, num_filters, filter_height=3, filter_width=3, batch_normalization=False, relu=False,
+                     name=None):
+        assert filter_height == filter_width
+        n = Node(name, "conv", [x], k=filter_height, cout=num_filters, bn=batch_normalization, relu=relu)
+        if batch_normalization:
+            n.bn_scope = self._bn_scope()
+        self.nodes.append(n)
+        return name
+
+    def Deconv2D_Block(self, x, num_filters_out, filter_height=4, filter_width=4, stride=2, name=None):
+        self.nodes.append(Node(name, "deconv", [x], k=filter_height, cout=num_filters_out, stride=stride))
+        return name
+
+    def Max_Pooling(self, x, name):
+        self.nodes.append(Node(name, "pool", [x]))
+        return name
+
+    def Concat(self, xs, name):
+        self.nodes.append(Node(name, "concat", list(xs)))
+        return name
+
+
+def unet_nodes(num_classes=2):
+    """SegNet.py:30-51 encoder (ReLU on) + FCDenseNet.py:141-160 decoder idiom; see module docstring."""
+    g = GraphBuilder()
+    c = lambda x, f, name: g.Conv2D_Block(x, f, batch_normalization=True, relu=True, name=name)
+    x = "input"
+    conv1 = c(x, 64, "conv1"); conv2 = c(conv1, 64, "conv2"); pool1 = g.Max_Pooling(conv2, "pool1")
+    conv3 = c(pool1, 128, "conv3"); conv4 = c(conv3, 128, "conv4"); pool2 = g.Max_Pooling(conv4, "pool2")
+    conv5 = c(pool2, 256, "conv5"); conv6 = c(conv5, 256, "conv6"); conv7 = c(conv6, 256, "conv7")
+    pool3 = g.Max_Pooling(conv7, "pool3")
+    conv8 = c(pool3, 512, "conv8"); conv9 = c(conv8, 512, "conv9"); conv10 = c(conv9, 512, "conv10")
+    pool4 = g.Max_Pooling(conv10, "pool4")
+    conv11 = c(pool4, 512, "conv11"); conv12 = c(conv11, 512, "conv12"); conv13 = c(conv12, 512, "conv13")
+    pool5 = g.Max_Pooling(conv13, "pool5")
+    up1 = g.Deconv2D_Block(pool5, 512, name="unpool1"); cat1 = g.Concat([up1, conv13], "concat1")
+    conv14 = c(cat1, 512, "conv14"); conv15 = c(conv14, 512, "conv15"); conv16 = c(conv15, 512, "conv16")
+    up2 = g.Deconv2D_Block(conv16, 512, name="unpool2"); cat2 = g.Concat([up2, conv10], "concat2")
+    conv17 = c(cat2, 512, "conv17"); conv18 = c(conv17, 512, "conv18"); conv19 = c(conv18, 256, "conv19")
+    up3 = g.Deconv2D_Block(conv19, 256, name="unpool3"); cat3 = g.Concat([up3, conv7], "concat3")
+    conv20 = c(cat3, 256, "conv20"); conv21 = c(conv20, 256, "conv21"); conv22 = c(conv21, 128, "conv22")
+    up4 = g.Deconv2D_Block(conv22, 128, name="unpool4"); cat4 = g.Concat([up4, conv4], "concat4")
+    conv23 = c(cat4, 128, "conv23"); conv24 = c(conv23, 64, "conv24")
+    up5 = g.Deconv2D_Block(conv24, 64, name="unpool5"); cat5 = g.Concat([up5, conv2], "concat5")
+    conv25 = c(cat5, 64, "conv25")
+    g.Conv2D_Block(conv25, num_classes, 1, 1, name="final_conv")          # FCDenseNet.py:157
+    return g.nodes
+
+
+def graph_variable_shapes(nodes, cin):
+    """Ordered {name: shape}: `<scope>/weights` (HWIO; deconv [k,k,Cout,Cin]), BN gamma/beta in TF naming."""
+    ch = {"input": cin}
+    shapes = OrderedDict()
+    for n in nodes:
+        if n.kind == "pool":
+            ch[n.name] = ch[n.inputs[0]]
+        elif n.kind == "concat":
+            ch[n.name] = sum(ch[i] for i in n.inputs)
+        else:
+            ci = ch[n.inputs[0]]
+            shapes[f"{n.name}/weights"] = (n.k, n.k, ci, n.cout) if n.kind == "conv" else (n.k, n.k, n.cout, ci)
+            if n.bias:
+                shapes[f"{n.name}/biases"] = (n.cout,)
+            if n.bn:
+                shapes[f"{n.bn_scope}/gamma"] = (n.cout,)
+                shapes[f"{n.bn_scope}/beta"] = (n.cout,)
+            ch[n.name] = n.cout
+    return shapes
+
+
+def graph_init(shapes, seed=1234, init="ref"):
+    """weights N(0, 0.01^2) (utils.py:179,266), gamma 1, beta/biases 0; 'he' for visibility tests."""
+    rng = np.random.default_rng(seed)
+    out = OrderedDict()
+    for name, shape in shapes.items():
+        if name.endswith("weights"):
+            z = rng.standard_normal(shape, dtype=np.float32)
+            if init == "ref":
+                std = 0.01
+            else:
+                fan_in = shape[0] * shape[1] * shape[2] if not name.startswith("unpool") else 4 * shape[3]
+                std = float(np.sqrt(2.0 / fan_in))
+            out[name] = (z * np.float32(std)).astype(np.float32)
+        elif name.endswith("gamma"):
+            out[name] = np.ones(shape, np.float32)
+        else:
+            out[name] = np.zeros(shape, np.float32)
+    return out
+
+
+class _Vars:
+    """Flat fp32 arenas in creation order (params, grads, optimizer slots)."""
+
+    def __init__(self, shapes, device, values):
+        self.shapes = shapes
+        self.slots, self.total = P.arena_layout(shapes)
+        self.p = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.g = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.m = None
+        self.v = None
+        for name, arr in values.items():
+            self.view(self.p, name).copy_(torch.as_tensor(np.asarray(arr), dtype=torch.float32))
+        self.wk, self.wd, self.weff = {}, {}, {}
+        self._repack = None
+
+    def view(self, arena, name):
+        s = self.slots[name]
+        return arena[s.offset:s.offset + s.size].view(s.shape)
+
+    def param(self, name):
+        return self.view(self.p, name)
+
+    def grad(self, name):
+        return self.view(self.g, name)
+
+    def export(self):
+        return OrderedDict((n, self.view(self.p, n).detach().cpu().numpy().copy()) for n in self.slots)
+
+    def repack(self, ops):
+        self._repack(ops)
+
+
+class GraphNet:
+    def __init__(self, x, num_classes, nodes, variables=None, init="ref", seed=1234, world_size=1):
+        if not torch.cuda.is_available():
+            raise RuntimeError("GraphNet needs a CUDA (sm_100a) device: the segmentation ops have no CPU fallback")
+        x = torch.as_tensor(x)
+        if x.dtype != torch.uint8:
+            x = x.round().clamp(0, 255).to(torch.uint8)
+        self.x = x.contiguous()
+        self.device = x.device
+        self.ops = Ops(self.device)
+        self.num_classes = int(num_classes)
+        self.N, self.H, self.W, self.Cin = self.x.shape
+        self.nodes = nodes
+        self.by_name = {n.name: n for n in nodes}
+        self.world_size = world_size
+        self.keep_prob = 1.0
+        self.step_count = 0
+        self.image, self.annotation, self.keep_probability = _Feed("input_image"), _Feed("annotation"), _Feed("keep_probability")
+        shapes = graph_variable_shapes(nodes, self.Cin)
+        values = variables if variables is not None else graph_init(shapes, seed, init)
+        self.vars = _Vars(shapes, self.device, values)
+        self.vars._repack = self._repack
+        self._plan()
+        self._repack(self.ops)
+        self._ran_forward = False
+
+    # ---- planning ---------------------------------------------------------------------------
+    def _route(self, n, cin):
+        if n.kind == "deconv":
+            if not (cin % 64 == 0 and n.cout % 64 == 0 and n.k == 4 and n.stride == 2):
+                raise ValueError(f"{n.name}: transposed conv needs 4x4 s2 with channels % 64 == 0 (no fallback)")
+            return "tc"
+        if cin % 64 == 0 and n.cout % 64 == 0:
+            return "tc"
+        if n.k * n.k * cin <= 64 and n.cout % 64 == 0 and n.inputs[0] == "input":
+            return "im2col"
+        if n.k == 1 and n.cout in (2, 4, 8) and cin % 8 == 0:
+            return "small"
+        raise ValueError(f"{n.name}: unsupported conv {n.k}x{n.k} {cin}->{n.cout} (no fallback)")
+
+    def _plan(self):
+        dev, N, bf = self.device, self.N, torch.bfloat16
+        shape = {"input": (N, self.H, self.W, self.Cin)}
+        self.route, self.act, self.idx, self.gbuf, self.patch, self.tmp = {}, OrderedDict(), {}, {}, {}, {}
+        last = self.nodes[-1].name
+        for n in self.nodes:
+            n_, h, w, c = shape[n.inputs[0]]
+            if n.kind == "pool":
+                shape[n.name] = (N, h // 2, w // 2, c)
+                self.idx[n.name] = torch.empty(shape[n.name], dtype=torch.uint8, device=dev)
+            elif n.kind == "concat":
+                for i in n.inputs:
+                    assert shape[i][:3] == (N, h, w), f"{n.name}: concat inputs differ in size"
+                shape[n.name] = (N, h, w, sum(shape[i][3] for i in n.inputs))
+            elif n.kind == "deconv":
+                self.route[n.name] = self._route(n, c)
+                shape[n.name] = (N, h * n.stride, w * n.stride, n.cout)
+            else:
+                self.route[n.name] = self._route(n, c)
+                shape[n.name] = (N, h, w, n.cout)
+                if self.route[n.name] == "im2col":
+                    self.patch[n.name] = torch.empty((N, h, w, 64), dtype=bf, device=dev)
+                    self.tmp[n.name] = torch.empty((1, 1, 64, n.cout), dtype=torch.float32, device=dev)
+            dt = torch.float32 if n.name == last else bf
+            self.act[n.name] = torch.empty(shape[n.name], dtype=dt, device=dev)
+            self.gbuf[n.name] = torch.empty(shape[n.name], dtype=dt, device=dev)
+        self.shape = shape
+        self.logits = self.act[last]
+        assert self.logits.shape[3] == self.num_classes
+        self.dlogits = self.gbuf[last]
+        self.dlogits_bf16 = torch.empty(shape[last], dtype=bf, device=dev)
+        npix = N * self.H * self.W
+        self.pred_u8 = torch.empty((N, self.H, self.W), dtype=torch.uint8, device=dev)
+        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.xent_ws = self.ops.xent_workspace(npix, dev)
+        self.bn_ws = torch.empty(8 << 20, dtype=torch.uint8, device=dev)
+        self.labels = torch.zeros((N, self.H, self.W), dtype=torch.uint8, device=dev)
+
+    def _repack(self, ops):
+        V = self.vars
+        for n in self.nodes:
+            if n.kind not in ("conv", "deconv"):
+                continue
+            w = V.param(f"{n.name}/weights")
+            if n.bn:   # fold gamma / sqrt(1 + eps) into the weights (columns = Cout for HWIO)
+                V.weff[n.name] = ops.scale_columns(w, V.param(f"{n.bn_scope}/gamma"), BN_SCALE, V.weff.get(n.name))
+                w = V.weff[n.name]
+            r = self.route[n.name]
+            if n.kind == "deconv":
+                V.wk[n.name], V.wd[n.name] = ops.pack_deconv_weights(w, n.stride, V.wk.get(n.name), V.wd.get(n.name))
+            elif r == "tc":
+                V.wk[n.name], V.wd[n.name] = ops.pack_conv_weights(w, V.wk.get(n.name), V.wd.get(n.name))
+            elif r == "im2col":
+                V.wk[n.name] = ops.pack_im2col_weights(w, V.wk.get(n.name))
+            else:
+                V.weff[n.name] = w
+
+    def _bias(self, n):
+        if n.bn:
+            return self.vars.param(f"{n.bn_scope}/beta")
+        if n.bias:
+            return self.vars.param(f"{n.name}/biases")
+        return None
+
+    # ---- feeds (FCN-compatible) -----------------------------------------------------------------
+    def feed(self, feed_dict):
+        for k, v in feed_dict.items():
+            name = k.name if isinstance(k, _Feed) else str(k)
+            if name == "input_image":
+                x = torch.as_tensor(v)
+                if x.dtype != torch.uint8:
+                    x = x.round().clamp(0, 255).to(torch.uint8)
+                if tuple(x.shape) != (self.N, self.H, self.W, self.Cin):
+                    raise ValueError(f"image shape {tuple(x.shape)} != planned {(self.N, self.H, self.W, self.Cin)}")
+                self.x = x.contiguous().to(self.device, non_blocking=True)
+            elif name == "annotation":
+                self.labels = self._as_labels(v)
+            elif name == "keep_probability":
+                self.keep_prob = float(v)     # the U-Net graph has no dropout node; accepted for API parity
+            else:
+                raise KeyError(name)
+
+    def _as_labels(self, y):
+        y = torch.as_tensor(y)
+        if y.dim() == 4:
+            y = y.to(self.device).argmax(dim=3)
+        return y.to(device=self.device, dtype=torch.uint8, non_blocking=True).contiguous()
+
+    # ---- forward ----------------------------------------------------------------------------------
+    def _in(self, name):
+        return self.x if name == "input" else self.act[name]
+
+    def forward(self):
+        ops, V = self.ops, self.vars
+        for n in self.nodes:
+            out = self.act[n.name]
+            if n.kind == "pool":
+                ops.maxpool_fwd(self._in(n.inputs[0]), out, self.idx[n.name])
+            elif n.kind == "concat":
+                off = 0
+                for i in n.inputs:
+                    c = self.shape[i][3]
+                    ops.channel_copy(self.act[i], 0, out, off, c)
+                    off += c
+            elif n.kind == "deconv":
+                ops.deconv2d_fwd(self._in(n.inputs[0]), V.wk[n.name], self._bias(n), out, n.k, n.stride, relu=n.relu)
+            else:
+                x, r = self._in(n.inputs[0]), self.route[n.name]
+                if r == "tc":
+                    ops.conv2d_fwd(x, V.wk[n.name], self._bias(n), out, n.k, n.k, relu=n.relu)
+                elif r == "im2col":
+                    P1 = ops.im2col_k64(x, self.patch[n.name], n.k, n.k)
+                    ops.conv2d_fwd(P1, V.wk[n.name], self._bias(n), out, 1, 1, relu=n.relu,
+                                   flops=conv_flops(self.N, out.shape[1], out.shape[2], x.shape[3], n.cout, n.k, n.k))
+                else:
+                    ops.conv2d_small_fwd(x, V.weff[n.name], self._bias(n), out, relu=n.relu)
+        self._ran_forward = True
+        return self.logits
+
+    def create(self):
+        self.forward()
+        self.ops.softmax_infer(self.logits, None, self.pred_u8)
+        return self.pred_u8.to(torch.int64).unsqueeze(3), self.logits
+
+    def loss(self, annotation=None, with_grad=False):
+        if annotation is not None:
+            self.labels = self._as_labels(annotation)
+        if not self._ran_forward:
+            self.forward()
+        npix = self.N * self.H * self.W
+        self.ops.softmax_xent(self.logits, self.labels, self.dlogits if with_grad else None, self.pred_u8,
+                              self.loss_sum, None, self.xent_ws, 1.0 / (npix * self.world_size))
+        return self.loss_sum[0] / npix
+
+    def confusion_matrix(self):
+        cm = torch.zeros(4, dtype=torch.int64, device=self.device)
+        self.ops.confusion_matrix(self.labels, self.pred_u8, cm)
+        return cm.view(2, 2)
+
+    # ---- backward -----------------------------------------------------------------------------------
+    def _relu_mask_of(self, name):
+        """Activation whose ReluGrad must be applied to a gradient flowing into tensor `name`."""
+        if name == "input":
+            return None
+        p = self.by_name[name]
+        return self.act[name] if (p.kind in ("conv", "deconv") and p.relu) else None
+
+    def backward(self, after_layer=None):
+        ops, V = self.ops, self.vars
+        has = {n.name: False for n in self.nodes}
+        last = self.nodes[-1].name
+        has[last] = True
+        for n in reversed(self.nodes):
+            if not has[n.name]:
+                raise RuntimeError(f"{n.name}: output has no consumer gradient")
+            G = self.gbuf[n.name]
+            if n.kind == "pool":
+                t = n.inputs[0]
+                ops.maxpool_bwd(G, self.idx[n.name], self.gbuf[t], act=self._relu_mask_of(t),
+                                residual=self.gbuf[t] if has[t] else None)
+                has[t] = True
+                continue
+            if n.kind == "concat":
+                off = 0
+                for t in n.inputs:
+                    c = self.shape[t][3]
+                    ops.channel_copy(G, off, self.gbuf[t], 0, c, mask=self._relu_mask_of(t), accumulate=has[t])
+                    has[t] = True
+                    off += c
+                continue
+            t = n.inputs[0]
+            x = self._in(t)
+            gw = V.grad(f"{n.name}/weights")
+            r = self.route[n.name]
+            dz = G
+            if r == "small" and G.dtype == torch.float32:
+                dz = ops.cast_to_bf16(G, self.dlogits_bf16)
+            if n.bn:
+                ops.bias_grad(dz, V.grad(f"{n.bn_scope}/beta"))
+                ops.bn_gamma_grad(dz, self.act[n.name], V.param(f"{n.bn_scope}/beta"), V.param(f"{n.bn_scope}/gamma"),
+                                  V.grad(f"{n.bn_scope}/gamma"), self.bn_ws)
+            elif n.bias:
+                ops.bias_grad(dz, V.grad(f"{n.name}/biases"))
+            # weight gradient (of the folded weights; unfold the BN scale afterwards)
+            if n.kind == "deconv":
+                ops.deconv2d_wgrad(x, dz, gw, n.k, n.stride)
+            elif r == "tc":
+                ops.conv2d_wgrad(x, dz, gw, n.k, n.k)
+            elif r == "im2col":
+                tmp = ops.conv2d_wgrad(self.patch[n.name], dz, self.tmp[n.name], 1, 1,
+                                       flops=conv_flops(self.N, dz.shape[1], dz.shape[2], x.shape[3], n.cout, n.k, n.k))
+                gw.view(-1).copy_(tmp.view(-1)[:gw.numel()])
+            else:
+                ops.conv2d_small_wgrad(x, dz, gw)
+            if n.bn:
+                ops.scale_columns(gw, V.param(f"{n.bn_scope}/gamma"), BN_SCALE, gw)
+            # input gradient
+            if t != "input":
+                mask = self._relu_mask_of(t)
+                res = self.gbuf[t] if has[t] else None
+                dx = self.gbuf[t]
+                if n.kind == "deconv":
+                    if res is not None:
+                        raise NotImplementedError("deconv input with a second consumer")
+                    ops.deconv2d_dgrad(dz, V.wd[n.name], dx, n.k, n.stride, relu_mask=mask)
+                elif r == "tc":
+                    ops.conv2d_dgrad(dz, V.wd[n.name], dx, n.k, n.k, relu_mask=mask, residual=res)
+                elif r == "small":
+                    if res is not None:
+                        raise NotImplementedError("1x1 head input with a second consumer")
+                    ops.conv2d_small_dgrad(dz, V.weff[n.name], dx, relu_mask=mask)
+                else:
+                    raise NotImplementedError("im2col route is for the first layer only")
+                has[t] = True
+            if after_layer is not None:
+                after_layer(n.name)
+
+    def infer(self, image=None):
+        if image is not None:
+            self.feed({self.image: image})
+        self.forward()
+        prob = torch.empty_like(self.logits)
+        mask = torch.empty((self.N, self.H, self.W), dtype=torch.uint8, device=self.device)
+        self.ops.softmax_infer(self.logits, prob, mask)
+        return prob, mask
+
+
+def UNet(x, num_classes=2, **kw):
+    """U-Net-style builder (see module docstring); same call shape as SegNet(x, num_classes) (SegNet.py:28)."""
+    return GraphNet(x, num_classes, unet_nodes(num_classes), **kw)

@@ -224,7 +224,7 @@ class Ops:
         kh, kw, _, cout = w.shape
         self._w(conv_flops(n, h, wd_, cin, cout, kh, kw), "flop")
         self.call("segk_conv2d_small_fwd", _p(x), _dt(x), _p(w), _p(bias), _p(y), n, h, wd_, cin, cout, kh, kw,
-                  EPI_RELU if relu else 0, _stream())
+                  (EPI_RELU if relu else 0) | (EPI_OUT_F32 if y.dtype == torch.float32 else 0), _stream())
         return y
 
     def conv2d_small_dgrad(self, dy, w, dx, relu_mask=None, scale=1.0):
@@ -274,11 +274,34 @@ class Ops:
         self.call("segk_maxpool2x2_fwd", _p(x), _p(y), _p(idx), n, h, w, c, _stream())
         return y, idx
 
-    def maxpool_bwd(self, dy, idx, dx, act=None):
+    def maxpool_bwd(self, dy, idx, dx, act=None, residual=None):
         n, h, w, c = dx.shape
-        self._w(2.0 * dx.numel() + 3.0 * dy.numel() + (2.0 * dx.numel() if act is not None else 0.0), "byte")
-        self.call("segk_maxpool2x2_bwd", _p(dy), _p(idx), _p(act), _p(dx), n, h, w, c, _stream())
+        extra = (2.0 * dx.numel() if act is not None else 0.0) + (2.0 * dx.numel() if residual is not None else 0.0)
+        self._w(2.0 * dx.numel() + 3.0 * dy.numel() + extra, "byte")
+        self.call("segk_maxpool2x2_bwd", _p(dy), _p(idx), _p(act), _p(residual), _p(dx), n, h, w, c, _stream())
         return dx
+
+    # ---- shared-helper layers (utils.py): BN-affine folding, concat ---------------------------------
+    def scale_columns(self, w, scale, mult, out=None):
+        c = w.shape[-1]
+        if out is None:
+            out = torch.empty_like(w)
+        self.call("segk_scale_columns", _p(w), _p(scale), float(mult), _p(out), w.numel() // c, c, _stream())
+        return out
+
+    def bn_gamma_grad(self, dz, y, beta, gamma, dgamma, workspace):
+        c = dz.shape[-1]
+        self._w(4.0 * dz.numel(), "byte")
+        self.call("segk_bn_gamma_grad", _p(dz), _p(y), _p(beta), _p(gamma), _p(dgamma), _p(workspace),
+                  workspace.numel() * workspace.element_size(), dz.numel() // c, c, _stream())
+        return dgamma
+
+    def channel_copy(self, src, coff_src, dst, coff_dst, c, mask=None, accumulate=False):
+        rows = src.numel() // src.shape[-1]
+        self._w(4.0 * rows * c, "byte")
+        self.call("segk_channel_copy", _p(src), src.shape[-1], coff_src, _p(dst), dst.shape[-1], coff_dst, _p(mask),
+                  int(accumulate), rows, c, _stream())
+        return dst
 
     def dropout(self, x, y, keep_prob, seed, mask=None):
         self.call("segk_dropout", _p(x), _p(y), _p(mask), x.numel(), float(keep_prob), int(seed), _stream())

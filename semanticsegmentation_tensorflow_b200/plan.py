@@ -134,6 +134,27 @@ def gradient_buckets(slots, layer_groups=None) -> List[Tuple[int, int, str]]:
     return out
 
 
+def gradient_buckets_even(slots, layer_names, nbuckets: int = 4) -> List[Tuple[int, int, str]]:
+    """Generic variant for any layer list (creation order): ~equal-size contiguous arena slices cut at
+    layer boundaries, returned in backward completion order with the layer that completes each."""
+    starts = []
+    for ln in layer_names:
+        key = f"{ln}/weights"
+        if key in slots:
+            starts.append((slots[key].offset, ln))
+    total_end = max(s.offset + -(-s.size // ALIGN) * ALIGN for s in slots.values())
+    target = total_end / float(max(nbuckets, 1))
+    out = []
+    end = total_end
+    for off, ln in reversed(starts):
+        if end - off >= target or off == starts[0][0]:
+            out.append((off, end, ln))
+            end = off
+    if out and out[-1][0] != 0:            # variables created before the first listed layer
+        out[-1] = (0, out[-1][1], out[-1][2])
+    return out
+
+
 def adam_lr_t(lr: float, t: int, beta1: float = 0.9, beta2: float = 0.999) -> float:
     """tf.train.AdamOptimizer's per-step rate: lr*sqrt(1-b2^t)/(1-b1^t), t starts at 1."""
     return lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)

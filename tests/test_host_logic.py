@@ -146,3 +146,17 @@ def test_bucketed_allreduce_gloo_world2(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{o}"
         assert f"rank {r} ok" in o
+
+
+def test_generic_even_buckets_cover_the_arena():
+    from semanticsegmentation_tensorflow_b200.graph import graph_variable_shapes, unet_nodes
+    nodes = unet_nodes(2)
+    slots, total = P.arena_layout(graph_variable_shapes(nodes, 3))
+    names = [n.name for n in nodes if n.kind in ("conv", "deconv")]
+    b = P.gradient_buckets_even(slots, names, 4)
+    assert b[0][1] == total and b[-1][0] == 0 and 2 <= len(b) <= 5
+    for (lo, hi, _), (lo2, hi2, _) in zip(b, b[1:]):
+        assert lo == hi2 and lo2 < hi2
+    # backward completion order: the completing layers appear in reverse creation order
+    idx = [names.index(x[2]) for x in b]
+    assert idx == sorted(idx, reverse=True)
