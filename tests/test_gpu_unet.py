@@ -76,7 +76,7 @@ def test_maxpool_bwd_with_second_gradient_path(ops, cuda_device):
     assert np.array_equal(host(dx), ref)
 
 
-N, H, W = 2, 64, 96
+N, H, W = 2, 128, 192
 
 
 def _build(cuda_device, init):
