@@ -158,7 +158,17 @@ def run_gpu(args):
     host_y = torch.randint(0, 2, (B, H, W), dtype=torch.uint8, generator=gen).pin_memory()
     dev_x, dev_y = host_x.to(dev), host_y.to(dev)
 
-    net = FCN(dev_x, KEEP_PROB, NCLS, init="device", seed=1234, world_size=world, dropout_seed=42 + rank)
+    if args.model == "unet":
+        from semanticsegmentation_tensorflow_b200.graph import UNet, graph_flops_per_image, unet_nodes
+        net = UNet(dev_x, NCLS, seed=1234, world_size=world)
+        train_gflop = graph_flops_per_image(unet_nodes(NCLS), H, W, CIN)[1] / 1e9
+        workload = "U-Net 2-class bf16 training (fwd+loss+bwd+Adam), batch 32 per GPU, 160x576x3 (BASELINE configs[2])"
+        metric = "train images/sec U-Net 160x576"
+    else:
+        net = FCN(dev_x, KEEP_PROB, NCLS, init="device", seed=1234, world_size=world, dropout_seed=42 + rank)
+        train_gflop = TRAIN_GFLOP_PER_IMAGE
+        workload = "FCN-8s 2-class bf16 training (fwd+loss+bwd+Adam), batch 32 per GPU, 160x576x3 (BASELINE configs[1])"
+        metric = METRIC
     allreduce = BucketedAllReduce.for_net(net) if world > 1 else None
     train_step = AdamOptimizer(1e-4).minimize(net, allreduce=allreduce)
     feed_dev = {net.image: dev_x, net.annotation: dev_y, net.keep_probability: KEEP_PROB}
@@ -250,7 +260,7 @@ def run_gpu(args):
                     ("tflops" if v["unit"] == "flop" else "gbs"):
                         (v["work"] / (v["ms"] / 1e3) / (1e12 if v["unit"] == "flop" else 1e9)) if v["ms"] > 0 else None}
                 for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
-    step_tflops = TRAIN_GFLOP_PER_IMAGE * 1e9 * value / world / 1e12
+    step_tflops = train_gflop * 1e9 * value / world / 1e12
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -259,10 +269,10 @@ def run_gpu(args):
                         "sample": f"batch 1 of the 32-image step, fp32 oracle, {done} step(s) after 1 warm-up, {ms:.0f} ms/step"}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "FCN-8s 2-class bf16 training (fwd+loss+bwd+Adam), batch 32 per GPU, 160x576x3 (BASELINE configs[1])",
+        "config": {"workload": workload,
                    "global_batch": world * B, "batch_per_gpu": B, "keep_prob": KEEP_PROB,
                    "parallelism": f"dp{world}", "init": "random N(0,0.01^2) (FCN.py:125)",
                    "l2": "working set (1.8 GiB activations + 2.2 GiB weights/optimizer state) >> 126 MB L2; no flush needed"},
@@ -272,7 +282,7 @@ def run_gpu(args):
         "clocks": clocks,
         "roofline": roofline,
         "tensor_util_step": {"train_tflops_per_gpu": step_tflops, "frac_of_peak": step_tflops / peaks["bf16_tflops_sustained"],
-                             "flops_per_image": TRAIN_GFLOP_PER_IMAGE * 1e9, "convention": "valid-tap fwd+dgrad+wgrad"},
+                             "flops_per_image": train_gflop * 1e9, "convention": "valid-tap fwd+dgrad+wgrad"},
         "kernel_families": families,
         "cpu_baseline": cpu_baseline,
         "final_loss": final_loss,
@@ -358,6 +368,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers-out", default=None, help="write the per-call (per-layer) timing table here")
+    ap.add_argument("--model", default="fcn", choices=["fcn", "unet"],
+                    help="fcn = FCN-8s (BASELINE configs[1], the driver's metric); unet = configs[2]")
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
                     help="train = BASELINE configs[1] (default, the driver's metric); infer = configs[3]: "
                          "FCN-8s forward + softmax + road mask at 384x1248, batch 16 (throughput and latency)")

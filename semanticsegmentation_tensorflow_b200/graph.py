@@ -448,6 +448,28 @@ class GraphNet:
         return prob, mask
 
 
+def graph_flops_per_image(nodes, h, w, cin):
+    """(forward, training) valid-tap FLOPs per image; training = fwd + dgrad + wgrad, no dgrad for the first layer."""
+    from .ops import deconv_flops
+    shape = {"input": (h, w, cin)}
+    fwd = train = 0.0
+    for n in nodes:
+        ih, iw, ic = shape[n.inputs[0]]
+        if n.kind == "pool":
+            shape[n.name] = (ih // 2, iw // 2, ic)
+        elif n.kind == "concat":
+            shape[n.name] = (ih, iw, sum(shape[i][2] for i in n.inputs))
+        elif n.kind == "deconv":
+            f = deconv_flops(1, ih, iw, ic, n.cout, n.k, n.stride)
+            fwd += f; train += 3 * f
+            shape[n.name] = (ih * n.stride, iw * n.stride, n.cout)
+        else:
+            f = conv_flops(1, ih, iw, ic, n.cout, n.k, n.k)
+            fwd += f; train += (2 if n.inputs[0] == "input" else 3) * f
+            shape[n.name] = (ih, iw, n.cout)
+    return fwd, train
+
+
 def UNet(x, num_classes=2, **kw):
     """U-Net-style builder (see module docstring); same call shape as SegNet(x, num_classes) (SegNet.py:28)."""
     return GraphNet(x, num_classes, unet_nodes(num_classes), **kw)
