@@ -216,6 +216,136 @@ __global__ void __launch_bounds__(kThreads) conv_skinny_wgrad_kernel(
   for (int c = 0; c < CO; ++c) atomicAdd(dw + (int64_t)ci * CO + c, acc[c]);
 }
 
+// ---- skinny 1x1 conv on LARGE pixel counts with small Cin (the 64 -> num_classes head of the
+// encoder-decoder builders at full resolution): HBM-bound streaming forms.
+// fwd: one thread per pixel; the Cin x CO weights live in shared memory (fp32).
+template <int CO>
+__global__ void __launch_bounds__(kThreads) conv_skinny_fwd_pixel_kernel(
+    const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+    void* __restrict__ y, int64_t npix, int Cin, int relu, int out_f32) {
+  extern __shared__ float wsm[];   // [Cin][CO]
+  for (int i = threadIdx.x; i < Cin * CO; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    float acc[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[c] = bias ? bias[c] : 0.f;
+    const uint4* xp = reinterpret_cast<const uint4*>(x + p * Cin);
+    for (int g = 0; g < Cin / 8; ++g) {
+      const uint4 v = __ldg(xp + g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&v.x)[j]);
+        const float* w0 = wsm + (g * 8 + 2 * j) * CO;
+#pragma unroll
+        for (int c = 0; c < CO; ++c) acc[c] += f.x * w0[c] + f.y * w0[CO + c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+      const float v = relu ? fmaxf(acc[c], 0.f) : acc[c];
+      if (out_f32) reinterpret_cast<float*>(y)[p * CO + c] = v;
+      else reinterpret_cast<bf16*>(y)[p * CO + c] = f2bf(v);
+    }
+  }
+}
+
+// dgrad: thread = 8 input channels of one pixel (16-byte store)
+template <int CO>
+__global__ void __launch_bounds__(kThreads) conv_skinny_dgrad_vec_kernel(
+    const bf16* __restrict__ dy, const float* __restrict__ w, const bf16* __restrict__ mask,
+    bf16* __restrict__ dx, int64_t npix, int Cin, float scale) {
+  extern __shared__ float wsm[];   // [Cin][CO]
+  for (int i = threadIdx.x; i < Cin * CO; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  const int C8 = Cin >> 3;
+  const int64_t total = npix * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % C8);
+    const int64_t p = i / C8;
+    float d[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) d[c] = bf2f(dy[p * CO + c]);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = 0.f;
+#pragma unroll
+      for (int c = 0; c < CO; ++c) a += d[c] * wsm[(g * 8 + j) * CO + c];
+      v[j] = a * scale;
+    }
+    if (mask) {
+      const uint4 m = __ldg(reinterpret_cast<const uint4*>(mask + p * Cin) + g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&m.x)[j]);
+        if (!(f.x > 0.f)) v[2 * j] = 0.f;
+        if (!(f.y > 0.f)) v[2 * j + 1] = 0.f;
+      }
+    }
+    reinterpret_cast<uint4*>(dx + p * Cin)[g] =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// wgrad stage 1: per-block partial dW[ci][co] over the block's pixels (thread = 8 channels of a pixel
+// per iteration), stage 2 sums the partials in a fixed order (no atomic chains).
+template <int CO>
+__global__ void __launch_bounds__(kThreads) conv_skinny_wgrad_partial_kernel(
+    const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ partial, int64_t npix, int Cin) {
+  __shared__ float sh[kThreads][8 * CO + 1];
+  const int C8 = Cin >> 3;                 // host guarantees C8 divides kThreads
+  const int R = kThreads / C8;
+  const int g = threadIdx.x % C8, rl = threadIdx.x / C8;
+  float acc[8][CO];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
+  for (int64_t p = (int64_t)blockIdx.x * R + rl; p < npix; p += (int64_t)gridDim.x * R) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + p * Cin) + g);
+    float d[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) d[c] = bf2f(dy[p * CO + c]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2((&v.x)[j]);
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        acc[2 * j][c] += f.x * d[c];
+        acc[2 * j + 1][c] += f.y * d[c];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) sh[threadIdx.x][j * CO + c] = acc[j][c];
+  __syncthreads();
+  if (rl == 0) {
+    for (int k = 1; k < R; ++k)
+#pragma unroll
+      for (int j = 0; j < 8 * CO; ++j) sh[threadIdx.x][j] += sh[threadIdx.x + k * C8][j];
+    float* out = partial + ((int64_t)blockIdx.x * Cin + g * 8) * CO;    // [block][ci][co]
+#pragma unroll
+    for (int j = 0; j < 8 * CO; ++j) out[j] = sh[threadIdx.x][j];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) sum_partials_rows_kernel(const float* __restrict__ partial,
+                                                                     float* __restrict__ out, int rows, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a0 = 0.f, a1 = 0.f;
+  int r = 0;
+  for (; r + 1 < rows; r += 2) {
+    a0 += partial[(int64_t)r * n + i];
+    a1 += partial[(int64_t)(r + 1) * n + i];
+  }
+  if (r < rows) a0 += partial[(int64_t)r * n + i];
+  out[i] = a0 + a1;
+}
+
 // ---------------------------------------------------------------------------------------
 // transposed conv, k = 2s, SAME (FCN.py:138-159) on CUDA cores, gather form:
 //   y[n,oy,ox,co] = b[co] + sum_{ty,tx in {0,1}} sum_ci x[n, qy-ty, qx-tx, ci] * W[ay+s*ty, ax+s*tx, co, ci]
@@ -405,6 +535,18 @@ int segk_conv2d_small_fwd(segk_ctx* ctx, const void* x, int x_dtype, const float
     SEGK_LAUNCHED(ctx, "conv_tinyk_fwd");
     return SEGK_OK;
   }
+  if (x_dtype == 0 && kh == 1 && kw == 1 && Cin % 8 == 0 && Cin <= 256 && npix >= 65536 &&
+      (Cout == 2 || Cout == 4)) {
+    // full-resolution head: thread per pixel, weights in shared memory
+    const int grid = sgrid(ctx, npix, 8);
+    const size_t sm = sizeof(float) * (size_t)Cin * Cout;
+    if (Cout == 2)
+      conv_skinny_fwd_pixel_kernel<2><<<grid, kThreads, sm, st>>>((const bf16*)x, w, bias, y, npix, Cin, relu, out_f32);
+    else
+      conv_skinny_fwd_pixel_kernel<4><<<grid, kThreads, sm, st>>>((const bf16*)x, w, bias, y, npix, Cin, relu, out_f32);
+    SEGK_LAUNCHED(ctx, "conv_skinny_fwd_pixel");
+    return SEGK_OK;
+  }
   if (x_dtype == 0 && kh == 1 && kw == 1 && Cin % 8 == 0 && (Cout == 2 || Cout == 4 || Cout == 8)) {
     const int grid = sgrid(ctx, npix * 32, 8);
     if (Cout == 2)
@@ -430,6 +572,16 @@ int segk_conv2d_small_dgrad(segk_ctx* ctx, const void* dy, const float* w, const
                "conv_small_dgrad: only 1x1 with Cout in {2,4,8} (got %dx%d Cout=%d)", kh, kw, Cout);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t npix = (int64_t)N * H * W;
+  if (Cin % 8 == 0 && Cin <= 256 && npix >= 65536 && (Cout == 2 || Cout == 4)) {
+    const int g = sgrid(ctx, npix * (Cin / 8), 8);
+    const size_t sm = sizeof(float) * (size_t)Cin * Cout;
+    if (Cout == 2)
+      conv_skinny_dgrad_vec_kernel<2><<<g, kThreads, sm, st>>>((const bf16*)dy, w, (const bf16*)relu_mask, (bf16*)dx, npix, Cin, scale);
+    else
+      conv_skinny_dgrad_vec_kernel<4><<<g, kThreads, sm, st>>>((const bf16*)dy, w, (const bf16*)relu_mask, (bf16*)dx, npix, Cin, scale);
+    SEGK_LAUNCHED(ctx, "conv_skinny_dgrad_vec");
+    return SEGK_OK;
+  }
   const int grid = sgrid(ctx, npix * Cin);
   if (Cout == 2)
     conv_skinny_dgrad_kernel<2><<<grid, kThreads, 0, st>>>((const bf16*)dy, w, (const bf16*)relu_mask, (bf16*)dx, npix, Cin, scale);
@@ -465,6 +617,29 @@ int segk_conv2d_small_wgrad(segk_ctx* ctx, const void* x, int x_dtype, const voi
       conv_tinyk_wgrad_kernel<bf16><<<grid, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, dw, N, H, W,
                                                                Cin, Cout, kh, kw, ppb);
     SEGK_LAUNCHED(ctx, "conv_tinyk_wgrad");
+  } else if (x_dtype == 0 && kh == 1 && kw == 1 && (Cout == 2 || Cout == 4) && Cin % 8 == 0 &&
+             kThreads % (Cin / 8) == 0 && npix >= 65536) {
+    // full-resolution head: two-stage reduction over pixels
+    const int R = kThreads / (Cin / 8);
+    int64_t gx = ceil_div64(npix, (int64_t)R * 8);
+    if (gx > (int64_t)ctx->sm_count * 4) gx = (int64_t)ctx->sm_count * 4;
+    const size_t need = sizeof(float) * (size_t)gx * Cin * Cout;
+    if (ctx->ws2_bytes < need) {
+      if (ctx->ws2) cudaFree(ctx->ws2);
+      ctx->ws2 = nullptr;
+      ctx->ws2_bytes = 0;
+      const size_t want = need < (size_t)(8 << 20) ? (size_t)(8 << 20) : need;
+      if (cudaMalloc(&ctx->ws2, want) != cudaSuccess) return segk_fail(ctx, SEGK_ENOMEM, "skinny wgrad workspace");
+      ctx->ws2_bytes = want;
+    }
+    if (Cout == 2)
+      conv_skinny_wgrad_partial_kernel<2><<<(unsigned)gx, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, (float*)ctx->ws2, npix, Cin);
+    else
+      conv_skinny_wgrad_partial_kernel<4><<<(unsigned)gx, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, (float*)ctx->ws2, npix, Cin);
+    SEGK_LAUNCHED(ctx, "conv_skinny_wgrad_partial");
+    const int n = Cin * Cout;
+    sum_partials_rows_kernel<<<ceil_div(n, kThreads), kThreads, 0, st>>>((const float*)ctx->ws2, dw, (int)gx, n);
+    SEGK_LAUNCHED(ctx, "conv_skinny_wgrad_sum");
   } else if (x_dtype == 0 && kh == 1 && kw == 1 && (Cout == 2 || Cout == 4 || Cout == 8)) {
     const int tx = 128;
     const int gy = ceil_div(Cin, tx);

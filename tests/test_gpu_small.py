@@ -170,3 +170,30 @@ def test_conv_t3_in_patch_space(ops, cuda_device):
     # dy is rounded to bf16 inside the patch tensor: 2^-9 relative per element
     assert_close(host(dw).reshape(k, k, co, ci), wtt.grad.numpy(), 5e-3, "conv_t3 patch wgrad")
     assert_close(host(dx), xt.grad.numpy(), 1e-2, "conv_t3 patch dgrad")
+
+
+@pytest.mark.parametrize("co", [2, 4])
+def test_full_resolution_1x1_head(ops, cuda_device, co):
+    """64 -> num_classes 1x1 `final_conv` head (FCDenseNet.py:157) on >= 65536 pixels: the streaming
+    thread-per-pixel / two-stage-reduction kernels, fp32 logits out."""
+    n, h, w, ci = 2, 160, 288, 64
+    rng = np.random.default_rng(30)
+    x = bf16_grid(np.maximum(rng.standard_normal((n, h, w, ci)), 0))
+    wt = (rng.standard_normal((1, 1, ci, co)) / 8).astype(np.float32)
+    xt = torch.tensor(x, requires_grad=True)
+    wtt = torch.tensor(wt, requires_grad=True)
+    z = T.conv2d_same(xt, wtt)
+    xd = dev_bf16(x, cuda_device)
+    y = torch.empty((n, h, w, co), dtype=torch.float32, device=cuda_device)
+    ops.conv2d_small_fwd(xd, dev_f32(wt, cuda_device), None, y, relu=False)
+    torch.cuda.synchronize()
+    assert_close(host(y), z.detach().numpy(), 1e-5, "head fwd")
+    dy = bf16_grid(rng.standard_normal((n, h, w, co)))
+    z.backward(torch.tensor(dy))
+    dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=cuda_device)
+    ops.conv2d_small_dgrad(dev_bf16(dy, cuda_device), dev_f32(wt, cuda_device), dx, relu_mask=xd)
+    dw = torch.empty((1, 1, ci, co), dtype=torch.float32, device=cuda_device)
+    ops.conv2d_small_wgrad(xd, dev_bf16(dy, cuda_device), dw)
+    torch.cuda.synchronize()
+    assert_close(host(dx), xt.grad.numpy() * (x > 0), 1e-2, "head dgrad")
+    assert_close(host(dw), wtt.grad.numpy(), 1e-4, "head wgrad")
