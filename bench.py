@@ -125,7 +125,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "FCN-8s 2-class training (fwd+loss+bwd+Adam), 160x576x3, CPU sample = 1 image/step",
+        "config": {"workload": "FCN-8s 2-class bf16 training (fwd+loss+bwd+Adam), batch 32 per GPU, 160x576x3 (BASELINE configs[1])",
+                   "sample": "CPU reference arm: 1 image of the 32-image step per timed step, fp32, keep_prob 1.0",
                    "global_batch": 1, "keep_prob": 1.0},
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -603,21 +603,7 @@ int segk_conv2d_small_wgrad(segk_ctx* ctx, const void* x, int x_dtype, const voi
   const int K = kh * kw * Cin;
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)K * Cout, st);
   if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "wgrad memset: %s", cudaGetErrorString(e));
-  if (K <= kTinyKMax && (kh & 1) && (kw & 1)) {
-    const int gy = ceil_div(Cout, 64);
-    int64_t blocks = (int64_t)ctx->sm_count * 4 / gy;
-    if (blocks < 1) blocks = 1;
-    int64_t ppb = ceil_div64(npix, blocks);
-    ppb = ceil_div64(ppb, 32) * 32;
-    dim3 grid((unsigned)ceil_div64(npix, ppb), gy);
-    if (x_dtype == 2)
-      conv_tinyk_wgrad_kernel<uint8_t><<<grid, kThreads, 0, st>>>((const uint8_t*)x, (const bf16*)dy, dw, N, H,
-                                                                  W, Cin, Cout, kh, kw, ppb);
-    else
-      conv_tinyk_wgrad_kernel<bf16><<<grid, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, dw, N, H, W,
-                                                               Cin, Cout, kh, kw, ppb);
-    SEGK_LAUNCHED(ctx, "conv_tinyk_wgrad");
-  } else if (x_dtype == 0 && kh == 1 && kw == 1 && (Cout == 2 || Cout == 4) && Cin % 8 == 0 &&
+  if (x_dtype == 0 && kh == 1 && kw == 1 && (Cout == 2 || Cout == 4) && Cin % 8 == 0 &&
              kThreads % (Cin / 8) == 0 && npix >= 65536) {
     // full-resolution head: two-stage reduction over pixels
     const int R = kThreads / (Cin / 8);
@@ -640,6 +626,20 @@ int segk_conv2d_small_wgrad(segk_ctx* ctx, const void* x, int x_dtype, const voi
     const int n = Cin * Cout;
     sum_partials_rows_kernel<<<ceil_div(n, kThreads), kThreads, 0, st>>>((const float*)ctx->ws2, dw, (int)gx, n);
     SEGK_LAUNCHED(ctx, "conv_skinny_wgrad_sum");
+  } else if (K <= kTinyKMax && (kh & 1) && (kw & 1)) {
+    const int gy = ceil_div(Cout, 64);
+    int64_t blocks = (int64_t)ctx->sm_count * 4 / gy;
+    if (blocks < 1) blocks = 1;
+    int64_t ppb = ceil_div64(npix, blocks);
+    ppb = ceil_div64(ppb, 32) * 32;
+    dim3 grid((unsigned)ceil_div64(npix, ppb), gy);
+    if (x_dtype == 2)
+      conv_tinyk_wgrad_kernel<uint8_t><<<grid, kThreads, 0, st>>>((const uint8_t*)x, (const bf16*)dy, dw, N, H,
+                                                                  W, Cin, Cout, kh, kw, ppb);
+    else
+      conv_tinyk_wgrad_kernel<bf16><<<grid, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, dw, N, H, W,
+                                                               Cin, Cout, kh, kw, ppb);
+    SEGK_LAUNCHED(ctx, "conv_tinyk_wgrad");
   } else if (x_dtype == 0 && kh == 1 && kw == 1 && (Cout == 2 || Cout == 4 || Cout == 8)) {
     const int tx = 128;
     const int gy = ceil_div(Cin, tx);
