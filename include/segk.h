@@ -202,7 +202,8 @@ int segk_dropout(segk_ctx* ctx, const void* x, void* y, const uint8_t* mask, int
  *   logits f32 [npix,C] (C = 2), labels u8 class ids [npix];
  *   dlogits (f32, may be NULL) = (softmax - onehot) * grad_scale   (grad_scale =
  *   1/(world*N*H*W)); pred (u8, may be NULL) = argmax, ties -> 0;
- *   loss_sum (f32[1]) = sum over pixels of the per-pixel loss (deterministic two-stage);
+ *   loss_sum (f32[2]): [0] = sum over pixels of the per-pixel loss (deterministic two-stage),
+ *   [1] = that sum / npix, i.e. the reduce_mean of FCN.py:334;
  *   cm (int64[4], may be NULL) += confusion counts cm[gt*2+pred].
  *   workspace: >= segk_xent_workspace_bytes(npix) bytes. */
 size_t segk_xent_workspace_bytes(int64_t npix);

@@ -40,6 +40,7 @@ int segk_create(int device, segk_ctx** out) {
 int segk_destroy(segk_ctx* ctx) {
   if (ctx && ctx->ws) cudaFree(ctx->ws);
   if (ctx && ctx->ws2) cudaFree(ctx->ws2);
+  if (ctx && ctx->ws3) cudaFree(ctx->ws3);
   delete ctx;
   return SEGK_OK;
 }

@@ -22,6 +22,8 @@ struct segk_ctx {
   size_t ws_bytes = 0;
   void* ws2 = nullptr;      // grow-only scratch for per-block BiasAddGrad partials (elementwise.cu)
   size_t ws2_bytes = 0;
+  void* ws3 = nullptr;      // grow-only scratch for the full-resolution 1x1 head's wgrad partials (smallconv.cu)
+  size_t ws3_bytes = 0;
   // driver entry point resolved at segk_create (no link-time libcuda dependency)
   CUresult (*encode_tiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                            const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,

@@ -243,12 +243,15 @@ __global__ void __launch_bounds__(kThreads) xent_kernel(const float* __restrict_
 }
 
 __global__ void __launch_bounds__(kThreads) sum_partials_kernel(const float* __restrict__ partial,
-                                                                int n, float* __restrict__ out) {
+                                                                int n, float* __restrict__ out, float mean_scale) {
   __shared__ float sh[32];
   float v = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) v += partial[i];
   const float t = block_sum(v, sh);
-  if (threadIdx.x == 0) *out = t;
+  if (threadIdx.x == 0) {
+    out[0] = t;                 // sum over pixels
+    out[1] = t * mean_scale;    // reduce_mean (FCN.py:334)
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) softmax_infer_kernel(const float* __restrict__ logits,
@@ -568,6 +571,7 @@ size_t segk_xent_workspace_bytes(int64_t npix) {
 int segk_softmax_xent_fwd_bwd(segk_ctx* ctx, const float* logits, const uint8_t* labels,
                               float* dlogits, uint8_t* pred, float* loss_sum, int64_t* cm,
                               void* workspace, int64_t npix, int C, float grad_scale, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, logits && labels && loss_sum && workspace, "xent: null pointer");
   SEGK_REQUIRE(ctx, npix > 0 && C >= 2 && C <= 64, "xent: bad npix/C (%lld, %d)", (long long)npix, C);
   SEGK_REQUIRE(ctx, cm == nullptr || C == 2, "xent: confusion counts need C == 2");
@@ -582,7 +586,7 @@ int segk_softmax_xent_fwd_bwd(segk_ctx* ctx, const float* logits, const uint8_t*
     xent_kernel<0><<<blocks, kThreads, 0, st>>>(logits, labels, dlogits, pred, partial,
                                                (unsigned long long*)cm, npix, C, grad_scale);
   SEGK_LAUNCHED(ctx, "xent");
-  sum_partials_kernel<<<1, kThreads, 0, st>>>(partial, blocks, loss_sum);
+  sum_partials_kernel<<<1, kThreads, 0, st>>>(partial, blocks, loss_sum, 1.0f / (float)npix);
   SEGK_LAUNCHED(ctx, "xent_sum");
   return SEGK_OK;
 }

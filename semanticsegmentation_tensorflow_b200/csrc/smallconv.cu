@@ -610,21 +610,22 @@ int segk_conv2d_small_wgrad(segk_ctx* ctx, const void* x, int x_dtype, const voi
     int64_t gx = ceil_div64(npix, (int64_t)R * 8);
     if (gx > (int64_t)ctx->sm_count * 4) gx = (int64_t)ctx->sm_count * 4;
     const size_t need = sizeof(float) * (size_t)gx * Cin * Cout;
-    if (ctx->ws2_bytes < need) {
-      if (ctx->ws2) cudaFree(ctx->ws2);
-      ctx->ws2 = nullptr;
-      ctx->ws2_bytes = 0;
-      const size_t want = need < (size_t)(8 << 20) ? (size_t)(8 << 20) : need;
-      if (cudaMalloc(&ctx->ws2, want) != cudaSuccess) return segk_fail(ctx, SEGK_ENOMEM, "skinny wgrad workspace");
-      ctx->ws2_bytes = want;
+    // own scratch (ws3): BiasAddGrad may run concurrently on another stream with ws2
+    if (ctx->ws3_bytes < need) {
+      if (ctx->ws3) cudaFree(ctx->ws3);
+      ctx->ws3 = nullptr;
+      ctx->ws3_bytes = 0;
+      const size_t want = need < (size_t)(4 << 20) ? (size_t)(4 << 20) : need;
+      if (cudaMalloc(&ctx->ws3, want) != cudaSuccess) return segk_fail(ctx, SEGK_ENOMEM, "skinny wgrad workspace");
+      ctx->ws3_bytes = want;
     }
     if (Cout == 2)
-      conv_skinny_wgrad_partial_kernel<2><<<(unsigned)gx, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, (float*)ctx->ws2, npix, Cin);
+      conv_skinny_wgrad_partial_kernel<2><<<(unsigned)gx, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, (float*)ctx->ws3, npix, Cin);
     else
-      conv_skinny_wgrad_partial_kernel<4><<<(unsigned)gx, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, (float*)ctx->ws2, npix, Cin);
+      conv_skinny_wgrad_partial_kernel<4><<<(unsigned)gx, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, (float*)ctx->ws3, npix, Cin);
     SEGK_LAUNCHED(ctx, "conv_skinny_wgrad_partial");
     const int n = Cin * Cout;
-    sum_partials_rows_kernel<<<ceil_div(n, kThreads), kThreads, 0, st>>>((const float*)ctx->ws2, dw, (int)gx, n);
+    sum_partials_rows_kernel<<<ceil_div(n, kThreads), kThreads, 0, st>>>((const float*)ctx->ws3, dw, (int)gx, n);
     SEGK_LAUNCHED(ctx, "conv_skinny_wgrad_sum");
   } else if (K <= kTinyKMax && (kh & 1) && (kw & 1)) {
     const int gy = ceil_div(Cout, 64);

@@ -18,6 +18,7 @@ import torch
 
 from . import plan as P
 from .ops import Ops, conv_flops, deconv_flops
+from .overlap import LocalBuckets, SideStream
 
 
 def reference_init(shapes, seed: int = 1234, init: str = "ref"):
@@ -95,9 +96,12 @@ class Variables:
         """{reference variable name: numpy array} in reference layouts (checkpoint interchange)."""
         return OrderedDict((n, self.view(self.p, n).detach().cpu().numpy().copy()) for n in self.slots)
 
-    def repack(self, ops: Ops):
-        """fp32 masters -> bf16 kernel layouts for the tensor-core layers (after each update)."""
+    def repack(self, ops: Ops, only=None):
+        """fp32 masters -> bf16 kernel layouts for the tensor-core layers (after each update);
+        `only`: restrict to these layer names (per-bucket repack)."""
         for l in self.layers:
+            if only is not None and l.name not in only:
+                continue
             w = self.param(f"{l.name}/weights")
             if l.path == "tc" and l.kind == "conv":
                 self.wk[l.name], self.wd[l.name] = ops.pack_conv_weights(w, self.wk.get(l.name), self.wd.get(l.name))
@@ -127,7 +131,7 @@ class FCN:
     """FCN-8s builder with the reference's constructor signature (FCN.py:31-47)."""
 
     def __init__(self, x, keep_prob=1.0, num_classess=2, variables=None, init="ref", seed=1234, fc=4096,
-                 dropout_seed=42, world_size=1):
+                 dropout_seed=42, world_size=1, overlap=True):
         if not torch.cuda.is_available():
             raise RuntimeError("FCN needs a CUDA (sm_100a) device: the segmentation ops have no CPU fallback")
         x = self._as_image(x)
@@ -153,6 +157,7 @@ class FCN:
         self.x = x
         self._alloc()
         self._ran_forward = False
+        self.side = SideStream(self.device, enabled=overlap)
 
     # -- buffers ------------------------------------------------------------------------
     @staticmethod
@@ -203,7 +208,7 @@ class FCN:
         npix = N * self.H * self.W
         self.dlogits = torch.empty_like(self.logits)
         self.pred_u8 = torch.empty((N, self.H, self.W), dtype=torch.uint8, device=dev)
-        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.loss_sum = torch.zeros(2, dtype=torch.float32, device=dev)   # [sum, mean]
         self.cm = torch.zeros(4, dtype=torch.int64, device=dev)
         self.xent_ws = self.ops.xent_workspace(npix, dev)
         self.labels = torch.zeros((N, self.H, self.W), dtype=torch.uint8, device=dev)
@@ -306,7 +311,7 @@ class FCN:
         npix = self.N * self.H * self.W
         self.ops.softmax_xent(self.logits, self.labels, self.dlogits if with_grad else None, self.pred_u8,
                               self.loss_sum, None, self.xent_ws, 1.0 / (npix * self.world_size))
-        return self.loss_sum[0] / npix
+        return self.loss_sum[1]
 
     def confusion_matrix(self):
         """Road / non-road confusion counts cm[gt, pred] of the last forward (int64 2x2)."""
@@ -333,13 +338,15 @@ class FCN:
             if l.kind == "pool":
                 # MaxPoolGrad fused with the ReluGrad of the pre-pool conv output
                 dx = self._g(flip, xin)
+                self.side.before_write(dx)
                 ops.maxpool_bwd(dcur, self.idx[l.name], dx, act=xin)
                 dcur = dx
                 flip ^= 1
                 continue
             gw = V.grad(f"{l.name}/weights")
             gb = V.grad(f"{l.name}/{l.bias_name}")
-            ops.bias_grad(dcur, gb)
+            # BiasAddGrad only reads dcur: HBM-bound, off the critical path -> side stream
+            self.side.run(lambda d=dcur, g=gb: ops.bias_grad(d, g), reads=(dcur,))
             prev = L[i - 1] if i > 0 else None
             if l.kind == "deconv":
                 if l.path == "tc":
@@ -358,6 +365,7 @@ class FCN:
                 else:
                     dx = self._g(flip, xin)
                     flip ^= 1
+                self.side.before_write(dx)
                 mask = xin if (prev is not None and prev.kind == "conv" and prev.relu) else None
                 if l.path == "tc":
                     ops.deconv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.stride, relu_mask=mask)
@@ -385,6 +393,7 @@ class FCN:
                     res = {"pool4": self.dfuse_1, "pool3": self.dfuse_2}.get(prev.name)
                     dx = self._g(flip, xin)
                     flip ^= 1
+                    self.side.before_write(dx)
                     if l.path == "tc":
                         ops.conv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.k, relu_mask=mask, residual=res, scale=scale)
                     else:
@@ -457,6 +466,14 @@ class TrainStep:
 
     def __init__(self, net: FCN, opt, allreduce=None):
         self.net, self.opt, self.allreduce = net, opt, allreduce
+        self.local = None
+        if allreduce is None and getattr(net, "side", None) is not None and net.side.enabled:
+            if hasattr(net, "nodes"):
+                names = [n.name for n in net.nodes if n.kind in ("conv", "deconv")]
+                buckets = P.gradient_buckets_even(net.vars.slots, names)
+            else:
+                buckets = P.gradient_buckets(net.vars.slots)
+            self.local = LocalBuckets(net, opt, buckets)
 
     def __call__(self, feed_dict=None):
         net, opt = self.net, self.opt
@@ -465,15 +482,28 @@ class TrainStep:
         net.forward()
         loss = net.loss(with_grad=True)
         opt.t += 1
-        if self.allreduce is None:
+        if self.local is not None:
+            # single GPU: per-bucket optimizer update + repack on the side stream, in the shadow of backward
+            self.local.begin_step()
+            net.backward(after_layer=self.local.layer_done)
+            self.local.finish()
+        elif self.allreduce is None:
             net.backward()
+            net.side.join()
             opt.apply(net)
+            net.vars.repack(net.ops)
         else:
             self.allreduce.begin_step()
-            net.backward(after_layer=self.allreduce.layer_done)
+
+            def layer_done(name):
+                net.side.join()                   # this layer's bias gradients are part of the reduced arena
+                self.allreduce.layer_done(name)
+
+            net.backward(after_layer=layer_done)
+            net.side.join()
             for lo, hi in self.allreduce.finish():
                 opt.apply(net, lo, hi)
-        net.vars.repack(net.ops)
+            net.vars.repack(net.ops)
         net.step_count += 1
         net._ran_forward = False
         return loss

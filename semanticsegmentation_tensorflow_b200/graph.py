@@ -28,6 +28,7 @@ import torch
 from . import plan as P
 from .fcn import _Feed
 from .ops import Ops, conv_flops
+from .overlap import SideStream
 
 BN_EPS = 1e-3          # tf.layers.batch_normalization default epsilon
 BN_SCALE = 1.0 / math.sqrt(1.0 + BN_EPS)   # moving_variance stays 1, moving_mean 0 (never updated)
@@ -177,12 +178,12 @@ class _Vars:
     def export(self):
         return OrderedDict((n, self.view(self.p, n).detach().cpu().numpy().copy()) for n in self.slots)
 
-    def repack(self, ops):
-        self._repack(ops)
+    def repack(self, ops, only=None):
+        self._repack(ops, only)
 
 
 class GraphNet:
-    def __init__(self, x, num_classes, nodes, variables=None, init="ref", seed=1234, world_size=1):
+    def __init__(self, x, num_classes, nodes, variables=None, init="ref", seed=1234, world_size=1, overlap=True):
         if not torch.cuda.is_available():
             raise RuntimeError("GraphNet needs a CUDA (sm_100a) device: the segmentation ops have no CPU fallback")
         x = torch.as_tensor(x)
@@ -206,6 +207,7 @@ class GraphNet:
         self._plan()
         self._repack(self.ops)
         self._ran_forward = False
+        self.side = SideStream(self.device, enabled=overlap)
 
     # ---- planning ---------------------------------------------------------------------------
     def _route(self, n, cin):
@@ -254,15 +256,17 @@ class GraphNet:
         self.dlogits_bf16 = torch.empty(shape[last], dtype=bf, device=dev)
         npix = N * self.H * self.W
         self.pred_u8 = torch.empty((N, self.H, self.W), dtype=torch.uint8, device=dev)
-        self.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.loss_sum = torch.zeros(2, dtype=torch.float32, device=dev)   # [sum, mean]
         self.xent_ws = self.ops.xent_workspace(npix, dev)
         self.bn_ws = torch.empty(8 << 20, dtype=torch.uint8, device=dev)
         self.labels = torch.zeros((N, self.H, self.W), dtype=torch.uint8, device=dev)
 
-    def _repack(self, ops):
+    def _repack(self, ops, only=None):
         V = self.vars
         for n in self.nodes:
             if n.kind not in ("conv", "deconv"):
+                continue
+            if only is not None and n.name not in only and n.bn_scope not in only:
                 continue
             w = V.param(f"{n.name}/weights")
             if n.bn:   # fold gamma / sqrt(1 + eps) into the weights (columns = Cout for HWIO)
@@ -353,7 +357,7 @@ class GraphNet:
         npix = self.N * self.H * self.W
         self.ops.softmax_xent(self.logits, self.labels, self.dlogits if with_grad else None, self.pred_u8,
                               self.loss_sum, None, self.xent_ws, 1.0 / (npix * self.world_size))
-        return self.loss_sum[0] / npix
+        return self.loss_sum[1]
 
     def confusion_matrix(self):
         cm = torch.zeros(4, dtype=torch.int64, device=self.device)
@@ -398,12 +402,14 @@ class GraphNet:
             dz = G
             if r == "small" and G.dtype == torch.float32:
                 dz = ops.cast_to_bf16(G, self.dlogits_bf16)
-            if n.bn:
-                ops.bias_grad(dz, V.grad(f"{n.bn_scope}/beta"))
-                ops.bn_gamma_grad(dz, self.act[n.name], V.param(f"{n.bn_scope}/beta"), V.param(f"{n.bn_scope}/gamma"),
-                                  V.grad(f"{n.bn_scope}/gamma"), self.bn_ws)
+            if n.bn:      # d(beta), d(gamma): HBM-bound column reductions off the critical path -> side stream
+                def bn_grads(dz=dz, n=n):
+                    ops.bias_grad(dz, V.grad(f"{n.bn_scope}/beta"))
+                    ops.bn_gamma_grad(dz, self.act[n.name], V.param(f"{n.bn_scope}/beta"),
+                                      V.param(f"{n.bn_scope}/gamma"), V.grad(f"{n.bn_scope}/gamma"), self.bn_ws)
+                self.side.run(bn_grads)
             elif n.bias:
-                ops.bias_grad(dz, V.grad(f"{n.name}/biases"))
+                self.side.run(lambda dz=dz, n=n: ops.bias_grad(dz, V.grad(f"{n.name}/biases")))
             # weight gradient (of the folded weights; unfold the BN scale afterwards)
             if n.kind == "deconv":
                 ops.deconv2d_wgrad(x, dz, gw, n.k, n.stride)

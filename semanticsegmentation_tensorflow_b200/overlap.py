@@ -1,0 +1,84 @@
+"""Second CUDA stream for the HBM-bound work that is off the tensor-core critical path of a training
+step: BiasAddGrad of each layer, and the optimizer update + bf16 weight repack of a gradient bucket as
+soon as that bucket is complete.  The persistent tensor-core kernels hold one 192-thread CTA per SM
+(~200 KB of shared memory), so these streaming kernels co-reside on the same SMs and run in the
+shadow of the conv GEMMs instead of after them."""
+from __future__ import annotations
+
+import torch
+
+
+class SideStream:
+    def __init__(self, device, enabled=True):
+        self.enabled = enabled
+        self.stream = torch.cuda.Stream(device) if enabled else None
+        self._reads = {}          # storage ptr -> event after the last side-stream read of that buffer
+
+    def run(self, fn, reads=()):
+        """Enqueue fn() on the side stream, ordered after everything enqueued on the current stream so
+        far.  `reads`: tensors the side work reads that the main stream may later overwrite."""
+        if not self.enabled:
+            fn()
+            return
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            fn()
+        if reads:
+            done = torch.cuda.Event()
+            done.record(self.stream)
+            for t in reads:
+                self._reads[t.untyped_storage().data_ptr()] = done
+
+    def before_write(self, t):
+        """Call before the main stream overwrites tensor t."""
+        if not self.enabled:
+            return
+        ev = self._reads.pop(t.untyped_storage().data_ptr(), None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def join(self):
+        if self.enabled:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self._reads.clear()
+
+
+class LocalBuckets:
+    """Single-GPU counterpart of dp.BucketedAllReduce: when a gradient bucket is complete, its optimizer
+    update and weight repack are issued on the side stream while backward continues."""
+
+    def __init__(self, net, opt, buckets):
+        self.net, self.opt, self.buckets = net, opt, list(buckets)
+        slots = net.vars.slots
+        self.layers = []
+        for lo, hi, _ in self.buckets:
+            self.layers.append({n.split("/")[0] for n, s in slots.items() if lo <= s.offset < hi})
+        self._next = 0
+
+    def begin_step(self):
+        self._next = 0
+
+    def _fire(self, b):
+        lo, hi, _ = self.buckets[b]
+        names = self.layers[b]
+        net, opt = self.net, self.opt
+
+        def work():
+            opt.apply(net, lo, hi)
+            net.vars.repack(net.ops, names)
+
+        net.side.run(work)
+
+    def layer_done(self, name):
+        while self._next < len(self.buckets) and self.buckets[self._next][2] == name:
+            self._fire(self._next)
+            self._next += 1
+
+    def finish(self):
+        while self._next < len(self.buckets):
+            self._fire(self._next)
+            self._next += 1
+        self.net.side.join()

@@ -61,19 +61,20 @@ def test_softmax_xent_grad_argmax_confusion(ops, cuda_device, npix):
     labd = torch.as_tensor(lab).to(cuda_device)
     dl = torch.empty_like(ld)
     pred = torch.empty(npix, dtype=torch.uint8, device=cuda_device)
-    loss_sum = torch.zeros(1, dtype=torch.float32, device=cuda_device)
+    loss_sum = torch.zeros(2, dtype=torch.float32, device=cuda_device)
     cm = torch.zeros(4, dtype=torch.int64, device=cuda_device)
     ws = ops.xent_workspace(npix, cuda_device)
     ops.softmax_xent(ld, labd, dl, pred, loss_sum, cm, ws, 1.0 / npix)
     torch.cuda.synchronize()
     assert abs(float(loss_sum[0]) / npix - float(per.mean())) <= 1e-5 * max(1.0, float(per.mean()))
+    assert abs(float(loss_sum[1]) - float(loss_sum[0]) / npix) <= 1e-6 * max(1.0, float(loss_sum[1]))
     np.testing.assert_allclose(host(dl), lt.grad.numpy(), rtol=1e-5, atol=1e-7 / npix)
     pred_ref = T.argmax_last(torch.tensor(lg)).numpy().astype(np.uint8)
     assert np.array_equal(pred.cpu().numpy(), pred_ref)                       # bit-exact, ties -> 0
     cm_ref = T.confusion_matrix(lab, pred_ref)
     assert np.array_equal(cm.cpu().numpy().reshape(2, 2), cm_ref)             # bit-exact
     # deterministic: same bits twice
-    loss2 = torch.zeros(1, dtype=torch.float32, device=cuda_device)
+    loss2 = torch.zeros(2, dtype=torch.float32, device=cuda_device)
     ops.softmax_xent(ld, labd, None, None, loss2, None, ws, 1.0)
     torch.cuda.synchronize()
     assert float(loss2[0]) == float(loss_sum[0])

@@ -106,7 +106,7 @@ def test_xent_and_confusion_full_size_properties(ops, cuda_device):
     lab = torch.randint(0, 2, (npix,), generator=g, device=cuda_device, dtype=torch.uint8)
     dl = torch.empty_like(lg)
     pred = torch.empty(npix, dtype=torch.uint8, device=cuda_device)
-    loss_sum = torch.zeros(1, device=cuda_device)
+    loss_sum = torch.zeros(2, device=cuda_device)
     cm = torch.zeros(4, dtype=torch.int64, device=cuda_device)
     ops.softmax_xent(lg, lab, dl, pred, loss_sum, cm, ops.xent_workspace(npix, cuda_device), 1.0 / npix)
     torch.cuda.synchronize()
