@@ -215,6 +215,12 @@ int segk_softmax_xent_fwd_bwd(segk_ctx* ctx, const float* logits, const uint8_t*
  * mask u8 [npix] = prob[...,1] > 0.5 (may be NULL) */
 int segk_softmax_infer(segk_ctx* ctx, const float* logits, float* prob, uint8_t* mask,
                        int64_t npix, int C, void* stream);
+/* paste_mask (FCN.py:203-211): the road overlay of gen_test_output — where mask != 0 the RGBA colour
+ * ([0,255,0,127] in the reference) is alpha-blended over the u8 image (C = 3 or 4 channels; for
+ * C = 4 the alpha channel is blended too, as PIL's Image.paste does), bit-exact with PIL's
+ * integer blend; elsewhere the image is copied. */
+int segk_overlay_mask(segk_ctx* ctx, const uint8_t* image, const uint8_t* mask, uint8_t* out,
+                      int64_t npix, int C, int r, int g, int b, int a, void* stream);
 /* road / non-road confusion matrix (new): cm[gt*2+pred] += counts */
 int segk_confusion_matrix(segk_ctx* ctx, const uint8_t* gt, const uint8_t* pred, int64_t* cm,
                           int64_t npix, void* stream);

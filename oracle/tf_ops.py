@@ -133,6 +133,21 @@ def iou_road(cm: np.ndarray) -> float:
     return float(cm[1, 1]) / float(d) if d else 0.0
 
 
+def paste_mask(image_u8: np.ndarray, road_prob: np.ndarray, color=(0, 255, 0, 127)) -> np.ndarray:
+    """paste_mask (FCN.py:203-211) restated with NumPy: segmentation = prob > 0.5; the RGBA colour is
+    pasted with itself as mask, i.e. PIL's integer alpha blend t = dst*(255-a) + src*a,
+    out = ((t+128) + ((t+128) >> 8)) >> 8 on every channel of the image (checked against PIL itself in
+    tests/test_oracle.py)."""
+    seg = road_prob > 0.5
+    img = image_u8.astype(np.int64)
+    a = int(color[3])
+    out = image_u8.copy()
+    for c in range(image_u8.shape[-1]):
+        t = img[..., c] * (255 - a) + int(color[c]) * a + 128
+        out[..., c] = np.where(seg, (t + (t >> 8)) >> 8, img[..., c]).astype(np.uint8)
+    return out
+
+
 def adam_tf_step(p, m, v, g, t: int, lr=1e-4, b1=0.9, b2=0.999, eps=1e-8):
     """tf.train.AdamOptimizer ApplyAdam (FCN.py:338-340), TF formula (epsilon outside the
     bias correction): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps).

@@ -313,6 +313,29 @@ __global__ void __launch_bounds__(kThreads) confusion_kernel(const uint8_t* __re
     atomicAdd(&cm[threadIdx.x], (unsigned long long)cm_sh[threadIdx.x]);
 }
 
+// paste_mask (FCN.py:203-211): where mask != 0 blend the RGBA colour over the image with PIL's
+// integer arithmetic  t = dst*(255-a) + src*a ; out = ((t+128) + ((t+128) >> 8)) >> 8 ; else copy.
+__global__ void __launch_bounds__(kThreads) overlay_kernel(const uint8_t* __restrict__ img,
+                                                           const uint8_t* __restrict__ mask,
+                                                           uint8_t* __restrict__ out, int64_t npix, int C,
+                                                           uint32_t rgba) {
+  const uint32_t a = rgba >> 24;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    const bool on = mask[p] != 0;
+    for (int c = 0; c < C; ++c) {
+      const uint32_t d = img[p * C + c];
+      uint32_t v = d;
+      if (on) {
+        const uint32_t s = (rgba >> (8 * c)) & 0xffu;
+        const uint32_t t = d * (255u - a) + s * a + 128u;
+        v = (t + (t >> 8)) >> 8;
+      }
+      out[p * C + c] = (uint8_t)v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // optimizers (FCN.py:338-340).  28 B/param: p,m,v read+write (24) + g read (4).
 // ------------------------------------------------------------------------------------
@@ -597,6 +620,17 @@ int segk_softmax_infer(segk_ctx* ctx, const float* logits, float* prob, uint8_t*
   softmax_infer_kernel<<<stream_grid(ctx, npix), kThreads, 0, (cudaStream_t)stream>>>(
       logits, prob, mask, npix, C);
   SEGK_LAUNCHED(ctx, "softmax_infer");
+  return SEGK_OK;
+}
+
+int segk_overlay_mask(segk_ctx* ctx, const uint8_t* image, const uint8_t* mask, uint8_t* out, int64_t npix,
+                      int C, int r, int g, int b, int a, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, image && mask && out && npix > 0 && (C == 3 || C == 4), "overlay: bad args (C must be 3 or 4)");
+  const uint32_t rgba = (uint32_t)(r & 255) | ((uint32_t)(g & 255) << 8) | ((uint32_t)(b & 255) << 16) |
+                        ((uint32_t)(a & 255) << 24);
+  overlay_kernel<<<stream_grid(ctx, npix), kThreads, 0, (cudaStream_t)stream>>>(image, mask, out, npix, C, rgba);
+  SEGK_LAUNCHED(ctx, "overlay");
   return SEGK_OK;
 }
 

@@ -419,6 +419,15 @@ class FCN:
         return prob, mask
 
 
+def gen_test_output(net, images):
+    """gen_test_output of FCN.py:213-233 without the file IO: for each u8 NHWC batch run the softmax at
+    keep_prob 1.0, threshold the road probability at 0.5 and paste the [0,255,0,127] overlay
+    (FCN.py:229-231).  Yields the overlaid u8 batches (device tensors)."""
+    for batch in images:
+        prob, mask = net.infer(batch)
+        yield net.ops.overlay_mask(net.x, mask)
+
+
 class AdamOptimizer:
     """tf.train.AdamOptimizer(learning_rate) with TF's update formula (FCN.py:338)."""
 
@@ -467,7 +476,7 @@ class TrainStep:
     def __init__(self, net: FCN, opt, allreduce=None):
         self.net, self.opt, self.allreduce = net, opt, allreduce
         self.local = None
-        if allreduce is None and getattr(net, "side", None) is not None and net.side.enabled:
+        if allreduce is None and getattr(net, "side", None) is not None and net.side.stream is not None:
             if hasattr(net, "nodes"):
                 names = [n.name for n in net.nodes if n.kind in ("conv", "deconv")]
                 buckets = P.gradient_buckets_even(net.vars.slots, names)
@@ -482,7 +491,7 @@ class TrainStep:
         net.forward()
         loss = net.loss(with_grad=True)
         opt.t += 1
-        if self.local is not None:
+        if self.local is not None and net.side.enabled:
             # single GPU: per-bucket optimizer update + repack on the side stream, in the shadow of backward
             self.local.begin_step()
             net.backward(after_layer=self.local.layer_done)

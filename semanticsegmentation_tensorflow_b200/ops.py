@@ -322,6 +322,14 @@ class Ops:
         c = logits.shape[-1]
         self.call("segk_softmax_infer", _p(logits), _p(prob), _p(mask), logits.numel() // c, c, _stream())
 
+    def overlay_mask(self, image, mask, out=None, color=(0, 255, 0, 127)):
+        """paste_mask of FCN.py:203-211 on the GPU (u8 NHWC image, u8 mask)."""
+        if out is None:
+            out = torch.empty_like(image)
+        self.call("segk_overlay_mask", _p(image), _p(mask), _p(out), mask.numel(), image.shape[-1], int(color[0]),
+                  int(color[1]), int(color[2]), int(color[3]), _stream())
+        return out
+
     def confusion_matrix(self, gt, pred, cm):
         self.call("segk_confusion_matrix", _p(gt), _p(pred), _p(cm), gt.numel(), _stream())
         return cm

@@ -191,3 +191,14 @@ def test_bias_grad_and_cast(ops, cuda_device):
     ops.cast_to_bf16(torch.as_tensor(img).to(cuda_device), out)
     torch.cuda.synchronize()
     assert np.array_equal(host(out), img.astype(np.float32))
+
+
+@pytest.mark.parametrize("c", [3, 4])
+def test_overlay_mask_bit_exact(ops, cuda_device, c):
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 256, (2, 37, 53, c), dtype=np.uint8)
+    prob = rng.random((2, 37, 53)).astype(np.float32)
+    mask = (prob > 0.5).astype(np.uint8)
+    out = ops.overlay_mask(torch.as_tensor(img).to(cuda_device), torch.as_tensor(mask).to(cuda_device))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), T.paste_mask(img, prob))

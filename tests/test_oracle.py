@@ -132,3 +132,18 @@ def test_fd_gradient_check_small_graph():
         return T.softmax_cross_entropy_with_logits(lg, lab).mean()
 
     assert torch.autograd.gradcheck(f, (w1, wt), eps=1e-6, atol=1e-5)
+
+
+def test_paste_mask_restatement_matches_pil():
+    """FCN.py:203-211 uses scipy.misc.toimage + PIL Image.paste(mask=mask): pin the NumPy restatement to PIL."""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    for c in (3, 4):
+        img = rng.integers(0, 256, (20, 33, c), dtype=np.uint8)
+        prob = rng.random((20, 33)).astype(np.float32)
+        seg = (prob > 0.5).reshape(20, 33, 1)
+        mask = np.dot(seg, np.array([[0, 255, 0, 127]])).astype(np.uint8)          # FCN.py:207
+        m = Image.fromarray(mask, mode="RGBA")
+        im = Image.fromarray(img, mode="RGB" if c == 3 else "RGBA")
+        im.paste(m, box=None, mask=m)                                              # FCN.py:209
+        assert np.array_equal(T.paste_mask(img, prob), np.array(im))
