@@ -256,11 +256,17 @@ def run_gpu(args):
         with open(args.layers_out, "w") as f:
             json.dump(rows, f, indent=1)
     peaks = measured_peaks()
-    # dominant kernel family by device time
-    fam_ms = {k: v["ms"] for k, v in prof.items()}
-    total_prof_ms = sum(fam_ms.values())
-    dom = max(fam_ms, key=fam_ms.get)
-    d = prof[dom]
+    # dominant kernel = the (entry point, shape) with the largest share of device time in the step
+    total_prof_ms = sum(v["ms"] for v in prof.values())
+    dom = max(prof_detail, key=lambda k: prof_detail[k]["ms"])
+    d = prof_detail[dom]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    ncu = {}
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            ncu = json.load(f).get(dom, {})
+        traffic = ncu.get("dram_bytes")
     if d["unit"] == "flop":
         achieved = d["work"] / (d["ms"] / 1e3) / 1e12
         peak, unit, bound = peaks["bf16_tflops_sustained"], "TFLOP/s", "tensor"
@@ -268,11 +274,20 @@ def run_gpu(args):
         achieved = d["work"] / (d["ms"] / 1e3) / 1e9
         peak, unit, bound = peaks["hbm_gbs"], "GB/s", "hbm"
     roofline = {"bound": bound, "kernel": dom, "achieved": achieved, "peak": peak, "unit": unit,
-                "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + (" sustained" if bound == "tensor" else ""),
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/ncu_traffic.json)" if traffic else None,
+                "ncu_tensor_pipe_active_pct": ncu.get("tensor_pipe_active_pct"),
+                "peak_source": peaks["source"] + (" sustained" if bound == "tensor" else ""),
+                "algorithmic_per_launch": d["work"] / d["launches"], "algorithmic_unit": d["unit"],
                 "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
                 "share_of_step": d["ms"] / total_prof_ms if total_prof_ms else None,
                 "measured_in": "second timed pass of the same K steps with per-launch CUDA events, side stream "
                                "off so each event pair brackets one kernel; that pass ran at %.3f ms/step" % ms_serial}
+    conv = [v for k, v in prof.items() if v["unit"] == "flop" and ("conv2d_fwd" in k or "conv2d_dgrad" in k or "conv2d_wgrad" in k) and "small" not in k]
+    conv_ms = sum(v["ms"] for v in conv)
+    conv_gemm = {"ms_per_step": conv_ms / steps, "tflops": sum(v["work"] for v in conv) / (conv_ms / 1e3) / 1e12 if conv_ms else None,
+                 "frac_of_sustained_peak": (sum(v["work"] for v in conv) / (conv_ms / 1e3) / 1e12 / peaks["bf16_tflops_sustained"]) if conv_ms else None,
+                 "frac_of_burst_peak": (sum(v["work"] for v in conv) / (conv_ms / 1e3) / 1e12 / peaks["bf16_tflops"]) if conv_ms else None}
     families = {k: {"ms_per_step": v["ms"] / steps, "launches_per_step": v["launches"] / steps,
                     ("tflops" if v["unit"] == "flop" else "gbs"):
                         (v["work"] / (v["ms"] / 1e3) / (1e12 if v["unit"] == "flop" else 1e9)) if v["ms"] > 0 else None}
@@ -300,6 +315,7 @@ def run_gpu(args):
         "roofline": roofline,
         "tensor_util_step": {"train_tflops_per_gpu": step_tflops, "frac_of_peak": step_tflops / peaks["bf16_tflops_sustained"],
                              "flops_per_image": train_gflop * 1e9, "convention": "valid-tap fwd+dgrad+wgrad"},
+        "conv_gemms": conv_gemm,
         "kernel_families": families,
         "cpu_baseline": cpu_baseline,
         "final_loss": final_loss,
