@@ -256,17 +256,24 @@ def run_gpu(args):
         with open(args.layers_out, "w") as f:
             json.dump(rows, f, indent=1)
     peaks = measured_peaks()
-    # dominant kernel = the (entry point, shape) with the largest share of device time in the step
+    # dominant kernel = the C entry point (one CUDA kernel template behind it) with the largest share of
+    # device time in the step; `traffic` = ncu DRAM bytes per launch averaged over that entry point's
+    # launches of one step (profiles/ncu_traffic.json, keyed by call shape), when every shape was captured
     total_prof_ms = sum(v["ms"] for v in prof.values())
-    dom = max(prof_detail, key=lambda k: prof_detail[k]["ms"])
-    d = prof_detail[dom]
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[dom]
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     ncu = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            ncu = json.load(f).get(dom, {})
-        traffic = ncu.get("dram_bytes")
+            table = json.load(f)
+        shapes = {k: v for k, v in prof_detail.items() if k.startswith(dom + "[")}
+        if shapes and all(k in table for k in shapes):
+            tot_b = sum(table[k]["dram_bytes"] * v["launches"] for k, v in shapes.items())
+            traffic = tot_b / sum(v["launches"] for v in shapes.values())
+            tp = sum(table[k]["tensor_pipe_active_pct"] * v["ms"] for k, v in shapes.items()) / sum(v["ms"] for v in shapes.values())
+            ncu = {"tensor_pipe_active_pct": tp}
     if d["unit"] == "flop":
         achieved = d["work"] / (d["ms"] / 1e3) / 1e12
         peak, unit, bound = peaks["bf16_tflops_sustained"], "TFLOP/s", "tensor"

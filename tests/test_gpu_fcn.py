@@ -210,5 +210,6 @@ def test_checkpoint_roundtrip_with_adam_slots(cuda_device, tmp_path):
     l3b = float(step2({net2.image: xd, net2.annotation: ld}))
     torch.cuda.synchronize()
     assert abs(l3 - l3b) <= 1e-5 * abs(l3)
-    # split-K wgrad atomics make gradients order-dependent at the 1e-7 level; parameters agree to that
-    assert torch.allclose(net.vars.p, net2.vars.p, rtol=1e-4, atol=1e-7)
+    # fp32 atomics (split-K) make the step order-dependent at rounding level, and a bf16 rounding flip
+    # changes an element's gradient by ~0.4 %: parameters agree to a few per cent of one Adam step (1e-4)
+    assert float((net.vars.p - net2.vars.p).abs().max()) <= 5e-6
