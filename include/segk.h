@@ -44,6 +44,10 @@ const char* segk_last_error(segk_ctx* ctx);
 /* number of kernels launched through this ctx since creation (bench.py gpu_launches) */
 int64_t segk_launch_count(segk_ctx* ctx);
 int segk_sm_count(segk_ctx* ctx);
+/* Tuning overrides (also read once at segk_create from SEGK_SLAB / SEGK_FORCE_BN / SEGK_FORCE_KSPLIT /
+ * SEGK_FORCE_WSPLIT): key in {"slab" (0 off, 1 auto, 2 wherever legal), "force_bn" (0|64|128|256),
+ * "force_ksplit", "force_wsplit" (0 = heuristic)}.  Results are identical under every setting. */
+int segk_set_tuning(segk_ctx* ctx, const char* key, int value);
 
 /* ---- epilogue flags for the conv family ------------------------------------------------ */
 #define SEGK_EPI_RELU 1u      /* y = max(y,0) after bias (+residual)            */

@@ -48,6 +48,8 @@ def parse_header(path: str = _HEADER):
 
 
 def _ctype(t: str):
+    if t == "const char*":
+        return ctypes.c_char_p
     if t.endswith("*"):
         return ctypes.c_void_p
     return _SCALARS[t]
@@ -114,6 +116,9 @@ class Context:
         rc = getattr(self.c, name)(self.h, *args)
         if rc != 0:
             raise SegkError(rc, name, self.last_error())
+
+    def set_tuning(self, key: str, value: int):
+        self.call("segk_set_tuning", key.encode(), int(value))
 
     @property
     def launches(self) -> int:

@@ -33,6 +33,10 @@ int segk_create(int device, segk_ctx** out) {
     return SEGK_ECUDA;
   }
   ctx->encode_tiled = reinterpret_cast<decltype(ctx->encode_tiled)>(fn);
+  if (segk_tc_init(ctx) != SEGK_OK) {
+    delete ctx;
+    return SEGK_ECUDA;
+  }
   *out = ctx;
   return SEGK_OK;
 }
@@ -46,6 +50,17 @@ int segk_destroy(segk_ctx* ctx) {
 }
 
 const char* segk_last_error(segk_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+int segk_set_tuning(segk_ctx* ctx, const char* key, int value) {
+  if (!ctx) return SEGK_EINVAL;
+  if (!ctx || !key) return SEGK_EINVAL;
+  if (!strcmp(key, "slab")) ctx->slab_mode = value;
+  else if (!strcmp(key, "force_bn")) ctx->force_bn = value;
+  else if (!strcmp(key, "force_ksplit")) ctx->force_ksplit = value;
+  else if (!strcmp(key, "force_wsplit")) ctx->force_wsplit = value;
+  else return segk_fail(ctx, SEGK_EINVAL, "set_tuning: unknown key '%s'", key);
+  return SEGK_OK;
+}
 
 int64_t segk_launch_count(segk_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 

@@ -18,6 +18,9 @@ struct segk_ctx {
   int sm_count = 148;
   std::atomic<int64_t> launches{0};
   char err[512] = {0};
+  // tuning overrides, read once from the environment (tools/sweep_tiles.py); 0 = heuristics
+  int force_bn = 0, force_ksplit = 0, force_wsplit = 0;
+  int slab_mode = 1;        // SEGK_SLAB: 0 off, 1 auto, 2 wherever legal
   void* ws = nullptr;       // grow-only scratch for split-K partial sums (tcconv.cu)
   size_t ws_bytes = 0;
   void* ws2 = nullptr;      // grow-only scratch for per-block BiasAddGrad partials (elementwise.cu)
@@ -30,6 +33,8 @@ struct segk_ctx {
                            CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                            CUtensorMapFloatOOBfill) = nullptr;
 };
+
+int segk_tc_init(segk_ctx* ctx);   // tcconv.cu
 
 inline int segk_fail(segk_ctx* ctx, int code, const char* fmt, ...) {
   if (ctx) {

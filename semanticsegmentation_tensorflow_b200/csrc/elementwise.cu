@@ -553,6 +553,7 @@ extern "C" {
 
 int segk_maxpool2x2_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int N, int H, int W,
                         int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, x && y && idx, "maxpool_fwd: null pointer");
   SEGK_REQUIRE(ctx, N > 0 && H >= 2 && W >= 2 && (H % 2 == 0) && (W % 2 == 0) && C % 8 == 0,
                "maxpool_fwd: need even H,W and C%%8==0 (got %dx%dx%dx%d)", N, H, W, C);
@@ -565,6 +566,7 @@ int segk_maxpool2x2_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int
 
 int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const void* act,
                         const void* residual, void* dx, int N, int H, int W, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, dy && idx && dx, "maxpool_bwd: null pointer");
   SEGK_REQUIRE(ctx, N > 0 && H >= 2 && W >= 2 && (H % 2 == 0) && (W % 2 == 0) && C % 8 == 0,
                "maxpool_bwd: need even H,W and C%%8==0 (got %dx%dx%dx%d)", N, H, W, C);
@@ -577,6 +579,7 @@ int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const
 
 int segk_dropout(segk_ctx* ctx, const void* x, void* y, const uint8_t* mask, int64_t n,
                  float keep_prob, uint64_t seed, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, x && y && n > 0, "dropout: null pointer / empty");
   SEGK_REQUIRE(ctx, keep_prob > 0.f && keep_prob <= 1.f, "dropout: keep_prob %f out of (0,1]",
                keep_prob);
@@ -616,6 +619,7 @@ int segk_softmax_xent_fwd_bwd(segk_ctx* ctx, const float* logits, const uint8_t*
 
 int segk_softmax_infer(segk_ctx* ctx, const float* logits, float* prob, uint8_t* mask, int64_t npix,
                        int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, logits && (prob || mask) && npix > 0 && C >= 2, "softmax_infer: bad args");
   softmax_infer_kernel<<<stream_grid(ctx, npix), kThreads, 0, (cudaStream_t)stream>>>(
       logits, prob, mask, npix, C);
@@ -636,6 +640,7 @@ int segk_overlay_mask(segk_ctx* ctx, const uint8_t* image, const uint8_t* mask, 
 
 int segk_confusion_matrix(segk_ctx* ctx, const uint8_t* gt, const uint8_t* pred, int64_t* cm,
                           int64_t npix, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, gt && pred && cm && npix > 0, "confusion: bad args");
   SEGK_REQUIRE(ctx, (((uintptr_t)gt | (uintptr_t)pred) & 15) == 0, "confusion: 16-byte alignment");
   // 2 blocks / SM: each block ends with 4 global atomics on the same 4 counters (serialised in L2)
@@ -647,6 +652,7 @@ int segk_confusion_matrix(segk_ctx* ctx, const uint8_t* gt, const uint8_t* pred,
 
 int segk_adam_step(segk_ctx* ctx, float* p, float* m, float* v, const float* g, int64_t n, float lr_t,
                    float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, p && m && v && g && n > 0, "adam: bad args");
   SEGK_REQUIRE(ctx, (((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)g) & 15) == 0,
                "adam: arenas must be 16-byte aligned");
@@ -658,6 +664,7 @@ int segk_adam_step(segk_ctx* ctx, float* p, float* m, float* v, const float* g, 
 
 int segk_momentum_step(segk_ctx* ctx, float* p, float* a, const float* g, int64_t n, float lr,
                        float mu, float grad_scale, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, p && a && g && n > 0, "momentum: bad args");
   momentum_kernel<<<stream_grid(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(p, a, g, n, lr, mu,
                                                                              grad_scale);
@@ -666,6 +673,7 @@ int segk_momentum_step(segk_ctx* ctx, float* p, float* a, const float* g, int64_
 }
 
 int segk_cast_to_bf16(segk_ctx* ctx, const void* x, int x_dtype, void* y, int64_t n, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, x && y && n > 0, "cast: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   if (x_dtype == 1)
@@ -680,6 +688,7 @@ int segk_cast_to_bf16(segk_ctx* ctx, const void* x, int x_dtype, void* y, int64_
 
 int segk_bias_grad(segk_ctx* ctx, const void* dy, int dy_is_f32, float* db, int64_t rows, int C,
                    void* stream) {
+  if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, dy && db && rows > 0 && C > 0, "bias_grad: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   if (!dy_is_f32 && C % 8 == 0 && (((uintptr_t)dy) & 15) == 0) {

@@ -917,14 +917,15 @@ int encode_weight_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int K, in
   return SEGK_OK;
 }
 
-// tuning overrides for sweeps (tools/sweep_tiles.py); 0 / unset = use the heuristics
-int env_int(const char* name) {
+// tuning overrides for sweeps (tools/sweep_tiles.py), read once per context in segk_tc_init;
+// 0 = use the heuristics
+int env_int(const char* name, int dflt = 0) {
   const char* v = getenv(name);
-  return v ? atoi(v) : 0;
+  return v ? atoi(v) : dflt;
 }
 
-int pick_block_n(int Cout) {
-  const int f = env_int("SEGK_FORCE_BN");
+int pick_block_n(const segk_ctx* ctx, int Cout) {
+  const int f = ctx->force_bn;
   if ((f == 64 || f == 128 || f == 256) && Cout % f == 0) return f;
   if (Cout % 256 == 0) return 256;
   if (Cout % 128 == 0) return 128;
@@ -935,12 +936,6 @@ template <int BLOCK_N>
 int launch_igemm_t(segk_ctx* ctx, const TensorMaps& maps, const IgemmParams& p, const TapTable& taps, int grid,
                    cudaStream_t st) {
   using C = Cfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "igemm smem attr: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
   igemm_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(maps, p, taps);
   SEGK_LAUNCHED(ctx, "igemm");
   return SEGK_OK;
@@ -961,12 +956,6 @@ template <int BLOCK_N>
 int launch_wgrad_t(segk_ctx* ctx, const TensorMaps& maps, const WgradParams& p, const TapTable& taps, int grid,
                    cudaStream_t st) {
   using C = WCfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "wgrad smem attr: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
   wgrad_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(maps, p, taps);
   SEGK_LAUNCHED(ctx, "wgrad");
   return SEGK_OK;
@@ -975,20 +964,14 @@ int launch_wgrad_t(segk_ctx* ctx, const TensorMaps& maps, const WgradParams& p, 
 template <int BLOCK_N>
 int launch_slab_t(segk_ctx* ctx, const TensorMaps& maps, const SlabParams& p, int grid, cudaStream_t st) {
   using C = SlabCfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(slab_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-    if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "slab smem attr: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
   slab_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(maps, p);
   SEGK_LAUNCHED(ctx, "slab");
   return SEGK_OK;
 }
 
 // 3x3 layers on large maps whose GEMM-N is small are activation-traffic bound in the tap-wise igemm
-bool slab_applicable(int N, int H, int W, int Ck, int Cn, int kh, int kw) {
-  const int mode = getenv("SEGK_SLAB") ? atoi(getenv("SEGK_SLAB")) : 1;   // 0 off, 1 auto, 2 whenever legal
+bool slab_applicable(const segk_ctx* ctx, int N, int H, int W, int Ck, int Cn, int kh, int kw) {
+  const int mode = ctx->slab_mode;   // 0 off, 1 auto, 2 whenever legal
   if (mode == 0) return false;
   const bool legal = kh == 3 && kw == 3 && H % kSlabH == 0 && W >= kSlabWV && Ck % 64 == 0 && Cn % 64 == 0;
   if (!legal) return false;
@@ -999,7 +982,7 @@ bool slab_applicable(int N, int H, int W, int Ck, int Cn, int kh, int kw) {
 int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, const float* bias, const void* residual,
               const void* mask, float scale, int relu, int out_f32, void* y, int N, int H, int W, int Ck, int Cn,
               void* stream) {
-  const int block_n = pick_block_n(Cn);
+  const int block_n = pick_block_n(ctx, Cn);
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Ck, Ck, (int64_t)W * Ck, (int64_t)H * W * Ck, kSlabP, kSlabH + 2, 1);
@@ -1046,11 +1029,11 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
                kMaxTaps, kh, kw);
   SEGK_REQUIRE(ctx, (((uintptr_t)x | (uintptr_t)wt | (uintptr_t)y | (uintptr_t)residual | (uintptr_t)mask) & 15) == 0,
                "%s: pointers must be 16-byte aligned", what);
-  if (slab_applicable(N, H, W, Ck, Cn, kh, kw))
+  if (slab_applicable(ctx, N, H, W, Ck, Cn, kh, kw))
     return conv_slab(ctx, what, x, wt, bias, residual, mask, scale, relu, out_f32, y, N, H, W, Ck, Cn, stream);
   const Box b = choose_box(N, H, W, kBlockM, false, 0, 0, kh, kw);
   SEGK_REQUIRE(ctx, b.rows > 0, "%s: no pixel box for %dx%dx%d", what, N, H, W);
-  const int block_n = pick_block_n(Cn);
+  const int block_n = pick_block_n(ctx, Cn);
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Ck, Ck, (int64_t)W * Ck, (int64_t)H * W * Ck, b.bw, b.bh, b.bn);
@@ -1076,7 +1059,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   conv_taps(taps, kh, kw);
   // few output tiles but a long K walk (conv6 dgrad: 48 tiles x 3136 k-steps): split K across SMs
   const int tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
-  const int force_ks = env_int("SEGK_FORCE_KSPLIT");
+  const int force_ks = ctx->force_ksplit;
   if ((tiles * 2 <= ctx->sm_count && p.ntaps * p.kchunks >= 32 && p.kchunks >= 2) || force_ks > 0) {
     int ks = ctx->sm_count / tiles;
     if (force_ks > 0) ks = force_ks;
@@ -1148,7 +1131,7 @@ int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float*
                Cout);
   const Box b = choose_box(N, H + 1, W + 1, kBlockM, false, H, W);
   SEGK_REQUIRE(ctx, b.rows > 0, "deconv2d_fwd: no pixel box");
-  const int block_n = pick_block_n(Cout);
+  const int block_n = pick_block_n(ctx, Cout);
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Cin, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin, b.bw, b.bh, b.bn);
@@ -1188,7 +1171,7 @@ int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const voi
                "deconv2d_dgrad: tensor-core path needs channels %% 64 == 0 (got %d -> %d)", Cin, Cout);
   const Box b = choose_box(N, H, W, kBlockM, false);
   SEGK_REQUIRE(ctx, b.rows > 0, "deconv2d_dgrad: no pixel box");
-  const int block_n = pick_block_n(Cin);
+  const int block_n = pick_block_n(ctx, Cin);
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc = encode_decimated_maps(ctx, maps, dy, N, H, W, Cout, s, b);
@@ -1224,7 +1207,7 @@ int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw,
   cudaStream_t st = (cudaStream_t)stream;
   const Box b = choose_box(N, H, W, 64, true);
   SEGK_REQUIRE(ctx, b.rows == 64, "deconv2d_wgrad: cannot tile %dx%dx%d into 64-pixel boxes", N, H, W);
-  const int block_n = pick_block_n(Cin);
+  const int block_n = pick_block_n(ctx, Cin);
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc = encode_decimated_maps(ctx, maps, dy, N, H, W, Cout, s, b);  // A side: dY (rows = (tap, co))
@@ -1295,7 +1278,7 @@ int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, i
   cudaStream_t st = (cudaStream_t)stream;
   const Box b = choose_box(N, H, W, 64, true);
   SEGK_REQUIRE(ctx, b.rows == 64, "conv2d_wgrad: cannot tile %dx%dx%d into 64-pixel boxes (need N*H*W >= 64)", N, H, W);
-  const int block_n = pick_block_n(Cout);
+  const int block_n = pick_block_n(ctx, Cout);
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Cin, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin, b.bw, b.bh, b.bn);
@@ -1317,7 +1300,7 @@ int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, i
   // measured (profiles/, sweep): one wave of items is best once there are >= 16 base items (the
   // atomics of extra splits cost more than the tail); tiny item counts want two waves
   int splits = base_items >= 16 ? ctx->sm_count / base_items : ceil_div(2 * ctx->sm_count, base_items);
-  if (env_int("SEGK_FORCE_WSPLIT") > 0) splits = env_int("SEGK_FORCE_WSPLIT");
+  if (ctx->force_wsplit > 0) splits = ctx->force_wsplit;
   const int max_splits = ceil_div(n_ptiles, 8);  // at least 8 k-steps per item
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -1345,3 +1328,27 @@ int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, i
 }
 
 }  // extern "C"
+
+// one-time per-context setup of the tensor-core kernels: opt in to > 48 KB dynamic shared memory for
+// every instantiation and read the tuning overrides (called from segk_create)
+int segk_tc_init(segk_ctx* ctx) {
+  ctx->force_bn = env_int("SEGK_FORCE_BN");
+  ctx->force_ksplit = env_int("SEGK_FORCE_KSPLIT");
+  ctx->force_wsplit = env_int("SEGK_FORCE_WSPLIT");
+  ctx->slab_mode = env_int("SEGK_SLAB", 1);
+  cudaError_t e = cudaSuccess;
+#define SEGK_SMEM_ATTR(kern, bytes) \
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+  SEGK_SMEM_ATTR(igemm_kernel<64>, Cfg<64>::kSmemBytes);
+  SEGK_SMEM_ATTR(igemm_kernel<128>, Cfg<128>::kSmemBytes);
+  SEGK_SMEM_ATTR(igemm_kernel<256>, Cfg<256>::kSmemBytes);
+  SEGK_SMEM_ATTR(wgrad_kernel<64>, WCfg<64>::kSmemBytes);
+  SEGK_SMEM_ATTR(wgrad_kernel<128>, WCfg<128>::kSmemBytes);
+  SEGK_SMEM_ATTR(wgrad_kernel<256>, WCfg<256>::kSmemBytes);
+  SEGK_SMEM_ATTR(slab_kernel<64>, SlabCfg<64>::kSmemBytes);
+  SEGK_SMEM_ATTR(slab_kernel<128>, SlabCfg<128>::kSmemBytes);
+  SEGK_SMEM_ATTR(slab_kernel<256>, SlabCfg<256>::kSmemBytes);
+#undef SEGK_SMEM_ATTR
+  if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "tensor-core kernel setup: %s", cudaGetErrorString(e));
+  return SEGK_OK;
+}

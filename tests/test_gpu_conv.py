@@ -192,9 +192,16 @@ def test_slab_conv_fwd_and_dgrad(ops, cuda_device, shape):
     assert_close(host(dx), xt.grad.numpy() * (x > 0) * 0.5, TOL_BF16, f"slab dgrad {shape}")
 
 
-def test_slab_forced_for_wide_layers(ops, cuda_device, monkeypatch):
-    """SEGK_SLAB=2 forces the slab kernel wherever it is legal (BLOCK_N = 256 instance)."""
-    monkeypatch.setenv("SEGK_SLAB", "2")
+def test_slab_forced_for_wide_layers(ops, cuda_device):
+    """slab = 2 forces the slab kernel wherever it is legal (BLOCK_N = 256 instance)."""
+    ops.ctx.set_tuning("slab", 2)
+    try:
+        _slab_forced_body(ops, cuda_device)
+    finally:
+        ops.ctx.set_tuning("slab", 1)
+
+
+def _slab_forced_body(ops, cuda_device):
     shape = (1, 40, 144, 128, 256, 3)
     n, h, w, ci, co, k = shape
     x, wt, b = _conv_case(shape, 22)

@@ -75,8 +75,7 @@ if __name__ == "__main__":
 
 def run_slab(bo_mode, n=1, h=8, w=64, ci=64, co=64):
     """3x3 conv through the slab kernel with integer data; prints the error under a base-offset mode."""
-    os.environ["SEGK_SLAB"] = "2"
-    os.environ["SEGK_SLAB_BO"] = str(bo_mode)
+    ops.ctx.set_tuning("slab", 2)
     rng = np.random.default_rng(1)
     x = torch.tensor(rng.integers(-2, 3, (n, h, w, ci)).astype(np.float32))
     wt = torch.tensor(rng.integers(-1, 2, (3, 3, ci, co)).astype(np.float32))
@@ -92,7 +91,7 @@ def run_slab(bo_mode, n=1, h=8, w=64, ci=64, co=64):
         print("  bad pixel map (n=0), rows = y:")
         for yy in range(min(h, 8)):
             print("   ", "".join("X" if bad[0, yy, xx] else "." for xx in range(w)))
-    os.environ["SEGK_SLAB"] = "1"
+    ops.ctx.set_tuning("slab", 1)
 
 
 if __name__ == "__main__":
