@@ -240,6 +240,24 @@ int segk_adam_step(segk_ctx* ctx, float* p, float* m, float* v, const float* g, 
 int segk_momentum_step(segk_ctx* ctx, float* p, float* a, const float* g, int64_t n, float lr,
                        float mu, float grad_scale, void* stream);
 
+/* ---- input pipeline (get_batches_fn, FCN.py:242-305, minus PNG decode) ------- */
+/* scipy.misc.imresize(..., interp='bilinear') = PIL Image.resize(BILINEAR), two passes of
+ *   out = clip8((2^21 + sum_i in[i] * k[i]) >> 22)
+ * with PIL's own coefficient tables (int32 [out_size][ksize]) and bounds (int32 [out_size][2] =
+ * first tap, tap count), computed on the host (pipeline.py: pil_bilinear_coeffs).  Bit-exact with PIL.
+ * Horizontal pass: src u8 [H][W][C] cropped to [y0,y0+crop_h) x [x0,x0+crop_w) (crop_image,
+ * FCN.py:176-182), optionally flipped horizontally (flip_image, :184-185) -> dst u8 [crop_h][out_w][C]. */
+int segk_resize_h_u8(segk_ctx* ctx, const uint8_t* src, uint8_t* dst, const int* coeffs,
+                     const int* bounds, int ksize, int W, int C, int x0, int y0, int crop_w,
+                     int crop_h, int out_w, int flip, void* stream);
+/* Vertical pass tmp u8 [in_h][out_w][C] -> out [out_h][out_w][C] with the per-image epilogue:
+ * mode 0 none; mode 1 bc_img (FCN.py:186-192): uint8(clip(v*contrast + brightness, 0, 255));
+ * mode 2 process_gt_image (FCN.py:194-201): out u8 [out_h][out_w] class id, 0 where the resized
+ * pixel == (255,0,0) (background) else 1 (road). */
+int segk_resize_v_u8(segk_ctx* ctx, const uint8_t* tmp, uint8_t* out, const int* coeffs,
+                     const int* bounds, int ksize, int C, int out_w, int out_h, int mode,
+                     double contrast, double brightness, void* stream);
+
 /* ---- misc device utilities ------------------------------------------------------------ */
 /* u8/f32 NHWC image -> bf16 NHWC (the feed_dict cast of FCN.py:312,395) */
 int segk_cast_to_bf16(segk_ctx* ctx, const void* x, int x_dtype, void* y, int64_t n, void* stream);

@@ -16,7 +16,7 @@ EPI_RELU, EPI_OUT_F32 = 1, 2
 DT_BF16, DT_F32, DT_U8 = 0, 1, 2
 
 _SCALARS = {
-    "int": ctypes.c_int, "unsigned": ctypes.c_uint, "float": ctypes.c_float,
+    "int": ctypes.c_int, "unsigned": ctypes.c_uint, "float": ctypes.c_float, "double": ctypes.c_double,
     "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "size_t": ctypes.c_size_t,
 }
 _RET = dict(_SCALARS)
