@@ -210,6 +210,8 @@ def test_checkpoint_roundtrip_with_adam_slots(cuda_device, tmp_path):
     l3b = float(step2({net2.image: xd, net2.annotation: ld}))
     torch.cuda.synchronize()
     assert abs(l3 - l3b) <= 1e-5 * abs(l3)
-    # fp32 atomics (split-K) make the step order-dependent at rounding level, and a bf16 rounding flip
-    # changes an element's gradient by ~0.4 %: parameters agree to a few per cent of one Adam step (1e-4)
-    assert float((net.vars.p - net2.vars.p).abs().max()) <= 5e-6
+    # fp32 atomics (split-K, used for the few-tile layers of this small net even in forward) make a step
+    # order-dependent at rounding level; a flipped bf16 rounding can flip a ReLU mask and with it the sign
+    # of a near-zero gradient, i.e. one full Adam step (~3e-4 at t=3) on isolated elements
+    dp = (net.vars.p - net2.vars.p).abs()
+    assert float(dp.max()) <= 1e-3 and float(dp.mean()) <= 2e-6

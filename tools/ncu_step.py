@@ -1,7 +1,8 @@
 """One FCN-8s training step (B=32, 160x576) for an ncu capture of every tensor-core launch in it.
 Plain run: writes the ordered list of tensor-core calls of step 3 to gpurun_out/step_calls.json and
 their count K to gpurun_out/step_k.txt.  Under ncu use  -k regex:'igemm_kernel|wgrad_kernel|slab_kernel'
--s $((2*K)) -c K  (the two warm-up steps launch 2K matching kernels)."""
+-s $((2*K)) -c K  (the two warm-up steps launch 2K matching kernels).  Use --metrics + --csv (a
+--set full report of ~60 launches exceeds gpurun's 64 MiB return limit)."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
