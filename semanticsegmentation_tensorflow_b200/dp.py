@@ -48,16 +48,25 @@ class BucketedAllReduce:
         self._works.append((lo, hi, w))
 
     def layer_done(self, name: str):
-        """Called by FCN.backward after each layer's dW/db kernels are enqueued."""
+        """Called by FCN.backward after each layer's dW/db kernels are enqueued.  Returns the buckets
+        whose all-reduce was launched by this call as (lo, hi, work) tuples."""
+        first = len(self._works)
         while self._next < len(self.buckets) and self.buckets[self._next][2] == name:
             self._launch(self._next)
             self._next += 1
+        return self._works[first:]
+
+    def flush(self):
+        """Launch the buckets whose completing layer was never reported (defensive); returns them."""
+        first = len(self._works)
+        while self._next < len(self.buckets):
+            self._launch(self._next)
+            self._next += 1
+        return self._works[first:]
 
     def finish(self):
         """Yields (lo, hi) arena slices as their reductions complete (stream-ordered wait)."""
-        while self._next < len(self.buckets):        # layers never reported (defensive)
-            self._launch(self._next)
-            self._next += 1
+        self.flush()
         for lo, hi, w in self._works:
             if w is not None:
                 w.wait()

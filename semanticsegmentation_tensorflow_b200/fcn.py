@@ -484,6 +484,12 @@ class TrainStep:
                 buckets = P.gradient_buckets(net.vars.slots)
             self.local = LocalBuckets(net, opt, buckets)
 
+    def _finalize_stream(self, net):
+        if getattr(self, "_fin", None) is None:
+            self._fin = SideStream(net.device, enabled=net.side.stream is not None)
+        self._fin.enabled = net.side.enabled
+        return self._fin
+
     def __call__(self, feed_dict=None):
         net, opt = self.net, self.opt
         if feed_dict:
@@ -502,17 +508,34 @@ class TrainStep:
             opt.apply(net)
             net.vars.repack(net.ops)
         else:
+            # data parallel: each bucket's all-reduce is launched as soon as its last layer is done; its
+            # optimizer update + repack then run on a second side stream right after the collective,
+            # in the shadow of the remaining backward
             self.allreduce.begin_step()
+            slots = net.vars.slots
+            fin = self._finalize_stream(net)
+
+            def finalize(lo, hi, work):
+                names = {n.split("/")[0] for n, s in slots.items() if lo <= s.offset < hi}
+
+                def go():
+                    if work is not None:
+                        work.wait()               # the side stream waits for the collective, not the main one
+                    opt.apply(net, lo, hi)
+                    net.vars.repack(net.ops, names)
+
+                fin.run(go)
 
             def layer_done(name):
                 net.side.join()                   # this layer's bias gradients are part of the reduced arena
-                self.allreduce.layer_done(name)
+                for lo, hi, work in self.allreduce.layer_done(name):
+                    finalize(lo, hi, work)
 
             net.backward(after_layer=layer_done)
             net.side.join()
-            for lo, hi in self.allreduce.finish():
-                opt.apply(net, lo, hi)
-            net.vars.repack(net.ops)
+            for lo, hi, work in self.allreduce.flush():
+                finalize(lo, hi, work)
+            fin.join()
         net.step_count += 1
         net._ran_forward = False
         return loss
