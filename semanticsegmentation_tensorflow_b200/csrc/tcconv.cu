@@ -89,6 +89,7 @@ struct IgemmParams {
   // atomically added into the fp32 workspace `ws` [pixels][ldo] and finished by epilogue_finish_kernel
   int ksplits;
   float* ws;
+  int m_fastest;   // tile order: 0 = channel tile fastest (activations shared), 1 = pixel tile fastest (weights shared)
 };
 
 struct PipeState {
@@ -111,6 +112,21 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
   TileCoord t;
   t.split = tile % p.ksplits;
   tile /= p.ksplits;
+  if (p.m_fastest) {
+    // weight-heavy layers (conv6: 205 MB of weights, 3 MB of activations): consecutive CTAs take
+    // different pixel tiles of the SAME channel tile, so a weight tile is fetched from DRAM once and
+    // shared through L2 by all the CTAs that need it at that moment
+    const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+    int r = tile % m_tiles;
+    const int q = tile / m_tiles;
+    t.nt = q % p.n_tiles;
+    t.phase = q / p.n_tiles;
+    t.x0 = (r % p.tiles_w) * p.bw;
+    r /= p.tiles_w;
+    t.y0 = (r % p.tiles_h) * p.bh;
+    t.n0 = (r / p.tiles_h) * p.bn;
+    return t;
+  }
   t.nt = tile % p.n_tiles;
   int r = tile / p.n_tiles;
   t.x0 = (r % p.tiles_w) * p.bw;
@@ -1055,6 +1071,8 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   p.bias = bias; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask;
   p.scale = scale; p.relu = relu;
   p.ksplits = 1; p.ws = nullptr;
+  // order the tiles so that what is larger (weights vs activations) is what concurrent CTAs share
+  p.m_fastest = ((int64_t)kh * kw * Cn > (int64_t)N * H * W) ? 1 : 0;
   TapTable taps;
   conv_taps(taps, kh, kw);
   // few output tiles but a long K walk (conv6 dgrad: 48 tiles x 3136 k-steps): split K across SMs
