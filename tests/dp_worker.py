@@ -22,7 +22,18 @@ variables = reference_init(P.variable_shapes(3, 2, FC), 1234, "he")
 lo, hi = P.shard_batch(GB, world, rank)
 xs, ys = torch.as_tensor(x[lo:hi]).to(dev), torch.as_tensor(y[lo:hi]).to(dev)
 net = FCN(xs, 1.0, 2, variables=variables, fc=FC, world_size=world)
-step = AdamOptimizer(1e-4).minimize(net, allreduce=BucketedAllReduce.for_net(net))
+ar = BucketedAllReduce.for_net(net)
+# (1) the reduced gradient itself (Adam is scale-invariant, so check it before any update)
+net.forward()
+net.loss(ys, with_grad=True)
+ar.begin_step()
+net.backward(after_layer=lambda name: (net.side.join(), ar.layer_done(name)))
+net.side.join()
+for _ in ar.finish():
+    pass
+torch.cuda.synchronize()
+g_dp = net.vars.g.clone()
+step = AdamOptimizer(1e-4).minimize(net, allreduce=ar)
 losses = []
 for _ in range(3):
     l = step({net.image: xs, net.annotation: ys, net.keep_probability: 1.0})
@@ -40,6 +51,13 @@ out = {"rank": rank, "replica_max_diff": max(gather), "losses": losses}
 if rank == 0:
     xf, yf = torch.as_tensor(x).to(dev), torch.as_tensor(y).to(dev)
     ref = FCN(xf, 1.0, 2, variables=variables, fc=FC, world_size=1)
+    ref.forward()
+    ref.loss(yf, with_grad=True)
+    ref.backward()
+    torch.cuda.synchronize()
+    g1 = ref.vars.g
+    out["grad_cosine"] = float(torch.dot(g_dp, g1) / (g_dp.norm() * g1.norm()))
+    out["grad_norm_ratio"] = float(g_dp.norm() / g1.norm())
     rstep = AdamOptimizer(1e-4).minimize(ref)
     out["single_losses"] = [float(rstep({ref.image: xf, ref.annotation: yf, ref.keep_probability: 1.0})) for _ in range(3)]
     torch.cuda.synchronize()
