@@ -55,6 +55,7 @@ int segk_set_tuning(segk_ctx* ctx, const char* key, int value) {
   if (!ctx) return SEGK_EINVAL;
   if (!ctx || !key) return SEGK_EINVAL;
   if (!strcmp(key, "slab")) ctx->slab_mode = value;
+  else if (!strcmp(key, "tma_store")) ctx->tma_store = value;
   else if (!strcmp(key, "force_bn")) ctx->force_bn = value;
   else if (!strcmp(key, "force_ksplit")) ctx->force_ksplit = value;
   else if (!strcmp(key, "force_wsplit")) ctx->force_wsplit = value;

@@ -21,6 +21,7 @@ struct segk_ctx {
   // tuning overrides, read once from the environment (tools/sweep_tiles.py); 0 = heuristics
   int force_bn = 0, force_ksplit = 0, force_wsplit = 0;
   int slab_mode = 1;        // SEGK_SLAB: 0 off, 1 auto, 2 wherever legal
+  int tma_store = 1;        // SEGK_TMA_STORE: bf16 conv outputs leave through smem + TMA store
   void* ws = nullptr;       // grow-only scratch for split-K partial sums (tcconv.cu)
   size_t ws_bytes = 0;
   void* ws2 = nullptr;      // grow-only scratch for per-block BiasAddGrad partials (elementwise.cu)

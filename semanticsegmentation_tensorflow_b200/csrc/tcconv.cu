@@ -28,7 +28,9 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;             // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * 128;  // 16 KB
 constexpr int kMaxTaps = 64;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudget = 192 * 1024;
+constexpr int kStageOutBytes = kBlockM * 128;     // epilogue staging: 128 rows x 64 bf16 channels, SWIZZLE_128B
+constexpr int kOutBytes = 2 * kStageOutBytes;     // double-buffered
 
 template <int BLOCK_N>
 struct Cfg {
@@ -36,7 +38,7 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = kSmemBudget / kStageBytes;  // 256:4  128:6  64:8
   static constexpr int kTmemCols = 2 * BLOCK_N;              // double-buffered accumulator
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // wgrad ring: a stage holds kPB 64-pixel boxes, so one barrier round-trip feeds 4*kPB MMAs
@@ -58,6 +60,7 @@ constexpr uint64_t kDescMNMajor = (512ull << 16) | (64ull << 32) | (1ull << 46) 
 struct alignas(64) TensorMaps {
   CUtensorMap a[4];
   CUtensorMap b;
+  CUtensorMap c;   // output tensor (TMA-store epilogue), box (64 ch, bw, bh, bn)
 };
 
 struct TapTable {
@@ -89,6 +92,7 @@ struct IgemmParams {
   // atomically added into the fp32 workspace `ws` [pixels][ldo] and finished by epilogue_finish_kernel
   int ksplits;
   float* ws;
+  int tma_store;   // 1: bf16 output leaves through shared memory + TMA store (coalesced, async, clipped)
   int m_fastest;   // tile order: 0 = channel tile fastest (activations shared), 1 = pixel tile fastest (weights shared)
 };
 
@@ -158,7 +162,8 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
   using C = Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* smem_out = smem + C::kStages * C::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_out + kOutBytes);
   uint64_t* empty_bar = full_bar + C::kStages;
   uint64_t* tfull_bar = empty_bar + C::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -260,6 +265,8 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
     const int iw = row % p.bw;
     const int ih = (row / p.bw) % p.bh;
     const int in = row / (p.bw * p.bh);
+    const bool ep_leader = (threadIdx.x == 64);     // first epilogue thread: issues / tracks the TMA stores
+    uint32_t sg = 0;                                // running 64-column group counter -> staging buffer
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int ay = t.phase / p.s, ax = t.phase % p.s;
@@ -274,6 +281,12 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint8_t* sbuf = smem_out + (sg & 1) * kStageOutBytes;
+        if (p.tma_store && (c0 & 32) == 0) {
+          // the store that used this staging buffer two groups ago must have finished reading it
+          if (ep_leader) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+        }
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
@@ -331,6 +344,14 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
             float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else if (p.tma_store) {
+            // staging row = box-linear pixel index, 128 B per row, 16-byte pieces XOR-swizzled by row & 7
+            const int pbase = (c0 & 32) ? 4 : 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(sbuf + row * 128 + (((pbase + i) ^ (row & 7)) << 4)) =
+                  make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                             pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
           } else {
             uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + obase + c0);
 #pragma unroll
@@ -339,12 +360,22 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
           }
         }
+        if (p.tma_store && (c0 & 32)) {
+          fence_proxy_async();                        // generic-proxy smem writes -> visible to the TMA engine
+          named_bar_sync(1, 128);
+          if (ep_leader) {
+            tma_store_4d(&maps.c, sbuf, t.nt * BLOCK_N + (c0 - 32), t.x0, t.y0, t.n0);
+            tma_store_commit();
+          }
+          ++sg;
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (p.tma_store && ep_leader) tma_store_wait_read<0>();
   }
   __syncwarp();
   tc_fence_before();
@@ -379,9 +410,9 @@ struct SlabCfg {
   static constexpr int kTapBytes = BLOCK_N * 128;
   static constexpr int kBBytes = kGroup * kTapBytes;
   static constexpr int kAStages = BLOCK_N == 256 ? 2 : 3;
-  static constexpr int kBStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 3 : 4);
+  static constexpr int kBStages = BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 2 : 4);
   static constexpr int kTmemCols = 2 * BLOCK_N;
-  static constexpr int kSmemBytes = kAStages * kSlabBytes + kBStages * kBBytes + 1024 + 512;
+  static constexpr int kSmemBytes = kAStages * kSlabBytes + kBStages * kBBytes + kOutBytes + 1024 + 512;
 };
 
 struct SlabParams {
@@ -390,6 +421,7 @@ struct SlabParams {
   int n_tiles;            // Cn / BLOCK_N
   int kchunks;            // Ck / 64
   int ldo;
+  int tma_store;
   void* out;
   int out_f32;
   const float* bias;
@@ -407,7 +439,8 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::kAStages * kSlabBytes;
-  uint64_t* fullA = reinterpret_cast<uint64_t*>(smem_b + C::kBStages * C::kBBytes);
+  uint8_t* smem_out = smem_b + C::kBStages * C::kBBytes;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(smem_out + kOutBytes);
   uint64_t* emptyA = fullA + C::kAStages;
   uint64_t* fullB = emptyA + C::kAStages;
   uint64_t* emptyB = fullB + C::kBStages;
@@ -516,6 +549,9 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
     const int q = warp & 3;       // TMEM lane quarter == image row of the tile
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool ep_leader = (threadIdx.x == 64);
+    const int srow = q * kSlabWV + lane;            // staging row: box (64 ch, 30 w, 4 h) is packed at pitch 30
+    uint32_t sg = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       int r = tile / p.n_tiles;
@@ -531,6 +567,11 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint8_t* sbuf = smem_out + (sg & 1) * kStageOutBytes;
+        if (p.tma_store && (c0 & 32) == 0) {
+          if (ep_leader) tma_store_wait_read<1>();
+          named_bar_sync(1, 128);
+        }
         uint32_t rr[32];
         tmem_ld32(taddr + c0, rr);
         tmem_ld_wait();
@@ -584,6 +625,13 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
             float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else if (p.tma_store) {
+            const int pbase = (c0 & 32) ? 4 : 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(sbuf + srow * 128 + (((pbase + i) ^ (srow & 7)) << 4)) =
+                  make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                             pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
           } else {
             uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + obase + c0);
 #pragma unroll
@@ -592,12 +640,22 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
           }
         }
+        if (p.tma_store && (c0 & 32)) {
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (ep_leader) {
+            tma_store_4d(&maps.c, sbuf, nt * BLOCK_N + (c0 - 32), x0, y0, n);
+            tma_store_commit();
+          }
+          ++sg;
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (p.tma_store && ep_leader) tma_store_wait_read<0>();
   }
   __syncwarp();
   tc_fence_before();
@@ -1013,6 +1071,11 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
   p.n_tiles = Cn / block_n; p.kchunks = Ck / 64; p.ldo = Cn;
   p.out = y; p.out_f32 = out_f32; p.bias = bias; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask;
   p.scale = scale; p.relu = relu;
+  p.tma_store = (!out_f32 && ctx->tma_store) ? 1 : 0;
+  if (p.tma_store) {
+    rc = encode_act_map(ctx, &maps.c, y, N, H, W, Cn, Cn, (int64_t)W * Cn, (int64_t)H * W * Cn, kSlabWV, kSlabH, 1);
+    if (rc) return rc;
+  }
   const int total = N * p.tiles_h * p.tiles_w * p.n_tiles;
   const int grid = total < ctx->sm_count ? total : ctx->sm_count;
   (void)what;
@@ -1101,6 +1164,11 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
       SEGK_LAUNCHED(ctx, "igemm split-K finish");
       return SEGK_OK;
     }
+  }
+  p.tma_store = (!out_f32 && ctx->tma_store) ? 1 : 0;
+  if (p.tma_store) {
+    rc = encode_act_map(ctx, &maps.c, y, N, H, W, Cn, Cn, (int64_t)W * Cn, (int64_t)H * W * Cn, b.bw, b.bh, b.bn);
+    if (rc) return rc;
   }
   return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
 }
@@ -1354,6 +1422,7 @@ int segk_tc_init(segk_ctx* ctx) {
   ctx->force_ksplit = env_int("SEGK_FORCE_KSPLIT");
   ctx->force_wsplit = env_int("SEGK_FORCE_WSPLIT");
   ctx->slab_mode = env_int("SEGK_SLAB", 1);
+  ctx->tma_store = env_int("SEGK_TMA_STORE", 1);
   cudaError_t e = cudaSuccess;
 #define SEGK_SMEM_ATTR(kern, bytes) \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
