@@ -287,6 +287,13 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
           if (ep_leader) tma_store_wait_read<1>();
           named_bar_sync(1, 128);
         }
+        // bias for these 32 columns: issued before the TMEM load so its L2/L1 latency hides behind it
+        float4 bv[8];
+        if (p.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + t.nt * BLOCK_N + c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = __ldg(b4 + i);
+        }
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
@@ -299,11 +306,9 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           if (p.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + t.nt * BLOCK_N + c0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(b4 + i);
-              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+              v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w;
             }
           }
           if (p.residual) {
@@ -572,6 +577,12 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
           if (ep_leader) tma_store_wait_read<1>();
           named_bar_sync(1, 128);
         }
+        float4 bv[8];
+        if (p.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = __ldg(b4 + i);
+        }
         uint32_t rr[32];
         tmem_ld32(taddr + c0, rr);
         tmem_ld_wait();
@@ -580,11 +591,9 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
           if (p.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + nt * BLOCK_N + c0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 b = __ldg(b4 + i);
-              v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+              v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w;
             }
           }
           if (p.residual) {
