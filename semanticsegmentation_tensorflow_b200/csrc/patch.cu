@@ -61,53 +61,6 @@ __global__ void __launch_bounds__(kThreads) im2col_k64_kernel(const XT* __restri
   }
 }
 
-// u8 fast path: one block = 256 consecutive pixels of one image row.  The kh x (256 + kw - 1) x Cin byte
-// neighbourhood is staged in shared memory with coalesced loads (borders zero-filled there), then 8
-// lanes per pixel assemble and write one 128-byte patch row (coalesced 16-byte stores).
-constexpr int kRowPix = 256;
-__global__ void __launch_bounds__(kThreads) im2col_k64_u8_rows_kernel(const uint8_t* __restrict__ x,
-                                                                      uint4* __restrict__ P, int H, int W, int Cin,
-                                                                      int kh, int kw, int segs) {
-  extern __shared__ uint8_t tile[];       // [kh][kRowPix + kw - 1][Cin]
-  const int seg = blockIdx.x % segs;
-  const int row = blockIdx.x / segs;      // n*H + y
-  const int y = row % H;
-  const int64_t img = (int64_t)(row / H) * H * W;
-  const int x0 = seg * kRowPix;
-  const int ph = kh / 2, pw = kw / 2;
-  const int tw = kRowPix + kw - 1;
-  const int tile_bytes = kh * tw * Cin;
-  for (int i = threadIdx.x; i < tile_bytes; i += kThreads) {
-    const int c = i % Cin;
-    const int px = (i / Cin) % tw;
-    const int ky = i / (Cin * tw);
-    const int yy = y + ky - ph, xx = x0 + px - pw;
-    tile[i] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? x[(img + (int64_t)yy * W + xx) * Cin + c] : (uint8_t)0;
-  }
-  __syncthreads();
-  const int K = kh * kw * Cin;
-  const int g = threadIdx.x & 7;
-  int off[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int kk = g * 8 + j;
-    if (kk < K) {
-      const int t = kk / Cin;
-      off[j] = ((t / kw) * tw + (t % kw)) * Cin + kk % Cin;
-    } else {
-      off[j] = -1;
-    }
-  }
-  for (int px = threadIdx.x >> 3; px < kRowPix; px += kThreads / 8) {
-    if (x0 + px >= W) break;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? (float)tile[px * Cin + off[j]] : 0.f;
-    P[((int64_t)row * W + x0 + px) * 8 + g] =
-        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-  }
-}
-
 // wk[co][kk] (bf16, 64 wide) = kk < K ? w[kk][co] : 0
 __global__ void __launch_bounds__(kThreads) pack_im2col_weights_kernel(const float* __restrict__ w,
                                                                        bf16* __restrict__ wk, int K, int Cout) {
@@ -290,12 +243,8 @@ int segk_im2col_k64(segk_ctx* ctx, const void* x, int x_dtype, void* P, int N, i
   SEGK_REQUIRE(ctx, kh * kw * Cin <= 64 && (kh & 1) && (kw & 1), "im2col_k64: need kh*kw*Cin <= 64, odd kernel");
   const int64_t items = (int64_t)N * H * W * 8;
   cudaStream_t st = (cudaStream_t)stream;
-  if (x_dtype == 2) {
-    const int segs = ceil_div(W, kRowPix);
-    const size_t smem = (size_t)kh * (kRowPix + kw - 1) * Cin;
-    im2col_k64_u8_rows_kernel<<<(unsigned)((int64_t)N * H * segs), kThreads, smem, st>>>(
-        (const uint8_t*)x, (uint4*)P, H, W, Cin, kh, kw, segs);
-  }
+  if (x_dtype == 2)
+    im2col_k64_kernel<uint8_t><<<sgrid(ctx, items, 16), kThreads, 0, st>>>((const uint8_t*)x, (uint4*)P, N, H, W, Cin, kh, kw);
   else if (x_dtype == 0)
     im2col_k64_kernel<bf16><<<sgrid(ctx, items, 16), kThreads, 0, st>>>((const bf16*)x, (uint4*)P, N, H, W, Cin, kh, kw);
   else
