@@ -207,11 +207,13 @@ def run_gpu(args):
     value = world * B * steps / (ms_total / 1e3)
     final_loss = float(loss)
 
-    # ---- timed region 1b: same K steps with per-launch CUDA events (roofline).  The side stream is
+    # ---- timed region 1b: same K steps with per-launch CUDA events (roofline).  The side streams are
     # disabled here so that every launch's event pair brackets that kernel alone.
-    side_was = net.side.enabled
+    side_was, wside_was = net.side.enabled, net.wside.enabled
     net.side.join()
+    net.wside.join()
     net.side.enabled = False
+    net.wside.enabled = False
     net.ops.profile = Profile()
     sync()
     e0.record()
@@ -224,6 +226,7 @@ def run_gpu(args):
     prof_detail = net.ops.profile.summary(detail=True)
     net.ops.profile = None
     net.side.enabled = side_was
+    net.wside.enabled = wside_was
 
     # ---- timed region 2: end to end through the public API with HOST buffers -------------
     feed_host = {net.image: host_x, net.annotation: host_y, net.keep_probability: KEEP_PROB}

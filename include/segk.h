@@ -104,6 +104,22 @@ int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const voi
 int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H,
                         int W, int Cin, int Cout, int k, int s, int accumulate, void* stream);
 
+/* ---- first layer on the tensor cores without a patch tensor --------------------------------
+ * conv_layer on the network input (conv1_1, FCN.py:52; U-Net first Conv2D, utils.py:165): 3x3 SAME,
+ * Cin in {1,3,4}, Cout in {64,128,256}.  Each pixel's 3x3xCin patch is built in shared memory
+ * straight from the image (x_dtype 2 = u8 as fed at FCN.py:312, 0 = bf16) and multiplied on
+ * tcgen05; wk is the segk_pack_im2col_weights layout [Cout][64] bf16.  y bf16, bias + optional
+ * SEGK_EPI_RELU fused. */
+int segk_conv2d_first_fwd(segk_ctx* ctx, const void* x, int x_dtype, const void* wk,
+                          const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
+                          int kh, int kw, unsigned flags, void* stream);
+
+/* Conv2DBackpropFilter (+ BiasAddGrad when dbias != NULL) of that layer (FCN.py:340): reads the
+ * image and dy once.  dw fp32 [kh,kw,Cin,Cout] (overwritten), dbias fp32 [Cout] (overwritten). */
+int segk_conv2d_first_wgrad(segk_ctx* ctx, const void* x, int x_dtype, const void* dy, float* dw,
+                            float* dbias, int N, int H, int W, int Cin, int Cout, int kh, int kw,
+                            void* stream);
+
 /* ---- small-channel layers on CUDA cores (conv1_1 Cin=3/4, conv8 Cout=2, conv_t1 Cin=2,
  *      conv_t3 Cout=2) ----------------------------------------------------------------- */
 /* conv_layer forward for ragged channel counts.  x_dtype: 0 = bf16, 2 = u8 (raw image,

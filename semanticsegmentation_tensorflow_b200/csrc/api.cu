@@ -45,6 +45,7 @@ int segk_destroy(segk_ctx* ctx) {
   if (ctx && ctx->ws) cudaFree(ctx->ws);
   if (ctx && ctx->ws2) cudaFree(ctx->ws2);
   if (ctx && ctx->ws3) cudaFree(ctx->ws3);
+  if (ctx && ctx->ws4) cudaFree(ctx->ws4);
   delete ctx;
   return SEGK_OK;
 }
@@ -56,6 +57,8 @@ int segk_set_tuning(segk_ctx* ctx, const char* key, int value) {
   if (!ctx || !key) return SEGK_EINVAL;
   if (!strcmp(key, "slab")) ctx->slab_mode = value;
   else if (!strcmp(key, "tma_store")) ctx->tma_store = value;
+  else if (!strcmp(key, "slab3")) ctx->slab3 = value;
+  else if (!strcmp(key, "wslab")) ctx->wslab = value;
   else if (!strcmp(key, "force_bn")) ctx->force_bn = value;
   else if (!strcmp(key, "force_ksplit")) ctx->force_ksplit = value;
   else if (!strcmp(key, "force_wsplit")) ctx->force_wsplit = value;

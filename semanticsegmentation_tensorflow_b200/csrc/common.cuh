@@ -22,10 +22,14 @@ struct segk_ctx {
   int force_bn = 0, force_ksplit = 0, force_wsplit = 0;
   int slab_mode = 1;        // SEGK_SLAB: 0 off, 1 auto, 2 wherever legal
   int tma_store = 1;        // SEGK_TMA_STORE: bf16 conv outputs leave through smem + TMA store
+  int slab3 = 1;            // SEGK_SLAB3: kx-fused N = 192 slab kernel with resident weights for Ck = 64
   void* ws = nullptr;       // grow-only scratch for split-K partial sums (tcconv.cu)
   size_t ws_bytes = 0;
   void* ws2 = nullptr;      // grow-only scratch for per-block BiasAddGrad partials (elementwise.cu)
   size_t ws2_bytes = 0;
+  int wslab = 1;            // SEGK_WSLAB: slab-formulated wgrad for 3x3 layers with Cin 64/128 on large maps (2 = wherever legal)
+  void* ws4 = nullptr;      // grow-only scratch for the slab wgrad's per-split partial sums (wslab.cu; own buffer:
+  size_t ws4_bytes = 0;     //   that kernel may run on a different stream than the users of ws)
   void* ws3 = nullptr;      // grow-only scratch for the full-resolution 1x1 head's wgrad partials (smallconv.cu)
   size_t ws3_bytes = 0;
   // driver entry point resolved at segk_create (no link-time libcuda dependency)

@@ -11,11 +11,15 @@
 // padding is the TMA unit's out-of-bounds zero fill: a tap (dy,dx) simply shifts the box
 // start coordinate, which may be negative.  Nothing is im2col'ed in memory.
 //
-// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (320 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0    TMA producer (one elected lane)        smem ring of kStages {A 16 KB, B BLOCK_N*128 B}
 //   warp 1    tcgen05.mma issuer (one lane) + TMEM allocator; 2 accumulators of BLOCK_N columns
-//   warps 2-5 epilogue: tcgen05.ld -> bias / residual / ReLU / ReLU-mask / scale -> global stores
+//   warps 2-9 epilogue: tcgen05.ld -> bias / residual / ReLU / ReLU-mask / scale -> staging -> TMA store.
+//             Two warps per TMEM lane quarter, one per 32-column half of each 64-column group: with
+//             one warp per quarter the epilogue of a 64-channel tile (~2300 cycles of dependent issue,
+//             ncu r1d) took longer than its MMAs (1152 tensor cycles) and set the pace of conv1_2.
 #include "tc_common.cuh"
+#include "tc_host.cuh"
 
 #include <cstdlib>
 
@@ -23,7 +27,9 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;            // igemm / slab kernels: warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kWgradThreads = 192;       // wgrad: warps 2-5 epilogue (one pass at the end of a long K walk)
+constexpr int kEpiThreads = 256;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;             // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * 128;  // 16 KB
@@ -181,7 +187,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kEpiThreads);
     }
     fence_barrier_init();
   }
@@ -257,8 +263,9 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ---- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----
+    // ---- epilogue: warps 2..9, TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ----
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -280,12 +287,13 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int g0 = 0; g0 < BLOCK_N; g0 += 64) {
+        const int c0 = g0 + half * 32;
         uint8_t* sbuf = smem_out + (sg & 1) * kStageOutBytes;
-        if (p.tma_store && (c0 & 32) == 0) {
+        if (p.tma_store) {
           // the store that used this staging buffer two groups ago must have finished reading it
           if (ep_leader) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, kEpiThreads);
         }
         // bias for these 32 columns: issued before the TMEM load so its L2/L1 latency hides behind it
         float4 bv[8];
@@ -351,7 +359,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
             for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           } else if (p.tma_store) {
             // staging row = box-linear pixel index, 128 B per row, 16-byte pieces XOR-swizzled by row & 7
-            const int pbase = (c0 & 32) ? 4 : 0;
+            const int pbase = half * 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               *reinterpret_cast<uint4*>(sbuf + row * 128 + (((pbase + i) ^ (row & 7)) << 4)) =
@@ -365,11 +373,11 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
           }
         }
-        if (p.tma_store && (c0 & 32)) {
+        if (p.tma_store) {
           fence_proxy_async();                        // generic-proxy smem writes -> visible to the TMA engine
-          named_bar_sync(1, 128);
+          named_bar_sync(1, kEpiThreads);
           if (ep_leader) {
-            tma_store_4d(&maps.c, sbuf, t.nt * BLOCK_N + (c0 - 32), t.x0, t.y0, t.n0);
+            tma_store_4d(&maps.c, sbuf, t.nt * BLOCK_N + g0, t.x0, t.y0, t.n0);
             tma_store_commit();
           }
           ++sg;
@@ -461,7 +469,7 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
     tma_prefetch_desc(&maps.b);
     for (int i = 0; i < C::kAStages; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < C::kBStages; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiThreads); }
     fence_barrier_init();
   }
   // the two spill rows past each slab are read (for discarded outputs only) but never written by
@@ -552,6 +560,7 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
     }
   } else {
     const int q = warp & 3;       // TMEM lane quarter == image row of the tile
+    const int half = (warp - 2) >> 2;   // which 32 columns of each 64-column group
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool ep_leader = (threadIdx.x == 64);
@@ -571,11 +580,12 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int g0 = 0; g0 < BLOCK_N; g0 += 64) {
+        const int c0 = g0 + half * 32;
         uint8_t* sbuf = smem_out + (sg & 1) * kStageOutBytes;
-        if (p.tma_store && (c0 & 32) == 0) {
+        if (p.tma_store) {
           if (ep_leader) tma_store_wait_read<1>();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, kEpiThreads);
         }
         float4 bv[8];
         if (p.bias) {
@@ -635,7 +645,7 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           } else if (p.tma_store) {
-            const int pbase = (c0 & 32) ? 4 : 0;
+            const int pbase = half * 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               *reinterpret_cast<uint4*>(sbuf + srow * 128 + (((pbase + i) ^ (srow & 7)) << 4)) =
@@ -649,11 +659,11 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
           }
         }
-        if (p.tma_store && (c0 & 32)) {
+        if (p.tma_store) {
           fence_proxy_async();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, kEpiThreads);
           if (ep_leader) {
-            tma_store_4d(&maps.c, sbuf, nt * BLOCK_N + (c0 - 32), x0, y0, n);
+            tma_store_4d(&maps.c, sbuf, nt * BLOCK_N + g0, x0, y0, n);
             tma_store_commit();
           }
           ++sg;
@@ -671,6 +681,239 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
   __syncthreads();
   tc_fence_after();
   if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------
+// slab3_kernel: the slab kernel for Ck = 64 and 64-channel output tiles (conv1_2 fwd / dgrad, conv2_1).
+// ncu (profiles/r1d): with N = 64 the slab kernel is bound by shared-memory bandwidth, not by the
+// tensor pipe: a 128x64x16 MMA reads 6 KB for 32 tensor cycles, and every tile re-loads all nine
+// 8 KB weight tiles.  Two changes:
+//   * the three kx taps of one ky share the A operand: B = [W(ky,0); W(ky,1); W(ky,2)] is one N = 192
+//     operand and column block kx of the accumulator holds  D_kx[r] = sum_ky slab[ky*32 + r] . W(ky,kx).
+//     The output is  out[o] = D_0[o] + D_1[o+1] + D_2[o+2]:  rows are TMEM lanes = threads of the
+//     epilogue warp, so the kx shift is two warp shuffles per value (o = i*32 + j; the lanes that would
+//     wrap, j >= 30, are the discarded halo columns anyway).  10 KB per 96 tensor cycles.
+//   * the 72 KB of weights of the CTA's channel tile stay resident in shared memory (every tile of a
+//     CTA has the same channel tile: the grid is a multiple of the number of channel tiles).
+// ------------------------------------------------------------------------------------------
+constexpr int kSlab3Bytes = kSlabRows * 128;                 // 24 KB: A rows ky*32 + r never leave the slab
+constexpr int kSlab3WBytes = 9 * 64 * 128;                   // 72 KB
+constexpr int kSlab3Stages = 4;
+constexpr int kSlab3Smem = kSlab3Stages * kSlab3Bytes + kSlab3WBytes + kOutBytes + 1024 + 512;
+
+__global__ void __launch_bounds__(kThreads, 1)
+slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
+  constexpr int kN = 192;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_w = smem + kSlab3Stages * kSlab3Bytes;
+  uint8_t* smem_out = smem_w + kSlab3WBytes;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(smem_out + kOutBytes);
+  uint64_t* emptyA = fullA + kSlab3Stages;
+  uint64_t* tfull_bar = emptyA + kSlab3Stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* wfull = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
+  const int nt = blockIdx.x % p.n_tiles;          // the same for every tile of this CTA (grid % n_tiles == 0)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a[0]);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < kSlab3Stages; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiThreads); }
+    mbar_init(wfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);      // 2 accumulators x 192 columns
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(wfull, (uint32_t)kSlab3WBytes);
+      for (int ky = 0; ky < 3; ++ky)     // box (64 k, 64 channels, 3 taps) -> rows kx*64 + c
+        tma_load_3d(&maps.b, wfull, smem_w + ky * (3 * 64 * 128), 0, nt * 64, ky * 3);
+    }
+    __syncwarp();
+    PipeState pa;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int r = tile / p.n_tiles;
+      const int x0 = (r % p.tiles_w) * kSlabWV;
+      r /= p.tiles_w;
+      const int y0 = (r % p.tiles_h) * kSlabH;
+      const int n = r / p.tiles_h;
+      mbar_wait(&emptyA[pa.stage], pa.phase ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&fullA[pa.stage], (uint32_t)kSlab3Bytes);
+        tma_load_4d(&maps.a[0], &fullA[pa.stage], smem_a + pa.stage * kSlab3Bytes, 0, x0 - 1, y0 - 1, n);
+      }
+      __syncwarp();
+      pa.advance<kSlab3Stages>();
+    }
+  } else if (warp == 1) {
+    PipeState pa;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    constexpr uint32_t idesc = make_idesc(kBlockM, kN, 0, 0);
+    const uint32_t a_lo0 = smem_u32(smem_a) >> 4, w_lo0 = smem_u32(smem_w) >> 4;
+    mbar_wait(wfull, 0);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      mbar_wait(&fullA[pa.stage], pa.phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_addr = tmem_base + (uint32_t)(acc * 256);
+        const uint32_t slab_lo = a_lo0 + (uint32_t)pa.stage * (uint32_t)(kSlab3Bytes >> 4);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const uint32_t a_lo = slab_lo + (uint32_t)(ky * kSlabP) * 8u;            // 32 rows = 4 swizzle atoms down
+          const uint32_t b_lo = w_lo0 + (uint32_t)ky * (uint32_t)((3 * 64 * 128) >> 4);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16(d_addr, kDescKMajor | (uint64_t)(a_lo + 2 * k), kDescKMajor | (uint64_t)(b_lo + 2 * k), idesc,
+                     (ky | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&emptyA[pa.stage]);
+        umma_commit(&tfull_bar[acc]);
+      }
+      __syncwarp();
+      pa.advance<kSlab3Stages>();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    const int q = warp & 3;       // TMEM lane quarter == image row of the tile
+    const int half = (warp - 2) >> 2;   // which 32 of the 64 output columns
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool ep_leader = (threadIdx.x == 64);
+    const int srow = q * kSlabWV + lane;
+    uint32_t sg = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int r = tile / p.n_tiles;
+      const int x0 = (r % p.tiles_w) * kSlabWV;
+      r /= p.tiles_w;
+      const int y0 = (r % p.tiles_h) * kSlabH;
+      const int n = r / p.tiles_h;
+      const int ox = x0 + lane, oy = y0 + q;
+      const bool valid = lane < kSlabWV && ox < p.W && oy < p.H;
+      const int64_t obase = (((int64_t)n * p.H + oy) * p.W + ox) * p.ldo + (int64_t)nt * 64;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+      {
+        const int c0 = half * 32;
+        uint8_t* sbuf = smem_out + (sg & 1) * kStageOutBytes;
+        if (p.tma_store) {
+          if (ep_leader) tma_store_wait_read<1>();
+          named_bar_sync(1, kEpiThreads);
+        }
+        float4 bv[8];
+        if (p.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + nt * 64 + c0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = __ldg(b4 + i);
+        }
+        float v[32];
+        {
+          uint32_t r0[32], r1[32], r2[32];
+          tmem_ld32(taddr + c0, r0);
+          tmem_ld32(taddr + 64 + c0, r1);
+          tmem_ld32(taddr + 128 + c0, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            v[i] = __uint_as_float(r0[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(r1[i]), 1) +
+                   __shfl_down_sync(0xffffffffu, __uint_as_float(r2[i]), 2);
+        }
+        if (valid) {
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w;
+            }
+          }
+          if (p.residual) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = __ldg(r4 + i);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2((&u.x)[j]);
+                v[8 * i + 2 * j] += f.x;
+                v[8 * i + 2 * j + 1] += f.y;
+              }
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (p.mask) {
+            const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 u = __ldg(m4 + i);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2((&u.x)[j]);
+                if (!(f.x > 0.f)) v[8 * i + 2 * j] = 0.f;
+                if (!(f.y > 0.f)) v[8 * i + 2 * j + 1] = 0.f;
+              }
+            }
+          }
+          if (p.scale != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+          }
+          if (p.out_f32) {
+            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else if (p.tma_store) {
+            const int pbase = half * 4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(sbuf + srow * 128 + (((pbase + i) ^ (srow & 7)) << 4)) =
+                  make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                             pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+          } else {
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + obase + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              o4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                                 pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+          }
+        }
+        if (p.tma_store) {
+          fence_proxy_async();
+          named_bar_sync(1, kEpiThreads);
+          if (ep_leader) {
+            tma_store_4d(&maps.c, sbuf, nt * 64, x0, y0, n);
+            tma_store_commit();
+          }
+          ++sg;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (p.tma_store && ep_leader) tma_store_wait_read<0>();
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -693,7 +936,7 @@ struct WgradParams {
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const TapTable taps) {
   using C = WCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -925,10 +1168,6 @@ int ensure_workspace(segk_ctx* ctx, size_t bytes) {
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-struct Box {
-  int bw, bh, bn, rows, tiles;
-};
-
 // Pick a pixel box bw x bh x bn with at most `max_rows` rows (exactly, when `exact`) that
 // covers [N,H,W] with the fewest tiles; ties -> wider bw (longer contiguous runs for TMA).
 // Number of (tile, tap) pairs that survive tile-level tap skipping for a kh x kw SAME conv when
@@ -1039,7 +1278,7 @@ template <int BLOCK_N>
 int launch_wgrad_t(segk_ctx* ctx, const TensorMaps& maps, const WgradParams& p, const TapTable& taps, int grid,
                    cudaStream_t st) {
   using C = WCfg<BLOCK_N>;
-  wgrad_kernel<BLOCK_N><<<grid, kThreads, C::kSmemBytes, st>>>(maps, p, taps);
+  wgrad_kernel<BLOCK_N><<<grid, kWgradThreads, C::kSmemBytes, st>>>(maps, p, taps);
   SEGK_LAUNCHED(ctx, "wgrad");
   return SEGK_OK;
 }
@@ -1065,14 +1304,31 @@ bool slab_applicable(const segk_ctx* ctx, int N, int H, int W, int Ck, int Cn, i
 int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, const float* bias, const void* residual,
               const void* mask, float scale, int relu, int out_f32, void* y, int N, int H, int W, int Ck, int Cn,
               void* stream) {
-  const int block_n = pick_block_n(ctx, Cn);
+  // Ck = 64: kx-fused N = 192 MMAs on resident weights (slab3_kernel), 64-channel output tiles.  Measured
+  // (tools/time_n64.py): wins for the plain forward of 64 -> 64 (264 vs 296 us at B=32 160x576), loses where
+  // the epilogue carries a ReLU mask (dgrad) or there are two channel tiles; slab3 = 2 forces it.
+  const bool fused3 = Ck == 64 && (Cn / 64) <= ctx->sm_count &&
+                      (ctx->slab3 == 2 || (ctx->slab3 == 1 && Cn == 64 && mask == nullptr));
+  const int block_n = fused3 ? 64 : pick_block_n(ctx, Cn);
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));
   int rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Ck, Ck, (int64_t)W * Ck, (int64_t)H * W * Ck, kSlabP, kSlabH + 2, 1);
   if (rc) return rc;
   maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
-  rc = encode_weight_map(ctx, &maps.b, wt, Ck, Cn, 9, block_n);
-  if (rc) return rc;
+  if (fused3) {
+    // box (64 k, 64 channels, 3 taps): the three kx taps of one ky land as one [192][64] operand
+    cuuint64_t dims[3] = {(cuuint64_t)Ck, (cuuint64_t)Cn, 9};
+    cuuint64_t strides[2] = {(cuuint64_t)Ck * 2, (cuuint64_t)Ck * Cn * 2};
+    cuuint32_t box[3] = {64, 64, 3};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ctx->encode_tiled(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wt), dims, strides, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return segk_fail(ctx, SEGK_ECUDA, "%s: cuTensorMapEncodeTiled(3-tap weights) failed: %d", what, (int)r);
+  } else {
+    rc = encode_weight_map(ctx, &maps.b, wt, Ck, Cn, 9, block_n);
+    if (rc) return rc;
+  }
   SlabParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.H = H; p.W = W;
@@ -1087,7 +1343,13 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
   }
   const int total = N * p.tiles_h * p.tiles_w * p.n_tiles;
   const int grid = total < ctx->sm_count ? total : ctx->sm_count;
-  (void)what;
+  if (fused3) {
+    // every CTA keeps one channel tile: grid = a multiple of n_tiles (total is one by construction)
+    const int g3 = total < ctx->sm_count ? total : (ctx->sm_count / p.n_tiles) * p.n_tiles;
+    slab3_kernel<<<g3, kThreads, kSlab3Smem, (cudaStream_t)stream>>>(maps, p);
+    SEGK_LAUNCHED(ctx, "slab3");
+    return SEGK_OK;
+  }
   switch (block_n) {
     case 256: return launch_slab_t<256>(ctx, maps, p, grid, (cudaStream_t)stream);
     case 128: return launch_slab_t<128>(ctx, maps, p, grid, (cudaStream_t)stream);
@@ -1213,6 +1475,17 @@ void strided_taps(TapTable& t, int k, int s) {
 }
 
 }  // namespace
+
+namespace tch {
+Box pick_box(int N, int H, int W, int max_rows, bool exact) { return choose_box(N, H, W, max_rows, exact); }
+int act_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn) {
+  return encode_act_map(ctx, m, base, N, H, W, C, C, (int64_t)W * C, (int64_t)H * W * C, bw, bh, bn);
+}
+int weight_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int K, int Nrows, int T, int block_n) {
+  return encode_weight_map(ctx, m, base, K, Nrows, T, block_n);
+}
+int workspace(segk_ctx* ctx, size_t bytes) { return ensure_workspace(ctx, bytes); }
+}  // namespace tch
 
 extern "C" {
 
@@ -1370,6 +1643,10 @@ int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, i
                Cin, Cout);
   SEGK_REQUIRE(ctx, (kh & 1) && (kw & 1) && kh * kw <= kMaxTaps, "conv2d_wgrad: odd kernel sizes up to %d taps", kMaxTaps);
   SEGK_REQUIRE(ctx, (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) == 0, "conv2d_wgrad: 16-byte alignment");
+  {
+    const int handled = segk_wslab_try(ctx, x, dy, dw, N, H, W, Cin, Cout, kh, kw, accumulate, stream);
+    if (handled != 0) return handled < 0 ? handled : SEGK_OK;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   const Box b = choose_box(N, H, W, 64, true);
   SEGK_REQUIRE(ctx, b.rows == 64, "conv2d_wgrad: cannot tile %dx%dx%d into 64-pixel boxes (need N*H*W >= 64)", N, H, W);
@@ -1432,6 +1709,7 @@ int segk_tc_init(segk_ctx* ctx) {
   ctx->force_wsplit = env_int("SEGK_FORCE_WSPLIT");
   ctx->slab_mode = env_int("SEGK_SLAB", 1);
   ctx->tma_store = env_int("SEGK_TMA_STORE", 1);
+  ctx->slab3 = env_int("SEGK_SLAB3", 1);
   cudaError_t e = cudaSuccess;
 #define SEGK_SMEM_ATTR(kern, bytes) \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
@@ -1444,7 +1722,10 @@ int segk_tc_init(segk_ctx* ctx) {
   SEGK_SMEM_ATTR(slab_kernel<64>, SlabCfg<64>::kSmemBytes);
   SEGK_SMEM_ATTR(slab_kernel<128>, SlabCfg<128>::kSmemBytes);
   SEGK_SMEM_ATTR(slab_kernel<256>, SlabCfg<256>::kSmemBytes);
+  SEGK_SMEM_ATTR(slab3_kernel, kSlab3Smem);
 #undef SEGK_SMEM_ATTR
   if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "tensor-core kernel setup: %s", cudaGetErrorString(e));
-  return SEGK_OK;
+  int rc = segk_first_init(ctx);
+  if (rc) return rc;
+  return segk_wslab_init(ctx);
 }

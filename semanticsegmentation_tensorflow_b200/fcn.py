@@ -108,7 +108,7 @@ class Variables:
             elif l.path == "tc":
                 self.wk[l.name], self.wd[l.name] = ops.pack_deconv_weights(w, l.stride, self.wk.get(l.name),
                                                                            self.wd.get(l.name))
-            elif l.path == "im2col":
+            elif l.path in ("first", "im2col"):
                 self.wk[l.name] = ops.pack_im2col_weights(w, self.wk.get(l.name))
             elif l.path == "patch":
                 # W[k,k,Cout,Cin] as the matrix [(ky,kx,co)][ci]: wk = fwd B operand, wd = its transpose
@@ -158,6 +158,7 @@ class FCN:
         self._alloc()
         self._ran_forward = False
         self.side = SideStream(self.device, enabled=overlap)
+        self.wside = SideStream(self.device, enabled=overlap)      # weight-gradient GEMMs beside the dgrad chain
 
     # -- buffers ------------------------------------------------------------------------
     @staticmethod
@@ -212,9 +213,10 @@ class FCN:
         self.cm = torch.zeros(4, dtype=torch.int64, device=dev)
         self.xent_ws = self.ops.xent_workspace(npix, dev)
         self.labels = torch.zeros((N, self.H, self.W), dtype=torch.uint8, device=dev)
-        # gradient ping-pong buffers (largest activation: N*H*W*64 bf16) + the two skip gradients
+        # rotating gradient buffers (largest activation: N*H*W*64 bf16) + the two skip gradients; three,
+        # so that a layer's wgrad on the side stream may still read dz while the next dgrad writes
         big = N * self.H * self.W * 64
-        self._gbuf = [torch.empty(big, dtype=bf, device=dev) for _ in range(2)]
+        self._gbuf = [torch.empty(big, dtype=bf, device=dev) for _ in range(3)]
         self.dfuse_1 = torch.empty_like(self.act["conv_t1"])
         self.dfuse_2 = torch.empty_like(self.act["conv_t2"])
 
@@ -278,6 +280,8 @@ class FCN:
                 b = V.param(f"{l.name}/{l.bias_name}")
                 if l.path == "tc":
                     ops.conv2d_fwd(cur, V.wk[l.name], b, out, l.k, l.k, relu=l.relu)
+                elif l.path == "first":
+                    ops.conv2d_first_fwd(cur, V.wk[l.name], b, out, l.k, l.k, relu=l.relu)
                 elif l.path == "im2col":
                     P1 = ops.im2col_k64(cur, self.patch[l.name], l.k, l.k)
                     ops.conv2d_fwd(P1, V.wk[l.name], b, out, 1, 1, relu=l.relu,
@@ -332,25 +336,39 @@ class FCN:
             return self.x if i == 0 else act[names[i - 1]]
         dcur = self.dlogits          # gradient wrt the current layer's output (pre-activation-grad applied)
         flip = 0
+        nbuf = len(self._gbuf)
+
+        def next_dx(like):
+            nonlocal flip
+            dx = self._g(flip, like)
+            flip = (flip + 1) % nbuf
+            self.side.before_write(dx)
+            self.wside.before_write(dx)
+            return dx
+
         for i in range(len(L) - 1, -1, -1):
             l = L[i]
             xin = prev_act(i)
             if l.kind == "pool":
                 # MaxPoolGrad fused with the ReluGrad of the pre-pool conv output
-                dx = self._g(flip, xin)
-                self.side.before_write(dx)
+                dx = next_dx(xin)
                 ops.maxpool_bwd(dcur, self.idx[l.name], dx, act=xin)
                 dcur = dx
-                flip ^= 1
                 continue
             gw = V.grad(f"{l.name}/weights")
             gb = V.grad(f"{l.name}/{l.bias_name}")
             # BiasAddGrad only reads dcur: HBM-bound, off the critical path -> side stream
-            self.side.run(lambda d=dcur, g=gb: ops.bias_grad(d, g), reads=(dcur,))
+            # (the fused first-layer wgrad produces it as one more row of its GEMM)
+            if l.path != "first":
+                self.side.run(lambda d=dcur, g=gb: ops.bias_grad(d, g), reads=(dcur,))
             prev = L[i - 1] if i > 0 else None
+            # tensor-core weight gradients go to the wgrad stream, ordered after this point (dcur is
+            # ready) but launched after the layer's dgrad so the critical-path kernel gets the SMs first
+            wjob, wmark, wreads = None, None, (dcur,)
             if l.kind == "deconv":
                 if l.path == "tc":
-                    ops.deconv2d_wgrad(xin, dcur, gw, l.k, l.stride)
+                    wjob = lambda x=xin, d=dcur, g=gw, l=l: ops.deconv2d_wgrad(x, d, g, l.k, l.stride)
+                    wmark = self.wside.mark()
                 elif l.path == "patch":
                     Pg = ops.deconv_patch_gather(dcur, self.patch[l.name], l.k, l.stride)
                     dfl = deconv_flops(self.N, xin.shape[1], xin.shape[2], l.cin, l.cout, l.k, l.stride)
@@ -363,9 +381,7 @@ class FCN:
                 elif l.name == "conv_t2":
                     dx = self.dfuse_1
                 else:
-                    dx = self._g(flip, xin)
-                    flip ^= 1
-                self.side.before_write(dx)
+                    dx = next_dx(xin)
                 mask = xin if (prev is not None and prev.kind == "conv" and prev.relu) else None
                 if l.path == "tc":
                     ops.deconv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.stride, relu_mask=mask)
@@ -373,10 +389,17 @@ class FCN:
                     ops.conv2d_dgrad(Pg, V.wd[l.name], dx, 1, 1, relu_mask=mask, flops=dfl)
                 else:
                     ops.deconv2d_small_dgrad(dcur, V.param(f"{l.name}/weights"), dx, l.stride, relu_mask=mask)
+                if wjob is not None:
+                    self.wside.run(wjob, reads=wreads, after=wmark)
                 dcur = dx
             else:
                 if l.path == "tc":
-                    ops.conv2d_wgrad(xin, dcur, gw, l.k, l.k)
+                    wjob = lambda x=xin, d=dcur, g=gw, l=l: ops.conv2d_wgrad(x, d, g, l.k, l.k)
+                    wmark = self.wside.mark()
+                elif l.path == "first":
+                    if i != 0:
+                        raise NotImplementedError("'first' route is for the first layer only (no input gradient)")
+                    ops.conv2d_first_wgrad(xin, dcur, gw, l.k, l.k, dbias=gb)
                 elif l.path == "im2col":
                     if i != 0:
                         raise NotImplementedError("im2col route is for the first layer only (no input gradient)")
@@ -385,21 +408,23 @@ class FCN:
                     gw.view(-1).copy_(tmp.view(-1)[:gw.numel()])      # rows >= K are the zero padding
                 else:
                     ops.conv2d_small_wgrad(xin, dcur, gw)
+                dnext = dcur
                 if i > 0:
                     # ReluGrad of the producer (mask = its output) and dropout backward (scale) fused
                     mask = xin if (prev.kind == "conv" and prev.relu) else None
                     scale = inv_keep if (prev.kind == "conv" and prev.dropout) else 1.0
                     # AddN of the skip gradients into pool4 / pool3 (FCN.py:92,96)
                     res = {"pool4": self.dfuse_1, "pool3": self.dfuse_2}.get(prev.name)
-                    dx = self._g(flip, xin)
-                    flip ^= 1
-                    self.side.before_write(dx)
+                    dx = next_dx(xin)
                     if l.path == "tc":
                         ops.conv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.k, relu_mask=mask, residual=res, scale=scale)
                     else:
                         assert res is None
                         ops.conv2d_small_dgrad(dcur, V.param(f"{l.name}/weights"), dx, relu_mask=mask, scale=scale)
-                    dcur = dx
+                    dnext = dx
+                if wjob is not None:
+                    self.wside.run(wjob, reads=wreads, after=wmark)
+                dcur = dnext
             if after_layer is not None:
                 after_layer(l.name)
 
@@ -505,6 +530,7 @@ class TrainStep:
         elif self.allreduce is None:
             net.backward()
             net.side.join()
+            net.wside.join()
             opt.apply(net)
             net.vars.repack(net.ops)
         else:
@@ -528,11 +554,13 @@ class TrainStep:
 
             def layer_done(name):
                 net.side.join()                   # this layer's bias gradients are part of the reduced arena
+                net.wside.join()                  # ... and so are its weight gradients
                 for lo, hi, work in self.allreduce.layer_done(name):
                     finalize(lo, hi, work)
 
             net.backward(after_layer=layer_done)
             net.side.join()
+            net.wside.join()
             for lo, hi, work in self.allreduce.flush():
                 finalize(lo, hi, work)
             fin.join()

@@ -208,6 +208,7 @@ class GraphNet:
         self._repack(self.ops)
         self._ran_forward = False
         self.side = SideStream(self.device, enabled=overlap)
+        self.wside = SideStream(self.device, enabled=False)      # (FCN runs its wgrad GEMMs on a second stream)
 
     # ---- planning ---------------------------------------------------------------------------
     def _route(self, n, cin):
@@ -217,6 +218,8 @@ class GraphNet:
             return "tc"
         if cin % 64 == 0 and n.cout % 64 == 0:
             return "tc"
+        if n.k == 3 and cin in (1, 3, 4) and n.cout in (64, 128, 256) and n.inputs[0] == "input":
+            return "first"
         if n.k * n.k * cin <= 64 and n.cout % 64 == 0 and n.inputs[0] == "input":
             return "im2col"
         if n.k == 1 and n.cout in (2, 4, 8) and cin % 8 == 0:
@@ -277,7 +280,7 @@ class GraphNet:
                 V.wk[n.name], V.wd[n.name] = ops.pack_deconv_weights(w, n.stride, V.wk.get(n.name), V.wd.get(n.name))
             elif r == "tc":
                 V.wk[n.name], V.wd[n.name] = ops.pack_conv_weights(w, V.wk.get(n.name), V.wd.get(n.name))
-            elif r == "im2col":
+            elif r in ("first", "im2col"):
                 V.wk[n.name] = ops.pack_im2col_weights(w, V.wk.get(n.name))
             else:
                 V.weff[n.name] = w
@@ -335,6 +338,8 @@ class GraphNet:
                 x, r = self._in(n.inputs[0]), self.route[n.name]
                 if r == "tc":
                     ops.conv2d_fwd(x, V.wk[n.name], self._bias(n), out, n.k, n.k, relu=n.relu)
+                elif r == "first":
+                    ops.conv2d_first_fwd(x, V.wk[n.name], self._bias(n), out, n.k, n.k, relu=n.relu)
                 elif r == "im2col":
                     P1 = ops.im2col_k64(x, self.patch[n.name], n.k, n.k)
                     ops.conv2d_fwd(P1, V.wk[n.name], self._bias(n), out, 1, 1, relu=n.relu,
@@ -408,13 +413,16 @@ class GraphNet:
                     ops.bn_gamma_grad(dz, self.act[n.name], V.param(f"{n.bn_scope}/beta"),
                                       V.param(f"{n.bn_scope}/gamma"), V.grad(f"{n.bn_scope}/gamma"), self.bn_ws)
                 self.side.run(bn_grads)
-            elif n.bias:
+            elif n.bias and r != "first":      # the fused first-layer wgrad also produces the bias gradient
                 self.side.run(lambda dz=dz, n=n: ops.bias_grad(dz, V.grad(f"{n.name}/biases")))
             # weight gradient (of the folded weights; unfold the BN scale afterwards)
             if n.kind == "deconv":
                 ops.deconv2d_wgrad(x, dz, gw, n.k, n.stride)
             elif r == "tc":
                 ops.conv2d_wgrad(x, dz, gw, n.k, n.k)
+            elif r == "first":
+                ops.conv2d_first_wgrad(x, dz, gw, n.k, n.k,
+                                       dbias=V.grad(f"{n.name}/biases") if (n.bias and not n.bn) else None)
             elif r == "im2col":
                 tmp = ops.conv2d_wgrad(self.patch[n.name], dz, self.tmp[n.name], 1, 1,
                                        flops=conv_flops(self.N, dz.shape[1], dz.shape[2], x.shape[3], n.cout, n.k, n.k))

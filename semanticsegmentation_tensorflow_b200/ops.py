@@ -147,6 +147,23 @@ class Ops:
         self.call("segk_pack_im2col_weights", _p(w), _p(wk), kh * kw * cin, cout, _stream())
         return wk
 
+    # ---- first layer: patches built in shared memory, no patch tensor (firstconv.cu) ------------
+    def conv2d_first_fwd(self, x, wk, bias, y, kh, kw, relu=True):
+        n, h, w, cin = x.shape
+        cout = y.shape[3]
+        self._w(float(x.numel() * x.element_size() + 2 * y.numel()), "byte")
+        self.call("segk_conv2d_first_fwd", _p(x), _dt(x), _p(wk), _p(bias), _p(y), n, h, w, cin, cout, kh, kw,
+                  EPI_RELU if relu else 0, _stream())
+        return y
+
+    def conv2d_first_wgrad(self, x, dy, dw, kh, kw, dbias=None):
+        n, h, w, cin = x.shape
+        cout = dy.shape[3]
+        self._w(float(x.numel() * x.element_size() + 2 * dy.numel()), "byte")
+        self.call("segk_conv2d_first_wgrad", _p(x), _dt(x), _p(dy), _p(dw), _p(dbias), n, h, w, cin, cout, kh, kw,
+                  _stream())
+        return dw
+
     # ---- patch-space helpers (conv1_1 / conv_t3 as tensor-core GEMMs) --------------------------
     def im2col_k64(self, x, P, kh, kw):
         n, h, w, cin = x.shape

@@ -1,8 +1,11 @@
-"""Second CUDA stream for the HBM-bound work that is off the tensor-core critical path of a training
+"""Side CUDA streams.  (1) For the HBM-bound work that is off the tensor-core critical path of a training
 step: BiasAddGrad of each layer, and the optimizer update + bf16 weight repack of a gradient bucket as
 soon as that bucket is complete.  The persistent tensor-core kernels hold one 192-thread CTA per SM
 (~200 KB of shared memory), so these streaming kernels co-reside on the same SMs and run in the
-shadow of the conv GEMMs instead of after them."""
+shadow of the conv GEMMs instead of after them.  (2) A second one carries the weight-gradient GEMMs:
+they are off the dgrad -> dgrad critical path of backward, so running them beside the next input-
+gradient kernels lets their CTAs fill the SMs a kernel's last partial wave leaves idle (conv5: 180
+tiles on 148 SMs = 61 % of two waves)."""
 from __future__ import annotations
 
 import torch
@@ -14,15 +17,26 @@ class SideStream:
         self.stream = torch.cuda.Stream(device) if enabled else None
         self._reads = {}          # storage ptr -> event after the last side-stream read of that buffer
 
-    def run(self, fn, reads=()):
+    def mark(self):
+        """Event on the current stream now; pass it to run(after=...) to order side work after this
+        point only (and not after what the main stream enqueues in between)."""
+        if not self.enabled:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return ev
+
+    def run(self, fn, reads=(), after=None):
         """Enqueue fn() on the side stream, ordered after everything enqueued on the current stream so
-        far.  `reads`: tensors the side work reads that the main stream may later overwrite."""
+        far (or up to the mark() event `after`).  `reads`: tensors the side work reads that the main
+        stream may later overwrite."""
         if not self.enabled:
             fn()
             return
-        main = torch.cuda.current_stream()
-        ev = torch.cuda.Event()
-        ev.record(main)
+        ev = after
+        if ev is None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
         self.stream.wait_event(ev)
         with torch.cuda.stream(self.stream):
             fn()
@@ -70,6 +84,9 @@ class LocalBuckets:
             opt.apply(net, lo, hi)
             net.vars.repack(net.ops, names)
 
+        wside = getattr(net, "wside", None)
+        if wside is not None and wside.enabled and net.side.enabled:
+            net.side.stream.wait_stream(wside.stream)     # the bucket's weight gradients come from there
         net.side.run(work)
 
     def layer_done(self, name):
@@ -82,3 +99,5 @@ class LocalBuckets:
             self._fire(self._next)
             self._next += 1
         self.net.side.join()
+        if getattr(self.net, "wside", None) is not None:
+            self.net.wside.join()

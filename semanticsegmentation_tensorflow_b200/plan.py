@@ -36,7 +36,8 @@ class Layer:
 
     @property
     def path(self) -> str:
-        """Kernel route: 'tc' implicit GEMM; 'im2col' = first layer with kh*kw*Cin <= 64 turned into
+        """Kernel route: 'tc' implicit GEMM; 'first' = 3x3 conv on the raw image (Cin 1/3/4) with the
+        patches built in shared memory; 'im2col' = other layers with kh*kw*Cin <= 64 turned into
         a 1x1 GEMM over a 64-wide patch tensor; 'patch' = transposed conv with tiny Cout run as
         GEMMs in patch space [N,H,W,k*k*Cout]; 'small' = CUDA-core kernels."""
         if self.kind == "pool":
@@ -44,6 +45,8 @@ class Layer:
         if self.kind == "conv":
             if self.cin % 64 == 0 and self.cout % 64 == 0:
                 return "tc"
+            if self.k == 3 and self.cin in (1, 3, 4) and self.cout in (64, 128, 256):
+                return "first"
             if self.k * self.k * self.cin <= 64 and self.cout % 64 == 0:
                 return "im2col"
             return "small"

@@ -27,8 +27,9 @@ ar = BucketedAllReduce.for_net(net)
 net.forward()
 net.loss(ys, with_grad=True)
 ar.begin_step()
-net.backward(after_layer=lambda name: (net.side.join(), ar.layer_done(name)))
+net.backward(after_layer=lambda name: (net.side.join(), net.wside.join(), ar.layer_done(name)))
 net.side.join()
+net.wside.join()
 for _ in ar.finish():
     pass
 torch.cuda.synchronize()

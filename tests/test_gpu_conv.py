@@ -158,6 +158,69 @@ def test_unsupported_shape_is_an_error_not_a_fallback(ops, cuda_device):
     assert ei.value.code == SEGK_EINVAL and "no fallback" in str(ei.value)
 
 
+Wdef test_slab3_forced_on_dgrad_with_mask(ops, cuda_device):
+    """slab3 = 2 also sends the masked / scaled dgrad epilogue through the kx-fused kernel."""
+    n, h, w, ci, co, k = 1, 64, 96, 64, 64, 3
+    x, wt, _ = _conv_case((n, h, w, ci, co, k), 24)
+    rng = np.random.default_rng(25)
+    dy = bf16_grid(rng.standard_normal((n, h, w, co)))
+    xt = torch.tensor(x, requires_grad=True)
+    T.conv2d_same(xt, torch.tensor(wt)).backward(torch.tensor(dy))
+    _, wd = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=cuda_device)
+    ops.ctx.set_tuning("slab3", 2)
+    try:
+        ops.conv2d_dgrad(dev_bf16(dy, cuda_device), wd, dx, k, k, relu_mask=dev_bf16(x, cuda_device), scale=0.5)
+        torch.cuda.synchronize()
+    finally:
+        ops.ctx.set_tuning("slab3", 1)
+    assert_close(host(dx), xt.grad.numpy() * (x > 0) * 0.5, TOL_BF16, "slab3 dgrad with mask")
+
+
+SLAB_SHAPES = [
+    # N, H, W, Cin, Cout: 3x3 layers routed to the slab-formulated wgrad (wslab = 2 forces it on small maps)
+    (2, 16, 64, 64, 64),          # all nine taps per item, tap pairs out of one slab
+    (1, 10, 37, 64, 128),         # ragged rows / columns, two 64-channel output tiles
+    (2, 12, 40, 128, 128),        # one filter row per item, (tap, both channel chunks) pairs, N = 128
+    (1, 9, 70, 128, 64),          # ... N = 64
+    (1, 64, 96, 64, 64),          # large enough for the automatic route
+    (3, 5, 33, 128, 256),
+]
+
+
+@pytest.mark.parametrize("shape", WSLAB_SHAPES)
+def test_slab_wgrad(ops, cuda_device, shape):
+    n, h, w, ci, co = shape
+    k = 3
+    x, wt, _ = _conv_case((n, h, w, ci, co, k), 30)
+    dy = bf16_grid(np.random.default_rng(31).standard_normal((n, h, w, co)))
+    wtt = torch.tensor(wt, requires_grad=True)
+    T.conv2d_same(torch.tensor(x), wtt).backward(torch.tensor(dy))
+    ref = wtt.grad.numpy()
+    xd, dyd = dev_bf16(x, cuda_device), dev_bf16(dy, cuda_device)
+    got = {}
+    try:
+        for mode in (2, 0):
+            ops.ctx.set_tuning("wslab", mode)
+            dw = torch.full((k, k, ci, co), 7.0, dtype=torch.float32, device=cuda_device)   # must be overwritten
+            ops.conv2d_wgrad(xd, dyd, dw, k, k)
+            torch.cuda.synchronize()
+            got[mode] = host(dw)
+            if mode == 2:
+                ops.conv2d_wgrad(xd, dyd, dw, k, k, accumulate=True)
+                torch.cuda.synchronize()
+                assert_close(host(dw), 2 * ref, TOL_F32, f"slab wgrad accumulate {shape}")
+                # deterministic: per-split partial sums + ordered reduction, no atomics
+                dw2 = torch.empty_like(dw)
+                ops.conv2d_wgrad(xd, dyd, dw2, k, k)
+                torch.cuda.synchronize()
+                assert np.array_equal(host(dw2), got[2])
+    finally:
+        ops.ctx.set_tuning("wslab", 1)
+    assert_close(got[2], ref, TOL_F32, f"slab wgrad {shape}")
+    assert_close(got[2], got[0], TOL_F32, f"slab wgrad vs tap-wise wgrad {shape}")
+
+
 SLAB_SHAPES = [
     # N, H, W, Cin, Cout  (3x3; routed to the haloed-slab kernel: Cout <= 128 and H*W >= 4096)
     (2, 64, 96, 64, 64),
@@ -165,6 +228,8 @@ SLAB_SHAPES = [
     (1, 160, 576, 64, 64),
     (2, 40, 144, 128, 128),
     (1, 64, 70, 128, 64),        # W not a multiple of 30: ragged last column tile
+    (1, 64, 70, 64, 64),         # the same through the kx-fused N = 192 kernel (Cin = 64)
+    (3, 8, 576, 64, 128),        # two channel tiles per CTA grid, short images
 ]
 
 
@@ -199,6 +264,30 @@ def test_slab_forced_for_wide_layers(ops, cuda_device):
         _slab_forced_body(ops, cuda_device)
     finally:
         ops.ctx.set_tuning("slab", 1)
+
+
+def test_slab3_matches_plain_slab_and_handles_three_channel_tiles(ops, cuda_device):
+    """Cin = 64 layers take the kx-fused kernel (three taps per N = 192 MMA, weights resident);
+    slab3 = 0 sends the same call through the tap-wise slab kernel: same sums, fp32 reassociated."""
+    n, h, w, ci, co, k = 2, 32, 150, 64, 192, 3
+    x, wt, b = _conv_case((n, h, w, ci, co, k), 23)
+    ref = T.relu(T.bias_add(T.conv2d_same(torch.tensor(x), torch.tensor(wt)), torch.tensor(b))).numpy()
+    wk, _ = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    xd, bd = dev_bf16(x, cuda_device), dev_f32(b, cuda_device)
+    ys = []
+    ops.ctx.set_tuning("slab", 2)
+    try:
+        for fused in (2, 0):
+            ops.ctx.set_tuning("slab3", fused)
+            y = torch.full((n, h, w, co), float("nan"), dtype=torch.bfloat16, device=cuda_device)
+            ops.conv2d_fwd(xd, wk, bd, y, k, k, relu=True)
+            torch.cuda.synchronize()
+            ys.append(host(y))
+    finally:
+        ops.ctx.set_tuning("slab", 1)
+        ops.ctx.set_tuning("slab3", 1)
+    assert_close(ys[0], ref, TOL_BF16, "slab3 fwd, 3 channel tiles")
+    assert_close(ys[0], ys[1], TOL_BF16, "slab3 vs tap-wise slab")
 
 
 def _slab_forced_body(ops, cuda_device):

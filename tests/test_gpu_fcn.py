@@ -188,7 +188,7 @@ def test_checkpoint_roundtrip_with_adam_slots(cuda_device, tmp_path):
     from semanticsegmentation_tensorflow_b200.checkpoint import load_checkpoint, save_checkpoint, state_dict
     from semanticsegmentation_tensorflow_b200.fcn import AdamOptimizer, FCN
     net, variables, x, lab = _build(cuda_device, "he")
-    net.side.enabled = False                      # deterministic kernel order for the bit-identity check
+    net.side.enabled = net.wside.enabled = False  # deterministic kernel order for the bit-identity check
     opt = AdamOptimizer(1e-4)
     step = opt.minimize(net)
     xd, ld = torch.as_tensor(x).to(cuda_device), torch.as_tensor(lab).to(cuda_device)
@@ -201,7 +201,7 @@ def test_checkpoint_roundtrip_with_adam_slots(cuda_device, tmp_path):
     assert "conv_t3/bias" in sd and "conv6/weights/Adam_1" in sd
     assert float(sd["beta1_power"]) == pytest.approx(0.9 ** 3)
     net2 = FCN(xd, 1.0, 2, variables=None, init="ref", fc=FC)
-    net2.side.enabled = False
+    net2.side.enabled = net2.wside.enabled = False
     opt2 = AdamOptimizer(1e-4)
     step2 = opt2.minimize(net2)
     load_checkpoint(path, net2, opt2)

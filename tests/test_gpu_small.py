@@ -139,6 +139,79 @@ def test_conv1_1_as_im2col_gemm(ops, cuda_device, cin):
     assert_close(got[:9 * cin].reshape(3, 3, cin, co), wtt.grad.numpy(), 2e-3, "conv1_1 im2col wgrad")
 
 
+@pytest.mark.parametrize("case", [(2, 16, 24, 3, 64, "u8"), (3, 10, 37, 3, 64, "u8"), (1, 5, 7, 4, 64, "u8"),
+                                  (2, 12, 20, 1, 128, "u8"), (2, 9, 33, 3, 256, "bf16"), (5, 4, 4, 3, 64, "u8")])
+def test_conv1_1_fused_first_layer(ops, cuda_device, case):
+    """conv1_1 with the 3x3 patches built in shared memory (no patch tensor): forward, and
+    Conv2DBackpropFilter + BiasAddGrad in one pass over dy (FCN.py:52,340)."""
+    n, h, w, cin, co, dt = case
+    rng = np.random.default_rng(12)
+    if dt == "u8":
+        img = rng.integers(0, 256, (n, h, w, cin), dtype=np.uint8)
+        xd = torch.as_tensor(img).to(cuda_device)
+        xf = img.astype(np.float32)
+    else:
+        xf = bf16_grid(rng.standard_normal((n, h, w, cin)))
+        xd = dev_bf16(xf, cuda_device)
+    wt = bf16_grid(rng.standard_normal((3, 3, cin, co)) * 0.01)
+    b = (rng.standard_normal(co) * 0.1).astype(np.float32)
+    wtt = torch.tensor(wt, requires_grad=True)
+    bt = torch.tensor(b, requires_grad=True)
+    z = T.bias_add(T.conv2d_same(torch.tensor(xf), wtt), bt)
+    wk = ops.pack_im2col_weights(dev_f32(wt, cuda_device))
+    y = torch.full((n, h, w, co), float("nan"), dtype=torch.bfloat16, device=cuda_device)
+    ops.conv2d_first_fwd(xd, wk, dev_f32(b, cuda_device), y, 3, 3, relu=True)
+    torch.cuda.synchronize()
+    assert_close(host(y), T.relu(z).detach().numpy(), 1e-2, f"first-layer fwd {case}")
+    dy = bf16_grid(rng.standard_normal((n, h, w, co)))
+    z.backward(torch.tensor(dy))
+    dw = torch.full((3, 3, cin, co), float("nan"), dtype=torch.float32, device=cuda_device)
+    db = torch.full((co,), float("nan"), dtype=torch.float32, device=cuda_device)
+    ops.conv2d_first_wgrad(xd, dev_bf16(dy, cuda_device), dw, 3, 3, dbias=db)
+    torch.cuda.synchronize()
+    assert_close(host(dw), wtt.grad.numpy(), 2e-3, f"first-layer wgrad {case}")
+    assert_close(host(db), bt.grad.numpy(), 2e-3, f"first-layer bias grad {case}")
+    # and without the bias gradient
+    dw2 = torch.empty_like(dw)
+    ops.conv2d_first_wgrad(xd, dev_bf16(dy, cuda_device), dw2, 3, 3)
+    torch.cuda.synchronize()
+    assert torch.equal(dw, dw2)
+
+
+def test_conv1_1_fused_matches_im2col_route_full_width(ops, cuda_device):
+    """Same layer through both tensor-core routes at a KITTI-width image: identical operands, so the
+    forward results agree to bf16 rounding of the same fp32 sums."""
+    n, h, w, cin, co = 2, 32, 576, 3, 64
+    rng = np.random.default_rng(13)
+    img = torch.as_tensor(rng.integers(0, 256, (n, h, w, cin), dtype=np.uint8)).to(cuda_device)
+    wt = dev_f32(bf16_grid(rng.standard_normal((3, 3, cin, co)) * 0.01), cuda_device)
+    b = dev_f32((rng.standard_normal(co) * 0.1).astype(np.float32), cuda_device)
+    wk = ops.pack_im2col_weights(wt)
+    P = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=cuda_device)
+    y1 = torch.empty((n, h, w, co), dtype=torch.bfloat16, device=cuda_device)
+    y2 = torch.empty_like(y1)
+    ops.im2col_k64(img, P, 3, 3)
+    ops.conv2d_fwd(P, wk, b, y1, 1, 1, relu=True)
+    ops.conv2d_first_fwd(img, wk, b, y2, 3, 3, relu=True)
+    dy = dev_bf16(bf16_grid(rng.standard_normal((n, h, w, co))), cuda_device)
+    dw1 = torch.empty((1, 1, 64, co), dtype=torch.float32, device=cuda_device)
+    dw2 = torch.empty((3, 3, cin, co), dtype=torch.float32, device=cuda_device)
+    ops.conv2d_wgrad(P, dy, dw1, 1, 1)
+    ops.conv2d_first_wgrad(img, dy, dw2, 3, 3)
+    torch.cuda.synchronize()
+    assert_close(host(y2), host(y1), 1e-2, "first-layer fwd vs im2col route")
+    assert_close(host(dw2).reshape(27, co), host(dw1).reshape(64, co)[:27], 1e-3, "first-layer wgrad vs im2col route")
+
+
+def test_conv1_1_fused_rejects_unsupported(ops, cuda_device):
+    from semanticsegmentation_tensorflow_b200._lib import SegkError
+    x = torch.zeros((1, 8, 8, 2), dtype=torch.uint8, device=cuda_device)
+    wk = torch.zeros((1, 64, 64), dtype=torch.bfloat16, device=cuda_device)
+    y = torch.zeros((1, 8, 8, 64), dtype=torch.bfloat16, device=cuda_device)
+    with pytest.raises(SegkError):
+        ops.conv2d_first_fwd(x, wk, None, y, 3, 3)
+
+
 def test_conv_t3_in_patch_space(ops, cuda_device):
     """conv_t3 (16x16 s8, Cout=2): fwd = 1x1 GEMM + col2im, bwd = patch gather + 1x1 GEMMs."""
     n, h, w, ci, co, k, s = 2, 5, 9, 256, 2, 16, 8
