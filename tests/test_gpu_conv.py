@@ -158,26 +158,7 @@ def test_unsupported_shape_is_an_error_not_a_fallback(ops, cuda_device):
     assert ei.value.code == SEGK_EINVAL and "no fallback" in str(ei.value)
 
 
-Wdef test_slab3_forced_on_dgrad_with_mask(ops, cuda_device):
-    """slab3 = 2 also sends the masked / scaled dgrad epilogue through the kx-fused kernel."""
-    n, h, w, ci, co, k = 1, 64, 96, 64, 64, 3
-    x, wt, _ = _conv_case((n, h, w, ci, co, k), 24)
-    rng = np.random.default_rng(25)
-    dy = bf16_grid(rng.standard_normal((n, h, w, co)))
-    xt = torch.tensor(x, requires_grad=True)
-    T.conv2d_same(xt, torch.tensor(wt)).backward(torch.tensor(dy))
-    _, wd = ops.pack_conv_weights(dev_f32(wt, cuda_device))
-    dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=cuda_device)
-    ops.ctx.set_tuning("slab3", 2)
-    try:
-        ops.conv2d_dgrad(dev_bf16(dy, cuda_device), wd, dx, k, k, relu_mask=dev_bf16(x, cuda_device), scale=0.5)
-        torch.cuda.synchronize()
-    finally:
-        ops.ctx.set_tuning("slab3", 1)
-    assert_close(host(dx), xt.grad.numpy() * (x > 0) * 0.5, TOL_BF16, "slab3 dgrad with mask")
-
-
-SLAB_SHAPES = [
+WSLAB_SHAPES = [
     # N, H, W, Cin, Cout: 3x3 layers routed to the slab-formulated wgrad (wslab = 2 forces it on small maps)
     (2, 16, 64, 64, 64),          # all nine taps per item, tap pairs out of one slab
     (1, 10, 37, 64, 128),         # ragged rows / columns, two 64-channel output tiles
@@ -219,6 +200,25 @@ def test_slab_wgrad(ops, cuda_device, shape):
         ops.ctx.set_tuning("wslab", 1)
     assert_close(got[2], ref, TOL_F32, f"slab wgrad {shape}")
     assert_close(got[2], got[0], TOL_F32, f"slab wgrad vs tap-wise wgrad {shape}")
+
+
+def test_slab3_forced_on_dgrad_with_mask(ops, cuda_device):
+    """slab3 = 2 also sends the masked / scaled dgrad epilogue through the kx-fused kernel."""
+    n, h, w, ci, co, k = 1, 64, 96, 64, 64, 3
+    x, wt, _ = _conv_case((n, h, w, ci, co, k), 24)
+    rng = np.random.default_rng(25)
+    dy = bf16_grid(rng.standard_normal((n, h, w, co)))
+    xt = torch.tensor(x, requires_grad=True)
+    T.conv2d_same(xt, torch.tensor(wt)).backward(torch.tensor(dy))
+    _, wd = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=cuda_device)
+    ops.ctx.set_tuning("slab3", 2)
+    try:
+        ops.conv2d_dgrad(dev_bf16(dy, cuda_device), wd, dx, k, k, relu_mask=dev_bf16(x, cuda_device), scale=0.5)
+        torch.cuda.synchronize()
+    finally:
+        ops.ctx.set_tuning("slab3", 1)
+    assert_close(host(dx), xt.grad.numpy() * (x > 0) * 0.5, TOL_BF16, "slab3 dgrad with mask")
 
 
 SLAB_SHAPES = [
