@@ -202,3 +202,20 @@ def test_overlay_mask_bit_exact(ops, cuda_device, c):
     out = ops.overlay_mask(torch.as_tensor(img).to(cuda_device), torch.as_tensor(mask).to(cuda_device))
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), T.paste_mask(img, prob))
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 64, 128), (1, 1, 192, 64), (7, 7, 64, 64), (3, 3, 32, 96), (3, 3, 3, 64)])
+def test_pack_conv_weights_layouts_bit_exact(ops, cuda_device, shape):
+    """fp32 HWIO master (FCN.py:125) -> wk[tap][Cout][Cin] and wd[rot180 tap][Cin][Cout], both the
+    round-to-nearest-even bf16 of the master (64-wide vectorised kernel and the generic one)."""
+    kh, kw, ci, co = shape
+    rng = np.random.default_rng(40)
+    w = rng.standard_normal(shape).astype(np.float32)
+    wd_ = torch.as_tensor(w).to(cuda_device)
+    wk, wd = ops.pack_conv_weights(wd_)
+    torch.cuda.synchronize()
+    ref = torch.as_tensor(w).to(torch.bfloat16).float().numpy().reshape(kh * kw, ci, co)
+    got_k = wk.float().cpu().numpy().reshape(kh * kw, co, ci)
+    got_d = wd.float().cpu().numpy().reshape(kh * kw, ci, co)
+    assert np.array_equal(got_k, ref.transpose(0, 2, 1))
+    assert np.array_equal(got_d, ref[::-1])
