@@ -18,6 +18,11 @@ int weight_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int K, int Nrows
 int workspace(segk_ctx* ctx, size_t bytes);
 }  // namespace tch
 
+// grow-only scratch for per-split weight-gradient partial sums (ctx->ws4) and their ordered reduction:
+// dw[i] (+)= sum_s part[s*n + i]   (n % 4 == 0)
+int segk_ws4(segk_ctx* ctx, size_t bytes);
+int segk_reduce_partials(segk_ctx* ctx, const float* part, float* dw, size_t n, int splits, int accumulate, cudaStream_t st);
+
 int segk_first_init(segk_ctx* ctx);
 int segk_wslab_init(segk_ctx* ctx);   // wslab.cu
 // slab-formulated Conv2DBackpropFilter: 1 = handled, 0 = not applicable, < 0 = error

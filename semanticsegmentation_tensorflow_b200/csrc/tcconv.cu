@@ -94,10 +94,12 @@ struct IgemmParams {
   const bf16* mask;
   float scale;
   int relu;
-  // split-K over the (tap, k-chunk) walk: unit = tile * ksplits + split; partial sums are
-  // atomically added into the fp32 workspace `ws` [pixels][ldo] and finished by epilogue_finish_kernel
+  // split-K over the (tap, k-chunk) walk: unit = tile * ksplits + split; split s stores its partial
+  // sums (plain 16-byte stores, no atomics: measured ~20 us per million scattered fp32 REDs) into slice s
+  // of the fp32 workspace `ws` [ksplits][pixels][ldo]; epilogue_finish_kernel adds the slices up
   int ksplits;
   float* ws;
+  int64_t ws_slice;   // elements per slice
   int tma_store;   // 1: bf16 output leaves through shared memory + TMA store (coalesced, async, clipped)
   int m_fastest;   // tile order: 0 = channel tile fastest (activations shared), 1 = pixel tile fastest (weights shared)
 };
@@ -120,8 +122,15 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
   TileCoord t;
-  t.split = tile % p.ksplits;
-  tile /= p.ksplits;
+  if (p.m_fastest) {
+    // split slowest: the CTAs running at the same time walk the same K range, i.e. share weight slices
+    const int tiles = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+    t.split = tile / tiles;
+    tile -= t.split * tiles;
+  } else {
+    t.split = tile % p.ksplits;
+    tile /= p.ksplits;
+  }
   if (p.m_fastest) {
     // weight-heavy layers (conv6: 205 MB of weights, 3 MB of activations): consecutive CTAs take
     // different pixel tiles of the SAME channel tile, so a weight tile is fetched from DRAM once and
@@ -207,8 +216,8 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
       const TileCoord t = decode_tile(p, tile);
       const uint64_t tm = tap_mask(p, taps, t);
       const int nall = __popcll(tm) * p.kchunks;
-      const int per = (nall + p.ksplits - 1) / p.ksplits;
-      const int lo = t.split * per, hi = min(lo + per, nall);
+      // balanced partition: no split is empty because ksplits <= kchunks <= nall
+      const int lo = (int)(((int64_t)nall * t.split) / p.ksplits), hi = (int)(((int64_t)nall * (t.split + 1)) / p.ksplits);
       int step = 0;
       for (int i = 0; i < p.ntaps; ++i) {
         if (!((tm >> i) & 1)) continue;
@@ -238,8 +247,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
       const TileCoord t = decode_tile(p, tile);
       const uint64_t tm = tap_mask(p, taps, t);
       const int nall = __popcll(tm) * p.kchunks;
-      const int per = (nall + p.ksplits - 1) / p.ksplits;
-      const int nsteps = min(t.split * per + per, nall) - t.split * per;   // host guarantees > 0
+      const int nsteps = (int)(((int64_t)nall * (t.split + 1)) / p.ksplits) - (int)(((int64_t)nall * t.split) / p.ksplits);   // > 0
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -306,9 +314,11 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
         if (valid && p.ksplits > 1) {
-          float* w = p.ws + obase + c0;
+          float4* w4 = reinterpret_cast<float4*>(p.ws + (int64_t)t.split * p.ws_slice + obase + c0);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(w + i, __uint_as_float(r[i]));
+          for (int i = 0; i < 8; ++i)
+            w4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                __uint_as_float(r[4 * i + 3]));
         } else if (valid) {
           float v[32];
 #pragma unroll
@@ -931,7 +941,8 @@ struct WgradParams {
   int dw_tap_stride;          // elements between taps in dW (= Cin*Cout for HWIO)
   int dw_row_stride;          // elements between consecutive ci rows (= Cout for HWIO)
   int dw_col_stride;          // elements between consecutive co (1 for HWIO)
-  int direct;                 // 1: single split, overwrite -> plain 16-byte stores instead of atomics
+  int direct;                 // 1: plain 16-byte stores (single split, or per-split partial buffers) instead of atomics
+  int64_t part_stride;        // elements between the partial buffers of consecutive splits (0: dw is the result itself)
   float* dw;
 };
 
@@ -1066,7 +1077,7 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
       const bool valid = rb < p.n_rb;
       const int tap = rb / p.kchunks_in;
       const int ci = (rb % p.kchunks_in) * 64 + (row & 63);
-      float* dst = p.dw + (int64_t)tap * p.dw_tap_stride + (int64_t)ci * p.dw_row_stride +
+      float* dst = p.dw + (int64_t)split * p.part_stride + (int64_t)tap * p.dw_tap_stride + (int64_t)ci * p.dw_row_stride +
                    (int64_t)(nt * BLOCK_N) * p.dw_col_stride;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -1102,8 +1113,9 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
   if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
-// Finishes a split-K igemm: out = epilogue(ws) over [rows][C], 8 channels per thread.
-__global__ void __launch_bounds__(256) epilogue_finish_kernel(const float* __restrict__ ws, const float* __restrict__ bias,
+// Finishes a split-K igemm: out = epilogue(sum of the ksplits slices of ws) over [rows][C], 8 channels per thread.
+__global__ void __launch_bounds__(256) epilogue_finish_kernel(const float* __restrict__ ws, int ksplits, int64_t slice,
+                                                              const float* __restrict__ bias,
                                                               const bf16* __restrict__ residual,
                                                               const bf16* __restrict__ mask, void* __restrict__ out,
                                                               int out_f32, int relu, float scale, int64_t rows, int C) {
@@ -1115,6 +1127,11 @@ __global__ void __launch_bounds__(256) epilogue_finish_kernel(const float* __res
     float v[8];
     const float4 a = *reinterpret_cast<const float4*>(ws + base), b = *reinterpret_cast<const float4*>(ws + base + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    for (int s = 1; s < ksplits; ++s) {
+      const float4 a2 = *reinterpret_cast<const float4*>(ws + s * slice + base);
+      const float4 b2 = *reinterpret_cast<const float4*>(ws + s * slice + base + 4);
+      v[0] += a2.x; v[1] += a2.y; v[2] += a2.z; v[3] += a2.w; v[4] += b2.x; v[5] += b2.y; v[6] += b2.z; v[7] += b2.w;
+    }
     if (bias) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += __ldg(bias + c + j);
@@ -1413,25 +1430,28 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   const int tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
   const int force_ks = ctx->force_ksplit;
   if ((tiles * 2 <= ctx->sm_count && p.ntaps * p.kchunks >= 32 && p.kchunks >= 2) || force_ks > 0) {
+    // one wave of work units.  Measured (tools/time_conv6.py, conv6 dgrad: 50 tiles x 2240 k-steps): 2 splits
+    // 483 us, 1: 766, 3: 596, 5: 562, 8: 692, 14: 918 -- more splits than one wave lets the m-tiles that share
+    // a weight slice drift apart in K, and the 205 MB of weights stream from DRAM several times over
     int ks = ctx->sm_count / tiles;
     if (force_ks > 0) ks = force_ks;
-    if (ks > p.kchunks) ks = p.kchunks;   // every split keeps >= 1 step even if a single tap is active
+    if (ks > p.kchunks) ks = p.kchunks;   // ksplits <= kchunks <= k-steps of any tile: no split is empty
     if (ks > 16) ks = 16;
     if (ks > 1) {
-      const size_t bytes = sizeof(float) * (size_t)N * H * W * Cn;
-      rc = ensure_workspace(ctx, bytes);
+      const size_t slice = (size_t)N * H * W * Cn;
+      rc = ensure_workspace(ctx, sizeof(float) * slice * ks);
       if (rc) return rc;
-      cudaError_t e = cudaMemsetAsync(ctx->ws, 0, bytes, (cudaStream_t)stream);
-      if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "%s: workspace memset: %s", what, cudaGetErrorString(e));
       p.ksplits = ks;
       p.ws = (float*)ctx->ws;
+      p.ws_slice = (int64_t)slice;
       rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
       if (rc) return rc;
       const int64_t rows = (int64_t)N * H * W;
       int64_t blocks = ceil_div64(rows * (Cn / 8), 256);
       if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
       epilogue_finish_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
-          (const float*)ctx->ws, bias, (const bf16*)residual, (const bf16*)mask, y, out_f32, relu, scale, rows, Cn);
+          (const float*)ctx->ws, ks, (int64_t)slice, bias, (const bf16*)residual, (const bf16*)mask, y, out_f32, relu, scale,
+          rows, Cn);
       SEGK_LAUNCHED(ctx, "igemm split-K finish");
       return SEGK_OK;
     }
@@ -1603,8 +1623,16 @@ int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw,
   p.dw_tap_stride = Cout * Cin; p.dw_row_stride = Cin; p.dw_col_stride = 1;
   p.dw = dw;
   p.direct = (!accumulate && p.splits == 1 && p.n_rb % 2 == 0) ? 1 : 0;
-  if (!accumulate && !p.direct) {
-    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * k * Cin * Cout, st);
+  const size_t n_dw = (size_t)k * k * Cin * Cout;
+  const bool partials = !p.direct && n_dw % 4 == 0 && sizeof(float) * n_dw * p.splits <= ((size_t)1 << 30);
+  if (partials) {
+    rc = segk_ws4(ctx, sizeof(float) * n_dw * p.splits);
+    if (rc) return rc;
+    p.dw = (float*)ctx->ws4;
+    p.part_stride = (int64_t)n_dw;
+    p.direct = 1;
+  } else if (!accumulate && !p.direct) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * n_dw, st);
     if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "deconv2d_wgrad memset: %s", cudaGetErrorString(e));
   }
   TapTable taps;
@@ -1612,10 +1640,13 @@ int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw,
   const int total = p.splits * p.n_rbp * p.n_tiles;
   const int grid = total < ctx->sm_count ? total : ctx->sm_count;
   switch (block_n) {
-    case 256: return launch_wgrad_t<256>(ctx, maps, p, taps, grid, st);
-    case 128: return launch_wgrad_t<128>(ctx, maps, p, taps, grid, st);
-    default: return launch_wgrad_t<64>(ctx, maps, p, taps, grid, st);
+    case 256: rc = launch_wgrad_t<256>(ctx, maps, p, taps, grid, st); break;
+    case 128: rc = launch_wgrad_t<128>(ctx, maps, p, taps, grid, st); break;
+    default: rc = launch_wgrad_t<64>(ctx, maps, p, taps, grid, st); break;
   }
+  if (rc) return rc;
+  if (partials) return segk_reduce_partials(ctx, (const float*)ctx->ws4, dw, n_dw, p.splits, accumulate, st);
+  return SEGK_OK;
 }
 
 int segk_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* bias, const void* residual, void* y,
@@ -1684,8 +1715,18 @@ int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, i
   p.dw_tap_stride = Cin * Cout; p.dw_row_stride = Cout; p.dw_col_stride = 1;
   p.dw = dw;
   p.direct = (!accumulate && p.splits == 1) ? 1 : 0;
-  if (!accumulate && !p.direct) {
-    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)kh * kw * Cin * Cout, st);
+  // several splits (or accumulate): every split stores its partial sums into its own buffer and an
+  // ordered reduction adds them up -- deterministic, and far cheaper than scattered fp32 atomics
+  const size_t n_dw = (size_t)kh * kw * Cin * Cout;
+  const bool partials = !p.direct && n_dw % 4 == 0 && sizeof(float) * n_dw * p.splits <= ((size_t)1 << 30);
+  if (partials) {
+    rc = segk_ws4(ctx, sizeof(float) * n_dw * p.splits);
+    if (rc) return rc;
+    p.dw = (float*)ctx->ws4;
+    p.part_stride = (int64_t)n_dw;
+    p.direct = 1;
+  } else if (!accumulate && !p.direct) {
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * n_dw, st);
     if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "conv2d_wgrad memset: %s", cudaGetErrorString(e));
   }
   TapTable taps;
@@ -1693,10 +1734,13 @@ int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, i
   const int total = p.splits * p.n_rbp * p.n_tiles;
   const int grid = total < ctx->sm_count ? total : ctx->sm_count;
   switch (block_n) {
-    case 256: return launch_wgrad_t<256>(ctx, maps, p, taps, grid, st);
-    case 128: return launch_wgrad_t<128>(ctx, maps, p, taps, grid, st);
-    default: return launch_wgrad_t<64>(ctx, maps, p, taps, grid, st);
+    case 256: rc = launch_wgrad_t<256>(ctx, maps, p, taps, grid, st); break;
+    case 128: rc = launch_wgrad_t<128>(ctx, maps, p, taps, grid, st); break;
+    default: rc = launch_wgrad_t<64>(ctx, maps, p, taps, grid, st); break;
   }
+  if (rc) return rc;
+  if (partials) return segk_reduce_partials(ctx, (const float*)ctx->ws4, dw, n_dw, p.splits, accumulate, st);
+  return SEGK_OK;
 }
 
 }  // extern "C"

@@ -243,7 +243,9 @@ int launch(segk_ctx* ctx, const WsMaps& maps, const WsParams& p, int grid, cudaS
   return SEGK_OK;
 }
 
-int ensure_ws4(segk_ctx* ctx, size_t bytes) {
+}  // namespace
+
+int segk_ws4(segk_ctx* ctx, size_t bytes) {
   if (ctx->ws4_bytes >= bytes) return SEGK_OK;
   if (ctx->ws4) cudaFree(ctx->ws4);       // (synchronises the device: nothing still reads the old buffer)
   ctx->ws4 = nullptr;
@@ -253,7 +255,12 @@ int ensure_ws4(segk_ctx* ctx, size_t bytes) {
   return SEGK_OK;
 }
 
-}  // namespace
+int segk_reduce_partials(segk_ctx* ctx, const float* part, float* dw, size_t n, int splits, int accumulate, cudaStream_t st) {
+  const int n4 = (int)(n / 4);
+  wslab_reduce_kernel<<<ceil_div(n4, 256), 256, 0, st>>>((const float4*)part, (float4*)dw, n4, splits, accumulate);
+  SEGK_LAUNCHED(ctx, "wgrad partial-sum reduce");
+  return SEGK_OK;
+}
 
 // -> 1 handled, 0 not applicable (caller uses the tap-wise kernel), < 0 error
 int segk_wslab_try(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int kh,
@@ -316,7 +323,7 @@ int segk_wslab_try(segk_ctx* ctx, const void* x, const void* dy, float* dw, int 
   if (direct) {
     p.out = dw;
   } else {
-    rc = ensure_ws4(ctx, sizeof(float) * n * p.splits);
+    rc = segk_ws4(ctx, sizeof(float) * n * p.splits);
     if (rc) return rc;
     p.out = (float*)ctx->ws4;
   }
@@ -327,9 +334,8 @@ int segk_wslab_try(segk_ctx* ctx, const void* x, const void* dy, float* dw, int 
   else rc = launch<64, 2>(ctx, maps, p, grid, st);
   if (rc) return rc;
   if (!direct) {
-    const int n4 = (int)(n / 4);
-    wslab_reduce_kernel<<<ceil_div(n4, 256), 256, 0, st>>>((const float4*)p.out, (float4*)dw, n4, p.splits, accumulate);
-    SEGK_LAUNCHED(ctx, "wslab reduce");
+    rc = segk_reduce_partials(ctx, p.out, dw, n, p.splits, accumulate, st);
+    if (rc) return rc;
   }
   return 1;
 }
