@@ -734,7 +734,7 @@ slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
     for (int i = 0; i < kSlab3Stages; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }   // one epilogue group per accumulator
     mbar_init(wfull, 1);
     fence_barrier_init();
   }
@@ -798,14 +798,18 @@ slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
+    // Two epilogue groups of four warps (one per TMEM lane quarter); group g owns accumulator g, i.e.
+    // every other tile of this CTA.  The epilogue of a tile is a long dependent chain (three TMEM loads at
+    // 64 B/clk, two shuffles per value, bias / mask / pack, staging, TMA store: ~2900 cycles measured with
+    // all eight warps on one tile) against 1152 tensor cycles of MMAs; with the groups on alternate tiles
+    // one group's TMEM reads run under the other's arithmetic and stores.
     const int q = warp & 3;       // TMEM lane quarter == image row of the tile
-    const int half = (warp - 2) >> 2;   // which 32 of the 64 output columns
-    int acc = 0;
+    const int grp = (warp - 2) >> 2;
     uint32_t acc_phase = 0;
-    const bool ep_leader = (threadIdx.x == 64);
+    const bool ep_leader = (threadIdx.x == 64 + grp * 128);
     const int srow = q * kSlabWV + lane;
-    uint32_t sg = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    uint8_t* sbuf = smem_out + grp * kStageOutBytes;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x) {
       int r = tile / p.n_tiles;
       const int x0 = (r % p.tiles_w) * kSlabWV;
       r /= p.tiles_w;
@@ -814,16 +818,15 @@ slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
       const int ox = x0 + lane, oy = y0 + q;
       const bool valid = lane < kSlabWV && ox < p.W && oy < p.H;
       const int64_t obase = (((int64_t)n * p.H + oy) * p.W + ox) * p.ldo + (int64_t)nt * 64;
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      mbar_wait(&tfull_bar[grp], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      {
-        const int c0 = half * 32;
-        uint8_t* sbuf = smem_out + (sg & 1) * kStageOutBytes;
-        if (p.tma_store) {
-          if (ep_leader) tma_store_wait_read<1>();
-          named_bar_sync(1, kEpiThreads);
-        }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 256);
+      if (p.tma_store) {
+        if (ep_leader) tma_store_wait_read<0>();     // this group's previous store has read the staging buffer
+        named_bar_sync(1 + grp, 128);
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < 64; c0 += 32) {
         float4 bv[8];
         if (p.bias) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + nt * 64 + c0);
@@ -888,7 +891,7 @@ slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           } else if (p.tma_store) {
-            const int pbase = half * 4;
+            const int pbase = c0 ? 4 : 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               *reinterpret_cast<uint4*>(sbuf + srow * 128 + (((pbase + i) ^ (srow & 7)) << 4)) =
@@ -902,20 +905,19 @@ slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
                                  pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
           }
         }
-        if (p.tma_store) {
-          fence_proxy_async();
-          named_bar_sync(1, kEpiThreads);
-          if (ep_leader) {
-            tma_store_4d(&maps.c, sbuf, nt * 64, x0, y0, n);
-            tma_store_commit();
-          }
-          ++sg;
+      }
+      // the accumulator is in registers / staging now: hand it back to the MMA warp before the store
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[grp]);
+      acc_phase ^= 1;
+      if (p.tma_store) {
+        fence_proxy_async();
+        named_bar_sync(1 + grp, 128);
+        if (ep_leader) {
+          tma_store_4d(&maps.c, sbuf, nt * 64, x0, y0, n);
+          tma_store_commit();
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
     }
     if (p.tma_store && ep_leader) tma_store_wait_read<0>();
   }
@@ -1322,10 +1324,10 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
               const void* mask, float scale, int relu, int out_f32, void* y, int N, int H, int W, int Ck, int Cn,
               void* stream) {
   // Ck = 64: kx-fused N = 192 MMAs on resident weights (slab3_kernel), 64-channel output tiles.  Measured
-  // (tools/time_n64.py): wins for the plain forward of 64 -> 64 (264 vs 296 us at B=32 160x576), loses where
-  // the epilogue carries a ReLU mask (dgrad) or there are two channel tiles; slab3 = 2 forces it.
-  const bool fused3 = Ck == 64 && (Cn / 64) <= ctx->sm_count &&
-                      (ctx->slab3 == 2 || (ctx->slab3 == 1 && Cn == 64 && mask == nullptr));
+  // (tools/time_n64.py, B=32 160x576): 64 -> 64 forward 228 vs 297 us, its dgrad 345 vs 372 us; with two
+  // channel tiles (64 -> 128) it is a wash (116 vs 112 us), so the tap-wise slab keeps those.  slab3 = 2 forces it.
+  const bool fused3 = Ck == 64 && (Cn / 64) <= ctx->sm_count && (ctx->slab3 == 2 || (ctx->slab3 == 1 && Cn == 64));
+  (void)mask;
   const int block_n = fused3 ? 64 : pick_block_n(ctx, Cn);
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));

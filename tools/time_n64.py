@@ -33,7 +33,7 @@ def case(N, H, W, ci, co):
     dx = torch.empty_like(x)
     dw = torch.empty_like(w)
     out = {}
-    for s3 in (1, 0):
+    for s3 in (2, 1, 0):
         ops.ctx.set_tuning("slab3", s3)
         out[f"fwd s3={s3}"] = timeit(lambda: ops.conv2d_fwd(x, wk, b, y, 3, 3, relu=True))
         out[f"dgrad s3={s3}"] = timeit(lambda: ops.conv2d_dgrad(dy, wd, dx, 3, 3, relu_mask=x))
