@@ -179,10 +179,11 @@ int segk_scale_columns(segk_ctx* ctx, const float* in, const float* scale, float
                        int64_t rows, int C, void* stream);
 /* dgamma[c] = sum_r dz[r][c] * (y[r][c] - beta[c]) / gamma[c]  (dz, y bf16 [rows][C]; dz already
  * carries the ReLU mask, so (y - beta)/gamma' is the raw conv output wherever dz != 0).
- * workspace: >= 4 * C * min(rows/4+1, 4*SMs) bytes (8 MB always suffices for C <= 4096). */
+ * dbeta (nullable): also dbeta[c] = sum_r dz[r][c] (the BiasAddGrad of the same dz) from the same pass.
+ * workspace: >= 8 * C * min(rows/4+1, 4*SMs) bytes (8 MB always suffices for C <= 4096). */
 int segk_bn_gamma_grad(segk_ctx* ctx, const void* dz, const void* y, const float* beta,
-                       const float* gamma, float* dgamma, void* workspace, size_t workspace_bytes,
-                       int64_t rows, int C, void* stream);
+                       const float* gamma, float* dgamma, float* dbeta, void* workspace,
+                       size_t workspace_bytes, int64_t rows, int C, void* stream);
 /* Concat (utils.py:332) and its gradient: dst[r][coff_dst + c] (=, or += when accumulate)
  * src[r][coff_src + c] for c < C, zeroed where mask[r][c] <= 0 (mask dense [rows][C] or NULL =
  * the fused ReluGrad of the producer).  bf16, all channel counts multiples of 8. */

@@ -146,20 +146,22 @@ __global__ void __launch_bounds__(kThreads) scale_columns_kernel(const float* __
     out[i] = in[i] * __ldg(scale + (int)(i % C)) * mult;
 }
 
-// partial[b][c]      = sum over the block's rows of dz[r][c] * (y[r][c] - beta[c])
-// (fixed-order second stage: bn_gamma_finish_kernel divides by gamma)
+// partial[b][0][c] = sum over the block's rows of dz[r][c] * (y[r][c] - beta[c])
+// partial[b][1][c] = sum over the block's rows of dz[r][c]            (BiasAddGrad = d beta, when kBeta)
+// (fixed-order second stage: bn_gamma_finish_kernel divides the first by gamma)
+template <bool kBeta>
 __global__ void __launch_bounds__(kThreads) bn_gamma_partial_kernel(const uint4* __restrict__ dz,
                                                                     const uint4* __restrict__ y,
                                                                     const float* __restrict__ beta,
                                                                     float* __restrict__ partial, int64_t rows, int C8) {
-  __shared__ float sh[kThreads][9];
+  __shared__ float sh[kThreads][kBeta ? 17 : 9];
   const int cpb = C8 < kThreads ? C8 : kThreads;
   const int R = kThreads / cpb;
   const int cg = blockIdx.y * cpb + (threadIdx.x % cpb);
   const int rl = threadIdx.x / cpb;
-  float acc[8], b[8];
+  float acc[8], sum[8], b[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { acc[j] = 0.f; b[j] = (cg < C8) ? __ldg(beta + cg * 8 + j) : 0.f; }
+  for (int j = 0; j < 8; ++j) { acc[j] = 0.f; sum[j] = 0.f; b[j] = (cg < C8) ? __ldg(beta + cg * 8 + j) : 0.f; }
   if (cg < C8 && rl < R) {
     for (int64_t r = (int64_t)blockIdx.x * R + rl; r < rows; r += (int64_t)gridDim.x * R) {
       const uint4 g = __ldg(dz + r * C8 + cg), v = __ldg(y + r * C8 + cg);
@@ -168,30 +170,60 @@ __global__ void __launch_bounds__(kThreads) bn_gamma_partial_kernel(const uint4*
         const float2 gf = unpack_bf16x2((&g.x)[j]), vf = unpack_bf16x2((&v.x)[j]);
         acc[2 * j] += gf.x * (vf.x - b[2 * j]);
         acc[2 * j + 1] += gf.y * (vf.y - b[2 * j + 1]);
+        if (kBeta) { sum[2 * j] += gf.x; sum[2 * j + 1] += gf.y; }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = acc[j];
+  for (int j = 0; j < 8; ++j) {
+    sh[threadIdx.x][j] = acc[j];
+    if (kBeta) sh[threadIdx.x][8 + j] = sum[j];
+  }
   __syncthreads();
   if (rl == 0 && cg < C8) {
     for (int k = 1; k < R; ++k)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += sh[threadIdx.x + k * cpb][j];
-    float* out = partial + (int64_t)blockIdx.x * (C8 * 8) + cg * 8;
+      for (int j = 0; j < 8; ++j) {
+        acc[j] += sh[threadIdx.x + k * cpb][j];
+        if (kBeta) sum[j] += sh[threadIdx.x + k * cpb][8 + j];
+      }
+    const int C = C8 * 8;
+    float* out = partial + (int64_t)blockIdx.x * (kBeta ? 2 : 1) * C + cg * 8;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) out[j] = acc[j];
+    for (int j = 0; j < 8; ++j) {
+      out[j] = acc[j];
+      if (kBeta) out[C + j] = sum[j];
+    }
   }
 }
 
+// block = 32 channels x 8 lanes over the partial rows (a single thread per channel walking all the
+// partial rows was latency-bound: 118 us for a 24 MB layer)
 __global__ void __launch_bounds__(kThreads) bn_gamma_finish_kernel(const float* __restrict__ partial,
                                                                    const float* __restrict__ gamma,
-                                                                   float* __restrict__ dgamma, int nparts, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float a = 0.f;
-  for (int r = 0; r < nparts; ++r) a += partial[(int64_t)r * C + c];
-  dgamma[c] = a / gamma[c];
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                   int nparts, int C) {
+  __shared__ float sa[8][33], sb[8][33];
+  const int cx = threadIdx.x & 31, l8 = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  const int stride = dbeta ? 2 * C : C;
+  float a = 0.f, s = 0.f;
+  if (c < C) {
+#pragma unroll 4
+    for (int r = l8; r < nparts; r += 8) {
+      a += partial[(int64_t)r * stride + c];
+      if (dbeta) s += partial[(int64_t)r * stride + C + c];
+    }
+  }
+  sa[l8][cx] = a;
+  sb[l8][cx] = s;
+  __syncthreads();
+  if (l8 == 0 && c < C) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { a += sa[i][cx]; s += sb[i][cx]; }
+    dgamma[c] = a / gamma[c];
+    if (dbeta) dbeta[c] = s;
+  }
 }
 
 // dst[r][coff_dst + c] (= or +=) src[r][coff_src + c], optionally zeroed where mask[r][c] <= 0; 8 channels/thread
@@ -302,7 +334,8 @@ int segk_scale_columns(segk_ctx* ctx, const float* in, const float* scale, float
 }
 
 int segk_bn_gamma_grad(segk_ctx* ctx, const void* dz, const void* y, const float* beta, const float* gamma,
-                       float* dgamma, void* workspace, size_t workspace_bytes, int64_t rows, int C, void* stream) {
+                       float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes, int64_t rows, int C,
+                       void* stream) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, dz && y && beta && gamma && dgamma && workspace && rows > 0, "bn_gamma_grad: bad args");
   SEGK_REQUIRE(ctx, C % 8 == 0 && (C / 8 <= kThreads ? kThreads % (C / 8) == 0 : (C / 8) % kThreads == 0),
@@ -311,16 +344,22 @@ int segk_bn_gamma_grad(segk_ctx* ctx, const void* dz, const void* y, const float
   const int cpb = C8 < kThreads ? C8 : kThreads;
   const int R = kThreads / cpb, gy = C8 / cpb;
   int64_t gx = ceil_div64(rows, (int64_t)R * 4);
-  const int64_t cap = ceil_div64((int64_t)ctx->sm_count * 4, gy);
+  int64_t cap = ceil_div64((int64_t)ctx->sm_count * 4, gy);
+  const int64_t few = ceil_div64(rows, (int64_t)R * 16);      // >= 16 row steps per block: small layers get fewer partials
+  if (cap > few) cap = few;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
-  SEGK_REQUIRE(ctx, workspace_bytes >= sizeof(float) * (size_t)gx * C, "bn_gamma_grad: workspace too small (%zu < %zu)",
-               workspace_bytes, sizeof(float) * (size_t)gx * C);
+  const size_t need = sizeof(float) * (size_t)gx * C * (dbeta ? 2 : 1);
+  SEGK_REQUIRE(ctx, workspace_bytes >= need, "bn_gamma_grad: workspace too small (%zu < %zu)", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
-  bn_gamma_partial_kernel<<<dim3((unsigned)gx, gy), kThreads, 0, st>>>((const uint4*)dz, (const uint4*)y, beta,
-                                                                    (float*)workspace, rows, C8);
+  if (dbeta)
+    bn_gamma_partial_kernel<true><<<dim3((unsigned)gx, gy), kThreads, 0, st>>>((const uint4*)dz, (const uint4*)y, beta,
+                                                                            (float*)workspace, rows, C8);
+  else
+    bn_gamma_partial_kernel<false><<<dim3((unsigned)gx, gy), kThreads, 0, st>>>((const uint4*)dz, (const uint4*)y, beta,
+                                                                             (float*)workspace, rows, C8);
   SEGK_LAUNCHED(ctx, "bn_gamma_partial");
-  bn_gamma_finish_kernel<<<ceil_div(C, kThreads), kThreads, 0, st>>>((const float*)workspace, gamma, dgamma, (int)gx, C);
+  bn_gamma_finish_kernel<<<ceil_div(C, 32), kThreads, 0, st>>>((const float*)workspace, gamma, dgamma, dbeta, (int)gx, C);
   SEGK_LAUNCHED(ctx, "bn_gamma_finish");
   return SEGK_OK;
 }

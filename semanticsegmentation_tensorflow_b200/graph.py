@@ -208,7 +208,7 @@ class GraphNet:
         self._repack(self.ops)
         self._ran_forward = False
         self.side = SideStream(self.device, enabled=overlap)
-        self.wside = SideStream(self.device, enabled=False)      # (FCN runs its wgrad GEMMs on a second stream)
+        self.wside = SideStream(self.device, enabled=overlap)    # weight-gradient GEMMs beside the dgrad chain
 
     # ---- planning ---------------------------------------------------------------------------
     def _route(self, n, cin):
@@ -407,30 +407,40 @@ class GraphNet:
             dz = G
             if r == "small" and G.dtype == torch.float32:
                 dz = ops.cast_to_bf16(G, self.dlogits_bf16)
-            if n.bn:      # d(beta), d(gamma): HBM-bound column reductions off the critical path -> side stream
+            if n.bn:      # d(beta), d(gamma): one HBM-bound pass over dz and the activation, off the critical path
                 def bn_grads(dz=dz, n=n):
-                    ops.bias_grad(dz, V.grad(f"{n.bn_scope}/beta"))
                     ops.bn_gamma_grad(dz, self.act[n.name], V.param(f"{n.bn_scope}/beta"),
-                                      V.param(f"{n.bn_scope}/gamma"), V.grad(f"{n.bn_scope}/gamma"), self.bn_ws)
+                                      V.param(f"{n.bn_scope}/gamma"), V.grad(f"{n.bn_scope}/gamma"), self.bn_ws,
+                                      dbeta=V.grad(f"{n.bn_scope}/beta"))
                 self.side.run(bn_grads)
             elif n.bias and r != "first":      # the fused first-layer wgrad also produces the bias gradient
                 self.side.run(lambda dz=dz, n=n: ops.bias_grad(dz, V.grad(f"{n.name}/biases")))
-            # weight gradient (of the folded weights; unfold the BN scale afterwards)
+            # weight gradient (of the folded weights; unfold the BN scale afterwards).  Tensor-core ones go to
+            # the wgrad stream, ordered after this point, launched behind the layer's dgrad
+            wjob, wmark = None, None
+
+            def unfold(gw=gw, n=n):
+                if n.bn:
+                    ops.scale_columns(gw, V.param(f"{n.bn_scope}/gamma"), BN_SCALE, gw)
+
             if n.kind == "deconv":
-                ops.deconv2d_wgrad(x, dz, gw, n.k, n.stride)
+                wjob = lambda x=x, dz=dz, gw=gw, n=n, unfold=unfold: (ops.deconv2d_wgrad(x, dz, gw, n.k, n.stride), unfold())
             elif r == "tc":
-                ops.conv2d_wgrad(x, dz, gw, n.k, n.k)
+                wjob = lambda x=x, dz=dz, gw=gw, n=n, unfold=unfold: (ops.conv2d_wgrad(x, dz, gw, n.k, n.k), unfold())
             elif r == "first":
                 ops.conv2d_first_wgrad(x, dz, gw, n.k, n.k,
                                        dbias=V.grad(f"{n.name}/biases") if (n.bias and not n.bn) else None)
+                unfold()
             elif r == "im2col":
                 tmp = ops.conv2d_wgrad(self.patch[n.name], dz, self.tmp[n.name], 1, 1,
                                        flops=conv_flops(self.N, dz.shape[1], dz.shape[2], x.shape[3], n.cout, n.k, n.k))
                 gw.view(-1).copy_(tmp.view(-1)[:gw.numel()])
+                unfold()
             else:
                 ops.conv2d_small_wgrad(x, dz, gw)
-            if n.bn:
-                ops.scale_columns(gw, V.param(f"{n.bn_scope}/gamma"), BN_SCALE, gw)
+                unfold()
+            if wjob is not None:
+                wmark = self.wside.mark()
             # input gradient
             if t != "input":
                 mask = self._relu_mask_of(t)
@@ -449,6 +459,8 @@ class GraphNet:
                 else:
                     raise NotImplementedError("im2col route is for the first layer only")
                 has[t] = True
+            if wjob is not None:
+                self.wside.run(wjob, after=wmark)
             if after_layer is not None:
                 after_layer(n.name)
 

@@ -306,10 +306,10 @@ class Ops:
         self.call("segk_scale_columns", _p(w), _p(scale), float(mult), _p(out), w.numel() // c, c, _stream())
         return out
 
-    def bn_gamma_grad(self, dz, y, beta, gamma, dgamma, workspace):
+    def bn_gamma_grad(self, dz, y, beta, gamma, dgamma, workspace, dbeta=None):
         c = dz.shape[-1]
         self._w(4.0 * dz.numel(), "byte")
-        self.call("segk_bn_gamma_grad", _p(dz), _p(y), _p(beta), _p(gamma), _p(dgamma), _p(workspace),
+        self.call("segk_bn_gamma_grad", _p(dz), _p(y), _p(beta), _p(gamma), _p(dgamma), _p(dbeta), _p(workspace),
                   workspace.numel() * workspace.element_size(), dz.numel() // c, c, _stream())
         return dgamma
 

@@ -57,6 +57,14 @@ def test_bn_affine_helpers(ops, cuda_device):
     torch.cuda.synchronize()
     ref = (dz.astype(np.float64) * (y - beta)).sum(0) / gamma
     np.testing.assert_allclose(host(dg), ref, rtol=1e-3, atol=1e-2)
+    # d(beta) = BiasAddGrad of the same dz out of the same pass
+    dg2 = torch.empty_like(dg)
+    db = torch.empty(128, dtype=torch.float32, device=cuda_device)
+    ops.bn_gamma_grad(dev_bf16(dz, cuda_device), dev_bf16(y, cuda_device), dev_f32(beta, cuda_device),
+                      dev_f32(gamma, cuda_device), dg2, ws, dbeta=db)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(host(dg2), ref, rtol=1e-3, atol=1e-2)
+    np.testing.assert_allclose(host(db), dz.astype(np.float64).sum(0), rtol=1e-3, atol=1e-2)
 
 
 def test_maxpool_bwd_with_second_gradient_path(ops, cuda_device):
