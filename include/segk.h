@@ -36,7 +36,14 @@ enum {
 
 typedef struct segk_ctx segk_ctx;
 
-/* ---- context ---------------------------------------------------------------------- */
+/* ---- context ----------------------------------------------------------------------
+ * One context per device.  All work is enqueued on the caller's stream.  A context owns a few grow-only
+ * device scratch buffers; calls that share one must not overlap on DIFFERENT streams:
+ *   - segk_conv2d_wgrad / segk_deconv2d_wgrad (per-split partial sums)            -> one stream
+ *   - split-K segk_conv2d_fwd / _dgrad and segk_conv2d_first_wgrad                -> one stream
+ *   - segk_bias_grad                                                              -> one stream
+ *   - segk_conv2d_small_wgrad                                                     -> one stream
+ * (fcn.py: wgrad stream / main stream / side stream / main stream).  Use one context per stream otherwise. */
 int segk_abi_version(void);
 int segk_create(int device, segk_ctx** out);
 int segk_destroy(segk_ctx* ctx);
@@ -44,9 +51,11 @@ const char* segk_last_error(segk_ctx* ctx);
 /* number of kernels launched through this ctx since creation (bench.py gpu_launches) */
 int64_t segk_launch_count(segk_ctx* ctx);
 int segk_sm_count(segk_ctx* ctx);
-/* Tuning overrides (also read once at segk_create from SEGK_SLAB / SEGK_FORCE_BN / SEGK_FORCE_KSPLIT /
- * SEGK_FORCE_WSPLIT): key in {"slab" (0 off, 1 auto, 2 wherever legal), "force_bn" (0|64|128|256),
- * "force_ksplit", "force_wsplit" (0 = heuristic)}.  Results are identical under every setting. */
+/* Kernel-selection overrides (also read once at segk_create from SEGK_SLAB / SEGK_SLAB3 / SEGK_WSLAB /
+ * SEGK_TMA_STORE / SEGK_FORCE_BN / SEGK_FORCE_KSPLIT / SEGK_FORCE_WSPLIT): key in {"slab", "slab3",
+ * "wslab" (0 off, 1 auto, 2 wherever legal), "tma_store" (0|1), "force_bn" (0|64|128|256),
+ * "force_ksplit", "force_wsplit" (0 = heuristic)}.  Every setting computes the same sums (fp32
+ * accumulation order differs between kernels). */
 int segk_set_tuning(segk_ctx* ctx, const char* key, int value);
 
 /* ---- epilogue flags for the conv family ------------------------------------------------ */

@@ -372,7 +372,11 @@ class FCN:
                 elif l.path == "patch":
                     Pg = ops.deconv_patch_gather(dcur, self.patch[l.name], l.k, l.stride)
                     dfl = deconv_flops(self.N, xin.shape[1], xin.shape[2], l.cin, l.cout, l.k, l.stride)
-                    ops.conv2d_wgrad(Pg, xin, gw.view(1, 1, l.k * l.k * l.cout, l.cin), 1, 1, flops=dfl)
+                    # (every tensor-core wgrad runs on the wgrad stream: they share one partial-sum scratch)
+                    wjob = lambda Pg=Pg, x=xin, g=gw, l=l, dfl=dfl: ops.conv2d_wgrad(
+                        Pg, x, g.view(1, 1, l.k * l.k * l.cout, l.cin), 1, 1, flops=dfl)
+                    wmark = self.wside.mark()
+                    wreads = ()
                 else:
                     ops.deconv2d_small_wgrad(xin, dcur, gw, l.stride)
                 # gradient wrt the deconv input
@@ -403,9 +407,12 @@ class FCN:
                 elif l.path == "im2col":
                     if i != 0:
                         raise NotImplementedError("im2col route is for the first layer only (no input gradient)")
-                    tmp = ops.conv2d_wgrad(self.patch[l.name], dcur, self.patch_f32[l.name], 1, 1,
-                                           flops=conv_flops(self.N, dcur.shape[1], dcur.shape[2], l.cin, l.cout, l.k, l.k))
-                    gw.view(-1).copy_(tmp.view(-1)[:gw.numel()])      # rows >= K are the zero padding
+                    def im2col_wgrad(P=self.patch[l.name], d=dcur, t=self.patch_f32[l.name], g=gw, l=l):
+                        tmp = ops.conv2d_wgrad(P, d, t, 1, 1,
+                                               flops=conv_flops(self.N, d.shape[1], d.shape[2], l.cin, l.cout, l.k, l.k))
+                        g.view(-1).copy_(tmp.view(-1)[:g.numel()])      # rows >= K are the zero padding
+                    wjob = im2col_wgrad
+                    wmark = self.wside.mark()
                 else:
                     ops.conv2d_small_wgrad(xin, dcur, gw)
                 dnext = dcur

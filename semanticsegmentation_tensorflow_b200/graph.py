@@ -432,10 +432,12 @@ class GraphNet:
                                        dbias=V.grad(f"{n.name}/biases") if (n.bias and not n.bn) else None)
                 unfold()
             elif r == "im2col":
-                tmp = ops.conv2d_wgrad(self.patch[n.name], dz, self.tmp[n.name], 1, 1,
-                                       flops=conv_flops(self.N, dz.shape[1], dz.shape[2], x.shape[3], n.cout, n.k, n.k))
-                gw.view(-1).copy_(tmp.view(-1)[:gw.numel()])
-                unfold()
+                def im2col_wgrad(P=self.patch[n.name], dz=dz, t=self.tmp[n.name], gw=gw, n=n, cin=x.shape[3], unfold=unfold):
+                    tmp = ops.conv2d_wgrad(P, dz, t, 1, 1,
+                                           flops=conv_flops(self.N, dz.shape[1], dz.shape[2], cin, n.cout, n.k, n.k))
+                    gw.view(-1).copy_(tmp.view(-1)[:gw.numel()])
+                    unfold()
+                wjob = im2col_wgrad      # (every tensor-core wgrad on one stream: they share a partial-sum scratch)
             else:
                 ops.conv2d_small_wgrad(x, dz, gw)
                 unfold()
