@@ -171,6 +171,74 @@ __device__ __forceinline__ uint64_t tap_mask(const IgemmParams& p, const TapTabl
   return m;
 }
 
+// Shared tail of every conv epilogue: v = the fp32 accumulators of 32 consecutive output channels of one
+// output pixel (element offset `off` into the output / residual / mask tensors), bv = their bias.
+// bias -> residual (skip-add / AddN) -> ReLU -> ReLU mask of the producer -> scale, then the store: fp32,
+// bf16 into the swizzled staging row of a TMA store (16-byte pieces pbase..pbase+3 of row `srow`), or
+// bf16 straight to global memory.  P = IgemmParams or SlabParams.
+template <class P>
+__device__ __forceinline__ void epilogue_apply_store(const P& p, float (&v)[32], const float4 (&bv)[8], int64_t off,
+                                                     uint8_t* sbuf, int srow, int pbase) {
+  if (p.bias) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w;
+    }
+  }
+  if (p.residual) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = __ldg(r4 + i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&u.x)[j]);
+        v[8 * i + 2 * j] += f.x;
+        v[8 * i + 2 * j + 1] += f.y;
+      }
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (p.mask) {
+    const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = __ldg(m4 + i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&u.x)[j]);
+        if (!(f.x > 0.f)) v[8 * i + 2 * j] = 0.f;
+        if (!(f.y > 0.f)) v[8 * i + 2 * j + 1] = 0.f;
+      }
+    }
+  }
+  if (p.scale != 1.f) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+  }
+  if (p.out_f32) {
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else if (p.tma_store) {
+    // staging row = box-linear pixel index, 128 B per row, 16-byte pieces XOR-swizzled by row & 7
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<uint4*>(sbuf + srow * 128 + (((pbase + i) ^ (srow & 7)) << 4)) =
+          make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                     pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+  } else {
+    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      o4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                         pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+  }
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const TapTable taps) {
@@ -323,65 +391,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w;
-            }
-          }
-          if (p.residual) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 u = __ldg(r4 + i);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2((&u.x)[j]);
-                v[8 * i + 2 * j] += f.x;
-                v[8 * i + 2 * j + 1] += f.y;
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (p.mask) {
-            const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 u = __ldg(m4 + i);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2((&u.x)[j]);
-                if (!(f.x > 0.f)) v[8 * i + 2 * j] = 0.f;
-                if (!(f.y > 0.f)) v[8 * i + 2 * j + 1] = 0.f;
-              }
-            }
-          }
-          if (p.scale != 1.f) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= p.scale;
-          }
-          if (p.out_f32) {
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else if (p.tma_store) {
-            // staging row = box-linear pixel index, 128 B per row, 16-byte pieces XOR-swizzled by row & 7
-            const int pbase = half * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<uint4*>(sbuf + row * 128 + (((pbase + i) ^ (row & 7)) << 4)) =
-                  make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                             pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-          } else {
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              o4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                 pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-          }
+          epilogue_apply_store(p, v, bv, obase + c0, sbuf, row, half * 4);
         }
         if (p.tma_store) {
           fence_proxy_async();                        // generic-proxy smem writes -> visible to the TMA engine
@@ -610,64 +620,7 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w;
-            }
-          }
-          if (p.residual) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 u = __ldg(r4 + i);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2((&u.x)[j]);
-                v[8 * i + 2 * j] += f.x;
-                v[8 * i + 2 * j + 1] += f.y;
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (p.mask) {
-            const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 u = __ldg(m4 + i);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2((&u.x)[j]);
-                if (!(f.x > 0.f)) v[8 * i + 2 * j] = 0.f;
-                if (!(f.y > 0.f)) v[8 * i + 2 * j + 1] = 0.f;
-              }
-            }
-          }
-          if (p.scale != 1.f) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= p.scale;
-          }
-          if (p.out_f32) {
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else if (p.tma_store) {
-            const int pbase = half * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<uint4*>(sbuf + srow * 128 + (((pbase + i) ^ (srow & 7)) << 4)) =
-                  make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                             pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-          } else {
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              o4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                 pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-          }
+          epilogue_apply_store(p, v, bv, obase + c0, sbuf, srow, half * 4);
         }
         if (p.tma_store) {
           fence_proxy_async();
@@ -845,66 +798,7 @@ slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
             v[i] = __uint_as_float(r0[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(r1[i]), 1) +
                    __shfl_down_sync(0xffffffffu, __uint_as_float(r2[i]), 2);
         }
-        if (valid) {
-          if (p.bias) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[4 * i] += bv[i].x; v[4 * i + 1] += bv[i].y; v[4 * i + 2] += bv[i].z; v[4 * i + 3] += bv[i].w;
-            }
-          }
-          if (p.residual) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 u = __ldg(r4 + i);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2((&u.x)[j]);
-                v[8 * i + 2 * j] += f.x;
-                v[8 * i + 2 * j + 1] += f.y;
-              }
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (p.mask) {
-            const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 u = __ldg(m4 + i);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2((&u.x)[j]);
-                if (!(f.x > 0.f)) v[8 * i + 2 * j] = 0.f;
-                if (!(f.y > 0.f)) v[8 * i + 2 * j + 1] = 0.f;
-              }
-            }
-          }
-          if (p.scale != 1.f) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= p.scale;
-          }
-          if (p.out_f32) {
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else if (p.tma_store) {
-            const int pbase = c0 ? 4 : 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              *reinterpret_cast<uint4*>(sbuf + srow * 128 + (((pbase + i) ^ (srow & 7)) << 4)) =
-                  make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                             pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-          } else {
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + obase + c0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              o4[i] = make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                                 pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
-          }
-        }
+        if (valid) epilogue_apply_store(p, v, bv, obase + c0, sbuf, srow, c0 ? 4 : 0);
       }
       // the accumulator is in registers / staging now: hand it back to the MMA warp before the store
       tc_fence_before();
