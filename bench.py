@@ -285,7 +285,7 @@ def run_gpu(args):
         peak, unit, bound = peaks["hbm_gbs"], "GB/s", "hbm"
     roofline = {"bound": bound, "kernel": dom, "achieved": achieved, "peak": peak, "unit": unit,
                 "frac": achieved / peak, "traffic": traffic,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/ncu_traffic.json)" if traffic else None,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, average over the entry point's launches of one step under ncu (profiles/ncu_traffic.json, r1d_ncu_step_tc_launches.md)" if traffic else None,
                 "ncu_tensor_pipe_active_pct": ncu.get("tensor_pipe_active_pct"),
                 "peak_source": peaks["source"] + (" sustained" if bound == "tensor" else ""),
                 "algorithmic_per_launch": d["work"] / d["launches"], "algorithmic_unit": d["unit"],
