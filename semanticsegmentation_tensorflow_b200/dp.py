@@ -47,6 +47,11 @@ class BucketedAllReduce:
             w = None
         self._works.append((lo, hi, w))
 
+    def fires_at(self, name: str) -> bool:
+        """Does reporting `name` launch a bucket?  (Lets the caller order the launch after the side
+        streams only when a collective is actually issued.)"""
+        return self._next < len(self.buckets) and self.buckets[self._next][2] == name
+
     def layer_done(self, name: str):
         """Called by FCN.backward after each layer's dW/db kernels are enqueued.  Returns the buckets
         whose all-reduce was launched by this call as (lo, hi, work) tuples."""

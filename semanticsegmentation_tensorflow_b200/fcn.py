@@ -516,6 +516,11 @@ class TrainStep:
                 buckets = P.gradient_buckets(net.vars.slots)
             self.local = LocalBuckets(net, opt, buckets)
 
+    def _launch_stream(self, net):
+        if getattr(self, "_ls", None) is None:
+            self._ls = torch.cuda.Stream(net.device)
+        return self._ls
+
     def _finalize_stream(self, net):
         if getattr(self, "_fin", None) is None:
             self._fin = SideStream(net.device, enabled=net.side.stream is not None)
@@ -560,10 +565,23 @@ class TrainStep:
                 fin.run(go)
 
             def layer_done(name):
-                net.side.join()                   # this layer's bias gradients are part of the reduced arena
-                net.wside.join()                  # ... and so are its weight gradients
-                for lo, hi, work in self.allreduce.layer_done(name):
-                    finalize(lo, hi, work)
+                if not self.allreduce.fires_at(name):
+                    return
+                # The bucket's gradients come from three streams (dgrad chain, bias gradients, weight
+                # gradients).  The collective is issued from a launch stream that waits for all three, so
+                # the main stream never blocks on the wgrad stream and backward keeps its overlap.
+                if net.side.enabled:
+                    ls = self._launch_stream(net)
+                    ls.wait_stream(torch.cuda.current_stream())
+                    ls.wait_stream(net.side.stream)
+                    if net.wside.enabled:
+                        ls.wait_stream(net.wside.stream)
+                    with torch.cuda.stream(ls):
+                        for lo, hi, work in self.allreduce.layer_done(name):
+                            finalize(lo, hi, work)
+                else:
+                    for lo, hi, work in self.allreduce.layer_done(name):
+                        finalize(lo, hi, work)
 
             net.backward(after_layer=layer_done)
             net.side.join()
