@@ -300,3 +300,58 @@ def _slab_forced_body(ops, cuda_device):
     ops.conv2d_fwd(dev_bf16(x, cuda_device), wk, dev_f32(b, cuda_device), y, k, k, relu=True)
     torch.cuda.synchronize()
     assert_close(host(y), ref, TOL_BF16, "slab forced BN=256")
+
+
+def _guarded(shape, dtype, device, pad=4096):
+    """A tensor view in the middle of a larger byte buffer filled with 0xA5: (view, check) where check()
+    asserts that the guard bytes before and after the view are untouched."""
+    n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+    raw = torch.full((pad + n + pad,), 0xA5, dtype=torch.uint8, device=device)
+    view = raw[pad:pad + n].view(dtype).view(shape)
+
+    def check(what):
+        torch.cuda.synchronize()
+        assert bool((raw[:pad] == 0xA5).all()) and bool((raw[pad + n:] == 0xA5).all()), f"{what}: wrote outside its output"
+
+    return view, check
+
+
+@pytest.mark.parametrize("shape", [(3, 10, 37, 64, 64), (2, 12, 70, 64, 128), (1, 9, 45, 128, 128), (2, 8, 33, 64, 64)])
+def test_slab_kernels_stay_inside_their_outputs(ops, cuda_device, shape):
+    """Ragged maps through the TMA-store epilogues (slab / slab3), the slab wgrad and the fused first
+    layer, with guard bytes around every output (compute-sanitizer is not available on the GPU pool)."""
+    n, h, w, ci, co = shape
+    k = 3
+    x, wt, b = _conv_case((n, h, w, ci, co, k), 50)
+    wk, wd = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    xd, bd = dev_bf16(x, cuda_device), dev_f32(b, cuda_device)
+    dy = dev_bf16(bf16_grid(np.random.default_rng(51).standard_normal((n, h, w, co))), cuda_device)
+    try:
+        ops.ctx.set_tuning("slab", 2)
+        ops.ctx.set_tuning("wslab", 2)
+        for s3 in (2, 0):
+            ops.ctx.set_tuning("slab3", s3)
+            y, chk = _guarded((n, h, w, co), torch.bfloat16, cuda_device)
+            ops.conv2d_fwd(xd, wk, bd, y, k, k, relu=True)          # (H % 4 != 0 goes through the igemm kernel)
+            chk(f"conv fwd slab3={s3}")
+            dx, chk = _guarded((n, h, w, ci), torch.bfloat16, cuda_device)
+            ops.conv2d_dgrad(dy, wd, dx, k, k, relu_mask=xd)
+            chk(f"conv dgrad slab3={s3}")
+        dw, chk = _guarded((k, k, ci, co), torch.float32, cuda_device)
+        ops.conv2d_wgrad(xd, dy, dw, k, k)
+        chk("slab wgrad")
+    finally:
+        ops.ctx.set_tuning("slab", 1)
+        ops.ctx.set_tuning("slab3", 1)
+        ops.ctx.set_tuning("wslab", 1)
+    img = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device=cuda_device)
+    wk1 = ops.pack_im2col_weights(dev_f32(_conv_case((1, 4, 4, 3, 64, 3), 52)[1], cuda_device))
+    y1, chk = _guarded((n, h, w, 64), torch.bfloat16, cuda_device)
+    ops.conv2d_first_fwd(img, wk1, None, y1, 3, 3, relu=True)
+    chk("first-layer fwd")
+    dw1, chk1 = _guarded((3, 3, 3, 64), torch.float32, cuda_device)
+    db1, chk2 = _guarded((64,), torch.float32, cuda_device)
+    dy1 = dev_bf16(bf16_grid(np.random.default_rng(53).standard_normal((n, h, w, 64))), cuda_device)
+    ops.conv2d_first_wgrad(img, dy1, dw1, 3, 3, dbias=db1)
+    chk1("first-layer wgrad")
+    chk2("first-layer bias grad")
