@@ -139,7 +139,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from semanticsegmentation_tensorflow_b200 import build_library
-    from semanticsegmentation_tensorflow_b200.dp import BucketedAllReduce, init_distributed
+    from semanticsegmentation_tensorflow_b200.dp import BucketedAllReduce, SymmetricAllReduce, init_distributed
     from semanticsegmentation_tensorflow_b200.fcn import FCN, AdamOptimizer
     from semanticsegmentation_tensorflow_b200.ops import Profile
 
@@ -170,7 +170,11 @@ def run_gpu(args):
         train_gflop = TRAIN_GFLOP_PER_IMAGE
         workload = "FCN-8s 2-class bf16 training (fwd+loss+bwd+Adam), batch 32 per GPU, 160x576x3 (BASELINE configs[1])"
         metric = METRIC
-    allreduce = BucketedAllReduce.for_net(net) if world > 1 else None
+    # gradient exchange: our NVLink kernel on a symmetric arena when the box offers symmetric memory, else NCCL
+    allreduce = None
+    if world > 1:
+        allreduce = SymmetricAllReduce.try_create(net) or BucketedAllReduce.for_net(net)
+    exchange = getattr(allreduce, "kind", "nccl") if allreduce is not None else None
     train_step = AdamOptimizer(1e-4).minimize(net, allreduce=allreduce)
     feed_dev = {net.image: dev_x, net.annotation: dev_y, net.keep_probability: KEEP_PROB}
 
@@ -316,7 +320,7 @@ def run_gpu(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload,
                    "global_batch": world * B, "batch_per_gpu": B, "keep_prob": KEEP_PROB,
-                   "parallelism": f"dp{world}", "init": "random N(0,0.01^2) (FCN.py:125)",
+                   "parallelism": f"dp{world}", "exchange": exchange, "init": "random N(0,0.01^2) (FCN.py:125)",
                    "l2": "working set (1.8 GiB activations + 2.2 GiB weights/optimizer state) >> 126 MB L2; no flush needed"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / steps,
                 "h2d_bytes_per_step": int(host_x.numel() + host_y.numel()), "d2h_bytes_per_step": 4},

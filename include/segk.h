@@ -291,6 +291,18 @@ int segk_cast_to_bf16(segk_ctx* ctx, const void* x, int x_dtype, void* y, int64_
 int segk_bias_grad(segk_ctx* ctx, const void* dy, int dy_is_f32, float* db, int64_t rows, int C,
                    void* stream);
 
+/* ---- gradient exchange over NVLink (data parallelism; replaces ncclAllReduce) ----------
+ * In-place SUM all-reduce of the fp32 elements [offset, offset + n) of a SYMMETRIC buffer (same layout on
+ * every rank; offset and n multiples of 4).  Rank r reduces the r-th 1/world share and broadcasts it:
+ *   multicast_ptr != NULL : NVLS -- multimem.ld_reduce / multimem.st through the NVSwitch multicast
+ *                           address of the buffer (the sum is formed inside the switch);
+ *   else                  : peer loads / stores; peer_ptrs = HOST array of `world` device addresses of
+ *                           the buffer on each rank (rank order), summed in rank order.
+ * Every rank must call it with the same (offset, n); the caller brackets the call with cross-rank
+ * barriers on the same stream (inputs complete on all ranks before; all shares stored after). */
+int segk_allreduce_f32(segk_ctx* ctx, void* multicast_ptr, const uint64_t* peer_ptrs, int64_t offset,
+                       int64_t n, int rank, int world, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

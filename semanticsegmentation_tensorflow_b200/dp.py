@@ -9,6 +9,8 @@ as soon as its last layer's weight gradient has been enqueued, and the optimizer
 that slice waits only on that bucket."""
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import List, Tuple
 
 import torch
@@ -76,6 +78,66 @@ class BucketedAllReduce:
             if w is not None:
                 w.wait()
             yield lo, hi
+
+
+class SymmetricAllReduce(BucketedAllReduce):
+    """Same bucket protocol, but the exchange is `segk_allreduce_f32`, our own kernel over NVLink, on a
+    gradient arena that lives in symmetric memory: NVLS `multimem.ld_reduce` / `multimem.st` through the
+    NVSwitch multicast address when the fabric offers one, peer loads / stores otherwise.  Its 128-thread
+    CTAs share SMs with the tensor-core CTAs; an NCCL CTA cannot, which costs the persistent conv kernels
+    a second wave while a bucket is in flight (profiles/r1d_scaling.md).  torch's symmetric-memory handle
+    provides the allocation, the rendezvous and the cross-rank stream barriers (plumbing); launches are
+    stream-ordered on the caller's current stream, so `work` is None."""
+
+    def __init__(self, net, handle, buckets, group=None):
+        super().__init__(net.vars.g, buckets, group)
+        self.ops = net.ops
+        self.hdl = handle
+        self.rank = dist.get_rank(group)
+        self.mc = int(getattr(handle, "multicast_ptr", 0) or 0)        # 0: no multicast on this fabric
+        # measured on idle B200s (tools/time_exchange.py, 537 MB): 2 GPUs peer 0.81 ms, multimem 1.34, NCCL 0.99
+        want = os.environ.get("SEGK_EXCHANGE", "").lower()
+        if want == "peer" or (want != "multimem" and self.world <= 2):
+            self.mc = 0
+        self.peers = (ctypes.c_uint64 * self.world)(*[int(p) for p in handle.buffer_ptrs])
+        self.kind = "nvls-multimem" if self.mc else "nvlink-peer"
+
+    @classmethod
+    def try_create(cls, net, group=None):
+        """Moves the gradient arena of `net` into symmetric memory and returns the exchange, or None (with
+        the reason on stderr) when symmetric memory is unavailable -- the caller then uses NCCL."""
+        import sys
+        if not dist.is_initialized() or dist.get_world_size(group) < 2:
+            return None
+        if os.environ.get("SEGK_EXCHANGE", "").lower() == "nccl":
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            g_old = net.vars.g
+            g = symm.empty(g_old.numel(), dtype=torch.float32, device=g_old.device)
+            g.zero_()
+            hdl = symm.rendezvous(g, group if group is not None else dist.group.WORLD)
+            ok = torch.tensor([1], device=g_old.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)         # every rank got here
+            net.vars.g = g
+            if hasattr(net, "nodes"):
+                names = [n.name for n in net.nodes if n.kind in ("conv", "deconv")]
+                buckets = P.gradient_buckets_even(net.vars.slots, names)
+            else:
+                buckets = P.gradient_buckets(net.vars.slots)
+            return cls(net, hdl, buckets, group)
+        except Exception as e:       # noqa: BLE001 -- any failure here means "no symmetric memory on this box"
+            print(f"segk: symmetric-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+            return None
+
+    def _launch(self, b):
+        lo, hi, _ = self.buckets[b]
+        # all ranks' gradients of this bucket are complete (the caller's stream waited for its producers)
+        self.hdl.barrier(channel=0, timeout_ms=60000)
+        self.ops.call("segk_allreduce_f32", self.mc, ctypes.addressof(self.peers), lo, hi - lo, self.rank, self.world,
+                      torch.cuda.current_stream().cuda_stream)
+        self.hdl.barrier(channel=0, timeout_ms=60000)                     # every share has been written everywhere
+        self._works.append((lo, hi, None))
 
 
 def init_distributed(backend: str = "nccl"):

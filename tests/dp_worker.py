@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 import torch.distributed as dist
-from semanticsegmentation_tensorflow_b200.dp import BucketedAllReduce, init_distributed
+from semanticsegmentation_tensorflow_b200.dp import BucketedAllReduce, SymmetricAllReduce, init_distributed
 from semanticsegmentation_tensorflow_b200.fcn import FCN, AdamOptimizer, reference_init
 from semanticsegmentation_tensorflow_b200 import plan as P
 
@@ -22,7 +22,17 @@ variables = reference_init(P.variable_shapes(3, 2, FC), 1234, "he")
 lo, hi = P.shard_batch(GB, world, rank)
 xs, ys = torch.as_tensor(x[lo:hi]).to(dev), torch.as_tensor(y[lo:hi]).to(dev)
 net = FCN(xs, 1.0, 2, variables=variables, fc=FC, world_size=world)
-ar = BucketedAllReduce.for_net(net)
+MODE = os.environ.get("DP_EXCHANGE", "nccl")
+if MODE == "symmetric":        # our NVLink kernel on a symmetric-memory gradient arena
+    ar = SymmetricAllReduce.try_create(net)
+    if ar is None:
+        if rank == 0:
+            print("DPRESULT " + json.dumps({"skipped": "no symmetric memory on this box"}), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0)
+else:
+    ar = BucketedAllReduce.for_net(net)
 # (1) the reduced gradient itself (Adam is scale-invariant, so check it before any update)
 net.forward()
 net.loss(ys, with_grad=True)
@@ -48,7 +58,7 @@ dist.broadcast(p0, 0)
 same = float((net.vars.p - p0).abs().max())
 gather = [None] * world
 dist.all_gather_object(gather, same)
-out = {"rank": rank, "replica_max_diff": max(gather), "losses": losses}
+out = {"rank": rank, "replica_max_diff": max(gather), "losses": losses, "exchange": getattr(ar, "kind", "nccl")}
 if rank == 0:
     xf, yf = torch.as_tensor(x).to(dev), torch.as_tensor(y).to(dev)
     ref = FCN(xf, 1.0, 2, variables=variables, fc=FC, world_size=1)

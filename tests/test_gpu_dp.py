@@ -14,15 +14,22 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_gpu_training_matches_single_gpu():
+@pytest.mark.parametrize("exchange", ["nccl", "symmetric"])
+def test_two_gpu_training_matches_single_gpu(exchange):
+    """exchange = nccl: bucketed ncclAllReduce; symmetric: segk_allreduce_f32 (our NVLS / peer kernel) on a
+    symmetric-memory gradient arena."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "dp_worker.py")]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+           "127.0.0.1", "--master-port", "29533" if exchange == "nccl" else "29534", os.path.join(ROOT, "tests", "dp_worker.py")]
+    env = dict(os.environ, DP_EXCHANGE=exchange)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("DPRESULT ")][-1]
     out = json.loads(line[len("DPRESULT "):])
+    if "skipped" in out:
+        pytest.skip(out["skipped"])
+    assert (out["exchange"] == "nccl") == (exchange == "nccl"), out
     assert out["replica_max_diff"] == 0.0                      # every rank applied the same reduced gradient
     # the all-reduced gradient equals the single-GPU gradient of the global batch (sum over shards of the
     # 1/(world*N*H*W)-scaled loss gradients): direction and norm, up to bf16 noise
