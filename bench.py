@@ -159,12 +159,17 @@ def run_gpu(args):
     host_y = torch.randint(0, 2, (B, H, W), dtype=torch.uint8, generator=gen).pin_memory()
     dev_x, dev_y = host_x.to(dev), host_y.to(dev)
 
-    if args.model == "unet":
-        from semanticsegmentation_tensorflow_b200.graph import UNet, graph_flops_per_image, unet_nodes
-        net = UNet(dev_x, NCLS, seed=1234, world_size=world)
-        train_gflop = graph_flops_per_image(unet_nodes(NCLS), H, W, CIN)[1] / 1e9
-        workload = "U-Net 2-class bf16 training (fwd+loss+bwd+Adam), batch 32 per GPU, 160x576x3 (BASELINE configs[2])"
-        metric = "train images/sec U-Net 160x576"
+    if args.model in ("unet", "segnet"):
+        from semanticsegmentation_tensorflow_b200.graph import SegNet, UNet, graph_flops_per_image, segnet_nodes, unet_nodes
+        build, nodes = (UNet, unet_nodes) if args.model == "unet" else (SegNet, segnet_nodes)
+        net = build(dev_x, NCLS, seed=1234, world_size=world)
+        train_gflop = graph_flops_per_image(nodes(NCLS), H, W, CIN)[1] / 1e9
+        if args.model == "unet":
+            workload = "U-Net 2-class bf16 training (fwd+loss+bwd+Adam), batch 32 per GPU, 160x576x3 (BASELINE configs[2])"
+            metric = "train images/sec U-Net 160x576"
+        else:
+            workload = "SegNet (SegNet.py:28-87) 2-class bf16 training (fwd+loss+bwd+Adam), batch 32 per GPU, 160x576x3"
+            metric = "train images/sec SegNet 160x576"
     else:
         net = FCN(dev_x, KEEP_PROB, NCLS, init="device", seed=1234, world_size=world, dropout_seed=42 + rank)
         train_gflop = TRAIN_GFLOP_PER_IMAGE
@@ -415,8 +420,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers-out", default=None, help="write the per-call (per-layer) timing table here")
-    ap.add_argument("--model", default="fcn", choices=["fcn", "unet"],
-                    help="fcn = FCN-8s (BASELINE configs[1], the driver's metric); unet = configs[2]")
+    ap.add_argument("--model", default="fcn", choices=["fcn", "unet", "segnet"],
+                    help="fcn = FCN-8s (BASELINE configs[1], the driver's metric); unet = configs[2]; segnet = the reference's SegNet")
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
                     help="train = BASELINE configs[1] (default, the driver's metric); infer = configs[3]: "
                          "FCN-8s forward + softmax + road mask at 384x1248, batch 16 (throughput and latency)")

@@ -193,6 +193,11 @@ int segk_scale_columns(segk_ctx* ctx, const float* in, const float* scale, float
 int segk_bn_gamma_grad(segk_ctx* ctx, const void* dz, const void* y, const float* beta,
                        const float* gamma, float* dgamma, float* dbeta, void* workspace,
                        size_t workspace_bytes, int64_t rows, int C, void* stream);
+/* The same two gradients for an fp32 head with C in {2,4,8} channels (dz, y fp32 [rows][C]): the
+ * Batch_Normalization the reference's SegNet applies to its logits (SegNet.py:80-81). */
+int segk_bn_grads_f32(segk_ctx* ctx, const float* dz, const float* y, const float* beta, const float* gamma,
+                      float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                      int64_t rows, int C, void* stream);
 /* Concat (utils.py:332) and its gradient: dst[r][coff_dst + c] (=, or += when accumulate)
  * src[r][coff_src + c] for c < C, zeroed where mask[r][c] <= 0 (mask dense [rows][C] or NULL =
  * the fused ReluGrad of the producer).  bf16, all channel counts multiples of 8. */

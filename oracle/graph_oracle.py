@@ -51,11 +51,41 @@ def unet_spec(num_classes=2):
     return S
 
 
-def unet_variable_shapes(cin=3, num_classes=2):
+def segnet_spec(num_classes=2):
+    """The reference's SegNet exactly as written (`SegNet.py:28-87`): every `Conv2D_Block(...,
+    batch_normalization=True)` keeps the helper's default `relu=False` (`utils.py:194`) -- the network has
+    no ReLU --, `Deconv2D_Block` 4x4 s2 "unpool" layers without skip connections, and a 3x3
+    `Conv2D_Layer` to `num_classes` followed by `Batch_Normalization` (`SegNet.py:80-81`)."""
+    S = []
+    def conv(name, src, co):
+        S.append((name, "conv_bn", [src], 3, co)); return name
+    def pool(name, src):
+        S.append((name, "pool", [src], 2, 0)); return name
+    def up(name, src, co):
+        S.append((name, "deconv", [src], 4, co)); return name
+    x = conv("conv1", "input", 64); x = conv("conv2", x, 64); x = pool("pool1", x)
+    x = conv("conv3", x, 128); x = conv("conv4", x, 128); x = pool("pool2", x)
+    x = conv("conv5", x, 256); x = conv("conv6", x, 256); x = conv("conv7", x, 256); x = pool("pool3", x)
+    x = conv("conv8", x, 512); x = conv("conv9", x, 512); x = conv("conv10", x, 512); x = pool("pool4", x)
+    x = conv("conv11", x, 512); x = conv("conv12", x, 512); x = conv("conv13", x, 512); x = pool("pool5", x)
+    x = up("unpool1", x, 512); x = conv("conv14", x, 512); x = conv("conv15", x, 512); x = conv("conv16", x, 512)
+    x = up("unpool2", x, 512); x = conv("conv17", x, 512); x = conv("conv18", x, 512); x = conv("conv19", x, 256)
+    x = up("unpool3", x, 256); x = conv("conv20", x, 256); x = conv("conv21", x, 256); x = conv("conv22", x, 128)
+    x = up("unpool4", x, 128); x = conv("conv23", x, 128); x = conv("conv24", x, 64)
+    x = up("unpool5", x, 64); x = conv("conv25", x, 64)
+    S.append(("conv26", "conv_bn_f32", [x], 3, num_classes))
+    return S
+
+
+def _spec(model, num_classes):
+    return {"unet": unet_spec, "segnet": segnet_spec}[model](num_classes)
+
+
+def unet_variable_shapes(cin=3, num_classes=2, model="unet"):
     ch = {"input": cin}
     shapes = OrderedDict()
     bn = 0
-    for name, kind, inputs, k, co in unet_spec(num_classes):
+    for name, kind, inputs, k, co in _spec(model, num_classes):
         if kind == "pool":
             ch[name] = ch[inputs[0]]
         elif kind == "concat":
@@ -65,7 +95,7 @@ def unet_variable_shapes(cin=3, num_classes=2):
             ch[name] = co
         else:
             shapes[f"{name}/weights"] = (k, k, ch[inputs[0]], co)          # utils.py:178, no bias (:180)
-            if kind == "conv_bn_relu":
+            if kind.startswith("conv_bn"):
                 scope = "batch_normalization" if bn == 0 else f"batch_normalization_{bn}"
                 bn += 1
                 shapes[f"{scope}/gamma"] = (co,)
@@ -74,10 +104,10 @@ def unet_variable_shapes(cin=3, num_classes=2):
     return shapes
 
 
-def unet_init(cin=3, num_classes=2, seed=1234, init="ref"):
+def unet_init(cin=3, num_classes=2, seed=1234, init="ref", model="unet"):
     rng = np.random.default_rng(seed)
     out = OrderedDict()
-    for name, shape in unet_variable_shapes(cin, num_classes).items():
+    for name, shape in unet_variable_shapes(cin, num_classes, model).items():
         if name.endswith("weights"):
             z = rng.standard_normal(shape, dtype=np.float32)
             if init == "ref":
@@ -94,8 +124,9 @@ def unet_init(cin=3, num_classes=2, seed=1234, init="ref"):
 
 
 class UNetOracle:
-    def __init__(self, variables, num_classes=2, bf16_storage=False, bf16_grads=False):
+    def __init__(self, variables, num_classes=2, bf16_storage=False, bf16_grads=False, model="unet"):
         self.ncls = num_classes
+        self.model = model
         self.bf16, self.bf16_grads = bf16_storage, bf16_grads
         self.vars = OrderedDict((k, torch.tensor(v, dtype=torch.float32, requires_grad=True)) for k, v in variables.items())
         self.m = OrderedDict((k, torch.zeros_like(v)) for k, v in self.vars.items())
@@ -116,7 +147,7 @@ class UNetOracle:
         A.clear()
         A["input"] = x
         bn = 0
-        for name, kind, inputs, k, co in unet_spec(self.ncls):
+        for name, kind, inputs, k, co in _spec(self.model, self.ncls):
             if kind == "pool":
                 A[name] = T.max_pool_2x2(A[inputs[0]])
             elif kind == "concat":
@@ -128,7 +159,7 @@ class UNetOracle:
                     w = w + (T.to_bf16_grid(w.detach()) - w.detach())
                 y = T.conv2d_transpose_same(src, w, (src.shape[1] * 2, src.shape[2] * 2), 2)   # utils.py:275
                 A[name] = self._q(y)
-            elif kind == "conv_bn_relu":
+            elif kind.startswith("conv_bn"):
                 scope = "batch_normalization" if bn == 0 else f"batch_normalization_{bn}"
                 bn += 1
                 g, b = self.vars[f"{scope}/gamma"], self.vars[f"{scope}/beta"]
@@ -138,11 +169,16 @@ class UNetOracle:
                 if self.bf16:
                     weff = weff + (T.to_bf16_grid(weff.detach()) - weff.detach())
                 y = T.conv2d_same(A[inputs[0]], weff) + b                                  # BN(conv(x)) (utils.py:196-201)
-                A[name] = self._q(T.relu(y))
+                if kind == "conv_bn_relu":
+                    A[name] = self._q(T.relu(y))
+                elif kind == "conv_bn":
+                    A[name] = self._q(y)                                                    # relu=False (utils.py:194)
+                else:
+                    A[name] = y                                                             # fp32 logits (SegNet.py:80-81)
             else:
                 w = self.vars[f"{name}/weights"]
                 A[name] = T.conv2d_same(A[inputs[0]], w)                                   # fp32 logits
-        logits = A["final_conv"]
+        logits = A[_spec(self.model, self.ncls)[-1][0]]
         return T.argmax_last(logits).unsqueeze(3), logits
 
     def loss(self, logits, labels_u8):

@@ -226,6 +226,43 @@ __global__ void __launch_bounds__(kThreads) bn_gamma_finish_kernel(const float* 
   }
 }
 
+// BN-affine gradients of an fp32 head with few channels (SegNet's conv26 + Batch_Normalization on the
+// logits, SegNet.py:80-81): partial[b][0][c] = sum dz*(y - beta), partial[b][1][c] = sum dz; thread = one row.
+template <int C>
+__global__ void __launch_bounds__(kThreads) bn_grads_f32_partial_kernel(const float* __restrict__ dz, const float* __restrict__ y,
+                                                                        const float* __restrict__ beta,
+                                                                        float* __restrict__ partial, int64_t rows) {
+  __shared__ float sh[kThreads / 32][2 * C];
+  float a[C], s[C], b[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) { a[c] = 0.f; s[c] = 0.f; b[c] = __ldg(beta + c); }
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float g = dz[r * C + c];
+      a[c] += g * (y[r * C + c] - b[c]);
+      s[c] += g;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    for (int o = 16; o > 0; o >>= 1) {
+      a[c] += __shfl_xor_sync(0xffffffffu, a[c], o);
+      s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) { sh[warp][c] = a[c]; sh[warp][C + c] = s[c]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * C) {
+    float t = 0.f;
+    for (int w = 0; w < kThreads / 32; ++w) t += sh[w][threadIdx.x];
+    partial[(int64_t)blockIdx.x * 2 * C + threadIdx.x] = t;      // [block][{dgamma*gamma, dbeta}][C]
+  }
+}
+
 // dst[r][coff_dst + c] (= or +=) src[r][coff_src + c], optionally zeroed where mask[r][c] <= 0; 8 channels/thread
 __global__ void __launch_bounds__(kThreads) channel_copy_kernel(const bf16* __restrict__ src, int ld_src, int coff_src,
                                                                 bf16* __restrict__ dst, int ld_dst, int coff_dst,
@@ -359,6 +396,26 @@ int segk_bn_gamma_grad(segk_ctx* ctx, const void* dz, const void* y, const float
     bn_gamma_partial_kernel<false><<<dim3((unsigned)gx, gy), kThreads, 0, st>>>((const uint4*)dz, (const uint4*)y, beta,
                                                                              (float*)workspace, rows, C8);
   SEGK_LAUNCHED(ctx, "bn_gamma_partial");
+  bn_gamma_finish_kernel<<<ceil_div(C, 32), kThreads, 0, st>>>((const float*)workspace, gamma, dgamma, dbeta, (int)gx, C);
+  SEGK_LAUNCHED(ctx, "bn_gamma_finish");
+  return SEGK_OK;
+}
+
+int segk_bn_grads_f32(segk_ctx* ctx, const float* dz, const float* y, const float* beta, const float* gamma, float* dgamma,
+                      float* dbeta, void* workspace, size_t workspace_bytes, int64_t rows, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, dz && y && beta && gamma && dgamma && dbeta && workspace && rows > 0, "bn_grads_f32: bad args");
+  SEGK_REQUIRE(ctx, C == 2 || C == 4 || C == 8, "bn_grads_f32: C must be 2, 4 or 8 (got %d)", C);
+  int64_t gx = ceil_div64(rows, (int64_t)kThreads * 8);
+  if (gx > (int64_t)ctx->sm_count * 4) gx = (int64_t)ctx->sm_count * 4;
+  if (gx < 1) gx = 1;
+  const size_t need = sizeof(float) * (size_t)gx * 2 * C;
+  SEGK_REQUIRE(ctx, workspace_bytes >= need, "bn_grads_f32: workspace too small (%zu < %zu)", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C == 2) bn_grads_f32_partial_kernel<2><<<(unsigned)gx, kThreads, 0, st>>>(dz, y, beta, (float*)workspace, rows);
+  else if (C == 4) bn_grads_f32_partial_kernel<4><<<(unsigned)gx, kThreads, 0, st>>>(dz, y, beta, (float*)workspace, rows);
+  else bn_grads_f32_partial_kernel<8><<<(unsigned)gx, kThreads, 0, st>>>(dz, y, beta, (float*)workspace, rows);
+  SEGK_LAUNCHED(ctx, "bn_grads_f32_partial");
   bn_gamma_finish_kernel<<<ceil_div(C, 32), kThreads, 0, st>>>((const float*)workspace, gamma, dgamma, dbeta, (int)gx, C);
   SEGK_LAUNCHED(ctx, "bn_gamma_finish");
   return SEGK_OK;

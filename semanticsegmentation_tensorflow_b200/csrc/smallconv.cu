@@ -332,6 +332,146 @@ __global__ void __launch_bounds__(kThreads) conv_skinny_wgrad_partial_kernel(
   }
 }
 
+// ---- skinny k x k conv (odd k, SAME) with Cout in {2,4}: the 3x3 64 -> num_classes head of the reference's
+// SegNet (`SegNet.py:80`, Conv2D_Layer default 3x3) at full resolution.  Same three forms as the 1x1 head
+// above with a tap loop; x is re-read kh*kw times through L1/L2, DRAM traffic stays one pass.
+template <int CO>
+__global__ void __launch_bounds__(kThreads) conv_skinny_kxk_fwd_kernel(
+    const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, void* __restrict__ y,
+    int N, int H, int W, int Cin, int kh, int kw, int relu, int out_f32) {
+  extern __shared__ float wsm[];   // [kh*kw][Cin][CO]
+  for (int i = threadIdx.x; i < kh * kw * Cin * CO; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  const int64_t npix = (int64_t)N * H * W;
+  const int ph = kh / 2, pw = kw / 2;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
+    const int xw = (int)(p % W), yh = (int)((p / W) % H);
+    float acc[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[c] = bias ? bias[c] : 0.f;
+    for (int t = 0; t < kh * kw; ++t) {
+      const int yy = yh + t / kw - ph, xx = xw + t % kw - pw;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const uint4* xp = reinterpret_cast<const uint4*>(x + (p + (int64_t)(yy - yh) * W + (xx - xw)) * Cin);
+      const float* wt = wsm + (int64_t)t * Cin * CO;
+      for (int g = 0; g < Cin / 8; ++g) {
+        const uint4 v = __ldg(xp + g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2((&v.x)[j]);
+          const float* w0 = wt + (g * 8 + 2 * j) * CO;
+#pragma unroll
+          for (int c = 0; c < CO; ++c) acc[c] += f.x * w0[c] + f.y * w0[CO + c];
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+      const float v = relu ? fmaxf(acc[c], 0.f) : acc[c];
+      if (out_f32) reinterpret_cast<float*>(y)[p * CO + c] = v;
+      else reinterpret_cast<bf16*>(y)[p * CO + c] = f2bf(v);
+    }
+  }
+}
+
+// dx[p][ci] = sum_taps sum_co dy[p - tap][co] * w[tap][ci][co]; thread = 8 input channels of one pixel
+template <int CO>
+__global__ void __launch_bounds__(kThreads) conv_skinny_kxk_dgrad_kernel(
+    const bf16* __restrict__ dy, const float* __restrict__ w, const bf16* __restrict__ mask, bf16* __restrict__ dx,
+    int N, int H, int W, int Cin, int kh, int kw, float scale) {
+  extern __shared__ float wsm[];   // [kh*kw][Cin][CO]
+  for (int i = threadIdx.x; i < kh * kw * Cin * CO; i += blockDim.x) wsm[i] = w[i];
+  __syncthreads();
+  const int C8 = Cin >> 3;
+  const int64_t total = (int64_t)N * H * W * C8;
+  const int ph = kh / 2, pw = kw / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % C8);
+    const int64_t p = i / C8;
+    const int xw = (int)(p % W), yh = (int)((p / W) % H);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    for (int t = 0; t < kh * kw; ++t) {
+      const int yy = yh - (t / kw - ph), xx = xw - (t % kw - pw);      // the output pixel this tap came from
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const bf16* dp = dy + (p + (int64_t)(yy - yh) * W + (xx - xw)) * CO;
+      float d[CO];
+#pragma unroll
+      for (int c = 0; c < CO; ++c) d[c] = bf2f(dp[c]);
+      const float* wt = wsm + ((int64_t)t * Cin + g * 8) * CO;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int c = 0; c < CO; ++c) v[j] += d[c] * wt[j * CO + c];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= scale;
+    if (mask) {
+      const uint4 m = __ldg(reinterpret_cast<const uint4*>(mask + p * Cin) + g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&m.x)[j]);
+        if (!(f.x > 0.f)) v[2 * j] = 0.f;
+        if (!(f.y > 0.f)) v[2 * j + 1] = 0.f;
+      }
+    }
+    reinterpret_cast<uint4*>(dx + p * Cin)[g] =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// wgrad stage 1 for one tap (blockIdx.y): per-block partial dW[tap][ci][co] over the block's pixels
+template <int CO>
+__global__ void __launch_bounds__(kThreads) conv_skinny_kxk_wgrad_partial_kernel(
+    const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ partial, int N, int H, int W, int Cin,
+    int kh, int kw) {
+  __shared__ float sh[kThreads][8 * CO + 1];
+  const int C8 = Cin >> 3;                 // host guarantees C8 divides kThreads
+  const int R = kThreads / C8;
+  const int g = threadIdx.x % C8, rl = threadIdx.x / C8;
+  const int t = blockIdx.y;
+  const int dyo = t / kw - kh / 2, dxo = t % kw - kw / 2;
+  const int64_t npix = (int64_t)N * H * W;
+  float acc[8][CO];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
+  for (int64_t p = (int64_t)blockIdx.x * R + rl; p < npix; p += (int64_t)gridDim.x * R) {
+    const int xw = (int)(p % W), yh = (int)((p / W) % H);
+    const int yy = yh + dyo, xx = xw + dxo;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (p + (int64_t)dyo * W + dxo) * Cin) + g);
+    float d[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) d[c] = bf2f(dy[p * CO + c]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2((&v.x)[j]);
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        acc[2 * j][c] += f.x * d[c];
+        acc[2 * j + 1][c] += f.y * d[c];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) sh[threadIdx.x][j * CO + c] = acc[j][c];
+  __syncthreads();
+  if (rl == 0) {
+    for (int k = 1; k < R; ++k)
+#pragma unroll
+      for (int j = 0; j < 8 * CO; ++j) sh[threadIdx.x][j] += sh[threadIdx.x + k * C8][j];
+    // [block][tap][ci][co]
+    float* out = partial + (((int64_t)blockIdx.x * gridDim.y + t) * Cin + g * 8) * CO;
+#pragma unroll
+    for (int j = 0; j < 8 * CO; ++j) out[j] = sh[threadIdx.x][j];
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) sum_partials_rows_kernel(const float* __restrict__ partial,
                                                                      float* __restrict__ out, int rows, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -558,6 +698,17 @@ int segk_conv2d_small_fwd(segk_ctx* ctx, const void* x, int x_dtype, const float
     SEGK_LAUNCHED(ctx, "conv_skinny_fwd");
     return SEGK_OK;
   }
+  if (x_dtype == 0 && (kh & 1) && (kw & 1) && kh * kw <= 25 && Cin % 8 == 0 && (Cout == 2 || Cout == 4) &&
+      (size_t)kh * kw * Cin * Cout * sizeof(float) <= 48 * 1024) {
+    const int grid = sgrid(ctx, npix, 8);
+    const size_t sm = sizeof(float) * (size_t)kh * kw * Cin * Cout;
+    if (Cout == 2)
+      conv_skinny_kxk_fwd_kernel<2><<<grid, kThreads, sm, st>>>((const bf16*)x, w, bias, y, N, H, W, Cin, kh, kw, relu, out_f32);
+    else
+      conv_skinny_kxk_fwd_kernel<4><<<grid, kThreads, sm, st>>>((const bf16*)x, w, bias, y, N, H, W, Cin, kh, kw, relu, out_f32);
+    SEGK_LAUNCHED(ctx, "conv_skinny_kxk_fwd");
+    return SEGK_OK;
+  }
   return segk_fail(ctx, SEGK_EINVAL,
                    "conv_small_fwd: unsupported shape k=%dx%d Cin=%d Cout=%d dtype=%d (no fallback)", kh, kw,
                    Cin, Cout, x_dtype);
@@ -568,10 +719,23 @@ int segk_conv2d_small_dgrad(segk_ctx* ctx, const void* dy, const float* w, const
                             void* stream) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, dy && w && dx && N > 0, "conv_small_dgrad: bad args");
-  SEGK_REQUIRE(ctx, kh == 1 && kw == 1 && (Cout == 2 || Cout == 4 || Cout == 8),
-               "conv_small_dgrad: only 1x1 with Cout in {2,4,8} (got %dx%d Cout=%d)", kh, kw, Cout);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t npix = (int64_t)N * H * W;
+  if (kh * kw > 1) {
+    SEGK_REQUIRE(ctx, (kh & 1) && (kw & 1) && kh * kw <= 25 && Cin % 8 == 0 && (Cout == 2 || Cout == 4) &&
+                          (size_t)kh * kw * Cin * Cout * sizeof(float) <= 48 * 1024,
+                 "conv_small_dgrad: k x k needs odd k <= 5, Cin %% 8 == 0, Cout in {2,4} (got %dx%d %d -> %d)", kh, kw, Cin, Cout);
+    const int g = sgrid(ctx, npix * (Cin / 8), 8);
+    const size_t sm = sizeof(float) * (size_t)kh * kw * Cin * Cout;
+    if (Cout == 2)
+      conv_skinny_kxk_dgrad_kernel<2><<<g, kThreads, sm, st>>>((const bf16*)dy, w, (const bf16*)relu_mask, (bf16*)dx, N, H, W, Cin, kh, kw, scale);
+    else
+      conv_skinny_kxk_dgrad_kernel<4><<<g, kThreads, sm, st>>>((const bf16*)dy, w, (const bf16*)relu_mask, (bf16*)dx, N, H, W, Cin, kh, kw, scale);
+    SEGK_LAUNCHED(ctx, "conv_skinny_kxk_dgrad");
+    return SEGK_OK;
+  }
+  SEGK_REQUIRE(ctx, kh == 1 && kw == 1 && (Cout == 2 || Cout == 4 || Cout == 8),
+               "conv_small_dgrad: only 1x1 with Cout in {2,4,8} (got %dx%d Cout=%d)", kh, kw, Cout);
   if (Cin % 8 == 0 && Cin <= 256 && npix >= 65536 && (Cout == 2 || Cout == 4)) {
     const int g = sgrid(ctx, npix * (Cin / 8), 8);
     const size_t sm = sizeof(float) * (size_t)Cin * Cout;
@@ -627,6 +791,32 @@ int segk_conv2d_small_wgrad(segk_ctx* ctx, const void* x, int x_dtype, const voi
     const int n = Cin * Cout;
     sum_partials_rows_kernel<<<ceil_div(n, kThreads), kThreads, 0, st>>>((const float*)ctx->ws3, dw, (int)gx, n);
     SEGK_LAUNCHED(ctx, "conv_skinny_wgrad_sum");
+  } else if (x_dtype == 0 && kh * kw > 1 && (kh & 1) && (kw & 1) && kh * kw <= 25 && (Cout == 2 || Cout == 4) &&
+             Cin % 8 == 0 && kThreads % (Cin / 8) == 0 && K > kTinyKMax) {
+    // k x k head: two-stage reduction over pixels, one grid row per tap
+    const int R = kThreads / (Cin / 8);
+    const int T = kh * kw;
+    int64_t gx = ceil_div64(npix, (int64_t)R * 8);
+    const int64_t cap = ceil_div64((int64_t)ctx->sm_count * 4, T);
+    if (gx > cap) gx = cap;
+    const size_t need = sizeof(float) * (size_t)gx * K * Cout;
+    if (ctx->ws3_bytes < need) {
+      if (ctx->ws3) cudaFree(ctx->ws3);
+      ctx->ws3 = nullptr;
+      ctx->ws3_bytes = 0;
+      const size_t want = need < (size_t)(4 << 20) ? (size_t)(4 << 20) : need;
+      if (cudaMalloc(&ctx->ws3, want) != cudaSuccess) return segk_fail(ctx, SEGK_ENOMEM, "skinny wgrad workspace");
+      ctx->ws3_bytes = want;
+    }
+    dim3 grid((unsigned)gx, T);
+    if (Cout == 2)
+      conv_skinny_kxk_wgrad_partial_kernel<2><<<grid, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, (float*)ctx->ws3, N, H, W, Cin, kh, kw);
+    else
+      conv_skinny_kxk_wgrad_partial_kernel<4><<<grid, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, (float*)ctx->ws3, N, H, W, Cin, kh, kw);
+    SEGK_LAUNCHED(ctx, "conv_skinny_kxk_wgrad_partial");
+    const int n = K * Cout;
+    sum_partials_rows_kernel<<<ceil_div(n, kThreads), kThreads, 0, st>>>((const float*)ctx->ws3, dw, (int)gx, n);
+    SEGK_LAUNCHED(ctx, "conv_skinny_kxk_wgrad_sum");
   } else if (K <= kTinyKMax && (kh & 1) && (kw & 1)) {
     const int gy = ceil_div(Cout, 64);
     int64_t blocks = (int64_t)ctx->sm_count * 4 / gy;

@@ -109,6 +109,26 @@ def unet_nodes(num_classes=2):
     return g.nodes
 
 
+def segnet_nodes(num_classes=2):
+    """The reference's SegNet as written (SegNet.py:28-87): Conv2D_Block(batch_normalization=True) with the
+    helper's default relu=False (utils.py:194), 4x4 s2 Deconv2D_Block "unpool" layers without skips, and a
+    3x3 Conv2D_Layer to num_classes + Batch_Normalization (SegNet.py:80-81)."""
+    g = GraphBuilder()
+    c = lambda x, f, name: g.Conv2D_Block(x, f, batch_normalization=True, name=name)
+    x = c("input", 64, "conv1"); x = c(x, 64, "conv2"); x = g.Max_Pooling(x, "pool1")
+    x = c(x, 128, "conv3"); x = c(x, 128, "conv4"); x = g.Max_Pooling(x, "pool2")
+    x = c(x, 256, "conv5"); x = c(x, 256, "conv6"); x = c(x, 256, "conv7"); x = g.Max_Pooling(x, "pool3")
+    x = c(x, 512, "conv8"); x = c(x, 512, "conv9"); x = c(x, 512, "conv10"); x = g.Max_Pooling(x, "pool4")
+    x = c(x, 512, "conv11"); x = c(x, 512, "conv12"); x = c(x, 512, "conv13"); x = g.Max_Pooling(x, "pool5")
+    x = g.Deconv2D_Block(x, 512, name="unpool1"); x = c(x, 512, "conv14"); x = c(x, 512, "conv15"); x = c(x, 512, "conv16")
+    x = g.Deconv2D_Block(x, 512, name="unpool2"); x = c(x, 512, "conv17"); x = c(x, 512, "conv18"); x = c(x, 256, "conv19")
+    x = g.Deconv2D_Block(x, 256, name="unpool3"); x = c(x, 256, "conv20"); x = c(x, 256, "conv21"); x = c(x, 128, "conv22")
+    x = g.Deconv2D_Block(x, 128, name="unpool4"); x = c(x, 128, "conv23"); x = c(x, 64, "conv24")
+    x = g.Deconv2D_Block(x, 64, name="unpool5"); x = c(x, 64, "conv25")
+    g.Conv2D_Block(x, num_classes, 3, 3, batch_normalization=True, name="conv26")     # Conv2D_Layer + Batch_Normalization
+    return g.nodes
+
+
 def graph_variable_shapes(nodes, cin):
     """Ordered {name: shape}: `<scope>/weights` (HWIO; deconv [k,k,Cout,Cin]), BN gamma/beta in TF naming."""
     ch = {"input": cin}
@@ -224,6 +244,8 @@ class GraphNet:
             return "im2col"
         if n.k == 1 and n.cout in (2, 4, 8) and cin % 8 == 0:
             return "small"
+        if n.k in (3, 5) and n.cout in (2, 4) and cin % 8 == 0 and 256 % (cin // 8) == 0 and n.k * n.k * cin * n.cout * 4 <= 48 * 1024:
+            return "small"        # k x k head to num_classes (SegNet.py:80)
         raise ValueError(f"{n.name}: unsupported conv {n.k}x{n.k} {cin}->{n.cout} (no fallback)")
 
     def _plan(self):
@@ -408,7 +430,11 @@ class GraphNet:
             if r == "small" and G.dtype == torch.float32:
                 dz = ops.cast_to_bf16(G, self.dlogits_bf16)
             if n.bn:      # d(beta), d(gamma): one HBM-bound pass over dz and the activation, off the critical path
-                def bn_grads(dz=dz, n=n):
+                def bn_grads(dz=dz, n=n, G=G):
+                    if self.act[n.name].dtype == torch.float32:      # BN on the fp32 logits (SegNet.py:80-81)
+                        ops.bn_grads_f32(G, self.act[n.name], V.param(f"{n.bn_scope}/beta"), V.param(f"{n.bn_scope}/gamma"),
+                                         V.grad(f"{n.bn_scope}/gamma"), V.grad(f"{n.bn_scope}/beta"), self.bn_ws)
+                        return
                     ops.bn_gamma_grad(dz, self.act[n.name], V.param(f"{n.bn_scope}/beta"),
                                       V.param(f"{n.bn_scope}/gamma"), V.grad(f"{n.bn_scope}/gamma"), self.bn_ws,
                                       dbeta=V.grad(f"{n.bn_scope}/beta"))
@@ -496,6 +522,11 @@ def graph_flops_per_image(nodes, h, w, cin):
             fwd += f; train += (2 if n.inputs[0] == "input" else 3) * f
             shape[n.name] = (ih, iw, n.cout)
     return fwd, train
+
+
+def SegNet(x, num_classes=2, **kw):
+    """`SegNet(x, num_classes)` of SegNet.py:28 on the same kernels."""
+    return GraphNet(x, num_classes, segnet_nodes(num_classes), **kw)
 
 
 def UNet(x, num_classes=2, **kw):

@@ -313,6 +313,12 @@ class Ops:
                   workspace.numel() * workspace.element_size(), dz.numel() // c, c, _stream())
         return dgamma
 
+    def bn_grads_f32(self, dz, y, beta, gamma, dgamma, dbeta, workspace):
+        c = dz.shape[-1]
+        self._w(8.0 * dz.numel(), "byte")
+        self.call("segk_bn_grads_f32", _p(dz), _p(y), _p(beta), _p(gamma), _p(dgamma), _p(dbeta), _p(workspace),
+                  workspace.numel() * workspace.element_size(), dz.numel() // c, c, _stream())
+
     def channel_copy(self, src, coff_src, dst, coff_dst, c, mask=None, accumulate=False):
         rows = src.numel() // src.shape[-1]
         self._w(4.0 * rows * c, "byte")

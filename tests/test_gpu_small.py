@@ -270,3 +270,31 @@ def test_full_resolution_1x1_head(ops, cuda_device, co):
     torch.cuda.synchronize()
     assert_close(host(dx), xt.grad.numpy() * (x > 0), 1e-2, "head dgrad")
     assert_close(host(dw), wtt.grad.numpy(), 1e-4, "head wgrad")
+
+
+@pytest.mark.parametrize("case", [(2, 16, 24, 64, 2, 3), (1, 9, 13, 32, 4, 3), (1, 12, 10, 64, 2, 5)])
+def test_skinny_kxk_head(ops, cuda_device, case):
+    """3x3 (5x5) conv to num_classes on CUDA cores: SegNet's conv26 (SegNet.py:80), fwd / dgrad / wgrad."""
+    n, h, w, ci, co, k = case
+    rng = np.random.default_rng(60)
+    x = bf16_grid(rng.standard_normal((n, h, w, ci)))
+    wt = (rng.standard_normal((k, k, ci, co)) / np.sqrt(k * k * ci)).astype(np.float32)
+    b = (rng.standard_normal(co) * 0.1).astype(np.float32)
+    xt, wtt = torch.tensor(x, requires_grad=True), torch.tensor(wt, requires_grad=True)
+    z = T.bias_add(T.conv2d_same(xt, wtt), torch.tensor(b))
+    y = torch.empty((n, h, w, co), dtype=torch.float32, device=cuda_device)
+    xd, wd_ = dev_bf16(x, cuda_device), dev_f32(wt, cuda_device)
+    ops.conv2d_small_fwd(xd, wd_, dev_f32(b, cuda_device), y, relu=False)
+    torch.cuda.synchronize()
+    assert_close(host(y), z.detach().numpy(), 1e-5, f"skinny kxk fwd {case}")
+    dy = bf16_grid(rng.standard_normal((n, h, w, co)))
+    z.backward(torch.tensor(dy))
+    dyd = dev_bf16(dy, cuda_device)
+    dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=cuda_device)
+    ops.conv2d_small_dgrad(dyd, wd_, dx, relu_mask=xd)
+    torch.cuda.synchronize()
+    assert_close(host(dx), xt.grad.numpy() * (x > 0), 1e-2, f"skinny kxk dgrad {case}")
+    dw = torch.full((k, k, ci, co), 7.0, dtype=torch.float32, device=cuda_device)
+    ops.conv2d_small_wgrad(xd, dyd, dw)
+    torch.cuda.synchronize()
+    assert_close(host(dw), wtt.grad.numpy(), 1e-4, f"skinny kxk wgrad {case}")

@@ -147,3 +147,64 @@ def test_unet_training_steps(cuda_device):
     print("unet loss gpu", got, "ref", ref)
     np.testing.assert_allclose(got, ref, rtol=5e-2)
     assert got[-1] < got[0]
+
+
+# ---- the reference's SegNet (SegNet.py:28-87): no ReLU, no skips, 3x3 conv to num_classes + BN -----------
+
+def _build_segnet(cuda_device):
+    from semanticsegmentation_tensorflow_b200.graph import SegNet
+    variables = unet_init(3, 2, seed=1234, init="he", model="segnet")
+    rng = np.random.default_rng(6)
+    for k in variables:
+        if k.endswith("weights"):            # the net is linear (relu=False): unit-gain init instead of He's sqrt(2)
+            variables[k] = (variables[k] / np.float32(math.sqrt(2.0))).astype(np.float32)
+        if k.endswith("gamma"):
+            variables[k] = (1 + 0.1 * rng.standard_normal(variables[k].shape)).astype(np.float32)
+        if k.endswith("beta"):
+            variables[k] = (0.05 * rng.standard_normal(variables[k].shape)).astype(np.float32)
+    x, lab = synthetic_batch(N, H, W, seed=0, road_shaped=True)
+    x = (x // 32).astype(np.uint8)
+    net = SegNet(torch.as_tensor(x).to(cuda_device), 2, variables=variables)
+    return net, variables, x, lab
+
+
+def test_segnet_graph_matches_oracle_definition():
+    from semanticsegmentation_tensorflow_b200.graph import graph_variable_shapes, segnet_nodes
+    from oracle.graph_oracle import unet_variable_shapes
+    shapes = graph_variable_shapes(segnet_nodes(2), 3)
+    assert list(shapes.items()) == list(unet_variable_shapes(3, 2, "segnet").items())
+    assert sum(int(np.prod(v)) for v in shapes.values()) == 39_201_092          # 39.2 M params
+
+
+def test_segnet_forward_and_gradients(cuda_device):
+    net, variables, x, lab = _build_segnet(cuda_device)
+    pred, logits = net.create()
+    loss = net.loss(torch.as_tensor(lab).to(cuda_device), with_grad=True)
+    net.backward()
+    torch.cuda.synchronize()
+    orc = UNetOracle(variables, bf16_storage=True, bf16_grads=True, model="segnet")
+    loss_ref, logits_ref, grads_ref = orc.loss_and_grads(x, lab)
+    _, _, grads_f32 = UNetOracle(variables, bf16_storage=False, model="segnet").loss_and_grads(x, lab)
+    for name, t in net.act.items():
+        e = rel_err(t.float().cpu().numpy(), orc.acts[name].detach().numpy())
+        assert e <= 2e-2, f"segnet activation {name}: rel err {e:.3e}"
+    assert abs(float(loss) - loss_ref) <= 2e-3 * abs(loss_ref)
+    for name in net.vars.slots:
+        g, r, f = net.vars.grad(name).cpu().numpy(), grads_ref[name].numpy(), grads_f32[name].numpy()
+        e, c = rel_err(g, r), cosine(g, r)
+        tol_e, tol_c = max(5e-2, 3 * rel_err(r, f)), min(0.999, 1 - 9 * (1 - cosine(r, f)))
+        assert e <= tol_e and c >= tol_c, f"segnet grad {name}: rel {e:.3e} (tol {tol_e:.3e}) cos {c:.6f} (tol {tol_c:.6f})"
+
+
+def test_segnet_training_steps(cuda_device):
+    from semanticsegmentation_tensorflow_b200.fcn import AdamOptimizer
+    net, variables, x, lab = _build_segnet(cuda_device)
+    step = AdamOptimizer(1e-4).minimize(net)
+    orc = UNetOracle(variables, bf16_storage=True, model="segnet")
+    xd, ld = torch.as_tensor(x).to(cuda_device), torch.as_tensor(lab).to(cuda_device)
+    got, ref = [], []
+    for _ in range(4):
+        got.append(float(step({net.image: xd, net.annotation: ld})))
+        ref.append(orc.train_step(x, lab)[0])
+    print("segnet loss gpu", got, "ref", ref)
+    np.testing.assert_allclose(got, ref, rtol=5e-2)
