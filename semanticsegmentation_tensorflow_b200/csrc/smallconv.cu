@@ -342,34 +342,45 @@ __global__ void __launch_bounds__(kThreads) conv_skinny_kxk_fwd_kernel(
   extern __shared__ float wsm[];   // [kh*kw][Cin][CO]
   for (int i = threadIdx.x; i < kh * kw * Cin * CO; i += blockDim.x) wsm[i] = w[i];
   __syncthreads();
-  const int64_t npix = (int64_t)N * H * W;
+  const int npix = N * H * W;      // host guarantees < 2^31 / Cin: 32-bit index arithmetic throughout
   const int ph = kh / 2, pw = kw / 2;
-  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < npix; p += (int64_t)gridDim.x * blockDim.x) {
-    const int xw = (int)(p % W), yh = (int)((p / W) % H);
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+    const int xw = p % W, yh = (p / W) % H;
     float acc[CO];
 #pragma unroll
     for (int c = 0; c < CO; ++c) acc[c] = bias ? bias[c] : 0.f;
     for (int t = 0; t < kh * kw; ++t) {
-      const int yy = yh + t / kw - ph, xx = xw + t % kw - pw;
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      const uint4* xp = reinterpret_cast<const uint4*>(x + (p + (int64_t)(yy - yh) * W + (xx - xw)) * Cin);
-      const float* wt = wsm + (int64_t)t * Cin * CO;
+      const int dyo = t / kw - ph, dxo = t % kw - pw;
+      if ((unsigned)(yh + dyo) >= (unsigned)H || (unsigned)(xw + dxo) >= (unsigned)W) continue;
+      const uint4* xp = reinterpret_cast<const uint4*>(x + (int64_t)(p + dyo * W + dxo) * Cin);
+      const float* wt = wsm + t * Cin * CO;
       for (int g = 0; g < Cin / 8; ++g) {
         const uint4 v = __ldg(xp + g);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = unpack_bf16x2((&v.x)[j]);
-          const float* w0 = wt + (g * 8 + 2 * j) * CO;
+          // the 2*CO weights of this channel pair are contiguous: vector shared-memory loads
+          float wv[2 * CO];
+          if (CO == 2) {
+            const float4 q = *reinterpret_cast<const float4*>(wt + (g * 8 + 2 * j) * CO);
+            wv[0] = q.x; wv[1] = q.y; wv[2] = q.z; wv[3] = q.w;
+          } else {
 #pragma unroll
-          for (int c = 0; c < CO; ++c) acc[c] += f.x * w0[c] + f.y * w0[CO + c];
+            for (int c = 0; c < 2 * CO; c += 4) {
+              const float4 q = *reinterpret_cast<const float4*>(wt + (g * 8 + 2 * j) * CO + c);
+              wv[c] = q.x; wv[c + 1] = q.y; wv[c + 2] = q.z; wv[c + 3] = q.w;
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < CO; ++c) acc[c] += f.x * wv[c] + f.y * wv[CO + c];
         }
       }
     }
 #pragma unroll
     for (int c = 0; c < CO; ++c) {
       const float v = relu ? fmaxf(acc[c], 0.f) : acc[c];
-      if (out_f32) reinterpret_cast<float*>(y)[p * CO + c] = v;
-      else reinterpret_cast<bf16*>(y)[p * CO + c] = f2bf(v);
+      if (out_f32) reinterpret_cast<float*>(y)[(int64_t)p * CO + c] = v;
+      else reinterpret_cast<bf16*>(y)[(int64_t)p * CO + c] = f2bf(v);
     }
   }
 }
@@ -383,32 +394,34 @@ __global__ void __launch_bounds__(kThreads) conv_skinny_kxk_dgrad_kernel(
   for (int i = threadIdx.x; i < kh * kw * Cin * CO; i += blockDim.x) wsm[i] = w[i];
   __syncthreads();
   const int C8 = Cin >> 3;
-  const int64_t total = (int64_t)N * H * W * C8;
+  const int total = N * H * W * C8;        // < 2^31 (host)
   const int ph = kh / 2, pw = kw / 2;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % C8);
-    const int64_t p = i / C8;
-    const int xw = (int)(p % W), yh = (int)((p / W) % H);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int g = i % C8, p = i / C8;
+    const int xw = p % W, yh = (p / W) % H;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.f;
     for (int t = 0; t < kh * kw; ++t) {
-      const int yy = yh - (t / kw - ph), xx = xw - (t % kw - pw);      // the output pixel this tap came from
-      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-      const bf16* dp = dy + (p + (int64_t)(yy - yh) * W + (xx - xw)) * CO;
+      const int dyo = -(t / kw - ph), dxo = -(t % kw - pw);      // the output pixel this tap came from
+      if ((unsigned)(yh + dyo) >= (unsigned)H || (unsigned)(xw + dxo) >= (unsigned)W) continue;
+      const bf16* dp = dy + (int64_t)(p + dyo * W + dxo) * CO;
       float d[CO];
 #pragma unroll
       for (int c = 0; c < CO; ++c) d[c] = bf2f(dp[c]);
-      const float* wt = wsm + ((int64_t)t * Cin + g * 8) * CO;
+      const float4* wt = reinterpret_cast<const float4*>(wsm + (t * Cin + g * 8) * CO);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int q = 0; q < 2 * CO; ++q) {       // 8*CO weights = 2*CO float4
+        const float4 ww = wt[q];
+        const float wl[4] = {ww.x, ww.y, ww.z, ww.w};
 #pragma unroll
-        for (int c = 0; c < CO; ++c) v[j] += d[c] * wt[j * CO + c];
+        for (int e = 0; e < 4; ++e) v[(4 * q + e) / CO] += d[(4 * q + e) % CO] * wl[e];
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= scale;
     if (mask) {
-      const uint4 m = __ldg(reinterpret_cast<const uint4*>(mask + p * Cin) + g);
+      const uint4 m = __ldg(reinterpret_cast<const uint4*>(mask + (int64_t)p * Cin) + g);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = unpack_bf16x2((&m.x)[j]);
@@ -416,7 +429,7 @@ __global__ void __launch_bounds__(kThreads) conv_skinny_kxk_dgrad_kernel(
         if (!(f.y > 0.f)) v[2 * j + 1] = 0.f;
       }
     }
-    reinterpret_cast<uint4*>(dx + p * Cin)[g] =
+    reinterpret_cast<uint4*>(dx + (int64_t)p * Cin)[g] =
         make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
 }
@@ -432,20 +445,19 @@ __global__ void __launch_bounds__(kThreads) conv_skinny_kxk_wgrad_partial_kernel
   const int g = threadIdx.x % C8, rl = threadIdx.x / C8;
   const int t = blockIdx.y;
   const int dyo = t / kw - kh / 2, dxo = t % kw - kw / 2;
-  const int64_t npix = (int64_t)N * H * W;
+  const int npix = N * H * W;              // < 2^31 / Cin (host)
   float acc[8][CO];
 #pragma unroll
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
-  for (int64_t p = (int64_t)blockIdx.x * R + rl; p < npix; p += (int64_t)gridDim.x * R) {
-    const int xw = (int)(p % W), yh = (int)((p / W) % H);
-    const int yy = yh + dyo, xx = xw + dxo;
-    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (p + (int64_t)dyo * W + dxo) * Cin) + g);
+  for (int p = blockIdx.x * R + rl; p < npix; p += gridDim.x * R) {
+    const int xw = p % W, yh = (p / W) % H;
+    if ((unsigned)(yh + dyo) >= (unsigned)H || (unsigned)(xw + dxo) >= (unsigned)W) continue;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (int64_t)(p + dyo * W + dxo) * Cin) + g);
     float d[CO];
 #pragma unroll
-    for (int c = 0; c < CO; ++c) d[c] = bf2f(dy[p * CO + c]);
+    for (int c = 0; c < CO; ++c) d[c] = bf2f(dy[(int64_t)p * CO + c]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = unpack_bf16x2((&v.x)[j]);
@@ -699,7 +711,7 @@ int segk_conv2d_small_fwd(segk_ctx* ctx, const void* x, int x_dtype, const float
     return SEGK_OK;
   }
   if (x_dtype == 0 && (kh & 1) && (kw & 1) && kh * kw <= 25 && Cin % 8 == 0 && (Cout == 2 || Cout == 4) &&
-      (size_t)kh * kw * Cin * Cout * sizeof(float) <= 48 * 1024) {
+      (size_t)kh * kw * Cin * Cout * sizeof(float) <= 48 * 1024 && npix * Cin < ((int64_t)1 << 31)) {
     const int grid = sgrid(ctx, npix, 8);
     const size_t sm = sizeof(float) * (size_t)kh * kw * Cin * Cout;
     if (Cout == 2)
@@ -723,8 +735,8 @@ int segk_conv2d_small_dgrad(segk_ctx* ctx, const void* dy, const float* w, const
   const int64_t npix = (int64_t)N * H * W;
   if (kh * kw > 1) {
     SEGK_REQUIRE(ctx, (kh & 1) && (kw & 1) && kh * kw <= 25 && Cin % 8 == 0 && (Cout == 2 || Cout == 4) &&
-                          (size_t)kh * kw * Cin * Cout * sizeof(float) <= 48 * 1024,
-                 "conv_small_dgrad: k x k needs odd k <= 5, Cin %% 8 == 0, Cout in {2,4} (got %dx%d %d -> %d)", kh, kw, Cin, Cout);
+                          (size_t)kh * kw * Cin * Cout * sizeof(float) <= 48 * 1024 && npix * Cin < ((int64_t)1 << 31),
+                 "conv_small_dgrad: k x k needs odd k <= 5, Cin %% 8 == 0, Cout in {2,4}, < 2^31 elements (got %dx%d %d -> %d)", kh, kw, Cin, Cout);
     const int g = sgrid(ctx, npix * (Cin / 8), 8);
     const size_t sm = sizeof(float) * (size_t)kh * kw * Cin * Cout;
     if (Cout == 2)
@@ -792,7 +804,7 @@ int segk_conv2d_small_wgrad(segk_ctx* ctx, const void* x, int x_dtype, const voi
     sum_partials_rows_kernel<<<ceil_div(n, kThreads), kThreads, 0, st>>>((const float*)ctx->ws3, dw, (int)gx, n);
     SEGK_LAUNCHED(ctx, "conv_skinny_wgrad_sum");
   } else if (x_dtype == 0 && kh * kw > 1 && (kh & 1) && (kw & 1) && kh * kw <= 25 && (Cout == 2 || Cout == 4) &&
-             Cin % 8 == 0 && kThreads % (Cin / 8) == 0 && K > kTinyKMax) {
+             Cin % 8 == 0 && kThreads % (Cin / 8) == 0 && K > kTinyKMax && npix * Cin < ((int64_t)1 << 31)) {
     // k x k head: two-stage reduction over pixels, one grid row per tap
     const int R = kThreads / (Cin / 8);
     const int T = kh * kw;
