@@ -132,12 +132,14 @@ int segk_conv2d_first_wgrad(segk_ctx* ctx, const void* x, int x_dtype, const voi
 /* ---- small-channel layers on CUDA cores (conv1_1 Cin=3/4, conv8 Cout=2, conv_t1 Cin=2,
  *      conv_t3 Cout=2) ----------------------------------------------------------------- */
 /* conv_layer forward for ragged channel counts.  x_dtype: 0 = bf16, 2 = u8 (raw image,
- * FCN.py:312).  w fp32 HWIO, output bf16.  Supported: K = kh*kw*Cin <= 64 (any Cout), or
- * 1x1 with Cout in {2,4,8} and Cin % 8 == 0 (this one also with SEGK_EPI_OUT_F32: fp32 logits). */
+ * FCN.py:312).  w fp32 HWIO, output bf16.  Supported: K = kh*kw*Cin <= 64 (any Cout); 1x1 with
+ * Cout in {2,4,8} and Cin % 8 == 0; odd k <= 5 with Cout in {2,4} and Cin % 8 == 0 (the 3x3 head
+ * of the reference's SegNet, SegNet.py:80) -- the last two also with SEGK_EPI_OUT_F32: fp32 logits. */
 int segk_conv2d_small_fwd(segk_ctx* ctx, const void* x, int x_dtype, const float* w,
                           const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
                           int kh, int kw, unsigned flags, void* stream);
-/* 1x1, Cout in {2,4,8}: dx = ((dy W^T) masked by relu_mask > 0) * scale */
+/* 1x1 with Cout in {2,4,8}, or odd k <= 5 with Cout in {2,4}: dx = ((dy * rot180(W)^T) masked by
+ * relu_mask > 0) * scale */
 int segk_conv2d_small_dgrad(segk_ctx* ctx, const void* dy, const float* w, const void* relu_mask,
                             void* dx, float scale, int N, int H, int W, int Cin, int Cout,
                             int kh, int kw, void* stream);
