@@ -335,52 +335,80 @@ __global__ void __launch_bounds__(kThreads) conv_skinny_wgrad_partial_kernel(
 // ---- skinny k x k conv (odd k, SAME) with Cout in {2,4}: the 3x3 64 -> num_classes head of the reference's
 // SegNet (`SegNet.py:80`, Conv2D_Layer default 3x3) at full resolution.  Same three forms as the 1x1 head
 // above with a tap loop; x is re-read kh*kw times through L1/L2, DRAM traffic stays one pass.
+// Shared-memory weight layout of the two kernels below: [tap][8-channel group][8*CO + 4 pad] floats.  A
+// quarter-warp reads the 8 groups of one pixel at once; without the pad their 16-byte loads sit 64 B apart
+// and collide four ways on the banks.
+template <int CO>
+__device__ __forceinline__ void load_skinny_weights(float* wsm, const float* __restrict__ w, int taps, int Cin) {
+  constexpr int kRow = 8 * CO + 4;
+  const int C8 = Cin >> 3;
+  for (int i = threadIdx.x; i < taps * Cin * CO; i += blockDim.x) {
+    const int c = i % (8 * CO), gg = (i / (8 * CO)) % C8, t = i / (8 * CO * C8);
+    wsm[(t * C8 + gg) * kRow + c] = w[i];
+  }
+}
+
+// forward: 8 lanes per pixel, one 16-byte piece of its Cin*2-byte row at a time (a warp reads
+// contiguous memory; one thread per pixel made every load touch 32 cache lines), partial sums over the
+// lane's 8 channels, three shuffle steps to combine.
 template <int CO>
 __global__ void __launch_bounds__(kThreads) conv_skinny_kxk_fwd_kernel(
     const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, void* __restrict__ y,
     int N, int H, int W, int Cin, int kh, int kw, int relu, int out_f32) {
-  extern __shared__ float wsm[];   // [kh*kw][Cin][CO]
-  for (int i = threadIdx.x; i < kh * kw * Cin * CO; i += blockDim.x) wsm[i] = w[i];
+  extern __shared__ float wsm[];
+  constexpr int kRow = 8 * CO + 4;
+  load_skinny_weights<CO>(wsm, w, kh * kw, Cin);
   __syncthreads();
-  const int npix = N * H * W;      // host guarantees < 2^31 / Cin: 32-bit index arithmetic throughout
+  const int C8 = Cin >> 3;                       // host: 8 % C8 == 0 or C8 % 8 == 0 handled by the loop below
+  const int npix = N * H * W;                    // < 2^31 / Cin (host): 32-bit index arithmetic
   const int ph = kh / 2, pw = kw / 2;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
-    const int xw = p % W, yh = (p / W) % H;
+  const int lane8 = threadIdx.x & 7;
+  const int ppb = blockDim.x >> 3;               // pixels per block pass
+  for (int p0 = blockIdx.x * ppb; p0 < npix; p0 += gridDim.x * ppb) {
+    const int p = p0 + (threadIdx.x >> 3);
+    const bool live = p < npix;
+    const int xw = live ? p % W : 0, yh = live ? (p / W) % H : 0;
     float acc[CO];
 #pragma unroll
-    for (int c = 0; c < CO; ++c) acc[c] = bias ? bias[c] : 0.f;
-    for (int t = 0; t < kh * kw; ++t) {
-      const int dyo = t / kw - ph, dxo = t % kw - pw;
-      if ((unsigned)(yh + dyo) >= (unsigned)H || (unsigned)(xw + dxo) >= (unsigned)W) continue;
-      const uint4* xp = reinterpret_cast<const uint4*>(x + (int64_t)(p + dyo * W + dxo) * Cin);
-      const float* wt = wsm + t * Cin * CO;
-      for (int g = 0; g < Cin / 8; ++g) {
-        const uint4 v = __ldg(xp + g);
+    for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+    if (live) {
+      for (int t = 0; t < kh * kw; ++t) {
+        const int dyo = t / kw - ph, dxo = t % kw - pw;
+        if ((unsigned)(yh + dyo) >= (unsigned)H || (unsigned)(xw + dxo) >= (unsigned)W) continue;
+        const uint4* xp = reinterpret_cast<const uint4*>(x + (int64_t)(p + dyo * W + dxo) * Cin);
+        for (int g = lane8; g < C8; g += 8) {
+          const uint4 v = __ldg(xp + g);
+          const float4* wt = reinterpret_cast<const float4*>(wsm + (t * C8 + g) * kRow);
+          float xv[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16x2((&v.x)[j]);
-          // the 2*CO weights of this channel pair are contiguous: vector shared-memory loads
-          float wv[2 * CO];
-          if (CO == 2) {
-            const float4 q = *reinterpret_cast<const float4*>(wt + (g * 8 + 2 * j) * CO);
-            wv[0] = q.x; wv[1] = q.y; wv[2] = q.z; wv[3] = q.w;
-          } else {
-#pragma unroll
-            for (int c = 0; c < 2 * CO; c += 4) {
-              const float4 q = *reinterpret_cast<const float4*>(wt + (g * 8 + 2 * j) * CO + c);
-              wv[c] = q.x; wv[c + 1] = q.y; wv[c + 2] = q.z; wv[c + 3] = q.w;
-            }
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2((&v.x)[j]);
+            xv[2 * j] = f.x; xv[2 * j + 1] = f.y;
           }
 #pragma unroll
-          for (int c = 0; c < CO; ++c) acc[c] += f.x * wv[c] + f.y * wv[CO + c];
+          for (int q = 0; q < 2 * CO; ++q) {       // 8*CO weights = 2*CO float4
+            const float4 ww = wt[q];
+            const float wl[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[(4 * q + e) % CO] += xv[(4 * q + e) / CO] * wl[e];
+          }
         }
       }
     }
 #pragma unroll
     for (int c = 0; c < CO; ++c) {
-      const float v = relu ? fmaxf(acc[c], 0.f) : acc[c];
-      if (out_f32) reinterpret_cast<float*>(y)[(int64_t)p * CO + c] = v;
-      else reinterpret_cast<bf16*>(y)[(int64_t)p * CO + c] = f2bf(v);
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
+    }
+    if (live && lane8 == 0) {
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        float v = acc[c] + (bias ? bias[c] : 0.f);
+        if (relu) v = fmaxf(v, 0.f);
+        if (out_f32) reinterpret_cast<float*>(y)[(int64_t)p * CO + c] = v;
+        else reinterpret_cast<bf16*>(y)[(int64_t)p * CO + c] = f2bf(v);
+      }
     }
   }
 }
@@ -390,8 +418,9 @@ template <int CO>
 __global__ void __launch_bounds__(kThreads) conv_skinny_kxk_dgrad_kernel(
     const bf16* __restrict__ dy, const float* __restrict__ w, const bf16* __restrict__ mask, bf16* __restrict__ dx,
     int N, int H, int W, int Cin, int kh, int kw, float scale) {
-  extern __shared__ float wsm[];   // [kh*kw][Cin][CO]
-  for (int i = threadIdx.x; i < kh * kw * Cin * CO; i += blockDim.x) wsm[i] = w[i];
+  extern __shared__ float wsm[];
+  constexpr int kRow = 8 * CO + 4;
+  load_skinny_weights<CO>(wsm, w, kh * kw, Cin);
   __syncthreads();
   const int C8 = Cin >> 3;
   const int total = N * H * W * C8;        // < 2^31 (host)
@@ -409,9 +438,9 @@ __global__ void __launch_bounds__(kThreads) conv_skinny_kxk_dgrad_kernel(
       float d[CO];
 #pragma unroll
       for (int c = 0; c < CO; ++c) d[c] = bf2f(dp[c]);
-      const float4* wt = reinterpret_cast<const float4*>(wsm + (t * Cin + g * 8) * CO);
+      const float4* wt = reinterpret_cast<const float4*>(wsm + (t * C8 + g) * kRow);
 #pragma unroll
-      for (int q = 0; q < 2 * CO; ++q) {       // 8*CO weights = 2*CO float4
+      for (int q = 0; q < 2 * CO; ++q) {
         const float4 ww = wt[q];
         const float wl[4] = {ww.x, ww.y, ww.z, ww.w};
 #pragma unroll
@@ -711,9 +740,9 @@ int segk_conv2d_small_fwd(segk_ctx* ctx, const void* x, int x_dtype, const float
     return SEGK_OK;
   }
   if (x_dtype == 0 && (kh & 1) && (kw & 1) && kh * kw <= 25 && Cin % 8 == 0 && (Cout == 2 || Cout == 4) &&
-      (size_t)kh * kw * Cin * Cout * sizeof(float) <= 48 * 1024 && npix * Cin < ((int64_t)1 << 31)) {
-    const int grid = sgrid(ctx, npix, 8);
-    const size_t sm = sizeof(float) * (size_t)kh * kw * Cin * Cout;
+      (size_t)kh * kw * (Cin / 8) * (8 * Cout + 4) * sizeof(float) <= 48 * 1024 && npix * Cin < ((int64_t)1 << 31)) {
+    const int grid = sgrid(ctx, npix * 8, 8);      // 8 lanes per pixel
+    const size_t sm = sizeof(float) * (size_t)kh * kw * (Cin / 8) * (8 * Cout + 4);
     if (Cout == 2)
       conv_skinny_kxk_fwd_kernel<2><<<grid, kThreads, sm, st>>>((const bf16*)x, w, bias, y, N, H, W, Cin, kh, kw, relu, out_f32);
     else
@@ -735,10 +764,10 @@ int segk_conv2d_small_dgrad(segk_ctx* ctx, const void* dy, const float* w, const
   const int64_t npix = (int64_t)N * H * W;
   if (kh * kw > 1) {
     SEGK_REQUIRE(ctx, (kh & 1) && (kw & 1) && kh * kw <= 25 && Cin % 8 == 0 && (Cout == 2 || Cout == 4) &&
-                          (size_t)kh * kw * Cin * Cout * sizeof(float) <= 48 * 1024 && npix * Cin < ((int64_t)1 << 31),
+                          (size_t)kh * kw * (Cin / 8) * (8 * Cout + 4) * sizeof(float) <= 48 * 1024 && npix * Cin < ((int64_t)1 << 31),
                  "conv_small_dgrad: k x k needs odd k <= 5, Cin %% 8 == 0, Cout in {2,4}, < 2^31 elements (got %dx%d %d -> %d)", kh, kw, Cin, Cout);
     const int g = sgrid(ctx, npix * (Cin / 8), 8);
-    const size_t sm = sizeof(float) * (size_t)kh * kw * Cin * Cout;
+    const size_t sm = sizeof(float) * (size_t)kh * kw * (Cin / 8) * (8 * Cout + 4);
     if (Cout == 2)
       conv_skinny_kxk_dgrad_kernel<2><<<g, kThreads, sm, st>>>((const bf16*)dy, w, (const bf16*)relu_mask, (bf16*)dx, N, H, W, Cin, kh, kw, scale);
     else

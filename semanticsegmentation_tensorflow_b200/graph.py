@@ -244,7 +244,8 @@ class GraphNet:
             return "im2col"
         if n.k == 1 and n.cout in (2, 4, 8) and cin % 8 == 0:
             return "small"
-        if n.k in (3, 5) and n.cout in (2, 4) and cin % 8 == 0 and 256 % (cin // 8) == 0 and n.k * n.k * cin * n.cout * 4 <= 48 * 1024:
+        if (n.k in (3, 5) and n.cout in (2, 4) and cin % 8 == 0 and 256 % (cin // 8) == 0
+                and n.k * n.k * (cin // 8) * (8 * n.cout + 4) * 4 <= 48 * 1024):
             return "small"        # k x k head to num_classes (SegNet.py:80)
         raise ValueError(f"{n.name}: unsupported conv {n.k}x{n.k} {cin}->{n.cout} (no fallback)")
 
