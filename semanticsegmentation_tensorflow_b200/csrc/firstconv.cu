@@ -364,14 +364,14 @@ first_wgrad_kernel(const __grid_constant__ FirstMaps maps, const FirstParams p) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const bool has_work = (int)blockIdx.x < total_tiles;
+  // (the host launches at most one CTA per tile, so every CTA owns at least one tile)
 
   if (warp < 4) {
     const int row = threadIdx.x;
     Pipe ps;
     uint32_t cur[9 * CIN], nxt[9 * CIN];
     bool cur_in = false, nxt_in = false;
-    if ((int)blockIdx.x < total_tiles) cur_in = load_patch<XT, CIN>(p, row, blockIdx.x, cur);
+    cur_in = load_patch<XT, CIN>(p, row, blockIdx.x, cur);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int next = tile + gridDim.x;
       if (next < total_tiles) nxt_in = load_patch<XT, CIN>(p, row, next, nxt);
@@ -387,21 +387,14 @@ first_wgrad_kernel(const __grid_constant__ FirstMaps maps, const FirstParams p) 
     // ---- epilogue: the CTA's partial sums, patch columns 0..K (K = the ones column = bias gradient) ----
     const int q = warp;                 // TMEM lane quarter
     float* dst = p.ws + ((int64_t)blockIdx.x * 64 + row) * BLOCK_N;
-    if (has_work) {
-      mbar_wait(tfull_bar, 0);
-      tc_fence_after();
-    }
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
     if (q < 2) {                        // patch columns live in TMEM lanes 0..63 (warp-uniform branch)
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t r[32];
-        if (has_work) {
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = 0;
-        }
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
         if (row <= PT::K) {
           float4* d4 = reinterpret_cast<float4*>(dst + c0);
 #pragma unroll

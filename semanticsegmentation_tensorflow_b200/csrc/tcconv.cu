@@ -1221,7 +1221,6 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
   // (tools/time_n64.py, B=32 160x576): 64 -> 64 forward 228 vs 297 us, its dgrad 345 vs 372 us; with two
   // channel tiles (64 -> 128) it is a wash (116 vs 112 us), so the tap-wise slab keeps those.  slab3 = 2 forces it.
   const bool fused3 = Ck == 64 && (Cn / 64) <= ctx->sm_count && (ctx->slab3 == 2 || (ctx->slab3 == 1 && Cn == 64));
-  (void)mask;
   const int block_n = fused3 ? 64 : pick_block_n(ctx, Cn);
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));
