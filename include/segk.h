@@ -309,6 +309,16 @@ int segk_bias_grad(segk_ctx* ctx, const void* dy, int dy_is_f32, float* db, int6
  * barriers on the same stream (inputs complete on all ranks before; all shares stored after). */
 int segk_allreduce_f32(segk_ctx* ctx, void* multicast_ptr, const uint64_t* peer_ptrs, int64_t offset,
                        int64_t n, int rank, int world, void* stream);
+/* Exchange fused with the optimizer (gradient all-reduce + tf.train.AdamOptimizer's ApplyAdam, FCN.py:338-340,
+ * in ONE kernel over NVLS): for its 1/world share of [offset, offset + n) rank r reads the gradient sum
+ * over all ranks through the multicast address of the gradient arena, updates its local m / v and the
+ * parameter values (TF formula, lr_t = lr*sqrt(1-b2^t)/(1-b1^t)), and multicasts the new parameters into
+ * every rank's parameter arena.  Both arenas symmetric; param_local = this rank's own mapping of the
+ * parameter arena.  m / v are only maintained for the rank's own shares.  Same barrier contract. */
+int segk_allreduce_adam_f32(segk_ctx* ctx, const void* grad_multicast_ptr, void* param_multicast_ptr,
+                            const float* param_local, float* m, float* v, int64_t offset, int64_t n,
+                            int rank, int world, float lr_t, float beta1, float beta2, float eps,
+                            void* stream);
 
 #ifdef __cplusplus
 }

@@ -89,18 +89,50 @@ class SymmetricAllReduce(BucketedAllReduce):
     provides the allocation, the rendezvous and the cross-rank stream barriers (plumbing); launches are
     stream-ordered on the caller's current stream, so `work` is None."""
 
-    def __init__(self, net, handle, buckets, group=None):
+    def __init__(self, net, handle, buckets, group=None, param_handle=None):
         super().__init__(net.vars.g, buckets, group)
+        self.net = net
         self.ops = net.ops
         self.hdl = handle
         self.rank = dist.get_rank(group)
         self.mc = int(getattr(handle, "multicast_ptr", 0) or 0)        # 0: no multicast on this fabric
         # measured on idle B200s (tools/time_exchange.py, 537 MB): 2 GPUs peer 0.81 ms, multimem 1.34, NCCL 0.99
-        want = os.environ.get("SEGK_EXCHANGE", "").lower()
-        if want == "peer" or (want != "multimem" and self.world <= 2):
+        want = os.environ.get("SEGK_EXCHANGE", "").lower()      # "", fused, multimem, peer (nccl is handled by try_create)
+        if want == "peer":
             self.mc = 0
         self.peers = (ctypes.c_uint64 * self.world)(*[int(p) for p in handle.buffer_ptrs])
         self.kind = "nvls-multimem" if self.mc else "nvlink-peer"
+        # fused exchange + Adam (segk_allreduce_adam_f32): needs the parameter arena in symmetric memory too
+        self.p_mc = int(getattr(param_handle, "multicast_ptr", 0) or 0) if param_handle is not None else 0
+        self.fused = bool(self.mc and self.p_mc) and want != "multimem"
+        self._adam = None
+        if self.fused:
+            self.kind = "nvls-multimem fused with Adam (sharded optimizer state)"
+
+    def set_adam(self, m, v, lr_t, beta1, beta2, eps):
+        """Arms the fused path for this step (TrainStep calls it before backward)."""
+        self._adam = (m, v, float(lr_t), float(beta1), float(beta2), float(eps))
+
+    def share(self, lo, hi):
+        """[a, b): the slice of arena range [lo, hi) this rank owns in the fused path."""
+        n4 = (hi - lo) // 4
+        per = -(-n4 // self.world)
+        a = lo + 4 * per * self.rank
+        return a, max(a, min(a + 4 * per, hi))
+
+    def gather_optimizer_state(self):
+        """Fused path: every rank only maintains Adam's m / v for its own shares.  Rebuilds the full slots on
+        every rank (e.g. before saving a checkpoint): foreign shares are zeroed, then a SUM all-reduce."""
+        V = self.net.vars
+        if not self.fused or V.m is None:
+            return
+        for t in (V.m, V.v):
+            keep = torch.zeros_like(t)
+            for lo, hi, _ in self.buckets:
+                a, b = self.share(lo, hi)
+                keep[a:b] = t[a:b]
+            dist.all_reduce(keep, op=dist.ReduceOp.SUM, group=self.group)
+            t.copy_(keep)
 
     @classmethod
     def try_create(cls, net, group=None):
@@ -116,26 +148,44 @@ class SymmetricAllReduce(BucketedAllReduce):
             g_old = net.vars.g
             g = symm.empty(g_old.numel(), dtype=torch.float32, device=g_old.device)
             g.zero_()
-            hdl = symm.rendezvous(g, group if group is not None else dist.group.WORLD)
+            grp = group if group is not None else dist.group.WORLD
+            hdl = symm.rendezvous(g, grp)
+            # the parameter arena too, so that the exchange can be fused with the optimizer update
+            phdl = None
+            mode = os.environ.get("SEGK_EXCHANGE", "").lower()
+            if mode in ("", "fused"):        # default: measured best at 2 and 8 GPUs (profiles/r1d_scaling.md)
+                p_new = symm.empty(net.vars.p.numel(), dtype=torch.float32, device=g_old.device)
+                p_new.copy_(net.vars.p)
+                phdl = symm.rendezvous(p_new, grp)
             ok = torch.tensor([1], device=g_old.device)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)         # every rank got here
             net.vars.g = g
+            if phdl is not None:
+                net.vars.p = p_new
             if hasattr(net, "nodes"):
                 names = [n.name for n in net.nodes if n.kind in ("conv", "deconv")]
                 buckets = P.gradient_buckets_even(net.vars.slots, names)
             else:
                 buckets = P.gradient_buckets(net.vars.slots)
-            return cls(net, hdl, buckets, group)
+            return cls(net, hdl, buckets, group, phdl)
         except Exception as e:       # noqa: BLE001 -- any failure here means "no symmetric memory on this box"
             print(f"segk: symmetric-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
             return None
 
     def _launch(self, b):
         lo, hi, _ = self.buckets[b]
-        # all ranks' gradients of this bucket are complete (the caller's stream waited for its producers)
+        stream = torch.cuda.current_stream().cuda_stream
+        # all ranks' gradients of this bucket are complete (the caller's stream waited for its producers),
+        # and no rank still reads the bucket's parameters in this step
         self.hdl.barrier(channel=0, timeout_ms=60000)
-        self.ops.call("segk_allreduce_f32", self.mc, ctypes.addressof(self.peers), lo, hi - lo, self.rank, self.world,
-                      torch.cuda.current_stream().cuda_stream)
+        if self.fused and self._adam is not None:
+            m, v, lr_t, b1, b2, eps = self._adam
+            V = self.net.vars
+            self.ops.call("segk_allreduce_adam_f32", self.mc, self.p_mc, V.p.data_ptr(), m.data_ptr(), v.data_ptr(), lo,
+                          hi - lo, self.rank, self.world, lr_t, b1, b2, eps, stream)
+        else:
+            self.ops.call("segk_allreduce_f32", self.mc, ctypes.addressof(self.peers), lo, hi - lo, self.rank, self.world,
+                          stream)
         self.hdl.barrier(channel=0, timeout_ms=60000)                     # every share has been written everywhere
         self._works.append((lo, hi, None))
 

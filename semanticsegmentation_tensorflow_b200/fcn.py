@@ -552,6 +552,14 @@ class TrainStep:
             self.allreduce.begin_step()
             slots = net.vars.slots
             fin = self._finalize_stream(net)
+            # exchange fused with the optimizer (dp.SymmetricAllReduce over NVLS): the collective kernel itself
+            # applies Adam to this rank's share and multicasts the new parameters; only the repack is left
+            fused = bool(getattr(self.allreduce, "fused", False)) and isinstance(opt, AdamOptimizer)
+            if fused:
+                self.allreduce.set_adam(net.vars.m, net.vars.v, P.adam_lr_t(opt.lr, opt.t, opt.beta1, opt.beta2),
+                                        opt.beta1, opt.beta2, opt.eps)
+            elif hasattr(self.allreduce, "_adam"):
+                self.allreduce._adam = None
 
             def finalize(lo, hi, work):
                 names = {n.split("/")[0] for n, s in slots.items() if lo <= s.offset < hi}
@@ -559,7 +567,8 @@ class TrainStep:
                 def go():
                     if work is not None:
                         work.wait()               # the side stream waits for the collective, not the main one
-                    opt.apply(net, lo, hi)
+                    if not fused:
+                        opt.apply(net, lo, hi)
                     net.vars.repack(net.ops, names)
 
                 fin.run(go)

@@ -23,7 +23,8 @@ lo, hi = P.shard_batch(GB, world, rank)
 xs, ys = torch.as_tensor(x[lo:hi]).to(dev), torch.as_tensor(y[lo:hi]).to(dev)
 net = FCN(xs, 1.0, 2, variables=variables, fc=FC, world_size=world)
 MODE = os.environ.get("DP_EXCHANGE", "nccl")
-if MODE == "symmetric":        # our NVLink kernel on a symmetric-memory gradient arena
+if MODE in ("symmetric", "fused"):   # our NVLink kernels on symmetric-memory arenas; fused = exchange + Adam in one kernel
+    os.environ["SEGK_EXCHANGE"] = "fused" if MODE == "fused" else "multimem"
     ar = SymmetricAllReduce.try_create(net)
     if ar is None:
         if rank == 0:
@@ -52,6 +53,11 @@ for _ in range(3):
     dist.all_reduce(t)                     # mean over ranks of per-shard mean losses = global mean loss
     losses.append(float(t) / world)
 torch.cuda.synchronize()
+if getattr(ar, "fused", False):
+    ar.gather_optimizer_state()           # every rank holds the full Adam slots again
+    m0 = net.vars.m.clone()
+    dist.broadcast(m0, 0)
+    assert float((net.vars.m - m0).abs().max()) == 0.0
 # replicas identical: max |p - p_rank0| == 0
 p0 = net.vars.p.clone()
 dist.broadcast(p0, 0)

@@ -14,14 +14,16 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("exchange", ["nccl", "symmetric"])
+@pytest.mark.parametrize("exchange", ["nccl", "symmetric", "fused"])
 def test_two_gpu_training_matches_single_gpu(exchange):
-    """exchange = nccl: bucketed ncclAllReduce; symmetric: segk_allreduce_f32 (our NVLS / peer kernel) on a
-    symmetric-memory gradient arena."""
+    """exchange = nccl: bucketed ncclAllReduce; symmetric: segk_allreduce_f32 (our NVLS kernel) on a
+    symmetric-memory gradient arena; fused: segk_allreduce_adam_f32 (exchange + Adam + parameter broadcast in
+    one NVLS kernel, optimizer state sharded over the ranks)."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29533" if exchange == "nccl" else "29534", os.path.join(ROOT, "tests", "dp_worker.py")]
+           "127.0.0.1", "--master-port", {"nccl": "29533", "symmetric": "29534", "fused": "29535"}[exchange],
+           os.path.join(ROOT, "tests", "dp_worker.py")]
     env = dict(os.environ, DP_EXCHANGE=exchange)
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:]
@@ -29,7 +31,7 @@ def test_two_gpu_training_matches_single_gpu(exchange):
     out = json.loads(line[len("DPRESULT "):])
     if "skipped" in out:
         pytest.skip(out["skipped"])
-    assert (out["exchange"] == "nccl") == (exchange == "nccl"), out
+    assert (out["exchange"] == "nccl") == (exchange == "nccl") and ("fused" in out["exchange"]) == (exchange == "fused"), out
     assert out["replica_max_diff"] == 0.0                      # every rank applied the same reduced gradient
     # the all-reduced gradient equals the single-GPU gradient of the global batch (sum over shards of the
     # 1/(world*N*H*W)-scaled loss gradients): direction and norm, up to bf16 noise
