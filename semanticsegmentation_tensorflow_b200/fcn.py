@@ -516,6 +516,12 @@ class TrainStep:
                 buckets = P.gradient_buckets(net.vars.slots)
             self.local = LocalBuckets(net, opt, buckets)
 
+    def sync_optimizer_state(self):
+        """Data parallel with the fused exchange: optimizer slots are sharded over the ranks; call this (on
+        every rank) before exporting them, e.g. `checkpoint.save_checkpoint`."""
+        if self.allreduce is not None and hasattr(self.allreduce, "gather_optimizer_state"):
+            self.allreduce.gather_optimizer_state()
+
     def _launch_stream(self, net):
         if getattr(self, "_ls", None) is None:
             self._ls = torch.cuda.Stream(net.device)
