@@ -32,7 +32,11 @@ def state_dict(net, opt=None) -> "OrderedDict[str, np.ndarray]":
     return out
 
 
-def save_checkpoint(path, net, opt=None):
+def save_checkpoint(path, net, opt=None, train_step=None):
+    """`train_step`: pass the data-parallel TrainStep so that optimizer slots sharded over the ranks by the
+    fused exchange (dp.SymmetricAllReduce) are gathered first -- a collective: call on every rank."""
+    if train_step is not None:
+        train_step.sync_optimizer_state()
     np.savez(path, **state_dict(net, opt))
 
 
