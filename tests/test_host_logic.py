@@ -160,3 +160,28 @@ def test_generic_even_buckets_cover_the_arena():
     # backward completion order: the completing layers appear in reverse creation order
     idx = [names.index(x[2]) for x in b]
     assert idx == sorted(idx, reverse=True)
+
+
+def test_exchange_shares_partition_every_bucket():
+    """dp.SymmetricAllReduce.share() must be the ownership rule of csrc/exchange.cu: rank r owns float4 units
+    [off4 + r*ceil(n4/world), ...) of a bucket -- a partition of the bucket for every world size."""
+    from semanticsegmentation_tensorflow_b200.dp import BucketedAllReduce, SymmetricAllReduce
+    slots, total = P.arena_layout(P.variable_shapes(3, 2, 4096))
+    buckets = P.gradient_buckets(slots)
+    by_offset = sorted((lo, hi) for lo, hi, _ in buckets)          # (listed in backward-completion order)
+    assert by_offset[0][0] == 0 and by_offset[-1][1] == total
+    assert all(by_offset[i][1] == by_offset[i + 1][0] for i in range(len(by_offset) - 1))
+    for world in (2, 3, 4, 8):
+        for lo, hi, _ in buckets:
+            assert lo % 4 == 0 and (hi - lo) % 4 == 0          # float4 granularity of the kernels
+            cover = []
+            for r in range(world):
+                o = object.__new__(SymmetricAllReduce)
+                o.world, o.rank = world, r
+                a, b = o.share(lo, hi)
+                assert lo <= a <= b <= hi and (a - lo) % 4 == 0
+                cover.append((a, b))
+            assert cover[0][0] == lo and cover[-1][1] == hi
+            assert all(cover[i][1] == cover[i + 1][0] or cover[i + 1][0] == cover[i + 1][1] for i in range(world - 1))
+    ar = BucketedAllReduce(torch.zeros(total), buckets)
+    assert ar.fires_at(buckets[0][2]) and not ar.fires_at("conv1_1")
