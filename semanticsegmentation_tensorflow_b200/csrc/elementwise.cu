@@ -429,7 +429,23 @@ __global__ void __launch_bounds__(kThreads) bias_grad_bf16x8_kernel(const uint4*
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   if (cg < C8 && rl < R) {
-    for (int64_t r = (int64_t)blockIdx.x * R + rl; r < rows; r += (int64_t)gridDim.x * R) {
+    const int64_t step = (int64_t)gridDim.x * R;
+    int64_t r = (int64_t)blockIdx.x * R + rl;
+    // four independent 16-byte loads in flight per thread (one load per iteration ran at 2 TB/s)
+    for (; r + 3 * step < rows; r += 4 * step) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(dy + (r + k * step) * C8 + cg);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2((&u[k].x)[j]);
+          acc[2 * j] += f.x;
+          acc[2 * j + 1] += f.y;
+        }
+    }
+    for (; r < rows; r += step) {
       const uint4 u = __ldg(dy + r * C8 + cg);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
