@@ -480,8 +480,13 @@ __global__ void __launch_bounds__(kThreads) conv_skinny_kxk_wgrad_partial_kernel
   for (int j = 0; j < 8; ++j)
 #pragma unroll
     for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
-  for (int p = blockIdx.x * R + rl; p < npix; p += gridDim.x * R) {
-    const int xw = p % W, yh = (p / W) % H;
+  // (x, y) of the pixel advance incrementally with the grid stride: no division in the loop
+  const int S = gridDim.x * R, sx = S % W, sy = (S / W) % H;
+  int p = blockIdx.x * R + rl;
+  int xw = p % W, yh = (p / W) % H;
+  for (; p < npix; p += S, xw += sx, yh += sy) {
+    if (xw >= W) { xw -= W; ++yh; }
+    while (yh >= H) yh -= H;
     if ((unsigned)(yh + dyo) >= (unsigned)H || (unsigned)(xw + dxo) >= (unsigned)W) continue;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (int64_t)(p + dyo * W + dxo) * Cin) + g);
     float d[CO];
