@@ -660,13 +660,19 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
 //     CTA has the same channel tile: the grid is a multiple of the number of channel tiles).
 // ------------------------------------------------------------------------------------------
 constexpr int kSlab3Bytes = kSlabRows * 128;                 // 24 KB: A rows ky*32 + r never leave the slab
-constexpr int kSlab3WBytes = 9 * 64 * 128;                   // 72 KB
-constexpr int kSlab3Stages = 4;
-constexpr int kSlab3Smem = kSlab3Stages * kSlab3Bytes + kSlab3WBytes + kOutBytes + 1024 + 512;
+template <int KCH>                                            // 64-channel chunks of the input (1 or 2)
+struct Slab3Cfg {
+  static constexpr int kWBytes = KCH * 9 * 64 * 128;         // 72 KB of resident weights per chunk
+  static constexpr int kStages = KCH == 1 ? 4 : 2;           // slab ring (KCH = 2: 144 KB of weights leave room for two)
+  static constexpr int kSmem = kStages * kSlab3Bytes + kWBytes + kOutBytes + 1024 + 512;
+};
 
+template <int KCH>
 __global__ void __launch_bounds__(kThreads, 1)
 slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
   constexpr int kN = 192;
+  constexpr int kSlab3Stages = Slab3Cfg<KCH>::kStages;
+  constexpr int kSlab3WBytes = Slab3Cfg<KCH>::kWBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -700,8 +706,9 @@ slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
   if (warp == 0) {
     if (elect_one()) {
       mbar_arrive_expect_tx(wfull, (uint32_t)kSlab3WBytes);
-      for (int ky = 0; ky < 3; ++ky)     // box (64 k, 64 channels, 3 taps) -> rows kx*64 + c
-        tma_load_3d(&maps.b, wfull, smem_w + ky * (3 * 64 * 128), 0, nt * 64, ky * 3);
+      for (int kc = 0; kc < KCH; ++kc)
+        for (int ky = 0; ky < 3; ++ky)     // box (64 k, 64 channels, 3 taps) -> rows kx*64 + c
+          tma_load_3d(&maps.b, wfull, smem_w + (kc * 3 + ky) * (3 * 64 * 128), kc * 64, nt * 64, ky * 3);
     }
     __syncwarp();
     PipeState pa;
@@ -711,13 +718,15 @@ slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
       r /= p.tiles_w;
       const int y0 = (r % p.tiles_h) * kSlabH;
       const int n = r / p.tiles_h;
-      mbar_wait(&emptyA[pa.stage], pa.phase ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&fullA[pa.stage], (uint32_t)kSlab3Bytes);
-        tma_load_4d(&maps.a[0], &fullA[pa.stage], smem_a + pa.stage * kSlab3Bytes, 0, x0 - 1, y0 - 1, n);
+      for (int kc = 0; kc < KCH; ++kc) {
+        mbar_wait(&emptyA[pa.stage], pa.phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&fullA[pa.stage], (uint32_t)kSlab3Bytes);
+          tma_load_4d(&maps.a[0], &fullA[pa.stage], smem_a + pa.stage * kSlab3Bytes, kc * 64, x0 - 1, y0 - 1, n);
+        }
+        __syncwarp();
+        pa.advance<kSlab3Stages>();
       }
-      __syncwarp();
-      pa.advance<kSlab3Stages>();
     }
   } else if (warp == 1) {
     PipeState pa;
@@ -728,25 +737,27 @@ slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
     mbar_wait(wfull, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-      mbar_wait(&fullA[pa.stage], pa.phase);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t d_addr = tmem_base + (uint32_t)(acc * 256);
-        const uint32_t slab_lo = a_lo0 + (uint32_t)pa.stage * (uint32_t)(kSlab3Bytes >> 4);
+      for (int kc = 0; kc < KCH; ++kc) {
+        mbar_wait(&fullA[pa.stage], pa.phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d_addr = tmem_base + (uint32_t)(acc * 256);
+          const uint32_t slab_lo = a_lo0 + (uint32_t)pa.stage * (uint32_t)(kSlab3Bytes >> 4);
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          const uint32_t a_lo = slab_lo + (uint32_t)(ky * kSlabP) * 8u;            // 32 rows = 4 swizzle atoms down
-          const uint32_t b_lo = w_lo0 + (uint32_t)ky * (uint32_t)((3 * 64 * 128) >> 4);
+          for (int ky = 0; ky < 3; ++ky) {
+            const uint32_t a_lo = slab_lo + (uint32_t)(ky * kSlabP) * 8u;            // 32 rows = 4 swizzle atoms down
+            const uint32_t b_lo = w_lo0 + (uint32_t)(kc * 3 + ky) * (uint32_t)((3 * 64 * 128) >> 4);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_f16(d_addr, kDescKMajor | (uint64_t)(a_lo + 2 * k), kDescKMajor | (uint64_t)(b_lo + 2 * k), idesc,
-                     (ky | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16(d_addr, kDescKMajor | (uint64_t)(a_lo + 2 * k), kDescKMajor | (uint64_t)(b_lo + 2 * k), idesc,
+                       (kc | ky | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&emptyA[pa.stage]);
+          if (kc == KCH - 1) umma_commit(&tfull_bar[acc]);
         }
-        umma_commit(&emptyA[pa.stage]);
-        umma_commit(&tfull_bar[acc]);
+        __syncwarp();
+        pa.advance<kSlab3Stages>();
       }
-      __syncwarp();
-      pa.advance<kSlab3Stages>();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -1220,7 +1231,8 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
   // Ck = 64: kx-fused N = 192 MMAs on resident weights (slab3_kernel), 64-channel output tiles.  Measured
   // (tools/time_n64.py, B=32 160x576): 64 -> 64 forward 228 vs 297 us, its dgrad 345 vs 372 us; with two
   // channel tiles (64 -> 128) it is a wash (116 vs 112 us), so the tap-wise slab keeps those.  slab3 = 2 forces it.
-  const bool fused3 = Ck == 64 && (Cn / 64) <= ctx->sm_count && (ctx->slab3 == 2 || (ctx->slab3 == 1 && Cn == 64));
+  const bool fused3 = (Ck == 64 || Ck == 128) && (Cn / 64) <= ctx->sm_count &&
+                      (ctx->slab3 == 2 || (ctx->slab3 == 1 && Cn == 64));
   const int block_n = fused3 ? 64 : pick_block_n(ctx, Cn);
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));
@@ -1258,7 +1270,8 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
   if (fused3) {
     // every CTA keeps one channel tile: grid = a multiple of n_tiles (total is one by construction)
     const int g3 = total < ctx->sm_count ? total : (ctx->sm_count / p.n_tiles) * p.n_tiles;
-    slab3_kernel<<<g3, kThreads, kSlab3Smem, (cudaStream_t)stream>>>(maps, p);
+    if (Ck == 64) slab3_kernel<1><<<g3, kThreads, Slab3Cfg<1>::kSmem, (cudaStream_t)stream>>>(maps, p);
+    else slab3_kernel<2><<<g3, kThreads, Slab3Cfg<2>::kSmem, (cudaStream_t)stream>>>(maps, p);
     SEGK_LAUNCHED(ctx, "slab3");
     return SEGK_OK;
   }
@@ -1661,7 +1674,8 @@ int segk_tc_init(segk_ctx* ctx) {
   SEGK_SMEM_ATTR(slab_kernel<64>, SlabCfg<64>::kSmemBytes);
   SEGK_SMEM_ATTR(slab_kernel<128>, SlabCfg<128>::kSmemBytes);
   SEGK_SMEM_ATTR(slab_kernel<256>, SlabCfg<256>::kSmemBytes);
-  SEGK_SMEM_ATTR(slab3_kernel, kSlab3Smem);
+  SEGK_SMEM_ATTR(slab3_kernel<1>, Slab3Cfg<1>::kSmem);
+  SEGK_SMEM_ATTR(slab3_kernel<2>, Slab3Cfg<2>::kSmem);
 #undef SEGK_SMEM_ATTR
   if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "tensor-core kernel setup: %s", cudaGetErrorString(e));
   int rc = segk_first_init(ctx);

@@ -42,6 +42,7 @@ def case(N, H, W, ci, co):
     print((N, H, W, ci, co), {k: round(v, 1) for k, v in out.items()})
 
 
+case(32, 160, 576, 128, 64)
 case(32, 160, 576, 64, 64)
 case(32, 80, 288, 64, 128)
 case(32, 80, 288, 128, 128)
