@@ -256,6 +256,9 @@ def run_gpu(args):
         ms_e2e = float(t[0])
     e2e_value = world * B * steps / (ms_e2e / 1e3)
 
+    # ---- data-parallel correctness, outside the timed regions (world > 1) ---------------------------
+    dp_check = dp_correctness(net, train_step, allreduce, feed_dev, world, dev) if world > 1 else None
+
     if rank != 0:
         return
     if args.layers_out:
@@ -292,8 +295,13 @@ def run_gpu(args):
     else:
         achieved = d["work"] / (d["ms"] / 1e3) / 1e9
         peak, unit, bound = peaks["hbm_gbs"], "GB/s", "hbm"
+    burst = peaks["bf16_tflops"] if bound == "tensor" else peaks["hbm_gbs"]
     roofline = {"bound": bound, "kernel": dom, "achieved": achieved, "peak": peak, "unit": unit,
-                "frac": achieved / peak, "traffic": traffic,
+                "frac": achieved / peak, "frac_burst": achieved / burst, "peak_burst": burst,
+                "clock_regime": ("timed inside a %.2f s region at SM clock %s MHz (max %s): `frac` is against the sustained "
+                                 "(power-capped, ~1340 MHz) cuBLAS figure, `frac_burst` against the burst figure" %
+                                 (ms_total / 1e3, clocks.get("sm_mhz") if clocks else None, clocks.get("sm_max_mhz") if clocks else None)),
+                "traffic": traffic,
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, average over the entry point's launches of one step under ncu (profiles/ncu_traffic.json, r1d_ncu_step_tc_launches.md)" if traffic else None,
                 "ncu_tensor_pipe_active_pct": ncu.get("tensor_pipe_active_pct"),
                 "peak_source": peaks["source"] + (" sustained" if bound == "tensor" else ""),
@@ -312,6 +320,12 @@ def run_gpu(args):
                         (v["work"] / (v["ms"] / 1e3) / (1e12 if v["unit"] == "flop" else 1e9)) if v["ms"] > 0 else None}
                 for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
     step_tflops = train_gflop * 1e9 * value / world / 1e12
+
+    secondary = None
+    if world == 1 and not args.no_secondary and args.model == "fcn":
+        del net, train_step
+        torch.cuda.empty_cache()
+        secondary = run_secondary(dev, peaks)
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -339,7 +353,138 @@ def run_gpu(args):
         "cpu_baseline": cpu_baseline,
         "final_loss": final_loss,
     }
+    if dp_check is not None:
+        line["dp_check"] = dp_check
+        line.update({k: dp_check[k] for k in ("replica_max_diff", "fused_vs_nccl_param_rel_err", "grad_checksum",
+                                              "grad_checksum_equal_across_ranks") if k in dp_check})
+    if secondary is not None:
+        line["secondary"] = secondary
     args.emit(json.dumps(line))
+
+
+def dp_correctness(net, train_step, allreduce, feed, world, dev):
+    """One more step from identical state through (a) the exchange the bench ran and (b) plain ncclAllReduce +
+    the local Adam kernel; reports whether the replicas stayed bit-identical and how far the two differ.
+    Runs on every rank (collectives inside); the timed regions are over."""
+    import torch
+    import torch.distributed as dist
+    from semanticsegmentation_tensorflow_b200.dp import BucketedAllReduce
+    from semanticsegmentation_tensorflow_b200.fcn import AdamOptimizer
+    V, opt = net.vars, train_step.opt
+
+    def spread(t):
+        """max over elements of (max over ranks - min over ranks): 0.0 iff bit-identical everywhere."""
+        hi, lo = t.clone(), t.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        return float((hi - lo).abs().max())
+
+    out = {"exchange": getattr(allreduce, "kind", "nccl")}
+    torch.cuda.synchronize()
+    out["replica_max_diff_after_timed_steps"] = spread(V.p)
+    train_step.sync_optimizer_state()                       # full m / v on every rank (fused path shards them)
+    p0, m0, v0 = V.p.clone(), V.m.clone(), V.v.clone()
+    t0, sc0 = opt.t, net.step_count
+
+    def restore():
+        V.p.copy_(p0); V.m.copy_(m0); V.v.copy_(v0)
+        opt.t, net.step_count = t0, sc0
+        V.repack(net.ops)
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    train_step(feed)
+    torch.cuda.synchronize()
+    p_a = V.p.clone()
+    out["replica_max_diff"] = spread(p_a)
+    restore()
+    nccl_step = AdamOptimizer(opt.lr, opt.beta1, opt.beta2, opt.eps)
+    nccl_step.t = t0
+    step_b = nccl_step.minimize(net, allreduce=BucketedAllReduce.for_net(net))
+    step_b(feed)
+    torch.cuda.synchronize()
+    p_b = V.p.clone()
+    out["replica_max_diff_nccl"] = spread(p_b)
+    upd = float((p_b - p0).abs().max())
+    out["fused_vs_nccl_param_rel_err"] = float((p_a - p_b).abs().max()) / max(float(p_b.abs().max()), 1e-30)
+    out["fused_vs_nccl_update_rel_err"] = float((p_a - p_b).abs().max()) / max(upd, 1e-30)
+    # the all-reduced gradient arena must be the same on every rank
+    cs = V.g.double().sum().reshape(1)
+    allcs = [torch.zeros_like(cs) for _ in range(world)]
+    dist.all_gather(allcs, cs)
+    vals = [float(c) for c in allcs]
+    out["grad_checksum"] = vals[0]
+    out["grad_checksum_equal_across_ranks"] = all(v == vals[0] for v in vals)
+    out["grad_replica_max_diff"] = spread(V.g)
+    restore()
+    return out
+
+
+def run_secondary(dev, peaks):
+    """Bounded runs of the other BASELINE configs on the same GPU, after the headline regions: U-Net training
+    (configs[2]), FCN-8s 384x1248 batch-16 inference (configs[3]) and batch-1 160x576 inference latency."""
+    import torch
+    from semanticsegmentation_tensorflow_b200.fcn import FCN, AdamOptimizer
+    from semanticsegmentation_tensorflow_b200.graph import UNet, graph_flops_per_image, unet_nodes
+    out = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gen = torch.Generator().manual_seed(2000)
+
+    def timed(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    # U-Net training, batch 32, host buffers in (e2e), loss out
+    B = BATCH_PER_GPU
+    hx = torch.randint(0, 256, (B, H, W, CIN), dtype=torch.uint8, generator=gen).pin_memory()
+    hy = torch.randint(0, 2, (B, H, W), dtype=torch.uint8, generator=gen).pin_memory()
+    net = UNet(hx.to(dev), NCLS, seed=1234)
+    step = AdamOptimizer(1e-4).minimize(net)
+    feed = {net.image: hx, net.annotation: hy}
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+    ms = timed(lambda: loss_host.copy_(step(feed).reshape(1), non_blocking=True), 10)
+    gf = graph_flops_per_image(unet_nodes(NCLS), H, W, CIN)[1]
+    tf = gf * B / (ms / 1e3) / 1e12
+    out["unet_train_160x576_b32"] = {"images_per_s": B / (ms / 1e3), "ms_per_step": ms, "tflops": tf,
+                                     "frac_of_burst_peak": tf / peaks["bf16_tflops"], "steps": 10,
+                                     "workload": "BASELINE configs[2] at 1 GPU, host buffers in / loss out"}
+    del net, step
+    torch.cuda.empty_cache()
+    # FCN-8s full-resolution inference, batch 16, host images in / road masks out
+    h2, w2, B2 = 384, 1248, 16
+    hx2 = torch.randint(0, 256, (B2, h2, w2, CIN), dtype=torch.uint8, generator=gen).pin_memory()
+    mask_host = torch.empty((B2, h2, w2), dtype=torch.uint8).pin_memory()
+    net = FCN(hx2.to(dev), 1.0, NCLS, init="device", seed=1234)
+    ms = timed(lambda: mask_host.copy_(net.infer(hx2)[1], non_blocking=True), 20)
+    tf = 428.29e9 * B2 / (ms / 1e3) / 1e12
+    out["fcn_infer_384x1248_b16"] = {"images_per_s": B2 / (ms / 1e3), "ms_per_batch": ms, "tflops": tf,
+                                     "frac_of_burst_peak": tf / peaks["bf16_tflops"], "iters": 20,
+                                     "workload": "BASELINE configs[3], host images in / road masks out"}
+    del net
+    torch.cuda.empty_cache()
+    # batch-1 latency at 160x576 (gen_test_output's per-image call, FCN.py:224-231)
+    hx1 = hx[:1].clone().pin_memory()
+    mask1 = torch.empty((1, H, W), dtype=torch.uint8).pin_memory()
+    net = FCN(hx1.to(dev), 1.0, NCLS, init="device", seed=1234)
+    lat = []
+    for i in range(53):
+        e0.record()
+        mask1.copy_(net.infer(hx1)[1], non_blocking=True)
+        e1.record()
+        e1.synchronize()
+        if i >= 3:
+            lat.append(e0.elapsed_time(e1))
+    lat.sort()
+    out["fcn_infer_160x576_b1_latency_ms"] = {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(0.99 * len(lat)))],
+                                              "min": lat[0], "iters": len(lat)}
+    return out
 
 
 def run_infer(args):
@@ -419,6 +564,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the bounded U-Net / inference runs after the headline regions")
     ap.add_argument("--layers-out", default=None, help="write the per-call (per-layer) timing table here")
     ap.add_argument("--model", default="fcn", choices=["fcn", "unet", "segnet"],
                     help="fcn = FCN-8s (BASELINE configs[1], the driver's metric); unet = configs[2]; segnet = the reference's SegNet")

@@ -87,8 +87,9 @@ int segk_conv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void*
 
 /*
  * Conv2DBackpropFilter of conv_layer (FCN.py:340): dw[kh,kw,Cin,Cout] fp32 HWIO
- * (+= when accumulate != 0, else overwritten).  Split-K over pixels with fp32 atomics.
- * BiasAddGrad is segk_bias_grad.  Requires N*H*W tileable into 64-pixel boxes.
+ * (+= when accumulate != 0, else overwritten).  Split-K over pixels: every split stores its partial
+ * sums into its own slice of a context-owned workspace and an ordered reduction adds them
+ * (deterministic, no atomics).  Requires N*H*W tileable into 64-pixel boxes.
  */
 int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H,
                       int W, int Cin, int Cout, int kh, int kw, int accumulate, void* stream);
@@ -225,8 +226,11 @@ int segk_maxpool2x2_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int
                         int C, void* stream);
 /* MaxPoolGrad from the stored index, fused with the ReluGrad of the pooled activation:
  * dx[n,y,x,c] = ((idx==k ? dy : 0) + residual) * [act > 0]  (act may be NULL: no mask; residual,
- * shape of dx or NULL, is a second gradient path into the same tensor, e.g. a skip connection). */
-int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const void* act,
+ * shape of dx or NULL, is a second gradient path into the same tensor, e.g. a skip connection).
+ * act_is_pooled != 0: `act` is the POOLED tensor y [N,H/2,W/2,C] instead of the pre-pool one (residual
+ * must be NULL): at the routed element the pre-pool activation equals the pooled value, so the result is
+ * bit-identical while a quarter of the mask bytes are read. */
+int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const void* act, int act_is_pooled,
                         const void* residual, void* dx, int N, int H, int W, int C, void* stream);
 
 /* tf.nn.dropout (FCN.py:165-167): y = x * keep_mask / keep_prob.  mask (u8 0/1) is used
@@ -236,7 +240,8 @@ int segk_dropout(segk_ctx* ctx, const void* x, void* y, const uint8_t* mask, int
                  float keep_prob, uint64_t seed, void* stream);
 
 /* reduce_mean(softmax_cross_entropy_with_logits) + its gradient + argmax (FCN.py:334,111):
- *   logits f32 [npix,C] (C = 2), labels u8 class ids [npix];
+ *   logits f32 [npix,C] (2 <= C <= 64), labels u8 class ids [npix]; a label >= C is ignored (no loss, zero
+ *   gradient, not counted; the mean still divides by npix);
  *   dlogits (f32, may be NULL) = (softmax - onehot) * grad_scale   (grad_scale =
  *   1/(world*N*H*W)); pred (u8, may be NULL) = argmax, ties -> 0;
  *   loss_sum (f32[2]): [0] = sum over pixels of the per-pixel loss (deterministic two-stage),
@@ -248,10 +253,14 @@ int segk_softmax_xent_fwd_bwd(segk_ctx* ctx, const float* logits, const uint8_t*
                               float* dlogits, uint8_t* pred, float* loss_sum, int64_t* cm,
                               void* workspace, int64_t npix, int C, float grad_scale,
                               void* stream);
-/* tf.nn.softmax + road mask (FCN.py:229,204-206): prob f32 [npix,C] (may be NULL),
- * mask u8 [npix] = prob[...,1] > 0.5 (may be NULL) */
-int segk_softmax_infer(segk_ctx* ctx, const float* logits, float* prob, uint8_t* mask,
+/* tf.nn.softmax + road mask (FCN.py:229,204-206) + tf.argmax (FCN.py:111): prob f32 [npix,C],
+ * mask u8 [npix] = prob[...,1] > 0.5, argmax u8 [npix] = first maximal class (each may be NULL) */
+int segk_softmax_infer(segk_ctx* ctx, const float* logits, float* prob, uint8_t* mask, uint8_t* argmax,
                        int64_t npix, int C, void* stream);
+/* the annotation placeholder as fed by the reference (one-hot [npix,C], FCN.py:313,195-201; dtype 1 = f32,
+ * 2 = u8 / bool) -> u8 class ids [npix] (first maximal channel) for segk_softmax_xent_fwd_bwd */
+int segk_onehot_to_ids(segk_ctx* ctx, const void* onehot, int dtype, uint8_t* ids, int64_t npix, int C,
+                       void* stream);
 /* paste_mask (FCN.py:203-211): the road overlay of gen_test_output — where mask != 0 the RGBA colour
  * ([0,255,0,127] in the reference) is alpha-blended over the u8 image (C = 3 or 4 channels; for
  * C = 4 the alpha channel is blended too, as PIL's Image.paste does), bit-exact with PIL's

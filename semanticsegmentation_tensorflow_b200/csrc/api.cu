@@ -24,16 +24,21 @@ int segk_create(int device, segk_ctx** out) {
     return SEGK_EINVAL;
   }
   ctx->sm_count = prop.multiProcessorCount;
+  int prev_device = -1;
+  cudaGetDevice(&prev_device);        // the kernel attributes below are per device; restored before returning
   cudaSetDevice(device);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
   if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    if (prev_device >= 0 && prev_device != device) cudaSetDevice(prev_device);
     delete ctx;
     return SEGK_ECUDA;
   }
   ctx->encode_tiled = reinterpret_cast<decltype(ctx->encode_tiled)>(fn);
-  if (segk_tc_init(ctx) != SEGK_OK) {
+  const int rc_init = segk_tc_init(ctx);
+  if (prev_device >= 0 && prev_device != device) cudaSetDevice(prev_device);
+  if (rc_init != SEGK_OK) {
     delete ctx;
     return SEGK_ECUDA;
   }
@@ -53,7 +58,6 @@ int segk_destroy(segk_ctx* ctx) {
 const char* segk_last_error(segk_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
 
 int segk_set_tuning(segk_ctx* ctx, const char* key, int value) {
-  if (!ctx) return SEGK_EINVAL;
   if (!ctx || !key) return SEGK_EINVAL;
   if (!strcmp(key, "slab")) ctx->slab_mode = value;
   else if (!strcmp(key, "tma_store")) ctx->tma_store = value;

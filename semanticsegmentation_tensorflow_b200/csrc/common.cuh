@@ -65,6 +65,23 @@ inline int segk_fail(segk_ctx* ctx, int code, const char* fmt, ...) {
       return segk_fail((ctx), SEGK_ECUDA, "%s: %s", (what), cudaGetErrorString(e__));   \
   } while (0)
 
+// Grow-only context scratch: (re)allocates *buf on the CONTEXT's device to at least `need` bytes (the
+// caller's current device is saved and restored; cudaFree synchronises, so nothing still reads the old one).
+inline int segk_grow(segk_ctx* ctx, void** buf, size_t* cur, size_t need, const char* what) {
+  if (*cur >= need) return SEGK_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != ctx->device) cudaSetDevice(ctx->device);
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr;
+  *cur = 0;
+  cudaError_t e = cudaMalloc(buf, need);
+  if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
+  if (e != cudaSuccess) return segk_fail(ctx, SEGK_ENOMEM, "%s: scratch of %zu bytes: %s", what, need, cudaGetErrorString(e));
+  *cur = need;
+  return SEGK_OK;
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

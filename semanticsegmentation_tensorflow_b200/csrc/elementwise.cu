@@ -63,6 +63,52 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const uint4* __re
   }
 }
 
+// MaxPoolGrad from the stored index when the pre-pool tensor is a ReLU output and no second gradient path
+// exists: ReluGrad needs [act > 0] only at the routed element, and there act == the pooled value, so the
+// mask comes from the POOLED activation (1/4 of the bytes): dx = idx == k && pooled > 0 ? dy : 0 -- the
+// same bits as masking with the full-resolution activation (a window whose max is 0 routes nothing).
+__global__ void __launch_bounds__(kThreads) maxpool_bwd_pooled_kernel(const uint4* __restrict__ dy,
+                                                                      const uint2* __restrict__ idx,
+                                                                      const uint4* __restrict__ pooled,
+                                                                      uint4* __restrict__ dx, int N, int H, int W,
+                                                                      int C8) {
+  const int OH = H >> 1, OW = W >> 1;
+  const int64_t total = (int64_t)N * OH * OW * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int c8 = (int)(i % C8);
+    int64_t p = i / C8;
+    int ox = (int)(p % OW);
+    p /= OW;
+    int oy = (int)(p % OH);
+    int n = (int)(p / OH);
+    const int64_t row0 = ((int64_t)(n * H + 2 * oy) * W + 2 * ox) * C8 + c8;
+    const int64_t offs[4] = {row0, row0 + C8, row0 + (int64_t)W * C8, row0 + (int64_t)W * C8 + C8};
+    uint4 g = __ldg(dy + i);
+    const uint2 id = __ldg(idx + i);
+    const uint4 a = __ldg(pooled + i);
+    uint32_t klo[4], khi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = 2 * j;
+      const float2 af = unpack_bf16x2((&a.x)[j]);
+      // a masked element gets an index no window position matches
+      klo[j] = af.x > 0.f ? (((&id.x)[e >> 2] >> (8 * (e & 3))) & 0xffu) : 4u;
+      khi[j] = af.y > 0.f ? (((&id.x)[e >> 2] >> (8 * ((e + 1) & 3))) & 0xffu) : 4u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t gw = (&g.x)[j];
+        o[j] = (klo[j] == (uint32_t)k ? (gw & 0xffffu) : 0u) | (khi[j] == (uint32_t)k ? (gw & 0xffff0000u) : 0u);
+      }
+      dx[offs[k]] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 // MaxPoolGrad from the stored index fused with ReluGrad of the pooled activation.
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const uint4* __restrict__ dy,
                                                                const uint2* __restrict__ idx,
@@ -194,6 +240,7 @@ __global__ void __launch_bounds__(kThreads) xent_kernel(const float* __restrict_
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int lab = labels[i];
+    const bool ignore = lab >= (C == 2 ? 2 : Crt);       // label outside [0, C): no loss, zero gradient
     int am = 0;
     if (C == 2) {
       const float2 l = __ldg(reinterpret_cast<const float2*>(logits) + i);
@@ -201,13 +248,13 @@ __global__ void __launch_bounds__(kThreads) xent_kernel(const float* __restrict_
       const float z0 = l.x - mx, z1 = l.y - mx;
       const float e0 = expf(z0), e1 = expf(z1);
       const float s = e0 + e1;
-      loss += logf(s) - (lab ? z1 : z0);
+      if (!ignore) loss += logf(s) - (lab ? z1 : z0);
       am = l.y > l.x ? 1 : 0;
       if (dlogits) {
         const float inv = 1.f / s;
         float2 d;
-        d.x = (e0 * inv - (lab == 0 ? 1.f : 0.f)) * scale;
-        d.y = (e1 * inv - (lab == 1 ? 1.f : 0.f)) * scale;
+        d.x = ignore ? 0.f : (e0 * inv - (lab == 0 ? 1.f : 0.f)) * scale;
+        d.y = ignore ? 0.f : (e1 * inv - (lab == 1 ? 1.f : 0.f)) * scale;
         reinterpret_cast<float2*>(dlogits)[i] = d;
       }
     } else {
@@ -218,15 +265,15 @@ __global__ void __launch_bounds__(kThreads) xent_kernel(const float* __restrict_
       }
       float s = 0.f;
       for (int c = 0; c < Crt; ++c) s += expf(l[c] - mx);
-      loss += logf(s) - (l[lab] - mx);
+      if (!ignore) loss += logf(s) - (l[lab] - mx);
       if (dlogits) {
         const float inv = 1.f / s;
         for (int c = 0; c < Crt; ++c)
-          dlogits[i * Crt + c] = (expf(l[c] - mx) * inv - (c == lab ? 1.f : 0.f)) * scale;
+          dlogits[i * Crt + c] = ignore ? 0.f : (expf(l[c] - mx) * inv - (c == lab ? 1.f : 0.f)) * scale;
       }
     }
     if (pred) pred[i] = (uint8_t)am;
-    if (C == 2) cnt[(lab & 1) * 2 + am]++;
+    if (C == 2 && !ignore) cnt[lab * 2 + am]++;
   }
   if (cm && C == 2) {
     // warp-aggregated: one shared-memory atomic per warp per bin, one global per block
@@ -257,12 +304,17 @@ __global__ void __launch_bounds__(kThreads) sum_partials_kernel(const float* __r
 __global__ void __launch_bounds__(kThreads) softmax_infer_kernel(const float* __restrict__ logits,
                                                                  float* __restrict__ prob,
                                                                  uint8_t* __restrict__ mask,
+                                                                 uint8_t* __restrict__ argmax,
                                                                  int64_t npix, int C) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix;
        i += (int64_t)gridDim.x * blockDim.x) {
     const float* l = logits + i * C;
     float mx = l[0];
-    for (int c = 1; c < C; ++c) mx = fmaxf(mx, l[c]);
+    int am = 0;
+    for (int c = 1; c < C; ++c)
+      if (l[c] > mx) { mx = l[c]; am = c; }       // strict '>': first index on ties (tf.argmax)
+    if (argmax) argmax[i] = (uint8_t)am;
+    if (!prob && !mask) continue;
     float s = 0.f;
     for (int c = 0; c < C; ++c) s += expf(l[c] - mx);
     const float inv = 1.f / s;
@@ -311,6 +363,23 @@ __global__ void __launch_bounds__(kThreads) confusion_kernel(const uint8_t* __re
   __syncthreads();
   if (threadIdx.x < 4 && cm_sh[threadIdx.x])
     atomicAdd(&cm[threadIdx.x], (unsigned long long)cm_sh[threadIdx.x]);
+}
+
+// annotation placeholder [N,H,W,C] one-hot (bool / u8 / f32, FCN.py:313; channel 0 = background, FCN.py:195-201)
+// -> u8 class ids: first maximal channel (what tf.argmax(annotation, 3) gives; exact for one-hot rows)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) onehot_to_ids_kernel(const T* __restrict__ onehot, uint8_t* __restrict__ ids,
+                                                                 int64_t npix, int C) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+    const T* r = onehot + i * C;
+    float mx = (float)r[0];
+    int am = 0;
+    for (int c = 1; c < C; ++c) {
+      const float v = (float)r[c];
+      if (v > mx) { mx = v; am = c; }
+    }
+    ids[i] = (uint8_t)am;
+  }
 }
 
 // paste_mask (FCN.py:203-211): where mask != 0 blend the RGBA colour over the image with PIL's
@@ -622,13 +691,20 @@ int segk_maxpool2x2_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int
   return SEGK_OK;
 }
 
-int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const void* act,
+int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const void* act, int act_is_pooled,
                         const void* residual, void* dx, int N, int H, int W, int C, void* stream) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, dy && idx && dx, "maxpool_bwd: null pointer");
   SEGK_REQUIRE(ctx, N > 0 && H >= 2 && W >= 2 && (H % 2 == 0) && (W % 2 == 0) && C % 8 == 0,
                "maxpool_bwd: need even H,W and C%%8==0 (got %dx%dx%dx%d)", N, H, W, C);
   const int64_t items = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  if (act && act_is_pooled) {
+    SEGK_REQUIRE(ctx, !residual, "maxpool_bwd: a second gradient path needs the full-resolution activation as mask");
+    maxpool_bwd_pooled_kernel<<<stream_grid(ctx, items), kThreads, 0, (cudaStream_t)stream>>>(
+        (const uint4*)dy, (const uint2*)idx, (const uint4*)act, (uint4*)dx, N, H, W, C / 8);
+    SEGK_LAUNCHED(ctx, "maxpool_bwd_pooled");
+    return SEGK_OK;
+  }
   maxpool_bwd_kernel<<<stream_grid(ctx, items), kThreads, 0, (cudaStream_t)stream>>>(
       (const uint4*)dy, (const uint2*)idx, (const uint4*)act, (const uint4*)residual, (uint4*)dx, N, H, W, C / 8);
   SEGK_LAUNCHED(ctx, "maxpool_bwd");
@@ -675,13 +751,27 @@ int segk_softmax_xent_fwd_bwd(segk_ctx* ctx, const float* logits, const uint8_t*
   return SEGK_OK;
 }
 
-int segk_softmax_infer(segk_ctx* ctx, const float* logits, float* prob, uint8_t* mask, int64_t npix,
-                       int C, void* stream) {
+int segk_softmax_infer(segk_ctx* ctx, const float* logits, float* prob, uint8_t* mask, uint8_t* argmax,
+                       int64_t npix, int C, void* stream) {
   if (!ctx) return SEGK_EINVAL;
-  SEGK_REQUIRE(ctx, logits && (prob || mask) && npix > 0 && C >= 2, "softmax_infer: bad args");
+  SEGK_REQUIRE(ctx, logits && (prob || mask || argmax) && npix > 0 && C >= 2 && C <= 255, "softmax_infer: bad args");
   softmax_infer_kernel<<<stream_grid(ctx, npix), kThreads, 0, (cudaStream_t)stream>>>(
-      logits, prob, mask, npix, C);
+      logits, prob, mask, argmax, npix, C);
   SEGK_LAUNCHED(ctx, "softmax_infer");
+  return SEGK_OK;
+}
+
+int segk_onehot_to_ids(segk_ctx* ctx, const void* onehot, int dtype, uint8_t* ids, int64_t npix, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, onehot && ids && npix > 0 && C >= 1 && C <= 255, "onehot_to_ids: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == 1)
+    onehot_to_ids_kernel<float><<<stream_grid(ctx, npix), kThreads, 0, st>>>((const float*)onehot, ids, npix, C);
+  else if (dtype == 2)
+    onehot_to_ids_kernel<uint8_t><<<stream_grid(ctx, npix), kThreads, 0, st>>>((const uint8_t*)onehot, ids, npix, C);
+  else
+    return segk_fail(ctx, SEGK_EINVAL, "onehot_to_ids: dtype must be 1 (f32) or 2 (u8 / bool)");
+  SEGK_LAUNCHED(ctx, "onehot_to_ids");
   return SEGK_OK;
 }
 
@@ -760,13 +850,9 @@ int segk_bias_grad(segk_ctx* ctx, const void* dy, int dy_is_f32, float* db, int6
       if (gx > cap) gx = cap;
       if (gx < 1) gx = 1;
       const size_t need = sizeof(float) * (size_t)gx * C;
-      if (ctx->ws2_bytes < need) {
-        if (ctx->ws2) cudaFree(ctx->ws2);
-        ctx->ws2 = nullptr;
-        ctx->ws2_bytes = 0;
-        const size_t want = need < (size_t)(8 << 20) ? (size_t)(8 << 20) : need;
-        if (cudaMalloc(&ctx->ws2, want) != cudaSuccess) return segk_fail(ctx, SEGK_ENOMEM, "bias_grad workspace");
-        ctx->ws2_bytes = want;
+      {
+        const int rc = segk_grow(ctx, &ctx->ws2, &ctx->ws2_bytes, need < (size_t)(8 << 20) ? (size_t)(8 << 20) : need, "bias_grad");
+        if (rc) return rc;
       }
       bias_grad_bf16x8_kernel<<<dim3((unsigned)gx, gy), kThreads, 0, st>>>((const uint4*)dy, (float*)ctx->ws2, rows, C8);
       SEGK_LAUNCHED(ctx, "bias_grad_bf16x8");

@@ -821,13 +821,9 @@ int segk_conv2d_small_wgrad(segk_ctx* ctx, const void* x, int x_dtype, const voi
     if (gx > (int64_t)ctx->sm_count * 4) gx = (int64_t)ctx->sm_count * 4;
     const size_t need = sizeof(float) * (size_t)gx * Cin * Cout;
     // own scratch (ws3): BiasAddGrad may run concurrently on another stream with ws2
-    if (ctx->ws3_bytes < need) {
-      if (ctx->ws3) cudaFree(ctx->ws3);
-      ctx->ws3 = nullptr;
-      ctx->ws3_bytes = 0;
-      const size_t want = need < (size_t)(4 << 20) ? (size_t)(4 << 20) : need;
-      if (cudaMalloc(&ctx->ws3, want) != cudaSuccess) return segk_fail(ctx, SEGK_ENOMEM, "skinny wgrad workspace");
-      ctx->ws3_bytes = want;
+    {
+      const int rc = segk_grow(ctx, &ctx->ws3, &ctx->ws3_bytes, need < (size_t)(4 << 20) ? (size_t)(4 << 20) : need, "skinny wgrad");
+      if (rc) return rc;
     }
     if (Cout == 2)
       conv_skinny_wgrad_partial_kernel<2><<<(unsigned)gx, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, (float*)ctx->ws3, npix, Cin);
@@ -846,13 +842,9 @@ int segk_conv2d_small_wgrad(segk_ctx* ctx, const void* x, int x_dtype, const voi
     const int64_t cap = ceil_div64((int64_t)ctx->sm_count * 4, T);
     if (gx > cap) gx = cap;
     const size_t need = sizeof(float) * (size_t)gx * K * Cout;
-    if (ctx->ws3_bytes < need) {
-      if (ctx->ws3) cudaFree(ctx->ws3);
-      ctx->ws3 = nullptr;
-      ctx->ws3_bytes = 0;
-      const size_t want = need < (size_t)(4 << 20) ? (size_t)(4 << 20) : need;
-      if (cudaMalloc(&ctx->ws3, want) != cudaSuccess) return segk_fail(ctx, SEGK_ENOMEM, "skinny wgrad workspace");
-      ctx->ws3_bytes = want;
+    {
+      const int rc = segk_grow(ctx, &ctx->ws3, &ctx->ws3_bytes, need < (size_t)(4 << 20) ? (size_t)(4 << 20) : need, "skinny wgrad");
+      if (rc) return rc;
     }
     dim3 grid((unsigned)gx, T);
     if (Cout == 2)

@@ -848,7 +848,7 @@ struct WgradParams {
   int dw_tap_stride;          // elements between taps in dW (= Cin*Cout for HWIO)
   int dw_row_stride;          // elements between consecutive ci rows (= Cout for HWIO)
   int dw_col_stride;          // elements between consecutive co (1 for HWIO)
-  int direct;                 // 1: plain 16-byte stores (single split, or per-split partial buffers) instead of atomics
+  int direct;                 // always 1: plain 16-byte stores into dW (single split) or into per-split partial buffers
   int64_t part_stride;        // elements between the partial buffers of consecutive splits (0: dw is the result itself)
   float* dw;
 };
@@ -995,16 +995,11 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
         if (valid) {
-          if (p.direct) {
-            float4* d4 = reinterpret_cast<float4*>(dst + c0);
+          float4* d4 = reinterpret_cast<float4*>(dst + c0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              d4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                  __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(dst + (int64_t)(c0 + i) * p.dw_col_stride, __uint_as_float(r[i]));
-          }
+          for (int i = 0; i < 8; ++i)
+            d4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
         }
       }
       tc_fence_before();
@@ -1078,16 +1073,7 @@ __global__ void __launch_bounds__(256) epilogue_finish_kernel(const float* __res
 }
 
 // grow-only device scratch owned by the context (first use allocates; never on the steady-state path)
-int ensure_workspace(segk_ctx* ctx, size_t bytes) {
-  if (ctx->ws_bytes >= bytes) return SEGK_OK;
-  if (ctx->ws) cudaFree(ctx->ws);
-  ctx->ws = nullptr;
-  ctx->ws_bytes = 0;
-  cudaError_t e = cudaMalloc(&ctx->ws, bytes);
-  if (e != cudaSuccess) return segk_fail(ctx, SEGK_ENOMEM, "workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
-  ctx->ws_bytes = bytes;
-  return SEGK_OK;
-}
+int ensure_workspace(segk_ctx* ctx, size_t bytes) { return segk_grow(ctx, &ctx->ws, &ctx->ws_bytes, bytes, "split-K workspace"); }
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -1539,10 +1525,8 @@ int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw,
     p.dw = (float*)ctx->ws4;
     p.part_stride = (int64_t)n_dw;
     p.direct = 1;
-  } else if (!accumulate && !p.direct) {
-    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * n_dw, st);
-    if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "deconv2d_wgrad memset: %s", cudaGetErrorString(e));
   }
+  SEGK_REQUIRE(ctx, p.direct, "deconv2d_wgrad: %d splits of %zu weights exceed the 1 GiB partial-sum workspace", p.splits, n_dw);
   TapTable taps;
   strided_taps(taps, k, s);
   const int total = p.splits * p.n_rbp * p.n_tiles;
@@ -1633,10 +1617,8 @@ int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, i
     p.dw = (float*)ctx->ws4;
     p.part_stride = (int64_t)n_dw;
     p.direct = 1;
-  } else if (!accumulate && !p.direct) {
-    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * n_dw, st);
-    if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "conv2d_wgrad memset: %s", cudaGetErrorString(e));
   }
+  SEGK_REQUIRE(ctx, p.direct, "conv2d_wgrad: %d splits of %zu weights exceed the 1 GiB partial-sum workspace", p.splits, n_dw);
   TapTable taps;
   conv_taps(taps, kh, kw);
   const int total = p.splits * p.n_rbp * p.n_tiles;

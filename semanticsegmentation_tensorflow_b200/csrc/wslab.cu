@@ -245,15 +245,7 @@ int launch(segk_ctx* ctx, const WsMaps& maps, const WsParams& p, int grid, cudaS
 
 }  // namespace
 
-int segk_ws4(segk_ctx* ctx, size_t bytes) {
-  if (ctx->ws4_bytes >= bytes) return SEGK_OK;
-  if (ctx->ws4) cudaFree(ctx->ws4);       // (synchronises the device: nothing still reads the old buffer)
-  ctx->ws4 = nullptr;
-  ctx->ws4_bytes = 0;
-  if (cudaMalloc(&ctx->ws4, bytes) != cudaSuccess) return segk_fail(ctx, SEGK_ENOMEM, "wgrad partial-sum workspace of %zu bytes", bytes);
-  ctx->ws4_bytes = bytes;
-  return SEGK_OK;
-}
+int segk_ws4(segk_ctx* ctx, size_t bytes) { return segk_grow(ctx, &ctx->ws4, &ctx->ws4_bytes, bytes, "wgrad partial sums"); }
 
 int segk_reduce_partials(segk_ctx* ctx, const float* part, float* dw, size_t n, int splits, int accumulate, cudaStream_t st) {
   const int n4 = (int)(n / 4);

@@ -106,6 +106,7 @@ class SymmetricAllReduce(BucketedAllReduce):
         self.p_mc = int(getattr(param_handle, "multicast_ptr", 0) or 0) if param_handle is not None else 0
         self.fused = bool(self.mc and self.p_mc) and want != "multimem"
         self._adam = None
+        self.slots_stale = False      # fused path: m / v of foreign shares are stale until gather_optimizer_state()
         if self.fused:
             self.kind = "nvls-multimem fused with Adam (sharded optimizer state)"
 
@@ -133,44 +134,69 @@ class SymmetricAllReduce(BucketedAllReduce):
                 keep[a:b] = t[a:b]
             dist.all_reduce(keep, op=dist.ReduceOp.SUM, group=self.group)
             t.copy_(keep)
+        self.slots_stale = False
 
     @classmethod
     def try_create(cls, net, group=None):
         """Moves the gradient arena of `net` into symmetric memory and returns the exchange, or None (with
-        the reason on stderr) when symmetric memory is unavailable -- the caller then uses NCCL."""
+        the reason on stderr) when symmetric memory is unavailable -- the caller then uses NCCL.  Every
+        rank takes the same branch: local failures are caught and a MIN all-reduce of the success flag
+        decides for all ranks before (and again after) the collective rendezvous."""
         import sys
         if not dist.is_initialized() or dist.get_world_size(group) < 2:
             return None
-        if os.environ.get("SEGK_EXCHANGE", "").lower() == "nccl":
+        mode = os.environ.get("SEGK_EXCHANGE", "").lower()
+        if mode == "nccl":
             return None
+        dev = net.vars.g.device
+
+        def all_ok(flag: bool) -> bool:
+            t = torch.tensor([1 if flag else 0], device=dev, dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+            return bool(int(t.item()))
+
+        def report(err):
+            if err is not None:
+                print(f"segk: symmetric-memory exchange unavailable ({type(err).__name__}: {err}); using NCCL", file=sys.stderr)
+
+        symm = g = p_new = None
+        err = None
+        want_params = mode in ("", "fused")     # default: measured best at 2 and 8 GPUs (profiles/r1d_scaling.md)
         try:
             import torch.distributed._symmetric_memory as symm
-            g_old = net.vars.g
-            g = symm.empty(g_old.numel(), dtype=torch.float32, device=g_old.device)
+            g = symm.empty(net.vars.g.numel(), dtype=torch.float32, device=dev)
             g.zero_()
+            if want_params:
+                # the parameter arena too, so that the exchange can be fused with the optimizer update
+                p_new = symm.empty(net.vars.p.numel(), dtype=torch.float32, device=dev)
+                p_new.copy_(net.vars.p)
+        except Exception as e:       # noqa: BLE001 -- any failure here means "no symmetric memory on this rank"
+            err = e
+        if not all_ok(err is None):              # some rank could not allocate: nobody enters the rendezvous
+            report(err)
+            return None
+        hdl = phdl = None
+        try:
             grp = group if group is not None else dist.group.WORLD
             hdl = symm.rendezvous(g, grp)
-            # the parameter arena too, so that the exchange can be fused with the optimizer update
-            phdl = None
-            mode = os.environ.get("SEGK_EXCHANGE", "").lower()
-            if mode in ("", "fused"):        # default: measured best at 2 and 8 GPUs (profiles/r1d_scaling.md)
-                p_new = symm.empty(net.vars.p.numel(), dtype=torch.float32, device=g_old.device)
-                p_new.copy_(net.vars.p)
+            if p_new is not None:
                 phdl = symm.rendezvous(p_new, grp)
-            ok = torch.tensor([1], device=g_old.device)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)         # every rank got here
-            net.vars.g = g
-            if phdl is not None:
-                net.vars.p = p_new
-            if hasattr(net, "nodes"):
-                names = [n.name for n in net.nodes if n.kind in ("conv", "deconv")]
-                buckets = P.gradient_buckets_even(net.vars.slots, names)
-            else:
-                buckets = P.gradient_buckets(net.vars.slots)
-            return cls(net, hdl, buckets, group, phdl)
-        except Exception as e:       # noqa: BLE001 -- any failure here means "no symmetric memory on this box"
-            print(f"segk: symmetric-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL", file=sys.stderr)
+        except Exception as e:       # noqa: BLE001
+            err = e
+        if not all_ok(err is None):
+            report(err)
             return None
+        net.vars.g = g
+        if phdl is not None:
+            net.vars.p = p_new
+        if hasattr(net, "nodes"):
+            names = [n.name for n in net.nodes if n.kind in ("conv", "deconv")]
+            buckets = P.gradient_buckets_even(net.vars.slots, names)
+        else:
+            buckets = P.gradient_buckets(net.vars.slots)
+        ex = cls(net, hdl, buckets, group, phdl)
+        net.exchange = ex            # checkpoint.state_dict gathers the sharded optimizer slots through this
+        return ex
 
     def _launch(self, b):
         lo, hi, _ = self.buckets[b]
@@ -183,6 +209,7 @@ class SymmetricAllReduce(BucketedAllReduce):
             V = self.net.vars
             self.ops.call("segk_allreduce_adam_f32", self.mc, self.p_mc, V.p.data_ptr(), m.data_ptr(), v.data_ptr(), lo,
                           hi - lo, self.rank, self.world, lr_t, b1, b2, eps, stream)
+            self.slots_stale = True
         else:
             self.ops.call("segk_allreduce_f32", self.mc, ctypes.addressof(self.peers), lo, hi - lo, self.rank, self.world,
                           stream)

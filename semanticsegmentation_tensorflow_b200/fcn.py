@@ -127,17 +127,127 @@ class _Feed:
         return f"<placeholder {self.name}>"
 
 
-class FCN:
+class _Feeds:
+    """Placeholder feeds shared by FCN and graph.GraphNet: image / annotation / keep_probability
+    (FCN.py:311-313,395).  Needs self.device, self.ops, self.N/H/W/Cin, self.num_classes."""
+
+    def _init_feeds(self):
+        self._stage_bufs = {}
+        self._staged_now = []
+        self._copy_stream = None
+        self.image = _Feed("input_image")
+        self.annotation = _Feed("annotation")
+        self.keep_probability = _Feed("keep_probability")
+
+    def _as_image(self, x, device=None):
+        """The image feed (FCN.py:312,395).  u8 pixels go to conv1_1 as they are (its kernel reads u8); a
+        float32 / bf16 feed -- legal for the reference's f32 placeholder, e.g. mean-subtracted or [0,1]
+        images -- is cast to bf16 by `segk_cast_to_bf16` and takes the bf16 first-layer path (the compute
+        dtype of this path; raw 0..255 integers are exact in bf16).  Nothing is rounded or clamped."""
+        x = torch.as_tensor(x)
+        if x.dim() != 4:
+            raise ValueError("image must be NHWC")
+        if x.dtype == torch.uint8 or x.dtype == torch.bfloat16:
+            return x.contiguous()
+        if x.dtype != torch.float32:
+            raise TypeError(f"image dtype {x.dtype} not supported: feed uint8, float32 or bfloat16")
+        device = device if device is not None else (x.device if x.is_cuda else self.device)
+        x = x.contiguous().to(device, non_blocking=True)
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=device)
+        with torch.cuda.device(device):
+            self.ops.cast_to_bf16(x, out)
+        return out
+
+    def feed(self, feed_dict):
+        for k, v in feed_dict.items():
+            name = k.name if isinstance(k, _Feed) else str(k)
+            if name == "input_image":
+                x = self._as_image(v)
+                if tuple(x.shape) != (self.N, self.H, self.W, self.Cin):
+                    raise ValueError(f"image shape {tuple(x.shape)} != planned {(self.N, self.H, self.W, self.Cin)}")
+                self.x = self._stage(x, "x")
+            elif name == "annotation":
+                self.labels = self._as_labels(v)
+            elif name == "keep_probability":
+                self.keep_prob = float(v)
+            else:
+                raise KeyError(name)
+
+    def _stage(self, t, slot):
+        """Host tensors are copied into preallocated device buffers on a COPY stream (two buffers per feed
+        slot): the H2D copy of step i+1 is enqueued while the GPU still runs step i and overlaps it; the
+        compute stream only waits for the copy's event.  A buffer is reused two steps later, after the
+        step-end event of its last user.  Device tensors are used in place."""
+        if t.is_cuda:
+            return t
+        st = self._stage_bufs.setdefault((slot, t.dtype, tuple(t.shape)), {"buf": [None, None], "busy": [None, None], "i": 0})
+        i = st["i"] = st["i"] ^ 1
+        if st["buf"][i] is None:
+            st["buf"][i] = torch.empty(t.shape, dtype=t.dtype, device=self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cs = self._copy_stream
+        if st["busy"][i] is not None:
+            cs.wait_event(st["busy"][i])
+        with torch.cuda.stream(cs):
+            st["buf"][i].copy_(t, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+        torch.cuda.current_stream().wait_event(ev)
+        self._staged_now.append((st, i))
+        return st["buf"][i]
+
+    def mark_step_end(self):
+        """Called once the step that consumed the staged feeds is fully enqueued on the current stream."""
+        if self._staged_now:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            for st, i in self._staged_now:
+                st["busy"][i] = ev
+            self._staged_now = []
+
+    def _as_labels(self, y):
+        """Class-id map u8 [N,H,W] (or [N,H,W,1], the sparse variant of FCN.py:329); also accepts the
+        reference's one-hot [N,H,W,num_classes] bool / u8 / float32 annotation (channel 1 = road,
+        FCN.py:195-201,313), converted to class ids by `segk_onehot_to_ids`.  Label values >= num_classes
+        are ignored by the loss kernel (no loss, zero gradient)."""
+        y = torch.as_tensor(y)
+        shape = (self.N, self.H, self.W)
+        if y.dim() == 4 and y.shape[3] == 1:
+            y = y[..., 0]
+        if y.dim() == 4:
+            if tuple(y.shape) != shape + (self.num_classes,):
+                raise ValueError(f"annotation shape {tuple(y.shape)}: expected {shape}, {shape + (1,)} or one-hot {shape + (self.num_classes,)}")
+            if y.dtype not in (torch.bool, torch.uint8, torch.float32):
+                raise TypeError(f"one-hot annotation dtype {y.dtype} not supported: feed bool, uint8 or float32")
+            y = self._stage(y.contiguous(), "onehot")
+            ids = torch.empty(shape, dtype=torch.uint8, device=self.device)
+            self.ops.onehot_to_ids(y, ids)
+            return ids
+        if tuple(y.shape) != shape:
+            raise ValueError(f"annotation shape {tuple(y.shape)} != {shape}")
+        if y.dtype != torch.uint8:
+            if y.dtype not in (torch.int32, torch.int64, torch.int16, torch.int8, torch.bool):
+                raise TypeError(f"class-id annotation dtype {y.dtype} not supported: feed an integer type")
+            y = y.to(torch.uint8)           # dtype conversion of ids only (values 0..C-1)
+        return self._stage(y.contiguous(), "labels")
+
+
+
+class FCN(_Feeds):
     """FCN-8s builder with the reference's constructor signature (FCN.py:31-47)."""
 
     def __init__(self, x, keep_prob=1.0, num_classess=2, variables=None, init="ref", seed=1234, fc=4096,
                  dropout_seed=42, world_size=1, overlap=True):
         if not torch.cuda.is_available():
             raise RuntimeError("FCN needs a CUDA (sm_100a) device: the segmentation ops have no CPU fallback")
-        x = self._as_image(x)
-        self.device = x.device
+        x = torch.as_tensor(x)
+        self.device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
         self.ops = Ops(self.device)
+        x = self._as_image(x).to(self.device)
         self.num_classes = int(num_classess)
+        if not 2 <= self.num_classes <= 64:
+            raise ValueError(f"num_classess must be in [2, 64] (got {self.num_classes})")
         self.keep_prob = float(keep_prob)
         self.N, self.H, self.W, self.Cin = x.shape
         if self.H % 32 or self.W % 32:
@@ -147,13 +257,10 @@ class FCN:
             self.layers, self.device, values=variables, init=init, seed=seed)
         self.vars.repack(self.ops)
         self.world_size = world_size
+        self._init_feeds()
         self.dropout_seed = dropout_seed
         self.step_count = 0
         self.injected_masks = None     # {"dropout6": u8 tensor, "dropout7": ...} for parity runs
-        # placeholders (FCN.py:311-313)
-        self.image = _Feed("input_image")
-        self.annotation = _Feed("annotation")
-        self.keep_probability = _Feed("keep_probability")
         self.x = x
         self._alloc()
         self._ran_forward = False
@@ -161,16 +268,6 @@ class FCN:
         self.wside = SideStream(self.device, enabled=overlap)      # weight-gradient GEMMs beside the dgrad chain
 
     # -- buffers ------------------------------------------------------------------------
-    @staticmethod
-    def _as_image(x):
-        x = torch.as_tensor(x)
-        if x.dim() != 4:
-            raise ValueError("image must be NHWC")
-        if x.dtype != torch.uint8:
-            # raw 0..255 pixels fed as float (FCN.py:312,395): exact in u8
-            x = x.round().clamp(0, 255).to(torch.uint8)
-        return x.contiguous()
-
     def _alloc(self):
         dev, N = self.device, self.N
         bf = torch.bfloat16
@@ -223,33 +320,6 @@ class FCN:
     def _g(self, i, like):
         return self._gbuf[i][:like.numel()].view(like.shape)
 
-    # -- feeds --------------------------------------------------------------------------
-    def feed(self, feed_dict):
-        for k, v in feed_dict.items():
-            name = k.name if isinstance(k, _Feed) else str(k)
-            if name == "input_image":
-                x = self._as_image(v)
-                if tuple(x.shape) != (self.N, self.H, self.W, self.Cin):
-                    raise ValueError(f"image shape {tuple(x.shape)} != planned {(self.N, self.H, self.W, self.Cin)}")
-                self.x = x.to(self.device, non_blocking=True)
-            elif name == "annotation":
-                self.labels = self._as_labels(v)
-            elif name == "keep_probability":
-                self.keep_prob = float(v)
-            else:
-                raise KeyError(name)
-
-    def _as_labels(self, y):
-        """Class-id map u8 [N,H,W]; also accepts the reference's one-hot [N,H,W,2] bool/float
-        (channel 1 = road, FCN.py:195-201)."""
-        y = torch.as_tensor(y)
-        if y.dim() == 4:
-            y = y.to(self.device).argmax(dim=3)
-        y = y.to(device=self.device, dtype=torch.uint8, non_blocking=True).contiguous()
-        if tuple(y.shape) != (self.N, self.H, self.W):
-            raise ValueError(f"annotation shape {tuple(y.shape)} != {(self.N, self.H, self.W)}")
-        return y
-
     # -- forward (FCN.py:49-114) ------------------------------------------------------
     def _dropout_fwd(self, l, t):
         if self.keep_prob >= 1.0:
@@ -261,12 +331,9 @@ class FCN:
     def create(self):
         """Run the forward pass; returns (pred [N,H,W,1] int64, logits [N,H,W,C] f32)."""
         self.forward()
-        if self.num_classes == 2:
-            # tf.argmax over 2 classes, ties -> 0 (FCN.py:111): computed by the softmax/mask kernel
-            self.ops.softmax_infer(self.logits, None, self.pred_u8)
-            pred = self.pred_u8.to(torch.int64).unsqueeze(3)
-        else:
-            pred = torch.argmax(self.logits, dim=3, keepdim=True)
+        # tf.argmax, first index on ties (FCN.py:111), by the softmax kernel; int64 [N,H,W,1] as expand_dims gives
+        self.ops.softmax_infer(self.logits, None, None, self.pred_u8)
+        pred = self.pred_u8.to(torch.int64).unsqueeze(3)
         return pred, self.logits
 
     def forward(self):
@@ -352,7 +419,8 @@ class FCN:
             if l.kind == "pool":
                 # MaxPoolGrad fused with the ReluGrad of the pre-pool conv output
                 dx = next_dx(xin)
-                ops.maxpool_bwd(dcur, self.idx[l.name], dx, act=xin)
+                # the pooled output doubles as the ReluGrad mask of the conv before the pool
+                ops.maxpool_bwd(dcur, self.idx[l.name], dx, pooled=act[l.name])
                 dcur = dx
                 continue
             gw = V.grad(f"{l.name}/weights")
@@ -448,6 +516,7 @@ class FCN:
         prob = torch.empty_like(self.logits)
         mask = torch.empty((self.N, self.H, self.W), dtype=torch.uint8, device=self.device)
         self.ops.softmax_infer(self.logits, prob, mask)
+        self.mark_step_end()
         return prob, mask
 
 
@@ -606,4 +675,5 @@ class TrainStep:
             fin.join()
         net.step_count += 1
         net._ran_forward = False
+        net.mark_step_end()
         return loss

@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 from . import plan as P
-from .fcn import _Feed
+from .fcn import _Feed, _Feeds
 from .ops import Ops, conv_flops
 from .overlap import SideStream
 
@@ -202,24 +202,24 @@ class _Vars:
         self._repack(ops, only)
 
 
-class GraphNet:
+class GraphNet(_Feeds):
     def __init__(self, x, num_classes, nodes, variables=None, init="ref", seed=1234, world_size=1, overlap=True):
         if not torch.cuda.is_available():
             raise RuntimeError("GraphNet needs a CUDA (sm_100a) device: the segmentation ops have no CPU fallback")
         x = torch.as_tensor(x)
-        if x.dtype != torch.uint8:
-            x = x.round().clamp(0, 255).to(torch.uint8)
-        self.x = x.contiguous()
-        self.device = x.device
+        self.device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
         self.ops = Ops(self.device)
+        self.x = self._as_image(x).to(self.device)
         self.num_classes = int(num_classes)
+        if not 2 <= self.num_classes <= 64:
+            raise ValueError(f"num_classes must be in [2, 64] (got {self.num_classes})")
         self.N, self.H, self.W, self.Cin = self.x.shape
         self.nodes = nodes
         self.by_name = {n.name: n for n in nodes}
         self.world_size = world_size
         self.keep_prob = 1.0
         self.step_count = 0
-        self.image, self.annotation, self.keep_probability = _Feed("input_image"), _Feed("annotation"), _Feed("keep_probability")
+        self._init_feeds()
         shapes = graph_variable_shapes(nodes, self.Cin)
         values = variables if variables is not None else graph_init(shapes, seed, init)
         self.vars = _Vars(shapes, self.device, values)
@@ -315,30 +315,6 @@ class GraphNet:
             return self.vars.param(f"{n.name}/biases")
         return None
 
-    # ---- feeds (FCN-compatible) -----------------------------------------------------------------
-    def feed(self, feed_dict):
-        for k, v in feed_dict.items():
-            name = k.name if isinstance(k, _Feed) else str(k)
-            if name == "input_image":
-                x = torch.as_tensor(v)
-                if x.dtype != torch.uint8:
-                    x = x.round().clamp(0, 255).to(torch.uint8)
-                if tuple(x.shape) != (self.N, self.H, self.W, self.Cin):
-                    raise ValueError(f"image shape {tuple(x.shape)} != planned {(self.N, self.H, self.W, self.Cin)}")
-                self.x = x.contiguous().to(self.device, non_blocking=True)
-            elif name == "annotation":
-                self.labels = self._as_labels(v)
-            elif name == "keep_probability":
-                self.keep_prob = float(v)     # the U-Net graph has no dropout node; accepted for API parity
-            else:
-                raise KeyError(name)
-
-    def _as_labels(self, y):
-        y = torch.as_tensor(y)
-        if y.dim() == 4:
-            y = y.to(self.device).argmax(dim=3)
-        return y.to(device=self.device, dtype=torch.uint8, non_blocking=True).contiguous()
-
     # ---- forward ----------------------------------------------------------------------------------
     def _in(self, name):
         return self.x if name == "input" else self.act[name]
@@ -374,7 +350,7 @@ class GraphNet:
 
     def create(self):
         self.forward()
-        self.ops.softmax_infer(self.logits, None, self.pred_u8)
+        self.ops.softmax_infer(self.logits, None, None, self.pred_u8)       # tf.argmax, first index on ties
         return self.pred_u8.to(torch.int64).unsqueeze(3), self.logits
 
     def loss(self, annotation=None, with_grad=False):
@@ -411,8 +387,12 @@ class GraphNet:
             G = self.gbuf[n.name]
             if n.kind == "pool":
                 t = n.inputs[0]
-                ops.maxpool_bwd(G, self.idx[n.name], self.gbuf[t], act=self._relu_mask_of(t),
-                                residual=self.gbuf[t] if has[t] else None)
+                mask = self._relu_mask_of(t)
+                if mask is not None and not has[t]:
+                    # single gradient path into a ReLU output: the pooled tensor is the same mask at 1/4 the bytes
+                    ops.maxpool_bwd(G, self.idx[n.name], self.gbuf[t], pooled=self.act[n.name])
+                else:
+                    ops.maxpool_bwd(G, self.idx[n.name], self.gbuf[t], act=mask, residual=self.gbuf[t] if has[t] else None)
                 has[t] = True
                 continue
             if n.kind == "concat":
@@ -500,6 +480,7 @@ class GraphNet:
         prob = torch.empty_like(self.logits)
         mask = torch.empty((self.N, self.H, self.W), dtype=torch.uint8, device=self.device)
         self.ops.softmax_infer(self.logits, prob, mask)
+        self.mark_step_end()
         return prob, mask
 
 

@@ -291,11 +291,18 @@ class Ops:
         self.call("segk_maxpool2x2_fwd", _p(x), _p(y), _p(idx), n, h, w, c, _stream())
         return y, idx
 
-    def maxpool_bwd(self, dy, idx, dx, act=None, residual=None):
+    def maxpool_bwd(self, dy, idx, dx, act=None, residual=None, pooled=None):
+        """`act`: pre-pool activation as ReluGrad mask; `pooled`: the pooled tensor as the same mask
+        (bit-identical, a quarter of the bytes; not with `residual`)."""
         n, h, w, c = dx.shape
+        if pooled is not None:
+            assert act is None and residual is None
+            self._w(2.0 * dx.numel() + 5.0 * dy.numel(), "byte")
+            self.call("segk_maxpool2x2_bwd", _p(dy), _p(idx), _p(pooled), 1, 0, _p(dx), n, h, w, c, _stream())
+            return dx
         extra = (2.0 * dx.numel() if act is not None else 0.0) + (2.0 * dx.numel() if residual is not None else 0.0)
         self._w(2.0 * dx.numel() + 3.0 * dy.numel() + extra, "byte")
-        self.call("segk_maxpool2x2_bwd", _p(dy), _p(idx), _p(act), _p(residual), _p(dx), n, h, w, c, _stream())
+        self.call("segk_maxpool2x2_bwd", _p(dy), _p(idx), _p(act), 0, _p(residual), _p(dx), n, h, w, c, _stream())
         return dx
 
     # ---- shared-helper layers (utils.py): BN-affine folding, concat ---------------------------------
@@ -341,9 +348,17 @@ class Ops:
         self.call("segk_softmax_xent_fwd_bwd", _p(logits), _p(labels), _p(dlogits), _p(pred), _p(loss_sum), _p(cm),
                   _p(workspace), npix, c, float(grad_scale), _stream())
 
-    def softmax_infer(self, logits, prob=None, mask=None):
+    def softmax_infer(self, logits, prob=None, mask=None, argmax=None):
         c = logits.shape[-1]
-        self.call("segk_softmax_infer", _p(logits), _p(prob), _p(mask), logits.numel() // c, c, _stream())
+        self.call("segk_softmax_infer", _p(logits), _p(prob), _p(mask), _p(argmax), logits.numel() // c, c, _stream())
+
+    def onehot_to_ids(self, onehot, ids):
+        """[..., C] one-hot annotation (bool / u8 / f32, FCN.py:313) -> u8 class ids."""
+        c = onehot.shape[-1]
+        if onehot.dtype == torch.bool:
+            onehot = onehot.view(torch.uint8)
+        self.call("segk_onehot_to_ids", _p(onehot), _dt(onehot), _p(ids), onehot.numel() // c, c, _stream())
+        return ids
 
     def overlay_mask(self, image, mask, out=None, color=(0, 255, 0, 127)):
         """paste_mask of FCN.py:203-211 on the GPU (u8 NHWC image, u8 mask)."""

@@ -14,7 +14,7 @@ from semanticsegmentation_tensorflow_b200 import plan as P
 rank, world, local = init_distributed("nccl")
 dev = torch.device("cuda", local)
 torch.cuda.set_device(dev)
-FC, H, W, GB = 128, 64, 96, 4
+FC, H, W, GB = 128, 64, 96, 8
 rng = np.random.default_rng(0)
 x = (rng.integers(0, 256, (GB, H, W, 3)) // 32).astype(np.uint8)
 y = rng.integers(0, 2, (GB, H, W)).astype(np.uint8)

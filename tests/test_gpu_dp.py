@@ -14,21 +14,24 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("exchange", ["nccl", "symmetric", "fused"])
-def test_two_gpu_training_matches_single_gpu(exchange):
+def test_multi_gpu_training_matches_single_gpu(exchange, world):
     """exchange = nccl: bucketed ncclAllReduce; symmetric: segk_allreduce_f32 (our NVLS kernel) on a
     symmetric-memory gradient arena; fused: segk_allreduce_adam_f32 (exchange + Adam + parameter broadcast in
     one NVLS kernel, optimizer state sharded over the ranks)."""
-    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", {"nccl": "29533", "symmetric": "29534", "fused": "29535"}[exchange],
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    port = {"nccl": 29533, "symmetric": 29534, "fused": 29535}[exchange] + 10 * world
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "dp_worker.py")]
     env = dict(os.environ, DP_EXCHANGE=exchange)
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:]
     line = [l for l in r.stdout.splitlines() if l.startswith("DPRESULT ")][-1]
     out = json.loads(line[len("DPRESULT "):])
+    print(f"world {world} exchange {exchange}: {line}")
     if "skipped" in out:
         pytest.skip(out["skipped"])
     assert (out["exchange"] == "nccl") == (exchange == "nccl") and ("fused" in out["exchange"]) == (exchange == "fused"), out

@@ -45,6 +45,12 @@ def test_maxpool_fwd_bwd_bit_exact(ops, cuda_device, shape, ties):
     ops.maxpool_bwd(dev_bf16(dy, cuda_device), idx, dx, act=xd)
     torch.cuda.synchronize()
     assert np.array_equal(host(dx), dx_ref * (x > 0))
+    # the same mask read from the POOLED tensor (a quarter of the bytes): bit-identical for a ReLU output
+    if x.min() >= 0:
+        dx2 = torch.full(shape, 7.0, dtype=torch.bfloat16, device=cuda_device)
+        ops.maxpool_bwd(dev_bf16(dy, cuda_device), idx, dx2, pooled=y)
+        torch.cuda.synchronize()
+        assert torch.equal(dx2, dx)
 
 
 @pytest.mark.parametrize("npix", [1, 255, 4096, 2 * 160 * 576])
@@ -219,3 +225,20 @@ def test_pack_conv_weights_layouts_bit_exact(ops, cuda_device, shape):
     got_d = wd.float().cpu().numpy().reshape(kh * kw, ci, co)
     assert np.array_equal(got_k, ref.transpose(0, 2, 1))
     assert np.array_equal(got_d, ref[::-1])
+
+
+def test_onehot_to_ids_and_argmax(ops, cuda_device):
+    rng = np.random.default_rng(9)
+    ids = rng.integers(0, 5, (3, 7, 11)).astype(np.uint8)
+    oh = np.eye(5, dtype=np.float32)[ids]
+    out = torch.empty(ids.shape, dtype=torch.uint8, device=cuda_device)
+    for t in (torch.as_tensor(oh), torch.as_tensor(oh.astype(np.uint8)), torch.as_tensor(oh.astype(bool))):
+        ops.onehot_to_ids(t.to(cuda_device), out.zero_())
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), ids)
+    # tf.argmax semantics of segk_softmax_infer: first index on ties
+    lg = torch.as_tensor(rng.integers(0, 3, (1000, 5)).astype(np.float32)).to(cuda_device)     # many exact ties
+    am = torch.empty(1000, dtype=torch.uint8, device=cuda_device)
+    ops.softmax_infer(lg, None, None, am)
+    torch.cuda.synchronize()
+    assert np.array_equal(am.cpu().numpy(), lg.cpu().numpy().argmax(-1))

@@ -21,6 +21,9 @@ pytestmark = pytest.mark.gpu
 
 FC = 128
 N, H, W = 2, 128, 192
+# hard floor under the adaptive gradient tolerances: whatever the oracle's own bf16-vs-fp32 noise is,
+# a gradient tensor below cosine 0.99 or beyond 15 % of its max fails
+HARD_COS, HARD_REL = 0.99, 0.15
 
 
 def _build(cuda_device, init, keep=1.0, scale_input=True):
@@ -86,6 +89,7 @@ def test_loss_and_all_gradients(cuda_device, init):
         f = grads_f32[name].numpy()
         e0, c0 = rel_err(r, f), cosine(r, f)                        # the oracle's own bf16 noise
         tol_e, tol_c = max(5e-2, 3 * e0), min(0.999, 1 - 9 * (1 - c0))   # 3x in amplitude = 9x in cosine deficit
+        tol_e, tol_c = min(tol_e, HARD_REL), max(tol_c, HARD_COS)        # ... but never beyond the hard floor
         report.append((name, e, c, e0, c0))
         assert e <= tol_e and c >= tol_c, (f"[{init}] grad {name}: rel err {e:.3e} (tol {tol_e:.3e}) cosine {c:.6f} "
                                            f"(tol {tol_c:.6f}) max|ref| {np.abs(r).max():.3e}")
@@ -98,28 +102,66 @@ def test_loss_and_all_gradients(cuda_device, init):
     assert cm.sum() == N * H * W
 
 
-def test_training_curve_matches_oracle(cuda_device):
-    """10 Adam steps at keep_prob 1.0 under the He init: same loss curve as the oracle."""
+def test_training_curve_100_steps_and_raw_argmax(cuda_device):
+    """north_star: "a matching loss curve over 100 steps" and "argmax agreement >= 99.9 %" (raw, every pixel).
+    100 TF-Adam steps (FCN.py:338-340,398) at keep_prob 1.0 under the He init, GPU path vs oracle.
+    Adam's first steps move every weight by ~lr * sign(g): bf16 noise flips the sign of near-zero
+    gradients, so the two trajectories agree to a few per cent, not to rounding (the loss falls >10x)."""
     from semanticsegmentation_tensorflow_b200.fcn import AdamOptimizer
     net, variables, x, lab = _build(cuda_device, "he")
     step = AdamOptimizer(1e-4).minimize(net)
     orc = FCN8sOracle(variables, bf16_storage=True)
     xd, ld = torch.as_tensor(x).to(cuda_device), torch.as_tensor(lab).to(cuda_device)
     got, ref = [], []
-    for _ in range(10):
+    for _ in range(100):
         got.append(float(step({net.image: xd, net.annotation: ld, net.keep_probability: 1.0})))
         ref.append(orc.train_step(x, lab)[0])
-    print("loss curve gpu", ["%.5f" % v for v in got])
-    print("loss curve ref", ["%.5f" % v for v in ref])
-    assert ref[-1] < ref[0]                                        # it trains
-    # Adam's first steps move every weight by ~lr * sign(g): bf16 noise flips the sign of near-zero
-    # gradients, so the two trajectories agree to a few per cent, not to rounding (loss falls 14x here)
-    np.testing.assert_allclose(got, ref, rtol=5e-2)
-    # variables after 10 steps
+    got, ref = np.array(got), np.array(ref)
+    print("loss curve gpu", ["%.5f" % v for v in got[::10]], "%.5f" % got[-1])
+    print("loss curve ref", ["%.5f" % v for v in ref[::10]], "%.5f" % ref[-1])
+    dev = np.abs(got - ref) / ref
+    print(f"relative deviation over 100 steps: max {dev.max():.3e} mean {dev.mean():.3e}; first 10: max {dev[:10].max():.3e}")
+    assert ref[-1] < 0.5 * ref[0] and got[-1] < 0.5 * got[0]            # it trains
+    np.testing.assert_allclose(got[:10], ref[:10], rtol=5e-2)
+    assert dev.max() <= 0.10 and dev.mean() <= 3e-2, (dev.max(), dev.mean())
+    # variables after 100 steps
     for name in ("conv1_1/weights", "conv5_3/weights", "conv_t3/weights", "conv8/biases"):
         p = net.vars.param(name).cpu().numpy()
         r = orc.vars[name].detach().numpy()
-        assert rel_err(p, r) <= 2e-2, name
+        assert rel_err(p, r) <= 5e-2, (name, rel_err(p, r))
+    # raw argmax agreement after training: (a) each path with its own trained weights
+    pred, _ = net.create()
+    pred_ref, _ = orc.forward(x)
+    own = float((pred.cpu().numpy() == pred_ref.numpy()).mean())
+    # (b) the GPU path on the ORACLE's trained weights: isolates the forward arithmetic from the
+    # trajectory drift; this is the >= 99.9 % criterion, over every pixel
+    net.vars.assign({k: v.detach().numpy() for k, v in orc.vars.items()})
+    net.vars.repack(net.ops)
+    pred2, _ = net.create()
+    same_w = float((pred2.cpu().numpy() == pred_ref.numpy()).mean())
+    print(f"raw argmax agreement after 100 steps: own weights {own:.5f}, same weights {same_w:.5f}")
+    assert same_w >= 0.999, same_w
+    assert own >= 0.99, own
+
+
+def test_training_curve_full_size_fc4096(cuda_device):
+    """The benchmarked configuration itself (fc = 4096, 160x576), batch 1: 12 Adam steps vs the oracle."""
+    from semanticsegmentation_tensorflow_b200.fcn import FCN, AdamOptimizer
+    variables = init_variables(cin=3, ncls=2, fc=4096, seed=1234, init="he")
+    x, lab = synthetic_batch(1, 160, 576, seed=0, road_shaped=True)
+    x = (x // 32).astype(np.uint8)
+    net = FCN(torch.as_tensor(x).to(cuda_device), 1.0, 2, variables=variables)
+    step = AdamOptimizer(1e-4).minimize(net)
+    orc = FCN8sOracle(variables, bf16_storage=True)
+    xd, ld = torch.as_tensor(x).to(cuda_device), torch.as_tensor(lab).to(cuda_device)
+    got, ref = [], []
+    for _ in range(12):
+        got.append(float(step({net.image: xd, net.annotation: ld, net.keep_probability: 1.0})))
+        ref.append(orc.train_step(x, lab)[0])
+    print("full-size loss curve gpu", ["%.5f" % v for v in got])
+    print("full-size loss curve ref", ["%.5f" % v for v in ref])
+    assert ref[-1] < ref[0]
+    np.testing.assert_allclose(got, ref, rtol=5e-2)
 
 
 def test_dropout_training_step_with_injected_masks(cuda_device):
@@ -140,6 +182,7 @@ def test_dropout_training_step_with_injected_masks(cuda_device):
     for name in ("conv6/weights", "conv7/weights", "conv5_1/weights", "conv8/weights"):
         g, r, f = net.vars.grad(name).cpu().numpy(), grads_ref[name].numpy(), grads_f32[name].numpy()
         tol_e, tol_c = max(5e-2, 3 * rel_err(r, f)), min(0.999, 1 - 9 * (1 - cosine(r, f)))
+        tol_e, tol_c = min(tol_e, HARD_REL), max(tol_c, HARD_COS)
         assert rel_err(g, r) <= tol_e and cosine(g, r) >= tol_c, (name, rel_err(g, r), cosine(g, r), tol_e, tol_c)
 
 

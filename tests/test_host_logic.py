@@ -185,3 +185,108 @@ def test_exchange_shares_partition_every_bucket():
             assert all(cover[i][1] == cover[i + 1][0] or cover[i + 1][0] == cover[i + 1][1] for i in range(world - 1))
     ar = BucketedAllReduce(torch.zeros(total), buckets)
     assert ar.fires_at(buckets[0][2]) and not ar.fires_at("conv1_1")
+
+
+class _FakeVars:
+    """CPU stand-in for fcn.Variables: enough for checkpoint.state_dict / load_state_dict."""
+
+    def __init__(self, shapes):
+        self.slots, self.total = P.arena_layout(shapes)
+        self.p = torch.arange(self.total, dtype=torch.float32) * 1e-3
+        self.m = torch.ones(self.total) * 0.5
+        self.v = torch.ones(self.total) * 0.25
+        self.repacked = 0
+
+    def view(self, arena, name):
+        s = self.slots[name]
+        return arena[s.offset:s.offset + s.size].view(s.shape)
+
+    def repack(self, ops):
+        self.repacked += 1
+
+
+class _FakeNet:
+    def __init__(self):
+        self.vars = _FakeVars(P.variable_shapes(3, 2, 64))
+        self.ops = None
+
+
+@pytest.mark.parametrize("t", [0, 3, 980, 986, 2000, 123456])
+def test_checkpoint_step_count_roundtrip_beyond_float32_underflow(tmp_path, t):
+    """0.9^(t+1) underflows float32 near t = 986: the step count travels as an int64 `global_step`."""
+    from semanticsegmentation_tensorflow_b200.checkpoint import load_checkpoint, save_checkpoint, state_dict
+    from semanticsegmentation_tensorflow_b200.fcn import AdamOptimizer, MomentumOptimizer
+    net, opt = _FakeNet(), AdamOptimizer(1e-4)
+    opt.t = t
+    sd = state_dict(net, opt)
+    assert int(sd["global_step"]) == t and sd["beta1_power"].dtype == np.float32
+    assert "conv6/weights/Adam" in sd and "conv6/weights/Adam_1" in sd and "conv_t3/bias/Adam" in sd
+    path = str(tmp_path / "c.npz")
+    save_checkpoint(path, net, opt)
+    net2, opt2 = _FakeNet(), AdamOptimizer(1e-4)
+    net2.vars.p.zero_(); net2.vars.m.zero_(); net2.vars.v.zero_()
+    load_checkpoint(path, net2, opt2)
+    assert opt2.t == t and net2.vars.repacked == 1
+    for name in net.vars.slots:      # (the alignment padding between variables is not part of a checkpoint)
+        for arena in ("p", "m", "v"):
+            assert torch.equal(net2.vars.view(getattr(net2.vars, arena), name), net.vars.view(getattr(net.vars, arena), name))
+    # checkpoints written before global_step existed: beta1_power is inverted only while float32 resolves it
+    old = {k: v for k, v in sd.items() if k != "global_step"}
+    from semanticsegmentation_tensorflow_b200.checkpoint import load_state_dict
+    opt3 = AdamOptimizer(1e-4)
+    if t < 900:
+        load_state_dict(_FakeNet(), old, opt3)
+        assert opt3.t == t
+    elif t >= 2000:
+        with pytest.raises(ValueError, match="underflowed"):
+            load_state_dict(_FakeNet(), old, opt3)
+    # tf.train.MomentumOptimizer names its slot <var>/Momentum
+    mopt = MomentumOptimizer(1e-3)
+    mopt.t = t
+    net.vars.v = None
+    sdm = state_dict(net, mopt)
+    assert "conv6/weights/Momentum" in sdm and "conv6/weights/Adam" not in sdm and "beta1_power" not in sdm
+    net4, mopt2 = _FakeNet(), MomentumOptimizer(1e-3)
+    net4.vars.m.zero_()
+    load_state_dict(net4, sdm, mopt2)
+    assert mopt2.t == t and all(torch.equal(net4.vars.view(net4.vars.m, n), net.vars.view(net.vars.m, n)) for n in net.vars.slots)
+
+
+def test_sharded_optimizer_slots_are_gathered_before_export():
+    """With the fused data-parallel exchange every rank holds 1/world of Adam's m / v: state_dict must gather
+    first -- through the TrainStep when given, else through the exchange attached to the net."""
+    from semanticsegmentation_tensorflow_b200.checkpoint import state_dict
+    from semanticsegmentation_tensorflow_b200.fcn import AdamOptimizer
+
+    class Ex:
+        fused, slots_stale, calls = True, True, 0
+
+        def gather_optimizer_state(self):
+            self.calls += 1
+            self.slots_stale = False
+
+    net = _FakeNet()
+    net.exchange = Ex()
+    state_dict(net, AdamOptimizer(1e-4))
+    assert net.exchange.calls == 1 and not net.exchange.slots_stale
+    state_dict(net, AdamOptimizer(1e-4))
+    assert net.exchange.calls == 1          # nothing stale: no second collective
+
+
+def test_reference_helper_signatures():
+    """The drop-in helpers keep the reference's argument names and defaults (FCN.py:117,138,161,165,169)."""
+    import inspect
+    from semanticsegmentation_tensorflow_b200 import layers
+    def sig(f):
+        return [(n, p.default) for n, p in inspect.signature(f).parameters.items() if n != "store" and n != "seed"]
+    E = inspect.Parameter.empty
+    assert sig(layers.conv_layer) == [("x", E), ("num_filters", E), ("name", E), ("filter_height", 3), ("filter_width", 3),
+                                      ("stride", 1), ("padding", "SAME")]
+    assert sig(layers.deconv_layer) == [("x", E), ("shape", E), ("num_filters", E), ("name", E), ("output_shape", E),
+                                        ("filter_height", 4), ("filter_width", 4), ("stride", 2), ("padding", "SAME")]
+    assert sig(layers.max_pool) == [("x", E), ("name", E), ("filter_height", 2), ("filter_width", 2), ("stride", 2),
+                                    ("padding", "VALID")]
+    assert sig(layers.dropout) == [("x", E), ("keep_prob", E)]
+    assert sig(layers.fuse) == [("x1", E), ("x2", E), ("name", E)]
+    import semanticsegmentation_tensorflow_b200 as pkg
+    assert pkg.conv_layer is layers.conv_layer and pkg.fuse is layers.fuse
