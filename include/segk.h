@@ -52,9 +52,9 @@ const char* segk_last_error(segk_ctx* ctx);
 int64_t segk_launch_count(segk_ctx* ctx);
 int segk_sm_count(segk_ctx* ctx);
 /* Kernel-selection overrides (also read once at segk_create from SEGK_SLAB / SEGK_SLAB3 / SEGK_WSLAB /
- * SEGK_TMA_STORE / SEGK_FORCE_BN / SEGK_FORCE_KSPLIT / SEGK_FORCE_WSPLIT): key in {"slab", "slab3",
- * "wslab" (0 off, 1 auto, 2 wherever legal), "tma_store" (0|1), "force_bn" (0|64|128|256),
- * "force_ksplit", "force_wsplit" (0 = heuristic)}.  Every setting computes the same sums (fp32
+ * SEGK_TMA_STORE / SEGK_TEAMK / SEGK_FORCE_BN / SEGK_FORCE_KSPLIT / SEGK_FORCE_WSPLIT): key in {"slab", "slab3",
+ * "wslab" (0 off, 1 auto, 2 wherever legal), "tma_store" (0|1), "teamk" (0|1: team stream-K instead of plain
+ * split-K for few-tile / long-K layers), "force_bn" (0|64|128|256), "force_ksplit", "force_wsplit" (0 = heuristic)}.  Every setting computes the same sums (fp32
  * accumulation order differs between kernels). */
 int segk_set_tuning(segk_ctx* ctx, const char* key, int value);
 
@@ -64,7 +64,7 @@ int segk_set_tuning(segk_ctx* ctx, const char* key, int value);
 
 /*
  * conv_layer forward: relu(conv2d(x, W, stride 1, SAME) + b)        (FCN.py:117-136)
- *   x [N,H,W,Cin] bf16; wk = kernel-layout weights [kh*kw][Cout][Cin] bf16 produced by
+ *   x [N,H,W,Cin] bf16; wk = kernel-layout weights [kh*kw][Cin/64][Cout][64] bf16 produced by
  *   segk_pack_conv_weights; bias fp32 [Cout] or NULL; residual (same shape as y, bf16) is
  *   added before the ReLU when non-NULL (the `fuse` skip-add, FCN.py:169-171).
  *   tcgen05 path: requires Cin % 64 == 0 and Cout % 64 == 0, odd kh,kw, kh*kw <= 64.
@@ -75,7 +75,7 @@ int segk_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* b
 
 /*
  * Conv2DBackpropInput of the above (part of what `optimizer.minimize` emits, FCN.py:340):
- *   dx = dy (*) rot180(W);  wd = dgrad-layout weights [kh*kw (taps reversed)][Cin][Cout] bf16.
+ *   dx = dy (*) rot180(W);  wd = dgrad-layout weights [kh*kw (taps reversed)][Cout/64][Cin][64] bf16.
  *   dx = ((acc + residual) masked by relu_mask > 0) * scale, where
  *   relu_mask (shape of dx, bf16, or NULL) is the forward activation whose ReluGrad is
  *   fused here, residual (or NULL) a second gradient path into the same tensor (AddN at
@@ -105,7 +105,7 @@ int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float*
                       int k, int s, unsigned flags, void* stream);
 
 /* gradient of deconv_layer wrt its input = conv2d(dy, W, stride s);
- * dy [N,sH,sW,Cout] bf16, wd [k*k][Cin][Cout] bf16, dx [N,H,W,Cin] bf16. k=4, s=2. */
+ * dy [N,sH,sW,Cout] bf16, wd [k*k][Cout/64][Cin][64] bf16, dx [N,H,W,Cin] bf16. k=4, s=2. */
 int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask,
                         void* dx, int N, int H, int W, int Cin, int Cout, int k, int s,
                         void* stream);
@@ -178,7 +178,8 @@ int segk_deconv_patch_gather(segk_ctx* ctx, const void* dy, int dy_is_f32, void*
 int segk_deconv_col2im(segk_ctx* ctx, const float* yp, const float* bias, const void* residual,
                        void* y, int out_f32, int N, int H, int W, int Cout, int k, int s,
                        void* stream);
-/* generic matrix pack: w fp32 [T][A][B] -> cp bf16 [T][A][B] and/or tr bf16 [T][B][A] */
+/* generic matrix pack: w fp32 [T][A][B] -> cp bf16 [T][ceil(B/64)][A][64] (rows A, k = B) and/or
+ * tr bf16 [T][ceil(A/64)][B][64] (rows B, k = A) */
 int segk_pack_matrix(segk_ctx* ctx, const float* w, void* cp, void* tr, int T, int A, int B,
                      void* stream);
 
@@ -208,14 +209,18 @@ int segk_channel_copy(segk_ctx* ctx, const void* src, int ld_src, int coff_src, 
                       int ld_dst, int coff_dst, const void* mask, int accumulate, int64_t rows, int C,
                       void* stream);
 
-/* ---- weight layout packing (fp32 master -> bf16 kernel layouts) ------------------------ */
-/* w[kh,kw,Cin,Cout] fp32 (HWIO, FCN.py:125) -> wk[tap][Cout][Cin] bf16 (fwd) and
- * wd[ntaps-1-tap][Cin][Cout] bf16 (dgrad: taps reversed = rot180).  Either may be NULL. */
+/* ---- weight layout packing (fp32 master -> bf16 kernel layouts) ------------------------
+ * Kernel layouts are BLOCKED by 64-wide chunks of the contraction dimension k: an operand [T taps][rows][K] is
+ * stored as [T][ceil(K/64)][rows][64] (zero-padded in K), so the operand tile of one (tap, k-chunk) is one
+ * contiguous run of rows x 128 bytes (a TMA box).  Any Cin / Cout; outputs 16-byte aligned. */
+/* w[kh,kw,Cin,Cout] fp32 (HWIO, FCN.py:125) -> wk[tap][Cin/64][Cout][64] bf16 (fwd: rows = Cout, k = Cin) and
+ * wd[ntaps-1-tap][Cout/64][Cin][64] bf16 (dgrad: rows = Cin, k = Cout; taps reversed = rot180).
+ * Either may be NULL. */
 int segk_pack_conv_weights(segk_ctx* ctx, const float* w, void* wk, void* wd, int kh, int kw,
                            int Cin, int Cout, void* stream);
 /* w[k,k,Cout,Cin] fp32 (k = 2s, FCN.py:143) ->
- *   wk[ay*s+ax][uy*2+ux][Cout][Cin] bf16 = w[ay+s*(1-uy)][ax+s*(1-ux)]  (deconv fwd phases)
- *   wd[ky*k+kx][Cin][Cout] bf16                                           (deconv dgrad)   */
+ *   wk[(ay*s+ax)*4 + uy*2+ux][Cin/64][Cout][64] bf16 = w[ay+s*(1-uy)][ax+s*(1-ux)]  (deconv fwd phases)
+ *   wd[ky*k+kx][Cout/64][Cin][64] bf16                                                (deconv dgrad)   */
 int segk_pack_deconv_weights(segk_ctx* ctx, const float* w, void* wk, void* wd, int k, int s,
                              int Cin, int Cout, void* stream);
 

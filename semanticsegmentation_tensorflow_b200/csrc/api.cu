@@ -63,6 +63,7 @@ int segk_set_tuning(segk_ctx* ctx, const char* key, int value) {
   else if (!strcmp(key, "tma_store")) ctx->tma_store = value;
   else if (!strcmp(key, "slab3")) ctx->slab3 = value;
   else if (!strcmp(key, "wslab")) ctx->wslab = value;
+  else if (!strcmp(key, "teamk")) ctx->teamk = value;
   else if (!strcmp(key, "force_bn")) ctx->force_bn = value;
   else if (!strcmp(key, "force_ksplit")) ctx->force_ksplit = value;
   else if (!strcmp(key, "force_wsplit")) ctx->force_wsplit = value;

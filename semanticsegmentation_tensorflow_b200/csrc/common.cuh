@@ -23,6 +23,7 @@ struct segk_ctx {
   int slab_mode = 1;        // SEGK_SLAB: 0 off, 1 auto, 2 wherever legal
   int tma_store = 1;        // SEGK_TMA_STORE: bf16 conv outputs leave through smem + TMA store
   int slab3 = 1;            // SEGK_SLAB3: kx-fused N = 192 slab kernel with resident weights for Ck = 64
+  int teamk = 1;            // SEGK_TEAMK: team stream-K instead of plain split-K for few-tile / long-K layers (conv6 dgrad)
   void* ws = nullptr;       // grow-only scratch for split-K partial sums (tcconv.cu)
   size_t ws_bytes = 0;
   void* ws2 = nullptr;      // grow-only scratch for per-block BiasAddGrad partials (elementwise.cu)

@@ -585,92 +585,85 @@ __global__ void __launch_bounds__(kThreads) bias_grad_f32_small_kernel(const flo
   }
 }
 
-// w fp32 [T][A][B] -> cp bf16 [T'][A][B] (cast) and/or tr bf16 [T][B][A] (per-tap transpose);
-// T' = T-1-t when rev_cp (rot180 of the filter for dgrad).
-__global__ void __launch_bounds__(kThreads) pack_weights_kernel(const float* __restrict__ w,
-                                                                bf16* __restrict__ cp,
-                                                                bf16* __restrict__ tr, int A, int B,
-                                                                int rev_cp) {
-  __shared__ float tile[32][33];
-  const int t = blockIdx.z;
-  const int tc = rev_cp ? (int)gridDim.z - 1 - t : t;
-  const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  const float* wt = w + (int64_t)t * A * B;
-  for (int r = ty; r < 32; r += 8) {
-    const int a = a0 + r, b = b0 + tx;
-    float v = 0.f;
-    if (a < A && b < B) {
-      v = wt[(int64_t)a * B + b];
-      if (cp) cp[(int64_t)tc * A * B + (int64_t)a * B + b] = f2bf(v);
-    }
-    tile[r][tx] = v;
-  }
-  __syncthreads();
-  if (tr) {
-    for (int r = ty; r < 32; r += 8) {
-      const int b = b0 + r, a = a0 + tx;
-      if (a < A && b < B) tr[(int64_t)t * A * B + (int64_t)b * A + a] = f2bf(tile[tx][r]);
-    }
-  }
-}
-
-// Same for A % 64 == 0 and B % 64 == 0 (every tensor-core layer): 64 x 64 tiles, 16-byte loads and
-// 16-byte bf16x8 stores on both outputs (the 32 x 32 version's 2-byte transposed stores ran the repack
-// of the 134 M FCN-8s parameters at 2.1 TB/s; it sits on the optimizer's side stream every step).
-__global__ void __launch_bounds__(kThreads) pack_weights64_kernel(const float* __restrict__ w, bf16* __restrict__ cp,
-                                                                  bf16* __restrict__ tr, int A, int B, int rev_cp) {
+// Kernel-layout weights are BLOCKED by 64-wide k-chunks: an operand [T taps][rows][K] is stored as
+// [T][ceil(K/64)][rows][64] (zero-padded in K), so the tile of one (tap, k-chunk) is one contiguous run of
+// rows x 128 bytes (tcconv.cu: encode_weight_map_blocked).
+//   w fp32 [T][A][B]  ->  cp bf16 [T'][ceil(B/64)][A][64]   (rows = A, k = B; T' = T-1-t when rev_cp: rot180 for dgrad)
+//                     ->  tr bf16 [T ][ceil(A/64)][B][64]   (rows = B, k = A: the per-tap transpose)
+// 64 x 64 tiles through shared memory, 16-byte loads and 16-byte bf16x8 stores on both outputs: every tile of
+// either output is a contiguous 8 KB block.  A, B arbitrary (edges guarded, padding written as zeros).
+__global__ void __launch_bounds__(kThreads) pack_blocked_kernel(const float* __restrict__ w, bf16* __restrict__ cp,
+                                                                bf16* __restrict__ tr, int A, int B, int rev_cp) {
   __shared__ float tile[64][65];
   const int t = blockIdx.z;
   const int tc = rev_cp ? (int)gridDim.z - 1 - t : t;
   const int a0 = blockIdx.y * 64, b0 = blockIdx.x * 64;
+  const int KCa = (int)gridDim.y, KCb = (int)gridDim.x;
   const float* wt = w + (int64_t)t * A * B;
   {
     const int c4 = threadIdx.x & 15, r0 = threadIdx.x >> 4;      // 16 float4 per row, 16 rows per pass
+    const bool vec = (B & 3) == 0 && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
 #pragma unroll
     for (int r = r0; r < 64; r += 16) {
-      const float4 v = *reinterpret_cast<const float4*>(wt + (int64_t)(a0 + r) * B + b0 + c4 * 4);
+      const int a = a0 + r, b = b0 + c4 * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a < A) {
+        if (vec && b + 3 < B) {
+          v = *reinterpret_cast<const float4*>(wt + (int64_t)a * B + b);
+        } else {
+          if (b < B) v.x = wt[(int64_t)a * B + b];
+          if (b + 1 < B) v.y = wt[(int64_t)a * B + b + 1];
+          if (b + 2 < B) v.z = wt[(int64_t)a * B + b + 2];
+          if (b + 3 < B) v.w = wt[(int64_t)a * B + b + 3];
+        }
+      }
       tile[r][c4 * 4] = v.x; tile[r][c4 * 4 + 1] = v.y; tile[r][c4 * 4 + 2] = v.z; tile[r][c4 * 4 + 3] = v.w;
     }
   }
   __syncthreads();
   const int pc = threadIdx.x & 7, q0 = threadIdx.x >> 3;         // 8 bf16x8 pieces per row, 32 rows per pass
   if (cp) {
-    bf16* dst = cp + (int64_t)tc * A * B;
+    bf16* dst = cp + ((int64_t)tc * KCb + blockIdx.x) * A * 64;
 #pragma unroll
     for (int r = q0; r < 64; r += 32) {
+      if (a0 + r >= A) continue;
       const float* s = &tile[r][pc * 8];
-      *reinterpret_cast<uint4*>(dst + (int64_t)(a0 + r) * B + b0 + pc * 8) =
+      *reinterpret_cast<uint4*>(dst + (int64_t)(a0 + r) * 64 + pc * 8) =
           make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
     }
   }
   if (tr) {
-    bf16* dst = tr + (int64_t)t * A * B;
+    bf16* dst = tr + ((int64_t)t * KCa + blockIdx.y) * B * 64;
 #pragma unroll
     for (int r = q0; r < 64; r += 32) {       // output row b0 + r holds A-values a0 + pc*8 .. +7
+      if (b0 + r >= B) continue;
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = tile[pc * 8 + j][r];
-      *reinterpret_cast<uint4*>(dst + (int64_t)(b0 + r) * A + a0 + pc * 8) =
+      *reinterpret_cast<uint4*>(dst + (int64_t)(b0 + r) * 64 + pc * 8) =
           make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     }
   }
 }
 
-// deconv forward phase packing: wk[ay*s+ax][uy*2+ux][co][ci] = w[ay+s*(1-uy)][ax+s*(1-ux)][co][ci]
+// deconv forward phase packing: wk[ay*s+ax][uy*2+ux][co][ci] = w[ay+s*(1-uy)][ax+s*(1-ux)][co][ci], blocked over ci:
+// wk[phase*4 + u][ci/64][co][ci%64]
 __global__ void __launch_bounds__(kThreads) pack_deconv_phase_kernel(const float* __restrict__ w,
                                                                      bf16* __restrict__ wk, int k, int s,
                                                                      int Cin, int Cout) {
-  const int64_t per = (int64_t)Cout * Cin;
+  const int KC = (Cin + 63) / 64;
+  const int64_t per = (int64_t)KC * Cout * 64;
   const int64_t total = (int64_t)s * s * 4 * per;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e = i % per;
     const int pu = (int)(i / per);
+    const int kk = (int)(e % 64), co = (int)((e / 64) % Cout), kc = (int)(e / (64 * (int64_t)Cout));
+    const int ci = kc * 64 + kk;
     const int u = pu & 3, ph = pu >> 2;
     const int uy = u >> 1, ux = u & 1, ay = ph / s, ax = ph % s;
     const int ky = ay + s * (1 - uy), kx = ax + s * (1 - ux);
-    wk[i] = f2bf(w[(int64_t)(ky * k + kx) * per + e]);
+    wk[i] = ci < Cin ? f2bf(w[((int64_t)(ky * k + kx) * Cout + co) * Cin + ci]) : f2bf(0.f);
   }
 }
 
@@ -888,18 +881,12 @@ int segk_pack_conv_weights(segk_ctx* ctx, const float* w, void* wk, void* wd, in
                            int Cout, void* stream) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, w && (wk || wd) && kh > 0 && kw > 0 && Cin > 0 && Cout > 0, "pack_conv: bad args");
+  SEGK_REQUIRE(ctx, (((uintptr_t)wk | (uintptr_t)wd) & 15) == 0, "pack_conv: outputs must be 16-byte aligned");
   const int T = kh * kw;
-  // w[t][Cin][Cout]: wd = cast copy with taps reversed, wk = per-tap transpose [Cout][Cin]
-  if (Cin % 64 == 0 && Cout % 64 == 0 && (((uintptr_t)w | (uintptr_t)wk | (uintptr_t)wd) & 15) == 0) {
-    dim3 g64(Cout / 64, Cin / 64, T);
-    SEGK_REQUIRE(ctx, g64.y <= 65535 && g64.z <= 65535, "pack_conv: dims too large");
-    pack_weights64_kernel<<<g64, kThreads, 0, (cudaStream_t)stream>>>(w, (bf16*)wd, (bf16*)wk, Cin, Cout, 1);
-    SEGK_LAUNCHED(ctx, "pack_conv_weights");
-    return SEGK_OK;
-  }
-  dim3 grid(ceil_div(Cout, 32), ceil_div(Cin, 32), T);
+  // w[t][Cin][Cout]: wd = cast copy with taps reversed (k = Cout), wk = per-tap transpose (k = Cin); both blocked
+  dim3 grid(ceil_div(Cout, 64), ceil_div(Cin, 64), T);
   SEGK_REQUIRE(ctx, grid.y <= 65535 && grid.z <= 65535, "pack_conv: dims too large");
-  pack_weights_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(w, (bf16*)wd, (bf16*)wk, Cin, Cout, 1);
+  pack_blocked_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(w, (bf16*)wd, (bf16*)wk, Cin, Cout, 1);
   SEGK_LAUNCHED(ctx, "pack_conv_weights");
   return SEGK_OK;
 }
@@ -907,16 +894,10 @@ int segk_pack_conv_weights(segk_ctx* ctx, const float* w, void* wk, void* wd, in
 int segk_pack_matrix(segk_ctx* ctx, const float* w, void* cp, void* tr, int T, int A, int B, void* stream) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, w && (cp || tr) && T > 0 && A > 0 && B > 0, "pack_matrix: bad args");
-  if (A % 64 == 0 && B % 64 == 0 && (((uintptr_t)w | (uintptr_t)cp | (uintptr_t)tr) & 15) == 0) {
-    dim3 g64(B / 64, A / 64, T);
-    SEGK_REQUIRE(ctx, g64.y <= 65535 && g64.z <= 65535, "pack_matrix: dims too large");
-    pack_weights64_kernel<<<g64, kThreads, 0, (cudaStream_t)stream>>>(w, (bf16*)cp, (bf16*)tr, A, B, 0);
-    SEGK_LAUNCHED(ctx, "pack_matrix");
-    return SEGK_OK;
-  }
-  dim3 grid(ceil_div(B, 32), ceil_div(A, 32), T);
+  SEGK_REQUIRE(ctx, (((uintptr_t)cp | (uintptr_t)tr) & 15) == 0, "pack_matrix: outputs must be 16-byte aligned");
+  dim3 grid(ceil_div(B, 64), ceil_div(A, 64), T);
   SEGK_REQUIRE(ctx, grid.y <= 65535 && grid.z <= 65535, "pack_matrix: dims too large");
-  pack_weights_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(w, (bf16*)cp, (bf16*)tr, A, B, 0);
+  pack_blocked_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(w, (bf16*)cp, (bf16*)tr, A, B, 0);
   SEGK_LAUNCHED(ctx, "pack_matrix");
   return SEGK_OK;
 }
@@ -925,16 +906,17 @@ int segk_pack_deconv_weights(segk_ctx* ctx, const float* w, void* wk, void* wd, 
                              int Cout, void* stream) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, w && (wk || wd) && k == 2 * s && s > 0 && Cin > 0 && Cout > 0, "pack_deconv: bad args");
+  SEGK_REQUIRE(ctx, (((uintptr_t)wk | (uintptr_t)wd) & 15) == 0, "pack_deconv: outputs must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   if (wd) {
-    // w[t][Cout][Cin] -> wd[t][Cin][Cout]
-    dim3 grid(ceil_div(Cin, 32), ceil_div(Cout, 32), k * k);
+    // w[t][Cout][Cin] -> wd[t][Cout/64][Cin][64]  (rows = Cin, k = Cout)
+    dim3 grid(ceil_div(Cin, 64), ceil_div(Cout, 64), k * k);
     SEGK_REQUIRE(ctx, grid.y <= 65535 && grid.z <= 65535, "pack_deconv: dims too large");
-    pack_weights_kernel<<<grid, kThreads, 0, st>>>(w, nullptr, (bf16*)wd, Cout, Cin, 0);
+    pack_blocked_kernel<<<grid, kThreads, 0, st>>>(w, nullptr, (bf16*)wd, Cout, Cin, 0);
     SEGK_LAUNCHED(ctx, "pack_deconv_wd");
   }
   if (wk) {
-    const int64_t n = (int64_t)s * s * 4 * Cout * Cin;
+    const int64_t n = (int64_t)s * s * 4 * ceil_div(Cin, 64) * 64 * Cout;
     pack_deconv_phase_kernel<<<stream_grid(ctx, n), kThreads, 0, st>>>(w, (bf16*)wk, k, s, Cin, Cout);
     SEGK_LAUNCHED(ctx, "pack_deconv_wk");
   }

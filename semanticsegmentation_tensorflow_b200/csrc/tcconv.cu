@@ -34,6 +34,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;             // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * 128;  // 16 KB
 constexpr int kMaxTaps = 64;
+constexpr int kMaxCols = 64;            // columns of the team stream-K schedule
 constexpr int kSmemBudget = 192 * 1024;
 constexpr int kStageOutBytes = kBlockM * 128;     // epilogue staging: 128 rows x 64 bf16 channels, SWIZZLE_128B
 constexpr int kOutBytes = 2 * kStageOutBytes;     // double-buffered
@@ -102,6 +103,15 @@ struct IgemmParams {
   int64_t ws_slice;   // elements per slice
   int tma_store;   // 1: bf16 output leaves through shared memory + TMA store (coalesced, async, clipped)
   int m_fastest;   // tile order: 0 = channel tile fastest (activations shared), 1 = pixel tile fastest (weights shared)
+  // "team stream-K" for layers with few output tiles and a long, weight-heavy K walk (conv6 dgrad: 50 tiles x ~2060
+  // k-steps, 205 MB of weights).  The tiles that differ only in the batch coordinate (team_members = tiles_n of them)
+  // share every weight slice, so they form a TEAM of CTAs that walk the same k-steps in lockstep (the slice comes from
+  // DRAM once and from L2 for the others).  The concatenated k-steps of all "columns" (nt, y-tile, x-tile) -- team_total,
+  // exclusive prefix sums in team_prefix -- are cut into team_T equal ranges, one per team: every SM gets the same
+  // number of k-steps, whatever the tile count.  A team's piece of a column goes to partial slice
+  // (team - first team of that column); epilogue_finish_kernel adds a column's slices in order.
+  int team, team_T, team_members, team_ncols, team_total;
+  int team_prefix[kMaxCols + 1];
 };
 
 struct PipeState {
@@ -170,6 +180,65 @@ __device__ __forceinline__ uint64_t tap_mask(const IgemmParams& p, const TapTabl
   if (m == 0) m = (p.ntaps >= 64) ? ~0ull : ((1ull << p.ntaps) - 1);  // all-zero tile: still produce zeros
   return m;
 }
+
+// first team whose k-step range [total*t/T, total*(t+1)/T) contains global step s
+__host__ __device__ __forceinline__ int team_of_step(int s, int T, int total) {
+  return (int)((((int64_t)s + 1) * T - 1) / total);
+}
+
+// The sequence of (tile, k-step range) work units of one CTA; all three warp roles walk it identically.
+struct Work {
+  TileCoord t;       // t.split = partial-sum slice
+  uint64_t tm;       // active taps of the tile
+  int lo, hi;        // k-step range within the tile's (active tap, k-chunk) walk
+};
+
+struct WorkIter {
+  int tile, col, tlo, thi, team, member;
+  __device__ __forceinline__ void init(const IgemmParams& p) {
+    tile = blockIdx.x;
+    col = 0;
+    team = member = tlo = thi = 0;
+    if (p.team) {
+      team = blockIdx.x / p.team_members;
+      member = blockIdx.x % p.team_members;
+      tlo = (int)(((int64_t)p.team_total * team) / p.team_T);
+      thi = (int)(((int64_t)p.team_total * (team + 1)) / p.team_T);
+    }
+  }
+  __device__ __forceinline__ bool next(const IgemmParams& p, const TapTable& taps, Work& w) {
+    if (!p.team) {
+      const int total_tiles = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.ksplits;
+      if (tile >= total_tiles) return false;
+      w.t = decode_tile(p, tile);
+      tile += gridDim.x;
+      w.tm = tap_mask(p, taps, w.t);
+      const int nall = __popcll(w.tm) * p.kchunks;
+      // balanced partition: no split is empty because ksplits <= kchunks <= nall
+      w.lo = (int)(((int64_t)nall * w.t.split) / p.ksplits);
+      w.hi = (int)(((int64_t)nall * (w.t.split + 1)) / p.ksplits);
+      return true;
+    }
+    while (col < p.team_ncols) {
+      const int c = col++;
+      const int cs = p.team_prefix[c], ce = p.team_prefix[c + 1];
+      const int a = tlo > cs ? tlo : cs, b = thi < ce ? thi : ce;
+      if (a >= b) continue;
+      int r = c / p.tiles_w;
+      w.t.x0 = (c % p.tiles_w) * p.bw;
+      w.t.y0 = (r % p.tiles_h) * p.bh;
+      w.t.nt = r / p.tiles_h;
+      w.t.n0 = member * p.bn;
+      w.t.phase = 0;
+      w.t.split = team - team_of_step(cs, p.team_T, p.team_total);
+      w.tm = tap_mask(p, taps, w.t);
+      w.lo = a - cs;
+      w.hi = b - cs;
+      return true;
+    }
+    return false;
+  }
+};
 
 // Shared tail of every conv epilogue: v = the fp32 accumulators of 32 consecutive output channels of one
 // output pixel (element offset `off` into the output / residual / mask tensors), bv = their bias.
@@ -253,7 +322,6 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.ksplits;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.a[i]);
@@ -280,25 +348,23 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
   if (warp == 0) {
     PipeState ps;
     const uint32_t tx_bytes = (uint32_t)p.rows * 128u + (uint32_t)C::kBBytes;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
-      const uint64_t tm = tap_mask(p, taps, t);
-      const int nall = __popcll(tm) * p.kchunks;
-      // balanced partition: no split is empty because ksplits <= kchunks <= nall
-      const int lo = (int)(((int64_t)nall * t.split) / p.ksplits), hi = (int)(((int64_t)nall * (t.split + 1)) / p.ksplits);
+    WorkIter it;
+    it.init(p);
+    Work w;
+    while (it.next(p, taps, w)) {
+      const TileCoord& t = w.t;
       int step = 0;
       for (int i = 0; i < p.ntaps; ++i) {
-        if (!((tm >> i) & 1)) continue;
+        if (!((w.tm >> i) & 1)) continue;
         const int dy = taps.dy[i], dx = taps.dx[i], mi = taps.map[i];
         for (int kc = 0; kc < p.kchunks; ++kc, ++step) {
-          if (step < lo || step >= hi) continue;
+          if (step < w.lo || step >= w.hi) continue;
           mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
           if (elect_one()) {
             uint8_t* sa = smem + ps.stage * C::kStageBytes;
             mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
             tma_load_4d(&maps.a[mi], &full_bar[ps.stage], sa, kc * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
-            tma_load_3d(&maps.b, &full_bar[ps.stage], sa + kABytes, kc * kBlockK, t.nt * BLOCK_N,
-                        t.phase * p.ntaps + i);
+            tma_load_4d(&maps.b, &full_bar[ps.stage], sa + kABytes, 0, t.nt * BLOCK_N, kc, t.phase * p.ntaps + i);
           }
           __syncwarp();
           ps.advance<C::kStages>();
@@ -311,11 +377,11 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
     uint32_t acc_phase = 0;
     constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 0, 0);
     const uint32_t smem_lo = smem_u32(smem) >> 4;          // descriptor start-address units (16 B)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
-      const uint64_t tm = tap_mask(p, taps, t);
-      const int nall = __popcll(tm) * p.kchunks;
-      const int nsteps = (int)(((int64_t)nall * (t.split + 1)) / p.ksplits) - (int)(((int64_t)nall * t.split) / p.ksplits);   // > 0
+    WorkIter it;
+    it.init(p);
+    Work w;
+    while (it.next(p, taps, w)) {
+      const int nsteps = w.hi - w.lo;   // > 0
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -350,8 +416,12 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
     const int in = row / (p.bw * p.bh);
     const bool ep_leader = (threadIdx.x == 64);     // first epilogue thread: issues / tracks the TMA stores
     uint32_t sg = 0;                                // running 64-column group counter -> staging buffer
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    const bool partial = p.ksplits > 1 || p.team;
+    WorkIter it;
+    it.init(p);
+    Work w;
+    while (it.next(p, taps, w)) {
+      const TileCoord& t = w.t;
       const int ay = t.phase / p.s, ax = t.phase % p.s;
       const int qx = t.x0 + iw, qy = t.y0 + ih, n = t.n0 + in;
       const int ox = qx * p.os + ax - p.opad, oy = qy * p.os + ay - p.opad;
@@ -381,7 +451,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
-        if (valid && p.ksplits > 1) {
+        if (valid && partial) {
           float4* w4 = reinterpret_cast<float4*>(p.ws + (int64_t)t.split * p.ws_slice + obase + c0);
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -526,8 +596,8 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
             mbar_arrive_expect_tx(&fullB[pb.stage], (uint32_t)C::kBBytes);
 #pragma unroll
             for (int j = 0; j < C::kGroup; ++j)
-              tma_load_3d(&maps.b, &fullB[pb.stage], smem_b + pb.stage * C::kBBytes + j * C::kTapBytes, kc * kBlockK,
-                          nt * BLOCK_N, tg + j);
+              tma_load_4d(&maps.b, &fullB[pb.stage], smem_b + pb.stage * C::kBBytes + j * C::kTapBytes, 0, nt * BLOCK_N, kc,
+                          tg + j);
           }
           __syncwarp();
           pb.advance<C::kBStages>();
@@ -708,7 +778,7 @@ slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
       mbar_arrive_expect_tx(wfull, (uint32_t)kSlab3WBytes);
       for (int kc = 0; kc < KCH; ++kc)
         for (int ky = 0; ky < 3; ++ky)     // box (64 k, 64 channels, 3 taps) -> rows kx*64 + c
-          tma_load_3d(&maps.b, wfull, smem_w + (kc * 3 + ky) * (3 * 64 * 128), kc * 64, nt * 64, ky * 3);
+          tma_load_4d(&maps.b, wfull, smem_w + (kc * 3 + ky) * (3 * 64 * 128), 0, nt * 64, kc, ky * 3);
     }
     __syncwarp();
     PipeState pa;
@@ -849,9 +919,39 @@ struct WgradParams {
   int dw_row_stride;          // elements between consecutive ci rows (= Cout for HWIO)
   int dw_col_stride;          // elements between consecutive co (1 for HWIO)
   int direct;                 // always 1: plain 16-byte stores into dW (single split) or into per-split partial buffers
+  int skip_oob;               // 1: pixel boxes whose shifted x boxes lie entirely in the SAME padding (for both row blocks
+                              //    of the item) are skipped: no TMA, no MMA (conv6: 7x7 taps on a 5x18 map, 38 % of the pairs)
   int64_t part_stride;        // elements between the partial buffers of consecutive splits (0: dw is the result itself)
   float* dw;
 };
+
+// wgrad: does pixel box (x0, y0) contribute to the item's row blocks?  A tap whose shifted box is entirely outside
+// the image reads only TMA zero fill.
+__device__ __forceinline__ bool wgrad_box_active(const WgradParams& p, int x0, int y0, int dx0, int dy0, int dx1, int dy1) {
+  const int xa = x0 + dx0, ya = y0 + dy0, xb = x0 + dx1, yb = y0 + dy1;
+  const bool a = !(ya + p.bh <= 0 || ya >= p.H || xa + p.bw <= 0 || xa >= p.W);
+  const bool b = !(yb + p.bh <= 0 || yb >= p.H || xb + p.bw <= 0 || xb >= p.W);
+  return a || b;
+}
+
+// number of contributing boxes among pixel tiles [pt0, pt1) (w fastest, then h, then n); 0 active -> all (the item still
+// has to produce its zeros)
+__device__ __forceinline__ int wgrad_count_active(const WgradParams& p, int pt0, int pt1, int dx0, int dy0, int dx1, int dy1) {
+  if (!p.skip_oob) return pt1 - pt0;
+  int x0 = (pt0 % p.tiles_w) * p.bw;
+  int y0 = ((pt0 / p.tiles_w) % p.tiles_h) * p.bh;
+  int n = 0;
+  for (int pt = pt0; pt < pt1; ++pt) {
+    n += wgrad_box_active(p, x0, y0, dx0, dy0, dx1, dy1) ? 1 : 0;
+    x0 += p.bw;
+    if (x0 >= p.tiles_w * p.bw) {
+      x0 = 0;
+      y0 += p.bh;
+      if (y0 >= p.tiles_h * p.bh) y0 = 0;
+    }
+  }
+  return n;
+}
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kWgradThreads, 1)
@@ -905,12 +1005,18 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
       int x0 = (pt0 % p.tiles_w) * p.bw;
       int y0 = ((pt0 / p.tiles_w) % p.tiles_h) * p.bh;
       int n0 = (pt0 / (p.tiles_w * p.tiles_h)) * p.bn;
-      for (int pt = pt0; pt < pt1; pt += C::kPB) {
-        const int nb = min(C::kPB, pt1 - pt);
-        mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
-        const bool leader = elect_one();
-        if (leader) mbar_arrive_expect_tx(&full_bar[ps.stage], (uint32_t)(nb * C::kBoxBytes));
-        for (int bi = 0; bi < nb; ++bi) {
+      int nact = wgrad_count_active(p, pt0, pt1, dx0, dy0, dx1, dy1);
+      const bool all = (nact == 0) || !p.skip_oob;
+      if (nact == 0) nact = pt1 - pt0;
+      int done = 0;
+      const bool leader = elect_one();
+      for (int pt = pt0; pt < pt1; ++pt) {
+        if (all || wgrad_box_active(p, x0, y0, dx0, dy0, dx1, dy1)) {
+          const int bi = done % C::kPB;
+          if (bi == 0) {
+            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+            if (leader) mbar_arrive_expect_tx(&full_bar[ps.stage], (uint32_t)(min(C::kPB, nact - done) * C::kBoxBytes));
+          }
           if (leader) {
             uint8_t* sa = smem + ps.stage * C::kStageBytes + bi * C::kBoxBytes;
             tma_load_4d(&maps.a[m0], &full_bar[ps.stage], sa, c0, x0 + dx0, y0 + dy0, n0);
@@ -919,16 +1025,19 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
             for (int j = 0; j < BLOCK_N / 64; ++j)
               tma_load_4d(&maps.b, &full_bar[ps.stage], sa + kABytes + j * 8192, nt * BLOCK_N + j * 64, x0, y0, n0);
           }
-          // next pixel box (w fastest, then h, then n) without divisions
-          x0 += p.bw;
-          if (x0 >= p.tiles_w * p.bw) {
-            x0 = 0;
-            y0 += p.bh;
-            if (y0 >= p.tiles_h * p.bh) { y0 = 0; n0 += p.bn; }
+          ++done;
+          if (bi == C::kPB - 1 || done == nact) {
+            __syncwarp();
+            ps.advance<C::kStages>();
           }
         }
-        __syncwarp();
-        ps.advance<C::kStages>();
+        // next pixel box (w fastest, then h, then n) without divisions
+        x0 += p.bw;
+        if (x0 >= p.tiles_w * p.bw) {
+          x0 = 0;
+          y0 += p.bh;
+          if (y0 >= p.tiles_h * p.bh) { y0 = 0; n0 += p.bn; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -941,8 +1050,15 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
       const int split = item / (p.n_tiles * p.n_rbp);
       const int pt0 = split * per_split;
       const int pt1 = min(pt0 + per_split, n_ptiles);
-      const int nboxes = pt1 - pt0;
-      if (nboxes <= 0) continue;
+      if (pt1 - pt0 <= 0) continue;
+      int nboxes = pt1 - pt0;
+      if (p.skip_oob) {
+        const int rbp = (item / p.n_tiles) % p.n_rbp;
+        const int rb0 = 2 * rbp, rb1 = (2 * rbp + 1 < p.n_rb) ? 2 * rbp + 1 : 2 * rbp;
+        const int tap0 = rb0 / p.kchunks_in, tap1 = rb1 / p.kchunks_in;
+        const int na = wgrad_count_active(p, pt0, pt1, taps.dx[tap0], taps.dy[tap0], taps.dx[tap1], taps.dy[tap1]);
+        if (na > 0) nboxes = na;
+      }
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -1072,6 +1188,73 @@ __global__ void __launch_bounds__(256) epilogue_finish_kernel(const float* __res
   }
 }
 
+// The same for the team stream-K schedule: the number of partial slices differs per column (nt, y-tile, x-tile).
+struct TeamFinish {
+  int T, total, ncols, tiles_w, tiles_h, bw, bh, H, W, block_n;
+  int prefix[kMaxCols + 1];
+};
+
+__global__ void __launch_bounds__(256) epilogue_finish_team_kernel(const float* __restrict__ ws, const TeamFinish tf, int64_t slice,
+                                                                   const float* __restrict__ bias,
+                                                                   const bf16* __restrict__ residual,
+                                                                   const bf16* __restrict__ mask, void* __restrict__ out,
+                                                                   int out_f32, int relu, float scale, int64_t rows, int C) {
+  const int C8 = C >> 3;
+  const int64_t total = rows * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    const int64_t row = i / C8;
+    const int64_t base = row * C + c;
+    const int x = (int)(row % tf.W), y = (int)((row / tf.W) % tf.H);
+    const int col = ((c / tf.block_n) * tf.tiles_h + y / tf.bh) * tf.tiles_w + x / tf.bw;
+    const int cs = tf.prefix[col], ce = tf.prefix[col + 1];
+    const int nparts = team_of_step(ce - 1, tf.T, tf.total) - team_of_step(cs, tf.T, tf.total) + 1;
+    float v[8];
+    const float4 a = *reinterpret_cast<const float4*>(ws + base), b = *reinterpret_cast<const float4*>(ws + base + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    for (int s = 1; s < nparts; ++s) {
+      const float4 a2 = *reinterpret_cast<const float4*>(ws + s * slice + base);
+      const float4 b2 = *reinterpret_cast<const float4*>(ws + s * slice + base + 4);
+      v[0] += a2.x; v[1] += a2.y; v[2] += a2.z; v[3] += a2.w; v[4] += b2.x; v[5] += b2.y; v[6] += b2.z; v[7] += b2.w;
+    }
+    if (bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += __ldg(bias + c + j);
+    }
+    if (residual) {
+      const uint4 u = *reinterpret_cast<const uint4*>(residual + base);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&u.x)[j]);
+        v[2 * j] += f.x; v[2 * j + 1] += f.y;
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (mask) {
+      const uint4 u = *reinterpret_cast<const uint4*>(mask + base);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&u.x)[j]);
+        if (!(f.x > 0.f)) v[2 * j] = 0.f;
+        if (!(f.y > 0.f)) v[2 * j + 1] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= scale;
+    if (out_f32) {
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + base);
+      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out) + base) =
+          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+  }
+}
+
 // grow-only device scratch owned by the context (first use allocates; never on the steady-state path)
 int ensure_workspace(segk_ctx* ctx, size_t bytes) { return segk_grow(ctx, &ctx->ws, &ctx->ws_bytes, bytes, "split-K workspace"); }
 
@@ -1149,6 +1332,26 @@ int encode_weight_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int K, in
   return SEGK_OK;
 }
 
+// Kernel-layout weights are BLOCKED: [T taps][KC = ceil(K/64) chunks][Nrows][64 k] bf16, i.e. the operand tile of
+// one (tap, k-chunk) -- Nrows x 128 bytes -- is one contiguous run in memory (an N = 256 tile: 32 KB).  With the
+// plain [T][Nrows][K] layout a tile is 256 pieces of 128 B at a stride of 2K bytes; for conv6's dgrad (K = 4096: 8 KB
+// stride, 205 MB of weights) ncu showed the tiles evicted from L2 before the CTAs sharing them arrived (L2 hit 49 %,
+// 2.2 GB of DRAM reads for 0.68 GB requested).  4-D map (64, Nrows, KC, T), box (64, box_rows, 1, box_taps).
+int encode_weight_map_blocked(segk_ctx* ctx, CUtensorMap* m, const void* base, int K, int Nrows, int T, int box_rows,
+                              int box_taps = 1) {
+  const int KC = ceil_div(K, 64);
+  cuuint64_t dims[4] = {64, (cuuint64_t)Nrows, (cuuint64_t)KC, (cuuint64_t)T};
+  cuuint64_t strides[3] = {128, (cuuint64_t)Nrows * 128, (cuuint64_t)KC * Nrows * 128};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, (cuuint32_t)box_taps};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = ctx->encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return segk_fail(ctx, SEGK_ECUDA, "cuTensorMapEncodeTiled(blocked weights K=%d N=%d T=%d) failed: %d", K, Nrows, T, (int)r);
+  return SEGK_OK;
+}
+
 // tuning overrides for sweeps (tools/sweep_tiles.py), read once per context in segk_tc_init;
 // 0 = use the heuristics
 int env_int(const char* name, int dflt = 0) {
@@ -1174,9 +1377,9 @@ int launch_igemm_t(segk_ctx* ctx, const TensorMaps& maps, const IgemmParams& p, 
 }
 
 int launch_igemm(segk_ctx* ctx, int block_n, const TensorMaps& maps, const IgemmParams& p, const TapTable& taps,
-                 cudaStream_t st) {
+                 cudaStream_t st, int team_grid = 0) {
   const int total = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.ksplits;
-  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  const int grid = team_grid > 0 ? team_grid : (total < ctx->sm_count ? total : ctx->sm_count);
   switch (block_n) {
     case 256: return launch_igemm_t<256>(ctx, maps, p, taps, grid, st);
     case 128: return launch_igemm_t<128>(ctx, maps, p, taps, grid, st);
@@ -1226,17 +1429,11 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
   if (rc) return rc;
   maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
   if (fused3) {
-    // box (64 k, 64 channels, 3 taps): the three kx taps of one ky land as one [192][64] operand
-    cuuint64_t dims[3] = {(cuuint64_t)Ck, (cuuint64_t)Cn, 9};
-    cuuint64_t strides[2] = {(cuuint64_t)Ck * 2, (cuuint64_t)Ck * Cn * 2};
-    cuuint32_t box[3] = {64, 64, 3};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = ctx->encode_tiled(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(wt), dims, strides, box,
-                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return segk_fail(ctx, SEGK_ECUDA, "%s: cuTensorMapEncodeTiled(3-tap weights) failed: %d", what, (int)r);
+    // box (64 k, 64 channels, 1 chunk, 3 taps): the three kx taps of one ky land as one [192][64] operand
+    rc = encode_weight_map_blocked(ctx, &maps.b, wt, Ck, Cn, 9, 64, 3);
+    if (rc) return rc;
   } else {
-    rc = encode_weight_map(ctx, &maps.b, wt, Ck, Cn, 9, block_n);
+    rc = encode_weight_map_blocked(ctx, &maps.b, wt, Ck, Cn, 9, block_n);
     if (rc) return rc;
   }
   SlabParams p;
@@ -1300,7 +1497,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   int rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Ck, Ck, (int64_t)W * Ck, (int64_t)H * W * Ck, b.bw, b.bh, b.bn);
   if (rc) return rc;
   maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
-  rc = encode_weight_map(ctx, &maps.b, wt, Ck, Cn, kh * kw, block_n);
+  rc = encode_weight_map_blocked(ctx, &maps.b, wt, Ck, Cn, kh * kw, block_n);
   if (rc) return rc;
   IgemmParams p;
   memset(&p, 0, sizeof(p));
@@ -1327,6 +1524,53 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
     // one wave of work units.  Measured (tools/time_conv6.py, conv6 dgrad: 50 tiles x 2240 k-steps): 2 splits
     // 483 us, 1: 766, 3: 596, 5: 562, 8: 692, 14: 918 -- more splits than one wave lets the m-tiles that share
     // a weight slice drift apart in K, and the 205 MB of weights stream from DRAM several times over
+    // team stream-K: every CTA gets the same number of k-steps; the tiles_n CTAs of a team share each weight slice
+    const int ncols = p.n_tiles * p.tiles_h * p.tiles_w;
+    if (force_ks <= 0 && ctx->teamk && ncols <= kMaxCols && p.tiles_n <= ctx->sm_count) {
+      TeamFinish tf;
+      memset(&tf, 0, sizeof(tf));
+      int total_steps = 0;
+      for (int c = 0; c < ncols; ++c) {
+        const int x0 = (c % p.tiles_w) * b.bw, y0 = ((c / p.tiles_w) % p.tiles_h) * b.bh;
+        int act = 0;
+        for (int i = 0; i < p.ntaps; ++i) {
+          const int ya = y0 + taps.dy[i], xa = x0 + taps.dx[i];
+          act += !(ya + b.bh <= 0 || ya >= H || xa + b.bw <= 0 || xa >= W);
+        }
+        if (act == 0) act = p.ntaps;                      // mirrors tap_mask(): an all-padding tile still produces zeros
+        p.team_prefix[c] = total_steps;
+        total_steps += act * p.kchunks;
+      }
+      p.team_prefix[ncols] = total_steps;
+      int T = ctx->sm_count / p.tiles_n;
+      if (T > total_steps / 8) T = total_steps / 8;       // at least 8 k-steps per team
+      if (T >= 2 && (int64_t)T * p.tiles_n * 100 >= (int64_t)85 * ctx->sm_count) {
+        int max_parts = 1;
+        for (int c = 0; c < ncols; ++c) {
+          const int np = team_of_step(p.team_prefix[c + 1] - 1, T, total_steps) - team_of_step(p.team_prefix[c], T, total_steps) + 1;
+          if (np > max_parts) max_parts = np;
+        }
+        const size_t slice = (size_t)N * H * W * Cn;
+        rc = ensure_workspace(ctx, sizeof(float) * slice * max_parts);
+        if (rc) return rc;
+        p.team = 1; p.team_T = T; p.team_members = p.tiles_n; p.team_ncols = ncols; p.team_total = total_steps;
+        p.ws = (float*)ctx->ws;
+        p.ws_slice = (int64_t)slice;
+        rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream, T * p.tiles_n);
+        if (rc) return rc;
+        tf.T = T; tf.total = total_steps; tf.ncols = ncols; tf.tiles_w = p.tiles_w; tf.tiles_h = p.tiles_h;
+        tf.bw = b.bw; tf.bh = b.bh; tf.H = H; tf.W = W; tf.block_n = block_n;
+        memcpy(tf.prefix, p.team_prefix, sizeof(tf.prefix));
+        const int64_t rows = (int64_t)N * H * W;
+        int64_t blocks = ceil_div64(rows * (Cn / 8), 256);
+        if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
+        epilogue_finish_team_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+            (const float*)ctx->ws, tf, (int64_t)slice, bias, (const bf16*)residual, (const bf16*)mask, y, out_f32, relu, scale,
+            rows, Cn);
+        SEGK_LAUNCHED(ctx, "igemm team stream-K finish");
+        return SEGK_OK;
+      }
+    }
     int ks = ctx->sm_count / tiles;
     if (force_ks > 0) ks = force_ks;
     if (ks > p.kchunks) ks = p.kchunks;   // ksplits <= kchunks <= k-steps of any tile: no split is empty
@@ -1419,7 +1663,7 @@ int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float*
   int rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Cin, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin, b.bw, b.bh, b.bn);
   if (rc) return rc;
   maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
-  rc = encode_weight_map(ctx, &maps.b, wk, Cin, Cout, s * s * 4, block_n);
+  rc = encode_weight_map_blocked(ctx, &maps.b, wk, Cin, Cout, s * s * 4, block_n);
   if (rc) return rc;
   IgemmParams p;
   memset(&p, 0, sizeof(p));
@@ -1458,7 +1702,7 @@ int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const voi
   memset(&maps, 0, sizeof(maps));
   int rc = encode_decimated_maps(ctx, maps, dy, N, H, W, Cout, s, b);
   if (rc) return rc;
-  rc = encode_weight_map(ctx, &maps.b, wd, Cout, Cin, k * k, block_n);
+  rc = encode_weight_map_blocked(ctx, &maps.b, wd, Cout, Cin, k * k, block_n);
   if (rc) return rc;
   IgemmParams p;
   memset(&p, 0, sizeof(p));
@@ -1621,6 +1865,8 @@ int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, i
   SEGK_REQUIRE(ctx, p.direct, "conv2d_wgrad: %d splits of %zu weights exceed the 1 GiB partial-sum workspace", p.splits, n_dw);
   TapTable taps;
   conv_taps(taps, kh, kw);
+  // (pixel box, tap) pairs that only see SAME padding carry no information: skip them when there are any
+  p.skip_oob = (active_taps_1d(W, b.bw, kw) * active_taps_1d(H, b.bh, kh) < (int64_t)p.tiles_w * p.tiles_h * kh * kw) ? 1 : 0;
   const int total = p.splits * p.n_rbp * p.n_tiles;
   const int grid = total < ctx->sm_count ? total : ctx->sm_count;
   switch (block_n) {
@@ -1644,6 +1890,7 @@ int segk_tc_init(segk_ctx* ctx) {
   ctx->slab_mode = env_int("SEGK_SLAB", 1);
   ctx->tma_store = env_int("SEGK_TMA_STORE", 1);
   ctx->slab3 = env_int("SEGK_SLAB3", 1);
+  ctx->teamk = env_int("SEGK_TEAMK", 1);
   cudaError_t e = cudaSuccess;
 #define SEGK_SMEM_ATTR(kern, bytes) \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)

@@ -106,14 +106,14 @@ class Ops:
         if self.profile is not None:
             self._work = (work, unit)
 
-    # ---- weight packing -------------------------------------------------------------
+    # ---- weight packing: kernel layouts are blocked by 64-wide k-chunks, [T][ceil(K/64)][rows][64] ------
     def pack_conv_weights(self, w, wk=None, wd=None):
         kh, kw, cin, cout = w.shape
         dev = w.device
         if wk is None:
-            wk = torch.empty((kh * kw, cout, cin), dtype=torch.bfloat16, device=dev)
+            wk = torch.empty((kh * kw, -(-cin // 64), cout, 64), dtype=torch.bfloat16, device=dev)
         if wd is None:
-            wd = torch.empty((kh * kw, cin, cout), dtype=torch.bfloat16, device=dev)
+            wd = torch.empty((kh * kw, -(-cout // 64), cin, 64), dtype=torch.bfloat16, device=dev)
         self._w(8.0 * w.numel(), "byte")
         self.call("segk_pack_conv_weights", _p(w), _p(wk), _p(wd), kh, kw, cin, cout, _stream())
         return wk, wd
@@ -122,20 +122,20 @@ class Ops:
         k, _, cout, cin = w.shape
         dev = w.device
         if wk is None:
-            wk = torch.empty((s * s, 4, cout, cin), dtype=torch.bfloat16, device=dev)
+            wk = torch.empty((s * s * 4, -(-cin // 64), cout, 64), dtype=torch.bfloat16, device=dev)
         if wd is None:
-            wd = torch.empty((k * k, cin, cout), dtype=torch.bfloat16, device=dev)
+            wd = torch.empty((k * k, -(-cout // 64), cin, 64), dtype=torch.bfloat16, device=dev)
         self._w(8.0 * w.numel(), "byte")
         self.call("segk_pack_deconv_weights", _p(w), _p(wk), _p(wd), k, s, cin, cout, _stream())
         return wk, wd
 
     def pack_matrix(self, w3, cp=None, tr=None):
-        """w3 fp32 [T][A][B] -> cp bf16 [T][A][B], tr bf16 [T][B][A]."""
+        """w3 fp32 [T][A][B] -> cp bf16 [T][ceil(B/64)][A][64] (rows A, k = B), tr bf16 [T][ceil(A/64)][B][64]."""
         t, a, b = w3.shape
         if cp is None:
-            cp = torch.empty((t, a, b), dtype=torch.bfloat16, device=w3.device)
+            cp = torch.empty((t, -(-b // 64), a, 64), dtype=torch.bfloat16, device=w3.device)
         if tr is None:
-            tr = torch.empty((t, b, a), dtype=torch.bfloat16, device=w3.device)
+            tr = torch.empty((t, -(-a // 64), b, 64), dtype=torch.bfloat16, device=w3.device)
         self._w(8.0 * w3.numel(), "byte")
         self.call("segk_pack_matrix", _p(w3), _p(cp), _p(tr), t, a, b, _stream())
         return cp, tr

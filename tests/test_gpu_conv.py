@@ -355,3 +355,47 @@ def test_slab_kernels_stay_inside_their_outputs(ops, cuda_device, shape):
     ops.conv2d_first_wgrad(img, dy1, dw1, 3, 3, dbias=db1)
     chk1("first-layer wgrad")
     chk2("first-layer bias grad")
+
+
+@pytest.mark.parametrize("shape", [(16, 5, 18, 256, 256, 7), (2, 5, 18, 512, 1024, 7), (9, 5, 18, 128, 512, 5)])
+def test_team_stream_k_fwd_dgrad_and_wgrad_box_skipping(ops, cuda_device, shape):
+    """conv6-like layers (k > map height, few output tiles, long K walk): the team stream-K schedule of
+    igemm_kernel (several batch tiles per team, columns with different tap counts, pieces of a column in
+    different partial slices) against the oracle and against the plain split-K path; and the weight gradient
+    with all-padding (pixel box, tap) pairs skipped."""
+    n, h, w, ci, co, k = shape
+    x, wt, b = _conv_case(shape, 40)
+    rng = np.random.default_rng(41)
+    dy = bf16_grid(rng.standard_normal((n, h, w, co)))
+    act = bf16_grid(rng.standard_normal((n, h, w, ci)))
+    xt = torch.tensor(x, requires_grad=True)
+    wtt = torch.tensor(wt, requires_grad=True)
+    z = T.conv2d_same(xt, wtt)
+    y_ref = T.relu(T.bias_add(z, torch.tensor(b))).detach().numpy()
+    z.backward(torch.tensor(dy))
+    dx_ref = xt.grad.numpy() * (act > 0)
+    wk, wd = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    xd, dyd, actd, bd = dev_bf16(x, cuda_device), dev_bf16(dy, cuda_device), dev_bf16(act, cuda_device), dev_f32(b, cuda_device)
+    out = {}
+    try:
+        for mode in (1, 0):
+            ops.ctx.set_tuning("teamk", mode)
+            y = torch.full((n, h, w, co), 7.0, dtype=torch.bfloat16, device=cuda_device)
+            dx = torch.full((n, h, w, ci), 7.0, dtype=torch.bfloat16, device=cuda_device)
+            ops.conv2d_fwd(xd, wk, bd, y, k, k, relu=True)
+            ops.conv2d_dgrad(dyd, wd, dx, k, k, relu_mask=actd)
+            torch.cuda.synchronize()
+            assert_close(host(y), y_ref, TOL_BF16, f"team-K fwd {shape} mode {mode}")
+            assert_close(host(dx), dx_ref, TOL_BF16, f"team-K dgrad {shape} mode {mode}")
+            out[mode] = (host(y), host(dx))
+            # deterministic: ordered partial sums, no atomics
+            y2 = torch.empty_like(y)
+            ops.conv2d_fwd(xd, wk, bd, y2, k, k, relu=True)
+            torch.cuda.synchronize()
+            assert torch.equal(y, y2)
+    finally:
+        ops.ctx.set_tuning("teamk", 1)
+    dw = torch.full((k, k, ci, co), 7.0, dtype=torch.float32, device=cuda_device)
+    ops.conv2d_wgrad(xd, dyd, dw, k, k)
+    torch.cuda.synchronize()
+    assert_close(host(dw), wtt.grad.numpy(), TOL_F32, f"wgrad with box skipping {shape}")

@@ -212,8 +212,8 @@ def test_overlay_mask_bit_exact(ops, cuda_device, c):
 
 @pytest.mark.parametrize("shape", [(3, 3, 64, 128), (1, 1, 192, 64), (7, 7, 64, 64), (3, 3, 32, 96), (3, 3, 3, 64)])
 def test_pack_conv_weights_layouts_bit_exact(ops, cuda_device, shape):
-    """fp32 HWIO master (FCN.py:125) -> wk[tap][Cout][Cin] and wd[rot180 tap][Cin][Cout], both the
-    round-to-nearest-even bf16 of the master (64-wide vectorised kernel and the generic one)."""
+    """fp32 HWIO master (FCN.py:125) -> wk[tap][Cin/64][Cout][64] and wd[rot180 tap][Cout/64][Cin][64]: the
+    round-to-nearest-even bf16 of the master in the blocked kernel layout, zero-padded in the k dimension."""
     kh, kw, ci, co = shape
     rng = np.random.default_rng(40)
     w = rng.standard_normal(shape).astype(np.float32)
@@ -221,10 +221,16 @@ def test_pack_conv_weights_layouts_bit_exact(ops, cuda_device, shape):
     wk, wd = ops.pack_conv_weights(wd_)
     torch.cuda.synchronize()
     ref = torch.as_tensor(w).to(torch.bfloat16).float().numpy().reshape(kh * kw, ci, co)
-    got_k = wk.float().cpu().numpy().reshape(kh * kw, co, ci)
-    got_d = wd.float().cpu().numpy().reshape(kh * kw, ci, co)
-    assert np.array_equal(got_k, ref.transpose(0, 2, 1))
-    assert np.array_equal(got_d, ref[::-1])
+
+    def blocked(m):      # [T][rows][K] -> [T][ceil(K/64)][rows][64]
+        t, rows, k = m.shape
+        kc = -(-k // 64)
+        p = np.zeros((t, rows, kc * 64), np.float32)
+        p[:, :, :k] = m
+        return p.reshape(t, rows, kc, 64).transpose(0, 2, 1, 3)
+
+    assert np.array_equal(wk.float().cpu().numpy(), blocked(ref.transpose(0, 2, 1)))
+    assert np.array_equal(wd.float().cpu().numpy(), blocked(ref[::-1]))
 
 
 def test_onehot_to_ids_and_argmax(ops, cuda_device):
