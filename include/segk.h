@@ -40,9 +40,10 @@ typedef struct segk_ctx segk_ctx;
  * One context per device.  All work is enqueued on the caller's stream.  A context owns a few grow-only
  * device scratch buffers; calls that share one must not overlap on DIFFERENT streams:
  *   - segk_conv2d_wgrad / segk_deconv2d_wgrad (per-split partial sums)            -> one stream
- *   - split-K segk_conv2d_fwd / _dgrad and segk_conv2d_first_wgrad                -> one stream
+ *   - split-K segk_conv2d_fwd / _dgrad, segk_conv2d_first_wgrad, any dgrad with dx_colsum,
+ *     segk_maxpool2x2_bwd with dbias                                              -> one stream
  *   - segk_bias_grad                                                              -> one stream
- *   - segk_conv2d_small_wgrad                                                     -> one stream
+ *   - segk_conv2d_small_wgrad / segk_deconv2d_small_wgrad                         -> one stream
  * (fcn.py: wgrad stream / main stream / side stream / main stream).  Use one context per stream otherwise. */
 int segk_abi_version(void);
 int segk_create(int device, segk_ctx** out);
@@ -54,7 +55,7 @@ int segk_sm_count(segk_ctx* ctx);
 /* Kernel-selection overrides (also read once at segk_create from SEGK_SLAB / SEGK_SLAB3 / SEGK_WSLAB /
  * SEGK_TMA_STORE / SEGK_TEAMK / SEGK_FORCE_BN / SEGK_FORCE_KSPLIT / SEGK_FORCE_WSPLIT): key in {"slab", "slab3",
  * "wslab" (0 off, 1 auto, 2 wherever legal), "tma_store" (0|1), "teamk" (0|1: team stream-K instead of plain
- * split-K for few-tile / long-K layers), "force_bn" (0|64|128|256), "force_ksplit", "force_wsplit" (0 = heuristic)}.  Every setting computes the same sums (fp32
+ * split-K for few-tile / long-K layers), "tail_wide" (0|1: 16-byte-access forms of conv8 / conv_t1 and their gradients), "force_bn" (0|64|128|256), "force_ksplit", "force_wsplit" (0 = heuristic)}.  Every setting computes the same sums (fp32
  * accumulation order differs between kernels). */
 int segk_set_tuning(segk_ctx* ctx, const char* key, int value);
 
@@ -80,9 +81,12 @@ int segk_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* b
  *   relu_mask (shape of dx, bf16, or NULL) is the forward activation whose ReluGrad is
  *   fused here, residual (or NULL) a second gradient path into the same tensor (AddN at
  *   pool3/pool4), and scale = 1/keep_prob folds the dropout backward (FCN.py:165-167).
+ *   dx_colsum (fp32 [Cin] or NULL): the column sums of dx over all pixels from the same pass, i.e. the
+ *   BiasAddGrad of the PRODUCER conv_layer, whose pre-activation gradient dx is (summed in the epilogue
+ *   from the fp32 values, fixed order; a separate pass over dx only for split-K / weight-heavy layers).
  */
 int segk_conv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask,
-                      const void* residual, void* dx, float scale, int N, int H, int W,
+                      const void* residual, void* dx, float* dx_colsum, float scale, int N, int H, int W,
                       int Cin, int Cout, int kh, int kw, void* stream);
 
 /*
@@ -105,9 +109,10 @@ int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float*
                       int k, int s, unsigned flags, void* stream);
 
 /* gradient of deconv_layer wrt its input = conv2d(dy, W, stride s);
- * dy [N,sH,sW,Cout] bf16, wd [k*k][Cout/64][Cin][64] bf16, dx [N,H,W,Cin] bf16. k=4, s=2. */
+ * dy [N,sH,sW,Cout] bf16, wd [k*k][Cout/64][Cin][64] bf16, dx [N,H,W,Cin] bf16. k=4, s=2.
+ * dx_colsum: as for segk_conv2d_dgrad. */
 int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask,
-                        void* dx, int N, int H, int W, int Cin, int Cout, int k, int s,
+                        void* dx, float* dx_colsum, int N, int H, int W, int Cin, int Cout, int k, int s,
                         void* stream);
 
 /* gradient of deconv_layer wrt W[k,k,Cout,Cin] (fp32). k=4, s=2. */
@@ -234,9 +239,11 @@ int segk_maxpool2x2_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int
  * shape of dx or NULL, is a second gradient path into the same tensor, e.g. a skip connection).
  * act_is_pooled != 0: `act` is the POOLED tensor y [N,H/2,W/2,C] instead of the pre-pool one (residual
  * must be NULL): at the routed element the pre-pool activation equals the pooled value, so the result is
- * bit-identical while a quarter of the mask bytes are read. */
+ * bit-identical while a quarter of the mask bytes are read.
+ * dbias (fp32 [C], pooled mode only, or NULL): BiasAddGrad of the conv_layer in front of the pool from the same
+ * pass -- db[c] = sum over dx[..., c] = sum of the masked dy (every dy lands on exactly one window element). */
 int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const void* act, int act_is_pooled,
-                        const void* residual, void* dx, int N, int H, int W, int C, void* stream);
+                        const void* residual, void* dx, float* dbias, int N, int H, int W, int C, void* stream);
 
 /* tf.nn.dropout (FCN.py:165-167): y = x * keep_mask / keep_prob.  mask (u8 0/1) is used
  * when non-NULL (parity runs); otherwise Philox4x32-10(seed, element index). Same call is

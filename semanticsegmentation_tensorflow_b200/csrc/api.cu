@@ -51,6 +51,8 @@ int segk_destroy(segk_ctx* ctx) {
   if (ctx && ctx->ws2) cudaFree(ctx->ws2);
   if (ctx && ctx->ws3) cudaFree(ctx->ws3);
   if (ctx && ctx->ws4) cudaFree(ctx->ws4);
+  if (ctx && ctx->ws5) cudaFree(ctx->ws5);
+  if (ctx && ctx->ws6) cudaFree(ctx->ws6);
   delete ctx;
   return SEGK_OK;
 }
@@ -64,6 +66,7 @@ int segk_set_tuning(segk_ctx* ctx, const char* key, int value) {
   else if (!strcmp(key, "slab3")) ctx->slab3 = value;
   else if (!strcmp(key, "wslab")) ctx->wslab = value;
   else if (!strcmp(key, "teamk")) ctx->teamk = value;
+  else if (!strcmp(key, "tail_wide")) ctx->tail_wide = value;
   else if (!strcmp(key, "force_bn")) ctx->force_bn = value;
   else if (!strcmp(key, "force_ksplit")) ctx->force_ksplit = value;
   else if (!strcmp(key, "force_wsplit")) ctx->force_wsplit = value;

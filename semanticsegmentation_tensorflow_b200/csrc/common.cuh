@@ -23,7 +23,11 @@ struct segk_ctx {
   int slab_mode = 1;        // SEGK_SLAB: 0 off, 1 auto, 2 wherever legal
   int tma_store = 1;        // SEGK_TMA_STORE: bf16 conv outputs leave through smem + TMA store
   int slab3 = 1;            // SEGK_SLAB3: kx-fused N = 192 slab kernel with resident weights for Ck = 64
-  int teamk = 1;            // SEGK_TEAMK: team stream-K instead of plain split-K for few-tile / long-K layers (conv6 dgrad)
+  int tail_wide = 1;        // SEGK_TAIL_WIDE: 16-byte-access forms of the few-pixel / wide-channel tail layers (conv8, conv_t1)
+  int teamk = 0;            // SEGK_TEAMK: team stream-K instead of plain split-K for few-tile / long-K layers.  Off by default:
+                            //   measured on conv6's dgrad (B=32) 595 us vs 471 us for 2-way split-K -- the teams walk 29 different
+                            //   K positions at once, the members of a team drift apart, and ncu shows L2 hit 49 % / 2.2 GB of DRAM
+                            //   reads (profiles/r2_conv6_probe.md); it needs cluster-multicast weight tiles to pay off
   void* ws = nullptr;       // grow-only scratch for split-K partial sums (tcconv.cu)
   size_t ws_bytes = 0;
   void* ws2 = nullptr;      // grow-only scratch for per-block BiasAddGrad partials (elementwise.cu)
@@ -31,6 +35,10 @@ struct segk_ctx {
   int wslab = 1;            // SEGK_WSLAB: slab-formulated wgrad for 3x3 layers with Cin 64/128 on large maps (2 = wherever legal)
   void* ws4 = nullptr;      // grow-only scratch for the slab wgrad's per-split partial sums (wslab.cu; own buffer:
   size_t ws4_bytes = 0;     //   that kernel may run on a different stream than the users of ws)
+  void* ws6 = nullptr;      // grow-only scratch for the dgrad epilogues' column-sum partial rows (tcconv.cu; main stream)
+  size_t ws6_bytes = 0;
+  void* ws5 = nullptr;      // grow-only scratch for the pool-backward's BiasAddGrad partial rows (elementwise.cu; main stream)
+  size_t ws5_bytes = 0;
   void* ws3 = nullptr;      // grow-only scratch for the full-resolution 1x1 head's wgrad partials (smallconv.cu)
   size_t ws3_bytes = 0;
   // driver entry point resolved at segk_create (no link-time libcuda dependency)

@@ -67,13 +67,23 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const uint4* __re
 // exists: ReluGrad needs [act > 0] only at the routed element, and there act == the pooled value, so the
 // mask comes from the POOLED activation (1/4 of the bytes): dx = idx == k && pooled > 0 ? dy : 0 -- the
 // same bits as masking with the full-resolution activation (a window whose max is 0 routes nothing).
+//
+// BIAS: BiasAddGrad of the conv in front of the pool falls out of the same pass.  Every dy lands on exactly one
+// element of the window, so the column sums of dx are the column sums of the masked dy: each thread always owns
+// the same 8 channels (the thread count is a multiple of C/8), accumulates them in registers, the block reduces
+// over its threads in a fixed order and writes one partial row; reduce_rows_kernel adds the rows.  Saves the
+// separate pass over the full-resolution dz (conv1_2: 377 MB).
+template <bool BIAS>
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_pooled_kernel(const uint4* __restrict__ dy,
                                                                       const uint2* __restrict__ idx,
                                                                       const uint4* __restrict__ pooled,
-                                                                      uint4* __restrict__ dx, int N, int H, int W,
-                                                                      int C8) {
+                                                                      uint4* __restrict__ dx, float* __restrict__ db_part,
+                                                                      int N, int H, int W, int C8) {
   const int OH = H >> 1, OW = W >> 1;
   const int64_t total = (int64_t)N * OH * OW * C8;
+  float bsum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     int c8 = (int)(i % C8);
@@ -95,6 +105,11 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_pooled_kernel(const uint
       // a masked element gets an index no window position matches
       klo[j] = af.x > 0.f ? (((&id.x)[e >> 2] >> (8 * (e & 3))) & 0xffu) : 4u;
       khi[j] = af.y > 0.f ? (((&id.x)[e >> 2] >> (8 * ((e + 1) & 3))) & 0xffu) : 4u;
+      if (BIAS) {
+        const float2 gf = unpack_bf16x2((&g.x)[j]);
+        if (af.x > 0.f) bsum[e] += gf.x;
+        if (af.y > 0.f) bsum[e + 1] += gf.y;
+      }
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -105,6 +120,20 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_pooled_kernel(const uint
         o[j] = (klo[j] == (uint32_t)k ? (gw & 0xffffu) : 0u) | (khi[j] == (uint32_t)k ? (gw & 0xffff0000u) : 0u);
       }
       dx[offs[k]] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  if (BIAS) {
+    __shared__ float sh[kThreads][9];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = bsum[j];
+    __syncthreads();
+    if ((int)threadIdx.x < C8) {            // thread t owns channel group t % C8: sum t, t + C8, t + 2 C8, ...
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = 0.f;
+        for (int k = threadIdx.x; k < kThreads; k += C8) t += sh[k][j];
+        db_part[(int64_t)blockIdx.x * (C8 * 8) + threadIdx.x * 8 + j] = t;
+      }
     }
   }
 }
@@ -197,6 +226,39 @@ __global__ void __launch_bounds__(kThreads) dropout_kernel(const bf16* __restric
       else kp = ((&r.x)[j] >> 8) * (1.0f / 16777216.0f) < keep;
       y[e] = kp ? f2bf(bf2f(x[e]) * inv_keep) : f2bf(0.f);
     }
+  }
+}
+
+// The same for n % 8 == 0 and 16-byte aligned buffers: 8 elements per thread (one 16-byte load / store, two
+// Philox blocks with the counters of the scalar form, so both produce the same keep pattern).
+__global__ void __launch_bounds__(kThreads) dropout_vec8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                                                const uint2* __restrict__ mask, int64_t n8,
+                                                                float keep, float inv_keep, uint64_t seed) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(x + i);
+    uint32_t kp = 0;      // bit j: keep element j
+    if (mask) {
+      const uint2 m = __ldg(mask + i);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) kp |= ((((&m.x)[j >> 2] >> (8 * (j & 3))) & 0xffu) != 0 ? 1u : 0u) << j;
+    } else {
+      const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+      const int64_t q = 2 * i;
+      const uint4 r0 = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), 0u, 0u), key);
+      const uint4 r1 = philox4x32_10(make_uint4((uint32_t)(q + 1), (uint32_t)((q + 1) >> 32), 0u, 0u), key);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        kp |= (((&r0.x)[j] >> 8) * (1.0f / 16777216.0f) < keep ? 1u : 0u) << j;
+        kp |= (((&r1.x)[j] >> 8) * (1.0f / 16777216.0f) < keep ? 1u : 0u) << (4 + j);
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2((&v.x)[j]);
+      o[j] = pack_bf16x2((kp >> (2 * j)) & 1u ? f.x * inv_keep : 0.f, (kp >> (2 * j + 1)) & 1u ? f.y * inv_keep : 0.f);
+    }
+    y[i] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -685,20 +747,35 @@ int segk_maxpool2x2_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int
 }
 
 int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const void* act, int act_is_pooled,
-                        const void* residual, void* dx, int N, int H, int W, int C, void* stream) {
+                        const void* residual, void* dx, float* dbias, int N, int H, int W, int C, void* stream) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, dy && idx && dx, "maxpool_bwd: null pointer");
   SEGK_REQUIRE(ctx, N > 0 && H >= 2 && W >= 2 && (H % 2 == 0) && (W % 2 == 0) && C % 8 == 0,
                "maxpool_bwd: need even H,W and C%%8==0 (got %dx%dx%dx%d)", N, H, W, C);
+  SEGK_REQUIRE(ctx, !dbias || (act && act_is_pooled), "maxpool_bwd: dbias needs the pooled-activation mask mode");
   const int64_t items = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  cudaStream_t st = (cudaStream_t)stream;
   if (act && act_is_pooled) {
     SEGK_REQUIRE(ctx, !residual, "maxpool_bwd: a second gradient path needs the full-resolution activation as mask");
-    maxpool_bwd_pooled_kernel<<<stream_grid(ctx, items), kThreads, 0, (cudaStream_t)stream>>>(
-        (const uint4*)dy, (const uint2*)idx, (const uint4*)act, (uint4*)dx, N, H, W, C / 8);
+    const int grid = stream_grid(ctx, items);
+    if (dbias) {
+      const int C8 = C / 8;
+      SEGK_REQUIRE(ctx, C8 <= kThreads && kThreads % C8 == 0, "maxpool_bwd: dbias needs C/8 to divide %d (got C = %d)", kThreads, C);
+      const int rc = segk_grow(ctx, &ctx->ws5, &ctx->ws5_bytes, sizeof(float) * (size_t)ctx->sm_count * 8 * 2048, "pool-bwd bias partials");
+      if (rc) return rc;
+      maxpool_bwd_pooled_kernel<true><<<grid, kThreads, 0, st>>>((const uint4*)dy, (const uint2*)idx, (const uint4*)act,
+                                                                 (uint4*)dx, (float*)ctx->ws5, N, H, W, C8);
+      SEGK_LAUNCHED(ctx, "maxpool_bwd_pooled_bias");
+      reduce_rows_kernel<<<ceil_div(C, 32), kThreads, 0, st>>>((const float*)ctx->ws5, dbias, grid, C);
+      SEGK_LAUNCHED(ctx, "maxpool_bwd_bias_reduce");
+      return SEGK_OK;
+    }
+    maxpool_bwd_pooled_kernel<false><<<grid, kThreads, 0, st>>>((const uint4*)dy, (const uint2*)idx, (const uint4*)act,
+                                                                (uint4*)dx, nullptr, N, H, W, C / 8);
     SEGK_LAUNCHED(ctx, "maxpool_bwd_pooled");
     return SEGK_OK;
   }
-  maxpool_bwd_kernel<<<stream_grid(ctx, items), kThreads, 0, (cudaStream_t)stream>>>(
+  maxpool_bwd_kernel<<<stream_grid(ctx, items), kThreads, 0, st>>>(
       (const uint4*)dy, (const uint2*)idx, (const uint4*)act, (const uint4*)residual, (uint4*)dx, N, H, W, C / 8);
   SEGK_LAUNCHED(ctx, "maxpool_bwd");
   return SEGK_OK;
@@ -710,6 +787,12 @@ int segk_dropout(segk_ctx* ctx, const void* x, void* y, const uint8_t* mask, int
   SEGK_REQUIRE(ctx, x && y && n > 0, "dropout: null pointer / empty");
   SEGK_REQUIRE(ctx, keep_prob > 0.f && keep_prob <= 1.f, "dropout: keep_prob %f out of (0,1]",
                keep_prob);
+  if (n % 8 == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && (((uintptr_t)mask) & 7) == 0) {
+    dropout_vec8_kernel<<<stream_grid(ctx, n / 8), kThreads, 0, (cudaStream_t)stream>>>(
+        (const uint4*)x, (uint4*)y, (const uint2*)mask, n / 8, keep_prob, 1.0f / keep_prob, seed);
+    SEGK_LAUNCHED(ctx, "dropout_vec8");
+    return SEGK_OK;
+  }
   dropout_kernel<<<stream_grid(ctx, (n + 3) / 4), kThreads, 0, (cudaStream_t)stream>>>(
       (const bf16*)x, (bf16*)y, mask, n, keep_prob, 1.0f / keep_prob, seed);
   SEGK_LAUNCHED(ctx, "dropout");

@@ -522,14 +522,16 @@ __global__ void __launch_bounds__(kThreads) sum_partials_rows_kernel(const float
                                                                      float* __restrict__ out, int rows, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float a0 = 0.f, a1 = 0.f;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four loads in flight; the order of the sum is fixed
   int r = 0;
-  for (; r + 1 < rows; r += 2) {
+  for (; r + 3 < rows; r += 4) {
     a0 += partial[(int64_t)r * n + i];
     a1 += partial[(int64_t)(r + 1) * n + i];
+    a2 += partial[(int64_t)(r + 2) * n + i];
+    a3 += partial[(int64_t)(r + 3) * n + i];
   }
-  if (r < rows) a0 += partial[(int64_t)r * n + i];
-  out[i] = a0 + a1;
+  for (; r < rows; ++r) a0 += partial[(int64_t)r * n + i];
+  out[i] = (a0 + a1) + (a2 + a3);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -690,6 +692,305 @@ __global__ void __launch_bounds__(kThreads) deconv_wgrad_kernel(
   atomicAdd(dw + e, acc);
 }
 
+// ---------------------------------------------------------------------------------------
+// The FCN tail at training batch sizes: few pixels (N*5*18), wide channels.  conv8 (1x1, 4096 -> 2) and
+// conv_t1 (4x4 s2, 2 -> 512) and their gradients are HBM-bound streams of 12-24 MB each; the per-element /
+// per-warp forms above ran them at 0.2-0.4 TB/s.  These forms use 16-byte accesses and keep many loads in flight.
+// ---------------------------------------------------------------------------------------
+constexpr int kWidePx = 8;
+
+// conv8 forward: a block handles 8 pixels at a time; thread t owns channel groups t and t + 256 (8 channels
+// each, weights in registers), so every thread has 16 independent 16-byte loads in flight per tile.
+template <int CO>
+__global__ void __launch_bounds__(kThreads) conv_skinny_fwd_wide_kernel(
+    const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, void* __restrict__ y,
+    int64_t npix, int Cin, int relu, int out_f32) {
+  __shared__ float red[kThreads / 32][kWidePx * CO];
+  const int G = Cin >> 3;
+  const int g0 = threadIdx.x, g1 = threadIdx.x + kThreads;
+  float wr[2][8][CO];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int g = u ? g1 : g0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int c = 0; c < CO; ++c) wr[u][j][c] = g < G ? __ldg(w + (int64_t)(g * 8 + j) * CO + c) : 0.f;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t p0 = (int64_t)blockIdx.x * kWidePx; p0 < npix; p0 += (int64_t)gridDim.x * kWidePx) {
+    uint4 xv[2][kWidePx];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int g = u ? g1 : g0;
+#pragma unroll
+      for (int q = 0; q < kWidePx; ++q)
+        xv[u][q] = (g < G && p0 + q < npix) ? __ldg(reinterpret_cast<const uint4*>(x + (p0 + q) * Cin) + g)
+                                            : make_uint4(0, 0, 0, 0);
+    }
+    float acc[kWidePx][CO];
+#pragma unroll
+    for (int q = 0; q < kWidePx; ++q) {
+#pragma unroll
+      for (int c = 0; c < CO; ++c) acc[q][c] = 0.f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2((&xv[u][q].x)[j]);
+#pragma unroll
+          for (int c = 0; c < CO; ++c) acc[q][c] += f.x * wr[u][2 * j][c] + f.y * wr[u][2 * j + 1][c];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kWidePx; ++q)
+#pragma unroll
+      for (int c = 0; c < CO; ++c) {
+        float v = acc[q][c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][q * CO + c] = v;
+      }
+    __syncthreads();
+    if (threadIdx.x < kWidePx * CO) {
+      const int q = threadIdx.x / CO, c = threadIdx.x % CO;
+      float v = bias ? bias[c] : 0.f;
+#pragma unroll
+      for (int k = 0; k < kThreads / 32; ++k) v += red[k][threadIdx.x];     // fixed order: deterministic
+      v = relu ? fmaxf(v, 0.f) : v;
+      if (p0 + q < npix) {
+        if (out_f32) reinterpret_cast<float*>(y)[(p0 + q) * CO + c] = v;
+        else reinterpret_cast<bf16*>(y)[(p0 + q) * CO + c] = f2bf(v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// conv8 weight gradient: block = 32 channel groups (8 channels each) x 8 pixel lanes over a slice of the pixels;
+// the pixel lanes are reduced through shared memory, per-slice partial sums [slices][Cin][CO] go to the workspace
+// and are added in a fixed order by sum_partials_rows_kernel.
+template <int CO>
+__global__ void __launch_bounds__(kThreads) conv_skinny_wgrad_wide_kernel(
+    const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ partial, int64_t npix, int Cin,
+    int pix_per_slice) {
+  __shared__ float sh[8][32][8 * CO + 1];
+  const int G = Cin >> 3;
+  const int gl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int g = blockIdx.x * 32 + gl;
+  const int64_t p0 = (int64_t)blockIdx.y * pix_per_slice;
+  const int64_t p1 = p0 + pix_per_slice < npix ? p0 + pix_per_slice : npix;
+  float acc[8][CO];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[j][c] = 0.f;
+  if (g < G) {
+#pragma unroll 4
+    for (int64_t p = p0 + pl; p < p1; p += 8) {
+      const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x + p * Cin) + g);
+      float d[CO];
+#pragma unroll
+      for (int c = 0; c < CO; ++c) d[c] = bf2f(dy[p * CO + c]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&xv.x)[j]);
+#pragma unroll
+        for (int c = 0; c < CO; ++c) {
+          acc[2 * j][c] += f.x * d[c];
+          acc[2 * j + 1][c] += f.y * d[c];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int c = 0; c < CO; ++c) sh[pl][gl][j * CO + c] = acc[j][c];
+  __syncthreads();
+  // 256 threads -> 32 groups x (8 * CO) values: thread t sums the 8 pixel lanes of value t % (8*CO) ... in order
+  for (int e = threadIdx.x; e < 32 * 8 * CO; e += kThreads) {
+    const int gg = e / (8 * CO), v = e % (8 * CO);
+    if (blockIdx.x * 32 + gg >= G) continue;
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][gg][v];
+    partial[((int64_t)blockIdx.y * Cin + (int64_t)(blockIdx.x * 32 + gg) * 8) * CO + v] = t;
+  }
+}
+
+// conv_t1 forward (k = 2s, tiny Cin): thread = 8 output channels of one output pixel, 16-byte residual load
+// and store; the <= 4 contributing input pixels and their CIN*8 weights each are read per thread.
+template <int CIN>
+__global__ void __launch_bounds__(kThreads) deconv_fwd_vec8_kernel(
+    const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, const bf16* __restrict__ res,
+    bf16* __restrict__ y, int N, int H, int W, int Cout, int k, int s, int relu) {
+  const int OH = H * s, OW = W * s, p = s / 2, C8 = Cout >> 3;
+  const int64_t total = (int64_t)N * OH * OW * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    int64_t r = i / C8;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int n = (int)(r / OH);
+    const int qy = (oy + p) / s, ay = (oy + p) % s;
+    const int qx = (ox + p) / s, ax = (ox + p) % s;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? __ldg(bias + c8 * 8 + j) : 0.f;
+#pragma unroll
+    for (int ty = 0; ty < 2; ++ty) {
+      const int iy = qy - ty;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int tx = 0; tx < 2; ++tx) {
+        const int ix = qx - tx;
+        if (ix < 0 || ix >= W) continue;
+        const bf16* xp = x + (((int64_t)n * H + iy) * W + ix) * CIN;
+        float xv[CIN];
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) xv[ci] = bf2f(xp[ci]);
+        // w[(ky*k+kx)][co][ci]: 8 consecutive co x CIN values are contiguous -> 16-byte loads (scalar loads at a
+        // 32*CIN-byte lane stride cost one L1 wavefront per sector: they, not HBM, bounded the first version)
+        const float4* wp = reinterpret_cast<const float4*>(w + (((int64_t)(ay + s * ty) * k + (ax + s * tx)) * Cout + c8 * 8) * CIN);
+        float wv[8 * CIN];
+#pragma unroll
+        for (int q = 0; q < 2 * CIN; ++q) {
+          const float4 t4 = __ldg(wp + q);
+          wv[4 * q] = t4.x; wv[4 * q + 1] = t4.y; wv[4 * q + 2] = t4.z; wv[4 * q + 3] = t4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) acc[j] += xv[ci] * wv[j * CIN + ci];
+      }
+    }
+    if (res) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(res) + i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&u.x)[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]),
+                                                 pack_bf16x2(acc[4], acc[5]), pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+// conv_t1 input gradient: one warp per input pixel; lanes stride over groups of 8 output channels of each of
+// the k*k taps (16-byte dy loads), CIN accumulators per lane, shuffle reduction.
+template <int CIN>
+__global__ void __launch_bounds__(kThreads) deconv_dgrad_pix_kernel(
+    const bf16* __restrict__ dy, const float* __restrict__ w, const bf16* __restrict__ mask, bf16* __restrict__ dx, int N,
+    int H, int W, int Cout, int k, int s) {
+  const int OH = H * s, OW = W * s, p = s / 2, C8 = Cout >> 3;
+  const int lane = threadIdx.x & 31;
+  const int64_t npix = (int64_t)N * H * W;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; i < npix; i += nwarps) {
+    const int ix = (int)(i % W), iy = (int)((i / W) % H), n = (int)(i / ((int64_t)W * H));
+    float acc[CIN];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) acc[ci] = 0.f;
+    for (int ky = 0; ky < k; ++ky) {
+      const int oy = iy * s - p + ky;
+      if (oy < 0 || oy >= OH) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int ox = ix * s - p + kx;
+        if (ox < 0 || ox >= OW) continue;
+        const uint4* gp = reinterpret_cast<const uint4*>(dy + (((int64_t)n * OH + oy) * OW + ox) * Cout);
+        const float* wp = w + ((int64_t)(ky * k + kx) * Cout) * CIN;
+        for (int c8 = lane; c8 < C8; c8 += 32) {
+          const uint4 g = __ldg(gp + c8);
+          const float4* w4 = reinterpret_cast<const float4*>(wp + (int64_t)c8 * 8 * CIN);
+          float wv[8 * CIN];
+#pragma unroll
+          for (int q = 0; q < 2 * CIN; ++q) {
+            const float4 t4 = __ldg(w4 + q);
+            wv[4 * q] = t4.x; wv[4 * q + 1] = t4.y; wv[4 * q + 2] = t4.z; wv[4 * q + 3] = t4.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2((&g.x)[j]);
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci)
+              acc[ci] += f.x * wv[(2 * j) * CIN + ci] + f.y * wv[(2 * j + 1) * CIN + ci];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[ci] += __shfl_xor_sync(0xffffffffu, acc[ci], o);
+    if (lane < CIN) {
+      float v = acc[0];
+#pragma unroll
+      for (int ci = 1; ci < CIN; ++ci) v = lane == ci ? acc[ci] : v;
+      if (mask && !(bf2f(mask[i * CIN + lane]) > 0.f)) v = 0.f;
+      dx[i * CIN + lane] = f2bf(v);
+    }
+  }
+}
+
+// conv_t1 weight gradient: thread = (tap, 8 output channels) over a slice of the input rows; per-slice partial
+// sums [slices][k*k][Cout][CIN] in the workspace, added in a fixed order afterwards.
+template <int CIN>
+__global__ void __launch_bounds__(kThreads) deconv_wgrad_vec8_kernel(
+    const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ partial, int N, int H, int W, int Cout,
+    int k, int s, int rows_per_slice) {
+  const int OH = H * s, OW = W * s, p = s / 2, C8 = Cout >> 3;
+  const int e = blockIdx.x * kThreads + threadIdx.x;          // (tap, c8)
+  if (e >= k * k * C8) return;
+  const int c8 = e % C8, tap = e / C8;
+  const int ky = tap / k, kx = tap % k;
+  const int row0 = blockIdx.y * rows_per_slice;
+  const int row1 = min(row0 + rows_per_slice, N * H);
+  float acc[8][CIN];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) acc[j][ci] = 0.f;
+  for (int row = row0; row < row1; ++row) {
+    const int n = row / H, iy = row % H;
+    const int oy = iy * s - p + ky;
+    if (oy < 0 || oy >= OH) continue;
+    const bf16* xp = x + (int64_t)row * W * CIN;
+    const uint4* gp = reinterpret_cast<const uint4*>(dy + (((int64_t)n * OH + oy) * OW) * Cout) + c8;
+#pragma unroll 6
+    for (int ix = 0; ix < W; ++ix) {
+      const int ox = ix * s - p + kx;
+      if (ox < 0 || ox >= OW) continue;
+      const uint4 g = __ldg(gp + (int64_t)ox * C8);
+      float xv[CIN];
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) xv[ci] = bf2f(xp[ix * CIN + ci]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&g.x)[j]);
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          acc[2 * j][ci] += f.x * xv[ci];
+          acc[2 * j + 1][ci] += f.y * xv[ci];
+        }
+      }
+    }
+  }
+  // dW[ky,kx,co,ci]: the 8 x CIN values of this thread are contiguous
+  float* out = partial + (int64_t)blockIdx.y * ((int64_t)k * k * Cout * CIN) + ((int64_t)tap * Cout + c8 * 8) * CIN;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) out[j * CIN + ci] = acc[j][ci];
+}
+
 inline int sgrid(segk_ctx* ctx, int64_t items, int per_sm = 8) {
   int64_t b = ceil_div64(items, kThreads), cap = (int64_t)ctx->sm_count * per_sm;
   return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
@@ -731,6 +1032,18 @@ int segk_conv2d_small_fwd(segk_ctx* ctx, const void* x, int x_dtype, const float
     else
       conv_skinny_fwd_pixel_kernel<4><<<grid, kThreads, sm, st>>>((const bf16*)x, w, bias, y, npix, Cin, relu, out_f32);
     SEGK_LAUNCHED(ctx, "conv_skinny_fwd_pixel");
+    return SEGK_OK;
+  }
+  if (x_dtype == 0 && kh == 1 && kw == 1 && Cin % 8 == 0 && Cin >= 512 && Cin / 8 <= 2 * kThreads &&
+      (Cout == 2 || Cout == 4) && ctx->tail_wide) {
+    // few pixels, wide channels (conv8 at training batch sizes): block per 8 pixels, weights in registers
+    int64_t grid = ceil_div64(npix, kWidePx);
+    if (grid > (int64_t)ctx->sm_count * 4) grid = (int64_t)ctx->sm_count * 4;
+    if (Cout == 2)
+      conv_skinny_fwd_wide_kernel<2><<<(unsigned)grid, kThreads, 0, st>>>((const bf16*)x, w, bias, y, npix, Cin, relu, out_f32);
+    else
+      conv_skinny_fwd_wide_kernel<4><<<(unsigned)grid, kThreads, 0, st>>>((const bf16*)x, w, bias, y, npix, Cin, relu, out_f32);
+    SEGK_LAUNCHED(ctx, "conv_skinny_fwd_wide");
     return SEGK_OK;
   }
   if (x_dtype == 0 && kh == 1 && kw == 1 && Cin % 8 == 0 && (Cout == 2 || Cout == 4 || Cout == 8)) {
@@ -782,8 +1095,10 @@ int segk_conv2d_small_dgrad(segk_ctx* ctx, const void* dy, const float* w, const
   }
   SEGK_REQUIRE(ctx, kh == 1 && kw == 1 && (Cout == 2 || Cout == 4 || Cout == 8),
                "conv_small_dgrad: only 1x1 with Cout in {2,4,8} (got %dx%d Cout=%d)", kh, kw, Cout);
-  if (Cin % 8 == 0 && Cin <= 256 && npix >= 65536 && (Cout == 2 || Cout == 4)) {
-    const int g = sgrid(ctx, npix * (Cin / 8), 8);
+  if (Cin % 8 == 0 && (Cout == 2 || Cout == 4) &&
+      ((Cin <= 256 && npix >= 65536) || (ctx->tail_wide && Cin >= 512 && (size_t)Cin * Cout * sizeof(float) <= 48 * 1024))) {
+    // (wide channels: every block stages Cin*Cout weights in shared memory, so fewer, longer-lived blocks)
+    const int g = sgrid(ctx, npix * (Cin / 8), Cin >= 512 ? 3 : 8);
     const size_t sm = sizeof(float) * (size_t)Cin * Cout;
     if (Cout == 2)
       conv_skinny_dgrad_vec_kernel<2><<<g, kThreads, sm, st>>>((const bf16*)dy, w, (const bf16*)relu_mask, (bf16*)dx, npix, Cin, scale);
@@ -869,6 +1184,28 @@ int segk_conv2d_small_wgrad(segk_ctx* ctx, const void* x, int x_dtype, const voi
       conv_tinyk_wgrad_kernel<bf16><<<grid, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, dw, N, H, W,
                                                                Cin, Cout, kh, kw, ppb);
     SEGK_LAUNCHED(ctx, "conv_tinyk_wgrad");
+  } else if (x_dtype == 0 && kh == 1 && kw == 1 && (Cout == 2 || Cout == 4) && Cin % 8 == 0 && Cin >= 512 && ctx->tail_wide) {
+    // few pixels, wide channels (conv8): 16-byte loads, per-slice partial sums + ordered reduction
+    const int G = Cin / 8;
+    int slices = ceil_div(2 * ctx->sm_count, ceil_div(G, 32));       // ~two blocks per SM
+    if (slices > 32) slices = 32;
+    if ((int64_t)slices * 8 > npix) slices = (int)ceil_div64(npix, 8);
+    const int pps = (int)ceil_div64(npix, slices);
+    slices = (int)ceil_div64(npix, pps);
+    const int n = Cin * Cout;
+    {
+      const size_t need = sizeof(float) * (size_t)slices * n;
+      const int rc = segk_grow(ctx, &ctx->ws3, &ctx->ws3_bytes, need < (size_t)(4 << 20) ? (size_t)(4 << 20) : need, "skinny wgrad");
+      if (rc) return rc;
+    }
+    dim3 grid(ceil_div(G, 32), slices);
+    if (Cout == 2)
+      conv_skinny_wgrad_wide_kernel<2><<<grid, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, (float*)ctx->ws3, npix, Cin, pps);
+    else
+      conv_skinny_wgrad_wide_kernel<4><<<grid, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, (float*)ctx->ws3, npix, Cin, pps);
+    SEGK_LAUNCHED(ctx, "conv_skinny_wgrad_wide");
+    sum_partials_rows_kernel<<<ceil_div(n, kThreads), kThreads, 0, st>>>((const float*)ctx->ws3, dw, slices, n);
+    SEGK_LAUNCHED(ctx, "conv_skinny_wgrad_sum");
   } else if (x_dtype == 0 && kh == 1 && kw == 1 && (Cout == 2 || Cout == 4 || Cout == 8)) {
     const int tx = 128;
     const int gy = ceil_div(Cin, tx);
@@ -901,6 +1238,16 @@ int segk_deconv2d_small_fwd(segk_ctx* ctx, const void* x, const float* w, const 
   const int relu = (flags & SEGK_EPI_RELU) ? 1 : 0;
   const int64_t total = (int64_t)N * H * s * W * s * Cout;
   cudaStream_t st = (cudaStream_t)stream;
+  if (!(flags & SEGK_EPI_OUT_F32) && Cout % 8 == 0 && (Cin == 2 || Cin == 4) && ctx->tail_wide &&
+      (((uintptr_t)y | (uintptr_t)residual) & 15) == 0) {
+    const int g = sgrid(ctx, total / 8, 16);
+    if (Cin == 2)
+      deconv_fwd_vec8_kernel<2><<<g, kThreads, 0, st>>>((const bf16*)x, w, bias, (const bf16*)residual, (bf16*)y, N, H, W, Cout, k, s, relu);
+    else
+      deconv_fwd_vec8_kernel<4><<<g, kThreads, 0, st>>>((const bf16*)x, w, bias, (const bf16*)residual, (bf16*)y, N, H, W, Cout, k, s, relu);
+    SEGK_LAUNCHED(ctx, "deconv_small_fwd_vec8");
+    return SEGK_OK;
+  }
   if (flags & SEGK_EPI_OUT_F32)
     deconv_fwd_kernel<float><<<sgrid(ctx, total, 16), kThreads, 0, st>>>(
         (const bf16*)x, w, bias, (const bf16*)residual, (float*)y, N, H, W, Cin, Cout, k, s, relu);
@@ -919,6 +1266,15 @@ int segk_deconv2d_small_dgrad(segk_ctx* ctx, const void* dy, int dy_is_f32, cons
   SEGK_REQUIRE(ctx, k == 2 * s && (s % 2 == 0), "deconv: need k == 2*stride, even stride (k=%d s=%d)", k, s);
   const int64_t total = (int64_t)N * H * W * Cin;
   cudaStream_t st = (cudaStream_t)stream;
+  if (!dy_is_f32 && Cout % 8 == 0 && (Cin == 2 || Cin == 4) && ctx->tail_wide && (((uintptr_t)dy) & 15) == 0) {
+    const int g = sgrid(ctx, (int64_t)N * H * W * 32, 16);
+    if (Cin == 2)
+      deconv_dgrad_pix_kernel<2><<<g, kThreads, 0, st>>>((const bf16*)dy, w, (const bf16*)relu_mask, (bf16*)dx, N, H, W, Cout, k, s);
+    else
+      deconv_dgrad_pix_kernel<4><<<g, kThreads, 0, st>>>((const bf16*)dy, w, (const bf16*)relu_mask, (bf16*)dx, N, H, W, Cout, k, s);
+    SEGK_LAUNCHED(ctx, "deconv_small_dgrad_pix");
+    return SEGK_OK;
+  }
   if (Cin <= 8 && Cout >= 64) {
     if (dy_is_f32)
       deconv_dgrad_warp_kernel<float><<<sgrid(ctx, total * 32, 16), kThreads, 0, st>>>(
@@ -946,6 +1302,27 @@ int segk_deconv2d_small_wgrad(segk_ctx* ctx, const void* x, const void* dy, int 
   SEGK_REQUIRE(ctx, k == 2 * s && (s % 2 == 0), "deconv: need k == 2*stride, even stride (k=%d s=%d)", k, s);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t nw = (int64_t)k * k * Cout * Cin;
+  if (!dy_is_f32 && Cout % 8 == 0 && (Cin == 2 || Cin == 4) && ctx->tail_wide && (((uintptr_t)dy) & 15) == 0) {
+    // tiny Cin (conv_t1): 16-byte dy loads, per-slice partial sums + ordered reduction (no atomics)
+    const int rows = N * H;
+    int slices = rows < 40 ? rows : 40;
+    const int rps = ceil_div(rows, slices);
+    slices = ceil_div(rows, rps);
+    {
+      const size_t need = sizeof(float) * (size_t)slices * nw;
+      const int rc = segk_grow(ctx, &ctx->ws3, &ctx->ws3_bytes, need < (size_t)(4 << 20) ? (size_t)(4 << 20) : need, "deconv wgrad");
+      if (rc) return rc;
+    }
+    dim3 grid(ceil_div(k * k * (Cout / 8), kThreads), slices);
+    if (Cin == 2)
+      deconv_wgrad_vec8_kernel<2><<<grid, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, (float*)ctx->ws3, N, H, W, Cout, k, s, rps);
+    else
+      deconv_wgrad_vec8_kernel<4><<<grid, kThreads, 0, st>>>((const bf16*)x, (const bf16*)dy, (float*)ctx->ws3, N, H, W, Cout, k, s, rps);
+    SEGK_LAUNCHED(ctx, "deconv_small_wgrad_vec8");
+    sum_partials_rows_kernel<<<ceil_div((int)nw, kThreads), kThreads, 0, st>>>((const float*)ctx->ws3, dw, slices, (int)nw);
+    SEGK_LAUNCHED(ctx, "deconv_small_wgrad_sum");
+    return SEGK_OK;
+  }
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)nw, st);
   if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "wgrad memset: %s", cudaGetErrorString(e));
   const int gx = (int)ceil_div64(nw, kThreads);

@@ -103,6 +103,10 @@ struct IgemmParams {
   int64_t ws_slice;   // elements per slice
   int tma_store;   // 1: bf16 output leaves through shared memory + TMA store (coalesced, async, clipped)
   int m_fastest;   // tile order: 0 = channel tile fastest (activations shared), 1 = pixel tile fastest (weights shared)
+  // BiasAddGrad of the PRODUCER layer from the dgrad epilogue: column sums of the output (its pre-activation gradient),
+  // per-(CTA, TMEM lane quarter) partial rows [n_tiles][(grid / n_tiles) * 4][BLOCK_N]; needs channel-tile-fastest
+  // order, no split-K and grid % n_tiles == 0 (every tile of a CTA then has the same channel tile)
+  float* colsum;
   // "team stream-K" for layers with few output tiles and a long, weight-heavy K walk (conv6 dgrad: 50 tiles x ~2060
   // k-steps, 205 MB of weights).  The tiles that differ only in the batch coordinate (team_members = tiles_n of them)
   // share every weight slice, so they form a TEAM of CTAs that walk the same k-steps in lockstep (the slice comes from
@@ -239,6 +243,23 @@ struct WorkIter {
     return false;
   }
 };
+
+// Column sums over the 32 rows held by the 32 lanes of a warp, for the 32 columns each lane has in registers:
+// a butterfly transpose-reduce (16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5).  Lane L returns the sum of
+// column L over the warp's rows.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const bool hi = (lane & m) != 0;
+#pragma unroll
+    for (int i = 0; i < m; ++i) {
+      const float keep = hi ? v[i + m] : v[i];
+      const float send = hi ? v[i] : v[i + m];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+    }
+  }
+  return v[0];
+}
 
 // Shared tail of every conv epilogue: v = the fp32 accumulators of 32 consecutive output channels of one
 // output pixel (element offset `off` into the output / residual / mask tensors), bv = their bias.
@@ -416,6 +437,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
     const int in = row / (p.bw * p.bh);
     const bool ep_leader = (threadIdx.x == 64);     // first epilogue thread: issues / tracks the TMA stores
     uint32_t sg = 0;                                // running 64-column group counter -> staging buffer
+    float ca0 = 0.f, ca1 = 0.f, ca2 = 0.f, ca3 = 0.f;      // column sums of this thread's columns (p.colsum)
     const bool partial = p.ksplits > 1 || p.team;
     WorkIter it;
     it.init(p);
@@ -457,11 +479,15 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
           for (int i = 0; i < 8; ++i)
             w4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
                                 __uint_as_float(r[4 * i + 3]));
-        } else if (valid) {
+        } else {
           float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          epilogue_apply_store(p, v, bv, obase + c0, sbuf, row, half * 4);
+          for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(r[i]) : 0.f;
+          if (valid) epilogue_apply_store(p, v, bv, obase + c0, sbuf, row, half * 4);
+          if (p.colsum) {        // rows outside the tensor contribute zeros
+            const float cs = warp_colsum32(v, lane);
+            if (g0 == 0) ca0 += cs; else if (g0 == 64) ca1 += cs; else if (g0 == 128) ca2 += cs; else ca3 += cs;
+          }
         }
         if (p.tma_store) {
           fence_proxy_async();                        // generic-proxy smem writes -> visible to the TMA engine
@@ -479,6 +505,14 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
       if (acc == 0) acc_phase ^= 1;
     }
     if (p.tma_store && ep_leader) tma_store_wait_read<0>();
+    if (p.colsum) {
+      const int nt = blockIdx.x % p.n_tiles;
+      const int rows_per_nt = (gridDim.x / p.n_tiles) * 4;
+      float* dst = p.colsum + ((int64_t)nt * rows_per_nt + (blockIdx.x / p.n_tiles) * 4 + q) * BLOCK_N + half * 32 + lane;
+      dst[0] = ca0;
+      if (BLOCK_N > 64) dst[64] = ca1;
+      if (BLOCK_N > 128) { dst[128] = ca2; dst[192] = ca3; }
+    }
   }
   __syncwarp();
   tc_fence_before();
@@ -525,6 +559,7 @@ struct SlabParams {
   int kchunks;            // Ck / 64
   int ldo;
   int tma_store;
+  float* colsum;          // see IgemmParams
   void* out;
   int out_f32;
   const float* bias;
@@ -656,6 +691,7 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
     const bool ep_leader = (threadIdx.x == 64);
     const int srow = q * kSlabWV + lane;            // staging row: box (64 ch, 30 w, 4 h) is packed at pitch 30
     uint32_t sg = 0;
+    float ca0 = 0.f, ca1 = 0.f, ca2 = 0.f, ca3 = 0.f;      // column sums of this thread's columns (p.colsum)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % p.n_tiles;
       int r = tile / p.n_tiles;
@@ -686,11 +722,15 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
         uint32_t rr[32];
         tmem_ld32(taddr + c0, rr);
         tmem_ld_wait();
-        if (valid) {
+        {
           float v[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
-          epilogue_apply_store(p, v, bv, obase + c0, sbuf, srow, half * 4);
+          for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(rr[i]) : 0.f;
+          if (valid) epilogue_apply_store(p, v, bv, obase + c0, sbuf, srow, half * 4);
+          if (p.colsum) {
+            const float cs = warp_colsum32(v, lane);
+            if (g0 == 0) ca0 += cs; else if (g0 == 64) ca1 += cs; else if (g0 == 128) ca2 += cs; else ca3 += cs;
+          }
         }
         if (p.tma_store) {
           fence_proxy_async();
@@ -708,6 +748,14 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
       if (acc == 0) acc_phase ^= 1;
     }
     if (p.tma_store && ep_leader) tma_store_wait_read<0>();
+    if (p.colsum) {
+      const int nt = blockIdx.x % p.n_tiles;
+      const int rows_per_nt = (gridDim.x / p.n_tiles) * 4;
+      float* dst = p.colsum + ((int64_t)nt * rows_per_nt + (blockIdx.x / p.n_tiles) * 4 + q) * BLOCK_N + half * 32 + lane;
+      dst[0] = ca0;
+      if (BLOCK_N > 64) dst[64] = ca1;
+      if (BLOCK_N > 128) { dst[128] = ca2; dst[192] = ca3; }
+    }
   }
   __syncwarp();
   tc_fence_before();
@@ -1188,6 +1236,66 @@ __global__ void __launch_bounds__(256) epilogue_finish_kernel(const float* __res
   }
 }
 
+// out[nt * BN + c] = sum over the partial rows of channel tile nt (fixed order): grid (BN / 32, n_tiles), 32 x 8 threads
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ part, float* __restrict__ out,
+                                                            int rows_per_nt, int BN) {
+  __shared__ float sh[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const float* base = part + (int64_t)blockIdx.y * rows_per_nt * BN + c;
+  float a0 = 0.f, a1 = 0.f;
+  int r = rl;
+  for (; r + 8 < rows_per_nt; r += 16) {
+    a0 += base[(int64_t)r * BN];
+    a1 += base[(int64_t)(r + 8) * BN];
+  }
+  if (r < rows_per_nt) a0 += base[(int64_t)r * BN];
+  sh[rl][cl] = a0 + a1;
+  __syncthreads();
+  if (rl == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][cl];
+    out[blockIdx.y * BN + c] = t;
+  }
+}
+
+// column sums of a finished bf16 [rows][C] tensor (the path taken when the fused epilogue sums are not available:
+// split-K, pixel-tile-fastest order): per-block partial rows + colsum_reduce_kernel
+__global__ void __launch_bounds__(256) colsum_rows_kernel(const uint4* __restrict__ x, float* __restrict__ part, int64_t rows,
+                                                          int C8) {
+  __shared__ float sh[256][9];
+  const int cpb = C8 < 256 ? C8 : 256;
+  const int R = 256 / cpb;
+  const int cg = blockIdx.y * cpb + (threadIdx.x % cpb);
+  const int rl = threadIdx.x / cpb;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (cg < C8 && rl < R) {
+    for (int64_t r = (int64_t)blockIdx.x * R + rl; r < rows; r += (int64_t)gridDim.x * R) {
+      const uint4 u = __ldg(x + r * C8 + cg);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&u.x)[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = acc[j];
+  __syncthreads();
+  if (rl == 0 && cg < C8) {
+    for (int k = 1; k < R; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += sh[threadIdx.x + k * cpb][j];
+    float* o = part + (int64_t)blockIdx.x * (C8 * 8) + cg * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = acc[j];
+  }
+}
+
 // The same for the team stream-K schedule: the number of partial slices differs per column (nt, y-tile, x-tile).
 struct TeamFinish {
   int T, total, ncols, tiles_w, tiles_h, bw, bh, H, W, block_n;
@@ -1257,6 +1365,39 @@ __global__ void __launch_bounds__(256) epilogue_finish_team_kernel(const float* 
 
 // grow-only device scratch owned by the context (first use allocates; never on the steady-state path)
 int ensure_workspace(segk_ctx* ctx, size_t bytes) { return segk_grow(ctx, &ctx->ws, &ctx->ws_bytes, bytes, "split-K workspace"); }
+
+// Scratch for the fused column sums (ctx->ws6, main stream) and the two ways of finishing them.
+int colsum_scratch(segk_ctx* ctx, int grid, int block_n, float** out) {
+  const int rc = segk_grow(ctx, &ctx->ws6, &ctx->ws6_bytes, sizeof(float) * (size_t)(ctx->sm_count * 8) * 4096, "column-sum partials");
+  if (rc) return rc;
+  (void)grid; (void)block_n;
+  *out = (float*)ctx->ws6;
+  return SEGK_OK;
+}
+
+int colsum_finish(segk_ctx* ctx, float* colsum_out, int grid, int n_tiles, int block_n, cudaStream_t st) {
+  colsum_reduce_kernel<<<dim3(block_n / 32, n_tiles), 256, 0, st>>>((const float*)ctx->ws6, colsum_out, (grid / n_tiles) * 4, block_n);
+  SEGK_LAUNCHED(ctx, "column-sum reduce");
+  return SEGK_OK;
+}
+
+int colsum_fallback(segk_ctx* ctx, const void* y, int64_t rows, int C, float* colsum_out, cudaStream_t st) {
+  SEGK_REQUIRE(ctx, C % 32 == 0 && (C / 8 <= 256 ? 256 % (C / 8) == 0 : (C / 8) % 256 == 0),
+               "dgrad column sums: unsupported channel count %d", C);
+  float* part = nullptr;
+  int rc = colsum_scratch(ctx, 0, 0, &part);
+  if (rc) return rc;
+  const int C8 = C / 8, cpb = C8 < 256 ? C8 : 256, R = 256 / cpb, gy = C8 / cpb;
+  int64_t gx = ceil_div64(rows, (int64_t)R * 4);
+  const int64_t cap = ceil_div64((int64_t)ctx->sm_count * 4, gy);
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  colsum_rows_kernel<<<dim3((unsigned)gx, gy), 256, 0, st>>>((const uint4*)y, part, rows, C8);
+  SEGK_LAUNCHED(ctx, "column sums");
+  colsum_reduce_kernel<<<dim3(C / 32, 1), 256, 0, st>>>(part, colsum_out, (int)gx, C);
+  SEGK_LAUNCHED(ctx, "column-sum reduce");
+  return SEGK_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -1379,7 +1520,8 @@ int launch_igemm_t(segk_ctx* ctx, const TensorMaps& maps, const IgemmParams& p, 
 int launch_igemm(segk_ctx* ctx, int block_n, const TensorMaps& maps, const IgemmParams& p, const TapTable& taps,
                  cudaStream_t st, int team_grid = 0) {
   const int total = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.ksplits;
-  const int grid = team_grid > 0 ? team_grid : (total < ctx->sm_count ? total : ctx->sm_count);
+  int grid = team_grid > 0 ? team_grid : (total < ctx->sm_count ? total : ctx->sm_count);
+  if (p.colsum) grid = (grid / p.n_tiles) * p.n_tiles;      // every tile of a CTA has the same channel tile
   switch (block_n) {
     case 256: return launch_igemm_t<256>(ctx, maps, p, taps, grid, st);
     case 128: return launch_igemm_t<128>(ctx, maps, p, taps, grid, st);
@@ -1416,7 +1558,7 @@ bool slab_applicable(const segk_ctx* ctx, int N, int H, int W, int Ck, int Cn, i
 
 int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, const float* bias, const void* residual,
               const void* mask, float scale, int relu, int out_f32, void* y, int N, int H, int W, int Ck, int Cn,
-              void* stream) {
+              void* stream, float* colsum_out) {
   // Ck = 64: kx-fused N = 192 MMAs on resident weights (slab3_kernel), 64-channel output tiles.  Measured
   // (tools/time_n64.py, B=32 160x576): 64 -> 64 forward 228 vs 297 us, its dgrad 345 vs 372 us; with two
   // channel tiles (64 -> 128) it is a wash (116 vs 112 us), so the tap-wise slab keeps those.  slab3 = 2 forces it.
@@ -1449,7 +1591,27 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
     if (rc) return rc;
   }
   const int total = N * p.tiles_h * p.tiles_w * p.n_tiles;
-  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  if (colsum_out) {
+    if (fused3) {
+      // slab3 has no column-sum epilogue (in FCN-8s the producers of its inputs are the first layer and the pools)
+      const int g3 = total < ctx->sm_count ? total : (ctx->sm_count / p.n_tiles) * p.n_tiles;
+      if (Ck == 64) slab3_kernel<1><<<g3, kThreads, Slab3Cfg<1>::kSmem, (cudaStream_t)stream>>>(maps, p);
+      else slab3_kernel<2><<<g3, kThreads, Slab3Cfg<2>::kSmem, (cudaStream_t)stream>>>(maps, p);
+      SEGK_LAUNCHED(ctx, "slab3");
+      return colsum_fallback(ctx, y, (int64_t)N * H * W, Cn, colsum_out, (cudaStream_t)stream);
+    }
+    rc = colsum_scratch(ctx, grid, block_n, &p.colsum);
+    if (rc) return rc;
+    grid = (grid / p.n_tiles) * p.n_tiles;
+    switch (block_n) {
+      case 256: rc = launch_slab_t<256>(ctx, maps, p, grid, (cudaStream_t)stream); break;
+      case 128: rc = launch_slab_t<128>(ctx, maps, p, grid, (cudaStream_t)stream); break;
+      default: rc = launch_slab_t<64>(ctx, maps, p, grid, (cudaStream_t)stream); break;
+    }
+    if (rc) return rc;
+    return colsum_finish(ctx, colsum_out, grid, p.n_tiles, block_n, (cudaStream_t)stream);
+  }
   if (fused3) {
     // every CTA keeps one channel tile: grid = a multiple of n_tiles (total is one by construction)
     const int g3 = total < ctx->sm_count ? total : (ctx->sm_count / p.n_tiles) * p.n_tiles;
@@ -1477,7 +1639,7 @@ void conv_taps(TapTable& t, int kh, int kw) {
 // shared body of conv fwd and dgrad: y[N,H,W,Cn] = epilogue( sum_taps x[.. + tap][Ck] * wt[tap][Cn][Ck] )
 int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, const float* bias, const void* residual,
                const void* mask, float scale, int relu, int out_f32, void* y, int N, int H, int W, int Ck, int Cn,
-               int kh, int kw, void* stream) {
+               int kh, int kw, void* stream, float* colsum_out = nullptr) {
   SEGK_REQUIRE(ctx, x && wt && y, "%s: null pointer", what);
   SEGK_REQUIRE(ctx, N > 0 && H > 0 && W > 0, "%s: empty tensor", what);
   SEGK_REQUIRE(ctx, Ck % 64 == 0 && Cn % 64 == 0 && Ck > 0 && Cn > 0,
@@ -1487,8 +1649,9 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
                kMaxTaps, kh, kw);
   SEGK_REQUIRE(ctx, (((uintptr_t)x | (uintptr_t)wt | (uintptr_t)y | (uintptr_t)residual | (uintptr_t)mask) & 15) == 0,
                "%s: pointers must be 16-byte aligned", what);
+  SEGK_REQUIRE(ctx, !colsum_out || !out_f32, "%s: column sums need a bf16 output", what);
   if (slab_applicable(ctx, N, H, W, Ck, Cn, kh, kw))
-    return conv_slab(ctx, what, x, wt, bias, residual, mask, scale, relu, out_f32, y, N, H, W, Ck, Cn, stream);
+    return conv_slab(ctx, what, x, wt, bias, residual, mask, scale, relu, out_f32, y, N, H, W, Ck, Cn, stream, colsum_out);
   const Box b = choose_box(N, H, W, kBlockM, false, 0, 0, kh, kw);
   SEGK_REQUIRE(ctx, b.rows > 0, "%s: no pixel box for %dx%dx%d", what, N, H, W);
   const int block_n = pick_block_n(ctx, Cn);
@@ -1568,6 +1731,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
             (const float*)ctx->ws, tf, (int64_t)slice, bias, (const bf16*)residual, (const bf16*)mask, y, out_f32, relu, scale,
             rows, Cn);
         SEGK_LAUNCHED(ctx, "igemm team stream-K finish");
+        if (colsum_out) return colsum_fallback(ctx, y, rows, Cn, colsum_out, (cudaStream_t)stream);
         return SEGK_OK;
       }
     }
@@ -1591,6 +1755,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
           (const float*)ctx->ws, ks, (int64_t)slice, bias, (const bf16*)residual, (const bf16*)mask, y, out_f32, relu, scale,
           rows, Cn);
       SEGK_LAUNCHED(ctx, "igemm split-K finish");
+      if (colsum_out) return colsum_fallback(ctx, y, rows, Cn, colsum_out, (cudaStream_t)stream);
       return SEGK_OK;
     }
   }
@@ -1598,6 +1763,19 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   if (p.tma_store) {
     rc = encode_act_map(ctx, &maps.c, y, N, H, W, Cn, Cn, (int64_t)W * Cn, (int64_t)H * W * Cn, b.bw, b.bh, b.bn);
     if (rc) return rc;
+  }
+  if (colsum_out) {
+    const int total = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+    if (p.m_fastest || total < p.n_tiles) {        // the tiles of a CTA change their channel tile: sum the finished tensor
+      rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+      if (rc) return rc;
+      return colsum_fallback(ctx, y, (int64_t)N * H * W, Cn, colsum_out, (cudaStream_t)stream);
+    }
+    rc = colsum_scratch(ctx, total, block_n, &p.colsum);
+    if (rc) return rc;
+    rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+    if (rc) return rc;
+    return colsum_finish(ctx, colsum_out, (total / p.n_tiles) * p.n_tiles, p.n_tiles, block_n, (cudaStream_t)stream);
   }
   return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
 }
@@ -1688,8 +1866,8 @@ int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float*
   return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
 }
 
-int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, void* dx, int N, int H,
-                        int W, int Cin, int Cout, int k, int s, void* stream) {
+int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, void* dx, float* dx_colsum,
+                        int N, int H, int W, int Cin, int Cout, int k, int s, void* stream) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, dy && wd && dx && N > 0 && H > 0 && W > 0, "deconv2d_dgrad: bad args");
   SEGK_REQUIRE(ctx, k == 4 && s == 2, "deconv2d_dgrad: tensor-core path supports k=4, stride 2 (got k=%d s=%d)", k, s);
@@ -1720,6 +1898,20 @@ int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const voi
   p.ksplits = 1; p.ws = nullptr;
   TapTable taps;
   strided_taps(taps, k, s);
+  if (dx_colsum) {
+    const int tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+    const int total = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+    if (total < p.n_tiles) {
+      rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+      if (rc) return rc;
+      return colsum_fallback(ctx, dx, (int64_t)N * H * W, Cin, dx_colsum, (cudaStream_t)stream);
+    }
+    rc = colsum_scratch(ctx, total, block_n, &p.colsum);
+    if (rc) return rc;
+    rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+    if (rc) return rc;
+    return colsum_finish(ctx, dx_colsum, (total / p.n_tiles) * p.n_tiles, p.n_tiles, block_n, (cudaStream_t)stream);
+  }
   return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
 }
 
@@ -1793,11 +1985,12 @@ int segk_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* b
 }
 
 int segk_conv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, const void* residual,
-                      void* dx, float scale, int N, int H, int W, int Cin, int Cout, int kh, int kw, void* stream) {
+                      void* dx, float* dx_colsum, float scale, int N, int H, int W, int Cin, int Cout, int kh, int kw,
+                      void* stream) {
   if (!ctx) return SEGK_EINVAL;
   // GEMM-K = Cout (channels of dy), GEMM-N = Cin (channels of dx); wd holds the taps reversed.
   return conv_igemm(ctx, "conv2d_dgrad", dy, wd, nullptr, residual, relu_mask, scale, 0, 0, dx, N, H, W, Cout, Cin, kh,
-                    kw, stream);
+                    kw, stream, dx_colsum);
 }
 
 int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
@@ -1890,7 +2083,7 @@ int segk_tc_init(segk_ctx* ctx) {
   ctx->slab_mode = env_int("SEGK_SLAB", 1);
   ctx->tma_store = env_int("SEGK_TMA_STORE", 1);
   ctx->slab3 = env_int("SEGK_SLAB3", 1);
-  ctx->teamk = env_int("SEGK_TEAMK", 1);
+  ctx->teamk = env_int("SEGK_TEAMK", 0);
   cudaError_t e = cudaSuccess;
 #define SEGK_SMEM_ATTR(kern, bytes) \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)

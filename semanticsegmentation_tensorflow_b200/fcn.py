@@ -402,6 +402,7 @@ class FCN(_Feeds):
         def prev_act(i):
             return self.x if i == 0 else act[names[i - 1]]
         dcur = self.dlogits          # gradient wrt the current layer's output (pre-activation-grad applied)
+        bias_done = set()            # layers whose BiasAddGrad came out of another kernel's pass
         flip = 0
         nbuf = len(self._gbuf)
 
@@ -413,21 +414,38 @@ class FCN(_Feeds):
             self.wside.before_write(dx)
             return dx
 
+        def fused_bias(prev):
+            """The input gradient a tensor-core dgrad writes is the pre-activation gradient of its producer layer:
+            its column sums are that layer's BiasAddGrad, summed in the dgrad epilogue (no second pass over dz)."""
+            if prev is None or prev.kind == "pool" or prev.path == "first" or prev.cout % 32:
+                return None
+            c8 = prev.cout // 8
+            if not (256 % c8 == 0 if c8 <= 256 else c8 % 256 == 0):
+                return None
+            bias_done.add(prev.name)
+            return V.grad(f"{prev.name}/{prev.bias_name}")
+
         for i in range(len(L) - 1, -1, -1):
             l = L[i]
             xin = prev_act(i)
             if l.kind == "pool":
                 # MaxPoolGrad fused with the ReluGrad of the pre-pool conv output
                 dx = next_dx(xin)
-                # the pooled output doubles as the ReluGrad mask of the conv before the pool
-                ops.maxpool_bwd(dcur, self.idx[l.name], dx, pooled=act[l.name])
+                # the pooled output doubles as the ReluGrad mask of the conv before the pool, and the column sums
+                # of the masked gradient are that conv's BiasAddGrad
+                before = L[i - 1]
+                db = None
+                if before.kind == "conv" and before.path != "first" and (before.cout // 8) <= 256 and 256 % (before.cout // 8) == 0:
+                    db = V.grad(f"{before.name}/{before.bias_name}")
+                    bias_done.add(before.name)
+                ops.maxpool_bwd(dcur, self.idx[l.name], dx, pooled=act[l.name], dbias=db)
                 dcur = dx
                 continue
             gw = V.grad(f"{l.name}/weights")
             gb = V.grad(f"{l.name}/{l.bias_name}")
             # BiasAddGrad only reads dcur: HBM-bound, off the critical path -> side stream
             # (the fused first-layer wgrad produces it as one more row of its GEMM)
-            if l.path != "first":
+            if l.path != "first" and l.name not in bias_done:
                 self.side.run(lambda d=dcur, g=gb: ops.bias_grad(d, g), reads=(dcur,))
             prev = L[i - 1] if i > 0 else None
             # tensor-core weight gradients go to the wgrad stream, ordered after this point (dcur is
@@ -455,10 +473,11 @@ class FCN(_Feeds):
                 else:
                     dx = next_dx(xin)
                 mask = xin if (prev is not None and prev.kind == "conv" and prev.relu) else None
+                cs = fused_bias(prev) if l.path in ("tc", "patch") else None
                 if l.path == "tc":
-                    ops.deconv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.stride, relu_mask=mask)
+                    ops.deconv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.stride, relu_mask=mask, colsum=cs)
                 elif l.path == "patch":
-                    ops.conv2d_dgrad(Pg, V.wd[l.name], dx, 1, 1, relu_mask=mask, flops=dfl)
+                    ops.conv2d_dgrad(Pg, V.wd[l.name], dx, 1, 1, relu_mask=mask, flops=dfl, colsum=cs)
                 else:
                     ops.deconv2d_small_dgrad(dcur, V.param(f"{l.name}/weights"), dx, l.stride, relu_mask=mask)
                 if wjob is not None:
@@ -492,7 +511,8 @@ class FCN(_Feeds):
                     res = {"pool4": self.dfuse_1, "pool3": self.dfuse_2}.get(prev.name)
                     dx = next_dx(xin)
                     if l.path == "tc":
-                        ops.conv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.k, relu_mask=mask, residual=res, scale=scale)
+                        ops.conv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.k, relu_mask=mask, residual=res, scale=scale,
+                                         colsum=fused_bias(prev))
                     else:
                         assert res is None
                         ops.conv2d_small_dgrad(dcur, V.param(f"{l.name}/weights"), dx, relu_mask=mask, scale=scale)

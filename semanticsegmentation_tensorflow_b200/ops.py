@@ -197,11 +197,12 @@ class Ops:
                   flags, _stream())
         return y
 
-    def conv2d_dgrad(self, dy, wd, dx, kh, kw, relu_mask=None, residual=None, scale=1.0, flops=None):
+    def conv2d_dgrad(self, dy, wd, dx, kh, kw, relu_mask=None, residual=None, scale=1.0, flops=None, colsum=None):
+        """`colsum` (fp32 [Cin]): column sums of dx from the same pass = BiasAddGrad of the producer layer."""
         n, h, w, cout = dy.shape
         cin = dx.shape[3]
         self._w(conv_flops(n, h, w, cin, cout, kh, kw) if flops is None else flops, "flop")
-        self.call("segk_conv2d_dgrad", _p(dy), _p(wd), _p(relu_mask), _p(residual), _p(dx), float(scale), n, h, w,
+        self.call("segk_conv2d_dgrad", _p(dy), _p(wd), _p(relu_mask), _p(residual), _p(dx), _p(colsum), float(scale), n, h, w,
                   cin, cout, kh, kw, _stream())
         return dx
 
@@ -221,11 +222,11 @@ class Ops:
                   _stream())
         return y
 
-    def deconv2d_dgrad(self, dy, wd, dx, k, s, relu_mask=None):
+    def deconv2d_dgrad(self, dy, wd, dx, k, s, relu_mask=None, colsum=None):
         n, h, w, cin = dx.shape
         cout = dy.shape[3]
         self._w(deconv_flops(n, h, w, cin, cout, k, s), "flop")
-        self.call("segk_deconv2d_dgrad", _p(dy), _p(wd), _p(relu_mask), _p(dx), n, h, w, cin, cout, k, s, _stream())
+        self.call("segk_deconv2d_dgrad", _p(dy), _p(wd), _p(relu_mask), _p(dx), _p(colsum), n, h, w, cin, cout, k, s, _stream())
         return dx
 
     def deconv2d_wgrad(self, x, dy, dw, k, s, accumulate=False):
@@ -291,18 +292,20 @@ class Ops:
         self.call("segk_maxpool2x2_fwd", _p(x), _p(y), _p(idx), n, h, w, c, _stream())
         return y, idx
 
-    def maxpool_bwd(self, dy, idx, dx, act=None, residual=None, pooled=None):
+    def maxpool_bwd(self, dy, idx, dx, act=None, residual=None, pooled=None, dbias=None):
         """`act`: pre-pool activation as ReluGrad mask; `pooled`: the pooled tensor as the same mask
-        (bit-identical, a quarter of the bytes; not with `residual`)."""
+        (bit-identical, a quarter of the bytes; not with `residual`); `dbias`: BiasAddGrad of the conv in
+        front of the pool from the same pass (pooled mode)."""
         n, h, w, c = dx.shape
         if pooled is not None:
             assert act is None and residual is None
             self._w(2.0 * dx.numel() + 5.0 * dy.numel(), "byte")
-            self.call("segk_maxpool2x2_bwd", _p(dy), _p(idx), _p(pooled), 1, 0, _p(dx), n, h, w, c, _stream())
+            self.call("segk_maxpool2x2_bwd", _p(dy), _p(idx), _p(pooled), 1, 0, _p(dx), _p(dbias), n, h, w, c, _stream())
             return dx
+        assert dbias is None
         extra = (2.0 * dx.numel() if act is not None else 0.0) + (2.0 * dx.numel() if residual is not None else 0.0)
         self._w(2.0 * dx.numel() + 3.0 * dy.numel() + extra, "byte")
-        self.call("segk_maxpool2x2_bwd", _p(dy), _p(idx), _p(act), 0, _p(residual), _p(dx), n, h, w, c, _stream())
+        self.call("segk_maxpool2x2_bwd", _p(dy), _p(idx), _p(act), 0, _p(residual), _p(dx), 0, n, h, w, c, _stream())
         return dx
 
     # ---- shared-helper layers (utils.py): BN-affine folding, concat ---------------------------------

@@ -88,6 +88,16 @@ def test_conv2d_dgrad(ops, cuda_device, shape):
                      residual=dev_bf16(res, cuda_device), scale=1.25)
     torch.cuda.synchronize()
     assert_close(host(dx), ref, TOL_BF16, f"conv dgrad {shape}")
+    # the same call with the fused BiasAddGrad of the producer layer: column sums of dx (fp32 epilogue values)
+    if ci % 32 == 0:
+        dx2 = torch.full((n, h, w, ci), 7.0, dtype=torch.bfloat16, device=cuda_device)
+        cs = torch.full((ci,), 7.0, dtype=torch.float32, device=cuda_device)
+        ops.conv2d_dgrad(dev_bf16(dy, cuda_device), wd, dx2, k, k, relu_mask=dev_bf16(act, cuda_device),
+                         residual=dev_bf16(res, cuda_device), scale=1.25, colsum=cs)
+        torch.cuda.synchronize()
+        assert torch.equal(dx2, dx)
+        ref_cs = ref.astype(np.float64).sum(axis=(0, 1, 2))
+        np.testing.assert_allclose(host(cs), ref_cs, rtol=0, atol=4e-3 * np.abs(ref).max() * np.sqrt(n * h * w))
 
 
 @pytest.mark.parametrize("shape", CONV_SHAPES)
@@ -138,9 +148,13 @@ def test_deconv2d_tc_fwd_dgrad_wgrad(ops, cuda_device, shape):
     torch.cuda.synchronize()
     assert_close(host(y), y_ref.detach().numpy(), TOL_BF16, f"deconv fwd {shape}")
     dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=cuda_device)
-    ops.deconv2d_dgrad(dev_bf16(dy, cuda_device), wd, dx, k, s)
+    cs = torch.full((ci,), 7.0, dtype=torch.float32, device=cuda_device)
+    ops.deconv2d_dgrad(dev_bf16(dy, cuda_device), wd, dx, k, s, colsum=cs)
     torch.cuda.synchronize()
     assert_close(host(dx), xt.grad.numpy(), TOL_BF16, f"deconv dgrad {shape}")
+    gx = xt.grad.numpy()
+    np.testing.assert_allclose(host(cs), gx.astype(np.float64).sum(axis=(0, 1, 2)), rtol=0,
+                               atol=4e-3 * np.abs(gx).max() * np.sqrt(n * h * w))
     if n * h * w >= 64:
         dw = torch.empty((k, k, co, ci), dtype=torch.float32, device=cuda_device)
         ops.deconv2d_wgrad(dev_bf16(x, cuda_device), dev_bf16(dy, cuda_device), dw, k, s)
@@ -252,9 +266,13 @@ def test_slab_conv_fwd_and_dgrad(ops, cuda_device, shape):
     dy = bf16_grid(rng.standard_normal((n, h, w, co)))
     z.backward(torch.tensor(dy))
     dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=cuda_device)
-    ops.conv2d_dgrad(dev_bf16(dy, cuda_device), wd, dx, k, k, relu_mask=dev_bf16(x, cuda_device), scale=0.5)
+    cs = torch.full((ci,), 7.0, dtype=torch.float32, device=cuda_device)
+    ops.conv2d_dgrad(dev_bf16(dy, cuda_device), wd, dx, k, k, relu_mask=dev_bf16(x, cuda_device), scale=0.5, colsum=cs)
     torch.cuda.synchronize()
-    assert_close(host(dx), xt.grad.numpy() * (x > 0) * 0.5, TOL_BF16, f"slab dgrad {shape}")
+    ref_dx = xt.grad.numpy() * (x > 0) * 0.5
+    assert_close(host(dx), ref_dx, TOL_BF16, f"slab dgrad {shape}")
+    np.testing.assert_allclose(host(cs), ref_dx.astype(np.float64).sum(axis=(0, 1, 2)), rtol=0,
+                               atol=4e-3 * np.abs(ref_dx).max() * np.sqrt(n * h * w))
 
 
 def test_slab_forced_for_wide_layers(ops, cuda_device):
@@ -394,7 +412,7 @@ def test_team_stream_k_fwd_dgrad_and_wgrad_box_skipping(ops, cuda_device, shape)
             torch.cuda.synchronize()
             assert torch.equal(y, y2)
     finally:
-        ops.ctx.set_tuning("teamk", 1)
+        ops.ctx.set_tuning("teamk", 0)
     dw = torch.full((k, k, ci, co), 7.0, dtype=torch.float32, device=cuda_device)
     ops.conv2d_wgrad(xd, dyd, dw, k, k)
     torch.cuda.synchronize()

@@ -51,6 +51,14 @@ def test_maxpool_fwd_bwd_bit_exact(ops, cuda_device, shape, ties):
         ops.maxpool_bwd(dev_bf16(dy, cuda_device), idx, dx2, pooled=y)
         torch.cuda.synchronize()
         assert torch.equal(dx2, dx)
+        # ... and BiasAddGrad of the conv in front of the pool from the same pass: column sums of dx
+        db = torch.full((c,), 7.0, dtype=torch.float32, device=cuda_device)
+        dx3 = torch.full(shape, 7.0, dtype=torch.bfloat16, device=cuda_device)
+        ops.maxpool_bwd(dev_bf16(dy, cuda_device), idx, dx3, pooled=y, dbias=db)
+        torch.cuda.synchronize()
+        assert torch.equal(dx3, dx)
+        ref_db = host(dx).astype(np.float64).sum(axis=(0, 1, 2))
+        np.testing.assert_allclose(host(db), ref_db, rtol=1e-5, atol=1e-4 * np.abs(ref_db).max())
 
 
 @pytest.mark.parametrize("npix", [1, 255, 4096, 2 * 160 * 576])
@@ -178,6 +186,15 @@ def test_dropout_injected_mask_and_philox_rate(ops, cuda_device):
     assert not np.array_equal(host(y), host(y3))
     nz = host(y) != 0
     assert np.array_equal(host(y)[nz], bf16_grid(x[nz] / np.float32(0.8)))
+    # the 8-wide form (n % 8 == 0) and the scalar form (here: n - 4 elements) draw the same Philox stream
+    ys = torch.empty(n - 4, dtype=torch.bfloat16, device=cuda_device)
+    ops.dropout(xd[:n - 4], ys, 0.8, 1234)
+    torch.cuda.synchronize()
+    assert torch.equal(ys, y[:n - 4])
+    ms = torch.as_tensor(mask).to(cuda_device)
+    ops.dropout(xd[:n - 4], ys, 0.8, 0, ms[:n - 4])
+    torch.cuda.synchronize()
+    assert np.array_equal(host(ys), ref[:n - 4])
 
 
 def test_bias_grad_and_cast(ops, cuda_device):

@@ -39,8 +39,20 @@ def test_conv1_1_u8_fwd_and_wgrad(ops, cuda_device, cin):
     assert_close(host(dw), wtt.grad.numpy(), 1e-4, "conv1_1 wgrad")
 
 
-def test_conv8_skinny_fwd_dgrad_wgrad(ops, cuda_device):
-    n, h, w, ci, co = 2, 5, 18, 4096, 2
+@pytest.mark.parametrize("tail_wide", [1, 0])
+@pytest.mark.parametrize("shape", [(2, 5, 18, 4096, 2), (3, 5, 7, 1024, 4), (32, 5, 18, 4096, 2)])
+def test_conv8_skinny_fwd_dgrad_wgrad(ops, cuda_device, shape, tail_wide):
+    """conv8 (1x1, fc -> num_classes, FCN.py:86): the 16-byte-access forms for few pixels / wide channels
+    (tail_wide = 1, the default) and the per-warp / per-element forms (0) against the oracle."""
+    ops.ctx.set_tuning("tail_wide", tail_wide)
+    try:
+        _conv8_case(ops, cuda_device, shape)
+    finally:
+        ops.ctx.set_tuning("tail_wide", 1)
+
+
+def _conv8_case(ops, cuda_device, shape):
+    n, h, w, ci, co = shape
     rng = np.random.default_rng(1)
     x = bf16_grid(np.maximum(rng.standard_normal((n, h, w, ci)), 0))
     wt = (rng.standard_normal((1, 1, ci, co)) / 64).astype(np.float32)
@@ -65,13 +77,24 @@ def test_conv8_skinny_fwd_dgrad_wgrad(ops, cuda_device):
     assert_close(host(dw), wtt.grad.numpy(), 1e-4, "conv8 wgrad")
 
 
+@pytest.mark.parametrize("tail_wide", [1, 0])
 @pytest.mark.parametrize("case", [
     # N, H, W, Cin, Cout, k, s, f32 output/grad
     (2, 5, 18, 2, 512, 4, 2, False),      # conv_t1
+    (32, 5, 18, 2, 512, 4, 2, False),     # conv_t1 at the benchmarked batch
+    (3, 3, 5, 4, 64, 4, 2, False),        # four classes
     (1, 6, 8, 256, 2, 16, 8, True),       # conv_t3 (logits fp32)
     (2, 4, 4, 16, 24, 4, 2, False),
 ])
-def test_deconv_small_fwd_dgrad_wgrad(ops, cuda_device, case):
+def test_deconv_small_fwd_dgrad_wgrad(ops, cuda_device, case, tail_wide):
+    ops.ctx.set_tuning("tail_wide", tail_wide)
+    try:
+        _deconv_small_case(ops, cuda_device, case)
+    finally:
+        ops.ctx.set_tuning("tail_wide", 1)
+
+
+def _deconv_small_case(ops, cuda_device, case):
     n, h, w, ci, co, k, s, f32 = case
     rng = np.random.default_rng(2)
     x = bf16_grid(np.maximum(rng.standard_normal((n, h, w, ci)), 0))
