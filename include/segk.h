@@ -183,6 +183,29 @@ int segk_deconv_patch_gather(segk_ctx* ctx, const void* dy, int dy_is_f32, void*
 int segk_deconv_col2im(segk_ctx* ctx, const float* yp, const float* bias, const void* residual,
                        void* y, int out_f32, int N, int H, int W, int Cout, int k, int s,
                        void* stream);
+/* ---- phase-packed transposed conv for tiny Cout (conv_t3: 16x16 s8, 256 -> 2, FCN.py:98-107) ---------------
+ * k = 2s, SAME: the s x s output pixels [r*s-p, (r+1)*s-p) x [c*s-p, (c+1)*s-p) (p = s/2) depend only on the
+ * 2 x 2 input neighbourhood (r-1+dy, c-1+dx), so the layer is ONE 4-tap stride-1 implicit GEMM over the
+ * (H+1) x (W+1) block grid with R = s*s*Cout columns (a,b,co) whose epilogue writes each row's block of fp32
+ * logits (+ bias) directly -- no patch-space tensor, no col2im pass.  Needs Cin % 64 == 0, R in {64,128,256}.
+ *   segk_pack_deconv_packed : w[k,k,Cout,Cin] fp32 -> bf[t][Cin/64][R][64] (fwd) and bt[t][R/64][Cin][64] (dgrad),
+ *                             t = dy*2+dx, value W[a+s(1-dy)][b+s(1-dx)][co][ci]
+ *   segk_deconv_pack_dy     : dy [N,sH,sW,Cout] (fp32 or bf16) -> dyb[N,H+1,W+1,R] bf16 blocks (0 outside the image)
+ *   segk_deconv2d_packed_dgrad : dx = 4-tap igemm over dyb (ReLU mask / dx_colsum as segk_conv2d_dgrad)
+ *   segk_deconv2d_packed_wgrad : dwt[t][Cin][R] fp32 (overwritten); segk_deconv_unpack_dw -> dw[k,k,Cout,Cin] */
+int segk_pack_deconv_packed(segk_ctx* ctx, const float* w, void* bf, void* bt, int k, int s, int Cin, int Cout,
+                            void* stream);
+int segk_deconv2d_packed_fwd(segk_ctx* ctx, const void* x, const void* bf, const float* bias, float* y, int N,
+                             int H, int W, int Cin, int Cout, int k, int s, void* stream);
+int segk_deconv_pack_dy(segk_ctx* ctx, const void* dy, int dy_is_f32, void* dyb, int N, int H, int W, int Cout,
+                        int s, void* stream);
+int segk_deconv2d_packed_dgrad(segk_ctx* ctx, const void* dyb, const void* bt, const void* relu_mask, void* dx,
+                               float* dx_colsum, int N, int H, int W, int Cin, int Cout, int k, int s,
+                               void* stream);
+int segk_deconv2d_packed_wgrad(segk_ctx* ctx, const void* x, const void* dyb, float* dwt, int N, int H, int W,
+                               int Cin, int Cout, int k, int s, void* stream);
+int segk_deconv_unpack_dw(segk_ctx* ctx, const float* dwt, float* dw, int k, int s, int Cin, int Cout,
+                          int accumulate, void* stream);
 /* generic matrix pack: w fp32 [T][A][B] -> cp bf16 [T][ceil(B/64)][A][64] (rows A, k = B) and/or
  * tr bf16 [T][ceil(A/64)][B][64] (rows B, k = A) */
 int segk_pack_matrix(segk_ctx* ctx, const float* w, void* cp, void* tr, int T, int A, int B,

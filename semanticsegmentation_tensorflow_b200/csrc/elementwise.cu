@@ -757,8 +757,10 @@ int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const
   cudaStream_t st = (cudaStream_t)stream;
   if (act && act_is_pooled) {
     SEGK_REQUIRE(ctx, !residual, "maxpool_bwd: a second gradient path needs the full-resolution activation as mask");
-    const int grid = stream_grid(ctx, items);
+    int grid = stream_grid(ctx, items);
     if (dbias) {
+      // one partial row per block: fewer, longer-lived blocks keep the row reduction short (1184 rows cost ~35 us)
+      if (grid > ctx->sm_count * 3) grid = ctx->sm_count * 3;
       const int C8 = C / 8;
       SEGK_REQUIRE(ctx, C8 <= kThreads && kThreads % C8 == 0, "maxpool_bwd: dbias needs C/8 to divide %d (got C = %d)", kThreads, C);
       const int rc = segk_grow(ctx, &ctx->ws5, &ctx->ws5_bytes, sizeof(float) * (size_t)ctx->sm_count * 8 * 2048, "pool-bwd bias partials");

@@ -301,6 +301,76 @@ __global__ void __launch_bounds__(kThreads) channel_copy_kernel(const bf16* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Phase-packed transposed conv for tiny Cout (conv_t3: 16x16 s8, 256 -> 2, FCN.py:98-107).
+// k = 2s, SAME: output block (r, c) = the s x s output pixels [r*s - p, (r+1)*s - p) x [c*s - p, (c+1)*s - p)
+// depends only on the 2 x 2 input neighbourhood (r-1+dy, c-1+dx), dy,dx in {0,1}:
+//   y[block (r,c)][(a,b,co)] = sum_{dy,dx,ci} x[r-1+dy, c-1+dx, ci] * W[a + s(1-dy), b + s(1-dx), co, ci]
+// i.e. ONE stride-1 4-tap implicit GEMM over the (H+1) x (W+1) block grid with R = s*s*Cout columns, whose
+// epilogue writes each row's s x s x Cout block of logits directly -- no patch-space tensor, no col2im.
+// Backward: dyb[n, r, c, (a,b,co)] = dy[n, r*s-p+a, c*s-p+b, co] (0 outside) is a plain re-blocking of dy (no
+// overlap), and dx / dW are a 4-tap igemm / wgrad over it with the same packed weights.
+//   bf[t][ci/64][R rows][64]   rows (a,b,co), k = ci        (forward B operand)
+//   bt[t][R/64][Cin rows][64]  rows ci,       k = (a,b,co)  (dgrad B operand)      t = dy*2 + dx
+__global__ void __launch_bounds__(kThreads) pack_deconv_packed_kernel(const float* __restrict__ w, bf16* __restrict__ bf,
+                                                                     bf16* __restrict__ bt, int k, int s, int Cin, int Cout) {
+  const int R = s * s * Cout;
+  const int64_t total = (int64_t)4 * Cin * R;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int row = (int)((i / Cin) % R);
+    const int t = (int)(i / ((int64_t)Cin * R));
+    const int dy = t >> 1, dx = t & 1;
+    const int co = row % Cout, b = (row / Cout) % s, a = row / (Cout * s);
+    const int ky = a + s * (1 - dy), kx = b + s * (1 - dx);
+    const bf16 v = f2bf(w[(((int64_t)ky * k + kx) * Cout + co) * Cin + ci]);
+    if (bf) bf[(((int64_t)t * (Cin / 64) + ci / 64) * R + row) * 64 + (ci & 63)] = v;
+    if (bt) bt[(((int64_t)t * (R / 64) + row / 64) * Cin + ci) * 64 + (row & 63)] = v;
+  }
+}
+
+// dyb[n, r, c, (a,b,co)] bf16 <- dy[n, r*s-p+a, c*s-p+b, co]; thread = 8 consecutive (b,co) of one a
+template <typename GT>
+__global__ void __launch_bounds__(kThreads) deconv_pack_dy_kernel(const GT* __restrict__ dy, uint4* __restrict__ dyb, int N,
+                                                                  int H, int W, int Co, int s) {
+  const int OH = H * s, OW = W * s, p = s / 2, R = s * s * Co, R8 = R >> 3, BH = H + 1, BW = W + 1;
+  const int64_t total = (int64_t)N * BH * BW * R8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % R8);
+    int64_t q = i / R8;
+    const int c = (int)(q % BW);
+    q /= BW;
+    const int r = (int)(q % BH);
+    const int n = (int)(q / BH);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = g * 8 + j;
+      const int co = e % Co, b = (e / Co) % s, a = e / (Co * s);
+      const int oy = r * s - p + a, ox = c * s - p + b;
+      v[j] = (oy >= 0 && oy < OH && ox >= 0 && ox < OW) ? ld_f(dy + (((int64_t)n * OH + oy) * OW + ox) * Co + co) : 0.f;
+    }
+    dyb[i] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// dW[ky,kx,co,ci] fp32 <- dwt[t][ci][(a,b,co)] with ky = a + s(1-dy), kx = b + s(1-dx), t = dy*2 + dx
+__global__ void __launch_bounds__(kThreads) deconv_unpack_dw_kernel(const float* __restrict__ dwt, float* __restrict__ dw,
+                                                                    int k, int s, int Cin, int Cout, int accumulate) {
+  const int R = s * s * Cout;
+  const int64_t total = (int64_t)k * k * Cout * Cin;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    int64_t q = i / Cin;
+    const int co = (int)(q % Cout);
+    q /= Cout;
+    const int kx = (int)(q % k), ky = (int)(q / k);
+    const int dy = 1 - ky / s, a = ky % s, dx = 1 - kx / s, b = kx % s;
+    const float v = dwt[((int64_t)(dy * 2 + dx) * Cin + ci) * R + (a * s + b) * Cout + co];
+    dw[i] = accumulate ? dw[i] + v : v;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -431,6 +501,42 @@ int segk_channel_copy(segk_ctx* ctx, const void* src, int ld_src, int coff_src, 
   channel_copy_kernel<<<sgrid(ctx, items, 16), kThreads, 0, (cudaStream_t)stream>>>(
       (const bf16*)src, ld_src, coff_src, (bf16*)dst, ld_dst, coff_dst, (const bf16*)mask, accumulate, rows, C / 8);
   SEGK_LAUNCHED(ctx, "channel_copy");
+  return SEGK_OK;
+}
+
+
+int segk_pack_deconv_packed(segk_ctx* ctx, const float* w, void* bf, void* bt, int k, int s, int Cin, int Cout, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, w && (bf || bt) && k == 2 * s && s > 0 && s % 2 == 0, "pack_deconv_packed: bad args");
+  SEGK_REQUIRE(ctx, Cin % 64 == 0 && (s * s * Cout) % 64 == 0, "pack_deconv_packed: needs Cin %% 64 == 0 and s*s*Cout %% 64 == 0");
+  pack_deconv_packed_kernel<<<sgrid(ctx, (int64_t)4 * Cin * s * s * Cout), kThreads, 0, (cudaStream_t)stream>>>(
+      w, (bf16*)bf, (bf16*)bt, k, s, Cin, Cout);
+  SEGK_LAUNCHED(ctx, "pack_deconv_packed");
+  return SEGK_OK;
+}
+
+int segk_deconv_pack_dy(segk_ctx* ctx, const void* dy, int dy_is_f32, void* dyb, int N, int H, int W, int Cout, int s,
+                        void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, dy && dyb && N > 0 && H > 0 && W > 0 && s > 0 && s % 2 == 0, "deconv_pack_dy: bad args");
+  SEGK_REQUIRE(ctx, (s * s * Cout) % 8 == 0 && (((uintptr_t)dyb) & 15) == 0, "deconv_pack_dy: s*s*Cout %% 8, 16-byte alignment");
+  const int64_t total = (int64_t)N * (H + 1) * (W + 1) * (s * s * Cout / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dy_is_f32)
+    deconv_pack_dy_kernel<float><<<sgrid(ctx, total), kThreads, 0, st>>>((const float*)dy, (uint4*)dyb, N, H, W, Cout, s);
+  else
+    deconv_pack_dy_kernel<bf16><<<sgrid(ctx, total), kThreads, 0, st>>>((const bf16*)dy, (uint4*)dyb, N, H, W, Cout, s);
+  SEGK_LAUNCHED(ctx, "deconv_pack_dy");
+  return SEGK_OK;
+}
+
+int segk_deconv_unpack_dw(segk_ctx* ctx, const float* dwt, float* dw, int k, int s, int Cin, int Cout, int accumulate,
+                          void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, dwt && dw && k == 2 * s && s > 0, "deconv_unpack_dw: bad args");
+  deconv_unpack_dw_kernel<<<sgrid(ctx, (int64_t)k * k * Cout * Cin), kThreads, 0, (cudaStream_t)stream>>>(
+      dwt, dw, k, s, Cin, Cout, accumulate);
+  SEGK_LAUNCHED(ctx, "deconv_unpack_dw");
   return SEGK_OK;
 }
 

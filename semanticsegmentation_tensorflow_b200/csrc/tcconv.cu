@@ -107,6 +107,9 @@ struct IgemmParams {
   // per-(CTA, TMEM lane quarter) partial rows [n_tiles][(grid / n_tiles) * 4][BLOCK_N]; needs channel-tile-fastest
   // order, no split-K and grid % n_tiles == 0 (every tile of a CTA then has the same channel tile)
   float* colsum;
+  // phase-packed transposed conv (segk_deconv2d_packed_fwd): GEMM column = (a*pack_s + b)*pack_co + co of the
+  // pack_s x pack_s x pack_co output block of row (n, qy, qx); fp32 stores at out pixel (qy*pack_s - opad + a, ...)
+  int pack_s, pack_co;
   // "team stream-K" for layers with few output tiles and a long, weight-heavy K walk (conv6 dgrad: 50 tiles x ~2060
   // k-steps, 205 MB of weights).  The tiles that differ only in the batch coordinate (team_members = tiles_n of them)
   // share every weight slice, so they form a TEAM of CTAs that walk the same k-steps in lockstep (the slice comes from
@@ -465,7 +468,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
         }
         // bias for these 32 columns: issued before the TMEM load so its L2/L1 latency hides behind it
         float4 bv[8];
-        if (p.bias) {
+        if (p.bias && !p.pack_s) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + t.nt * BLOCK_N + c0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) bv[i] = __ldg(b4 + i);
@@ -473,7 +476,25 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
-        if (valid && partial) {
+        if (p.pack_s) {
+          // 32 columns = 32 / (pack_s * pack_co) output rows `a`, each pack_s pixels x pack_co classes contiguous
+          const bool rv = row < p.rows && qx < p.W && qy < p.H && n < p.N;
+          const int run = p.pack_s * p.pack_co;
+          if (rv) {
+            float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const int col = t.nt * BLOCK_N + c0 + i;
+              const int a = col / run, b = (col % run) / p.pack_co, co = col % p.pack_co;
+              const int oy2 = qy * p.pack_s - p.opad + a, ox2 = qx * p.pack_s - p.opad + b;
+              if (oy2 < 0 || oy2 >= p.out_H || ox2 < 0 || ox2 >= p.out_W) continue;
+              const int64_t off = (((int64_t)n * p.out_H + oy2) * p.out_W + ox2) * p.pack_co + co;
+              float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
+              if (p.bias) { v0 += __ldg(p.bias + co); v1 += __ldg(p.bias + co + 1); }
+              *reinterpret_cast<float2*>(o + off) = make_float2(v0, v1);      // pack_co is even: (co, co+1) of one pixel
+            }
+          }
+        } else if (valid && partial) {
           float4* w4 = reinterpret_cast<float4*>(p.ws + (int64_t)t.split * p.ws_slice + obase + c0);
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -1974,6 +1995,185 @@ int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw,
   }
   if (rc) return rc;
   if (partials) return segk_reduce_partials(ctx, (const float*)ctx->ws4, dw, n_dw, p.splits, accumulate, st);
+  return SEGK_OK;
+}
+
+// ---- phase-packed transposed conv for tiny Cout (conv_t3; patch.cu has the layout kernels) ----------------------
+static int packed_check(segk_ctx* ctx, const char* what, int N, int H, int W, int Cin, int Cout, int k, int s) {
+  SEGK_REQUIRE(ctx, N > 0 && H > 0 && W > 0, "%s: empty tensor", what);
+  SEGK_REQUIRE(ctx, k == 2 * s && s >= 2 && s % 2 == 0, "%s: need k == 2*stride, even stride", what);
+  const int R = s * s * Cout;
+  SEGK_REQUIRE(ctx, Cin % 64 == 0 && (R == 64 || R == 128 || R == 256) && Cout % 2 == 0 && 32 % (s * Cout) == 0,
+               "%s: packed form needs Cin %% 64 == 0, s*s*Cout in {64,128,256}, even Cout, s*Cout | 32 (got %d -> %d, s=%d); no fallback",
+               what, Cin, Cout, s);
+  return SEGK_OK;
+}
+
+int segk_deconv2d_packed_fwd(segk_ctx* ctx, const void* x, const void* bf, const float* bias, float* y, int N, int H, int W,
+                             int Cin, int Cout, int k, int s, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && bf && y, "deconv2d_packed_fwd: null pointer");
+  int rc = packed_check(ctx, "deconv2d_packed_fwd", N, H, W, Cin, Cout, k, s);
+  if (rc) return rc;
+  const int R = s * s * Cout;
+  const Box b = choose_box(N, H + 1, W + 1, kBlockM, false, H, W);
+  SEGK_REQUIRE(ctx, b.rows > 0, "deconv2d_packed_fwd: no pixel box");
+  const int block_n = R;                  // one channel tile: 64 / 128 / 256 columns
+  TensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Cin, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin, b.bw, b.bh, b.bn);
+  if (rc) return rc;
+  maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
+  rc = encode_weight_map_blocked(ctx, &maps.b, bf, Cin, R, 4, block_n);
+  if (rc) return rc;
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H + 1; p.W = W + 1;
+  p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.rows;
+  p.tiles_w = ceil_div(W + 1, b.bw); p.tiles_h = ceil_div(H + 1, b.bh); p.tiles_n = ceil_div(N, b.bn);
+  p.n_tiles = 1;
+  p.phases = 1; p.s = 1;
+  p.ntaps = 4; p.kchunks = Cin / 64;
+  p.in_H = H; p.in_W = W;
+  p.out_H = H * s; p.out_W = W * s; p.ldo = Cout; p.os = 1; p.opad = s / 2;
+  p.out = y; p.out_f32 = 1;
+  p.bias = bias; p.scale = 1.f;
+  p.ksplits = 1;
+  p.pack_s = s; p.pack_co = Cout;
+  TapTable taps;
+  memset(&taps, 0, sizeof(taps));
+  for (int u = 0; u < 4; ++u) {            // tap t = dy*2 + dx reads x[r - 1 + dy, c - 1 + dx]
+    taps.dy[u] = (int8_t)(u / 2 - 1);
+    taps.dx[u] = (int8_t)(u % 2 - 1);
+  }
+  return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+}
+
+int segk_deconv2d_packed_dgrad(segk_ctx* ctx, const void* dyb, const void* bt, const void* relu_mask, void* dx,
+                               float* dx_colsum, int N, int H, int W, int Cin, int Cout, int k, int s, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, dyb && bt && dx, "deconv2d_packed_dgrad: null pointer");
+  int rc = packed_check(ctx, "deconv2d_packed_dgrad", N, H, W, Cin, Cout, k, s);
+  if (rc) return rc;
+  const int R = s * s * Cout;
+  const Box b = choose_box(N, H, W, kBlockM, false);
+  SEGK_REQUIRE(ctx, b.rows > 0, "deconv2d_packed_dgrad: no pixel box");
+  const int block_n = pick_block_n(ctx, Cin);
+  TensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  // A = dyb [N, H+1, W+1, R]; tap t = dy*2 + dx reads block (i + 1 - dy, j + 1 - dx): always inside the block grid
+  rc = encode_act_map(ctx, &maps.a[0], dyb, N, H + 1, W + 1, R, R, (int64_t)(W + 1) * R, (int64_t)(H + 1) * (W + 1) * R, b.bw,
+                      b.bh, b.bn);
+  if (rc) return rc;
+  maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
+  rc = encode_weight_map_blocked(ctx, &maps.b, bt, R, Cin, 4, block_n);
+  if (rc) return rc;
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H; p.W = W;
+  p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.rows;
+  p.tiles_w = ceil_div(W, b.bw); p.tiles_h = ceil_div(H, b.bh); p.tiles_n = ceil_div(N, b.bn);
+  p.n_tiles = Cin / block_n;
+  p.phases = 1; p.s = 1;
+  p.ntaps = 4; p.kchunks = R / 64;
+  p.in_H = H + 1; p.in_W = W + 1;
+  p.out_H = H; p.out_W = W; p.ldo = Cin; p.os = 1; p.opad = 0;
+  p.out = dx; p.out_f32 = 0;
+  p.mask = (const bf16*)relu_mask;
+  p.scale = 1.f;
+  p.ksplits = 1;
+  p.tma_store = ctx->tma_store ? 1 : 0;
+  if (p.tma_store) {
+    rc = encode_act_map(ctx, &maps.c, dx, N, H, W, Cin, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin, b.bw, b.bh, b.bn);
+    if (rc) return rc;
+  }
+  TapTable taps;
+  memset(&taps, 0, sizeof(taps));
+  for (int u = 0; u < 4; ++u) {
+    taps.dy[u] = (int8_t)(1 - u / 2);
+    taps.dx[u] = (int8_t)(1 - u % 2);
+  }
+  if (dx_colsum) {
+    const int tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+    const int total = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+    if (total < p.n_tiles) {
+      rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+      if (rc) return rc;
+      return colsum_fallback(ctx, dx, (int64_t)N * H * W, Cin, dx_colsum, (cudaStream_t)stream);
+    }
+    rc = colsum_scratch(ctx, total, block_n, &p.colsum);
+    if (rc) return rc;
+    rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+    if (rc) return rc;
+    return colsum_finish(ctx, dx_colsum, (total / p.n_tiles) * p.n_tiles, p.n_tiles, block_n, (cudaStream_t)stream);
+  }
+  return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+}
+
+int segk_deconv2d_packed_wgrad(segk_ctx* ctx, const void* x, const void* dyb, float* dwt, int N, int H, int W, int Cin,
+                               int Cout, int k, int s, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && dyb && dwt, "deconv2d_packed_wgrad: null pointer");
+  int rc = packed_check(ctx, "deconv2d_packed_wgrad", N, H, W, Cin, Cout, k, s);
+  if (rc) return rc;
+  const int R = s * s * Cout;
+  cudaStream_t st = (cudaStream_t)stream;
+  // pixels = blocks (n, r, c) of the (H+1) x (W+1) block grid; rows (t, ci) from x shifted by (dy-1, dx-1), cols = R
+  const Box b = choose_box(N, H + 1, W + 1, 64, true);
+  SEGK_REQUIRE(ctx, b.rows == 64, "deconv2d_packed_wgrad: cannot tile %dx%dx%d into 64-block boxes", N, H + 1, W + 1);
+  const int block_n = R;
+  TensorMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Cin, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin, b.bw, b.bh, b.bn);
+  if (rc) return rc;
+  maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
+  rc = encode_act_map(ctx, &maps.b, dyb, N, H + 1, W + 1, R, R, (int64_t)(W + 1) * R, (int64_t)(H + 1) * (W + 1) * R, b.bw, b.bh,
+                      b.bn);
+  if (rc) return rc;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.N = N; p.H = H + 1; p.W = W + 1;
+  p.bw = b.bw; p.bh = b.bh; p.bn = b.bn;
+  p.tiles_w = ceil_div(W + 1, b.bw); p.tiles_h = ceil_div(H + 1, b.bh); p.tiles_n = ceil_div(N, b.bn);
+  const int n_ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.kchunks_in = Cin / 64;
+  p.n_rb = 4 * p.kchunks_in;
+  p.n_rbp = (p.n_rb + 1) / 2;
+  p.n_tiles = 1;
+  const int base_items = p.n_rbp;
+  int splits = base_items >= 16 ? ctx->sm_count / base_items : ceil_div(2 * ctx->sm_count, base_items);
+  const int max_splits = ceil_div(n_ptiles, 8);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const int per_split = ceil_div(n_ptiles, splits);
+  p.splits = ceil_div(n_ptiles, per_split);
+  p.Cin_total = Cin; p.Cout_total = R;
+  p.dw_tap_stride = Cin * R; p.dw_row_stride = R; p.dw_col_stride = 1;
+  p.dw = dwt;
+  p.direct = 1;
+  const size_t n_dw = (size_t)4 * Cin * R;
+  const bool partials = p.splits > 1;
+  if (partials) {
+    rc = segk_ws4(ctx, sizeof(float) * n_dw * p.splits);
+    if (rc) return rc;
+    p.dw = (float*)ctx->ws4;
+    p.part_stride = (int64_t)n_dw;
+  }
+  TapTable taps;
+  memset(&taps, 0, sizeof(taps));
+  for (int u = 0; u < 4; ++u) {
+    taps.dy[u] = (int8_t)(u / 2 - 1);
+    taps.dx[u] = (int8_t)(u % 2 - 1);
+  }
+  const int total = p.splits * p.n_rbp * p.n_tiles;
+  const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  switch (block_n) {
+    case 256: rc = launch_wgrad_t<256>(ctx, maps, p, taps, grid, st); break;
+    case 128: rc = launch_wgrad_t<128>(ctx, maps, p, taps, grid, st); break;
+    default: rc = launch_wgrad_t<64>(ctx, maps, p, taps, grid, st); break;
+  }
+  if (rc) return rc;
+  if (partials) return segk_reduce_partials(ctx, (const float*)ctx->ws4, dwt, n_dw, p.splits, 0, st);
   return SEGK_OK;
 }
 

@@ -110,6 +110,8 @@ class Variables:
                                                                            self.wd.get(l.name))
             elif l.path in ("first", "im2col"):
                 self.wk[l.name] = ops.pack_im2col_weights(w, self.wk.get(l.name))
+            elif l.path == "packed":
+                self.wk[l.name], self.wd[l.name] = ops.pack_deconv_packed(w, l.stride, self.wk.get(l.name), self.wd.get(l.name))
             elif l.path == "patch":
                 # W[k,k,Cout,Cin] as the matrix [(ky,kx,co)][ci]: wk = fwd B operand, wd = its transpose
                 e = l.k * l.k * l.cout
@@ -297,7 +299,13 @@ class FCN(_Feeds):
                 self.patch[l.name] = torch.empty((N, h, w, 64), dtype=bf, device=dev)
                 self.patch_f32[l.name] = torch.empty((1, 1, 64, l.cout), dtype=torch.float32, device=dev)
             elif l.kind == "deconv":
-                if l.path == "patch":
+                if l.path == "packed":
+                    r = l.stride * l.stride * l.cout
+                    # dy re-blocked per 2x2 input neighbourhood; zero-initialised once (every entry is rewritten
+                    # each step, the ones outside the image with zeros)
+                    self.patch[l.name] = torch.zeros((N, h + 1, w + 1, r), dtype=bf, device=dev)
+                    self.patch_f32[l.name] = torch.empty((4, l.cin, r), dtype=torch.float32, device=dev)
+                elif l.path == "patch":
                     e = l.k * l.k * l.cout
                     self.patch[l.name] = torch.empty((N, h, w, e), dtype=bf, device=dev)
                     self.patch_f32[l.name] = torch.empty((N, h, w, e), dtype=torch.float32, device=dev)
@@ -362,6 +370,9 @@ class FCN(_Feeds):
                 res = {"conv_t1": act["pool4"], "conv_t2": act["pool3"]}.get(l.name)   # fuse, FCN.py:92,96
                 if l.path == "tc":
                     ops.deconv2d_fwd(cur, V.wk[l.name], b, out, l.k, l.stride, residual=res)
+                elif l.path == "packed":
+                    assert res is None and out.dtype == torch.float32
+                    ops.deconv2d_packed_fwd(cur, V.wk[l.name], b, out, l.k, l.stride)
                 elif l.path == "patch":
                     yp = ops.conv2d_fwd(cur, V.wk[l.name], None, self.patch_f32[l.name], 1, 1, relu=False,
                                         flops=deconv_flops(self.N, cur.shape[1], cur.shape[2], l.cin, l.cout, l.k, l.stride))
@@ -455,6 +466,11 @@ class FCN(_Feeds):
                 if l.path == "tc":
                     wjob = lambda x=xin, d=dcur, g=gw, l=l: ops.deconv2d_wgrad(x, d, g, l.k, l.stride)
                     wmark = self.wside.mark()
+                elif l.path == "packed":
+                    Pg = ops.deconv_pack_dy(dcur, self.patch[l.name], l.stride)
+                    wjob = lambda Pg=Pg, x=xin, g=gw, l=l: ops.deconv2d_packed_wgrad(x, Pg, g, self.patch_f32[l.name], l.k, l.stride)
+                    wmark = self.wside.mark()
+                    wreads = ()
                 elif l.path == "patch":
                     Pg = ops.deconv_patch_gather(dcur, self.patch[l.name], l.k, l.stride)
                     dfl = deconv_flops(self.N, xin.shape[1], xin.shape[2], l.cin, l.cout, l.k, l.stride)
@@ -473,9 +489,11 @@ class FCN(_Feeds):
                 else:
                     dx = next_dx(xin)
                 mask = xin if (prev is not None and prev.kind == "conv" and prev.relu) else None
-                cs = fused_bias(prev) if l.path in ("tc", "patch") else None
+                cs = fused_bias(prev) if l.path in ("tc", "patch", "packed") else None
                 if l.path == "tc":
                     ops.deconv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.stride, relu_mask=mask, colsum=cs)
+                elif l.path == "packed":
+                    ops.deconv2d_packed_dgrad(Pg, V.wd[l.name], dx, l.cout, l.k, l.stride, relu_mask=mask, colsum=cs)
                 elif l.path == "patch":
                     ops.conv2d_dgrad(Pg, V.wd[l.name], dx, 1, 1, relu_mask=mask, flops=dfl, colsum=cs)
                 else:

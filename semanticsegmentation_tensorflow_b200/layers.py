@@ -124,6 +124,10 @@ def deconv_layer(x, shape, num_filters, name, output_shape, filter_height=4, fil
     if route == "tc":
         wk, _ = st.packed(name, lambda: ops.pack_deconv_weights(w, stride))
         ops.deconv2d_fwd(x, wk, b, y, k, stride)
+    elif route == "packed":
+        bf, _ = st.packed(name, lambda: ops.pack_deconv_packed(w, stride))
+        y = torch.empty((n, h * stride, wd * stride, cout), dtype=torch.float32, device=x.device)    # fp32 logits
+        ops.deconv2d_packed_fwd(x, bf, b, y, k, stride)
     elif route == "patch":
         e = k * k * cout
         wk, _ = st.packed(name, lambda: ops.pack_matrix(w.view(1, e, cin)))

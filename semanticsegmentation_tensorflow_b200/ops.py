@@ -140,6 +140,47 @@ class Ops:
         self.call("segk_pack_matrix", _p(w3), _p(cp), _p(tr), t, a, b, _stream())
         return cp, tr
 
+    # ---- phase-packed transposed conv with tiny Cout (conv_t3): one 4-tap GEMM over the block grid ----
+    def pack_deconv_packed(self, w, s, bf=None, bt=None):
+        k, _, cout, cin = w.shape
+        r = s * s * cout
+        if bf is None:
+            bf = torch.empty((4, cin // 64, r, 64), dtype=torch.bfloat16, device=w.device)
+        if bt is None:
+            bt = torch.empty((4, r // 64, cin, 64), dtype=torch.bfloat16, device=w.device)
+        self.call("segk_pack_deconv_packed", _p(w), _p(bf), _p(bt), k, s, cin, cout, _stream())
+        return bf, bt
+
+    def deconv2d_packed_fwd(self, x, bf, bias, y, k, s):
+        n, h, w, cin = x.shape
+        cout = y.shape[3]
+        self._w(deconv_flops(n, h, w, cin, cout, k, s), "flop")
+        self.call("segk_deconv2d_packed_fwd", _p(x), _p(bf), _p(bias), _p(y), n, h, w, cin, cout, k, s, _stream())
+        return y
+
+    def deconv_pack_dy(self, dy, dyb, s):
+        n, hb, wb, r = dyb.shape
+        cout = dy.shape[3]
+        self._w(float(dy.numel() * dy.element_size() + 2 * dyb.numel()), "byte")
+        self.call("segk_deconv_pack_dy", _p(dy), int(dy.dtype == torch.float32), _p(dyb), n, hb - 1, wb - 1, cout, s, _stream())
+        return dyb
+
+    def deconv2d_packed_dgrad(self, dyb, bt, dx, cout, k, s, relu_mask=None, colsum=None):
+        n, h, w, cin = dx.shape
+        self._w(deconv_flops(n, h, w, cin, cout, k, s), "flop")
+        self.call("segk_deconv2d_packed_dgrad", _p(dyb), _p(bt), _p(relu_mask), _p(dx), _p(colsum), n, h, w, cin, cout, k, s,
+                  _stream())
+        return dx
+
+    def deconv2d_packed_wgrad(self, x, dyb, dw, dwt, k, s, accumulate=False):
+        """dw [k,k,Cout,Cin] fp32; dwt: fp32 scratch [4, Cin, s*s*Cout]."""
+        n, h, w, cin = x.shape
+        cout = dw.shape[2]
+        self._w(deconv_flops(n, h, w, cin, cout, k, s), "flop")
+        self.call("segk_deconv2d_packed_wgrad", _p(x), _p(dyb), _p(dwt), n, h, w, cin, cout, k, s, _stream())
+        self.call("segk_deconv_unpack_dw", _p(dwt), _p(dw), k, s, cin, cout, int(accumulate), _stream())
+        return dw
+
     def pack_im2col_weights(self, w, wk=None):
         kh, kw, cin, cout = w.shape
         if wk is None:

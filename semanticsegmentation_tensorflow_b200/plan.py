@@ -38,8 +38,9 @@ class Layer:
     def path(self) -> str:
         """Kernel route: 'tc' implicit GEMM; 'first' = 3x3 conv on the raw image (Cin 1/3/4) with the
         patches built in shared memory; 'im2col' = other layers with kh*kw*Cin <= 64 turned into
-        a 1x1 GEMM over a 64-wide patch tensor; 'patch' = transposed conv with tiny Cout run as
-        GEMMs in patch space [N,H,W,k*k*Cout]; 'small' = CUDA-core kernels."""
+        a 1x1 GEMM over a 64-wide patch tensor; 'packed' = transposed conv with tiny Cout as ONE 4-tap
+        phase-packed GEMM over the block grid (conv_t3); 'patch' = the same layer as GEMMs in patch space
+        [N,H,W,k*k*Cout] (shapes the packed form does not take); 'small' = CUDA-core kernels."""
         if self.kind == "pool":
             return "none"
         if self.kind == "conv":
@@ -52,6 +53,9 @@ class Layer:
             return "small"
         if self.cin % 64 == 0 and self.cout % 64 == 0 and self.k == 4 and self.stride == 2:
             return "tc"
+        if (self.cin % 64 == 0 and self.k == 2 * self.stride and self.stride % 2 == 0 and self.cout % 2 == 0
+                and self.stride * self.stride * self.cout in (64, 128, 256) and 32 % (self.stride * self.cout) == 0):
+            return "packed"
         if self.cin % 64 == 0 and (self.k * self.k * self.cout) % 64 == 0 and self.k == 2 * self.stride:
             return "patch"
         return "small"

@@ -321,3 +321,59 @@ def test_skinny_kxk_head(ops, cuda_device, case):
     ops.conv2d_small_wgrad(xd, dyd, dw)
     torch.cuda.synchronize()
     assert_close(host(dw), wtt.grad.numpy(), 1e-4, f"skinny kxk wgrad {case}")
+
+
+@pytest.mark.parametrize("case", [
+    # N, H, W, Cin, Cout, k, s
+    (2, 5, 9, 256, 2, 16, 8),        # conv_t3 (FCN.py:98-107)
+    (32, 20, 72, 256, 2, 16, 8),     # ... at the benchmarked shape (only spot-checked against the oracle below)
+    (1, 7, 10, 64, 4, 16, 8),        # four classes: R = 256
+    (3, 6, 5, 128, 4, 8, 4),         # k = 8, s = 4: R = 64
+])
+def test_conv_t3_phase_packed(ops, cuda_device, case):
+    """The phase-packed form of the tiny-Cout transposed conv: one 4-tap GEMM over the block grid with the logits
+    written by the epilogue; backward from the re-blocked dy.  Against oracle/tf_ops.conv2d_transpose_same."""
+    n, h, w, ci, co, k, s = case
+    rng = np.random.default_rng(12)
+    full = n * h * w <= 4000
+    x = bf16_grid(rng.standard_normal((n, h, w, ci)))
+    wt = bf16_grid(rng.standard_normal((k, k, co, ci)) / np.sqrt(4 * ci))
+    b = (rng.standard_normal(co) * 0.1).astype(np.float32)
+    dy = (rng.standard_normal((n, h * s, w * s, co)) / 64).astype(np.float32)
+    bf, bt = ops.pack_deconv_packed(dev_f32(wt, cuda_device), s)
+    xd = dev_bf16(x, cuda_device)
+    y = torch.full((n, h * s, w * s, co), 7.0, dtype=torch.float32, device=cuda_device)
+    ops.deconv2d_packed_fwd(xd, bf, dev_f32(b, cuda_device), y, k, s)
+    r = s * s * co
+    dyb = torch.full((n, h + 1, w + 1, r), 7.0, dtype=torch.bfloat16, device=cuda_device)
+    ops.deconv_pack_dy(dev_f32(dy, cuda_device), dyb, s)
+    dx = torch.full((n, h, w, ci), 7.0, dtype=torch.bfloat16, device=cuda_device)
+    cs = torch.full((ci,), 7.0, dtype=torch.float32, device=cuda_device)
+    ops.deconv2d_packed_dgrad(dyb, bt, dx, co, k, s, colsum=cs)
+    dw = torch.full((k, k, co, ci), 7.0, dtype=torch.float32, device=cuda_device)
+    dwt = torch.empty((4, ci, r), dtype=torch.float32, device=cuda_device)
+    ops.deconv2d_packed_wgrad(xd, dyb, dw, dwt, k, s)
+    torch.cuda.synchronize()
+    sl = slice(None) if full else slice(0, 2)          # the oracle on the first two images of the large case
+    xt = torch.tensor(x[sl], requires_grad=True)
+    wtt = torch.tensor(wt, requires_grad=True)
+    y_ref = T.bias_add(T.conv2d_transpose_same(xt, wtt, (h * s, w * s), s), torch.tensor(b))
+    assert_close(host(y)[sl], y_ref.detach().numpy(), 1e-4, f"packed deconv fwd {case}")
+    y_ref.backward(torch.tensor(bf16_grid(dy[sl])))     # dy is rounded to bf16 in the block tensor
+    assert_close(host(dx)[sl], xt.grad.numpy(), 1e-2, f"packed deconv dgrad {case}")
+    if full:
+        assert_close(host(dw), wtt.grad.numpy(), 2e-3, f"packed deconv wgrad {case}")
+        gx = xt.grad.numpy()
+        np.testing.assert_allclose(host(cs), gx.astype(np.float64).sum(axis=(0, 1, 2)), rtol=0,
+                                   atol=4e-3 * np.abs(gx).max() * np.sqrt(n * h * w))
+    else:
+        # wgrad is additive over images: the full batch equals the sum over two halves
+        dwa = torch.empty_like(dw)
+        dwb = torch.empty_like(dw)
+        half = n // 2
+        for lo, hi, out in ((0, half, dwa), (half, n, dwb)):
+            d2 = torch.empty((hi - lo, h + 1, w + 1, r), dtype=torch.bfloat16, device=cuda_device)
+            ops.deconv_pack_dy(dev_f32(dy[lo:hi], cuda_device), d2, s)
+            ops.deconv2d_packed_wgrad(xd[lo:hi].contiguous(), d2, out, dwt, k, s)
+        torch.cuda.synchronize()
+        assert_close(host(dw), host(dwa) + host(dwb), 1e-4, f"packed deconv wgrad additivity {case}")
