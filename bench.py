@@ -159,7 +159,13 @@ def run_gpu(args):
     host_y = torch.randint(0, 2, (B, H, W), dtype=torch.uint8, generator=gen).pin_memory()
     dev_x, dev_y = host_x.to(dev), host_y.to(dev)
 
-    if args.model in ("unet", "segnet"):
+    if args.model == "fcdensenet":
+        from semanticsegmentation_tensorflow_b200.densenet import FCDenseNet, fcdensenet_flops_per_image
+        net = FCDenseNet(dev_x, KEEP_PROB, NCLS, seed=1234, world_size=world, dropout_seed=42 + rank)
+        train_gflop = fcdensenet_flops_per_image(net.nodes, net.ch, H, W)[1] / 1e9
+        workload = f"FCDenseNet (FCDenseNet.py:83-163, 130 conv layers) 2-class bf16 training (fwd+loss+bwd+Adam), batch {B} per GPU, 160x576x3 (BASELINE configs[4] at the configs[1] resolution)"
+        metric = "train images/sec FCDenseNet 160x576"
+    elif args.model in ("unet", "segnet"):
         from semanticsegmentation_tensorflow_b200.graph import SegNet, UNet, graph_flops_per_image, segnet_nodes, unet_nodes
         build, nodes = (UNet, unet_nodes) if args.model == "unet" else (SegNet, segnet_nodes)
         net = build(dev_x, NCLS, seed=1234, world_size=world)
@@ -566,7 +572,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the bounded U-Net / inference runs after the headline regions")
     ap.add_argument("--layers-out", default=None, help="write the per-call (per-layer) timing table here")
-    ap.add_argument("--model", default="fcn", choices=["fcn", "unet", "segnet"],
+    ap.add_argument("--model", default="fcn", choices=["fcn", "unet", "segnet", "fcdensenet"],
                     help="fcn = FCN-8s (BASELINE configs[1], the driver's metric); unet = configs[2]; segnet = the reference's SegNet")
     ap.add_argument("--workload", default="train", choices=["train", "infer"],
                     help="train = BASELINE configs[1] (default, the driver's metric); infer = configs[3]: "

@@ -230,6 +230,37 @@ int segk_bn_gamma_grad(segk_ctx* ctx, const void* dz, const void* y, const float
 int segk_bn_grads_f32(segk_ctx* ctx, const float* dz, const float* y, const float* beta, const float* gamma,
                       float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
                       int64_t rows, int C, void* stream);
+/* ---- dense-block builders (Network/model/FCDenseNet.py:23-60) ---------------------------------------------
+ * Tensors of these builders are stored with every channel segment padded to a multiple of 8 and the total to a
+ * multiple of 64 (pads are zero), so each conv is a tcgen05 GEMM over 64-wide channel chunks; parameters are
+ * remapped logical <-> physical with `map[physical] = logical index or -1`.  Rows are `ld` elements apart, so a
+ * kernel can work on a channel PREFIX of a concat buffer (the zero-copy view of Concat(layers_concat), :55).
+ *
+ * Pre-activation Batch_Normalization + ReLU (utils.py:300-303; BN is the inference-mode affine):
+ *   y[r][c] = act(x[r][c] * scale[c] + shift[c]), c < C, with scale = gamma / sqrt(1 + 1e-3), shift = beta
+ *   (physical arrays); relu != 0 applies max(., 0). */
+int segk_bn_act_fwd(segk_ctx* ctx, const void* x, int ldx, void* y, int ldy, const float* scale, const float* shift,
+                    int64_t rows, int C, int relu, void* stream);
+/* its gradient: g = dy * [y > 0]; dx (=, or += when accumulate) g * scale; dscale[c] = sum_r g * x, dshift[c] = sum_r g
+ * (two-stage, deterministic).  dy / y have row pitch ldy, x / dx row pitch ldx.  workspace >= the _bytes() value. */
+size_t segk_bn_act_bwd_workspace_bytes(segk_ctx* ctx, int C);
+int segk_bn_act_bwd(segk_ctx* ctx, const void* dy, const void* y, int ldy, const void* x, void* dx, int ldx,
+                    const float* scale, float* dscale, float* dshift, void* workspace, size_t workspace_bytes,
+                    int64_t rows, int C, int relu, int accumulate, void* stream);
+/* Avg_Pooling 2x2 / stride 2 / VALID (utils.py:309) and AvgPoolGrad (dx = dy / 4 on every window element) */
+int segk_avgpool2x2_fwd(segk_ctx* ctx, const void* x, int ldx, void* y, int ldy, int N, int H, int W, int C,
+                        void* stream);
+int segk_avgpool2x2_bwd(segk_ctx* ctx, const void* dy, int lddy, void* dx, int lddx, int N, int H, int W, int C,
+                        void* stream);
+/* logical w[T][A][B] fp32 <-> physical wp[T][Ap][Bp]: to_phys != 0: wp = mapped ? w : 0; else w[mapped] = wp.
+ * amap[Ap] / bmap[Bp] device int32 arrays (NULL = identity on the first A / B entries). */
+int segk_remap_weights(segk_ctx* ctx, float* w, float* wp, int T, int A, int B, int Ap, int Bp, const int* amap,
+                       const int* bmap, int to_phys, void* stream);
+/* per-channel parameters: dst[i] = map[i] >= 0 ? src[map[i]] * mul + add : 0; and dst[map[i]] = src[i] * mul */
+int segk_gather_f32(segk_ctx* ctx, const float* src, const int* map, float* dst, int n, float mul, float add,
+                    void* stream);
+int segk_scatter_f32(segk_ctx* ctx, const float* src, const int* map, float* dst, int n, float mul, void* stream);
+
 /* Concat (utils.py:332) and its gradient: dst[r][coff_dst + c] (=, or += when accumulate)
  * src[r][coff_src + c] for c < C, zeroed where mask[r][c] <= 0 (mask dense [rows][C] or NULL =
  * the fused ReluGrad of the producer).  bf16, all channel counts multiples of 8. */

@@ -4,7 +4,7 @@ Drop-in surface (names follow `Network/model/FCN.py` and `Network/utils/utils.py
     FCN(x, keep_prob, num_classess).create() -> (pred, logits)        FCN.py:31-114      (fcn.py)
     conv_layer / deconv_layer / max_pool / dropout / fuse              FCN.py:117-171     (layers.py)
     AdamOptimizer(lr).minimize(net) -> train_step(feed_dict)           FCN.py:338-340,398 (fcn.py)
-    SegNet(x, num_classes) / FCDenseNet(x, keep_prob, num_classes) / UNet(x, num_classes)  (graph.py)
+    SegNet(x, num_classes) / UNet(x, num_classes) (graph.py); FCDenseNet(x, keep_prob, num_classes) (densenet.py)
 
 All arithmetic runs in hand-written CUDA kernels reached through the C ABI of
 `libsegk.so` (`include/segk.h`) via ctypes.  torch is used for device memory, streams and
@@ -17,7 +17,7 @@ _LAZY = {
     "FCN": "fcn", "AdamOptimizer": "fcn", "MomentumOptimizer": "fcn", "gen_test_output": "fcn",
     "conv_layer": "layers", "deconv_layer": "layers", "max_pool": "layers", "dropout": "layers", "fuse": "layers",
     "VariableStore": "layers",
-    "SegNet": "graph", "UNet": "graph", "FCDenseNet": "graph",
+    "SegNet": "graph", "UNet": "graph", "FCDenseNet": "densenet",
 }
 
 __all__ = ["build_library", "library_path"] + sorted(_LAZY)

@@ -1,0 +1,316 @@
+// HBM-bound kernels of the dense-block builders (Network/model/FCDenseNet.py: bottleneck_layer :23-35,
+// Transition_Layer :37-46) that the VGG-style models do not need:
+//   * pre-activation  Batch_Normalization (inference-mode affine, utils.py:300-301) + ReLU (utils.py:303) on a
+//     channel PREFIX of a concat buffer (the zero-copy view of Concat(layers_concat), FCDenseNet.py:55) and its
+//     gradient (dx accumulated into the concat buffer's gradient, d gamma / d beta by a two-stage reduction);
+//   * Avg_Pooling 2x2 / stride 2 / VALID (utils.py:309) forward and backward;
+//   * logical <-> physical remapping of weights and per-channel parameters.  Tensors are stored with their
+//     channel segments padded to multiples of 8 and the total to a multiple of 64 (pads are always zero) so that
+//     every conv is a tcgen05 GEMM on 64-wide channel chunks; `map[physical] = logical index or -1`.
+// All kernels: 16-byte accesses over rows of `ld` elements (strided channel views), grid-stride loops.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int sgrid(segk_ctx* ctx, int64_t items, int per_sm = 8) {
+  int64_t b = ceil_div64(items, kThreads), cap = (int64_t)ctx->sm_count * per_sm;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+// y[r][c] = act(x[r][c] * scale[c] + shift[c]) for c < C (C % 8 == 0); thread = 8 channels of one row
+__global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y,
+                                                              int ldy, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, int64_t rows, int C8,
+                                                              int relu) {
+  const int64_t total = rows * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % C8);
+    const int64_t r = i / C8;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * ldx) + g);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * g), s1 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * g + 1);
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * g), h1 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * g + 1);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2((&u.x)[j]);
+      v[2 * j] = f.x * sc[2 * j] + sh[2 * j];
+      v[2 * j + 1] = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    reinterpret_cast<uint4*>(y + r * ldy)[g] =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// g = dy * [y > 0] (relu) ; dx (+)= g * scale ; per-block partial sums of g * x (-> d scale) and g (-> d shift).
+// Every thread keeps the same 8 channels over its grid-stride iterations (the thread count is a multiple of C8).
+__global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, int ldy,
+                                                              const bf16* __restrict__ x, bf16* __restrict__ dx, int ldx,
+                                                              const float* __restrict__ scale, float* __restrict__ part,
+                                                              int64_t rows, int C8, int relu, int accumulate) {
+  __shared__ float sh[kThreads][17];
+  const int cpb = C8 < kThreads ? C8 : kThreads;          // channel groups per block row
+  const int R = kThreads / cpb;
+  const int g = blockIdx.y * cpb + (threadIdx.x % cpb);
+  const int rl = threadIdx.x / cpb;
+  float ax[8], as[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ax[j] = as[j] = 0.f;
+  if (g < C8 && rl < R) {
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * g), s1 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * g + 1);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    for (int64_t r = (int64_t)blockIdx.x * R + rl; r < rows; r += (int64_t)gridDim.x * R) {
+      const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + r * ldy) + g);
+      const uint4 uy = __ldg(reinterpret_cast<const uint4*>(y + r * ldy) + g);
+      const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + r * ldx) + g);
+      uint4* dxp = reinterpret_cast<uint4*>(dx + r * ldx) + g;
+      uint4 uo = make_uint4(0, 0, 0, 0);
+      if (accumulate) uo = *dxp;
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fd = unpack_bf16x2((&ud.x)[j]), fy = unpack_bf16x2((&uy.x)[j]), fx = unpack_bf16x2((&ux.x)[j]);
+        const float2 fo = unpack_bf16x2((&uo.x)[j]);
+        const float g0 = (!relu || fy.x > 0.f) ? fd.x : 0.f, g1 = (!relu || fy.y > 0.f) ? fd.y : 0.f;
+        ax[2 * j] += g0 * fx.x; ax[2 * j + 1] += g1 * fx.y;
+        as[2 * j] += g0; as[2 * j + 1] += g1;
+        o[j] = pack_bf16x2(fo.x + g0 * sc[2 * j], fo.y + g1 * sc[2 * j + 1]);
+      }
+      *dxp = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sh[threadIdx.x][j] = ax[j]; sh[threadIdx.x][8 + j] = as[j]; }
+  __syncthreads();
+  if (rl == 0 && g < C8) {
+    for (int k = 1; k < R; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ax[j] += sh[threadIdx.x + k * cpb][j]; as[j] += sh[threadIdx.x + k * cpb][8 + j]; }
+    // partial rows [gridDim.x][2][C]: d scale then d shift
+    float* o = part + (int64_t)blockIdx.x * (2 * C8 * 8) + g * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j] = ax[j]; o[C8 * 8 + j] = as[j]; }
+  }
+}
+
+// out[c] = sum_r part[r][c] (fixed order), 32 columns x 8 row lanes per block
+__global__ void __launch_bounds__(kThreads) dense_reduce_rows_kernel(const float* __restrict__ part, float* __restrict__ out0,
+                                                                     float* __restrict__ out1, int rows, int C) {
+  __shared__ float sh[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;          // over 2C columns
+  float a0 = 0.f, a1 = 0.f;
+  if (c < 2 * C) {
+    int r = rl;
+    for (; r + 8 < rows; r += 16) {
+      a0 += part[(int64_t)r * 2 * C + c];
+      a1 += part[(int64_t)(r + 8) * 2 * C + c];
+    }
+    if (r < rows) a0 += part[(int64_t)r * 2 * C + c];
+  }
+  sh[rl][cl] = a0 + a1;
+  __syncthreads();
+  if (rl == 0 && c < 2 * C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][cl];
+    if (c < C) out0[c] = t;
+    else out1[c - C] = t;
+  }
+}
+
+// Avg_Pooling 2x2 / s2 / VALID: y = mean of the window (fp32 sum, one rounding); thread = 8 channels of a pooled pixel
+__global__ void __launch_bounds__(kThreads) avgpool_fwd_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y,
+                                                               int ldy, int N, int H, int W, int C8) {
+  const int OH = H >> 1, OW = W >> 1;
+  const int64_t total = (int64_t)N * OH * OW * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % C8);
+    int64_t p = i / C8;
+    const int ox = (int)(p % OW);
+    p /= OW;
+    const int oy = (int)(p % OH);
+    const int n = (int)(p / OH);
+    const int64_t r0 = ((int64_t)n * H + 2 * oy) * W + 2 * ox;
+    const int64_t rr[4] = {r0, r0 + 1, r0 + W, r0 + W + 1};
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + rr[k] * ldx) + g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&u.x)[j]);
+        a[2 * j] += f.x; a[2 * j + 1] += f.y;
+      }
+    }
+    const int64_t ro = ((int64_t)n * OH + oy) * OW + ox;
+    reinterpret_cast<uint4*>(y + ro * ldy)[g] = make_uint4(pack_bf16x2(0.25f * a[0], 0.25f * a[1]), pack_bf16x2(0.25f * a[2], 0.25f * a[3]),
+                                                           pack_bf16x2(0.25f * a[4], 0.25f * a[5]), pack_bf16x2(0.25f * a[6], 0.25f * a[7]));
+  }
+}
+
+// AvgPoolGrad: every window element receives dy / 4 (overwrites dx)
+__global__ void __launch_bounds__(kThreads) avgpool_bwd_kernel(const bf16* __restrict__ dy, int lddy, bf16* __restrict__ dx,
+                                                               int lddx, int N, int H, int W, int C8) {
+  const int OH = H >> 1, OW = W >> 1;
+  const int64_t total = (int64_t)N * OH * OW * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % C8);
+    int64_t p = i / C8;
+    const int ox = (int)(p % OW);
+    p /= OW;
+    const int oy = (int)(p % OH);
+    const int n = (int)(p / OH);
+    const int64_t ro = ((int64_t)n * OH + oy) * OW + ox;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy + ro * lddy) + g);
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2((&u.x)[j]);
+      o[j] = pack_bf16x2(0.25f * f.x, 0.25f * f.y);
+    }
+    const uint4 v = make_uint4(o[0], o[1], o[2], o[3]);
+    const int64_t r0 = ((int64_t)n * H + 2 * oy) * W + 2 * ox;
+    reinterpret_cast<uint4*>(dx + r0 * lddx)[g] = v;
+    reinterpret_cast<uint4*>(dx + (r0 + 1) * lddx)[g] = v;
+    reinterpret_cast<uint4*>(dx + (r0 + W) * lddx)[g] = v;
+    reinterpret_cast<uint4*>(dx + (r0 + W + 1) * lddx)[g] = v;
+  }
+}
+
+// logical w[T][A][B] <-> physical wp[T][Ap][Bp]; amap[Ap], bmap[Bp] = logical index or -1 (NULL = identity on the
+// first A / B entries).  to_phys: wp = mapped ? w : 0;  else: w[mapped] = wp * mul
+__global__ void __launch_bounds__(kThreads) remap_weights_kernel(float* __restrict__ w, float* __restrict__ wp, int T, int A,
+                                                                 int B, int Ap, int Bp, const int* __restrict__ amap,
+                                                                 const int* __restrict__ bmap, int to_phys) {
+  const int64_t total = (int64_t)T * Ap * Bp;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int bp = (int)(i % Bp), ap = (int)((i / Bp) % Ap), t = (int)(i / ((int64_t)Ap * Bp));
+    const int la = amap ? amap[ap] : (ap < A ? ap : -1);
+    const int lb = bmap ? bmap[bp] : (bp < B ? bp : -1);
+    if (to_phys) {
+      wp[i] = (la >= 0 && lb >= 0) ? w[((int64_t)t * A + la) * B + lb] : 0.f;
+    } else if (la >= 0 && lb >= 0) {
+      w[((int64_t)t * A + la) * B + lb] = wp[i];
+    }
+  }
+}
+
+// dst[i] = map[i] >= 0 ? src[map[i]] * mul + add : 0   (logical -> physical per-channel parameters)
+__global__ void __launch_bounds__(kThreads) gather_f32_kernel(const float* __restrict__ src, const int* __restrict__ map,
+                                                              float* __restrict__ dst, int n, float mul, float add) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = map[i] >= 0 ? src[map[i]] * mul + add : 0.f;
+}
+// dst[map[i]] = src[i] * mul for map[i] >= 0   (physical -> logical gradients)
+__global__ void __launch_bounds__(kThreads) scatter_f32_kernel(const float* __restrict__ src, const int* __restrict__ map,
+                                                               float* __restrict__ dst, int n, float mul) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && map[i] >= 0) dst[map[i]] = src[i] * mul;
+}
+
+}  // namespace
+
+extern "C" {
+
+int segk_bn_act_fwd(segk_ctx* ctx, const void* x, int ldx, void* y, int ldy, const float* scale, const float* shift,
+                    int64_t rows, int C, int relu, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && y && scale && shift && rows > 0 && C > 0, "bn_act_fwd: bad args");
+  SEGK_REQUIRE(ctx, C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C &&
+                        (((uintptr_t)x | (uintptr_t)y | (uintptr_t)scale | (uintptr_t)shift) & 15) == 0,
+               "bn_act_fwd: C, ldx, ldy multiples of 8, 16-byte aligned pointers");
+  bn_act_fwd_kernel<<<sgrid(ctx, rows * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, scale,
+                                                                                       shift, rows, C / 8, relu);
+  SEGK_LAUNCHED(ctx, "bn_act_fwd");
+  return SEGK_OK;
+}
+
+size_t segk_bn_act_bwd_workspace_bytes(segk_ctx* ctx, int C) {
+  return sizeof(float) * (size_t)(ctx ? ctx->sm_count : 148) * 4 * 2 * (size_t)C;
+}
+
+int segk_bn_act_bwd(segk_ctx* ctx, const void* dy, const void* y, int ldy, const void* x, void* dx, int ldx,
+                    const float* scale, float* dscale, float* dshift, void* workspace, size_t workspace_bytes, int64_t rows,
+                    int C, int relu, int accumulate, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, dy && y && x && dx && scale && dscale && dshift && workspace && rows > 0 && C > 0, "bn_act_bwd: bad args");
+  SEGK_REQUIRE(ctx, C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 &&
+                        (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)scale) & 15) == 0,
+               "bn_act_bwd: C, ldx, ldy multiples of 8, 16-byte aligned pointers");
+  const int C8 = C / 8;
+  const int cpb = C8 < kThreads ? C8 : kThreads;
+  const int R = kThreads / cpb;             // row lanes per block (threads beyond R * cpb idle)
+  const int gy = ceil_div(C8, cpb);
+  int64_t gx = ceil_div64(rows, (int64_t)R * 4);
+  const int64_t cap = ceil_div64((int64_t)ctx->sm_count * 4, gy);
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  SEGK_REQUIRE(ctx, workspace_bytes >= sizeof(float) * (size_t)gx * 2 * C, "bn_act_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_act_bwd_kernel<<<dim3((unsigned)gx, gy), kThreads, 0, st>>>((const bf16*)dy, (const bf16*)y, ldy, (const bf16*)x, (bf16*)dx,
+                                                                 ldx, scale, (float*)workspace, rows, C8, relu, accumulate);
+  SEGK_LAUNCHED(ctx, "bn_act_bwd");
+  dense_reduce_rows_kernel<<<ceil_div(2 * C, 32), kThreads, 0, st>>>((const float*)workspace, dscale, dshift, (int)gx, C);
+  SEGK_LAUNCHED(ctx, "bn_act_bwd_reduce");
+  return SEGK_OK;
+}
+
+int segk_avgpool2x2_fwd(segk_ctx* ctx, const void* x, int ldx, void* y, int ldy, int N, int H, int W, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && y && N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "avgpool_fwd: bad args (even H, W)");
+  SEGK_REQUIRE(ctx, C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0,
+               "avgpool_fwd: C, ldx, ldy multiples of 8, 16-byte aligned pointers");
+  const int64_t items = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  avgpool_fwd_kernel<<<sgrid(ctx, items), kThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, N, H, W, C / 8);
+  SEGK_LAUNCHED(ctx, "avgpool_fwd");
+  return SEGK_OK;
+}
+
+int segk_avgpool2x2_bwd(segk_ctx* ctx, const void* dy, int lddy, void* dx, int lddx, int N, int H, int W, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, dy && dx && N > 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "avgpool_bwd: bad args (even H, W)");
+  SEGK_REQUIRE(ctx, C % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && (((uintptr_t)dy | (uintptr_t)dx) & 15) == 0,
+               "avgpool_bwd: C, ld multiples of 8, 16-byte aligned pointers");
+  const int64_t items = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  avgpool_bwd_kernel<<<sgrid(ctx, items), kThreads, 0, (cudaStream_t)stream>>>((const bf16*)dy, lddy, (bf16*)dx, lddx, N, H, W, C / 8);
+  SEGK_LAUNCHED(ctx, "avgpool_bwd");
+  return SEGK_OK;
+}
+
+int segk_remap_weights(segk_ctx* ctx, float* w, float* wp, int T, int A, int B, int Ap, int Bp, const int* amap, const int* bmap,
+                       int to_phys, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, w && wp && T > 0 && A > 0 && B > 0 && Ap >= 1 && Bp >= 1, "remap_weights: bad args");
+  remap_weights_kernel<<<sgrid(ctx, (int64_t)T * Ap * Bp), kThreads, 0, (cudaStream_t)stream>>>(w, wp, T, A, B, Ap, Bp, amap, bmap,
+                                                                                               to_phys);
+  SEGK_LAUNCHED(ctx, "remap_weights");
+  return SEGK_OK;
+}
+
+int segk_gather_f32(segk_ctx* ctx, const float* src, const int* map, float* dst, int n, float mul, float add, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, src && map && dst && n > 0, "gather_f32: bad args");
+  gather_f32_kernel<<<ceil_div(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(src, map, dst, n, mul, add);
+  SEGK_LAUNCHED(ctx, "gather_f32");
+  return SEGK_OK;
+}
+
+int segk_scatter_f32(segk_ctx* ctx, const float* src, const int* map, float* dst, int n, float mul, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, src && map && dst && n > 0, "scatter_f32: bad args");
+  scatter_f32_kernel<<<ceil_div(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(src, map, dst, n, mul);
+  SEGK_LAUNCHED(ctx, "scatter_f32");
+  return SEGK_OK;
+}
+
+}  // extern "C"

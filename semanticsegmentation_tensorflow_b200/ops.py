@@ -370,6 +370,51 @@ class Ops:
         self.call("segk_bn_grads_f32", _p(dz), _p(y), _p(beta), _p(gamma), _p(dgamma), _p(dbeta), _p(workspace),
                   workspace.numel() * workspace.element_size(), dz.numel() // c, c, _stream())
 
+    # ---- dense-block builders (FCDenseNet.py): strided channel views, physical <-> logical remaps ----
+    def bn_act_fwd(self, x, c, y, scale, shift, relu=True):
+        """x, y: [..., ld] bf16 buffers; the first c channels of every row are processed."""
+        rows = x.numel() // x.shape[-1]
+        self._w(4.0 * rows * c, "byte")
+        self.call("segk_bn_act_fwd", _p(x), x.shape[-1], _p(y), y.shape[-1], _p(scale), _p(shift), rows, c, int(relu), _stream())
+        return y
+
+    def bn_act_bwd(self, dy, y, x, dx, c, scale, dscale, dshift, workspace, relu=True, accumulate=True):
+        rows = x.numel() // x.shape[-1]
+        self._w((8.0 + (4.0 if accumulate else 2.0)) * rows * c, "byte")
+        self.call("segk_bn_act_bwd", _p(dy), _p(y), y.shape[-1], _p(x), _p(dx), x.shape[-1], _p(scale), _p(dscale), _p(dshift),
+                  _p(workspace), workspace.numel() * workspace.element_size(), rows, c, int(relu), int(accumulate), _stream())
+
+    def bn_act_bwd_workspace(self, c, device):
+        n = int(self.ctx.c.segk_bn_act_bwd_workspace_bytes(self.ctx.h, int(c)))
+        return torch.empty(n, dtype=torch.uint8, device=device)
+
+    def avgpool_fwd(self, x, c, y):
+        n, h, w, ldx = x.shape
+        self._w(2.5 * n * h * w * c, "byte")
+        self.call("segk_avgpool2x2_fwd", _p(x), ldx, _p(y), y.shape[-1], n, h, w, c, _stream())
+        return y
+
+    def avgpool_bwd(self, dy, c, dx):
+        n, h, w, lddx = dx.shape
+        self._w(2.5 * n * h * w * c, "byte")
+        self.call("segk_avgpool2x2_bwd", _p(dy), dy.shape[-1], _p(dx), lddx, n, h, w, c, _stream())
+        return dx
+
+    def remap_weights(self, w, wp, amap=None, bmap=None, to_phys=True):
+        """w logical [T..., A, B] fp32 <-> wp physical [T..., Ap, Bp]."""
+        a, b = w.shape[-2], w.shape[-1]
+        ap, bp = wp.shape[-2], wp.shape[-1]
+        t = w.numel() // (a * b)
+        self.call("segk_remap_weights", _p(w), _p(wp), t, a, b, ap, bp, _p(amap), _p(bmap), int(to_phys), _stream())
+
+    def gather_f32(self, src, cmap, dst, mul=1.0, add=0.0):
+        self.call("segk_gather_f32", _p(src), _p(cmap), _p(dst), dst.numel(), float(mul), float(add), _stream())
+        return dst
+
+    def scatter_f32(self, src, cmap, dst, mul=1.0):
+        self.call("segk_scatter_f32", _p(src), _p(cmap), _p(dst), src.numel(), float(mul), _stream())
+        return dst
+
     def channel_copy(self, src, coff_src, dst, coff_dst, c, mask=None, accumulate=False):
         rows = src.numel() // src.shape[-1]
         self._w(4.0 * rows * c, "byte")
