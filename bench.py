@@ -152,6 +152,9 @@ def run_gpu(args):
     torch.cuda.set_device(dev)
     B = args.batch
     steps, warmup = args.steps, max(args.warmup, 3)
+    global H, W
+    if args.res:
+        H, W = (int(v) for v in args.res.lower().split("x"))
 
     # synthetic KITTI-road-shaped batch (raw 0..255 u8 pixels, class-id labels), per rank
     gen = torch.Generator().manual_seed(1000 + rank)
@@ -163,8 +166,8 @@ def run_gpu(args):
         from semanticsegmentation_tensorflow_b200.densenet import FCDenseNet, fcdensenet_flops_per_image
         net = FCDenseNet(dev_x, KEEP_PROB, NCLS, seed=1234, world_size=world, dropout_seed=42 + rank)
         train_gflop = fcdensenet_flops_per_image(net.nodes, net.ch, H, W)[1] / 1e9
-        workload = f"FCDenseNet (FCDenseNet.py:83-163, 130 conv layers) 2-class bf16 training (fwd+loss+bwd+Adam), batch {B} per GPU, 160x576x3 (BASELINE configs[4] at the configs[1] resolution)"
-        metric = "train images/sec FCDenseNet 160x576"
+        workload = f"FCDenseNet (FCDenseNet.py:83-163, 130 conv layers) 2-class bf16 training (fwd+loss+bwd+Adam), batch {B} per GPU, {H}x{W}x3 (BASELINE configs[4])"
+        metric = f"train images/sec FCDenseNet {H}x{W}"
     elif args.model in ("unet", "segnet"):
         from semanticsegmentation_tensorflow_b200.graph import SegNet, UNet, graph_flops_per_image, segnet_nodes, unet_nodes
         build, nodes = (UNet, unet_nodes) if args.model == "unet" else (SegNet, segnet_nodes)
@@ -569,6 +572,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
+    ap.add_argument("--res", default=None, help="HxW of the synthetic images for the secondary models (default 160x576), e.g. 384x1248")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the bounded U-Net / inference runs after the headline regions")
     ap.add_argument("--layers-out", default=None, help="write the per-call (per-layer) timing table here")

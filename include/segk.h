@@ -353,6 +353,8 @@ int segk_momentum_step(segk_ctx* ctx, float* p, float* a, const float* g, int64_
  *   out = clip8((2^21 + sum_i in[i] * k[i]) >> 22)
  * with PIL's own coefficient tables (int32 [out_size][ksize]) and bounds (int32 [out_size][2] =
  * first tap, tap count), computed on the host (pipeline.py: pil_bilinear_coeffs).  Bit-exact with PIL.
+ * C = 1, 3 or 4; C = 4 is RGBA (the reference's "merge" PNGs, FCN.py:225,312) with PIL's premultiplied-alpha
+ * resize: RGBA -> RGBa before the horizontal pass, RGBa -> RGBA after the vertical one.
  * Horizontal pass: src u8 [H][W][C] cropped to [y0,y0+crop_h) x [x0,x0+crop_w) (crop_image,
  * FCN.py:176-182), optionally flipped horizontally (flip_image, :184-185) -> dst u8 [crop_h][out_w][C]. */
 int segk_resize_h_u8(segk_ctx* ctx, const uint8_t* src, uint8_t* dst, const int* coeffs,

@@ -21,6 +21,14 @@ __device__ __forceinline__ int clip8(long long v) {
   return v < 0 ? 0 : (v > 255 ? 255 : (int)v);
 }
 
+// C == 4 is PIL's RGBA (the reference's 4-channel "merge" PNGs, FCN.py:225,312): Image.resize converts to
+// premultiplied alpha (RGBA -> RGBa: c' = MULDIV255(c, a)) before filtering and back afterwards
+// (RGBa -> RGBA: c = min(255, 255 c' / a) unless a is 0 or 255) -- restated here bit for bit.
+__device__ __forceinline__ int muldiv255(int a, int b) {
+  const int t = a * b + 128;
+  return ((t >> 8) + t) >> 8;
+}
+
 // horizontal pass over the crop [y0, y0+ch) x [x0, x0+cw) of src [H][W][C]: dst [ch][ow][C]
 __global__ void __launch_bounds__(kThreads) resize_h_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                             const int* __restrict__ kk, const int* __restrict__ bounds,
@@ -37,7 +45,9 @@ __global__ void __launch_bounds__(kThreads) resize_h_kernel(const uint8_t* __res
       for (int x = 0; x < n; ++x) {
         const int xi = xmin + x;                                   // position inside the (possibly flipped) crop
         const int xs = x0 + (flip ? (cw - 1 - xi) : xi);
-        ss += (long long)row[(int64_t)xs * C + c] * k[x];
+        int v = row[(int64_t)xs * C + c];
+        if (C == 4 && c < 3) v = muldiv255(v, row[(int64_t)xs * C + 3]);
+        ss += (long long)v * k[x];
       }
       dst[((int64_t)y * ow + xx) * C + c] = (uint8_t)clip8(ss);
     }
@@ -61,6 +71,12 @@ __global__ void __launch_bounds__(kThreads) resize_v_kernel(const uint8_t* __res
       long long ss = 1ll << (kPrec - 1);
       for (int y = 0; y < n; ++y) ss += (long long)tmp[((int64_t)(ymin + y) * ow + xx) * C + c] * k[y];
       v[c] = clip8(ss);
+    }
+    if (C == 4 && v[3] != 0 && v[3] != 255) {
+      for (int c = 0; c < 3; ++c) {
+        const int u = (255 * v[c]) / v[3];
+        v[c] = u > 255 ? 255 : u;
+      }
     }
     if (mode == 2) {
       out[i] = (C >= 3 && v[0] == 255 && v[1] == 0 && v[2] == 0) ? 0 : 1;
@@ -87,7 +103,7 @@ int segk_resize_h_u8(segk_ctx* ctx, const uint8_t* src, uint8_t* dst, const int*
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, src && dst && coeffs && bounds && ksize > 0 && crop_w > 0 && crop_h > 0 && out_w > 0,
                "resize_h: bad args");
-  SEGK_REQUIRE(ctx, C == 1 || C == 3, "resize_h: C must be 1 or 3 (PIL premultiplies alpha for RGBA; unsupported)");
+  SEGK_REQUIRE(ctx, C == 1 || C == 3 || C == 4, "resize_h: C must be 1, 3 or 4 (4 = RGBA with PIL's premultiplied-alpha resize)");
   resize_h_kernel<<<pgrid(ctx, (int64_t)crop_h * out_w), kThreads, 0, (cudaStream_t)stream>>>(
       src, dst, coeffs, bounds, ksize, W, C, x0, y0, crop_w, crop_h, out_w, flip);
   SEGK_LAUNCHED(ctx, "resize_h");
@@ -98,7 +114,7 @@ int segk_resize_v_u8(segk_ctx* ctx, const uint8_t* tmp, uint8_t* out, const int*
                      int C, int out_w, int out_h, int mode, double contrast, double brightness, void* stream) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, tmp && out && coeffs && bounds && ksize > 0 && out_w > 0 && out_h > 0, "resize_v: bad args");
-  SEGK_REQUIRE(ctx, (C == 1 || C == 3) && mode >= 0 && mode <= 2, "resize_v: C must be 1 or 3, mode 0..2");
+  SEGK_REQUIRE(ctx, (C == 1 || C == 3 || C == 4) && mode >= 0 && mode <= 2, "resize_v: C must be 1, 3 or 4, mode 0..2");
   resize_v_kernel<<<pgrid(ctx, (int64_t)out_h * out_w), kThreads, 0, (cudaStream_t)stream>>>(
       tmp, out, coeffs, bounds, ksize, C, out_w, out_h, mode, contrast, brightness);
   SEGK_LAUNCHED(ctx, "resize_v");

@@ -325,11 +325,24 @@ class FCDenseNet(_Feeds):
                 gw_max = max(gw_max, int(np.prod(shape)))
                 if n.inputs[0] != "input":
                     self.cmap_dev[n.name] = torch.as_tensor(lay[n.inputs[0]].cmap).to(dev)
-            elif n.kind == "bnrelu":
-                L = lay[n.inputs[0]]
-                self.cmap_dev[n.name] = torch.as_tensor(L.cmap).to(dev)
-                for d in (self.scale_p, self.shift_p, self.dscale_p, self.dshift_p):
-                    d[n.name] = torch.zeros(L.cp, dtype=torch.float32, device=dev)
+        # BN parameters of ALL layers live in four flat physical buffers; one global map per buffer points into the
+        # variable arena (logical gamma / beta), so a step needs two gathers and two scatters, not four per layer
+        bns = [n for n in nodes if n.kind == "bnrelu"]
+        total_p = sum(lay[n.inputs[0]].cp for n in bns)
+        flat = {k: torch.zeros(total_p, dtype=torch.float32, device=dev) for k in ("scale", "shift", "dscale", "dshift")}
+        gmap, bmap = np.full(total_p, -1, np.int32), np.full(total_p, -1, np.int32)
+        o = 0
+        for n in bns:
+            L = lay[n.inputs[0]]
+            go, bo = V.slots[f"{n.bn_scope}/gamma"].offset, V.slots[f"{n.bn_scope}/beta"].offset
+            m = L.cmap >= 0
+            gmap[o:o + L.cp][m] = go + L.cmap[m]
+            bmap[o:o + L.cp][m] = bo + L.cmap[m]
+            self.scale_p[n.name], self.shift_p[n.name] = flat["scale"][o:o + L.cp], flat["shift"][o:o + L.cp]
+            self.dscale_p[n.name], self.dshift_p[n.name] = flat["dscale"][o:o + L.cp], flat["dshift"][o:o + L.cp]
+            o += L.cp
+        self.bn_flat = flat
+        self.bn_gmap, self.bn_bmap = torch.as_tensor(gmap).to(dev), torch.as_tensor(bmap).to(dev)
         self.gw_scratch = torch.empty(gw_max, dtype=torch.float32, device=dev)
         self.bn_ws = self.ops.bn_act_bwd_workspace(max(l.cp for l in lay.values()), dev)
         self.logits = self.act[last]
@@ -393,6 +406,9 @@ class FCDenseNet(_Feeds):
     # ---- parameters: logical -> physical -> bf16 kernel layouts -----------------------------------------
     def _repack(self, ops, only=None):
         V = self.vars
+        # scale = gamma / sqrt(1 + eps), shift = beta, for every BN layer at once (physical order, pads 0)
+        ops.gather_f32(V.p, self.bn_gmap, self.bn_flat["scale"], mul=BN_SCALE)
+        ops.gather_f32(V.p, self.bn_bmap, self.bn_flat["shift"])
         for n in self.nodes:
             if n.kind in ("conv", "deconv"):
                 if only is not None and n.name not in only:
@@ -410,12 +426,6 @@ class FCDenseNet(_Feeds):
                 else:                          # [k,k,Cout,Cin]: rows = Cout (padded), cols = Cin (mapped)
                     ops.remap_weights(w, weff, amap=None, bmap=cm, to_phys=True)
                     V.wk[n.name], V.wd[n.name] = ops.pack_deconv_weights(weff, n.stride, V.wk.get(n.name), V.wd.get(n.name))
-            elif n.kind == "bnrelu":
-                if only is not None and n.bn_scope not in only and n.name not in only:
-                    continue
-                cm = self.cmap_dev[n.name]
-                ops.gather_f32(V.param(f"{n.bn_scope}/gamma"), cm, self.scale_p[n.name], mul=BN_SCALE)
-                ops.gather_f32(V.param(f"{n.bn_scope}/beta"), cm, self.shift_p[n.name])
 
     # ---- forward ------------------------------------------------------------------------------------
     def _dropout_args(self, n, idx):
@@ -561,6 +571,7 @@ class FCDenseNet(_Feeds):
 
         last = self.nodes[-1].name
         has.add(last)
+        done = []
         for idx in range(len(self.nodes) - 1, -1, -1):
             n = self.nodes[idx]
             if n.kind == "concat":
@@ -583,9 +594,6 @@ class FCDenseNet(_Feeds):
                     acc = True
                 ops.bn_act_bwd(dy, self.act[n.name], xs, dx, c, self.scale_p[n.name], self.dscale_p[n.name],
                                self.dshift_p[n.name], self.bn_ws, relu=n.relu, accumulate=acc)
-                cm = self.cmap_dev[n.name]
-                ops.scatter_f32(self.dscale_p[n.name], cm, V.grad(f"{n.bn_scope}/gamma"), mul=BN_SCALE)
-                ops.scatter_f32(self.dshift_p[n.name], cm, V.grad(f"{n.bn_scope}/beta"))
                 continue
             if n.kind == "avgpool":
                 if n.name in self.member:
@@ -634,8 +642,13 @@ class FCDenseNet(_Feeds):
                     ops.remap_weights(gw, gwp, amap=cm, bmap=None, to_phys=False)
                     dx, _, acc = into(src)
                     ops.conv2d_dgrad(dz, V.wd[n.name], dx, n.k, n.k, residual=dx if acc else None)
-            if after_layer is not None:
-                after_layer(n.name)
+            done.append(n.name)
+        # d gamma = d scale / sqrt(1 + eps), d beta = d shift: all BN layers at once, into the gradient arena
+        ops.scatter_f32(self.bn_flat["dscale"], self.bn_gmap, V.g, mul=BN_SCALE)
+        ops.scatter_f32(self.bn_flat["dshift"], self.bn_bmap, V.g)
+        if after_layer is not None:          # (data parallel: the BN gradients interleave with the conv weights in the
+            for name in done:                #  arena, so the gradient buckets are released once everything is written)
+                after_layer(name)
 
 
 def fcdensenet_flops_per_image(nodes, ch, h, w):

@@ -8,7 +8,8 @@ and for each the ground-truth image resized the same way and colour-matched to c
 
 `scipy.misc.imresize` is PIL's `Image.resize(BILINEAR)`; its coefficient tables are restated here
 (host, double precision, as PIL's precompute_coeffs / normalize_coeffs_8bpc) and the kernels apply
-them in integer arithmetic, so results are bit-exact with PIL (tests pin this against PIL itself)."""
+them in integer arithmetic, so results are bit-exact with PIL (tests pin this against PIL itself), including
+PIL's premultiplied-alpha handling of 4-channel (RGBA) images.  PNG inflate stays on the host."""
 from __future__ import annotations
 
 import math
@@ -98,10 +99,16 @@ class GpuBatcher:
         return x1, y1, nw, nh
 
     def batch(self, images, gt_images, params=None):
-        """images / gt_images: lists of decoded u8 [H,W,3] arrays or tensors.  `params` (optional) pins the
-        random draws per image: dicts with crop=(x0,y0,w,h), contrast, brightness — for parity tests."""
+        """images: decoded u8 [H,W,3] or [H,W,4] arrays / tensors (4 = the RGBA "merge" PNGs the reference trains on,
+        FCN.py:225,257,312: resized with PIL's premultiplied-alpha semantics); gt_images: u8 [H,W,3].  `params`
+        (optional) pins the random draws per image: dicts with crop=(x0,y0,w,h), contrast, brightness."""
         n = len(images)
-        out_x = torch.empty((3 * n, self.oh, self.ow, 3), dtype=torch.uint8, device=self.device)
+        chans = {int(torch.as_tensor(im).shape[2]) for im in images}
+        if len(chans) != 1 or next(iter(chans)) not in (3, 4):
+            raise ValueError(f"images must all have 3 or all have 4 channels (got {sorted(chans)})")
+        if any(torch.as_tensor(g).shape[2] != 3 for g in gt_images):
+            raise ValueError("ground-truth images must be RGB (FCN.py:196: compared against [255, 0, 0])")
+        out_x = torch.empty((3 * n, self.oh, self.ow, next(iter(chans))), dtype=torch.uint8, device=self.device)
         out_y = torch.empty((3 * n, self.oh, self.ow), dtype=torch.uint8, device=self.device)
         for i, (im, gt) in enumerate(zip(images, gt_images)):
             im = torch.as_tensor(im).to(self.device, non_blocking=True).contiguous()

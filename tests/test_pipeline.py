@@ -43,19 +43,45 @@ def _kitti_like(rng, h=375, w=1242):
     return img, gt
 
 
+def test_rgba_resize_restatement_matches_pil():
+    """PIL resizes RGBA through premultiplied alpha (RGBA -> RGBa, filter, RGBa -> RGBA); the integer formulas the
+    kernels use (csrc/pipeline.cu) restated in NumPy and pinned against PIL itself."""
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, (37, 51, 4), dtype=np.uint8)
+    a[:5, :5, 3] = 0
+    a[5:10, :, 3] = 255
+    al = a[..., 3:4].astype(np.int64)
+    t = a[..., :3].astype(np.int64) * al + 128
+    pm = np.concatenate([((t >> 8) + t) >> 8, al], -1).astype(np.uint8)
+    from PIL import Image
+    assert np.array_equal(pm, np.array(Image.fromarray(a, "RGBA").convert("RGBa")))
+    r = _numpy_resize(pm, 16, 24).astype(np.int64)
+    ra = r[..., 3:4]
+    rgb = np.where((ra == 0) | (ra == 255), r[..., :3], np.minimum(255, (255 * r[..., :3]) // np.where(ra == 0, 1, ra)))
+    got = np.concatenate([rgb, ra], -1).astype(np.uint8)
+    assert np.array_equal(got, PO.imresize(a, (16, 24)))
+
+
 @pytest.mark.gpu
-def test_gpu_batcher_bit_exact_vs_reference_pipeline(cuda_device):
+@pytest.mark.parametrize("channels", [3, 4])
+def test_gpu_batcher_bit_exact_vs_reference_pipeline(cuda_device, channels):
     from semanticsegmentation_tensorflow_b200.pipeline import GpuBatcher
     rng = np.random.default_rng(1)
     imgs, gts, params = [], [], []
     for i in range(2):
         img, gt = _kitti_like(rng)
+        if channels == 4:      # the reference's "merge" PNGs: RGB + a fourth (LiDAR) channel that PIL treats as alpha
+            alpha = rng.integers(0, 256, img.shape[:2] + (1,), dtype=np.uint8)
+            alpha[:40] = 255
+            alpha[40:60] = 0
+            img = np.concatenate([img, alpha], axis=2)
         imgs.append(img); gts.append(gt)
         params.append({"crop": (17 + i, 9, 1180 + i, int((1180 + i) / 3.3)), "contrast": 0.93 + 0.1 * i, "brightness": -20 + 35 * i})
     gb = GpuBatcher((160, 576), cuda_device)
     x, y = gb.batch(imgs, gts, params)
     torch.cuda.synchronize()
     x, y = x.cpu().numpy(), y.cpu().numpy()
+    assert x.shape == (6, 160, 576, channels)
     for i in range(2):
         views, labels = PO.three_views(imgs[i], gts[i], (160, 576), params[i]["crop"], params[i]["contrast"], params[i]["brightness"])
         for v in range(3):
