@@ -261,6 +261,27 @@ int segk_gather_f32(segk_ctx* ctx, const float* src, const int* map, float* dst,
                     void* stream);
 int segk_scatter_f32(segk_ctx* ctx, const float* src, const int* map, float* dst, int n, float mul, void* stream);
 
+/* ---- remaining op families of Network/utils/utils.py -----------------------------------------
+ * Atrous_Conv2D_Layer (utils.py:210-231: tf.nn.atrous_conv2d(x, W, rate, SAME)) on the same tcgen05 implicit GEMM:
+ * the taps of the tap table sit `rate` pixels apart; same operands / layouts / epilogue as segk_conv2d_*. */
+int segk_atrous_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* bias, const void* residual,
+                           void* y, int N, int H, int W, int Cin, int Cout, int kh, int kw, int rate,
+                           unsigned flags, void* stream);
+int segk_atrous_conv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask,
+                             const void* residual, void* dx, float* dx_colsum, float scale, int N, int H, int W,
+                             int Cin, int Cout, int kh, int kw, int rate, void* stream);
+int segk_atrous_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin,
+                             int Cout, int kh, int kw, int rate, int accumulate, void* stream);
+/* Resize_Bilinear (utils.py:329-330: tf.image.resize_bilinear(x, size, align_corners=True)) x [N,H,W,C] -> y [N,OH,OW,C]
+ * bf16, fp32 interpolation in TF's evaluation order; its gradient in gather form (deterministic). */
+int segk_resize_bilinear_fwd(segk_ctx* ctx, const void* x, void* y, int N, int H, int W, int OH, int OW, int C,
+                             void* stream);
+int segk_resize_bilinear_bwd(segk_ctx* ctx, const void* dy, void* dx, int N, int H, int W, int OH, int OW, int C,
+                             void* stream);
+/* Global_Avg_Pool (utils.py:312-313: tflearn global_avg_pool = mean over H, W): x [N,H,W,C] -> y [N,C]; gradient dx = dy / (H W) */
+int segk_global_avgpool_fwd(segk_ctx* ctx, const void* x, void* y, int N, int H, int W, int C, void* stream);
+int segk_global_avgpool_bwd(segk_ctx* ctx, const void* dy, void* dx, int N, int H, int W, int C, void* stream);
+
 /* Concat (utils.py:332) and its gradient: dst[r][coff_dst + c] (=, or += when accumulate)
  * src[r][coff_src + c] for c < C, zeroed where mask[r][c] <= 0 (mask dense [rows][C] or NULL =
  * the fused ReluGrad of the producer).  bf16, all channel counts multiples of 8. */

@@ -56,6 +56,30 @@ def conv2d_transpose_same(x: torch.Tensor, w: torch.Tensor, out_hw, stride: int)
     return y.permute(0, 2, 3, 1).contiguous()
 
 
+def atrous_conv2d_same(x: torch.Tensor, w: torch.Tensor, rate: int) -> torch.Tensor:
+    """tf.nn.atrous_conv2d(x, W[kh,kw,Cin,Cout], rate, padding='SAME')  (utils.py:210-231): the filter taps sit `rate`
+    pixels apart; effective size k + (k-1)(rate-1), odd for odd k, so SAME pads rate*(k//2) on every side."""
+    kh, kw = w.shape[0], w.shape[1]
+    y = F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), dilation=rate, padding=(rate * (kh // 2), rate * (kw // 2)))
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def resize_bilinear_align_corners(x: torch.Tensor, size) -> torch.Tensor:
+    """tf.image.resize_bilinear(x, size, align_corners=True)  (utils.py:329-330): src = dst * (in-1)/(out-1)."""
+    y = F.interpolate(x.permute(0, 3, 1, 2), size=tuple(size), mode="bilinear", align_corners=True)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def global_avg_pool(x: torch.Tensor) -> torch.Tensor:
+    """tflearn global_avg_pool (utils.py:312-313): reduce_mean over H and W -> [N, C]."""
+    return x.mean(dim=(1, 2))
+
+
+def avg_pool_2x2(x: torch.Tensor) -> torch.Tensor:
+    """tf.nn.avg_pool(ksize 2x2, stride 2, 'VALID')  (utils.py:309)."""
+    return F.avg_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).contiguous()
+
+
 def bias_add(x: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """tf.nn.bias_add (FCN.py:107,132,157)."""
     return x + b

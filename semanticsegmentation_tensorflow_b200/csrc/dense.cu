@@ -218,6 +218,152 @@ __global__ void __launch_bounds__(kThreads) scatter_f32_kernel(const float* __re
   if (i < n && map[i] >= 0) dst[map[i]] = src[i] * mul;
 }
 
+// ---------------------------------------------------------------------------------------
+// Remaining op families of Network/utils/utils.py
+// ---------------------------------------------------------------------------------------
+// Resize_Bilinear (utils.py:329-330: tf.image.resize_bilinear(x, size, align_corners=True)): src = dst * (in-1)/(out-1);
+// top = tl + (tr - tl) * fx; bottom = bl + (br - bl) * fx; out = top + (bottom - top) * fy   (TF's evaluation order, fp32)
+__device__ __forceinline__ void bilinear_src(int o, float scale, int in, int& i0, int& i1, float& f) {
+  const float s = (float)o * scale;
+  i0 = (int)floorf(s);
+  i1 = i0 + 1 < in ? i0 + 1 : in - 1;
+  f = s - (float)i0;
+}
+
+__global__ void __launch_bounds__(kThreads) resize_bilinear_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H,
+                                                                       int W, int OH, int OW, int C8, float sy, float sx) {
+  const int64_t total = (int64_t)N * OH * OW * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % C8);
+    int64_t p = i / C8;
+    const int ox = (int)(p % OW);
+    p /= OW;
+    const int oy = (int)(p % OH);
+    const int n = (int)(p / OH);
+    int y0, y1, x0, x1;
+    float fy, fx;
+    bilinear_src(oy, sy, H, y0, y1, fy);
+    bilinear_src(ox, sx, W, x0, x1, fx);
+    const uint4* base = reinterpret_cast<const uint4*>(x) + (int64_t)n * H * W * C8 + g;
+    const uint4 tl = __ldg(base + ((int64_t)y0 * W + x0) * C8), tr = __ldg(base + ((int64_t)y0 * W + x1) * C8);
+    const uint4 bl = __ldg(base + ((int64_t)y1 * W + x0) * C8), br = __ldg(base + ((int64_t)y1 * W + x1) * C8);
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = unpack_bf16x2((&tl.x)[j]), b = unpack_bf16x2((&tr.x)[j]), c = unpack_bf16x2((&bl.x)[j]), d = unpack_bf16x2((&br.x)[j]);
+      const float t0 = a.x + (b.x - a.x) * fx, t1 = a.y + (b.y - a.y) * fx;
+      const float u0 = c.x + (d.x - c.x) * fx, u1 = c.y + (d.y - c.y) * fx;
+      o[j] = pack_bf16x2(t0 + (u0 - t0) * fy, t1 + (u1 - t1) * fy);
+    }
+    reinterpret_cast<uint4*>(y)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ResizeBilinearGrad in GATHER form (deterministic, no atomics): input pixel (iy, ix) collects dy from every output
+// whose bilinear footprint touches it.  Output o touches input i as its lower tap (weight 1 - f) when floor(o*s) == i and
+// as its upper tap (weight f) when min(floor(o*s) + 1, in - 1) == i.
+__device__ __forceinline__ float bilinear_weight(int o, float scale, int in, int i) {
+  int i0, i1;
+  float f;
+  bilinear_src(o, scale, in, i0, i1, f);
+  float w = 0.f;
+  if (i0 == i) w += 1.f - f;
+  if (i1 == i) w += f;
+  return w;
+}
+
+__global__ void __launch_bounds__(kThreads) resize_bilinear_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N,
+                                                                       int H, int W, int OH, int OW, int C8, float sy, float sx) {
+  const int64_t total = (int64_t)N * H * W * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % C8);
+    int64_t p = i / C8;
+    const int ix = (int)(p % W);
+    p /= W;
+    const int iy = (int)(p % H);
+    const int n = (int)(p / H);
+    // candidate outputs: o * s in (i - 1, i + 1)  (everything when s == 0, i.e. a single output row / column)
+    int oy0 = 0, oy1 = OH - 1, ox0 = 0, ox1 = OW - 1;
+    if (sy > 0.f) { oy0 = max(0, (int)floorf((iy - 1) / sy)); oy1 = min(OH - 1, (int)ceilf((iy + 1) / sy)); }
+    if (sx > 0.f) { ox0 = max(0, (int)floorf((ix - 1) / sx)); ox1 = min(OW - 1, (int)ceilf((ix + 1) / sx)); }
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int oy = oy0; oy <= oy1; ++oy) {
+      const float wy = bilinear_weight(oy, sy, H, iy);
+      if (wy == 0.f) continue;
+      for (int ox = ox0; ox <= ox1; ++ox) {
+        const float w = wy * bilinear_weight(ox, sx, W, ix);
+        if (w == 0.f) continue;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy) + (((int64_t)n * OH + oy) * OW + ox) * C8 + g);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2((&u.x)[j]);
+          acc[2 * j] += w * f.x;
+          acc[2 * j + 1] += w * f.y;
+        }
+      }
+    }
+    reinterpret_cast<uint4*>(dx)[i] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                                                 pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+// Global_Avg_Pool (utils.py:312-313: tflearn global_avg_pool = reduce_mean over H, W): block = 32 channel groups x 8 pixel lanes
+__global__ void __launch_bounds__(kThreads) global_avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int HW, int C8) {
+  __shared__ float sh[8][32][9];
+  const int gl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int g = blockIdx.x * 32 + gl, n = blockIdx.y;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  if (g < C8) {
+    const uint4* base = reinterpret_cast<const uint4*>(x) + (int64_t)n * HW * C8 + g;
+    for (int p = pl; p < HW; p += 8) {
+      const uint4 u = __ldg(base + (int64_t)p * C8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&u.x)[j]);
+        a[2 * j] += f.x; a[2 * j + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[pl][gl][j] = a[j];
+  __syncthreads();
+  if (pl == 0 && g < C8) {
+    const float inv = 1.f / (float)HW;
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      t[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t[j] += sh[k][gl][j];
+      t[j] *= inv;
+    }
+    reinterpret_cast<uint4*>(y)[(int64_t)n * C8 + g] =
+        make_uint4(pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7]));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) global_avgpool_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int HW,
+                                                                      int C8) {
+  const int64_t total = (int64_t)N * HW * C8;
+  const float inv = 1.f / (float)HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % C8);
+    const int n = (int)(i / ((int64_t)HW * C8));
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(dy) + (int64_t)n * C8 + g);
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2((&u.x)[j]);
+      o[j] = pack_bf16x2(f.x * inv, f.y * inv);
+    }
+    reinterpret_cast<uint4*>(dx)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -310,6 +456,43 @@ int segk_scatter_f32(segk_ctx* ctx, const float* src, const int* map, float* dst
   SEGK_REQUIRE(ctx, src && map && dst && n > 0, "scatter_f32: bad args");
   scatter_f32_kernel<<<ceil_div(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(src, map, dst, n, mul);
   SEGK_LAUNCHED(ctx, "scatter_f32");
+  return SEGK_OK;
+}
+
+int segk_resize_bilinear_fwd(segk_ctx* ctx, const void* x, void* y, int N, int H, int W, int OH, int OW, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && y && N > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && C % 8 == 0 && C > 0, "resize_bilinear_fwd: bad args (C %% 8 == 0)");
+  const float sy = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f, sx = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+  resize_bilinear_fwd_kernel<<<sgrid(ctx, (int64_t)N * OH * OW * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (bf16*)y, N, H, W, OH, OW, C / 8, sy, sx);
+  SEGK_LAUNCHED(ctx, "resize_bilinear_fwd");
+  return SEGK_OK;
+}
+
+int segk_resize_bilinear_bwd(segk_ctx* ctx, const void* dy, void* dx, int N, int H, int W, int OH, int OW, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, dy && dx && N > 0 && H > 0 && W > 0 && OH > 0 && OW > 0 && C % 8 == 0 && C > 0, "resize_bilinear_bwd: bad args (C %% 8 == 0)");
+  const float sy = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f, sx = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+  resize_bilinear_bwd_kernel<<<sgrid(ctx, (int64_t)N * H * W * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, (bf16*)dx, N, H, W, OH, OW, C / 8, sy, sx);
+  SEGK_LAUNCHED(ctx, "resize_bilinear_bwd");
+  return SEGK_OK;
+}
+
+int segk_global_avgpool_fwd(segk_ctx* ctx, const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && y && N > 0 && H > 0 && W > 0 && C % 8 == 0 && C > 0 && N <= 65535, "global_avgpool_fwd: bad args (C %% 8 == 0)");
+  global_avgpool_fwd_kernel<<<dim3(ceil_div(C / 8, 32), N), kThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, H * W, C / 8);
+  SEGK_LAUNCHED(ctx, "global_avgpool_fwd");
+  return SEGK_OK;
+}
+
+int segk_global_avgpool_bwd(segk_ctx* ctx, const void* dy, void* dx, int N, int H, int W, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, dy && dx && N > 0 && H > 0 && W > 0 && C % 8 == 0 && C > 0, "global_avgpool_bwd: bad args (C %% 8 == 0)");
+  global_avgpool_bwd_kernel<<<sgrid(ctx, (int64_t)N * H * W * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>((const bf16*)dy, (bf16*)dx, N,
+                                                                                                      H * W, C / 8);
+  SEGK_LAUNCHED(ctx, "global_avgpool_bwd");
   return SEGK_OK;
 }
 

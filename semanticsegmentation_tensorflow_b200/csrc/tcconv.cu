@@ -1648,11 +1648,12 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
   }
 }
 
-void conv_taps(TapTable& t, int kh, int kw) {
+// taps of a SAME conv; rate > 1: tf.nn.atrous_conv2d (utils.py:210-231) -- the taps simply sit `rate` pixels apart
+void conv_taps(TapTable& t, int kh, int kw, int rate = 1) {
   memset(&t, 0, sizeof(t));
   for (int i = 0; i < kh * kw; ++i) {
-    t.dy[i] = (int8_t)(i / kw - kh / 2);
-    t.dx[i] = (int8_t)(i % kw - kw / 2);
+    t.dy[i] = (int8_t)((i / kw - kh / 2) * rate);
+    t.dx[i] = (int8_t)((i % kw - kw / 2) * rate);
     t.map[i] = 0;
   }
 }
@@ -1660,7 +1661,7 @@ void conv_taps(TapTable& t, int kh, int kw) {
 // shared body of conv fwd and dgrad: y[N,H,W,Cn] = epilogue( sum_taps x[.. + tap][Ck] * wt[tap][Cn][Ck] )
 int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, const float* bias, const void* residual,
                const void* mask, float scale, int relu, int out_f32, void* y, int N, int H, int W, int Ck, int Cn,
-               int kh, int kw, void* stream, float* colsum_out = nullptr) {
+               int kh, int kw, void* stream, float* colsum_out = nullptr, int rate = 1) {
   SEGK_REQUIRE(ctx, x && wt && y, "%s: null pointer", what);
   SEGK_REQUIRE(ctx, N > 0 && H > 0 && W > 0, "%s: empty tensor", what);
   SEGK_REQUIRE(ctx, Ck % 64 == 0 && Cn % 64 == 0 && Ck > 0 && Cn > 0,
@@ -1671,7 +1672,8 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   SEGK_REQUIRE(ctx, (((uintptr_t)x | (uintptr_t)wt | (uintptr_t)y | (uintptr_t)residual | (uintptr_t)mask) & 15) == 0,
                "%s: pointers must be 16-byte aligned", what);
   SEGK_REQUIRE(ctx, !colsum_out || !out_f32, "%s: column sums need a bf16 output", what);
-  if (slab_applicable(ctx, N, H, W, Ck, Cn, kh, kw))
+  SEGK_REQUIRE(ctx, rate >= 1 && (kh / 2) * rate <= 127 && (kw / 2) * rate <= 127, "%s: dilation rate %d out of range", what, rate);
+  if (rate == 1 && slab_applicable(ctx, N, H, W, Ck, Cn, kh, kw))
     return conv_slab(ctx, what, x, wt, bias, residual, mask, scale, relu, out_f32, y, N, H, W, Ck, Cn, stream, colsum_out);
   const Box b = choose_box(N, H, W, kBlockM, false, 0, 0, kh, kw);
   SEGK_REQUIRE(ctx, b.rows > 0, "%s: no pixel box for %dx%dx%d", what, N, H, W);
@@ -1700,7 +1702,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   // order the tiles so that what is larger (weights vs activations) is what concurrent CTAs share
   p.m_fastest = ((int64_t)kh * kw * Cn > (int64_t)N * H * W) ? 1 : 0;
   TapTable taps;
-  conv_taps(taps, kh, kw);
+  conv_taps(taps, kh, kw, rate);
   // few output tiles but a long K walk (conv6 dgrad: 48 tiles x 3136 k-steps): split K across SMs
   const int tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
   const int force_ks = ctx->force_ksplit;
@@ -2193,17 +2195,18 @@ int segk_conv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void*
                     kw, stream, dx_colsum);
 }
 
-int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
-                      int kh, int kw, int accumulate, void* stream) {
+static int conv2d_wgrad_impl(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                             int kh, int kw, int accumulate, void* stream, int rate) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, x && dy && dw, "conv2d_wgrad: null pointer");
+  SEGK_REQUIRE(ctx, rate >= 1 && (kh / 2) * rate <= 127 && (kw / 2) * rate <= 127, "conv2d_wgrad: dilation rate %d out of range", rate);
   SEGK_REQUIRE(ctx, N > 0 && H > 0 && W > 0, "conv2d_wgrad: empty tensor");
   SEGK_REQUIRE(ctx, Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0,
                "conv2d_wgrad: tensor-core path needs channel counts that are multiples of 64 (got %d -> %d); no fallback",
                Cin, Cout);
   SEGK_REQUIRE(ctx, (kh & 1) && (kw & 1) && kh * kw <= kMaxTaps, "conv2d_wgrad: odd kernel sizes up to %d taps", kMaxTaps);
   SEGK_REQUIRE(ctx, (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) == 0, "conv2d_wgrad: 16-byte alignment");
-  {
+  if (rate == 1) {
     const int handled = segk_wslab_try(ctx, x, dy, dw, N, H, W, Cin, Cout, kh, kw, accumulate, stream);
     if (handled != 0) return handled < 0 ? handled : SEGK_OK;
   }
@@ -2257,9 +2260,9 @@ int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, i
   }
   SEGK_REQUIRE(ctx, p.direct, "conv2d_wgrad: %d splits of %zu weights exceed the 1 GiB partial-sum workspace", p.splits, n_dw);
   TapTable taps;
-  conv_taps(taps, kh, kw);
+  conv_taps(taps, kh, kw, rate);
   // (pixel box, tap) pairs that only see SAME padding carry no information: skip them when there are any
-  p.skip_oob = (active_taps_1d(W, b.bw, kw) * active_taps_1d(H, b.bh, kh) < (int64_t)p.tiles_w * p.tiles_h * kh * kw) ? 1 : 0;
+  p.skip_oob = (rate > 1 || active_taps_1d(W, b.bw, kw) * active_taps_1d(H, b.bh, kh) < (int64_t)p.tiles_w * p.tiles_h * kh * kw) ? 1 : 0;
   const int total = p.splits * p.n_rbp * p.n_tiles;
   const int grid = total < ctx->sm_count ? total : ctx->sm_count;
   switch (block_n) {
@@ -2270,6 +2273,33 @@ int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, i
   if (rc) return rc;
   if (partials) return segk_reduce_partials(ctx, (const float*)ctx->ws4, dw, n_dw, p.splits, accumulate, st);
   return SEGK_OK;
+}
+
+int segk_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                      int kh, int kw, int accumulate, void* stream) {
+  return conv2d_wgrad_impl(ctx, x, dy, dw, N, H, W, Cin, Cout, kh, kw, accumulate, stream, 1);
+}
+
+// Atrous_Conv2D_Layer (utils.py:210-231: tf.nn.atrous_conv2d(x, W, rate, SAME)): the same implicit GEMM with the taps
+// `rate` pixels apart; forward, Conv2DBackpropInput and Conv2DBackpropFilter.
+int segk_atrous_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* bias, const void* residual, void* y,
+                           int N, int H, int W, int Cin, int Cout, int kh, int kw, int rate, unsigned flags, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  return conv_igemm(ctx, "atrous_conv2d_fwd", x, wk, bias, residual, nullptr, 1.f, (flags & SEGK_EPI_RELU) ? 1 : 0,
+                    (flags & SEGK_EPI_OUT_F32) ? 1 : 0, y, N, H, W, Cin, Cout, kh, kw, stream, nullptr, rate);
+}
+
+int segk_atrous_conv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, const void* residual,
+                             void* dx, float* dx_colsum, float scale, int N, int H, int W, int Cin, int Cout, int kh, int kw,
+                             int rate, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  return conv_igemm(ctx, "atrous_conv2d_dgrad", dy, wd, nullptr, residual, relu_mask, scale, 0, 0, dx, N, H, W, Cout, Cin, kh,
+                    kw, stream, dx_colsum, rate);
+}
+
+int segk_atrous_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                             int kh, int kw, int rate, int accumulate, void* stream) {
+  return conv2d_wgrad_impl(ctx, x, dy, dw, N, H, W, Cin, Cout, kh, kw, accumulate, stream, rate);
 }
 
 }  // extern "C"

@@ -415,6 +415,51 @@ class Ops:
         self.call("segk_scatter_f32", _p(src), _p(cmap), _p(dst), src.numel(), float(mul), _stream())
         return dst
 
+    # ---- remaining op families of utils.py: atrous conv, align-corners bilinear resize, global average pool ----
+    def atrous_conv2d_fwd(self, x, wk, bias, y, k, rate, relu=False, residual=None):
+        n, h, w, cin = x.shape
+        cout = y.shape[3]
+        flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if y.dtype == torch.float32 else 0)
+        self._w(2.0 * n * h * w * k * k * cin * cout, "flop")
+        self.call("segk_atrous_conv2d_fwd", _p(x), _p(wk), _p(bias), _p(residual), _p(y), n, h, w, cin, cout, k, k, int(rate),
+                  flags, _stream())
+        return y
+
+    def atrous_conv2d_dgrad(self, dy, wd, dx, k, rate, relu_mask=None, residual=None, scale=1.0, colsum=None):
+        n, h, w, cout = dy.shape
+        cin = dx.shape[3]
+        self._w(2.0 * n * h * w * k * k * cin * cout, "flop")
+        self.call("segk_atrous_conv2d_dgrad", _p(dy), _p(wd), _p(relu_mask), _p(residual), _p(dx), _p(colsum), float(scale), n, h,
+                  w, cin, cout, k, k, int(rate), _stream())
+        return dx
+
+    def atrous_conv2d_wgrad(self, x, dy, dw, k, rate, accumulate=False):
+        n, h, w, cin = x.shape
+        cout = dy.shape[3]
+        self._w(2.0 * n * h * w * k * k * cin * cout, "flop")
+        self.call("segk_atrous_conv2d_wgrad", _p(x), _p(dy), _p(dw), n, h, w, cin, cout, k, k, int(rate), int(accumulate), _stream())
+        return dw
+
+    def resize_bilinear_fwd(self, x, y):
+        n, h, w, c = x.shape
+        self.call("segk_resize_bilinear_fwd", _p(x), _p(y), n, h, w, y.shape[1], y.shape[2], c, _stream())
+        return y
+
+    def resize_bilinear_bwd(self, dy, dx):
+        n, h, w, c = dx.shape
+        self.call("segk_resize_bilinear_bwd", _p(dy), _p(dx), n, h, w, dy.shape[1], dy.shape[2], c, _stream())
+        return dx
+
+    def global_avgpool_fwd(self, x, y):
+        n, h, w, c = x.shape
+        self.call("segk_global_avgpool_fwd", _p(x), _p(y), n, h, w, c, _stream())
+        return y
+
+    def global_avgpool_bwd(self, dy, dx):
+        n, h, w, c = dx.shape
+        self.call("segk_global_avgpool_bwd", _p(dy), _p(dx), n, h, w, c, _stream())
+        return dx
+
     def channel_copy(self, src, coff_src, dst, coff_dst, c, mask=None, accumulate=False):
         rows = src.numel() // src.shape[-1]
         self._w(4.0 * rows * c, "byte")

@@ -1,0 +1,98 @@
+"""GPU parity of the remaining op families of Network/utils/utils.py against oracle/tf_ops.py:
+Atrous_Conv2D_Layer (:210-231) forward / dgrad / wgrad on the tcgen05 implicit GEMM, Resize_Bilinear with
+align_corners=True (:329-330) forward / backward, Global_Avg_Pool (:312-313), Avg_Pooling (:309)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tf_ops as T
+from tests.gpu_util import assert_close, bf16_grid, dev_bf16, dev_f32, host
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_device):
+    from semanticsegmentation_tensorflow_b200.ops import Ops
+    return Ops(cuda_device)
+
+
+@pytest.mark.parametrize("case", [(2, 20, 24, 64, 128, 3, 2), (1, 12, 36, 128, 64, 3, 4), (2, 17, 19, 64, 64, 3, 6),
+                                  (1, 10, 36, 256, 256, 3, 12)])
+def test_atrous_conv_fwd_dgrad_wgrad(ops, cuda_device, case):
+    n, h, w, ci, co, k, rate = case
+    rng = np.random.default_rng(50)
+    x = bf16_grid(rng.standard_normal((n, h, w, ci)))
+    wt = bf16_grid(rng.standard_normal((k, k, ci, co)) / np.sqrt(k * k * ci))
+    b = (rng.standard_normal(co) * 0.1).astype(np.float32)
+    dy = bf16_grid(rng.standard_normal((n, h, w, co)))
+    act = bf16_grid(rng.standard_normal((n, h, w, ci)))
+    xt, wtt = torch.tensor(x, requires_grad=True), torch.tensor(wt, requires_grad=True)
+    z = T.atrous_conv2d_same(xt, wtt, rate)
+    y_ref = T.relu(T.bias_add(z, torch.tensor(b))).detach().numpy()
+    z.backward(torch.tensor(dy))
+    wk, wd = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    xd, dyd = dev_bf16(x, cuda_device), dev_bf16(dy, cuda_device)
+    y = torch.full((n, h, w, co), 7.0, dtype=torch.bfloat16, device=cuda_device)
+    ops.atrous_conv2d_fwd(xd, wk, dev_f32(b, cuda_device), y, k, rate, relu=True)
+    dx = torch.full((n, h, w, ci), 7.0, dtype=torch.bfloat16, device=cuda_device)
+    ops.atrous_conv2d_dgrad(dyd, wd, dx, k, rate, relu_mask=dev_bf16(act, cuda_device))
+    dw = torch.full((k, k, ci, co), 7.0, dtype=torch.float32, device=cuda_device)
+    ops.atrous_conv2d_wgrad(xd, dyd, dw, k, rate)
+    torch.cuda.synchronize()
+    assert_close(host(y), y_ref, 1e-2, f"atrous fwd {case}")
+    assert_close(host(dx), xt.grad.numpy() * (act > 0), 1e-2, f"atrous dgrad {case}")
+    assert_close(host(dw), wtt.grad.numpy(), 2e-3, f"atrous wgrad {case}")
+
+
+@pytest.mark.parametrize("case", [(2, 5, 18, 64, 160, 576), (1, 20, 72, 32, 160, 576), (2, 7, 9, 8, 7, 9), (1, 12, 10, 16, 5, 1),
+                                  (1, 10, 36, 64, 1, 1)])
+def test_resize_bilinear_align_corners_fwd_bwd(ops, cuda_device, case):
+    n, h, w, c, oh, ow = case
+    rng = np.random.default_rng(51)
+    x = bf16_grid(rng.standard_normal((n, h, w, c)))
+    dy = bf16_grid(rng.standard_normal((n, oh, ow, c)))
+    xt = torch.tensor(x, requires_grad=True)
+    y_ref = T.resize_bilinear_align_corners(xt, (oh, ow))
+    y_ref.backward(torch.tensor(dy))
+    y = torch.empty((n, oh, ow, c), dtype=torch.bfloat16, device=cuda_device)
+    ops.resize_bilinear_fwd(dev_bf16(x, cuda_device), y)
+    dx = torch.full((n, h, w, c), 7.0, dtype=torch.bfloat16, device=cuda_device)
+    ops.resize_bilinear_bwd(dev_bf16(dy, cuda_device), dx)
+    torch.cuda.synchronize()
+    assert_close(host(y), y_ref.detach().numpy(), 1e-2, f"resize_bilinear fwd {case}")
+    assert_close(host(dx), xt.grad.numpy(), 1e-2, f"resize_bilinear bwd {case}")
+    # deterministic (gather form, no atomics)
+    dx2 = torch.empty_like(dx)
+    ops.resize_bilinear_bwd(dev_bf16(dy, cuda_device), dx2)
+    torch.cuda.synchronize()
+    assert torch.equal(dx, dx2)
+
+
+def test_global_and_2x2_average_pools(ops, cuda_device):
+    rng = np.random.default_rng(52)
+    n, h, w, c = 3, 10, 36, 520
+    x = bf16_grid(rng.standard_normal((n, h, w, c)))
+    xd = dev_bf16(x, cuda_device)
+    y = torch.empty((n, c), dtype=torch.bfloat16, device=cuda_device)
+    ops.global_avgpool_fwd(xd, y)
+    dyg = bf16_grid(rng.standard_normal((n, c)))
+    dx = torch.empty_like(xd)
+    ops.global_avgpool_bwd(dev_bf16(dyg, cuda_device), dx)
+    torch.cuda.synchronize()
+    assert_close(host(y), T.global_avg_pool(torch.tensor(x)).numpy(), 1e-2, "global avg pool")
+    assert_close(host(dx), np.broadcast_to(dyg[:, None, None, :] / (h * w), x.shape), 1e-2, "global avg pool grad")
+    # Avg_Pooling 2x2 on a channel prefix of a wider buffer (the strided view the dense blocks use)
+    ld, cu = 64, 40
+    xb = bf16_grid(rng.standard_normal((2, 8, 12, ld)))
+    yb = torch.zeros((2, 4, 6, ld), dtype=torch.bfloat16, device=cuda_device)
+    ops.avgpool_fwd(dev_bf16(xb, cuda_device), cu, yb)
+    torch.cuda.synchronize()
+    ref = bf16_grid(T.avg_pool_2x2(torch.tensor(xb[..., :cu])).numpy())
+    assert np.array_equal(host(yb)[..., :cu], ref) and float(yb[..., cu:].abs().max()) == 0.0
+    dyb = bf16_grid(rng.standard_normal((2, 4, 6, ld)))
+    dxb = torch.zeros((2, 8, 12, ld), dtype=torch.bfloat16, device=cuda_device)
+    ops.avgpool_bwd(dev_bf16(dyb, cuda_device), cu, dxb)
+    torch.cuda.synchronize()
+    up = np.repeat(np.repeat(dyb[..., :cu], 2, axis=1), 2, axis=2) * 0.25
+    assert np.array_equal(host(dxb)[..., :cu], bf16_grid(up)) and float(dxb[..., cu:].abs().max()) == 0.0

@@ -147,3 +147,33 @@ def test_paste_mask_restatement_matches_pil():
         im = Image.fromarray(img, mode="RGB" if c == 3 else "RGBA")
         im.paste(m, box=None, mask=m)                                              # FCN.py:209
         assert np.array_equal(T.paste_mask(img, prob), np.array(im))
+
+
+def test_atrous_conv_equals_conv_with_zero_inserted_filter():
+    """tf.nn.atrous_conv2d == conv2d with the filter up-sampled by inserting rate-1 zeros between taps (its definition)."""
+    rng = np.random.default_rng(20)
+    x = torch.tensor(rng.standard_normal((2, 9, 11, 3)).astype(np.float32))
+    w = torch.tensor(rng.standard_normal((3, 3, 3, 4)).astype(np.float32))
+    for rate in (1, 2, 3):
+        k = 3 + 2 * (rate - 1)
+        wz = torch.zeros((k, k, 3, 4))
+        wz[::rate, ::rate] = w
+        assert torch.allclose(T.atrous_conv2d_same(x, w, rate), T.conv2d_same(x, wz), atol=1e-5)
+
+
+def test_resize_bilinear_align_corners_against_the_formula():
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((1, 4, 5, 2)).astype(np.float32)
+    oh, ow = 7, 11
+    got = T.resize_bilinear_align_corners(torch.tensor(x), (oh, ow)).numpy()
+    ref = np.zeros((1, oh, ow, 2), np.float32)
+    for oy in range(oh):
+        sy = oy * (4 - 1) / (oh - 1); y0 = int(np.floor(sy)); y1 = min(y0 + 1, 3); fy = sy - y0
+        for ox in range(ow):
+            sx = ox * (5 - 1) / (ow - 1); x0 = int(np.floor(sx)); x1 = min(x0 + 1, 4); fx = sx - x0
+            top = x[0, y0, x0] + (x[0, y0, x1] - x[0, y0, x0]) * fx
+            bot = x[0, y1, x0] + (x[0, y1, x1] - x[0, y1, x0]) * fx
+            ref[0, oy, ox] = top + (bot - top) * fy
+    assert np.allclose(got, ref, atol=1e-5)
+    assert np.allclose(T.global_avg_pool(torch.tensor(x)).numpy(), x.mean(axis=(1, 2)), atol=1e-6)
+    assert np.allclose(T.avg_pool_2x2(torch.tensor(x[:, :4, :4])).numpy()[0, 0, 0], x[0, :2, :2].mean(axis=(0, 1)), atol=1e-6)
