@@ -365,6 +365,16 @@ int segk_confusion_matrix(segk_ctx* ctx, const uint8_t* gt, const uint8_t* pred,
 int segk_adam_step(segk_ctx* ctx, float* p, float* m, float* v, const float* g, int64_t n,
                    float lr_t, float beta1, float beta2, float eps, float grad_scale,
                    void* stream);
+/* The same update on `nranges` element ranges [offsets[i], offsets[i] + lengths[i]) of the arenas in one launch
+ * (offsets / lengths: HOST int64 arrays) -- the small variables between the conv weights of a gradient bucket. */
+int segk_adam_step_ranges(segk_ctx* ctx, float* p, float* m, float* v, const float* g, const int64_t* offsets,
+                          const int64_t* lengths, int nranges, float lr_t, float beta1, float beta2, float eps,
+                          float grad_scale, void* stream);
+/* The same update for ONE conv_layer weight tensor [kh,kw,Cin,Cout] (Cin, Cout multiples of 64) fused with
+ * segk_pack_conv_weights: the fresh parameters are written back and, from the same pass, as bf16 into wk / wd. */
+int segk_adam_pack_conv_weights(segk_ctx* ctx, float* p, float* m, float* v, const float* g, void* wk, void* wd,
+                                int kh, int kw, int Cin, int Cout, float lr_t, float beta1, float beta2, float eps,
+                                float grad_scale, void* stream);
 /* tf.train.MomentumOptimizer: a = mu a + g; p -= lr a (new) */
 int segk_momentum_step(segk_ctx* ctx, float* p, float* a, const float* g, int64_t n, float lr,
                        float mu, float grad_scale, void* stream);

@@ -508,6 +508,28 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, f
   }
 }
 
+// ApplyAdam on a LIST of arena ranges in one launch (the variables of a gradient bucket that are not conv weights of the
+// tensor-core layers -- those take adam_pack_blocked_kernel): blockIdx.y = range, grid-stride over its elements.
+constexpr int kMaxRanges = 64;
+struct AdamRanges {
+  int64_t off[kMaxRanges];
+  int64_t len[kMaxRanges];
+};
+__global__ void __launch_bounds__(kThreads) adam_ranges_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                               const float* __restrict__ g, const AdamRanges r, float lr_t, float b1,
+                                                               float b2, float eps, float gs) {
+  const int64_t o = r.off[blockIdx.y], n = r.len[blockIdx.y];
+  const float c1 = 1.f - b1, c2 = 1.f - b2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gj = g[o + i] * gs;
+    const float mj = m[o + i] + (gj - m[o + i]) * c1;
+    const float vj = v[o + i] + (gj * gj - v[o + i]) * c2;
+    m[o + i] = mj;
+    v[o + i] = vj;
+    p[o + i] -= lr_t * mj / (sqrtf(vj) + eps);
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) momentum_kernel(float* __restrict__ p,
                                                             float* __restrict__ a,
                                                             const float* __restrict__ g, int64_t n,
@@ -704,6 +726,67 @@ __global__ void __launch_bounds__(kThreads) pack_blocked_kernel(const float* __r
       for (int j = 0; j < 8; ++j) v[j] = tile[pc * 8 + j][r];
       *reinterpret_cast<uint4*>(dst + (int64_t)(b0 + r) * 64 + pc * 8) =
           make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+  }
+}
+
+// ApplyAdam (adam_kernel's arithmetic) and the bf16 repack of a conv layer's weights in ONE pass: a 64 x 64 tile of
+// p, m, v, g is read once, updated, written back, and its bf16 image goes to both kernel layouts (cp: k = B, tr: k = A,
+// as pack_blocked_kernel).  Saves the packer's second read of the fresh parameters (4 B/param) and one launch per layer.
+__global__ void __launch_bounds__(kThreads) adam_pack_blocked_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
+                                                                     const float* __restrict__ g, bf16* __restrict__ cp,
+                                                                     bf16* __restrict__ tr, int A, int B, int rev_cp, float lr_t,
+                                                                     float b1, float b2, float eps, float gs) {
+  __shared__ float tile[64][65];
+  const int t = blockIdx.z;
+  const int tc = rev_cp ? (int)gridDim.z - 1 - t : t;
+  const int a0 = blockIdx.y * 64, b0 = blockIdx.x * 64;
+  const int KCa = (int)gridDim.y, KCb = (int)gridDim.x;
+  const int64_t base = (int64_t)t * A * B;
+  const float c1 = 1.f - b1, c2 = 1.f - b2;
+  {
+    const int c4 = threadIdx.x & 15, r0 = threadIdx.x >> 4;      // A % 64 == 0 and B % 64 == 0: 16-byte accesses, no edges
+#pragma unroll
+    for (int r = r0; r < 64; r += 16) {
+      const int64_t o = base + (int64_t)(a0 + r) * B + b0 + c4 * 4;
+      float4 pp = *reinterpret_cast<const float4*>(p + o), mm = *reinterpret_cast<const float4*>(m + o);
+      float4 vv = *reinterpret_cast<const float4*>(v + o);
+      const float4 gg = __ldg(reinterpret_cast<const float4*>(g + o));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float gj = (&gg.x)[j] * gs;
+        const float mj = (&mm.x)[j] + (gj - (&mm.x)[j]) * c1;
+        const float vj = (&vv.x)[j] + (gj * gj - (&vv.x)[j]) * c2;
+        (&mm.x)[j] = mj;
+        (&vv.x)[j] = vj;
+        (&pp.x)[j] -= lr_t * mj / (sqrtf(vj) + eps);
+      }
+      *reinterpret_cast<float4*>(p + o) = pp;
+      *reinterpret_cast<float4*>(m + o) = mm;
+      *reinterpret_cast<float4*>(v + o) = vv;
+      tile[r][c4 * 4] = pp.x; tile[r][c4 * 4 + 1] = pp.y; tile[r][c4 * 4 + 2] = pp.z; tile[r][c4 * 4 + 3] = pp.w;
+    }
+  }
+  __syncthreads();
+  const int pc = threadIdx.x & 7, q0 = threadIdx.x >> 3;
+  if (cp) {
+    bf16* dst = cp + ((int64_t)tc * KCb + blockIdx.x) * A * 64;
+#pragma unroll
+    for (int r = q0; r < 64; r += 32) {
+      const float* s = &tile[r][pc * 8];
+      *reinterpret_cast<uint4*>(dst + (int64_t)(a0 + r) * 64 + pc * 8) =
+          make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]), pack_bf16x2(s[6], s[7]));
+    }
+  }
+  if (tr) {
+    bf16* dst = tr + ((int64_t)t * KCa + blockIdx.y) * B * 64;
+#pragma unroll
+    for (int r = q0; r < 64; r += 32) {
+      float vv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vv[j] = tile[pc * 8 + j][r];
+      *reinterpret_cast<uint4*>(dst + (int64_t)(b0 + r) * 64 + pc * 8) =
+          make_uint4(pack_bf16x2(vv[0], vv[1]), pack_bf16x2(vv[2], vv[3]), pack_bf16x2(vv[4], vv[5]), pack_bf16x2(vv[6], vv[7]));
     }
   }
 }
@@ -973,6 +1056,47 @@ int segk_pack_conv_weights(segk_ctx* ctx, const float* w, void* wk, void* wd, in
   SEGK_REQUIRE(ctx, grid.y <= 65535 && grid.z <= 65535, "pack_conv: dims too large");
   pack_blocked_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(w, (bf16*)wd, (bf16*)wk, Cin, Cout, 1);
   SEGK_LAUNCHED(ctx, "pack_conv_weights");
+  return SEGK_OK;
+}
+
+int segk_adam_step_ranges(segk_ctx* ctx, float* p, float* m, float* v, const float* g, const int64_t* offsets,
+                          const int64_t* lengths, int nranges, float lr_t, float beta1, float beta2, float eps, float grad_scale,
+                          void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, p && m && v && g && offsets && lengths && nranges > 0, "adam_ranges: bad args");
+  for (int r0 = 0; r0 < nranges; r0 += kMaxRanges) {
+    AdamRanges r;
+    memset(&r, 0, sizeof(r));
+    const int nr = nranges - r0 < kMaxRanges ? nranges - r0 : kMaxRanges;
+    int64_t longest = 0;
+    for (int i = 0; i < nr; ++i) {
+      SEGK_REQUIRE(ctx, offsets[r0 + i] >= 0 && lengths[r0 + i] >= 0, "adam_ranges: negative range");
+      r.off[i] = offsets[r0 + i];
+      r.len[i] = lengths[r0 + i];
+      if (r.len[i] > longest) longest = r.len[i];
+    }
+    int64_t gx = ceil_div64(longest, kThreads);
+    if (gx > 2 * ctx->sm_count) gx = 2 * ctx->sm_count;
+    if (gx < 1) gx = 1;
+    adam_ranges_kernel<<<dim3((unsigned)gx, nr), kThreads, 0, (cudaStream_t)stream>>>(p, m, v, g, r, lr_t, beta1, beta2, eps, grad_scale);
+    SEGK_LAUNCHED(ctx, "adam_ranges");
+  }
+  return SEGK_OK;
+}
+
+int segk_adam_pack_conv_weights(segk_ctx* ctx, float* p, float* m, float* v, const float* g, void* wk, void* wd, int kh,
+                                int kw, int Cin, int Cout, float lr_t, float beta1, float beta2, float eps, float grad_scale,
+                                void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, p && m && v && g && (wk || wd) && kh > 0 && kw > 0, "adam_pack_conv: bad args");
+  SEGK_REQUIRE(ctx, Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0, "adam_pack_conv: needs Cin, Cout multiples of 64 (got %d, %d)", Cin, Cout);
+  SEGK_REQUIRE(ctx, (((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)g | (uintptr_t)wk | (uintptr_t)wd) & 15) == 0,
+               "adam_pack_conv: 16-byte alignment");
+  dim3 grid(Cout / 64, Cin / 64, kh * kw);
+  SEGK_REQUIRE(ctx, grid.y <= 65535 && grid.z <= 65535, "adam_pack_conv: dims too large");
+  adam_pack_blocked_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(p, m, v, g, (bf16*)wd, (bf16*)wk, Cin, Cout, 1, lr_t, beta1,
+                                                                       beta2, eps, grad_scale);
+  SEGK_LAUNCHED(ctx, "adam_pack_conv_weights");
   return SEGK_OK;
 }
 

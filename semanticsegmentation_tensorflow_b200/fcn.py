@@ -77,6 +77,8 @@ class Variables:
             self.assign(values)
         self.wk = {}
         self.wd = {}
+        # conv layers whose Adam update and bf16 repack run as one kernel (AdamOptimizer.apply_and_repack)
+        self.fused_adam_layers = {l.name for l in self.layers if l.kind == "conv" and l.path == "tc"}
 
     def view(self, arena, name):
         s = self.slots[name]
@@ -588,6 +590,36 @@ class AdamOptimizer:
         net.ops.adam_step(V.p[lo:hi], V.m[lo:hi], V.v[lo:hi], V.g[lo:hi], lr_t, self.beta1, self.beta2, self.eps,
                           grad_scale)
 
+    def apply_and_repack(self, net, lo=0, hi=None, names=None, grad_scale=1.0):
+        """ApplyAdam on the arena slice [lo, hi) + the bf16 repack of its layers.  The conv weights of the tensor-core
+        layers (nearly all parameters) take ONE fused kernel each -- update and both kernel layouts from a single pass
+        over p, m, v, g --, every other variable of the slice one multi-range Adam launch, and only the remaining
+        layers are repacked separately."""
+        V = net.vars
+        hi = V.total if hi is None else hi
+        fused = getattr(V, "fused_adam_layers", None)
+        if not fused:
+            self.apply(net, lo, hi, grad_scale)
+            net.vars.repack(net.ops, names)
+            return
+        lr_t = P.adam_lr_t(self.lr, self.t, self.beta1, self.beta2)
+        ranges, rest = [], set()
+        for name, s in V.slots.items():
+            if not (lo <= s.offset < hi):
+                continue
+            layer = name.split("/")[0]
+            if name.endswith("/weights") and layer in fused:
+                net.ops.adam_pack_conv_weights(V.view(V.p, name), V.view(V.m, name), V.view(V.v, name), V.view(V.g, name),
+                                               V.wk[layer], V.wd[layer], lr_t, self.beta1, self.beta2, self.eps, grad_scale)
+            else:
+                ranges.append((s.offset, s.size))
+                if name.endswith("/weights"):
+                    rest.add(layer)
+        if ranges:
+            net.ops.adam_step_ranges(V.p, V.m, V.v, V.g, ranges, lr_t, self.beta1, self.beta2, self.eps, grad_scale)
+        if rest:
+            net.vars.repack(net.ops, rest)
+
 
 class MomentumOptimizer:
     """tf.train.MomentumOptimizer: a = mu*a + g; p -= lr*a (new functionality)."""
@@ -656,8 +688,11 @@ class TrainStep:
             net.backward()
             net.side.join()
             net.wside.join()
-            opt.apply(net)
-            net.vars.repack(net.ops)
+            if hasattr(opt, "apply_and_repack"):
+                opt.apply_and_repack(net)
+            else:
+                opt.apply(net)
+                net.vars.repack(net.ops)
         else:
             # data parallel: each bucket's all-reduce is launched as soon as its last layer is done; its
             # optimizer update + repack then run on a second side stream right after the collective,
@@ -680,9 +715,12 @@ class TrainStep:
                 def go():
                     if work is not None:
                         work.wait()               # the side stream waits for the collective, not the main one
-                    if not fused:
-                        opt.apply(net, lo, hi)
-                    net.vars.repack(net.ops, names)
+                    if not fused and hasattr(opt, "apply_and_repack"):
+                        opt.apply_and_repack(net, lo, hi, names)
+                    else:
+                        if not fused:
+                            opt.apply(net, lo, hi)
+                        net.vars.repack(net.ops, names)
 
                 fin.run(go)
 

@@ -81,8 +81,11 @@ class LocalBuckets:
         net, opt = self.net, self.opt
 
         def work():
-            opt.apply(net, lo, hi)
-            net.vars.repack(net.ops, names)
+            if hasattr(opt, "apply_and_repack"):
+                opt.apply_and_repack(net, lo, hi, names)     # Adam fused with the bf16 repack where a layer allows it
+            else:
+                opt.apply(net, lo, hi)
+                net.vars.repack(net.ops, names)
 
         wside = getattr(net, "wside", None)
         if wside is not None and wside.enabled and net.side.enabled:

@@ -265,3 +265,32 @@ def test_onehot_to_ids_and_argmax(ops, cuda_device):
     ops.softmax_infer(lg, None, None, am)
     torch.cuda.synchronize()
     assert np.array_equal(am.cpu().numpy(), lg.cpu().numpy().argmax(-1))
+
+
+def test_adam_fused_with_repack_and_multi_range(ops, cuda_device):
+    """segk_adam_pack_conv_weights == segk_adam_step followed by segk_pack_conv_weights, bit for bit; and
+    segk_adam_step_ranges == segk_adam_step on each range (the rest of the arena untouched)."""
+    g_ = torch.Generator(device=cuda_device).manual_seed(8)
+    shape = (3, 3, 128, 192)
+    mk = lambda s=1.0: torch.randn(shape, generator=g_, device=cuda_device) * s
+    p, m, v, g = mk(0.05), mk(1e-3), mk(1e-3).abs() * 1e-3, mk(1e-2)
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    lr_t = 3.1e-4
+    ops.adam_step(p.view(-1), m.view(-1), v.view(-1), g.view(-1), lr_t)
+    wk, wd = ops.pack_conv_weights(p)
+    wk2, wd2 = torch.zeros_like(wk), torch.zeros_like(wd)
+    ops.adam_pack_conv_weights(p2, m2, v2, g, wk2, wd2, lr_t)
+    torch.cuda.synchronize()
+    assert torch.equal(p, p2) and torch.equal(m, m2) and torch.equal(v, v2)
+    assert torch.equal(wk, wk2) and torch.equal(wd, wd2)
+    n = 10000
+    P_, M_, V_, G_ = (torch.randn(n, generator=g_, device=cuda_device) for _ in range(4))
+    V_.abs_()
+    ref = [t.clone() for t in (P_, M_, V_)]
+    ranges = [(0, 7), (64, 100), (1024, 4097), (9000, 1000)]
+    ops.adam_step_ranges(P_, M_, V_, G_, ranges, lr_t)
+    for o, l in ranges:
+        ops.adam_step(ref[0][o:o + l], ref[1][o:o + l], ref[2][o:o + l], G_[o:o + l], lr_t)
+    torch.cuda.synchronize()
+    for a, b in zip((P_, M_, V_), ref):
+        assert torch.allclose(a, b, rtol=1e-6, atol=0)
