@@ -106,16 +106,18 @@ __global__ void __launch_bounds__(kThreads) dense_reduce_rows_kernel(const float
   __shared__ float sh[8][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;          // over 2C columns
-  float a0 = 0.f, a1 = 0.f;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
   if (c < 2 * C) {
     int r = rl;
-    for (; r + 8 < rows; r += 16) {
-      a0 += part[(int64_t)r * 2 * C + c];
-      a1 += part[(int64_t)(r + 8) * 2 * C + c];
+    for (; r + 56 < rows; r += 64) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += part[(int64_t)(r + 8 * j) * 2 * C + c];
     }
-    if (r < rows) a0 += part[(int64_t)r * 2 * C + c];
+    for (; r < rows; r += 8) a[0] += part[(int64_t)r * 2 * C + c];
   }
-  sh[rl][cl] = a0 + a1;
+  sh[rl][cl] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   __syncthreads();
   if (rl == 0 && c < 2 * C) {
     float t = 0.f;

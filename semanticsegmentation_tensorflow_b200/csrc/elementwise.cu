@@ -630,18 +630,18 @@ __global__ void __launch_bounds__(kThreads) reduce_rows_kernel(const float* __re
   __shared__ float sh[8][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
   if (c < C) {
     int r = rl;
-    for (; r + 24 < rows; r += 32) {
-      a0 += part[(int64_t)r * C + c];
-      a1 += part[(int64_t)(r + 8) * C + c];
-      a2 += part[(int64_t)(r + 16) * C + c];
-      a3 += part[(int64_t)(r + 24) * C + c];
+    for (; r + 56 < rows; r += 64) {        // eight loads in flight per thread (this small kernel is L2-latency bound)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += part[(int64_t)(r + 8 * j) * C + c];
     }
-    for (; r < rows; r += 8) a0 += part[(int64_t)r * C + c];
+    for (; r < rows; r += 8) a[0] += part[(int64_t)r * C + c];
   }
-  sh[rl][cl] = (a0 + a1) + (a2 + a3);
+  sh[rl][cl] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   __syncthreads();
   if (rl == 0 && c < C) {
     float t = 0.f;
