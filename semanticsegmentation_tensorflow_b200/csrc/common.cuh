@@ -24,10 +24,8 @@ struct segk_ctx {
   int tma_store = 1;        // SEGK_TMA_STORE: bf16 conv outputs leave through smem + TMA store
   int slab3 = 1;            // SEGK_SLAB3: kx-fused N = 192 slab kernel with resident weights for Ck = 64
   int tail_wide = 1;        // SEGK_TAIL_WIDE: 16-byte-access forms of the few-pixel / wide-channel tail layers (conv8, conv_t1)
-  int teamk = 0;            // SEGK_TEAMK: team stream-K instead of plain split-K for few-tile / long-K layers.  Off by default:
-                            //   measured on conv6's dgrad (B=32) 595 us vs 471 us for 2-way split-K -- the teams walk 29 different
-                            //   K positions at once, the members of a team drift apart, and ncu shows L2 hit 49 % / 2.2 GB of DRAM
-                            //   reads (profiles/r2_conv6_probe.md); it needs cluster-multicast weight tiles to pay off
+  int teamk = 1;            // SEGK_TEAMK: lockstep tap-split schedule instead of plain split-K for few-tile / long-K layers
+                            //   (conv6 dgrad; IgemmParams::ts in tcconv.cu).  0 = plain split-K
   void* ws = nullptr;       // grow-only scratch for split-K partial sums (tcconv.cu)
   size_t ws_bytes = 0;
   void* ws2 = nullptr;      // grow-only scratch for per-block BiasAddGrad partials (elementwise.cu)

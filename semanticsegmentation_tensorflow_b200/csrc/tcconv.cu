@@ -34,7 +34,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;             // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * 128;  // 16 KB
 constexpr int kMaxTaps = 64;
-constexpr int kMaxCols = 64;            // columns of the team stream-K schedule
+constexpr int kMaxCols = 64;            // pixel tiles per channel tile of the lockstep tap-split schedule
 constexpr int kSmemBudget = 192 * 1024;
 constexpr int kStageOutBytes = kBlockM * 128;     // epilogue staging: 128 rows x 64 bf16 channels, SWIZZLE_128B
 constexpr int kOutBytes = 2 * kStageOutBytes;     // double-buffered
@@ -110,15 +110,19 @@ struct IgemmParams {
   // phase-packed transposed conv (segk_deconv2d_packed_fwd): GEMM column = (a*pack_s + b)*pack_co + co of the
   // pack_s x pack_s x pack_co output block of row (n, qy, qx); fp32 stores at out pixel (qy*pack_s - opad + a, ...)
   int pack_s, pack_co;
-  // "team stream-K" for layers with few output tiles and a long, weight-heavy K walk (conv6 dgrad: 50 tiles x ~2060
-  // k-steps, 205 MB of weights).  The tiles that differ only in the batch coordinate (team_members = tiles_n of them)
-  // share every weight slice, so they form a TEAM of CTAs that walk the same k-steps in lockstep (the slice comes from
-  // DRAM once and from L2 for the others).  The concatenated k-steps of all "columns" (nt, y-tile, x-tile) -- team_total,
-  // exclusive prefix sums in team_prefix -- are cut into team_T equal ranges, one per team: every SM gets the same
-  // number of k-steps, whatever the tile count.  A team's piece of a column goes to partial slice
-  // (team - first team of that column); epilogue_finish_kernel adds a column's slices in order.
-  int team, team_T, team_members, team_ncols, team_total;
-  int team_prefix[kMaxCols + 1];
+  // Lockstep tap-split schedule for layers with few output tiles and a long, weight-heavy K walk (conv6 dgrad:
+  // 50 tiles x ~2060 k-steps over 205 MB of weights, which do not fit in L2).  Plain split-K leaves SMs idle
+  // (50 x 2 units on 148 SMs) and lets CTAs whose tiles skip different taps walk the weights at different
+  // positions, so every (y-tile, channel tile) streams its own copy from DRAM (ncu r2: 720 MB for 205 MB).
+  // Here the work of a channel tile is the list of (pixel tile, active tap) pairs -- ts_total of them, exclusive
+  // prefix sums per pixel tile in ts_prefix -- cut into ts_G equal ranges, one per CTA (ts_G * n_tiles CTAs, all
+  // resident).  A CTA owns at most two pixel tiles (one TMEM accumulator each) and walks  k-chunk (outer) ->
+  // its (tile, tap) pairs (inner): every CTA is at the same k-chunk at the same time, so a weight slice
+  // (tap, k-chunk) comes from DRAM once and from L2 for everyone else, and every SM gets the same number of
+  // k-steps (+-1 tap).  A CTA's piece of a tile goes to partial slice (CTA - first CTA of that tile);
+  // epilogue_finish_ts_kernel adds a tile's slices in order (deterministic, no atomics).
+  int ts, ts_G, ts_tiles, ts_total;
+  int ts_prefix[kMaxCols + 1];
 };
 
 struct PipeState {
@@ -188,33 +192,32 @@ __device__ __forceinline__ uint64_t tap_mask(const IgemmParams& p, const TapTabl
   return m;
 }
 
-// first team whose k-step range [total*t/T, total*(t+1)/T) contains global step s
-__host__ __device__ __forceinline__ int team_of_step(int s, int T, int total) {
-  return (int)((((int64_t)s + 1) * T - 1) / total);
+// owner of entry e when `total` entries are cut into T ranges [total*t/T, total*(t+1)/T)
+__host__ __device__ __forceinline__ int ts_owner(int e, int T, int total) {
+  return (int)((((int64_t)e + 1) * T - 1) / total);
 }
 
 // The sequence of (tile, k-step range) work units of one CTA; all three warp roles walk it identically.
 struct Work {
   TileCoord t;       // t.split = partial-sum slice
-  uint64_t tm;       // active taps of the tile
-  int lo, hi;        // k-step range within the tile's (active tap, k-chunk) walk
+  uint64_t tm;       // taps of the tile this unit walks
+  int lo, hi;        // k-step range within the unit's (tap, k-chunk) walk
 };
 
 struct WorkIter {
-  int tile, col, tlo, thi, team, member;
+  int tile, tlo, thi, cta;
   __device__ __forceinline__ void init(const IgemmParams& p) {
     tile = blockIdx.x;
-    col = 0;
-    team = member = tlo = thi = 0;
-    if (p.team) {
-      team = blockIdx.x / p.team_members;
-      member = blockIdx.x % p.team_members;
-      tlo = (int)(((int64_t)p.team_total * team) / p.team_T);
-      thi = (int)(((int64_t)p.team_total * (team + 1)) / p.team_T);
+    tlo = thi = cta = 0;
+    if (p.ts) {
+      cta = blockIdx.x % p.ts_G;
+      tlo = (int)(((int64_t)p.ts_total * cta) / p.ts_G);
+      thi = (int)(((int64_t)p.ts_total * (cta + 1)) / p.ts_G);
+      tile = 0;
     }
   }
   __device__ __forceinline__ bool next(const IgemmParams& p, const TapTable& taps, Work& w) {
-    if (!p.team) {
+    if (!p.ts) {
       const int total_tiles = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.ksplits;
       if (tile >= total_tiles) return false;
       w.t = decode_tile(p, tile);
@@ -226,21 +229,30 @@ struct WorkIter {
       w.hi = (int)(((int64_t)nall * (w.t.split + 1)) / p.ksplits);
       return true;
     }
-    while (col < p.team_ncols) {
-      const int c = col++;
-      const int cs = p.team_prefix[c], ce = p.team_prefix[c + 1];
-      const int a = tlo > cs ? tlo : cs, b = thi < ce ? thi : ce;
-      if (a >= b) continue;
-      int r = c / p.tiles_w;
-      w.t.x0 = (c % p.tiles_w) * p.bw;
-      w.t.y0 = (r % p.tiles_h) * p.bh;
-      w.t.nt = r / p.tiles_h;
-      w.t.n0 = member * p.bn;
+    while (tile < p.ts_tiles) {
+      const int tau = tile++;
+      const int cs = p.ts_prefix[tau], ce = p.ts_prefix[tau + 1];
+      if (ce <= tlo) continue;
+      if (cs >= thi) return false;
+      const int a = (tlo > cs ? tlo : cs) - cs, b = (thi < ce ? thi : ce) - cs;
+      const int col = tau / p.tiles_n;
+      w.t.x0 = (col % p.tiles_w) * p.bw;
+      w.t.y0 = (col / p.tiles_w) * p.bh;
+      w.t.n0 = (tau % p.tiles_n) * p.bn;
+      w.t.nt = blockIdx.x / p.ts_G;
       w.t.phase = 0;
-      w.t.split = team - team_of_step(cs, p.team_T, p.team_total);
-      w.tm = tap_mask(p, taps, w.t);
-      w.lo = a - cs;
-      w.hi = b - cs;
+      w.t.split = cta - ts_owner(cs, p.ts_G, p.ts_total);
+      const uint64_t full = tap_mask(p, taps, w.t);
+      uint64_t sel = 0;
+      int ord = 0;
+      for (int i = 0; i < p.ntaps; ++i)
+        if ((full >> i) & 1) {
+          if (ord >= a && ord < b) sel |= (1ull << i);
+          ++ord;
+        }
+      w.tm = sel;
+      w.lo = 0;
+      w.hi = (b - a) * p.kchunks;
       return true;
     }
     return false;
@@ -375,6 +387,28 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
     WorkIter it;
     it.init(p);
     Work w;
+    if (p.ts) {
+      // lockstep tap-split: k-chunk outer, this CTA's (tile, tap) pairs inner
+      Work u[2];
+      int nu = 0;
+      while (nu < 2 && it.next(p, taps, u[nu])) ++nu;
+      for (int kc = 0; kc < p.kchunks; ++kc)
+        for (int k = 0; k < nu; ++k) {
+          const TileCoord& t = u[k].t;
+          for (uint64_t m = u[k].tm; m; m &= m - 1) {
+            const int i = __ffsll((long long)m) - 1;
+            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+            if (elect_one()) {
+              uint8_t* sa = smem + ps.stage * C::kStageBytes;
+              mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
+              tma_load_4d(&maps.a[taps.map[i]], &full_bar[ps.stage], sa, kc * kBlockK, t.x0 + taps.dx[i], t.y0 + taps.dy[i], t.n0);
+              tma_load_4d(&maps.b, &full_bar[ps.stage], sa + kABytes, 0, t.nt * BLOCK_N, kc, i);
+            }
+            __syncwarp();
+            ps.advance<C::kStages>();
+          }
+        }
+    } else
     while (it.next(p, taps, w)) {
       const TileCoord& t = w.t;
       int step = 0;
@@ -404,6 +438,37 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
     WorkIter it;
     it.init(p);
     Work w;
+    if (p.ts) {
+      // both accumulators stay live for the whole walk (first and only use: no wait on tempty)
+      Work u[2];
+      int nu = 0;
+      while (nu < 2 && it.next(p, taps, u[nu])) ++nu;
+      for (int kc = 0; kc < p.kchunks; ++kc)
+        for (int k = 0; k < nu; ++k) {
+          const uint32_t d_addr = tmem_base + (uint32_t)(k * BLOCK_N);
+          const int n = __popcll(u[k].tm);
+          for (int sidx = 0; sidx < n; ++sidx) {
+            mbar_wait(&full_bar[ps.stage], ps.phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a_lo = smem_lo + (uint32_t)ps.stage * (uint32_t)(C::kStageBytes >> 4);
+              const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
+#pragma unroll
+              for (int kk = 0; kk < kBlockK / 16; ++kk)
+                umma_f16(d_addr, kDescKMajor | (uint64_t)(a_lo + 2 * kk), kDescKMajor | (uint64_t)(b_lo + 2 * kk), idesc,
+                         (kc | sidx | kk) != 0 ? 1u : 0u);
+              umma_commit(&empty_bar[ps.stage]);
+            }
+            __syncwarp();
+            ps.advance<C::kStages>();
+          }
+        }
+      if (elect_one()) {
+        umma_commit(&tfull_bar[0]);
+        if (nu > 1) umma_commit(&tfull_bar[1]);
+      }
+      __syncwarp();
+    } else
     while (it.next(p, taps, w)) {
       const int nsteps = w.hi - w.lo;   // > 0
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -441,7 +506,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
     const bool ep_leader = (threadIdx.x == 64);     // first epilogue thread: issues / tracks the TMA stores
     uint32_t sg = 0;                                // running 64-column group counter -> staging buffer
     float ca0 = 0.f, ca1 = 0.f, ca2 = 0.f, ca3 = 0.f;      // column sums of this thread's columns (p.colsum)
-    const bool partial = p.ksplits > 1 || p.team;
+    const bool partial = p.ksplits > 1 || p.ts;
     WorkIter it;
     it.init(p);
     Work w;
@@ -1320,27 +1385,27 @@ __global__ void __launch_bounds__(256) colsum_rows_kernel(const uint4* __restric
   }
 }
 
-// The same for the team stream-K schedule: the number of partial slices differs per column (nt, y-tile, x-tile).
-struct TeamFinish {
-  int T, total, ncols, tiles_w, tiles_h, bw, bh, H, W, block_n;
+// The same for the lockstep tap-split schedule: the number of partial slices differs per (pixel tile, channel tile).
+struct TsFinish {
+  int G, total, tiles_w, tiles_n, bw, bh, bn, H, W;
   int prefix[kMaxCols + 1];
 };
 
-__global__ void __launch_bounds__(256) epilogue_finish_team_kernel(const float* __restrict__ ws, const TeamFinish tf, int64_t slice,
-                                                                   const float* __restrict__ bias,
-                                                                   const bf16* __restrict__ residual,
-                                                                   const bf16* __restrict__ mask, void* __restrict__ out,
-                                                                   int out_f32, int relu, float scale, int64_t rows, int C) {
+__global__ void __launch_bounds__(256) epilogue_finish_ts_kernel(const float* __restrict__ ws, const TsFinish tf, int64_t slice,
+                                                                 const float* __restrict__ bias,
+                                                                 const bf16* __restrict__ residual,
+                                                                 const bf16* __restrict__ mask, void* __restrict__ out,
+                                                                 int out_f32, int relu, float scale, int64_t rows, int C) {
   const int C8 = C >> 3;
   const int64_t total = rows * C8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C8) * 8;
     const int64_t row = i / C8;
     const int64_t base = row * C + c;
-    const int x = (int)(row % tf.W), y = (int)((row / tf.W) % tf.H);
-    const int col = ((c / tf.block_n) * tf.tiles_h + y / tf.bh) * tf.tiles_w + x / tf.bw;
-    const int cs = tf.prefix[col], ce = tf.prefix[col + 1];
-    const int nparts = team_of_step(ce - 1, tf.T, tf.total) - team_of_step(cs, tf.T, tf.total) + 1;
+    const int x = (int)(row % tf.W), y = (int)((row / tf.W) % tf.H), n = (int)(row / ((int64_t)tf.W * tf.H));
+    const int tau = ((y / tf.bh) * tf.tiles_w + x / tf.bw) * tf.tiles_n + n / tf.bn;
+    const int cs = tf.prefix[tau], ce = tf.prefix[tau + 1];
+    const int nparts = ts_owner(ce - 1, tf.G, tf.total) - ts_owner(cs, tf.G, tf.total) + 1;
     float v[8];
     const float4 a = *reinterpret_cast<const float4*>(ws + base), b = *reinterpret_cast<const float4*>(ws + base + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -1542,9 +1607,9 @@ int launch_igemm_t(segk_ctx* ctx, const TensorMaps& maps, const IgemmParams& p, 
 }
 
 int launch_igemm(segk_ctx* ctx, int block_n, const TensorMaps& maps, const IgemmParams& p, const TapTable& taps,
-                 cudaStream_t st, int team_grid = 0) {
+                 cudaStream_t st, int fixed_grid = 0) {
   const int total = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.ksplits;
-  int grid = team_grid > 0 ? team_grid : (total < ctx->sm_count ? total : ctx->sm_count);
+  int grid = fixed_grid > 0 ? fixed_grid : (total < ctx->sm_count ? total : ctx->sm_count);
   if (p.colsum) grid = (grid / p.n_tiles) * p.n_tiles;      // every tile of a CTA has the same channel tile
   switch (block_n) {
     case 256: return launch_igemm_t<256>(ctx, maps, p, taps, grid, st);
@@ -1713,50 +1778,55 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
     // one wave of work units.  Measured (tools/time_conv6.py, conv6 dgrad: 50 tiles x 2240 k-steps): 2 splits
     // 483 us, 1: 766, 3: 596, 5: 562, 8: 692, 14: 918 -- more splits than one wave lets the m-tiles that share
     // a weight slice drift apart in K, and the 205 MB of weights stream from DRAM several times over
-    // team stream-K: every CTA gets the same number of k-steps; the tiles_n CTAs of a team share each weight slice
-    const int ncols = p.n_tiles * p.tiles_h * p.tiles_w;
-    if (force_ks <= 0 && ctx->teamk && ncols <= kMaxCols && p.tiles_n <= ctx->sm_count) {
-      TeamFinish tf;
-      memset(&tf, 0, sizeof(tf));
-      int total_steps = 0;
-      for (int c = 0; c < ncols; ++c) {
-        const int x0 = (c % p.tiles_w) * b.bw, y0 = ((c / p.tiles_w) % p.tiles_h) * b.bh;
+    // lockstep tap-split (IgemmParams::ts): every CTA gets the same number of k-steps and all CTAs sweep the k-chunks
+    // together, so a weight slice is fetched from DRAM once.  Needs >= 2 (tile, tap) pairs per CTA and at most two
+    // pixel tiles per CTA (two TMEM accumulators).
+    const int tiles_per_nt = p.tiles_h * p.tiles_w * p.tiles_n;
+    if (force_ks <= 0 && ctx->teamk && tiles_per_nt <= kMaxCols && p.n_tiles <= ctx->sm_count) {
+      int total_taps = 0, min_act = p.ntaps;
+      for (int tau = 0; tau < tiles_per_nt; ++tau) {
+        const int col = tau / p.tiles_n;
+        const int x0 = (col % p.tiles_w) * b.bw, y0 = (col / p.tiles_w) * b.bh;
         int act = 0;
         for (int i = 0; i < p.ntaps; ++i) {
           const int ya = y0 + taps.dy[i], xa = x0 + taps.dx[i];
           act += !(ya + b.bh <= 0 || ya >= H || xa + b.bw <= 0 || xa >= W);
         }
         if (act == 0) act = p.ntaps;                      // mirrors tap_mask(): an all-padding tile still produces zeros
-        p.team_prefix[c] = total_steps;
-        total_steps += act * p.kchunks;
+        if (act < min_act) min_act = act;
+        p.ts_prefix[tau] = total_taps;
+        total_taps += act;
       }
-      p.team_prefix[ncols] = total_steps;
-      int T = ctx->sm_count / p.tiles_n;
-      if (T > total_steps / 8) T = total_steps / 8;       // at least 8 k-steps per team
-      if (T >= 2 && (int64_t)T * p.tiles_n * 100 >= (int64_t)85 * ctx->sm_count) {
+      p.ts_prefix[tiles_per_nt] = total_taps;
+      int G = ctx->sm_count / p.n_tiles;
+      if (G > total_taps / 2) G = total_taps / 2;
+      const int share = G > 0 ? ceil_div(total_taps, G) : 0;
+      if (G >= 1 && share <= min_act && G > tiles_per_nt) {
         int max_parts = 1;
-        for (int c = 0; c < ncols; ++c) {
-          const int np = team_of_step(p.team_prefix[c + 1] - 1, T, total_steps) - team_of_step(p.team_prefix[c], T, total_steps) + 1;
+        for (int tau = 0; tau < tiles_per_nt; ++tau) {
+          const int np = ts_owner(p.ts_prefix[tau + 1] - 1, G, total_taps) - ts_owner(p.ts_prefix[tau], G, total_taps) + 1;
           if (np > max_parts) max_parts = np;
         }
         const size_t slice = (size_t)N * H * W * Cn;
         rc = ensure_workspace(ctx, sizeof(float) * slice * max_parts);
         if (rc) return rc;
-        p.team = 1; p.team_T = T; p.team_members = p.tiles_n; p.team_ncols = ncols; p.team_total = total_steps;
+        p.ts = 1; p.ts_G = G; p.ts_tiles = tiles_per_nt; p.ts_total = total_taps;
         p.ws = (float*)ctx->ws;
         p.ws_slice = (int64_t)slice;
-        rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream, T * p.tiles_n);
+        rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream, G * p.n_tiles);
         if (rc) return rc;
-        tf.T = T; tf.total = total_steps; tf.ncols = ncols; tf.tiles_w = p.tiles_w; tf.tiles_h = p.tiles_h;
-        tf.bw = b.bw; tf.bh = b.bh; tf.H = H; tf.W = W; tf.block_n = block_n;
-        memcpy(tf.prefix, p.team_prefix, sizeof(tf.prefix));
+        TsFinish tf;
+        memset(&tf, 0, sizeof(tf));
+        tf.G = G; tf.total = total_taps; tf.tiles_w = p.tiles_w; tf.tiles_n = p.tiles_n;
+        tf.bw = b.bw; tf.bh = b.bh; tf.bn = b.bn; tf.H = H; tf.W = W;
+        memcpy(tf.prefix, p.ts_prefix, sizeof(tf.prefix));
         const int64_t rows = (int64_t)N * H * W;
         int64_t blocks = ceil_div64(rows * (Cn / 8), 256);
         if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
-        epilogue_finish_team_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+        epilogue_finish_ts_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
             (const float*)ctx->ws, tf, (int64_t)slice, bias, (const bf16*)residual, (const bf16*)mask, y, out_f32, relu, scale,
             rows, Cn);
-        SEGK_LAUNCHED(ctx, "igemm team stream-K finish");
+        SEGK_LAUNCHED(ctx, "igemm tap-split finish");
         if (colsum_out) return colsum_fallback(ctx, y, rows, Cn, colsum_out, (cudaStream_t)stream);
         return SEGK_OK;
       }
@@ -2316,7 +2386,7 @@ int segk_tc_init(segk_ctx* ctx) {
   ctx->slab_mode = env_int("SEGK_SLAB", 1);
   ctx->tma_store = env_int("SEGK_TMA_STORE", 1);
   ctx->slab3 = env_int("SEGK_SLAB3", 1);
-  ctx->teamk = env_int("SEGK_TEAMK", 0);
+  ctx->teamk = env_int("SEGK_TEAMK", 1);
   cudaError_t e = cudaSuccess;
 #define SEGK_SMEM_ATTR(kern, bytes) \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)

@@ -377,10 +377,10 @@ def test_slab_kernels_stay_inside_their_outputs(ops, cuda_device, shape):
 
 @pytest.mark.parametrize("shape", [(16, 5, 18, 256, 256, 7), (2, 5, 18, 512, 1024, 7), (9, 5, 18, 128, 512, 5)])
 def test_team_stream_k_fwd_dgrad_and_wgrad_box_skipping(ops, cuda_device, shape):
-    """conv6-like layers (k > map height, few output tiles, long K walk): the team stream-K schedule of
-    igemm_kernel (several batch tiles per team, columns with different tap counts, pieces of a column in
-    different partial slices) against the oracle and against the plain split-K path; and the weight gradient
-    with all-padding (pixel box, tap) pairs skipped."""
+    """conv6-like layers (k > map height, few output tiles, long K walk): the lockstep tap-split schedule of
+    igemm_kernel (a CTA owns (tile, tap) pairs of up to two pixel tiles, tiles with different tap counts, pieces
+    of a tile in different partial slices) against the oracle and against the plain split-K path; and the weight
+    gradient with all-padding (pixel box, tap) pairs skipped."""
     n, h, w, ci, co, k = shape
     x, wt, b = _conv_case(shape, 40)
     rng = np.random.default_rng(41)
@@ -412,7 +412,7 @@ def test_team_stream_k_fwd_dgrad_and_wgrad_box_skipping(ops, cuda_device, shape)
             torch.cuda.synchronize()
             assert torch.equal(y, y2)
     finally:
-        ops.ctx.set_tuning("teamk", 0)
+        ops.ctx.set_tuning("teamk", 1)
     dw = torch.full((k, k, ci, co), 7.0, dtype=torch.float32, device=cuda_device)
     ops.conv2d_wgrad(xd, dyd, dw, k, k)
     torch.cuda.synchronize()
