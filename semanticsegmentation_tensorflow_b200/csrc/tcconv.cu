@@ -21,7 +21,10 @@
 #include "tc_common.cuh"
 #include "tc_host.cuh"
 
+#include <algorithm>
 #include <cstdlib>
+#include <utility>
+#include <vector>
 
 namespace {
 
@@ -34,6 +37,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;             // bf16 elements = one 128-byte swizzle row
 constexpr int kABytes = kBlockM * 128;  // 16 KB
 constexpr int kMaxTaps = 64;
+constexpr int kMaxRbp = 512;            // row-block pairs a wgrad launch can reorder by cost
 constexpr int kMaxCols = 64;            // pixel tiles per channel tile of the lockstep tap-split schedule
 constexpr int kSmemBudget = 192 * 1024;
 constexpr int kStageOutBytes = kBlockM * 128;     // epilogue staging: 128 rows x 64 bf16 channels, SWIZZLE_128B
@@ -281,9 +285,26 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 // bias -> residual (skip-add / AddN) -> ReLU -> ReLU mask of the producer -> scale, then the store: fp32,
 // bf16 into the swizzled staging row of a TMA store (16-byte pieces pbase..pbase+3 of row `srow`), or
 // bf16 straight to global memory.  P = IgemmParams or SlabParams.
+// The residual / ReLU-mask values of those 32 channels.  They are loaded ahead of the accumulator (before the wait on
+// the MMA barrier for a tile's first column group, during the previous group's arithmetic for the others): issued after
+// the TMEM load they cost a full global-memory latency per column group, which made the dgrad epilogues of the
+// 64-channel layers longer than their MMAs (ncu r1d: conv1_2 dgrad epilogue-bound).
+struct EpiPre {
+  uint4 a[4];     // the residual when there is one, else the mask (both at once -- no layer of the three nets -- loads the mask late)
+};
 template <class P>
-__device__ __forceinline__ void epilogue_apply_store(const P& p, float (&v)[32], const float4 (&bv)[8], int64_t off,
-                                                     uint8_t* sbuf, int srow, int pbase) {
+__device__ __forceinline__ void epilogue_prefetch(const P& p, int64_t off, EpiPre& e) {
+  const bf16* src = p.residual ? p.residual : p.mask;
+  if (src) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + off);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) e.a[i] = __ldg(s4 + i);
+  }
+}
+
+template <class P>
+__device__ __forceinline__ void epilogue_apply_store(const P& p, float (&v)[32], const float4 (&bv)[8], const EpiPre& pre,
+                                                     int64_t off, uint8_t* sbuf, int srow, int pbase) {
   if (p.bias) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -291,10 +312,9 @@ __device__ __forceinline__ void epilogue_apply_store(const P& p, float (&v)[32],
     }
   }
   if (p.residual) {
-    const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + off);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const uint4 u = __ldg(r4 + i);
+      const uint4 u = pre.a[i];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = unpack_bf16x2((&u.x)[j]);
@@ -311,7 +331,7 @@ __device__ __forceinline__ void epilogue_apply_store(const P& p, float (&v)[32],
     const uint4* m4 = reinterpret_cast<const uint4*>(p.mask + off);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const uint4 u = __ldg(m4 + i);
+      const uint4 u = p.residual ? __ldg(m4 + i) : pre.a[i];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = unpack_bf16x2((&u.x)[j]);
@@ -519,6 +539,9 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
                          oy >= 0 && oy < p.out_H;
       const int64_t opix = ((int64_t)n * p.out_H + oy) * p.out_W + ox;
       const int64_t obase = opix * p.ldo + (int64_t)t.nt * BLOCK_N;
+      const bool full_epi = valid && !partial && !p.pack_s;
+      EpiPre pre;
+      if (full_epi) epilogue_prefetch(p, obase + half * 32, pre);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
@@ -569,7 +592,9 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(r[i]) : 0.f;
-          if (valid) epilogue_apply_store(p, v, bv, obase + c0, sbuf, row, half * 4);
+          const EpiPre cur = pre;
+          if (full_epi && g0 + 64 < BLOCK_N) epilogue_prefetch(p, obase + c0 + 64, pre);
+          if (valid) epilogue_apply_store(p, v, bv, cur, obase + c0, sbuf, row, half * 4);
           if (p.colsum) {        // rows outside the tensor contribute zeros
             const float cs = warp_colsum32(v, lane);
             if (g0 == 0) ca0 += cs; else if (g0 == 64) ca1 += cs; else if (g0 == 128) ca2 += cs; else ca3 += cs;
@@ -788,6 +813,8 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
       const int ox = x0 + lane, oy = y0 + q;
       const bool valid = lane < kSlabWV && ox < p.W && oy < p.H;
       const int64_t obase = (((int64_t)n * p.H + oy) * p.W + ox) * p.ldo + (int64_t)nt * BLOCK_N;
+      EpiPre pre;
+      if (valid) epilogue_prefetch(p, obase + half * 32, pre);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
@@ -812,7 +839,9 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = valid ? __uint_as_float(rr[i]) : 0.f;
-          if (valid) epilogue_apply_store(p, v, bv, obase + c0, sbuf, srow, half * 4);
+          const EpiPre cur = pre;
+          if (valid && g0 + 64 < BLOCK_N) epilogue_prefetch(p, obase + c0 + 64, pre);
+          if (valid) epilogue_apply_store(p, v, bv, cur, obase + c0, sbuf, srow, half * 4);
           if (p.colsum) {
             const float cs = warp_colsum32(v, lane);
             if (g0 == 0) ca0 += cs; else if (g0 == 64) ca1 += cs; else if (g0 == 128) ca2 += cs; else ca3 += cs;
@@ -986,6 +1015,11 @@ slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
       const int ox = x0 + lane, oy = y0 + q;
       const bool valid = lane < kSlabWV && ox < p.W && oy < p.H;
       const int64_t obase = (((int64_t)n * p.H + oy) * p.W + ox) * p.ldo + (int64_t)nt * 64;
+      EpiPre pre0, pre1;
+      if (valid) {
+        epilogue_prefetch(p, obase, pre0);
+        epilogue_prefetch(p, obase + 32, pre1);
+      }
       mbar_wait(&tfull_bar[grp], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * 256);
@@ -993,7 +1027,7 @@ slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
         if (ep_leader) tma_store_wait_read<0>();     // this group's previous store has read the staging buffer
         named_bar_sync(1 + grp, 128);
       }
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 32) {
         float4 bv[8];
         if (p.bias) {
@@ -1013,7 +1047,7 @@ slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
             v[i] = __uint_as_float(r0[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(r1[i]), 1) +
                    __shfl_down_sync(0xffffffffu, __uint_as_float(r2[i]), 2);
         }
-        if (valid) epilogue_apply_store(p, v, bv, obase + c0, sbuf, srow, c0 ? 4 : 0);
+        if (valid) epilogue_apply_store(p, v, bv, c0 ? pre1 : pre0, obase + c0, sbuf, srow, c0 ? 4 : 0);
       }
       // the accumulator is in registers / staging now: hand it back to the MMA warp before the store
       tc_fence_before();
@@ -1057,6 +1091,13 @@ struct WgradParams {
                               //    of the item) are skipped: no TMA, no MMA (conv6: 7x7 taps on a 5x18 map, 38 % of the pairs)
   int64_t part_stride;        // elements between the partial buffers of consecutive splits (0: dw is the result itself)
   float* dw;
+  // with skip_oob the items cost between a few and all of the pixel boxes (conv6: corner taps see 8 of 45): the row-block
+  // pairs are visited in order of decreasing cost (host-sorted), so the static round-robin over CTAs stays balanced
+  int wide_store;             // dW (or the partial buffers) and its strides are 32-byte aligned: 256-bit stores
+  int use_perm;
+  uint16_t rbp_perm[kMaxRbp];
+  uint16_t rbp_nact[kMaxRbp];   // contributing pixel boxes of the pair at sorted position r (splits == 1): counting them in
+                                // the kernel took ~3 us per item in the TMA and MMA warps, a third of a conv6 item
 };
 
 // wgrad: does pixel box (x0, y0) contribute to the item's row blocks?  A tap whose shifted box is entirely outside
@@ -1087,9 +1128,14 @@ __device__ __forceinline__ int wgrad_count_active(const WgradParams& p, int pt0,
   return n;
 }
 
+__device__ __forceinline__ int wgrad_rbp(const WgradParams& p, int item) {
+  const int r = (item / p.n_tiles) % p.n_rbp;
+  return p.use_perm ? (int)p.rbp_perm[r] : r;
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kWgradThreads, 1)
-wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const TapTable taps) {
+wgrad_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ WgradParams p, const TapTable taps) {
   using C = WCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1127,7 +1173,7 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
     PipeState ps;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int nt = item % p.n_tiles;
-      const int rbp = (item / p.n_tiles) % p.n_rbp;
+      const int rbp = wgrad_rbp(p, item);
       const int split = item / (p.n_tiles * p.n_rbp);
       const int rb0 = 2 * rbp, rb1 = (2 * rbp + 1 < p.n_rb) ? 2 * rbp + 1 : 2 * rbp;
       const int tap0 = rb0 / p.kchunks_in, c0 = (rb0 % p.kchunks_in) * 64;
@@ -1139,7 +1185,7 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
       int x0 = (pt0 % p.tiles_w) * p.bw;
       int y0 = ((pt0 / p.tiles_w) % p.tiles_h) * p.bh;
       int n0 = (pt0 / (p.tiles_w * p.tiles_h)) * p.bn;
-      int nact = wgrad_count_active(p, pt0, pt1, dx0, dy0, dx1, dy1);
+      int nact = p.use_perm ? (int)p.rbp_nact[(item / p.n_tiles) % p.n_rbp] : wgrad_count_active(p, pt0, pt1, dx0, dy0, dx1, dy1);
       const bool all = (nact == 0) || !p.skip_oob;
       if (nact == 0) nact = pt1 - pt0;
       int done = 0;
@@ -1187,10 +1233,11 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
       if (pt1 - pt0 <= 0) continue;
       int nboxes = pt1 - pt0;
       if (p.skip_oob) {
-        const int rbp = (item / p.n_tiles) % p.n_rbp;
+        const int rbp = wgrad_rbp(p, item);
         const int rb0 = 2 * rbp, rb1 = (2 * rbp + 1 < p.n_rb) ? 2 * rbp + 1 : 2 * rbp;
         const int tap0 = rb0 / p.kchunks_in, tap1 = rb1 / p.kchunks_in;
-        const int na = wgrad_count_active(p, pt0, pt1, taps.dx[tap0], taps.dy[tap0], taps.dx[tap1], taps.dy[tap1]);
+        const int na = p.use_perm ? (int)p.rbp_nact[(item / p.n_tiles) % p.n_rbp]
+                                  : wgrad_count_active(p, pt0, pt1, taps.dx[tap0], taps.dy[tap0], taps.dx[tap1], taps.dy[tap1]);
         if (na > 0) nboxes = na;
       }
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -1225,7 +1272,7 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int nt = item % p.n_tiles;
-      const int rbp = (item / p.n_tiles) % p.n_rbp;
+      const int rbp = wgrad_rbp(p, item);
       const int split = item / (p.n_tiles * p.n_rbp);
       const int pt0 = split * per_split;
       const int pt1 = min(pt0 + per_split, n_ptiles);
@@ -1245,11 +1292,22 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const WgradParams p, const
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
         if (valid) {
-          float4* d4 = reinterpret_cast<float4*>(dst + c0);
+          if (p.wide_store) {
+            // 32-byte stores: every lane writes whole sectors of its own dW row (rows are Cout * 4 bytes apart, so a
+            // warp store touches 32 lines either way; this halves the requests)
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            d4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+            for (int i = 0; i < 4; ++i)
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + c0 + 8 * i), "r"(r[8 * i]),
+                           "r"(r[8 * i + 1]), "r"(r[8 * i + 2]), "r"(r[8 * i + 3]), "r"(r[8 * i + 4]), "r"(r[8 * i + 5]),
+                           "r"(r[8 * i + 6]), "r"(r[8 * i + 7])
+                           : "memory");
+          } else {
+            float4* d4 = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              d4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                  __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+          }
         }
       }
       tc_fence_before();
@@ -1622,7 +1680,10 @@ template <int BLOCK_N>
 int launch_wgrad_t(segk_ctx* ctx, const TensorMaps& maps, const WgradParams& p, const TapTable& taps, int grid,
                    cudaStream_t st) {
   using C = WCfg<BLOCK_N>;
-  wgrad_kernel<BLOCK_N><<<grid, kWgradThreads, C::kSmemBytes, st>>>(maps, p, taps);
+  WgradParams q = p;
+  q.wide_store = (((uintptr_t)p.dw & 31) == 0 && p.dw_col_stride == 1 && p.dw_row_stride % 8 == 0 && p.dw_tap_stride % 8 == 0 &&
+                  p.part_stride % 8 == 0) ? 1 : 0;
+  wgrad_kernel<BLOCK_N><<<grid, kWgradThreads, C::kSmemBytes, st>>>(maps, q, taps);
   SEGK_LAUNCHED(ctx, "wgrad");
   return SEGK_OK;
 }
@@ -2338,6 +2399,30 @@ static int conv2d_wgrad_impl(segk_ctx* ctx, const void* x, const void* dy, float
   p.skip_oob = (rate > 1 || active_taps_1d(W, b.bw, kw) * active_taps_1d(H, b.bh, kh) < (int64_t)p.tiles_w * p.tiles_h * kh * kw) ? 1 : 0;
   const int total = p.splits * p.n_rbp * p.n_tiles;
   const int grid = total < ctx->sm_count ? total : ctx->sm_count;
+  if (p.skip_oob && p.n_rbp <= kMaxRbp && p.splits == 1 && n_ptiles < 65536) {
+    // cost of a row-block pair = pixel boxes (x-tile, y-tile) that either of its taps can see
+    std::vector<std::pair<int, int>> cost(p.n_rbp);
+    for (int r = 0; r < p.n_rbp; ++r) {
+      const int rb0 = 2 * r, rb1 = (2 * r + 1 < p.n_rb) ? 2 * r + 1 : 2 * r;
+      const int t0 = rb0 / p.kchunks_in, t1 = rb1 / p.kchunks_in;
+      int act = 0;
+      for (int ty = 0; ty < p.tiles_h; ++ty)
+        for (int tx = 0; tx < p.tiles_w; ++tx) {
+          const int x0 = tx * b.bw, y0 = ty * b.bh;
+          const int xa = x0 + taps.dx[t0], ya = y0 + taps.dy[t0], xb = x0 + taps.dx[t1], yb = y0 + taps.dy[t1];
+          const bool a = !(ya + b.bh <= 0 || ya >= H || xa + b.bw <= 0 || xa >= W);
+          const bool bb = !(yb + b.bh <= 0 || yb >= H || xb + b.bw <= 0 || xb >= W);
+          act += (a || bb) ? 1 : 0;
+        }
+      cost[r] = std::make_pair(-act, r);
+    }
+    std::sort(cost.begin(), cost.end());
+    for (int r = 0; r < p.n_rbp; ++r) {
+      p.rbp_perm[r] = (uint16_t)cost[r].second;
+      p.rbp_nact[r] = (uint16_t)(-cost[r].first * p.tiles_n);
+    }
+    p.use_perm = 1;
+  }
   switch (block_n) {
     case 256: rc = launch_wgrad_t<256>(ctx, maps, p, taps, grid, st); break;
     case 128: rc = launch_wgrad_t<128>(ctx, maps, p, taps, grid, st); break;
