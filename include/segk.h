@@ -53,9 +53,9 @@ const char* segk_last_error(segk_ctx* ctx);
 int64_t segk_launch_count(segk_ctx* ctx);
 int segk_sm_count(segk_ctx* ctx);
 /* Kernel-selection overrides (also read once at segk_create from SEGK_SLAB / SEGK_SLAB3 / SEGK_WSLAB /
- * SEGK_TMA_STORE / SEGK_TEAMK / SEGK_FORCE_BN / SEGK_FORCE_KSPLIT / SEGK_FORCE_WSPLIT): key in {"slab", "slab3",
+ * SEGK_TMA_STORE / SEGK_TEAMK / SEGK_HYBRID / SEGK_FORCE_BN / SEGK_FORCE_KSPLIT / SEGK_FORCE_WSPLIT): key in {"slab", "slab3",
  * "wslab" (0 off, 1 auto, 2 wherever legal), "tma_store" (0|1), "teamk" (0|1: lockstep tap-split schedule instead of plain
- * split-K for few-tile / long-K layers), "tail_wide" (0|1: 16-byte-access forms of conv8 / conv_t1 and their gradients), "force_bn" (0|64|128|256), "force_ksplit", "force_wsplit" (0 = heuristic)}.  Every setting computes the same sums (fp32
+ * split-K for few-tile / long-K layers), "hybrid" (0|1: whole waves + K-split remainder tiles), "tail_wide" (0|1: 16-byte-access forms of conv8 / conv_t1 and their gradients), "force_bn" (0|64|128|256), "force_ksplit", "force_wsplit" (0 = heuristic)}.  Every setting computes the same sums (fp32
  * accumulation order differs between kernels). */
 int segk_set_tuning(segk_ctx* ctx, const char* key, int value);
 

@@ -26,6 +26,10 @@ struct segk_ctx {
   int tail_wide = 1;        // SEGK_TAIL_WIDE: 16-byte-access forms of the few-pixel / wide-channel tail layers (conv8, conv_t1)
   int teamk = 1;            // SEGK_TEAMK: lockstep tap-split schedule instead of plain split-K for few-tile / long-K layers
                             //   (conv6 dgrad; IgemmParams::ts in tcconv.cu).  0 = plain split-K
+  int hybrid = 0;           // SEGK_HYBRID: whole waves + K-split remainder tiles when the last wave of an igemm launch is partly
+                            //   filled.  Off by default: measured on conv5_x (B=32, 180 tiles on 148 SMs) 58 us vs 51 us for two
+                            //   plain waves -- the two epilogues after the last MMA and the finish kernel (launch + 10 us) cost
+                            //   more than the 54 idle k-steps they save (profiles/r2_hybrid_probe.md)
   void* ws = nullptr;       // grow-only scratch for split-K partial sums (tcconv.cu)
   size_t ws_bytes = 0;
   void* ws2 = nullptr;      // grow-only scratch for per-block BiasAddGrad partials (elementwise.cu)

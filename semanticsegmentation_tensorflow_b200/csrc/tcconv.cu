@@ -127,6 +127,7 @@ struct IgemmParams {
   // epilogue_finish_ts_kernel adds a tile's slices in order (deterministic, no atomics).
   int ts, ts_G, ts_tiles, ts_total;
   int ts_prefix[kMaxCols + 1];
+  int hyb, hyb_full; // hyb = 1: hybrid schedule -- tiles [0, hyb_full) whole, the rest in ksplits pieces
 };
 
 struct PipeState {
@@ -147,15 +148,7 @@ struct TileCoord {
 
 __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
   TileCoord t;
-  if (p.m_fastest) {
-    // split slowest: the CTAs running at the same time walk the same K range, i.e. share weight slices
-    const int tiles = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
-    t.split = tile / tiles;
-    tile -= t.split * tiles;
-  } else {
-    t.split = tile % p.ksplits;
-    tile /= p.ksplits;
-  }
+  t.split = 0;
   if (p.m_fastest) {
     // weight-heavy layers (conv6: 205 MB of weights, 3 MB of activations): consecutive CTAs take
     // different pixel tiles of the SAME channel tile, so a weight tile is fetched from DRAM once and
@@ -206,6 +199,7 @@ struct Work {
   TileCoord t;       // t.split = partial-sum slice
   uint64_t tm;       // taps of the tile this unit walks
   int lo, hi;        // k-step range within the unit's (tap, k-chunk) walk
+  int partial;       // 1: the unit stores fp32 partial sums into its workspace slice (a finish kernel completes the tile)
 };
 
 struct WorkIter {
@@ -222,15 +216,38 @@ struct WorkIter {
   }
   __device__ __forceinline__ bool next(const IgemmParams& p, const TapTable& taps, Work& w) {
     if (!p.ts) {
-      const int total_tiles = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.ksplits;
-      if (tile >= total_tiles) return false;
-      w.t = decode_tile(p, tile);
+      const int tiles = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+      // units: every tile in ksplits pieces -- or, hybrid (p.hyb): the first hyb_full tiles whole (whole waves
+      // of the persistent grid) and only the remainder in ksplits pieces, so the last, partly filled wave is spread
+      // over all SMs (conv5_x at B=32: 180 tiles on 148 SMs ran as two waves)
+      const int whole = p.hyb ? p.hyb_full : 0;
+      const int total_units = whole + (tiles - whole) * p.ksplits;
+      if (tile >= total_units) return false;
+      const int unit = tile;
       tile += gridDim.x;
+      int tl, split, nsp;
+      const int nsplit_units = (tiles - whole) * p.ksplits;
+      // the split units come FIRST: their fp32 partial stores then run under the MMAs of the CTA's whole tiles
+      if (unit >= nsplit_units) {
+        tl = unit - nsplit_units; split = 0; nsp = 1;
+      } else {
+        const int r = unit, rem = tiles - whole;
+        nsp = p.ksplits;
+        if (p.m_fastest || p.hyb) {
+          // split slowest: the CTAs running at the same time walk the same K range, i.e. share weight slices
+          split = r / rem; tl = whole + r % rem;
+        } else {
+          split = r % nsp; tl = whole + r / nsp;
+        }
+      }
+      w.t = decode_tile(p, tl);
+      w.t.split = split;
+      w.partial = nsp > 1;
       w.tm = tap_mask(p, taps, w.t);
       const int nall = __popcll(w.tm) * p.kchunks;
       // balanced partition: no split is empty because ksplits <= kchunks <= nall
-      w.lo = (int)(((int64_t)nall * w.t.split) / p.ksplits);
-      w.hi = (int)(((int64_t)nall * (w.t.split + 1)) / p.ksplits);
+      w.lo = (int)(((int64_t)nall * split) / nsp);
+      w.hi = (int)(((int64_t)nall * (split + 1)) / nsp);
       return true;
     }
     while (tile < p.ts_tiles) {
@@ -257,6 +274,7 @@ struct WorkIter {
       w.tm = sel;
       w.lo = 0;
       w.hi = (b - a) * p.kchunks;
+      w.partial = 1;
       return true;
     }
     return false;
@@ -526,12 +544,12 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
     const bool ep_leader = (threadIdx.x == 64);     // first epilogue thread: issues / tracks the TMA stores
     uint32_t sg = 0;                                // running 64-column group counter -> staging buffer
     float ca0 = 0.f, ca1 = 0.f, ca2 = 0.f, ca3 = 0.f;      // column sums of this thread's columns (p.colsum)
-    const bool partial = p.ksplits > 1 || p.ts;
     WorkIter it;
     it.init(p);
     Work w;
     while (it.next(p, taps, w)) {
       const TileCoord& t = w.t;
+      const bool partial = w.partial != 0;
       const int ay = t.phase / p.s, ax = t.phase % p.s;
       const int qx = t.x0 + iw, qy = t.y0 + ih, n = t.n0 + in;
       const int ox = qx * p.os + ax - p.opad, oy = qy * p.os + ay - p.opad;
@@ -540,6 +558,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
       const int64_t opix = ((int64_t)n * p.out_H + oy) * p.out_W + ox;
       const int64_t obase = opix * p.ldo + (int64_t)t.nt * BLOCK_N;
       const bool full_epi = valid && !partial && !p.pack_s;
+      const bool do_tma = p.tma_store && !partial;      // (uniform over the epilogue warps: barriers stay matched)
       EpiPre pre;
       if (full_epi) epilogue_prefetch(p, obase + half * 32, pre);
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -549,7 +568,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
       for (int g0 = 0; g0 < BLOCK_N; g0 += 64) {
         const int c0 = g0 + half * 32;
         uint8_t* sbuf = smem_out + (sg & 1) * kStageOutBytes;
-        if (p.tma_store) {
+        if (do_tma) {
           // the store that used this staging buffer two groups ago must have finished reading it
           if (ep_leader) tma_store_wait_read<1>();
           named_bar_sync(1, kEpiThreads);
@@ -600,7 +619,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
             if (g0 == 0) ca0 += cs; else if (g0 == 64) ca1 += cs; else if (g0 == 128) ca2 += cs; else ca3 += cs;
           }
         }
-        if (p.tma_store) {
+        if (do_tma) {
           fence_proxy_async();                        // generic-proxy smem writes -> visible to the TMA engine
           named_bar_sync(1, kEpiThreads);
           if (ep_leader) {
@@ -1510,6 +1529,66 @@ __global__ void __launch_bounds__(256) epilogue_finish_ts_kernel(const float* __
   }
 }
 
+// Finishes the split tiles [first, first + ntiles) of a hybrid launch: the same arithmetic as epilogue_finish_kernel, over
+// the pixel boxes of those tiles only (8 channels per thread).
+__global__ void __launch_bounds__(256) epilogue_finish_tiles_kernel(const float* __restrict__ ws, const IgemmParams p, int first,
+                                                                    int ntiles, int block_n) {
+  const int C8 = block_n >> 3;
+  const int64_t total = (int64_t)ntiles * p.rows * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    const int row = (int)((i / C8) % p.rows);
+    const TileCoord t = decode_tile(p, first + (int)(i / ((int64_t)C8 * p.rows)));
+    const int qx = t.x0 + row % p.bw, qy = t.y0 + (row / p.bw) % p.bh, n = t.n0 + row / (p.bw * p.bh);
+    if (qx >= p.W || qy >= p.H || n >= p.N) continue;
+    const int ch = t.nt * block_n + c;
+    const int64_t base = (((int64_t)n * p.out_H + qy) * p.out_W + qx) * p.ldo + ch;
+    float v[8];
+    const float4 a = *reinterpret_cast<const float4*>(ws + base), b = *reinterpret_cast<const float4*>(ws + base + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    for (int s = 1; s < p.ksplits; ++s) {
+      const float4 a2 = *reinterpret_cast<const float4*>(ws + s * p.ws_slice + base);
+      const float4 b2 = *reinterpret_cast<const float4*>(ws + s * p.ws_slice + base + 4);
+      v[0] += a2.x; v[1] += a2.y; v[2] += a2.z; v[3] += a2.w; v[4] += b2.x; v[5] += b2.y; v[6] += b2.z; v[7] += b2.w;
+    }
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += __ldg(p.bias + ch + j);
+    }
+    if (p.residual) {
+      const uint4 u = *reinterpret_cast<const uint4*>(p.residual + base);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&u.x)[j]);
+        v[2 * j] += f.x; v[2 * j + 1] += f.y;
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (p.mask) {
+      const uint4 u = *reinterpret_cast<const uint4*>(p.mask + base);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&u.x)[j]);
+        if (!(f.x > 0.f)) v[2 * j] = 0.f;
+        if (!(f.y > 0.f)) v[2 * j + 1] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= p.scale;
+    if (p.out_f32) {
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + base);
+      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + base) =
+          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    }
+  }
+}
+
 // grow-only device scratch owned by the context (first use allocates; never on the steady-state path)
 int ensure_workspace(segk_ctx* ctx, size_t bytes) { return segk_grow(ctx, &ctx->ws, &ctx->ws_bytes, bytes, "split-K workspace"); }
 
@@ -1666,7 +1745,8 @@ int launch_igemm_t(segk_ctx* ctx, const TensorMaps& maps, const IgemmParams& p, 
 
 int launch_igemm(segk_ctx* ctx, int block_n, const TensorMaps& maps, const IgemmParams& p, const TapTable& taps,
                  cudaStream_t st, int fixed_grid = 0) {
-  const int total = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles * p.ksplits;
+  const int tiles_all = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+  const int total = p.hyb ? p.hyb_full + (tiles_all - p.hyb_full) * p.ksplits : tiles_all * p.ksplits;
   int grid = fixed_grid > 0 ? fixed_grid : (total < ctx->sm_count ? total : ctx->sm_count);
   if (p.colsum) grid = (grid / p.n_tiles) * p.n_tiles;      // every tile of a CTA has the same channel tile
   switch (block_n) {
@@ -1920,6 +2000,31 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   if (p.tma_store) {
     rc = encode_act_map(ctx, &maps.c, y, N, H, W, Cn, Cn, (int64_t)W * Cn, (int64_t)H * W * Cn, b.bw, b.bh, b.bn);
     if (rc) return rc;
+  }
+  // Hybrid schedule for a partly filled last wave (conv5_x: 180 tiles on 148 SMs, conv6/conv7 forward: 368): whole waves
+  // run as they are, the remaining tiles are split in K so that their units fill one more (short) wave.
+  {
+    const int sm = ctx->sm_count;
+    const int waves = tiles / sm, rem = tiles % sm;
+    int ksr = rem > 0 ? sm / rem : 0;
+    if (ksr > p.kchunks) ksr = p.kchunks;            // ksplits <= kchunks <= k-steps of any tile: no piece is empty
+    if (ksr > 8) ksr = 8;
+    if (ctx->hybrid && waves >= 1 && waves <= 4 && ksr >= 2 && p.ntaps * p.kchunks >= 8 * ksr) {
+      const size_t slice = (size_t)N * H * W * Cn;
+      rc = ensure_workspace(ctx, sizeof(float) * slice * ksr);
+      if (rc) return rc;
+      p.hyb = 1; p.hyb_full = tiles - rem; p.ksplits = ksr;
+      p.ws = (float*)ctx->ws;
+      p.ws_slice = (int64_t)slice;
+      rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+      if (rc) return rc;
+      int64_t blocks = ceil_div64((int64_t)rem * p.rows * (block_n / 8), 256);
+      if (blocks > (int64_t)sm * 8) blocks = (int64_t)sm * 8;
+      epilogue_finish_tiles_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)ctx->ws, p, p.hyb_full, rem, block_n);
+      SEGK_LAUNCHED(ctx, "igemm hybrid finish");
+      if (colsum_out) return colsum_fallback(ctx, y, (int64_t)N * H * W, Cn, colsum_out, (cudaStream_t)stream);
+      return SEGK_OK;
+    }
   }
   if (colsum_out) {
     const int total = tiles < ctx->sm_count ? tiles : ctx->sm_count;
@@ -2472,6 +2577,7 @@ int segk_tc_init(segk_ctx* ctx) {
   ctx->tma_store = env_int("SEGK_TMA_STORE", 1);
   ctx->slab3 = env_int("SEGK_SLAB3", 1);
   ctx->teamk = env_int("SEGK_TEAMK", 1);
+  ctx->hybrid = env_int("SEGK_HYBRID", 0);
   cudaError_t e = cudaSuccess;
 #define SEGK_SMEM_ATTR(kern, bytes) \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)

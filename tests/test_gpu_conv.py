@@ -33,6 +33,7 @@ CONV_SHAPES = [
     (2, 40, 144, 128, 256, 3),
     (1, 7, 9, 64, 192, 3),       # ragged box, Cout = 3 x 64
     (1, 5, 18, 256, 128, 7),     # few tiles, long K walk -> split-K path (fwd and dgrad)
+    (4, 48, 100, 128, 256, 3),   # 150 tiles on 148 SMs: a second, nearly empty wave
 ]
 
 
@@ -417,3 +418,39 @@ def test_team_stream_k_fwd_dgrad_and_wgrad_box_skipping(ops, cuda_device, shape)
     ops.conv2d_wgrad(xd, dyd, dw, k, k)
     torch.cuda.synchronize()
     assert_close(host(dw), wtt.grad.numpy(), TOL_F32, f"wgrad with box skipping {shape}")
+
+
+@pytest.mark.parametrize("shape", [(4, 48, 100, 128, 256, 3), (32, 10, 36, 128, 512, 3), (8, 16, 16, 4096, 2560, 1)])
+def test_hybrid_schedule_matches_plain_waves(ops, cuda_device, shape):
+    """A partly filled last wave (150 / 180 tiles on 148 SMs): whole tiles leave through the TMA-store epilogue, the
+    remainder tiles as K-split fp32 partial sums finished by epilogue_finish_tiles_kernel (channel-tile-fastest and
+    pixel-tile-fastest orders).  Against the oracle, against the plain schedule, and deterministic."""
+    n, h, w, ci, co, k = shape
+    x, wt, b = _conv_case(shape, 60)
+    res = bf16_grid(np.random.default_rng(61).standard_normal((n, h, w, co)))
+    ref = T.relu(T.bias_add(T.conv2d_same(torch.tensor(x), torch.tensor(wt)), torch.tensor(b)) + torch.tensor(res)).numpy()
+    wk, _ = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    xd, bd, rd = dev_bf16(x, cuda_device), dev_f32(b, cuda_device), dev_bf16(res, cuda_device)
+    out = {}
+    try:
+        for mode in (1, 0):
+            ops.ctx.set_tuning("hybrid", mode)
+            y = torch.full((n, h, w, co), 7.0, dtype=torch.bfloat16, device=cuda_device)
+            n0 = ops.ctx.launches
+            ops.conv2d_fwd(xd, wk, bd, y, k, k, relu=True, residual=rd)
+            torch.cuda.synchronize()
+            out[mode] = (y, ops.ctx.launches - n0)
+            assert_close(host(y), ref, TOL_BF16, f"hybrid={mode} fwd {shape}")
+        assert out[1][1] == 2 and out[0][1] == 1, (out[1][1], out[0][1])       # igemm + finish vs igemm alone
+        y2 = torch.empty_like(out[1][0])
+        ops.ctx.set_tuning("hybrid", 1)
+        ops.conv2d_fwd(xd, wk, bd, y2, k, k, relu=True, residual=rd)
+        torch.cuda.synchronize()
+        assert torch.equal(y2, out[1][0])
+        # fp32 output through the same path
+        yf = torch.full((n, h, w, co), 7.0, dtype=torch.float32, device=cuda_device)
+        ops.conv2d_fwd(xd, wk, bd, yf, k, k, relu=True, residual=rd)
+        torch.cuda.synchronize()
+        assert_close(host(yf), ref, TOL_F32, f"hybrid fwd f32 {shape}")
+    finally:
+        ops.ctx.set_tuning("hybrid", 0)
