@@ -75,6 +75,18 @@ int segk_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* b
                     int kh, int kw, unsigned flags, void* stream);
 
 /*
+ * conv_layer followed by max_pool (FCN.py:54-56, 58-60, 62-65, 67-71, 73-76: conv -> ReLU -> max_pool 2x2/2, the
+ * max_pool helper of FCN.py:161-163): the same forward conv with the pool computed in its epilogue from the staged
+ * bf16 tile.  pooled [N,H/2,W/2,Cout] bf16 and idx [N,H/2,W/2,Cout] u8 (first-max window position 0..3, the layout
+ * of segk_maxpool2x2_fwd) are bit-identical to segk_conv2d_fwd + segk_maxpool2x2_fwd.  pool_only != 0: y need not be
+ * written (FCN-8s training never reads the pre-pool tensor again; y must still be a valid buffer -- geometries
+ * whose tiles do not hold whole 2x2 windows run the two kernels one after the other).
+ */
+int segk_conv2d_fwd_pool(segk_ctx* ctx, const void* x, const void* wk, const float* bias, void* y,
+                         void* pooled, uint8_t* idx, int pool_only, int N, int H, int W, int Cin,
+                         int Cout, int kh, int kw, unsigned flags, void* stream);
+
+/*
  * Conv2DBackpropInput of the above (part of what `optimizer.minimize` emits, FCN.py:340):
  *   dx = dy (*) rot180(W);  wd = dgrad-layout weights [kh*kw (taps reversed)][Cout/64][Cin][64] bf16.
  *   dx = ((acc + residual) masked by relu_mask > 0) * scale, where

@@ -128,6 +128,12 @@ struct IgemmParams {
   int ts, ts_G, ts_tiles, ts_total;
   int ts_prefix[kMaxCols + 1];
   int hyb, hyb_full; // hyb = 1: hybrid schedule -- tiles [0, hyb_full) whole, the rest in ksplits pieces
+  // max_pool 2x2/2 of the output fused into the epilogue (conv -> ReLU -> pool, FCN.py:56,60,65,71,76): pooled values
+  // [N,H/2,W/2,ldo] bf16 and first-max indices (u8) computed from the staged bf16 tile; pool_only = 1 skips the store of
+  // the full-resolution tensor (nothing in FCN-8s training reads it again)
+  bf16* pool_out;
+  uint8_t* pool_idx;
+  int pool_only;
 };
 
 struct PipeState {
@@ -382,6 +388,52 @@ __device__ __forceinline__ void epilogue_apply_store(const P& p, float (&v)[32],
   }
 }
 
+// 2x2 / stride-2 max-pool of one staged tile: `sbuf` holds the tile's bf16 outputs as written by epilogue_apply_store
+// (row = box-linear pixel index at pitch bw, 128 B = 64 channels per row, 16-byte pieces XOR-swizzled by row & 7).
+// Item = (pooled pixel of the box, 16-byte piece): the first maximal element under a strict '>' scan in (dy,dx)
+// row-major order, exactly as maxpool_fwd_kernel (elementwise.cu) computes it from the stored tensor -- the values
+// pooled here are the same rounded bf16 values, so the fused and the two-kernel paths agree bit for bit.
+template <class P>
+__device__ __forceinline__ void epilogue_pool_store(const P& p, const uint8_t* sbuf, int item, int bw, int bh, int x0, int y0,
+                                                    int n0, int ch0) {
+  const int pc = item & 7;
+  int pp = item >> 3;
+  const int hw = bw >> 1, hh = bh >> 1;
+  const int ppx = pp % hw;
+  pp /= hw;
+  const int ppy = pp % hh;
+  const int pn = pp / hh;
+  const int ix = x0 + 2 * ppx, iy = y0 + 2 * ppy, n = n0 + pn;
+  if (ix >= p.W || iy >= p.H || n >= p.N) return;
+  const int r00 = (pn * bh + 2 * ppy) * bw + 2 * ppx;
+  const int rows[4] = {r00, r00 + 1, r00 + bw, r00 + bw + 1};
+  uint4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const uint4*>(sbuf + rows[k] * 128 + ((pc ^ (rows[k] & 7)) << 4));
+  uint32_t outw[4];
+  uint32_t idxw[2] = {0u, 0u};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t w0 = (&v[0].x)[j];
+    float2 best = unpack_bf16x2(w0);
+    uint32_t bits_lo = w0 & 0xffffu, bits_hi = w0 >> 16;
+    uint32_t k_lo = 0, k_hi = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const uint32_t wk = (&v[k].x)[j];
+      const float2 f = unpack_bf16x2(wk);
+      if (f.x > best.x) { best.x = f.x; bits_lo = wk & 0xffffu; k_lo = k; }
+      if (f.y > best.y) { best.y = f.y; bits_hi = wk >> 16; k_hi = k; }
+    }
+    outw[j] = bits_lo | (bits_hi << 16);
+    const int e = 2 * j;
+    idxw[e >> 2] |= (k_lo << (8 * (e & 3))) | (k_hi << (8 * ((e + 1) & 3)));
+  }
+  const int64_t o = (((int64_t)n * (p.H >> 1) + (iy >> 1)) * (p.W >> 1) + (ix >> 1)) * p.ldo + ch0 + pc * 8;
+  *reinterpret_cast<uint4*>(p.pool_out + o) = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+  *reinterpret_cast<uint2*>(p.pool_idx + o) = make_uint2(idxw[0], idxw[1]);
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const TapTable taps) {
@@ -622,11 +674,18 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
         if (do_tma) {
           fence_proxy_async();                        // generic-proxy smem writes -> visible to the TMA engine
           named_bar_sync(1, kEpiThreads);
-          if (ep_leader) {
+          if (ep_leader && !p.pool_only) {
             tma_store_4d(&maps.c, sbuf, t.nt * BLOCK_N + g0, t.x0, t.y0, t.n0);
             tma_store_commit();
           }
           ++sg;
+          // (the staging buffer is rewritten two groups later, behind that group's barrier: every thread has finished
+          // these reads by then)
+          if (p.pool_out) {
+            const int items = (p.rows >> 2) * 8;
+            for (int item = (int)threadIdx.x - 64; item < items; item += kEpiThreads)
+              epilogue_pool_store(p, sbuf, item, p.bw, p.bh, t.x0, t.y0, t.n0, t.nt * BLOCK_N + g0);
+          }
         }
       }
       tc_fence_before();
@@ -690,6 +749,9 @@ struct SlabParams {
   int ldo;
   int tma_store;
   float* colsum;          // see IgemmParams
+  bf16* pool_out;         // fused 2x2 max-pool of the output (see IgemmParams)
+  uint8_t* pool_idx;
+  int pool_only;
   void* out;
   int out_f32;
   const float* bias;
@@ -869,11 +931,15 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
         if (p.tma_store) {
           fence_proxy_async();
           named_bar_sync(1, kEpiThreads);
-          if (ep_leader) {
+          if (ep_leader && !p.pool_only) {
             tma_store_4d(&maps.c, sbuf, nt * BLOCK_N + g0, x0, y0, n);
             tma_store_commit();
           }
           ++sg;
+          if (p.pool_out) {
+            for (int item = (int)threadIdx.x - 64; item < (kSlabWV / 2) * (kSlabH / 2) * 8; item += kEpiThreads)
+              epilogue_pool_store(p, sbuf, item, kSlabWV, kSlabH, x0, y0, n, nt * BLOCK_N + g0);
+          }
         }
       }
       tc_fence_before();
@@ -1075,9 +1141,14 @@ slab3_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
       if (p.tma_store) {
         fence_proxy_async();
         named_bar_sync(1 + grp, 128);
-        if (ep_leader) {
+        if (ep_leader && !p.pool_only) {
           tma_store_4d(&maps.c, sbuf, nt * 64, x0, y0, n);
           tma_store_commit();
+        }
+        // (the group's next tile starts behind a barrier: these reads are done before the buffer is rewritten)
+        if (p.pool_out) {
+          for (int item = (int)threadIdx.x - 64 - grp * 128; item < (kSlabWV / 2) * (kSlabH / 2) * 8; item += 128)
+            epilogue_pool_store(p, sbuf, item, kSlabWV, kSlabH, x0, y0, n, nt * 64);
         }
       }
     }
@@ -1644,14 +1715,17 @@ int64_t active_taps_1d(int n, int b, int k) {
 // Pick a pixel box bw x bh x bn with at most `max_rows` rows (exactly, when `exact`) that covers
 // [N,H,W] with the least work = sum over tiles of active taps (kh = kw = 1: the tile count);
 // ties -> wider bw (longer contiguous runs for TMA).
-Box choose_box(int N, int H, int W, int max_rows, bool exact, int lim_h = 0, int lim_w = 0, int kh = 1, int kw = 1) {
+Box choose_box(int N, int H, int W, int max_rows, bool exact, int lim_h = 0, int lim_w = 0, int kh = 1, int kw = 1,
+               bool even = false) {
   Box best{0, 0, 0, 0, 0};
   int64_t best_cost = -1;
   if (lim_h <= 0) lim_h = H;
   if (lim_w <= 0) lim_w = W;
   for (int bw = 1; bw <= lim_w && bw <= max_rows && bw <= 256; ++bw) {
     const int64_t ax = active_taps_1d(W, bw, kw);
+    if (even && (bw & 1)) continue;                 // fused 2x2 pool: whole windows per box
     for (int bh = 1; bh <= lim_h && bw * bh <= max_rows && bh <= 256; ++bh) {
+      if (even && (bh & 1)) continue;
       int bn = max_rows / (bw * bh);
       // exact boxes may run past the batch (TMA zero-fills the out-of-bounds images)
       if (!exact && bn > N) bn = N;
@@ -1786,9 +1860,17 @@ bool slab_applicable(const segk_ctx* ctx, int N, int H, int W, int Ck, int Cn, i
   return Cn <= 128 && (int64_t)H * W >= 4096;
 }
 
+// fused 2x2 max-pool of a forward conv's output (segk_conv2d_fwd_pool)
+struct PoolArgs {
+  void* pooled;
+  uint8_t* idx;
+  int pool_only;
+  bool fused;      // out: the launch produced pooled / idx itself
+};
+
 int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, const float* bias, const void* residual,
               const void* mask, float scale, int relu, int out_f32, void* y, int N, int H, int W, int Ck, int Cn,
-              void* stream, float* colsum_out) {
+              void* stream, float* colsum_out, PoolArgs* pool = nullptr) {
   // Ck = 64: kx-fused N = 192 MMAs on resident weights (slab3_kernel), 64-channel output tiles.  Measured
   // (tools/time_n64.py, B=32 160x576): 64 -> 64 forward 228 vs 297 us, its dgrad 345 vs 372 us; with two
   // channel tiles (64 -> 128) it is a wash (116 vs 112 us), so the tap-wise slab keeps those.  slab3 = 2 forces it.
@@ -1819,6 +1901,10 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
   if (p.tma_store) {
     rc = encode_act_map(ctx, &maps.c, y, N, H, W, Cn, Cn, (int64_t)W * Cn, (int64_t)H * W * Cn, kSlabWV, kSlabH, 1);
     if (rc) return rc;
+  }
+  if (pool && p.tma_store && !colsum_out && (W & 1) == 0) {      // 4 x 30 tiles at even origins: whole pool windows
+    p.pool_out = (bf16*)pool->pooled; p.pool_idx = pool->idx; p.pool_only = pool->pool_only;
+    pool->fused = true;
   }
   const int total = N * p.tiles_h * p.tiles_w * p.n_tiles;
   int grid = total < ctx->sm_count ? total : ctx->sm_count;
@@ -1870,7 +1956,7 @@ void conv_taps(TapTable& t, int kh, int kw, int rate = 1) {
 // shared body of conv fwd and dgrad: y[N,H,W,Cn] = epilogue( sum_taps x[.. + tap][Ck] * wt[tap][Cn][Ck] )
 int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, const float* bias, const void* residual,
                const void* mask, float scale, int relu, int out_f32, void* y, int N, int H, int W, int Ck, int Cn,
-               int kh, int kw, void* stream, float* colsum_out = nullptr, int rate = 1) {
+               int kh, int kw, void* stream, float* colsum_out = nullptr, int rate = 1, PoolArgs* pool = nullptr) {
   SEGK_REQUIRE(ctx, x && wt && y, "%s: null pointer", what);
   SEGK_REQUIRE(ctx, N > 0 && H > 0 && W > 0, "%s: empty tensor", what);
   SEGK_REQUIRE(ctx, Ck % 64 == 0 && Cn % 64 == 0 && Ck > 0 && Cn > 0,
@@ -1883,8 +1969,14 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   SEGK_REQUIRE(ctx, !colsum_out || !out_f32, "%s: column sums need a bf16 output", what);
   SEGK_REQUIRE(ctx, rate >= 1 && (kh / 2) * rate <= 127 && (kw / 2) * rate <= 127, "%s: dilation rate %d out of range", what, rate);
   if (rate == 1 && slab_applicable(ctx, N, H, W, Ck, Cn, kh, kw))
-    return conv_slab(ctx, what, x, wt, bias, residual, mask, scale, relu, out_f32, y, N, H, W, Ck, Cn, stream, colsum_out);
-  const Box b = choose_box(N, H, W, kBlockM, false, 0, 0, kh, kw);
+    return conv_slab(ctx, what, x, wt, bias, residual, mask, scale, relu, out_f32, y, N, H, W, Ck, Cn, stream, colsum_out, pool);
+  // the fused pool needs boxes of whole 2x2 windows, the TMA-store epilogue and unsplit tiles
+  bool want_pool = pool && !out_f32 && ctx->tma_store && !colsum_out && (H & 1) == 0 && (W & 1) == 0;
+  Box b = choose_box(N, H, W, kBlockM, false, 0, 0, kh, kw, want_pool);
+  if (want_pool && b.rows <= 0) {
+    want_pool = false;
+    b = choose_box(N, H, W, kBlockM, false, 0, 0, kh, kw);
+  }
   SEGK_REQUIRE(ctx, b.rows > 0, "%s: no pixel box for %dx%dx%d", what, N, H, W);
   const int block_n = pick_block_n(ctx, Cn);
   TensorMaps maps;
@@ -1915,6 +2007,15 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   // few output tiles but a long K walk (conv6 dgrad: 48 tiles x 3136 k-steps): split K across SMs
   const int tiles = p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
   const int force_ks = ctx->force_ksplit;
+  if (want_pool) {
+    // (few-tile layers are not split when the pool is fused: their tiles are small anyway)
+    p.tma_store = 1;
+    rc = encode_act_map(ctx, &maps.c, y, N, H, W, Cn, Cn, (int64_t)W * Cn, (int64_t)H * W * Cn, b.bw, b.bh, b.bn);
+    if (rc) return rc;
+    p.pool_out = (bf16*)pool->pooled; p.pool_idx = pool->idx; p.pool_only = pool->pool_only;
+    pool->fused = true;
+    return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+  }
   if ((tiles * 2 <= ctx->sm_count && p.ntaps * p.kchunks >= 32 && p.kchunks >= 2) || force_ks > 0) {
     // one wave of work units.  Measured (tools/time_conv6.py, conv6 dgrad: 50 tiles x 2240 k-steps): 2 splits
     // 483 us, 1: 766, 3: 596, 5: 562, 8: 692, 14: 918 -- more splits than one wave lets the m-tiles that share
@@ -2423,6 +2524,19 @@ int segk_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* b
   if (!ctx) return SEGK_EINVAL;
   return conv_igemm(ctx, "conv2d_fwd", x, wk, bias, residual, nullptr, 1.f, (flags & SEGK_EPI_RELU) ? 1 : 0,
                     (flags & SEGK_EPI_OUT_F32) ? 1 : 0, y, N, H, W, Cin, Cout, kh, kw, stream);
+}
+
+int segk_conv2d_fwd_pool(segk_ctx* ctx, const void* x, const void* wk, const float* bias, void* y, void* pooled, uint8_t* idx,
+                         int pool_only, int N, int H, int W, int Cin, int Cout, int kh, int kw, unsigned flags, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, y && pooled && idx, "conv2d_fwd_pool: null pointer");
+  SEGK_REQUIRE(ctx, !(flags & SEGK_EPI_OUT_F32), "conv2d_fwd_pool: bf16 output only");
+  SEGK_REQUIRE(ctx, (H & 1) == 0 && (W & 1) == 0, "conv2d_fwd_pool: need even H, W (got %dx%d)", H, W);
+  PoolArgs pool{pooled, idx, pool_only ? 1 : 0, false};
+  const int rc = conv_igemm(ctx, "conv2d_fwd_pool", x, wk, bias, nullptr, nullptr, 1.f, (flags & SEGK_EPI_RELU) ? 1 : 0, 0, y, N, H,
+                            W, Cin, Cout, kh, kw, stream, nullptr, 1, &pool);
+  if (rc || pool.fused) return rc;
+  return segk_maxpool2x2_fwd(ctx, y, pooled, idx, N, H, W, Cout, stream);     // (tile geometry without whole windows)
 }
 
 int segk_conv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, const void* residual,

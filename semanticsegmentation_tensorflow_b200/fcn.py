@@ -265,6 +265,8 @@ class FCN(_Feeds):
         self.dropout_seed = dropout_seed
         self.step_count = 0
         self.injected_masks = None     # {"dropout6": u8 tensor, "dropout7": ...} for parity runs
+        self.fuse_pool = True          # max_pool in the epilogue of the conv in front of it (segk_conv2d_fwd_pool)
+        self.keep_prepool = False      # True: also store the pre-pool conv outputs (per-activation parity tests)
         self.x = x
         self._alloc()
         self._ran_forward = False
@@ -349,13 +351,23 @@ class FCN(_Feeds):
     def forward(self):
         ops, V, act = self.ops, self.vars, self.act
         cur = self.x
-        for l in self.layers:
+        L = self.layers
+        pooled_by_conv = None
+        for i, l in enumerate(L):
             out = act[l.name]
             if l.kind == "pool":
-                ops.maxpool_fwd(cur, out, self.idx[l.name])
+                if pooled_by_conv != l.name:
+                    ops.maxpool_fwd(cur, out, self.idx[l.name])
             elif l.kind == "conv":
                 b = V.param(f"{l.name}/{l.bias_name}")
-                if l.path == "tc":
+                nxt = L[i + 1] if i + 1 < len(L) else None
+                if l.path == "tc" and self.fuse_pool and nxt is not None and nxt.kind == "pool" and l.relu and not l.dropout:
+                    # conv -> ReLU -> max_pool (FCN.py:54-76): the pool runs in the conv's epilogue; nothing reads the
+                    # pre-pool tensor again (MaxPoolGrad routes by the stored index, ReluGrad masks by the pooled value)
+                    ops.conv2d_fwd_pool(cur, V.wk[l.name], b, out, act[nxt.name], self.idx[nxt.name], l.k, l.k, relu=True,
+                                        pool_only=not self.keep_prepool)
+                    pooled_by_conv = nxt.name
+                elif l.path == "tc":
                     ops.conv2d_fwd(cur, V.wk[l.name], b, out, l.k, l.k, relu=l.relu)
                 elif l.path == "first":
                     ops.conv2d_first_fwd(cur, V.wk[l.name], b, out, l.k, l.k, relu=l.relu)

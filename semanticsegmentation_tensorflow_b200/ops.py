@@ -327,6 +327,15 @@ class Ops:
         return dw
 
     # ---- HBM-bound kernels ----------------------------------------------------------------
+    def conv2d_fwd_pool(self, x, wk, bias, y, pooled, idx, kh, kw, relu=True, pool_only=False):
+        """conv_layer + max_pool 2x2 in one launch (pool in the conv epilogue); `pool_only`: y need not be written."""
+        n, h, w, cin = x.shape
+        cout = y.shape[3]
+        self._w(conv_flops(n, h, w, cin, cout, kh, kw), "flop")
+        self.call("segk_conv2d_fwd_pool", _p(x), _p(wk), _p(bias), _p(y), _p(pooled), _p(idx), int(pool_only), n, h, w, cin,
+                  cout, kh, kw, EPI_RELU if relu else 0, _stream())
+        return pooled, idx
+
     def maxpool_fwd(self, x, y, idx):
         n, h, w, c = x.shape
         self._w(2.0 * x.numel() + 3.0 * y.numel(), "byte")

@@ -116,6 +116,7 @@ def full_net(cuda_device):
 
 def test_full_network_fc4096_all_gradients_hard_floor(cuda_device, full_net):
     net, variables, x, lab = full_net
+    net.keep_prepool = True          # conv5_3 is compared below (default: only its pooled output is stored)
     net.forward()
     loss = net.loss(torch.as_tensor(lab).to(cuda_device), with_grad=True)
     net.backward()

@@ -454,3 +454,43 @@ def test_hybrid_schedule_matches_plain_waves(ops, cuda_device, shape):
         assert_close(host(yf), ref, TOL_F32, f"hybrid fwd f32 {shape}")
     finally:
         ops.ctx.set_tuning("hybrid", 0)
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 16, 60, 64, 64, 3),      # slab3 (4 x 30 tiles, Cin = Cout = 64)
+    (2, 64, 96, 64, 128, 3),     # slab_kernel<128>
+    (3, 20, 72, 128, 256, 3),    # igemm<256>, even box
+    (2, 10, 36, 256, 512, 3),    # igemm<256>, two channel tiles, few tiles (no split-K when the pool is fused)
+    (1, 8, 62, 64, 64, 3),       # ragged right edge (62 = 2 x 30 + 2)
+    (2, 6, 10, 64, 192, 1),      # 1x1, Cout = 3 x 64
+])
+def test_conv2d_fwd_pool_bit_exact_vs_two_kernels(ops, cuda_device, shape):
+    """conv -> ReLU -> max_pool 2x2 (FCN.py:54-76) with the pool in the conv epilogue: pooled values and first-max
+    indices bit-identical to segk_conv2d_fwd + segk_maxpool2x2_fwd (tie-heavy: ReLU zeros), y identical when stored,
+    untouched with pool_only."""
+    n, h, w, ci, co, k = shape
+    x, wt, b = _conv_case(shape, 70)
+    wk, _ = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    xd, bd = dev_bf16(x, cuda_device), dev_f32(b - 0.3, cuda_device)          # shifted bias: many ReLU zeros -> ties
+    y0 = torch.empty((n, h, w, co), dtype=torch.bfloat16, device=cuda_device)
+    ops.conv2d_fwd(xd, wk, bd, y0, k, k, relu=True)
+    # fused, pre-pool tensor stored too: the pool of exactly that tensor (the plain conv may take a split-K schedule on
+    # few-tile shapes, i.e. another fp32 summation order: y is compared to tolerance, the pool bit for bit)
+    y1 = torch.full_like(y0, 7.0)
+    p1 = torch.full((n, h // 2, w // 2, co), 7.0, dtype=torch.bfloat16, device=cuda_device)
+    i1 = torch.full((n, h // 2, w // 2, co), 9, dtype=torch.uint8, device=cuda_device)
+    ops.conv2d_fwd_pool(xd, wk, bd, y1, p1, i1, k, k, relu=True, pool_only=False)
+    p0, i0 = torch.empty_like(p1), torch.empty_like(i1)
+    ops.maxpool_fwd(y1, p0, i0)
+    torch.cuda.synchronize()
+    assert_close(host(y1), host(y0), TOL_BF16, f"fused-pool conv output {shape}")
+    assert torch.equal(p1, p0), f"pooled values {shape}"
+    assert torch.equal(i1, i0), f"pool indices {shape}"
+    # pool only: same pooled tensor and indices, y untouched
+    y2 = torch.full_like(y0, 7.0)
+    p2, i2 = torch.full_like(p1, 7.0), torch.full_like(i1, 9)
+    ops.conv2d_fwd_pool(xd, wk, bd, y2, p2, i2, k, k, relu=True, pool_only=True)
+    torch.cuda.synchronize()
+    assert torch.equal(p2, p1) and torch.equal(i2, i1), f"pool_only {shape}"
+    assert bool((y2 == 7.0).all()), "pool_only must not write the pre-pool tensor"
+    assert float((p0 == 0).float().mean()) > 0.05          # the tie case is exercised
