@@ -230,6 +230,16 @@ int segk_pack_matrix(segk_ctx* ctx, const float* w, void* cp, void* tr, int T, i
  * weight gradient; beta is the conv epilogue's bias.  in/out fp32 [rows][C], out may alias in. */
 int segk_scale_columns(segk_ctx* ctx, const float* in, const float* scale, float mult, float* out,
                        int64_t rows, int C, void* stream);
+/* Batch_Normalization gradients without a pass over activations (utils.py:300-301, inference-mode affine folded
+ * into the conv weights W' = W * gamma * mult): given the weight gradient of the folded conv in gw [rows][C] (HWIO
+ * flattened, C = Cout) and the unfolded weights w, writes dgamma[c] = mult * sum_k w[k][c] * gw[k][c] and rescales
+ * gw in place to the gradient of the unfolded weights (gw[k][c] *= gamma[c] * mult).  d(beta) is the BiasAddGrad
+ * of dz (segk_bias_grad).  workspace: >= 4 * C * min(ceil(rows / 64), ceil(2 * SMs / ceil(C / 32))) bytes of
+ * device scratch for the per-block partial rows (deterministic two-stage sum). */
+int segk_bn_unfold_grads(segk_ctx* ctx, float* gw, const float* w, const float* gamma, float mult,
+                         float* dgamma, void* workspace, size_t workspace_bytes, int64_t rows, int C,
+                         void* stream);
+
 /* dgamma[c] = sum_r dz[r][c] * (y[r][c] - beta[c]) / gamma[c]  (dz, y bf16 [rows][C]; dz already
  * carries the ReLU mask, so (y - beta)/gamma' is the raw conv output wherever dz != 0).
  * dbeta (nullable): also dbeta[c] = sum_r dz[r][c] (the BiasAddGrad of the same dz) from the same pass.

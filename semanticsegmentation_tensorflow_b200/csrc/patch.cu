@@ -146,6 +146,55 @@ __global__ void __launch_bounds__(kThreads) scale_columns_kernel(const float* __
     out[i] = in[i] * __ldg(scale + (int)(i % C)) * mult;
 }
 
+// Gradients of the folded BN scale from the WEIGHT gradient (no pass over activations):  y = s_c (W * x)_c + beta_c with
+// s_c = gamma_c * mult is computed as a conv with W'[k][c] = W[k][c] s_c, and the wgrad kernels produce dW'.  Then
+//   dL/ds_c = sum_pix dz_c (W * x)_c = sum_k W[k][c] dW'[k][c]      ->  dgamma[c] = mult * sum_k W[k][c] dW'[k][c]
+//   dL/dW[k][c] = dW'[k][c] s_c                                      (in place)
+// Two stages, fixed summation order (deterministic): grid (C/32, S) blocks each take a slice of the rows (8 row lanes x 4
+// rows in flight) and write one partial row; the finish kernel adds the S partial rows.
+__global__ void __launch_bounds__(kThreads) bn_unfold_grads_kernel(float* __restrict__ gw, const float* __restrict__ w,
+                                                                   const float* __restrict__ gamma, float mult,
+                                                                   float* __restrict__ partial, int64_t rows, int C,
+                                                                   int rows_per_block) {
+  __shared__ float sh[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    const float s = __ldg(gamma + c) * mult;
+    for (int64_t r = r0 + rl; r < r1; r += 32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t rr = r + 8 * j;
+        if (rr < r1) {
+          const float g = gw[rr * C + c];
+          acc[j] += g * __ldg(w + rr * C + c);
+          gw[rr * C + c] = g * s;
+        }
+      }
+    }
+  }
+  sh[rl][cl] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sh[k][cl];
+    partial[(int64_t)blockIdx.y * C + c] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) bn_unfold_finish_kernel(const float* __restrict__ partial, float* __restrict__ dgamma,
+                                                                    float mult, int S, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = 0.f;
+  for (int s = 0; s < S; ++s) t += partial[(int64_t)s * C + c];
+  dgamma[c] = t * mult;
+}
+
 // partial[b][0][c] = sum over the block's rows of dz[r][c] * (y[r][c] - beta[c])
 // partial[b][1][c] = sum over the block's rows of dz[r][c]            (BiasAddGrad = d beta, when kBeta)
 // (fixed-order second stage: bn_gamma_finish_kernel divides the first by gamma)
@@ -437,6 +486,28 @@ int segk_scale_columns(segk_ctx* ctx, const float* in, const float* scale, float
   const int64_t n = rows * C;
   scale_columns_kernel<<<sgrid(ctx, n), kThreads, 0, (cudaStream_t)stream>>>(in, scale, mult, out, n, C);
   SEGK_LAUNCHED(ctx, "scale_columns");
+  return SEGK_OK;
+}
+
+int segk_bn_unfold_grads(segk_ctx* ctx, float* gw, const float* w, const float* gamma, float mult, float* dgamma,
+                         void* workspace, size_t workspace_bytes, int64_t rows, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, gw && w && gamma && dgamma && workspace && rows > 0 && C > 0, "bn_unfold_grads: bad args");
+  const int cb = (C + 31) / 32;
+  // enough blocks to fill the GPU, at least 64 rows each
+  int S = (int)((2 * (int64_t)ctx->sm_count + cb - 1) / cb);
+  const int64_t max_s = (rows + 63) / 64;
+  if (S > max_s) S = (int)max_s;
+  if (S < 1) S = 1;
+  const int rpb = (int)((rows + S - 1) / S);
+  S = (int)((rows + rpb - 1) / rpb);
+  SEGK_REQUIRE(ctx, workspace_bytes >= sizeof(float) * (size_t)S * C, "bn_unfold_grads: workspace too small (%zu < %zu)",
+               workspace_bytes, sizeof(float) * (size_t)S * C);
+  bn_unfold_grads_kernel<<<dim3(cb, S), kThreads, 0, (cudaStream_t)stream>>>(gw, w, gamma, mult, (float*)workspace, rows, C, rpb);
+  SEGK_LAUNCHED(ctx, "bn_unfold_grads");
+  bn_unfold_finish_kernel<<<(C + kThreads - 1) / kThreads, kThreads, 0, (cudaStream_t)stream>>>((const float*)workspace, dgamma, mult,
+                                                                                               S, C);
+  SEGK_LAUNCHED(ctx, "bn_unfold_finish");
   return SEGK_OK;
 }
 

@@ -285,6 +285,10 @@ class GraphNet(_Feeds):
         self.loss_sum = torch.zeros(2, dtype=torch.float32, device=dev)   # [sum, mean]
         self.xent_ws = self.ops.xent_workspace(npix, dev)
         self.bn_ws = torch.empty(8 << 20, dtype=torch.uint8, device=dev)
+        # per-block partial rows of segk_bn_unfold_grads: one for the wgrad stream (tensor-core layers), one for the main
+        # stream (first layer)
+        max_c = max([n.cout for n in self.nodes if n.kind == "conv"] + [64])
+        self.unfold_ws = [self.ops.bn_unfold_workspace(max_c, dev) for _ in range(2)]
         self.labels = torch.zeros((N, self.H, self.W), dtype=torch.uint8, device=dev)
 
     def _repack(self, ops, only=None):
@@ -319,12 +323,26 @@ class GraphNet(_Feeds):
     def _in(self, name):
         return self.x if name == "input" else self.act[name]
 
+    def _fusable_pool(self, n):
+        """The Max_Pooling node whose 2x2 pool can run in the epilogue of tensor-core conv `n`, and whether the pre-pool
+        tensor may stay unwritten (no other consumer; backward never reads it: d(gamma) comes from the weight gradient)."""
+        if not getattr(self, "fuse_pool", True) or n.kind != "conv" or self.route[n.name] != "tc":
+            return None, False
+        users = [m for m in self.nodes if n.name in m.inputs]
+        pools = [m for m in users if m.kind == "pool"]
+        if len(pools) != 1 or self.act[n.name].dtype != torch.bfloat16:
+            return None, False
+        only = len(users) == 1 and not getattr(self, "keep_prepool", False)
+        return pools[0], only
+
     def forward(self):
         ops, V = self.ops, self.vars
+        pooled = set()
         for n in self.nodes:
             out = self.act[n.name]
             if n.kind == "pool":
-                ops.maxpool_fwd(self._in(n.inputs[0]), out, self.idx[n.name])
+                if n.name not in pooled:
+                    ops.maxpool_fwd(self._in(n.inputs[0]), out, self.idx[n.name])
             elif n.kind == "concat":
                 off = 0
                 for i in n.inputs:
@@ -335,7 +353,12 @@ class GraphNet(_Feeds):
                 ops.deconv2d_fwd(self._in(n.inputs[0]), V.wk[n.name], self._bias(n), out, n.k, n.stride, relu=n.relu)
             else:
                 x, r = self._in(n.inputs[0]), self.route[n.name]
-                if r == "tc":
+                pool, only = self._fusable_pool(n)
+                if pool is not None:          # Max_Pooling in the conv's epilogue (segk_conv2d_fwd_pool)
+                    ops.conv2d_fwd_pool(x, V.wk[n.name], self._bias(n), out, self.act[pool.name], self.idx[pool.name], n.k, n.k,
+                                        relu=n.relu, pool_only=only)
+                    pooled.add(pool.name)
+                elif r == "tc":
                     ops.conv2d_fwd(x, V.wk[n.name], self._bias(n), out, n.k, n.k, relu=n.relu)
                 elif r == "first":
                     ops.conv2d_first_fwd(x, V.wk[n.name], self._bias(n), out, n.k, n.k, relu=n.relu)
@@ -410,15 +433,21 @@ class GraphNet(_Feeds):
             dz = G
             if r == "small" and G.dtype == torch.float32:
                 dz = ops.cast_to_bf16(G, self.dlogits_bf16)
-            if n.bn:      # d(beta), d(gamma): one HBM-bound pass over dz and the activation, off the critical path
-                def bn_grads(dz=dz, n=n, G=G):
-                    if self.act[n.name].dtype == torch.float32:      # BN on the fp32 logits (SegNet.py:80-81)
+            # d(gamma) comes out of the weight gradient (segk_bn_unfold_grads below: dgamma = mult * sum_k W dW', no pass over
+            # activations); d(beta) is the BiasAddGrad of dz, off the critical path.  The fp32-logit BN of SegNet's
+            # head (SegNet.py:80-81) and non-tensor-core routes keep the activation pass.
+            gamma_from_dw = n.bn and n.kind == "conv" and r in ("tc", "first") and self.act[n.name].dtype != torch.float32
+            if n.bn:
+                def bn_grads(dz=dz, n=n, G=G, gamma_from_dw=gamma_from_dw):
+                    if self.act[n.name].dtype == torch.float32:
                         ops.bn_grads_f32(G, self.act[n.name], V.param(f"{n.bn_scope}/beta"), V.param(f"{n.bn_scope}/gamma"),
                                          V.grad(f"{n.bn_scope}/gamma"), V.grad(f"{n.bn_scope}/beta"), self.bn_ws)
-                        return
-                    ops.bn_gamma_grad(dz, self.act[n.name], V.param(f"{n.bn_scope}/beta"),
-                                      V.param(f"{n.bn_scope}/gamma"), V.grad(f"{n.bn_scope}/gamma"), self.bn_ws,
-                                      dbeta=V.grad(f"{n.bn_scope}/beta"))
+                    elif gamma_from_dw:
+                        ops.bias_grad(dz, V.grad(f"{n.bn_scope}/beta"))
+                    else:
+                        ops.bn_gamma_grad(dz, self.act[n.name], V.param(f"{n.bn_scope}/beta"),
+                                          V.param(f"{n.bn_scope}/gamma"), V.grad(f"{n.bn_scope}/gamma"), self.bn_ws,
+                                          dbeta=V.grad(f"{n.bn_scope}/beta"))
                 self.side.run(bn_grads)
             elif n.bias and r != "first":      # the fused first-layer wgrad also produces the bias gradient
                 self.side.run(lambda dz=dz, n=n: ops.bias_grad(dz, V.grad(f"{n.name}/biases")))
@@ -426,8 +455,11 @@ class GraphNet(_Feeds):
             # the wgrad stream, ordered after this point, launched behind the layer's dgrad
             wjob, wmark = None, None
 
-            def unfold(gw=gw, n=n):
-                if n.bn:
+            def unfold(gw=gw, n=n, gamma_from_dw=gamma_from_dw):
+                if gamma_from_dw:
+                    ops.bn_unfold_grads(gw, V.param(f"{n.name}/weights"), V.param(f"{n.bn_scope}/gamma"), BN_SCALE,
+                                        V.grad(f"{n.bn_scope}/gamma"), self.unfold_ws[0 if self.route[n.name] == "tc" else 1])
+                elif n.bn:
                     ops.scale_columns(gw, V.param(f"{n.bn_scope}/gamma"), BN_SCALE, gw)
 
             if n.kind == "deconv":

@@ -366,6 +366,17 @@ class Ops:
         self.call("segk_scale_columns", _p(w), _p(scale), float(mult), _p(out), w.numel() // c, c, _stream())
         return out
 
+    def bn_unfold_workspace(self, max_c, device):
+        return torch.empty(2 * self.ctx.sm_count * max(int(max_c), 32), dtype=torch.float32, device=device)
+
+    def bn_unfold_grads(self, gw, w, gamma, mult, dgamma, workspace):
+        """gw: gradient of the BN-folded weights -> (in place) gradient of the unfolded weights; dgamma from gw . w."""
+        c = gw.shape[-1]
+        self._w(12.0 * gw.numel(), "byte")
+        self.call("segk_bn_unfold_grads", _p(gw), _p(w), _p(gamma), float(mult), _p(dgamma), _p(workspace),
+                  workspace.numel() * workspace.element_size(), gw.numel() // c, c, _stream())
+        return dgamma
+
     def bn_gamma_grad(self, dz, y, beta, gamma, dgamma, workspace, dbeta=None):
         c = dz.shape[-1]
         self._w(4.0 * dz.numel(), "byte")

@@ -100,6 +100,7 @@ def _build(cuda_device, init):
     if init == "he":
         x = (x // 32).astype(np.uint8)
     net = UNet(torch.as_tensor(x).to(cuda_device), 2, variables=variables)
+    net.keep_prepool = True       # every activation is compared (default: a conv read only by its pool stores the pooled tensor only)
     return net, variables, x, lab
 
 
@@ -137,6 +138,7 @@ def test_unet_forward_and_gradients(cuda_device, init):
 def test_unet_training_steps(cuda_device):
     from semanticsegmentation_tensorflow_b200.fcn import AdamOptimizer
     net, variables, x, lab = _build(cuda_device, "he")
+    net.keep_prepool = False      # the default training path
     step = AdamOptimizer(1e-4).minimize(net)
     orc = UNetOracle(variables, bf16_storage=True)
     xd, ld = torch.as_tensor(x).to(cuda_device), torch.as_tensor(lab).to(cuda_device)
@@ -165,6 +167,7 @@ def _build_segnet(cuda_device):
     x, lab = synthetic_batch(N, H, W, seed=0, road_shaped=True)
     x = (x // 32).astype(np.uint8)
     net = SegNet(torch.as_tensor(x).to(cuda_device), 2, variables=variables)
+    net.keep_prepool = True
     return net, variables, x, lab
 
 
@@ -199,6 +202,7 @@ def test_segnet_forward_and_gradients(cuda_device):
 def test_segnet_training_steps(cuda_device):
     from semanticsegmentation_tensorflow_b200.fcn import AdamOptimizer
     net, variables, x, lab = _build_segnet(cuda_device)
+    net.keep_prepool = False      # the default training path: pre-pool conv outputs are not stored
     step = AdamOptimizer(1e-4).minimize(net)
     orc = UNetOracle(variables, bf16_storage=True, model="segnet")
     xd, ld = torch.as_tensor(x).to(cuda_device), torch.as_tensor(lab).to(cuda_device)
