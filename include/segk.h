@@ -262,13 +262,18 @@ int segk_bn_grads_f32(segk_ctx* ctx, const float* dz, const float* y, const floa
  *   y[r][c] = act(x[r][c] * scale[c] + shift[c]), c < C, with scale = gamma / sqrt(1 + 1e-3), shift = beta
  *   (physical arrays); relu != 0 applies max(., 0). */
 int segk_bn_act_fwd(segk_ctx* ctx, const void* x, int ldx, void* y, int ldy, const float* scale, const float* shift,
-                    int64_t rows, int C, int relu, void* stream);
+                    int64_t rows, int C, int relu, const uint8_t* drop_mask, float drop_keep, uint64_t drop_seed,
+                    void* stream);
 /* its gradient: g = dy * [y > 0]; dx (=, or += when accumulate) g * scale; dscale[c] = sum_r g * x, dshift[c] = sum_r g
  * (two-stage, deterministic).  dy / y have row pitch ldy, x / dx row pitch ldx.  workspace >= the _bytes() value. */
 size_t segk_bn_act_bwd_workspace_bytes(segk_ctx* ctx, int C);
 int segk_bn_act_bwd(segk_ctx* ctx, const void* dy, const void* y, int ldy, const void* x, void* dx, int ldx,
                     const float* scale, float* dscale, float* dshift, void* workspace, size_t workspace_bytes,
-                    int64_t rows, int C, int relu, int accumulate, void* stream);
+                    int64_t rows, int C, int relu, int accumulate, const uint8_t* drop_mask, float drop_keep,
+                    uint64_t drop_seed, void* stream);
+/* drop_keep in (0,1) (both calls): the Dropout in front of the BN (FCDenseNet.py:27-28: conv -> Dropout -> BN -> ReLU) is
+ * applied to x on the fly, with segk_dropout's keep pattern over the [rows][ldx] tensor x (drop_mask: injected u8 mask
+ * or NULL = Philox(drop_seed)); the backward also applies the DropoutGrad to dx (no accumulate).  drop_keep >= 1: none. */
 /* Avg_Pooling 2x2 / stride 2 / VALID (utils.py:309) and AvgPoolGrad (dx = dy / 4 on every window element) */
 int segk_avgpool2x2_fwd(segk_ctx* ctx, const void* x, int ldx, void* y, int ldy, int N, int H, int W, int C,
                         void* stream);
@@ -309,7 +314,11 @@ int segk_global_avgpool_bwd(segk_ctx* ctx, const void* dy, void* dx, int N, int 
  * the fused ReluGrad of the producer).  bf16, all channel counts multiples of 8. */
 int segk_channel_copy(segk_ctx* ctx, const void* src, int ld_src, int coff_src, void* dst,
                       int ld_dst, int coff_dst, const void* mask, int accumulate, int64_t rows, int C,
+                      int drop_side, const uint8_t* drop_mask, float drop_keep, uint64_t drop_seed,
                       void* stream);
+/* drop_side 1 / 2 with drop_keep in (0,1): tf.nn.dropout of the copied values on the fly, the keep pattern indexed by
+ * the elements of the source (1) or destination (2) tensor -- the Dropout between a dense-block conv and its concat
+ * slot (FCDenseNet.py:33-34,55) and its gradient.  0: plain copy. */
 
 /* ---- weight layout packing (fp32 master -> bf16 kernel layouts) ------------------------
  * Kernel layouts are BLOCKED by 64-wide chunks of the contraction dimension k: an operand [T taps][rows][K] is

@@ -109,3 +109,39 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
   return __bfloat1622float2(t);
 }
+
+// ---- dropout pattern shared by segk_dropout and the kernels that apply it on the fly ---------------------------
+// Philox4x32-10 keyed by the seed, counter = element index / 4 (tf.nn.dropout, FCN.py:165-167 / utils.py:318).
+__device__ __forceinline__ uint4 segk_philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+// keep bits (bit j = element 8 i + j is kept) of the i-th 8-element group of a dropout tensor: from the injected
+// u8 mask when there is one, else from the Philox stream
+__device__ __forceinline__ uint32_t segk_dropout_keep8(const uint2* __restrict__ mask, int64_t i, float keep, uint64_t seed) {
+  uint32_t kp = 0;
+  if (mask) {
+    const uint2 m = __ldg(mask + i);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) kp |= ((((&m.x)[j >> 2] >> (8 * (j & 3))) & 0xffu) != 0 ? 1u : 0u) << j;
+  } else {
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const int64_t q = 2 * i;
+    const uint4 r0 = segk_philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), 0u, 0u), key);
+    const uint4 r1 = segk_philox4x32_10(make_uint4((uint32_t)(q + 1), (uint32_t)((q + 1) >> 32), 0u, 0u), key);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      kp |= (((&r0.x)[j] >> 8) * (1.0f / 16777216.0f) < keep ? 1u : 0u) << j;
+      kp |= (((&r1.x)[j] >> 8) * (1.0f / 16777216.0f) < keep ? 1u : 0u) << (4 + j);
+    }
+  }
+  return kp;
+}

@@ -19,16 +19,47 @@ inline int sgrid(segk_ctx* ctx, int64_t items, int per_sm = 8) {
   return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
+// Dropout (utils.py:318) of the kernel's INPUT tensor applied on the fly: in FCDenseNet every conv is followed by a
+// Dropout whose only reader is the next BN/ReLU (bottleneck conv1) or the concat slot copy (conv2), so the dropped
+// tensor is never materialised.  The keep pattern is segk_dropout's (Philox counter = element index in the
+// [rows][ld] tensor, or the injected u8 mask), and the value is rounded to bf16 where segk_dropout would have
+// stored it: both ways give the same bits.
+struct Drop {
+  int on;
+  const uint2* mask;
+  float keep, inv_keep;
+  uint64_t seed;
+};
+__device__ __forceinline__ uint4 drop_apply(uint4 u, uint32_t kp, float inv_keep) {
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2((&u.x)[j]);
+    o[j] = pack_bf16x2((kp >> (2 * j)) & 1u ? f.x * inv_keep : 0.f, (kp >> (2 * j + 1)) & 1u ? f.y * inv_keep : 0.f);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+inline Drop make_drop(const uint8_t* mask, float keep_prob, uint64_t seed) {
+  Drop d;
+  d.on = (keep_prob > 0.f && keep_prob < 1.f) ? 1 : 0;
+  d.mask = (const uint2*)mask;
+  d.keep = keep_prob;
+  d.inv_keep = d.on ? 1.0f / keep_prob : 1.f;
+  d.seed = seed;
+  return d;
+}
+
 // y[r][c] = act(x[r][c] * scale[c] + shift[c]) for c < C (C % 8 == 0); thread = 8 channels of one row
 __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(const bf16* __restrict__ x, int ldx, bf16* __restrict__ y,
                                                               int ldy, const float* __restrict__ scale,
                                                               const float* __restrict__ shift, int64_t rows, int C8,
-                                                              int relu) {
+                                                              int relu, Drop drop) {
   const int64_t total = rows * C8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int g = (int)(i % C8);
     const int64_t r = i / C8;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * ldx) + g);
+    uint4 u = __ldg(reinterpret_cast<const uint4*>(x + r * ldx) + g);
+    if (drop.on) u = drop_apply(u, segk_dropout_keep8(drop.mask, r * (ldx >> 3) + g, drop.keep, drop.seed), drop.inv_keep);
     const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * g), s1 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * g + 1);
     const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * g), h1 = __ldg(reinterpret_cast<const float4*>(shift) + 2 * g + 1);
     const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
@@ -54,7 +85,7 @@ __global__ void __launch_bounds__(kThreads) bn_act_fwd_kernel(const bf16* __rest
 __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, int ldy,
                                                               const bf16* __restrict__ x, bf16* __restrict__ dx, int ldx,
                                                               const float* __restrict__ scale, float* __restrict__ part,
-                                                              int64_t rows, int C8, int relu, int accumulate) {
+                                                              int64_t rows, int C8, int relu, int accumulate, Drop drop) {
   __shared__ float sh[kThreads][17];
   const int cpb = C8 < kThreads ? C8 : kThreads;          // channel groups per block row
   const int R = kThreads / cpb;
@@ -69,7 +100,12 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(const bf16* __rest
     for (int64_t r = (int64_t)blockIdx.x * R + rl; r < rows; r += (int64_t)gridDim.x * R) {
       const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy + r * ldy) + g);
       const uint4 uy = __ldg(reinterpret_cast<const uint4*>(y + r * ldy) + g);
-      const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + r * ldx) + g);
+      uint4 ux = __ldg(reinterpret_cast<const uint4*>(x + r * ldx) + g);
+      uint32_t kp = 0xffu;
+      if (drop.on) {
+        kp = segk_dropout_keep8(drop.mask, r * (ldx >> 3) + g, drop.keep, drop.seed);
+        ux = drop_apply(ux, kp, drop.inv_keep);            // the BN input was the dropped tensor
+      }
       uint4* dxp = reinterpret_cast<uint4*>(dx + r * ldx) + g;
       uint4 uo = make_uint4(0, 0, 0, 0);
       if (accumulate) uo = *dxp;
@@ -81,7 +117,12 @@ __global__ void __launch_bounds__(kThreads) bn_act_bwd_kernel(const bf16* __rest
         const float g0 = (!relu || fy.x > 0.f) ? fd.x : 0.f, g1 = (!relu || fy.y > 0.f) ? fd.y : 0.f;
         ax[2 * j] += g0 * fx.x; ax[2 * j + 1] += g1 * fx.y;
         as[2 * j] += g0; as[2 * j + 1] += g1;
-        o[j] = pack_bf16x2(fo.x + g0 * sc[2 * j], fo.y + g1 * sc[2 * j + 1]);
+        float d0 = fo.x + g0 * sc[2 * j], d1 = fo.y + g1 * sc[2 * j + 1];
+        if (drop.on) {      // DropoutGrad: the gradient reaching the conv in front of the dropout (never accumulated)
+          d0 = (kp >> (2 * j)) & 1u ? bf2f(f2bf(d0)) * drop.inv_keep : 0.f;
+          d1 = (kp >> (2 * j + 1)) & 1u ? bf2f(f2bf(d1)) * drop.inv_keep : 0.f;
+        }
+        o[j] = pack_bf16x2(d0, d1);
       }
       *dxp = make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -371,14 +412,16 @@ __global__ void __launch_bounds__(kThreads) global_avgpool_bwd_kernel(const bf16
 extern "C" {
 
 int segk_bn_act_fwd(segk_ctx* ctx, const void* x, int ldx, void* y, int ldy, const float* scale, const float* shift,
-                    int64_t rows, int C, int relu, void* stream) {
+                    int64_t rows, int C, int relu, const uint8_t* drop_mask, float drop_keep, uint64_t drop_seed, void* stream) {
   if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, !(drop_keep > 0.f && drop_keep < 1.f) || ((uintptr_t)drop_mask & 7) == 0, "bn_act_fwd: dropout mask alignment");
   SEGK_REQUIRE(ctx, x && y && scale && shift && rows > 0 && C > 0, "bn_act_fwd: bad args");
   SEGK_REQUIRE(ctx, C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C &&
                         (((uintptr_t)x | (uintptr_t)y | (uintptr_t)scale | (uintptr_t)shift) & 15) == 0,
                "bn_act_fwd: C, ldx, ldy multiples of 8, 16-byte aligned pointers");
   bn_act_fwd_kernel<<<sgrid(ctx, rows * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (bf16*)y, ldy, scale,
-                                                                                       shift, rows, C / 8, relu);
+                                                                                       shift, rows, C / 8, relu,
+                                                                                       make_drop(drop_mask, drop_keep, drop_seed));
   SEGK_LAUNCHED(ctx, "bn_act_fwd");
   return SEGK_OK;
 }
@@ -389,8 +432,10 @@ size_t segk_bn_act_bwd_workspace_bytes(segk_ctx* ctx, int C) {
 
 int segk_bn_act_bwd(segk_ctx* ctx, const void* dy, const void* y, int ldy, const void* x, void* dx, int ldx,
                     const float* scale, float* dscale, float* dshift, void* workspace, size_t workspace_bytes, int64_t rows,
-                    int C, int relu, int accumulate, void* stream) {
+                    int C, int relu, int accumulate, const uint8_t* drop_mask, float drop_keep, uint64_t drop_seed, void* stream) {
   if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, !(drop_keep > 0.f && drop_keep < 1.f) || (!accumulate && ((uintptr_t)drop_mask & 7) == 0),
+               "bn_act_bwd: the fused DropoutGrad overwrites dx (no accumulate); 8-byte aligned mask");
   SEGK_REQUIRE(ctx, dy && y && x && dx && scale && dscale && dshift && workspace && rows > 0 && C > 0, "bn_act_bwd: bad args");
   SEGK_REQUIRE(ctx, C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 &&
                         (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)x | (uintptr_t)dx | (uintptr_t)scale) & 15) == 0,
@@ -406,7 +451,8 @@ int segk_bn_act_bwd(segk_ctx* ctx, const void* dy, const void* y, int ldy, const
   SEGK_REQUIRE(ctx, workspace_bytes >= sizeof(float) * (size_t)gx * 2 * C, "bn_act_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   bn_act_bwd_kernel<<<dim3((unsigned)gx, gy), kThreads, 0, st>>>((const bf16*)dy, (const bf16*)y, ldy, (const bf16*)x, (bf16*)dx,
-                                                                 ldx, scale, (float*)workspace, rows, C8, relu, accumulate);
+                                                                 ldx, scale, (float*)workspace, rows, C8, relu, accumulate,
+                                                                 make_drop(drop_mask, drop_keep, drop_seed));
   SEGK_LAUNCHED(ctx, "bn_act_bwd");
   dense_reduce_rows_kernel<<<ceil_div(2 * C, 32), kThreads, 0, st>>>((const float*)workspace, dscale, dshift, (int)gx, C);
   SEGK_LAUNCHED(ctx, "bn_act_bwd_reduce");

@@ -193,18 +193,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const uint4* __re
 // ------------------------------------------------------------------------------------
 // dropout (FCN.py:165-167).  Philox4x32-10 keyed by (seed), counter = element index / 4.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) { return segk_philox4x32_10(ctr, key); }
 
 __global__ void __launch_bounds__(kThreads) dropout_kernel(const bf16* __restrict__ x,
                                                            bf16* __restrict__ y,
@@ -236,22 +225,7 @@ __global__ void __launch_bounds__(kThreads) dropout_vec8_kernel(const uint4* __r
                                                                 float keep, float inv_keep, uint64_t seed) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
     const uint4 v = __ldg(x + i);
-    uint32_t kp = 0;      // bit j: keep element j
-    if (mask) {
-      const uint2 m = __ldg(mask + i);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) kp |= ((((&m.x)[j >> 2] >> (8 * (j & 3))) & 0xffu) != 0 ? 1u : 0u) << j;
-    } else {
-      const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-      const int64_t q = 2 * i;
-      const uint4 r0 = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), 0u, 0u), key);
-      const uint4 r1 = philox4x32_10(make_uint4((uint32_t)(q + 1), (uint32_t)((q + 1) >> 32), 0u, 0u), key);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        kp |= (((&r0.x)[j] >> 8) * (1.0f / 16777216.0f) < keep ? 1u : 0u) << j;
-        kp |= (((&r1.x)[j] >> 8) * (1.0f / 16777216.0f) < keep ? 1u : 0u) << (4 + j);
-      }
-    }
+    const uint32_t kp = segk_dropout_keep8(mask, i, keep, seed);      // bit j: keep element j
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

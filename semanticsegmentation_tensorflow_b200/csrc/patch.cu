@@ -316,12 +316,24 @@ __global__ void __launch_bounds__(kThreads) bn_grads_f32_partial_kernel(const fl
 __global__ void __launch_bounds__(kThreads) channel_copy_kernel(const bf16* __restrict__ src, int ld_src, int coff_src,
                                                                 bf16* __restrict__ dst, int ld_dst, int coff_dst,
                                                                 const bf16* __restrict__ mask, int accumulate,
-                                                                int64_t rows, int C8) {
+                                                                int64_t rows, int C8, int drop_side, const uint2* drop_mask,
+                                                                float drop_keep, float drop_inv_keep, uint64_t drop_seed) {
   const int64_t total = rows * C8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C8) * 8;
     const int64_t r = i / C8;
     uint4 v = *reinterpret_cast<const uint4*>(src + r * ld_src + coff_src + c);
+    if (drop_side) {
+      // dropout of the copied tensor on the fly (drop_side 1: the pattern is indexed by the SOURCE tensor's elements --
+      // forward, conv output -> concat slot; 2: by the DESTINATION's -- backward, slot gradient -> conv output gradient)
+      const int64_t e8 = drop_side == 1 ? (r * ld_src + coff_src + c) >> 3 : (r * ld_dst + coff_dst + c) >> 3;
+      const uint32_t kp = segk_dropout_keep8(drop_mask, e8, drop_keep, drop_seed);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16x2((&v.x)[j]);
+        (&v.x)[j] = pack_bf16x2((kp >> (2 * j)) & 1u ? t.x * drop_inv_keep : 0.f, (kp >> (2 * j + 1)) & 1u ? t.y * drop_inv_keep : 0.f);
+      }
+    }
     uint4* d = reinterpret_cast<uint4*>(dst + r * ld_dst + coff_dst + c);
     float f[8];
 #pragma unroll
@@ -563,14 +575,18 @@ int segk_bn_grads_f32(segk_ctx* ctx, const float* dz, const float* y, const floa
 }
 
 int segk_channel_copy(segk_ctx* ctx, const void* src, int ld_src, int coff_src, void* dst, int ld_dst, int coff_dst,
-                      const void* mask, int accumulate, int64_t rows, int C, void* stream) {
+                      const void* mask, int accumulate, int64_t rows, int C, int drop_side, const uint8_t* drop_mask,
+                      float drop_keep, uint64_t drop_seed, void* stream) {
   if (!ctx) return SEGK_EINVAL;
+  if (!(drop_keep > 0.f && drop_keep < 1.f)) drop_side = 0;
+  SEGK_REQUIRE(ctx, drop_side >= 0 && drop_side <= 2 && ((uintptr_t)drop_mask & 7) == 0, "channel_copy: bad dropout arguments");
   SEGK_REQUIRE(ctx, src && dst && rows > 0 && C > 0, "channel_copy: bad args");
   SEGK_REQUIRE(ctx, C % 8 == 0 && ld_src % 8 == 0 && ld_dst % 8 == 0 && coff_src % 8 == 0 && coff_dst % 8 == 0,
                "channel_copy: channel counts / offsets must be multiples of 8");
   const int64_t items = rows * (C / 8);
   channel_copy_kernel<<<sgrid(ctx, items, 16), kThreads, 0, (cudaStream_t)stream>>>(
-      (const bf16*)src, ld_src, coff_src, (bf16*)dst, ld_dst, coff_dst, (const bf16*)mask, accumulate, rows, C / 8);
+      (const bf16*)src, ld_src, coff_src, (bf16*)dst, ld_dst, coff_dst, (const bf16*)mask, accumulate, rows, C / 8, drop_side,
+      (const uint2*)drop_mask, drop_keep, drop_side ? 1.0f / drop_keep : 1.f, drop_seed);
   SEGK_LAUNCHED(ctx, "channel_copy");
   return SEGK_OK;
 }

@@ -295,6 +295,23 @@ class FCDenseNet(_Feeds):
                 self.member[b] = (n.name, off)
                 self.copy_after[t] = b
                 off += lay[t].used
+        # Dropout nodes applied on the fly by their only reader: the next BN/ReLU (bottleneck conv1 -> Dropout -> BN) or the
+        # copy into the concat slot (conv2 -> Dropout -> Concat); the others run segk_dropout in place
+        self.node_index = {n.name: i for i, n in enumerate(nodes)}
+        self.drop_fused, self.bn_drop, self.copy_drop = {}, {}, {}
+        for d in nodes:
+            if d.kind != "dropout":
+                continue
+            b = self._base(d.name)
+            users = [m for m in nodes if d.name in m.inputs]
+            if self.by_name[b].kind not in ("conv", "deconv") or not users:
+                continue
+            if len(users) == 1 and users[0].kind == "bnrelu" and b not in self.member and d.inputs[0] == b:
+                self.drop_fused[d.name] = "bn"
+                self.bn_drop[users[0].name] = d
+            elif all(m.kind == "concat" for m in users) and self.copy_after.get(d.name) == b and d.inputs[0] == b:
+                self.drop_fused[d.name] = "copy"
+                self.copy_drop[b] = d
         last = nodes[-1].name
         self.act, self.g = {}, {}
         for n in nodes:
@@ -434,6 +451,11 @@ class FCDenseNet(_Feeds):
         seed = (self.dropout_seed * 1000003 + self.step_count) * 1024 + idx
         return keep, seed, mask
 
+    def _drop_of(self, d):
+        """(keep_prob, seed, mask) of Dropout node d, or None when it is inactive (keep_prob 1)."""
+        keep, seed, mask = self._dropout_args(d, self.node_index[d.name])
+        return (keep, seed, mask) if keep < 1.0 else None
+
     def _to_root(self, name):
         """After node `name` ran: if it ends the chain feeding a concat slot, copy the produced tensor into the slot."""
         b = self.copy_after.get(name)
@@ -447,7 +469,12 @@ class FCDenseNet(_Feeds):
             src, c = self.buf[self.root[b]], self.lay[b].used
         else:
             src, c = self.act[b], self.lay[b].used
-        self.ops.channel_copy(src, 0, self.buf[r], off, c)
+        drop = None
+        d = self.copy_drop.get(b)
+        if d is not None and d.name == name:
+            a = self._drop_of(d)
+            drop = None if a is None else (1,) + a
+        self.ops.channel_copy(src, 0, self.buf[r], off, c, drop=drop)
 
     def forward(self):
         ops, V = self.ops, self.vars
@@ -458,10 +485,12 @@ class FCDenseNet(_Feeds):
             elif n.kind == "bnrelu":
                 src, off, c = self._storage(n.inputs[0])
                 assert off == 0, "BN/ReLU reads a channel prefix"
-                ops.bn_act_fwd(src, c, self.act[n.name], self.scale_p[n.name], self.shift_p[n.name], relu=n.relu)
+                d = self.bn_drop.get(n.name)
+                ops.bn_act_fwd(src, c, self.act[n.name], self.scale_p[n.name], self.shift_p[n.name], relu=n.relu,
+                               drop=None if d is None else self._drop_of(d))
             elif n.kind == "dropout":
                 keep, seed, mask = self._dropout_args(n, idx)
-                if keep < 1.0:
+                if keep < 1.0 and n.name not in self.drop_fused:
                     t = self.act[self._base(n.name)]
                     ops.dropout(t, t, keep, seed, mask)
             elif n.kind == "avgpool":
@@ -545,7 +574,11 @@ class FCDenseNet(_Feeds):
                     ops.channel_copy(self.gbufs[r], off, dst, 0, self.lay[b].used, accumulate=self.root[b] in has)
                     has.add(self.root[b])
                 else:
-                    ops.channel_copy(self.gbufs[r], off, self.g[b], 0, self.lay[b].used)
+                    d, drop = self.copy_drop.get(b), None
+                    if d is not None:            # DropoutGrad of the Dropout between this conv and its concat slot
+                        a = self._drop_of(d)
+                        drop = None if a is None else (2,) + a
+                    ops.channel_copy(self.gbufs[r], off, self.g[b], 0, self.lay[b].used, drop=drop)
             if n.kind == "concat":
                 return self.gbufs[self.root[b]]
             return self.g[b]
@@ -580,7 +613,7 @@ class FCDenseNet(_Feeds):
                 continue
             if n.kind == "dropout":
                 keep, seed, mask = self._dropout_args(n, idx)
-                if keep < 1.0:
+                if keep < 1.0 and n.name not in self.drop_fused:
                     g = grad_of(n.name)
                     ops.dropout(g, g, keep, seed, mask)
                 continue
@@ -592,8 +625,11 @@ class FCDenseNet(_Feeds):
                 if not acc and c < full:
                     dx.zero_()                      # the first writer covers only a prefix: the rest starts at zero
                     acc = True
+                d = self.bn_drop.get(n.name)
+                drop = None if d is None else self._drop_of(d)
+                assert drop is None or not acc, "a tensor behind a fused Dropout has one reader"
                 ops.bn_act_bwd(dy, self.act[n.name], xs, dx, c, self.scale_p[n.name], self.dscale_p[n.name],
-                               self.dshift_p[n.name], self.bn_ws, relu=n.relu, accumulate=acc)
+                               self.dshift_p[n.name], self.bn_ws, relu=n.relu, accumulate=acc, drop=drop)
                 continue
             if n.kind == "avgpool":
                 if n.name in self.member:

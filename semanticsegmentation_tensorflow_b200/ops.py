@@ -391,18 +391,23 @@ class Ops:
                   workspace.numel() * workspace.element_size(), dz.numel() // c, c, _stream())
 
     # ---- dense-block builders (FCDenseNet.py): strided channel views, physical <-> logical remaps ----
-    def bn_act_fwd(self, x, c, y, scale, shift, relu=True):
-        """x, y: [..., ld] bf16 buffers; the first c channels of every row are processed."""
+    def bn_act_fwd(self, x, c, y, scale, shift, relu=True, drop=None):
+        """x, y: [..., ld] bf16 buffers; the first c channels of every row are processed.  `drop` = (keep_prob, seed,
+        u8 mask or None): the Dropout in front of the BN applied to x on the fly."""
         rows = x.numel() // x.shape[-1]
         self._w(4.0 * rows * c, "byte")
-        self.call("segk_bn_act_fwd", _p(x), x.shape[-1], _p(y), y.shape[-1], _p(scale), _p(shift), rows, c, int(relu), _stream())
+        keep, seed, dmask = drop if drop is not None else (1.0, 0, None)
+        self.call("segk_bn_act_fwd", _p(x), x.shape[-1], _p(y), y.shape[-1], _p(scale), _p(shift), rows, c, int(relu),
+                  _p(dmask), float(keep), int(seed), _stream())
         return y
 
-    def bn_act_bwd(self, dy, y, x, dx, c, scale, dscale, dshift, workspace, relu=True, accumulate=True):
+    def bn_act_bwd(self, dy, y, x, dx, c, scale, dscale, dshift, workspace, relu=True, accumulate=True, drop=None):
         rows = x.numel() // x.shape[-1]
         self._w((8.0 + (4.0 if accumulate else 2.0)) * rows * c, "byte")
+        keep, seed, dmask = drop if drop is not None else (1.0, 0, None)
         self.call("segk_bn_act_bwd", _p(dy), _p(y), y.shape[-1], _p(x), _p(dx), x.shape[-1], _p(scale), _p(dscale), _p(dshift),
-                  _p(workspace), workspace.numel() * workspace.element_size(), rows, c, int(relu), int(accumulate), _stream())
+                  _p(workspace), workspace.numel() * workspace.element_size(), rows, c, int(relu), int(accumulate),
+                  _p(dmask), float(keep), int(seed), _stream())
 
     def bn_act_bwd_workspace(self, c, device):
         n = int(self.ctx.c.segk_bn_act_bwd_workspace_bytes(self.ctx.h, int(c)))
@@ -480,11 +485,14 @@ class Ops:
         self.call("segk_global_avgpool_bwd", _p(dy), _p(dx), n, h, w, c, _stream())
         return dx
 
-    def channel_copy(self, src, coff_src, dst, coff_dst, c, mask=None, accumulate=False):
+    def channel_copy(self, src, coff_src, dst, coff_dst, c, mask=None, accumulate=False, drop=None):
+        """`drop` = (side, keep_prob, seed, u8 mask or None): dropout of the copied values on the fly, pattern indexed by
+        the source (side 1) or destination (side 2) tensor."""
         rows = src.numel() // src.shape[-1]
         self._w(4.0 * rows * c, "byte")
+        side, keep, seed, dmask = drop if drop is not None else (0, 1.0, 0, None)
         self.call("segk_channel_copy", _p(src), src.shape[-1], coff_src, _p(dst), dst.shape[-1], coff_dst, _p(mask),
-                  int(accumulate), rows, c, _stream())
+                  int(accumulate), rows, c, int(side), _p(dmask), float(keep), int(seed), _stream())
         return dst
 
     def dropout(self, x, y, keep_prob, seed, mask=None):

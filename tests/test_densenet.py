@@ -131,8 +131,11 @@ def test_fcdensenet_dropout_with_injected_masks(cuda_device):
     # Philox masks: the keep rate is right and the step runs
     net.injected_masks = None
     net.forward()
-    t = net.act["denseblock1bottleneck_layer_0_conv1"].float()
-    assert 0.7 < float((t[..., :64] != 0).float().mean()) <= 0.85
+    # (the Dropout nodes are applied on the fly by their readers: the dropped conv2 output is visible in its concat slot)
+    r, off = net.member["denseblock1bottleneck_layer_0_conv2"]
+    t = net.buf[r][..., off:off + 16].float()
+    assert 0.7 < float((t != 0).float().mean()) <= 0.85
+    assert set(net.drop_fused.values()) == {"bn", "copy"} and len(net.drop_fused) == sum(n.kind == "dropout" for n in net.nodes)
 
 
 @pytest.mark.gpu
