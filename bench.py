@@ -447,7 +447,8 @@ def dp_correctness(net, train_step, allreduce, feed, world, dev):
 
 def run_secondary(dev, peaks):
     """Bounded runs of the other BASELINE configs on the same GPU, after the headline regions: U-Net training
-    (configs[2]), FCN-8s 384x1248 batch-16 inference (configs[3]) and batch-1 160x576 inference latency."""
+    (configs[2]), FCN-8s 384x1248 batch-16 inference (configs[3]), FCDenseNet training (the model of configs[4]) and
+    batch-1 160x576 inference latency."""
     import torch
     from semanticsegmentation_tensorflow_b200.fcn import FCN, AdamOptimizer
     from semanticsegmentation_tensorflow_b200.graph import UNet, graph_flops_per_image, unet_nodes
@@ -493,6 +494,20 @@ def run_secondary(dev, peaks):
                                      "frac_of_burst_peak": tf / peaks["bf16_tflops"], "iters": 20,
                                      "workload": "BASELINE configs[3], host images in / road masks out"}
     del net
+    torch.cuda.empty_cache()
+    # FCDenseNet (FCDenseNet.py:83-163, BASELINE configs[4]'s model) training, batch 32, host buffers in, loss out
+    from semanticsegmentation_tensorflow_b200.densenet import FCDenseNet, fcdensenet_flops_per_image
+    net = FCDenseNet(hx.to(dev), KEEP_PROB, NCLS, seed=1234)
+    step = AdamOptimizer(1e-4).minimize(net)
+    feed = {net.image: hx, net.annotation: hy, net.keep_probability: KEEP_PROB}
+    ms = timed(lambda: loss_host.copy_(step(feed).reshape(1), non_blocking=True), 6)
+    gf = fcdensenet_flops_per_image(net.nodes, net.ch, H, W)[1]
+    tf = gf * B / (ms / 1e3) / 1e12
+    out["fcdensenet_train_160x576_b32"] = {"images_per_s": B / (ms / 1e3), "ms_per_step": ms, "tflops": tf,
+                                           "frac_of_burst_peak": tf / peaks["bf16_tflops"], "steps": 6,
+                                           "workload": "FCDenseNet (103-layer Tiramisu of FCDenseNet.py, BASELINE configs[4]'s model) at "
+                                                       "160x576, 1 GPU, keep_prob 0.8, host buffers in / loss out; logical-channel FLOPs"}
+    del net, step
     torch.cuda.empty_cache()
     # batch-1 latency at 160x576 (gen_test_output's per-image call, FCN.py:224-231)
     hx1 = hx[:1].clone().pin_memory()
