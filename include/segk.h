@@ -71,8 +71,13 @@ int segk_set_tuning(segk_ctx* ctx, const char* key, int value);
  *   tcgen05 path: requires Cin % 64 == 0 and Cout % 64 == 0, odd kh,kw, kh*kw <= 64.
  */
 int segk_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* bias,
-                    const void* residual, void* y, int N, int H, int W, int Cin, int Cout,
-                    int kh, int kw, unsigned flags, void* stream);
+                    const void* residual, void* y, uint32_t* relu_bits, int N, int H, int W, int Cin,
+                    int Cout, int kh, int kw, unsigned flags, void* stream);
+/* the same words from a finished bf16 tensor y [rows][C] (C % 32 == 0): bits[r][w] bit i = (y[r][32 w + i] > 0) */
+int segk_relu_bits(segk_ctx* ctx, const void* y, uint32_t* bits, int64_t rows, int C, void* stream);
+/* relu_bits (or NULL): 1-bit ReLU mask of the bf16 output, u32 [N*H*W][Cout/32], bit i of word w = (y[.., 32 w + i] > 0),
+ * written by the same epilogue (Cout % 32 == 0).  The consumer layer's segk_conv2d_dgrad takes it as relu_mask_bits:
+ * the ReluGrad of this layer then reads 1/16 of the bytes of the bf16 activation with one coalesced load. */
 
 /*
  * conv_layer followed by max_pool (FCN.py:54-56, 58-60, 62-65, 67-71, 73-76: conv -> ReLU -> max_pool 2x2/2, the
@@ -98,8 +103,10 @@ int segk_conv2d_fwd_pool(segk_ctx* ctx, const void* x, const void* wk, const flo
  *   from the fp32 values, fixed order; a separate pass over dx only for split-K / weight-heavy layers).
  */
 int segk_conv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask,
-                      const void* residual, void* dx, float* dx_colsum, float scale, int N, int H, int W,
-                      int Cin, int Cout, int kh, int kw, void* stream);
+                      const uint32_t* relu_mask_bits, const void* residual, void* dx, float* dx_colsum,
+                      float scale, int N, int H, int W, int Cin, int Cout, int kh, int kw, void* stream);
+/* relu_mask_bits (instead of relu_mask, not both): the producer's mask as written by segk_conv2d_fwd /
+ * segk_conv2d_first_fwd (relu_bits), u32 [N*H*W][Cin/32]; same result bit for bit. */
 
 /*
  * Conv2DBackpropFilter of conv_layer (FCN.py:340): dw[kh,kw,Cin,Cout] fp32 HWIO
@@ -138,8 +145,8 @@ int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw,
  * tcgen05; wk is the segk_pack_im2col_weights layout [Cout][64] bf16.  y bf16, bias + optional
  * SEGK_EPI_RELU fused. */
 int segk_conv2d_first_fwd(segk_ctx* ctx, const void* x, int x_dtype, const void* wk,
-                          const float* bias, void* y, int N, int H, int W, int Cin, int Cout,
-                          int kh, int kw, unsigned flags, void* stream);
+                          const float* bias, void* y, uint32_t* relu_bits, int N, int H, int W, int Cin,
+                          int Cout, int kh, int kw, unsigned flags, void* stream);
 
 /* Conv2DBackpropFilter (+ BiasAddGrad when dbias != NULL) of that layer (FCN.py:340): reads the
  * image and dy once.  dw fp32 [kh,kw,Cin,Cout] (overwritten), dbias fp32 [Cout] (overwritten). */

@@ -110,6 +110,12 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
   return __bfloat1622float2(t);
 }
 
+// [bf16 value > 0] of the two halves of a packed pair (bit 0: low half, bit 1: high half): a bf16 pattern is positive
+// iff it is > 0 as a signed 16-bit integer
+__device__ __forceinline__ uint32_t bf16x2_pos_bits(uint32_t pk) {
+  return ((int)(short)(pk & 0xffffu) > 0 ? 1u : 0u) | ((int)pk > 0xffff ? 2u : 0u);
+}
+
 // ---- dropout pattern shared by segk_dropout and the kernels that apply it on the fly ---------------------------
 // Philox4x32-10 keyed by the seed, counter = element index / 4 (tf.nn.dropout, FCN.py:165-167 / utils.py:318).
 __device__ __forceinline__ uint4 segk_philox4x32_10(uint4 ctr, uint2 key) {

@@ -40,6 +40,7 @@ struct FirstParams {
   const float* bias;
   int relu;
   float* ws;        // wgrad: per-CTA partial [grid][64][Cout]
+  uint32_t* bits_out;   // forward: 1-bit ReLU mask of the output, [pixel][Cout/32] (see IgemmParams in tcconv.cu), or NULL
 };
 
 struct Pipe {
@@ -252,6 +253,12 @@ first_fwd_kernel(const __grid_constant__ FirstMaps maps, const FirstParams p) {
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int x0, y0, n0;
       decode_tile(p, tile, x0, y0, n0);
+      uint32_t* bits_row = nullptr;      // this thread's row of the 1-bit ReLU mask, when it is inside the tensor
+      if (p.bits_out) {
+        const int px = x0 + row % p.bw, py = y0 + (row / p.bw) % p.bh, pn = n0 + row / (p.bw * p.bh);
+        if (row < p.rows && px < p.W && py < p.H && pn < p.N)
+          bits_row = p.bits_out + (((int64_t)pn * p.H + py) * p.W + px) * (BLOCK_N / 32);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
@@ -285,11 +292,19 @@ first_fwd_kernel(const __grid_constant__ FirstMaps maps, const FirstParams p) {
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         const int pbase = (c0 & 32) ? 4 : 0;
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           *reinterpret_cast<uint4*>(sbuf + row * 128 + (((pbase + i) ^ (row & 7)) << 4)) =
-              make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
-                         pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+              make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        if (bits_row) {
+          uint32_t word = 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) word |= bf16x2_pos_bits(pk[i]) << (2 * i);
+          bits_row[c0 >> 5] = word;
+        }
         if (c0 & 32) {
           fence_proxy_async();
           named_bar_sync(1, 128);
@@ -536,8 +551,9 @@ int check_args(segk_ctx* ctx, const char* what, int x_dtype, int N, int H, int W
 
 extern "C" {
 
-int segk_conv2d_first_fwd(segk_ctx* ctx, const void* x, int x_dtype, const void* wk, const float* bias, void* y, int N,
-                          int H, int W, int Cin, int Cout, int kh, int kw, unsigned flags, void* stream) {
+int segk_conv2d_first_fwd(segk_ctx* ctx, const void* x, int x_dtype, const void* wk, const float* bias, void* y,
+                          uint32_t* relu_bits, int N, int H, int W, int Cin, int Cout, int kh, int kw, unsigned flags,
+                          void* stream) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, x && wk && y, "conv2d_first_fwd: null pointer");
   int rc = check_args(ctx, "conv2d_first_fwd", x_dtype, N, H, W, Cin, Cout, kh, kw);
@@ -558,6 +574,7 @@ int segk_conv2d_first_fwd(segk_ctx* ctx, const void* x, int x_dtype, const void*
   p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.rows;
   p.tiles_w = ceil_div(W, b.bw); p.tiles_h = ceil_div(H, b.bh); p.tiles_n = ceil_div(N, b.bn);
   p.bias = bias; p.relu = (flags & SEGK_EPI_RELU) ? 1 : 0;
+  p.bits_out = relu_bits;
   const int tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   FIRST_DISPATCH(launch_fwd, ctx, Cout, maps, p, tiles, (cudaStream_t)stream);
 }

@@ -134,6 +134,11 @@ struct IgemmParams {
   bf16* pool_out;
   uint8_t* pool_idx;
   int pool_only;
+  // 1-bit ReLU masks: bits_out[pixel][C/32] (bit i of word w = the stored bf16 output of channel 32 w + i is > 0) written
+  // by a forward epilogue; mask_bits = the producer layer's words, read by its consumer's dgrad epilogue instead of the
+  // bf16 activation (1/16 of the bytes, one coalesced 4-byte load per thread and column group)
+  uint32_t* bits_out;
+  const uint32_t* mask_bits;
 };
 
 struct PipeState {
@@ -315,9 +320,11 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 // 64-channel layers longer than their MMAs (ncu r1d: conv1_2 dgrad epilogue-bound).
 struct EpiPre {
   uint4 a[4];     // the residual when there is one, else the mask (both at once -- no layer of the three nets -- loads the mask late)
+  uint32_t mb;    // the 32 mask bits of these channels (p.mask_bits)
 };
 template <class P>
 __device__ __forceinline__ void epilogue_prefetch(const P& p, int64_t off, EpiPre& e) {
+  if (p.mask_bits) e.mb = __ldg(p.mask_bits + (off >> 5));
   const bf16* src = p.residual ? p.residual : p.mask;
   if (src) {
     const uint4* s4 = reinterpret_cast<const uint4*>(src + off);
@@ -364,9 +371,21 @@ __device__ __forceinline__ void epilogue_apply_store(const P& p, float (&v)[32],
       }
     }
   }
+  if (p.mask_bits) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (!((pre.mb >> i) & 1u)) v[i] = 0.f;
+  }
   if (p.scale != 1.f) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] *= p.scale;
+  }
+  if (p.bits_out) {
+    // from the rounded bf16 values, so that the bits equal [stored tensor > 0] exactly
+    uint32_t word = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) word |= bf16x2_pos_bits(pack_bf16x2(v[2 * i], v[2 * i + 1])) << (2 * i);
+    p.bits_out[off >> 5] = word;
   }
   if (p.out_f32) {
     float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
@@ -752,6 +771,8 @@ struct SlabParams {
   bf16* pool_out;         // fused 2x2 max-pool of the output (see IgemmParams)
   uint8_t* pool_idx;
   int pool_only;
+  uint32_t* bits_out;     // 1-bit ReLU masks out / in (see IgemmParams)
+  const uint32_t* mask_bits;
   void* out;
   int out_f32;
   const float* bias;
@@ -1418,7 +1439,8 @@ __global__ void __launch_bounds__(256) epilogue_finish_kernel(const float* __res
                                                               const float* __restrict__ bias,
                                                               const bf16* __restrict__ residual,
                                                               const bf16* __restrict__ mask, void* __restrict__ out,
-                                                              int out_f32, int relu, float scale, int64_t rows, int C) {
+                                                              int out_f32, int relu, float scale, int64_t rows, int C,
+                                                              const uint32_t* __restrict__ mask_bits) {
   const int C8 = C >> 3;
   const int64_t total = rows * C8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1456,6 +1478,12 @@ __global__ void __launch_bounds__(256) epilogue_finish_kernel(const float* __res
         if (!(f.x > 0.f)) v[2 * j] = 0.f;
         if (!(f.y > 0.f)) v[2 * j + 1] = 0.f;
       }
+    }
+    if (mask_bits) {
+      const uint32_t mb = __ldg(mask_bits + (base >> 5)) >> (base & 31);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (!((mb >> j) & 1u)) v[j] = 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= scale;
@@ -1543,7 +1571,8 @@ __global__ void __launch_bounds__(256) epilogue_finish_ts_kernel(const float* __
                                                                  const float* __restrict__ bias,
                                                                  const bf16* __restrict__ residual,
                                                                  const bf16* __restrict__ mask, void* __restrict__ out,
-                                                                 int out_f32, int relu, float scale, int64_t rows, int C) {
+                                                                 int out_f32, int relu, float scale, int64_t rows, int C,
+                                                                 const uint32_t* __restrict__ mask_bits) {
   const int C8 = C >> 3;
   const int64_t total = rows * C8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1586,6 +1615,12 @@ __global__ void __launch_bounds__(256) epilogue_finish_ts_kernel(const float* __
         if (!(f.x > 0.f)) v[2 * j] = 0.f;
         if (!(f.y > 0.f)) v[2 * j + 1] = 0.f;
       }
+    }
+    if (mask_bits) {
+      const uint32_t mb = __ldg(mask_bits + (base >> 5)) >> (base & 31);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (!((mb >> j) & 1u)) v[j] = 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= scale;
@@ -1646,6 +1681,12 @@ __global__ void __launch_bounds__(256) epilogue_finish_tiles_kernel(const float*
         if (!(f.x > 0.f)) v[2 * j] = 0.f;
         if (!(f.y > 0.f)) v[2 * j + 1] = 0.f;
       }
+    }
+    if (p.mask_bits) {
+      const uint32_t mb = __ldg(p.mask_bits + (base >> 5)) >> (base & 31);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (!((mb >> j) & 1u)) v[j] = 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= p.scale;
@@ -1866,7 +1907,24 @@ struct PoolArgs {
   uint8_t* idx;
   int pool_only;
   bool fused;      // out: the launch produced pooled / idx itself
+  uint32_t* bits_out = nullptr;          // 1-bit ReLU mask of the output (forward)
+  const uint32_t* mask_bits = nullptr;   // 1-bit ReLU mask of the producer layer (dgrad)
+  bool bits_done = false;                // out: the launch wrote bits_out itself
 };
+
+// bits[r][c / 32] from a finished bf16 tensor [rows][C] (forward paths whose epilogue runs in a finish kernel)
+__global__ void __launch_bounds__(256) relu_bits_kernel(const uint4* __restrict__ y, uint32_t* __restrict__ bits, int64_t nwords) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 u = __ldg(y + i * 4 + q);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) word |= bf16x2_pos_bits((&u.x)[j]) << (8 * q + 2 * j);
+    }
+    bits[i] = word;
+  }
+}
 
 int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, const float* bias, const void* residual,
               const void* mask, float scale, int relu, int out_f32, void* y, int N, int H, int W, int Ck, int Cn,
@@ -1902,9 +1960,13 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
     rc = encode_act_map(ctx, &maps.c, y, N, H, W, Cn, Cn, (int64_t)W * Cn, (int64_t)H * W * Cn, kSlabWV, kSlabH, 1);
     if (rc) return rc;
   }
-  if (pool && p.tma_store && !colsum_out && (W & 1) == 0) {      // 4 x 30 tiles at even origins: whole pool windows
+  if (pool && pool->pooled && p.tma_store && !colsum_out && (W & 1) == 0) {      // 4 x 30 tiles at even origins: whole pool windows
     p.pool_out = (bf16*)pool->pooled; p.pool_idx = pool->idx; p.pool_only = pool->pool_only;
     pool->fused = true;
+  }
+  if (pool) {
+    p.mask_bits = pool->mask_bits;
+    if (pool->bits_out && !out_f32) { p.bits_out = pool->bits_out; pool->bits_done = true; }
   }
   const int total = N * p.tiles_h * p.tiles_w * p.n_tiles;
   int grid = total < ctx->sm_count ? total : ctx->sm_count;
@@ -1971,7 +2033,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   if (rate == 1 && slab_applicable(ctx, N, H, W, Ck, Cn, kh, kw))
     return conv_slab(ctx, what, x, wt, bias, residual, mask, scale, relu, out_f32, y, N, H, W, Ck, Cn, stream, colsum_out, pool);
   // the fused pool needs boxes of whole 2x2 windows, the TMA-store epilogue and unsplit tiles
-  bool want_pool = pool && !out_f32 && ctx->tma_store && !colsum_out && (H & 1) == 0 && (W & 1) == 0;
+  bool want_pool = pool && pool->pooled && !out_f32 && ctx->tma_store && !colsum_out && (H & 1) == 0 && (W & 1) == 0;
   Box b = choose_box(N, H, W, kBlockM, false, 0, 0, kh, kw, want_pool);
   if (want_pool && b.rows <= 0) {
     want_pool = false;
@@ -2000,6 +2062,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   p.bias = bias; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask;
   p.scale = scale; p.relu = relu;
   p.ksplits = 1; p.ws = nullptr;
+  if (pool) p.mask_bits = pool->mask_bits;         // (bits_out is set below, on the paths whose epilogue runs in the igemm kernel)
   // order the tiles so that what is larger (weights vs activations) is what concurrent CTAs share
   p.m_fastest = ((int64_t)kh * kw * Cn > (int64_t)N * H * W) ? 1 : 0;
   TapTable taps;
@@ -2014,6 +2077,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
     if (rc) return rc;
     p.pool_out = (bf16*)pool->pooled; p.pool_idx = pool->idx; p.pool_only = pool->pool_only;
     pool->fused = true;
+    if (pool->bits_out) { p.bits_out = pool->bits_out; pool->bits_done = true; }
     return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
   }
   if ((tiles * 2 <= ctx->sm_count && p.ntaps * p.kchunks >= 32 && p.kchunks >= 2) || force_ks > 0) {
@@ -2067,7 +2131,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
         if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
         epilogue_finish_ts_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
             (const float*)ctx->ws, tf, (int64_t)slice, bias, (const bf16*)residual, (const bf16*)mask, y, out_f32, relu, scale,
-            rows, Cn);
+            rows, Cn, p.mask_bits);
         SEGK_LAUNCHED(ctx, "igemm tap-split finish");
         if (colsum_out) return colsum_fallback(ctx, y, rows, Cn, colsum_out, (cudaStream_t)stream);
         return SEGK_OK;
@@ -2091,7 +2155,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
       if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
       epilogue_finish_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
           (const float*)ctx->ws, ks, (int64_t)slice, bias, (const bf16*)residual, (const bf16*)mask, y, out_f32, relu, scale,
-          rows, Cn);
+          rows, Cn, p.mask_bits);
       SEGK_LAUNCHED(ctx, "igemm split-K finish");
       if (colsum_out) return colsum_fallback(ctx, y, rows, Cn, colsum_out, (cudaStream_t)stream);
       return SEGK_OK;
@@ -2102,6 +2166,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
     rc = encode_act_map(ctx, &maps.c, y, N, H, W, Cn, Cn, (int64_t)W * Cn, (int64_t)H * W * Cn, b.bw, b.bh, b.bn);
     if (rc) return rc;
   }
+  if (pool && pool->bits_out && !out_f32 && !(ctx->hybrid)) { p.bits_out = pool->bits_out; pool->bits_done = true; }
   // Hybrid schedule for a partly filled last wave (conv5_x: 180 tiles on 148 SMs, conv6/conv7 forward: 368): whole waves
   // run as they are, the remaining tiles are split in K so that their units fill one more (short) wave.
   {
@@ -2519,11 +2584,35 @@ int segk_deconv2d_packed_wgrad(segk_ctx* ctx, const void* x, const void* dyb, fl
   return SEGK_OK;
 }
 
-int segk_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* bias, const void* residual, void* y,
-                    int N, int H, int W, int Cin, int Cout, int kh, int kw, unsigned flags, void* stream) {
+// bits of a finished bf16 tensor (paths whose epilogue did not write them)
+static int relu_bits_of(segk_ctx* ctx, const void* y, uint32_t* bits, int64_t rows, int C, void* stream) {
+  const int64_t nwords = rows * (C / 32);
+  int64_t blocks = ceil_div64(nwords, 256);
+  if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
+  relu_bits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)y, bits, nwords);
+  SEGK_LAUNCHED(ctx, "relu bits");
+  return SEGK_OK;
+}
+
+int segk_relu_bits(segk_ctx* ctx, const void* y, uint32_t* bits, int64_t rows, int C, void* stream) {
   if (!ctx) return SEGK_EINVAL;
-  return conv_igemm(ctx, "conv2d_fwd", x, wk, bias, residual, nullptr, 1.f, (flags & SEGK_EPI_RELU) ? 1 : 0,
-                    (flags & SEGK_EPI_OUT_F32) ? 1 : 0, y, N, H, W, Cin, Cout, kh, kw, stream);
+  SEGK_REQUIRE(ctx, y && bits && rows > 0 && C > 0 && C % 32 == 0 && (((uintptr_t)y) & 15) == 0, "relu_bits: bad args (C %% 32 == 0)");
+  return relu_bits_of(ctx, y, bits, rows, C, stream);
+}
+
+int segk_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* bias, const void* residual, void* y,
+                    uint32_t* relu_bits, int N, int H, int W, int Cin, int Cout, int kh, int kw, unsigned flags, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  if (!relu_bits)
+    return conv_igemm(ctx, "conv2d_fwd", x, wk, bias, residual, nullptr, 1.f, (flags & SEGK_EPI_RELU) ? 1 : 0,
+                      (flags & SEGK_EPI_OUT_F32) ? 1 : 0, y, N, H, W, Cin, Cout, kh, kw, stream);
+  SEGK_REQUIRE(ctx, !(flags & SEGK_EPI_OUT_F32) && Cout % 32 == 0, "conv2d_fwd: relu_bits need a bf16 output with Cout %% 32 == 0");
+  PoolArgs ex{nullptr, nullptr, 0, false};
+  ex.bits_out = relu_bits;
+  const int rc = conv_igemm(ctx, "conv2d_fwd", x, wk, bias, residual, nullptr, 1.f, (flags & SEGK_EPI_RELU) ? 1 : 0, 0, y, N, H, W,
+                            Cin, Cout, kh, kw, stream, nullptr, 1, &ex);
+  if (rc || ex.bits_done) return rc;
+  return relu_bits_of(ctx, y, relu_bits, (int64_t)N * H * W, Cout, stream);
 }
 
 int segk_conv2d_fwd_pool(segk_ctx* ctx, const void* x, const void* wk, const float* bias, void* y, void* pooled, uint8_t* idx,
@@ -2539,13 +2628,17 @@ int segk_conv2d_fwd_pool(segk_ctx* ctx, const void* x, const void* wk, const flo
   return segk_maxpool2x2_fwd(ctx, y, pooled, idx, N, H, W, Cout, stream);     // (tile geometry without whole windows)
 }
 
-int segk_conv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, const void* residual,
-                      void* dx, float* dx_colsum, float scale, int N, int H, int W, int Cin, int Cout, int kh, int kw,
-                      void* stream) {
+int segk_conv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, const uint32_t* relu_mask_bits,
+                      const void* residual, void* dx, float* dx_colsum, float scale, int N, int H, int W, int Cin, int Cout,
+                      int kh, int kw, void* stream) {
   if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, !(relu_mask && relu_mask_bits), "conv2d_dgrad: pass the ReLU mask as a tensor OR as bits");
+  SEGK_REQUIRE(ctx, !relu_mask_bits || Cin % 32 == 0, "conv2d_dgrad: mask bits need Cin %% 32 == 0");
   // GEMM-K = Cout (channels of dy), GEMM-N = Cin (channels of dx); wd holds the taps reversed.
+  PoolArgs ex{nullptr, nullptr, 0, false};
+  ex.mask_bits = relu_mask_bits;
   return conv_igemm(ctx, "conv2d_dgrad", dy, wd, nullptr, residual, relu_mask, scale, 0, 0, dx, N, H, W, Cout, Cin, kh,
-                    kw, stream, dx_colsum);
+                    kw, stream, dx_colsum, 1, relu_mask_bits ? &ex : nullptr);
 }
 
 static int conv2d_wgrad_impl(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,

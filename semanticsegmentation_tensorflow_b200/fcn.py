@@ -267,6 +267,7 @@ class FCN(_Feeds):
         self.injected_masks = None     # {"dropout6": u8 tensor, "dropout7": ...} for parity runs
         self.fuse_pool = True          # max_pool in the epilogue of the conv in front of it (segk_conv2d_fwd_pool)
         self.keep_prepool = False      # True: also store the pre-pool conv outputs (per-activation parity tests)
+        self.use_mask_bits = True      # ReluGrad masks as 1-bit words written by the forward epilogues (self.bits)
         self.x = x
         self._alloc()
         self._ran_forward = False
@@ -314,6 +315,17 @@ class FCN(_Feeds):
                     self.patch[l.name] = torch.empty((N, h, w, e), dtype=bf, device=dev)
                     self.patch_f32[l.name] = torch.empty((N, h, w, e), dtype=torch.float32, device=dev)
                 h, w = h * l.stride, w * l.stride
+        # 1-bit ReLU masks (u32 [N,H,W,C/32]) of the conv outputs whose ReluGrad runs in the epilogue of the NEXT conv's
+        # dgrad: written by the forward epilogue, read there instead of the bf16 activation (1/16 of the bytes)
+        self.bits = {}
+        h, w = self.H, self.W
+        for i, l in enumerate(self.layers):
+            if l.kind == "pool":
+                h, w = h // 2, w // 2
+            nxt = self.layers[i + 1] if i + 1 < len(self.layers) else None
+            if (l.kind == "conv" and l.path in ("tc", "first") and l.relu and not l.dropout and l.cout % 32 == 0 and
+                    nxt is not None and nxt.kind == "conv" and nxt.path == "tc"):
+                self.bits[l.name] = torch.empty((N, h, w, l.cout // 32), dtype=torch.int32, device=dev)
         self.logits = self.act["conv_t3"]
         npix = N * self.H * self.W
         self.dlogits = torch.empty_like(self.logits)
@@ -339,6 +351,9 @@ class FCN(_Feeds):
         mask = None if self.injected_masks is None else self.injected_masks.get("dropout" + l.name[-1])
         seed = (self.dropout_seed * 1000003 + self.step_count) * 16 + int(l.name[-1])
         self.ops.dropout(t, t, self.keep_prob, seed, mask)
+
+    def _bits_of(self, l):
+        return self.bits.get(l.name) if self.use_mask_bits else None
 
     def create(self):
         """Run the forward pass; returns (pred [N,H,W,1] int64, logits [N,H,W,C] f32)."""
@@ -368,9 +383,11 @@ class FCN(_Feeds):
                                         pool_only=not self.keep_prepool)
                     pooled_by_conv = nxt.name
                 elif l.path == "tc":
-                    ops.conv2d_fwd(cur, V.wk[l.name], b, out, l.k, l.k, relu=l.relu)
+                    ops.conv2d_fwd(cur, V.wk[l.name], b, out, l.k, l.k, relu=l.relu, relu_bits=self._bits_of(l))
                 elif l.path == "first":
-                    ops.conv2d_first_fwd(cur, V.wk[l.name], b, out, l.k, l.k, relu=l.relu)
+                    # (measured: the bits in this kernel's epilogue cost 47 us; a streaming segk_relu_bits pass on the side
+                    # stream under conv1_2's forward costs more of the step, 8.15 vs 8.07 ms)
+                    ops.conv2d_first_fwd(cur, V.wk[l.name], b, out, l.k, l.k, relu=l.relu, relu_bits=self._bits_of(l))
                 elif l.path == "im2col":
                     P1 = ops.im2col_k64(cur, self.patch[l.name], l.k, l.k)
                     ops.conv2d_fwd(P1, V.wk[l.name], b, out, 1, 1, relu=l.relu,
@@ -543,8 +560,9 @@ class FCN(_Feeds):
                     res = {"pool4": self.dfuse_1, "pool3": self.dfuse_2}.get(prev.name)
                     dx = next_dx(xin)
                     if l.path == "tc":
-                        ops.conv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.k, relu_mask=mask, residual=res, scale=scale,
-                                         colsum=fused_bias(prev))
+                        mbits = self._bits_of(prev) if mask is not None else None
+                        ops.conv2d_dgrad(dcur, V.wd[l.name], dx, l.k, l.k, relu_mask=None if mbits is not None else mask,
+                                         relu_mask_bits=mbits, residual=res, scale=scale, colsum=fused_bias(prev))
                     else:
                         assert res is None
                         ops.conv2d_small_dgrad(dcur, V.param(f"{l.name}/weights"), dx, relu_mask=mask, scale=scale)
@@ -561,10 +579,12 @@ class FCN(_Feeds):
         if image is not None:
             self.feed({self.image: image})
         kp, self.keep_prob = self.keep_prob, 1.0
+        mb, self.use_mask_bits = self.use_mask_bits, False        # (no backward follows: no ReluGrad masks)
         try:
             self.forward()
         finally:
             self.keep_prob = kp
+            self.use_mask_bits = mb
         prob = torch.empty_like(self.logits)
         mask = torch.empty((self.N, self.H, self.W), dtype=torch.uint8, device=self.device)
         self.ops.softmax_infer(self.logits, prob, mask)

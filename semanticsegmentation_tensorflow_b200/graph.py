@@ -276,6 +276,15 @@ class GraphNet(_Feeds):
             self.act[n.name] = torch.empty(shape[n.name], dtype=dt, device=dev)
             self.gbuf[n.name] = torch.empty(shape[n.name], dtype=dt, device=dev)
         self.shape = shape
+        # 1-bit ReLU masks of the conv outputs that a tensor-core conv reads (its dgrad epilogue applies the producer's
+        # ReluGrad): written by the forward epilogue, 1/16 of the bytes of the bf16 activation
+        self.bits = {}
+        self.use_mask_bits = True
+        for n in self.nodes:
+            if n.kind == "conv" and n.relu and self.route[n.name] in ("tc", "first") and n.cout % 32 == 0 and n.name != last:
+                readers = [m for m in self.nodes if n.name in m.inputs]
+                if any(m.kind == "conv" and self.route[m.name] == "tc" for m in readers):
+                    self.bits[n.name] = torch.empty(shape[n.name][:3] + (n.cout // 32,), dtype=torch.int32, device=dev)
         self.logits = self.act[last]
         assert self.logits.shape[3] == self.num_classes
         self.dlogits = self.gbuf[last]
@@ -328,12 +337,17 @@ class GraphNet(_Feeds):
         tensor may stay unwritten (no other consumer; backward never reads it: d(gamma) comes from the weight gradient)."""
         if not getattr(self, "fuse_pool", True) or n.kind != "conv" or self.route[n.name] != "tc":
             return None, False
+        if n.name in self.bits:        # (a conv whose mask bits another conv's dgrad reads keeps the plain forward call)
+            return None, False
         users = [m for m in self.nodes if n.name in m.inputs]
         pools = [m for m in users if m.kind == "pool"]
         if len(pools) != 1 or self.act[n.name].dtype != torch.bfloat16:
             return None, False
         only = len(users) == 1 and not getattr(self, "keep_prepool", False)
         return pools[0], only
+
+    def _bits_of(self, name):
+        return self.bits.get(name) if self.use_mask_bits else None
 
     def forward(self):
         ops, V = self.ops, self.vars
@@ -359,9 +373,10 @@ class GraphNet(_Feeds):
                                         relu=n.relu, pool_only=only)
                     pooled.add(pool.name)
                 elif r == "tc":
-                    ops.conv2d_fwd(x, V.wk[n.name], self._bias(n), out, n.k, n.k, relu=n.relu)
+                    ops.conv2d_fwd(x, V.wk[n.name], self._bias(n), out, n.k, n.k, relu=n.relu, relu_bits=self._bits_of(n.name))
                 elif r == "first":
-                    ops.conv2d_first_fwd(x, V.wk[n.name], self._bias(n), out, n.k, n.k, relu=n.relu)
+                    ops.conv2d_first_fwd(x, V.wk[n.name], self._bias(n), out, n.k, n.k, relu=n.relu,
+                                         relu_bits=self._bits_of(n.name))
                 elif r == "im2col":
                     P1 = ops.im2col_k64(x, self.patch[n.name], n.k, n.k)
                     ops.conv2d_fwd(P1, V.wk[n.name], self._bias(n), out, 1, 1, relu=n.relu,
@@ -492,7 +507,9 @@ class GraphNet(_Feeds):
                         raise NotImplementedError("deconv input with a second consumer")
                     ops.deconv2d_dgrad(dz, V.wd[n.name], dx, n.k, n.stride, relu_mask=mask)
                 elif r == "tc":
-                    ops.conv2d_dgrad(dz, V.wd[n.name], dx, n.k, n.k, relu_mask=mask, residual=res)
+                    mbits = self._bits_of(t) if mask is not None else None
+                    ops.conv2d_dgrad(dz, V.wd[n.name], dx, n.k, n.k, relu_mask=None if mbits is not None else mask,
+                                     relu_mask_bits=mbits, residual=res)
                 elif r == "small":
                     if res is not None:
                         raise NotImplementedError("1x1 head input with a second consumer")

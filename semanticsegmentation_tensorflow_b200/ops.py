@@ -189,11 +189,11 @@ class Ops:
         return wk
 
     # ---- first layer: patches built in shared memory, no patch tensor (firstconv.cu) ------------
-    def conv2d_first_fwd(self, x, wk, bias, y, kh, kw, relu=True):
+    def conv2d_first_fwd(self, x, wk, bias, y, kh, kw, relu=True, relu_bits=None):
         n, h, w, cin = x.shape
         cout = y.shape[3]
         self._w(float(x.numel() * x.element_size() + 2 * y.numel()), "byte")
-        self.call("segk_conv2d_first_fwd", _p(x), _dt(x), _p(wk), _p(bias), _p(y), n, h, w, cin, cout, kh, kw,
+        self.call("segk_conv2d_first_fwd", _p(x), _dt(x), _p(wk), _p(bias), _p(y), _p(relu_bits), n, h, w, cin, cout, kh, kw,
                   EPI_RELU if relu else 0, _stream())
         return y
 
@@ -229,22 +229,32 @@ class Ops:
         return y
 
     # ---- tensor-core conv family ------------------------------------------------------
-    def conv2d_fwd(self, x, wk, bias, y, kh, kw, relu=True, residual=None, flops=None):
+    def conv2d_fwd(self, x, wk, bias, y, kh, kw, relu=True, residual=None, flops=None, relu_bits=None):
+        """`relu_bits` (int32 [N,H,W,Cout/32]): 1-bit ReLU mask of y written by the same epilogue."""
         n, h, w, cin = x.shape
         cout = y.shape[3]
         flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if y.dtype == torch.float32 else 0)
         self._w(conv_flops(n, h, w, cin, cout, kh, kw) if flops is None else flops, "flop")
-        self.call("segk_conv2d_fwd", _p(x), _p(wk), _p(bias), _p(residual), _p(y), n, h, w, cin, cout, kh, kw,
+        self.call("segk_conv2d_fwd", _p(x), _p(wk), _p(bias), _p(residual), _p(y), _p(relu_bits), n, h, w, cin, cout, kh, kw,
                   flags, _stream())
         return y
 
-    def conv2d_dgrad(self, dy, wd, dx, kh, kw, relu_mask=None, residual=None, scale=1.0, flops=None, colsum=None):
-        """`colsum` (fp32 [Cin]): column sums of dx from the same pass = BiasAddGrad of the producer layer."""
+    def relu_bits(self, y, bits):
+        """bits (int32 [..., C/32]) <- [y > 0] of a finished bf16 tensor."""
+        c = y.shape[-1]
+        self._w(float(y.numel() * y.element_size()), "byte")
+        self.call("segk_relu_bits", _p(y), _p(bits), y.numel() // c, c, _stream())
+        return bits
+
+    def conv2d_dgrad(self, dy, wd, dx, kh, kw, relu_mask=None, residual=None, scale=1.0, flops=None, colsum=None,
+                     relu_mask_bits=None):
+        """`colsum` (fp32 [Cin]): column sums of dx from the same pass = BiasAddGrad of the producer layer.
+        `relu_mask_bits`: the producer's 1-bit mask (conv2d_fwd's relu_bits) instead of the bf16 tensor `relu_mask`."""
         n, h, w, cout = dy.shape
         cin = dx.shape[3]
         self._w(conv_flops(n, h, w, cin, cout, kh, kw) if flops is None else flops, "flop")
-        self.call("segk_conv2d_dgrad", _p(dy), _p(wd), _p(relu_mask), _p(residual), _p(dx), _p(colsum), float(scale), n, h, w,
-                  cin, cout, kh, kw, _stream())
+        self.call("segk_conv2d_dgrad", _p(dy), _p(wd), _p(relu_mask), _p(relu_mask_bits), _p(residual), _p(dx), _p(colsum),
+                  float(scale), n, h, w, cin, cout, kh, kw, _stream())
         return dx
 
     def conv2d_wgrad(self, x, dy, dw, kh, kw, accumulate=False, flops=None):

@@ -494,3 +494,73 @@ def test_conv2d_fwd_pool_bit_exact_vs_two_kernels(ops, cuda_device, shape):
     assert torch.equal(p2, p1) and torch.equal(i2, i1), f"pool_only {shape}"
     assert bool((y2 == 7.0).all()), "pool_only must not write the pre-pool tensor"
     assert float((p0 == 0).float().mean()) > 0.05          # the tie case is exercised
+
+
+def _pack_bits(y):
+    """[N,H,W,C] bf16 tensor -> int32 [N,H,W,C/32] words, bit i of word w = (y[..., 32 w + i] > 0)."""
+    n, h, w, c = y.shape
+    b = (y.float() > 0).to(torch.int64).view(n, h, w, c // 32, 32)
+    weights = (1 << torch.arange(32, device=y.device, dtype=torch.int64))
+    words = (b * weights).sum(-1)
+    return torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 16, 60, 64, 64, 3),      # slab3
+    (2, 64, 96, 64, 128, 3),     # slab_kernel<128>
+    (3, 20, 72, 128, 256, 3),    # igemm<256>
+    (1, 5, 18, 256, 128, 7),     # few tiles, long K walk: split / tap-split schedules (finish kernels)
+    (2, 6, 10, 64, 192, 1),      # 1x1, three channel tiles
+])
+def test_relu_mask_bits_fwd_and_dgrad(ops, cuda_device, shape):
+    """1-bit ReLU masks: the forward epilogue's relu_bits equal [stored y > 0] exactly, and a dgrad that takes the
+    producer's mask as bits gives the same bits as one that reads the bf16 activation."""
+    n, h, w, ci, co, k = shape
+    x, wt, b = _conv_case(shape, 80)
+    wk, wd = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    xd, bd = dev_bf16(x, cuda_device), dev_f32(b - 0.2, cuda_device)
+    y0 = torch.empty((n, h, w, co), dtype=torch.bfloat16, device=cuda_device)
+    y1 = torch.empty_like(y0)
+    bits = torch.full((n, h, w, co // 32), 0x5a5a5a5a, dtype=torch.int32, device=cuda_device)
+    ops.conv2d_fwd(xd, wk, bd, y0, k, k, relu=True)
+    ops.conv2d_fwd(xd, wk, bd, y1, k, k, relu=True, relu_bits=bits)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y0)
+    assert torch.equal(bits, _pack_bits(y1)), f"relu bits {shape}"
+    assert 0.05 < float((y1 > 0).float().mean()) < 0.95
+    # consumer side: dgrad of a layer whose INPUT is `act` (mask of shape dx)
+    rng = np.random.default_rng(81)
+    dy = dev_bf16(bf16_grid(rng.standard_normal((n, h, w, co))), cuda_device)
+    act = dev_bf16(bf16_grid(rng.standard_normal((n, h, w, ci))), cuda_device)
+    res = dev_bf16(bf16_grid(rng.standard_normal((n, h, w, ci))), cuda_device)
+    abits = _pack_bits(act)
+    dx0 = torch.full((n, h, w, ci), 7.0, dtype=torch.bfloat16, device=cuda_device)
+    dx1 = torch.full_like(dx0, 7.0)
+    ops.conv2d_dgrad(dy, wd, dx0, k, k, relu_mask=act, residual=res, scale=1.25)
+    ops.conv2d_dgrad(dy, wd, dx1, k, k, relu_mask_bits=abits, residual=res, scale=1.25)
+    torch.cuda.synchronize()
+    assert torch.equal(dx1, dx0), f"dgrad with mask bits {shape}"
+    if ci % 32 == 0:
+        cs0 = torch.empty(ci, dtype=torch.float32, device=cuda_device)
+        cs1 = torch.empty_like(cs0)
+        ops.conv2d_dgrad(dy, wd, dx0, k, k, relu_mask=act, colsum=cs0)
+        ops.conv2d_dgrad(dy, wd, dx1, k, k, relu_mask_bits=abits, colsum=cs1)
+        torch.cuda.synchronize()
+        assert torch.equal(dx1, dx0) and torch.equal(cs1, cs0)
+
+
+def test_first_layer_relu_bits(ops, cuda_device):
+    n, h, w = 2, 16, 72
+    img = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device=cuda_device)
+    wt = _conv_case((1, 4, 4, 3, 64, 3), 82)[1] * 0.05
+    wk1 = ops.pack_im2col_weights(dev_f32(wt, cuda_device))
+    bias = dev_f32(np.full(64, -2.0, np.float32), cuda_device)
+    y0 = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=cuda_device)
+    y1 = torch.empty_like(y0)
+    bits = torch.full((n, h, w, 2), 0x5a5a5a5a, dtype=torch.int32, device=cuda_device)
+    ops.conv2d_first_fwd(img, wk1, bias, y0, 3, 3, relu=True)
+    ops.conv2d_first_fwd(img, wk1, bias, y1, 3, 3, relu=True, relu_bits=bits)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y0)
+    assert torch.equal(bits, _pack_bits(y1))
+    assert 0.05 < float((y1 > 0).float().mean()) < 0.95

@@ -9,8 +9,9 @@ import torch
 from semanticsegmentation_tensorflow_b200.fcn import FCN, AdamOptimizer
 from semanticsegmentation_tensorflow_b200.ops import Profile
 
-TC = ("segk_conv2d_fwd", "segk_conv2d_dgrad", "segk_conv2d_wgrad", "segk_deconv2d_fwd", "segk_deconv2d_dgrad",
-      "segk_deconv2d_wgrad", "segk_conv2d_first_fwd", "segk_conv2d_first_wgrad")
+TC = ("segk_conv2d_fwd", "segk_conv2d_fwd_pool", "segk_conv2d_dgrad", "segk_conv2d_wgrad", "segk_deconv2d_fwd",
+      "segk_deconv2d_dgrad", "segk_deconv2d_wgrad", "segk_deconv2d_packed_fwd", "segk_deconv2d_packed_dgrad",
+      "segk_deconv2d_packed_wgrad", "segk_conv2d_first_fwd", "segk_conv2d_first_wgrad")
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 x = torch.randint(0, 256, (32, 160, 576, 3), dtype=torch.uint8, generator=g).to(dev)
