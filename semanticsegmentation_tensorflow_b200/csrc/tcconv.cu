@@ -431,22 +431,39 @@ __device__ __forceinline__ void epilogue_pool_store(const P& p, const uint8_t* s
   for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const uint4*>(sbuf + rows[k] * 128 + ((pc ^ (rows[k] & 7)) << 4));
   uint32_t outw[4];
   uint32_t idxw[2] = {0u, 0u};
+  if (p.relu) {
+    // ReLU outputs are non-negative (never -0: max(-0, +0) = +0), and non-negative bf16 patterns order like 16-bit
+    // integers: per-halfword SIMD max / compare instead of unpacking to fp32.  First-max index = the first window
+    // position whose value equals the maximum -- the element a strict '>' scan stops at.
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t w0 = (&v[0].x)[j];
-    float2 best = unpack_bf16x2(w0);
-    uint32_t bits_lo = w0 & 0xffffu, bits_hi = w0 >> 16;
-    uint32_t k_lo = 0, k_hi = 0;
-#pragma unroll
-    for (int k = 1; k < 4; ++k) {
-      const uint32_t wk = (&v[k].x)[j];
-      const float2 f = unpack_bf16x2(wk);
-      if (f.x > best.x) { best.x = f.x; bits_lo = wk & 0xffffu; k_lo = k; }
-      if (f.y > best.y) { best.y = f.y; bits_hi = wk >> 16; k_hi = k; }
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w0 = (&v[0].x)[j], w1 = (&v[1].x)[j], w2 = (&v[2].x)[j], w3 = (&v[3].x)[j];
+      const uint32_t m = __vmaxu2(__vmaxu2(w0, w1), __vmaxu2(w2, w3));
+      const uint32_t e0 = __vcmpeq2(w0, m), e1 = __vcmpeq2(w1, m), e2 = __vcmpeq2(w2, m);      // 0xffff per equal half
+      // per half: e0 ? 0 : e1 ? 1 : e2 ? 2 : 3
+      const uint32_t k = ~e0 & ((e1 & 0x00010001u) | (~e1 & ((e2 & 0x00020002u) | (~e2 & 0x00030003u))));
+      outw[j] = m;
+      const int e = 2 * j;
+      idxw[e >> 2] |= ((k & 0xffu) << (8 * (e & 3))) | (((k >> 16) & 0xffu) << (8 * ((e + 1) & 3)));
     }
-    outw[j] = bits_lo | (bits_hi << 16);
-    const int e = 2 * j;
-    idxw[e >> 2] |= (k_lo << (8 * (e & 3))) | (k_hi << (8 * ((e + 1) & 3)));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w0 = (&v[0].x)[j];
+      float2 best = unpack_bf16x2(w0);
+      uint32_t bits_lo = w0 & 0xffffu, bits_hi = w0 >> 16;
+      uint32_t k_lo = 0, k_hi = 0;
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        const uint32_t wk = (&v[k].x)[j];
+        const float2 f = unpack_bf16x2(wk);
+        if (f.x > best.x) { best.x = f.x; bits_lo = wk & 0xffffu; k_lo = k; }
+        if (f.y > best.y) { best.y = f.y; bits_hi = wk >> 16; k_hi = k; }
+      }
+      outw[j] = bits_lo | (bits_hi << 16);
+      const int e = 2 * j;
+      idxw[e >> 2] |= (k_lo << (8 * (e & 3))) | (k_hi << (8 * ((e + 1) & 3)));
+    }
   }
   const int64_t o = (((int64_t)n * (p.H >> 1) + (iy >> 1)) * (p.W >> 1) + (ix >> 1)) * p.ldo + ch0 + pc * 8;
   *reinterpret_cast<uint4*>(p.pool_out + o) = make_uint4(outw[0], outw[1], outw[2], outw[3]);

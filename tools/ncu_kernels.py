@@ -35,11 +35,25 @@ order = []
 
 
 def fwd(c, name):
-    ops.conv2d_fwd(c["x"], c["wk"], c["b"], c["y"], c["k"], c["k"], relu=True); order.append(name + " fwd")
+    if name == "conv6":
+        ops.conv2d_fwd(c["x"], c["wk"], c["b"], c["y"], c["k"], c["k"], relu=True); order.append(name + " fwd")
+        return
+    # the step's real call for the conv in front of a pool: pool in the epilogue, pre-pool tensor not stored
+    n, h, w, co = c["y"].shape
+    if "pooled" not in c:
+        c["pooled"] = torch.empty((n, h // 2, w // 2, co), dtype=torch.bfloat16, device=dev)
+        c["idx"] = torch.empty((n, h // 2, w // 2, co), dtype=torch.uint8, device=dev)
+    ops.conv2d_fwd_pool(c["x"], c["wk"], c["b"], c["y"], c["pooled"], c["idx"], c["k"], c["k"], relu=True, pool_only=True)
+    order.append(name + " fwd + pool")
 
 
 def dgrad(c, name):
-    ops.conv2d_dgrad(c["dy"], c["wd"], c["dx"], c["k"], c["k"], relu_mask=c["x"]); order.append(name + " dgrad")
+    if name == "conv6":
+        ops.conv2d_dgrad(c["dy"], c["wd"], c["dx"], c["k"], c["k"], relu_mask=c["x"]); order.append(name + " dgrad")
+        return
+    if "bits" not in c:
+        c["bits"] = ops.relu_bits(c["x"], torch.empty(c["x"].shape[:3] + (c["x"].shape[3] // 32,), dtype=torch.int32, device=dev))
+    ops.conv2d_dgrad(c["dy"], c["wd"], c["dx"], c["k"], c["k"], relu_mask_bits=c["bits"]); order.append(name + " dgrad (mask bits)")
 
 
 def wgrad(c, name):
