@@ -524,6 +524,18 @@ def run_secondary(dev, peaks):
     lat.sort()
     out["fcn_infer_160x576_b1_latency_ms"] = {"p50": lat[len(lat) // 2], "p99": lat[min(len(lat) - 1, int(0.99 * len(lat)))],
                                               "min": lat[0], "iters": len(lat)}
+    # the same call replayed from a CUDA graph (net.infer_graphed: one H2D copy + one graph launch + the D2H of the mask)
+    glat = []
+    for i in range(53):
+        e0.record()
+        mask1.copy_(net.infer_graphed(hx1)[1], non_blocking=True)
+        e1.record()
+        e1.synchronize()
+        if i >= 3:
+            glat.append(e0.elapsed_time(e1))
+    glat.sort()
+    out["fcn_infer_160x576_b1_latency_ms"]["cuda_graph"] = {"p50": glat[len(glat) // 2],
+                                                            "p99": glat[min(len(glat) - 1, int(0.99 * len(glat)))], "min": glat[0]}
     return out
 
 

@@ -574,6 +574,9 @@ class FCN(_Feeds):
                 after_layer(l.name)
 
     # -- inference (FCN.py:229,204-206) -----------------------------------------------------
+    def infer_graphed(self, image):
+        return _infer_graphed(self, image)
+
     def infer(self, image=None):
         """softmax at keep_prob 1.0 and the road mask softmax[...,1] > 0.5."""
         if image is not None:
@@ -590,6 +593,51 @@ class FCN(_Feeds):
         self.ops.softmax_infer(self.logits, prob, mask)
         self.mark_step_end()
         return prob, mask
+
+
+def _infer_graphed(net, image):
+    """`net.infer(image)` replayed from a CUDA graph: the forward pass + softmax + road mask are captured once (the
+    launches are static: same pointers, shapes and tensor maps every call) and each call is one host->static-buffer
+    copy plus one graph launch -- for the per-image inference loop of gen_test_output (FCN.py:224-231), where the
+    23 kernel launches of a batch-1 forward cost more host time than GPU time.  Returns (prob, mask) in static
+    buffers that the next call overwrites."""
+    st = net.__dict__.setdefault("_igraph", {})
+    img = net._as_image(image)
+    if tuple(img.shape) != (net.N, net.H, net.W, net.Cin):
+        raise ValueError(f"image shape {tuple(img.shape)} != planned {(net.N, net.H, net.W, net.Cin)}")
+    if not st:
+        st["x"] = torch.empty((net.N, net.H, net.W, net.Cin), dtype=img.dtype, device=net.device)
+        st["prob"] = torch.empty_like(net.logits)
+        st["mask"] = torch.empty((net.N, net.H, net.W), dtype=torch.uint8, device=net.device)
+        st["x"].copy_(img)
+
+        def body():
+            kp, net.keep_prob = net.keep_prob, 1.0
+            mb = getattr(net, "use_mask_bits", False)
+            net.use_mask_bits = False
+            x0, net.x = net.x, st["x"]
+            try:
+                net.forward()
+                net.ops.softmax_infer(net.logits, st["prob"], st["mask"])
+            finally:
+                net.keep_prob, net.use_mask_bits, net.x = kp, mb, x0
+
+        side = torch.cuda.Stream(net.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):            # warm-up outside the capture: the context's grow-only scratch is allocated here
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(net.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            body()
+        st["graph"] = g
+    if st["x"].dtype != img.dtype:
+        raise TypeError("graphed inference was captured for another image dtype")
+    st["x"].copy_(img, non_blocking=True)
+    st["graph"].replay()
+    return st["prob"], st["mask"]
 
 
 def gen_test_output(net, images):

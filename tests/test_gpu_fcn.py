@@ -239,6 +239,27 @@ def test_inference_softmax_and_road_mask(cuda_device):
     assert mask.shape == (N, H, W)
 
 
+def test_graphed_inference_matches_eager(cuda_device):
+    """net.infer_graphed: the forward + softmax + road mask replayed from a CUDA graph give the bits of net.infer, for
+    the captured image and for later images (host and device feeds)."""
+    net, variables, x, lab = _build(cuda_device, "he")
+    rng = np.random.default_rng(5)
+    imgs = [x, rng.integers(0, 8, x.shape, dtype=np.uint8), rng.integers(0, 8, x.shape, dtype=np.uint8)]
+    for i, im in enumerate(imgs):
+        t = torch.as_tensor(im)
+        feed = t.pin_memory() if i % 2 else t.to(cuda_device)
+        p0, m0 = net.infer(t.to(cuda_device))
+        p0, m0 = p0.clone(), m0.clone()
+        p1, m1 = net.infer_graphed(feed)
+        torch.cuda.synchronize()
+        assert torch.equal(p1, p0) and torch.equal(m1, m0), f"image {i}"
+    # training still works on the same net afterwards (the capture left no state behind)
+    from semanticsegmentation_tensorflow_b200.fcn import AdamOptimizer
+    step = AdamOptimizer(1e-4).minimize(net)
+    l0 = float(step({net.image: torch.as_tensor(x).to(cuda_device), net.annotation: torch.as_tensor(lab).to(cuda_device)}))
+    assert np.isfinite(l0)
+
+
 def test_full_resolution_inference_384x1248(cuda_device):
     """BASELINE configs[3] shape: FCN-8s forward at 384x1248 with the real fc=4096 head, batch 1,
     vs the fp32-arithmetic oracle mirroring bf16 storage (logits rtol 2e-2, margin-conditioned argmax
