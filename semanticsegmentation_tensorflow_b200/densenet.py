@@ -195,11 +195,11 @@ def _r64(c):
 class _Layout:
     """Physical channel layout of a tensor: logical segments, each padded to a multiple of 8."""
 
-    def __init__(self, segs):
+    def __init__(self, segs, align=64):
         self.segs = list(segs)
         self.logical = sum(self.segs)
         self.used = sum(_r8(s) for s in self.segs)           # physical channels carrying data (+ inner pads)
-        self.cp = _r64(self.used)
+        self.cp = -(-self.used // align) * align
         cmap = np.full(self.cp, -1, np.int32)
         lo = po = 0
         for s in self.segs:
@@ -272,7 +272,12 @@ class FCDenseNet(_Feeds):
                 h, w = h * 2, w * 2
             hw[n.name] = (h, w)
             if n.kind == "concat":
-                lay[n.name] = _Layout([s for t in n.inputs for s in lay[t].segs])
+                # A concat that only feeds a transposed conv (the decoder's Concat([up, skip]), FCDenseNet.py:146-147) is that
+                # layer's GEMM-N in dgrad / wgrad: 320 / 448 / 576 / 704 channels would mean 64-wide tiles (bound by shared-
+                # memory operand reads, measured 0.28 PFLOP/s); padded to a multiple of 128 they take 128 / 256-wide tiles
+                readers = [m for m in nodes if n.name in m.inputs]
+                wide = bool(readers) and all(m.kind == "deconv" for m in readers)
+                lay[n.name] = _Layout([s for t in n.inputs for s in lay[t].segs], align=128 if wide else 64)
             elif n.kind in ("conv", "deconv"):
                 lay[n.name] = _Layout([n.cout])
             else:
