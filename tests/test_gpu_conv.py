@@ -566,3 +566,34 @@ def test_first_layer_relu_bits(ops, cuda_device):
     assert torch.equal(y1, y0)
     assert torch.equal(bits, _pack_bits(y1))
     assert 0.05 < float((y1 > 0).float().mean()) < 0.95
+
+
+@pytest.mark.parametrize("shape", [(3, 10, 38, 64, 64, 3), (2, 12, 70, 64, 128, 3), (1, 6, 46, 128, 256, 3), (2, 8, 34, 64, 64, 3),
+                                   (5, 6, 10, 64, 192, 1)])
+def test_fused_pool_and_mask_bits_stay_inside_their_outputs(ops, cuda_device, shape):
+    """Ragged maps (widths that are not multiples of the 30- / box-wide tiles, batches that do not fill the last box)
+    through the fused pool epilogue and the mask-bit stores, with guard bytes around every output."""
+    n, h, w, ci, co, k = shape
+    x, wt, b = _conv_case(shape, 90)
+    wk, wd = ops.pack_conv_weights(dev_f32(wt, cuda_device))
+    xd, bd = dev_bf16(x, cuda_device), dev_f32(b, cuda_device)
+    y, chk_y = _guarded((n, h, w, co), torch.bfloat16, cuda_device)
+    p, chk_p = _guarded((n, h // 2, w // 2, co), torch.bfloat16, cuda_device)
+    i, chk_i = _guarded((n, h // 2, w // 2, co), torch.uint8, cuda_device)
+    for pool_only in (False, True):
+        ops.conv2d_fwd_pool(xd, wk, bd, y, p, i, k, k, relu=True, pool_only=pool_only)
+        chk_y("fused-pool conv output"); chk_p("pooled tensor"); chk_i("pool indices")
+    y0 = torch.empty((n, h, w, co), dtype=torch.bfloat16, device=cuda_device)
+    p0, i0 = torch.empty_like(p), torch.empty_like(i)
+    ops.conv2d_fwd_pool(xd, wk, bd, y, p, i, k, k, relu=True, pool_only=False)
+    ops.maxpool_fwd(y, p0, i0)
+    torch.cuda.synchronize()
+    assert torch.equal(p, p0) and torch.equal(i, i0)
+    bits, chk_b = _guarded((n, h, w, co // 32), torch.int32, cuda_device)
+    ops.conv2d_fwd(xd, wk, bd, y0, k, k, relu=True, relu_bits=bits)
+    chk_b("relu bits")
+    assert torch.equal(bits, _pack_bits(y0))
+    dx, chk_dx = _guarded((n, h, w, ci), torch.bfloat16, cuda_device)
+    dy = dev_bf16(bf16_grid(np.random.default_rng(91).standard_normal((n, h, w, co))), cuda_device)
+    ops.conv2d_dgrad(dy, wd, dx, k, k, relu_mask_bits=_pack_bits(xd))
+    chk_dx("dgrad with mask bits")

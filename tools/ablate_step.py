@@ -33,13 +33,14 @@ print("full step            %.3f ms" % timeit(lambda: step(feed)))
 real_bias = ops.bias_grad
 ops.bias_grad = lambda d, g: g
 print("no bias_grad         %.3f ms" % timeit(lambda: step(feed)))
-real_apply, real_repack = opt.apply, net.vars.repack
+real_apply, real_repack, real_fused = opt.apply, net.vars.repack, opt.apply_and_repack
 opt.apply = lambda *a, **k: None
+opt.apply_and_repack = lambda *a, **k: None
 net.vars.repack = lambda *a, **k: None
 print("no bias, adam, pack  %.3f ms" % timeit(lambda: step(feed)))
 ops.bias_grad = real_bias
 print("no adam, pack        %.3f ms" % timeit(lambda: step(feed)))
-opt.apply, net.vars.repack = real_apply, real_repack
+opt.apply, net.vars.repack, opt.apply_and_repack = real_apply, real_repack, real_fused
 
 
 def fwd_only():
@@ -58,7 +59,6 @@ def fwd_bwd():
     net.wside.join()
 
 
-opt.apply = lambda *a, **k: None
 print("fwd + bwd (no opt)   %.3f ms" % timeit(fwd_bwd))
 net.side.enabled = net.wside.enabled = False
 print("fwd + bwd serial     %.3f ms" % timeit(fwd_bwd))
