@@ -31,7 +31,8 @@ namespace {
 using namespace tc;
 
 constexpr int kThreads = 320;            // igemm / slab kernels: warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
-constexpr int kWgradThreads = 192;       // wgrad: warps 2-5 epilogue (one pass at the end of a long K walk)
+constexpr int kWgradThreads = 320;       // wgrad: warps 2-9 epilogue, two per TMEM lane quarter (one 32-column half of every 64-column group each):
+                                         // a 128 x 256 fp32 tile is 128 KB of row-strided stores per item, which four warps could not hide under conv6's 10.6 us items
 constexpr int kEpiThreads = 256;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;             // bf16 elements = one 128-byte swizzle row
@@ -1287,7 +1288,7 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ Wg
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kWgradThreads - 64);
     }
     fence_barrier_init();
   }
@@ -1395,6 +1396,7 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ Wg
     }
   } else {
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -1415,7 +1417,7 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ Wg
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
         tmem_ld_wait();
