@@ -133,6 +133,13 @@ int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float*
 int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask,
                         void* dx, float* dx_colsum, int N, int H, int W, int Cin, int Cout, int k, int s,
                         void* stream);
+/* Conv2D with a 2s x 2s kernel, stride s, SAME padding (the 4x4 stride-2 encoder convs of LidCamNet.py:28-33): the same
+ * strided implicit GEMM with the conv_layer epilogue.  x [N,sH,sW,Cin] bf16 -> y [N,H,W,Cout] = relu(conv(x, W, stride s)
+ * + b); wd = the dgrad layout segk_pack_deconv_weights produces from the HWIO weights W [k,k,Cin,Cout] (read as the
+ * weights of a transposed conv Cout -> Cin).  Its input gradient is segk_deconv2d_fwd(dy, wk, ...) and its weight
+ * gradient segk_deconv2d_wgrad with x and dy swapped (x := dy [N,H,W,Cout], dy := x [N,sH,sW,Cin]); k = 4, s = 2. */
+int segk_conv2d_strided_fwd(segk_ctx* ctx, const void* x, const void* wd, const float* bias, void* y, int N, int H,
+                            int W, int Cin, int Cout, int k, int s, unsigned flags, void* stream);
 
 /* gradient of deconv_layer wrt W[k,k,Cout,Cin] (fp32). k=4, s=2. */
 int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H,
@@ -315,6 +322,15 @@ int segk_resize_bilinear_bwd(segk_ctx* ctx, const void* dy, void* dx, int N, int
 /* Global_Avg_Pool (utils.py:312-313: tflearn global_avg_pool = mean over H, W): x [N,H,W,C] -> y [N,C]; gradient dx = dy / (H W) */
 int segk_global_avgpool_fwd(segk_ctx* ctx, const void* x, void* y, int N, int H, int W, int C, void* stream);
 int segk_global_avgpool_bwd(segk_ctx* ctx, const void* dy, void* dx, int N, int H, int W, int C, void* stream);
+/* Global_Max_Pool (utils.py:315-316: tflearn global_max_pool = reduce_max over H, W): x [N,H,W,C] bf16 -> y [N,C];
+ * count [N,C] int32 = number of maximal elements, for the gradient, which TF's reduce_max spreads equally over ties:
+ * dx = (x == y) ? dy / count : 0 */
+int segk_global_maxpool_fwd(segk_ctx* ctx, const void* x, void* y, int* count, int N, int H, int W, int C, void* stream);
+int segk_global_maxpool_bwd(segk_ctx* ctx, const void* dy, const void* x, const void* y, const int* count, void* dx,
+                            int N, int H, int W, int C, void* stream);
+/* Zero_Padding (utils.py:325-327: tf.pad with `pad` zeros on each side of H and W): crop == 0: y [N,H+2p,W+2p,C] <-
+ * x [N,H,W,C]; crop == 1 (its gradient): y [N,H,W,C] <- the centre of x [N,H+2p,W+2p,C].  bf16, C % 8 == 0. */
+int segk_zero_pad(segk_ctx* ctx, const void* x, void* y, int N, int H, int W, int C, int pad, int crop, void* stream);
 
 /* Concat (utils.py:332) and its gradient: dst[r][coff_dst + c] (=, or += when accumulate)
  * src[r][coff_src + c] for c < C, zeroed where mask[r][c] <= 0 (mask dense [rows][C] or NULL =

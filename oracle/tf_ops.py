@@ -75,6 +75,17 @@ def global_avg_pool(x: torch.Tensor) -> torch.Tensor:
     return x.mean(dim=(1, 2))
 
 
+def global_max_pool(x: torch.Tensor) -> torch.Tensor:
+    """tflearn global_max_pool (utils.py:315-316): reduce_max over H and W -> [N, C].  Its TF gradient divides dy
+    equally among the maximal elements (math_grad._MinOrMaxGrad: indicators / num_selected); torch.amax does the same."""
+    return x.amax(dim=(1, 2))
+
+
+def zero_padding(x: torch.Tensor, pad: int) -> torch.Tensor:
+    """Zero_Padding (utils.py:325-327): tf.pad with `pad` zeros on every side of H and W."""
+    return F.pad(x, (0, 0, pad, pad, pad, pad))
+
+
 def avg_pool_2x2(x: torch.Tensor) -> torch.Tensor:
     """tf.nn.avg_pool(ksize 2x2, stride 2, 'VALID')  (utils.py:309)."""
     return F.avg_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).contiguous()

@@ -407,9 +407,135 @@ __global__ void __launch_bounds__(kThreads) global_avgpool_bwd_kernel(const bf16
   }
 }
 
+// Global_Max_Pool (utils.py:315-316: tflearn global_max_pool = reduce_max over H, W).  Forward also counts the maximal
+// elements per (n, c): TF's gradient of reduce_max spreads dy equally over ties (indicators / num_selected).
+__global__ void __launch_bounds__(kThreads) global_maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                                      int* __restrict__ count, int HW, int C8) {
+  __shared__ float shm[8][32][9];
+  __shared__ int shc[8][32][9];
+  const int gl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int g = blockIdx.x * 32 + gl, n = blockIdx.y;
+  float m[8];
+  int cnt[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; cnt[j] = 0; }
+  if (g < C8) {
+    const uint4* base = reinterpret_cast<const uint4*>(x) + (int64_t)n * HW * C8 + g;
+    for (int p = pl; p < HW; p += 8) {
+      const uint4 u = __ldg(base + (int64_t)p * C8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2((&u.x)[j]);
+        const float v[2] = {f.x, f.y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int e = 2 * j + h;
+          if (v[h] > m[e]) { m[e] = v[h]; cnt[e] = 1; }
+          else if (v[h] == m[e]) ++cnt[e];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { shm[pl][gl][j] = m[j]; shc[pl][gl][j] = cnt[j]; }
+  __syncthreads();
+  if (pl == 0 && g < C8) {
+    float t[8];
+    int c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      t[j] = shm[0][gl][j]; c[j] = shc[0][gl][j];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) {
+        const float v = shm[k][gl][j];
+        if (v > t[j]) { t[j] = v; c[j] = shc[k][gl][j]; }
+        else if (v == t[j]) c[j] += shc[k][gl][j];
+      }
+    }
+    reinterpret_cast<uint4*>(y)[(int64_t)n * C8 + g] =
+        make_uint4(pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7]));
+    int4* cp = reinterpret_cast<int4*>(count + ((int64_t)n * C8 + g) * 8);
+    cp[0] = make_int4(c[0], c[1], c[2], c[3]);
+    cp[1] = make_int4(c[4], c[5], c[6], c[7]);
+  }
+}
+
+// dx = (x == y) ? dy / count : 0
+__global__ void __launch_bounds__(kThreads) global_maxpool_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                                      const bf16* __restrict__ y, const int* __restrict__ count,
+                                                                      bf16* __restrict__ dx, int N, int HW, int C8) {
+  const int64_t total = (int64_t)N * HW * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % C8);
+    const int n = (int)(i / ((int64_t)HW * C8));
+    const int64_t nc = (int64_t)n * C8 + g;
+    const uint4 ud = __ldg(reinterpret_cast<const uint4*>(dy) + nc), uy = __ldg(reinterpret_cast<const uint4*>(y) + nc);
+    const uint4 ux = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    const int4 c0 = __ldg(reinterpret_cast<const int4*>(count + nc * 8)), c1 = __ldg(reinterpret_cast<const int4*>(count + nc * 8) + 1);
+    const int c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fd = unpack_bf16x2((&ud.x)[j]), fy = unpack_bf16x2((&uy.x)[j]), fx = unpack_bf16x2((&ux.x)[j]);
+      o[j] = pack_bf16x2(fx.x == fy.x ? fd.x / (float)c[2 * j] : 0.f, fx.y == fy.y ? fd.y / (float)c[2 * j + 1] : 0.f);
+    }
+    reinterpret_cast<uint4*>(dx)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// Zero_Padding (utils.py:325-327: tf.pad with `pad` zeros on every side of H and W); backward = the centre crop
+__global__ void __launch_bounds__(kThreads) zero_pad_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W,
+                                                            int C8, int pad, int crop) {
+  // crop == 0: y [N,H+2p,W+2p,C] <- x [N,H,W,C];  crop == 1: y [N,H,W,C] <- x [N,H+2p,W+2p,C]
+  const int OH = crop ? H : H + 2 * pad, OW = crop ? W : W + 2 * pad;
+  const int IH = crop ? H + 2 * pad : H, IW = crop ? W + 2 * pad : W;
+  const int64_t total = (int64_t)N * OH * OW * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % C8);
+    int64_t p = i / C8;
+    const int ox = (int)(p % OW);
+    p /= OW;
+    const int oy = (int)(p % OH);
+    const int n = (int)(p / OH);
+    const int iy = crop ? oy + pad : oy - pad, ix = crop ? ox + pad : ox - pad;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < IH && ix >= 0 && ix < IW) v = __ldg(x + (((int64_t)n * IH + iy) * IW + ix) * C8 + g);
+    y[i] = v;
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int segk_global_maxpool_fwd(segk_ctx* ctx, const void* x, void* y, int* count, int N, int H, int W, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && y && count && N > 0 && H > 0 && W > 0 && C % 8 == 0 && C > 0 && N <= 65535,
+               "global_maxpool_fwd: bad args (C %% 8 == 0)");
+  global_maxpool_fwd_kernel<<<dim3(ceil_div(C / 8, 32), N), kThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, count, H * W,
+                                                                                                  C / 8);
+  SEGK_LAUNCHED(ctx, "global_maxpool_fwd");
+  return SEGK_OK;
+}
+
+int segk_global_maxpool_bwd(segk_ctx* ctx, const void* dy, const void* x, const void* y, const int* count, void* dx, int N, int H,
+                            int W, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, dy && x && y && count && dx && N > 0 && H > 0 && W > 0 && C % 8 == 0 && C > 0, "global_maxpool_bwd: bad args (C %% 8 == 0)");
+  global_maxpool_bwd_kernel<<<sgrid(ctx, (int64_t)N * H * W * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, (const bf16*)x, (const bf16*)y, count, (bf16*)dx, N, H * W, C / 8);
+  SEGK_LAUNCHED(ctx, "global_maxpool_bwd");
+  return SEGK_OK;
+}
+
+int segk_zero_pad(segk_ctx* ctx, const void* x, void* y, int N, int H, int W, int C, int pad, int crop, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, x && y && N > 0 && H > 0 && W > 0 && C % 8 == 0 && C > 0 && pad >= 0, "zero_pad: bad args (C %% 8 == 0)");
+  const int64_t items = (int64_t)N * (crop ? H : H + 2 * pad) * (crop ? W : W + 2 * pad) * (C / 8);
+  zero_pad_kernel<<<sgrid(ctx, items), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, N, H, W, C / 8, pad, crop ? 1 : 0);
+  SEGK_LAUNCHED(ctx, "zero_pad");
+  return SEGK_OK;
+}
 
 int segk_bn_act_fwd(segk_ctx* ctx, const void* x, int ldx, void* y, int ldy, const float* scale, const float* shift,
                     int64_t rows, int C, int relu, const uint8_t* drop_mask, float drop_keep, uint64_t drop_seed, void* stream) {

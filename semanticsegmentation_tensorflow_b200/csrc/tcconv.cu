@@ -2313,8 +2313,27 @@ int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float*
   return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
 }
 
+static int strided_conv_impl(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, const float* bias, int relu,
+                            void* dx, float* dx_colsum, int N, int H, int W, int Cin, int Cout, int k, int s, void* stream);
+
 int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, void* dx, float* dx_colsum,
                         int N, int H, int W, int Cin, int Cout, int k, int s, void* stream) {
+  return strided_conv_impl(ctx, dy, wd, relu_mask, nullptr, 0, dx, dx_colsum, N, H, W, Cin, Cout, k, s, stream);
+}
+
+// Conv2D with kernel 2s x 2s, stride s, SAME (LidCamNet.py:28-33's 4x4 stride-2 encoder convs) = the strided conv that is
+// the transposed conv's input gradient, with the conv_layer epilogue (bias, ReLU).  x [N,sH,sW,Cin] -> y [N,H,W,Cout];
+// wd = the dgrad layout of segk_pack_deconv_weights applied to the HWIO weights [k,k,Cin,Cout] (the layout of a transposed
+// conv Cout -> Cin).  Gradients: segk_deconv2d_fwd (input gradient) and segk_deconv2d_wgrad with the roles of x / dy swapped.
+int segk_conv2d_strided_fwd(segk_ctx* ctx, const void* x, const void* wd, const float* bias, void* y, int N, int H, int W,
+                            int Cin, int Cout, int k, int s, unsigned flags, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, !(flags & SEGK_EPI_OUT_F32), "conv2d_strided_fwd: bf16 output only");
+  return strided_conv_impl(ctx, x, wd, nullptr, bias, (flags & SEGK_EPI_RELU) ? 1 : 0, y, nullptr, N, H, W, Cout, Cin, k, s, stream);
+}
+
+static int strided_conv_impl(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, const float* bias, int relu,
+                            void* dx, float* dx_colsum, int N, int H, int W, int Cin, int Cout, int k, int s, void* stream) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, dy && wd && dx && N > 0 && H > 0 && W > 0, "deconv2d_dgrad: bad args");
   SEGK_REQUIRE(ctx, k == 4 && s == 2, "deconv2d_dgrad: tensor-core path supports k=4, stride 2 (got k=%d s=%d)", k, s);
@@ -2341,6 +2360,7 @@ int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const voi
   p.out_H = H; p.out_W = W; p.ldo = Cin; p.os = 1; p.opad = 0;
   p.out = dx; p.out_f32 = 0;
   p.mask = (const bf16*)relu_mask;
+  p.bias = bias; p.relu = relu;
   p.scale = 1.f;
   p.ksplits = 1; p.ws = nullptr;
   TapTable taps;

@@ -287,6 +287,23 @@ class Ops:
         self.call("segk_deconv2d_wgrad", _p(x), _p(dy), _p(dw), n, h, w, cin, cout, k, s, int(accumulate), _stream())
         return dw
 
+    # ---- Conv2D 4x4 stride 2 SAME (LidCamNet.py:28-33) on the transposed conv's kernels ---------------
+    def conv2d_s2_fwd(self, x, wd, bias, y, relu=True):
+        """x [N,2H,2W,Cin] -> y [N,H,W,Cout]; wd from pack_deconv_weights(W_hwio [4,4,Cin,Cout], 2)[1]."""
+        n, h, w, cout = y.shape
+        cin = x.shape[3]
+        self._w(deconv_flops(n, h, w, cout, cin, 4, 2), "flop")
+        self.call("segk_conv2d_strided_fwd", _p(x), _p(wd), _p(bias), _p(y), n, h, w, cin, cout, 4, 2, EPI_RELU if relu else 0, _stream())
+        return y
+
+    def conv2d_s2_dgrad(self, dy, wk, dx):
+        """dx [N,2H,2W,Cin] = conv2d_transpose(dy [N,H,W,Cout], W); wk from pack_deconv_weights(W_hwio, 2)[0]."""
+        return self.deconv2d_fwd(dy, wk, None, dx, 4, 2)
+
+    def conv2d_s2_wgrad(self, x, dy, dw, accumulate=False):
+        """dw [4,4,Cin,Cout] (HWIO) from x [N,2H,2W,Cin] and dy [N,H,W,Cout]."""
+        return self.deconv2d_wgrad(dy, x, dw, 4, 2, accumulate=accumulate)
+
     # ---- CUDA-core layers for ragged channel counts -------------------------------------
     def conv2d_small_fwd(self, x, w, bias, y, relu=True):
         n, h, wd_, cin = x.shape
@@ -494,6 +511,22 @@ class Ops:
         n, h, w, c = dx.shape
         self.call("segk_global_avgpool_bwd", _p(dy), _p(dx), n, h, w, c, _stream())
         return dx
+
+    def global_maxpool_fwd(self, x, y, count):
+        n, h, w, c = x.shape
+        self.call("segk_global_maxpool_fwd", _p(x), _p(y), _p(count), n, h, w, c, _stream())
+        return y
+
+    def global_maxpool_bwd(self, dy, x, y, count, dx):
+        n, h, w, c = x.shape
+        self.call("segk_global_maxpool_bwd", _p(dy), _p(x), _p(y), _p(count), _p(dx), n, h, w, c, _stream())
+        return dx
+
+    def zero_pad(self, x, y, pad, crop=False):
+        """crop=False: y [N,H+2p,W+2p,C] <- x [N,H,W,C] (Zero_Padding); crop=True: its gradient, y [N,H,W,C] <- centre of x."""
+        n, h, w, c = (y if crop else x).shape
+        self.call("segk_zero_pad", _p(x), _p(y), n, h, w, c, int(pad), int(crop), _stream())
+        return y
 
     def channel_copy(self, src, coff_src, dst, coff_dst, c, mask=None, accumulate=False, drop=None):
         """`drop` = (side, keep_prob, seed, u8 mask or None): dropout of the copied values on the fly, pattern indexed by

@@ -1,6 +1,7 @@
 """GPU parity of the remaining op families of Network/utils/utils.py against oracle/tf_ops.py:
 Atrous_Conv2D_Layer (:210-231) forward / dgrad / wgrad on the tcgen05 implicit GEMM, Resize_Bilinear with
-align_corners=True (:329-330) forward / backward, Global_Avg_Pool (:312-313), Avg_Pooling (:309)."""
+align_corners=True (:329-330) forward / backward, Global_Avg_Pool (:312-313), Global_Max_Pool (:315-316), Avg_Pooling
+(:309), Zero_Padding (:325-327), and the 4x4 stride-2 Conv2D of LidCamNet.py:28-33."""
 import numpy as np
 import pytest
 import torch
@@ -96,3 +97,61 @@ def test_global_and_2x2_average_pools(ops, cuda_device):
     torch.cuda.synchronize()
     up = np.repeat(np.repeat(dyb[..., :cu], 2, axis=1), 2, axis=2) * 0.25
     assert np.array_equal(host(dxb)[..., :cu], bf16_grid(up)) and float(dxb[..., cu:].abs().max()) == 0.0
+
+
+def test_global_max_pool_and_zero_padding(ops, cuda_device):
+    """Global_Max_Pool (utils.py:315-316) with TF's tie-sharing gradient, Zero_Padding (utils.py:325-327) and its crop."""
+    rng = np.random.default_rng(60)
+    n, h, w, c = 3, 9, 14, 136
+    x = bf16_grid(np.round(rng.standard_normal((n, h, w, c)) * 2) / 2)          # coarse grid: ties at the maximum do occur
+    xt = torch.tensor(x, requires_grad=True)
+    y_ref = T.global_max_pool(xt)
+    dy = bf16_grid(rng.standard_normal((n, c)))
+    y_ref.backward(torch.tensor(dy))
+    xd = dev_bf16(x, cuda_device)
+    y = torch.empty((n, c), dtype=torch.bfloat16, device=cuda_device)
+    cnt = torch.empty((n, c), dtype=torch.int32, device=cuda_device)
+    dx = torch.empty_like(xd)
+    ops.global_maxpool_fwd(xd, y, cnt)
+    ops.global_maxpool_bwd(dev_bf16(dy, cuda_device), xd, y, cnt, dx)
+    torch.cuda.synchronize()
+    assert np.array_equal(host(y), y_ref.detach().numpy())
+    ties = (x == x.max(axis=(1, 2), keepdims=True)).sum(axis=(1, 2))
+    assert np.array_equal(cnt.cpu().numpy(), ties) and ties.max() > 1
+    assert_close(host(dx), xt.grad.numpy(), 1e-2, "global max pool grad (dy / ties on every maximal element)")
+    pad = 3
+    yp = torch.empty((n, h + 2 * pad, w + 2 * pad, c), dtype=torch.bfloat16, device=cuda_device)
+    ops.zero_pad(xd, yp, pad)
+    back = torch.empty_like(xd)
+    ops.zero_pad(yp, back, pad, crop=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(host(yp), T.zero_padding(torch.tensor(x), pad).numpy())
+    assert torch.equal(back, xd)
+
+
+@pytest.mark.parametrize("shape", [(2, 12, 20, 64, 128), (3, 10, 36, 128, 64)])
+def test_conv2d_4x4_stride2_fwd_dgrad_wgrad(ops, cuda_device, shape):
+    """Conv2D 4x4 / stride 2 / SAME (LidCamNet.py:28-33) on the transposed conv's kernels: forward = the strided implicit
+    GEMM with bias + ReLU, input gradient = conv2d_transpose, weight gradient with x / dy swapped; vs tf.nn.conv2d."""
+    n, h, w, ci, co = shape                       # (h, w) = OUTPUT size; the input is 2h x 2w
+    rng = np.random.default_rng(61)
+    x = bf16_grid(rng.standard_normal((n, 2 * h, 2 * w, ci)))
+    wt = bf16_grid(rng.standard_normal((4, 4, ci, co)) / np.sqrt(16 * ci))
+    b = rng.standard_normal(co).astype(np.float32) * 0.1
+    dy = bf16_grid(rng.standard_normal((n, h, w, co)))
+    xt, wtt = torch.tensor(x, requires_grad=True), torch.tensor(wt, requires_grad=True)
+    z = T.bias_add(T.conv2d_same(xt, wtt, stride=2), torch.tensor(b))
+    y_ref = T.relu(z).detach().numpy()
+    z.backward(torch.tensor(dy))
+    wk, wd = ops.pack_deconv_weights(dev_f32(wt, cuda_device), 2)
+    xd, dyd = dev_bf16(x, cuda_device), dev_bf16(dy, cuda_device)
+    y = torch.empty((n, h, w, co), dtype=torch.bfloat16, device=cuda_device)
+    dx = torch.empty_like(xd)
+    dw = torch.full((4, 4, ci, co), 7.0, dtype=torch.float32, device=cuda_device)
+    ops.conv2d_s2_fwd(xd, wd, dev_f32(b, cuda_device), y, relu=True)
+    ops.conv2d_s2_dgrad(dyd, wk, dx)
+    ops.conv2d_s2_wgrad(xd, dyd, dw)
+    torch.cuda.synchronize()
+    assert_close(host(y), y_ref, 1e-2, f"4x4 s2 conv fwd {shape}")
+    assert_close(host(dx), xt.grad.numpy(), 1e-2, f"4x4 s2 conv dgrad {shape}")
+    assert_close(host(dw), wtt.grad.numpy(), 2e-3, f"4x4 s2 conv wgrad {shape}")
