@@ -326,7 +326,7 @@ def run_gpu(args):
                                  "(power-capped, ~1340 MHz) cuBLAS figure, `frac_burst` against the burst figure" %
                                  (ms_total / 1e3, clocks.get("sm_mhz") if clocks else None, clocks.get("sm_max_mhz") if clocks else None)),
                 "traffic": traffic,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, average over the entry point's launches of one step under ncu (profiles/ncu_traffic.json, r1d_ncu_step_tc_launches.md)" if traffic else None,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, average over the entry point's launches of one step under ncu (profiles/ncu_traffic.json, r2_ncu_step_tc_launches.md)" if traffic else None,
                 "ncu_tensor_pipe_active_pct": ncu.get("tensor_pipe_active_pct"),
                 "peak_source": peaks["source"] + (" sustained" if bound == "tensor" else ""),
                 "algorithmic_per_launch": d["work"] / d["launches"], "algorithmic_unit": d["unit"],
