@@ -419,6 +419,26 @@ class GraphNet(_Feeds):
         has = {n.name: False for n in self.nodes}
         last = self.nodes[-1].name
         has[last] = True
+        bias_done = set()        # layers whose d(beta) / BiasAddGrad came out of their consumer's dgrad epilogue
+
+        def fused_bias(t):
+            """The input gradient a tensor-core dgrad writes into tensor t -- when this is t's only consumer -- is the
+            pre-activation gradient of t's producer: its column sums, summed in the dgrad epilogue, are that layer's
+            BiasAddGrad / d(beta) (no separate pass over dz)."""
+            p = self.by_name.get(t)
+            if p is None or p.kind not in ("conv", "deconv") or has[t] or not (p.bn or p.bias):
+                return None
+            if sum(1 for m in self.nodes if t in m.inputs) != 1 or self.route.get(p.name) not in ("tc", None):
+                return None
+            if p.kind == "conv" and self.route[p.name] != "tc":
+                return None
+            if self.act[t].dtype != torch.bfloat16 or p.cout % 32:
+                return None
+            c8 = p.cout // 8
+            if not (256 % c8 == 0 if c8 <= 256 else c8 % 256 == 0):
+                return None
+            bias_done.add(p.name)
+            return V.grad(f"{p.bn_scope}/beta") if p.bn else V.grad(f"{p.name}/biases")
         for n in reversed(self.nodes):
             if not has[n.name]:
                 raise RuntimeError(f"{n.name}: output has no consumer gradient")
@@ -452,7 +472,9 @@ class GraphNet(_Feeds):
             # activations); d(beta) is the BiasAddGrad of dz, off the critical path.  The fp32-logit BN of SegNet's
             # head (SegNet.py:80-81) and non-tensor-core routes keep the activation pass.
             gamma_from_dw = n.bn and n.kind == "conv" and r in ("tc", "first") and self.act[n.name].dtype != torch.float32
-            if n.bn:
+            if n.name in bias_done and (gamma_from_dw or not n.bn):
+                pass                               # d(beta) / BiasAddGrad: column sums of the consumer's dgrad epilogue
+            elif n.bn:
                 def bn_grads(dz=dz, n=n, G=G, gamma_from_dw=gamma_from_dw):
                     if self.act[n.name].dtype == torch.float32:
                         ops.bn_grads_f32(G, self.act[n.name], V.param(f"{n.bn_scope}/beta"), V.param(f"{n.bn_scope}/gamma"),
@@ -505,11 +527,11 @@ class GraphNet(_Feeds):
                 if n.kind == "deconv":
                     if res is not None:
                         raise NotImplementedError("deconv input with a second consumer")
-                    ops.deconv2d_dgrad(dz, V.wd[n.name], dx, n.k, n.stride, relu_mask=mask)
+                    ops.deconv2d_dgrad(dz, V.wd[n.name], dx, n.k, n.stride, relu_mask=mask, colsum=fused_bias(t))
                 elif r == "tc":
                     mbits = self._bits_of(t) if mask is not None else None
                     ops.conv2d_dgrad(dz, V.wd[n.name], dx, n.k, n.k, relu_mask=None if mbits is not None else mask,
-                                     relu_mask_bits=mbits, residual=res)
+                                     relu_mask_bits=mbits, residual=res, colsum=fused_bias(t))
                 elif r == "small":
                     if res is not None:
                         raise NotImplementedError("1x1 head input with a second consumer")
