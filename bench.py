@@ -483,6 +483,19 @@ def run_secondary(dev, peaks):
                                      "workload": "BASELINE configs[2] at 1 GPU, host buffers in / loss out"}
     del net, step
     torch.cuda.empty_cache()
+    # the reference's SegNet (SegNet.py:28-87), same workload
+    from semanticsegmentation_tensorflow_b200.graph import SegNet, segnet_nodes
+    net = SegNet(hx.to(dev), NCLS, seed=1234)
+    step = AdamOptimizer(1e-4).minimize(net)
+    feed = {net.image: hx, net.annotation: hy}
+    ms = timed(lambda: loss_host.copy_(step(feed).reshape(1), non_blocking=True), 10)
+    gf = graph_flops_per_image(segnet_nodes(NCLS), H, W, CIN)[1]
+    tf = gf * B / (ms / 1e3) / 1e12
+    out["segnet_train_160x576_b32"] = {"images_per_s": B / (ms / 1e3), "ms_per_step": ms, "tflops": tf,
+                                       "frac_of_burst_peak": tf / peaks["bf16_tflops"], "steps": 10,
+                                       "workload": "the reference's SegNet (SegNet.py:28-87) at 1 GPU, host buffers in / loss out"}
+    del net, step
+    torch.cuda.empty_cache()
     # FCN-8s full-resolution inference, batch 16, host images in / road masks out
     h2, w2, B2 = 384, 1248, 16
     hx2 = torch.randint(0, 256, (B2, h2, w2, CIN), dtype=torch.uint8, generator=gen).pin_memory()

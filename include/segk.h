@@ -73,6 +73,15 @@ int segk_set_tuning(segk_ctx* ctx, const char* key, int value);
 int segk_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* bias,
                     const void* residual, void* y, uint32_t* relu_bits, int N, int H, int W, int Cin,
                     int Cout, int kh, int kw, unsigned flags, void* stream);
+/* conv_layer to a FEW output channels on the tensor cores (a k x k conv to num_classes, e.g. SegNet.py:80's 3x3 64 -> 2
+ * head): wk / bias hold the weights zero-padded to Cout (a multiple of 64) output channels; only the first out_cols
+ * columns of the result are stored, as fp32 y [N,H,W,out_cols].  Backward: segk_pad_channels(dy [rows][out_cols] ->
+ * bf16 [rows][Cout]) and the ordinary segk_conv2d_dgrad / segk_conv2d_wgrad on the padded tensors. */
+int segk_conv2d_fwd_narrow(segk_ctx* ctx, const void* x, const void* wk, const float* bias, float* y, int out_cols,
+                           int N, int H, int W, int Cin, int Cout, int kh, int kw, unsigned flags, void* stream);
+/* dst bf16 [rows][C] = src (fp32 or bf16) [rows][c] zero-padded to C channels (C % 8 == 0) */
+int segk_pad_channels(segk_ctx* ctx, const void* src, int src_is_f32, void* dst, int64_t rows, int c, int C,
+                      void* stream);
 /* the same words from a finished bf16 tensor y [rows][C] (C % 32 == 0): bits[r][w] bit i = (y[r][32 w + i] > 0) */
 int segk_relu_bits(segk_ctx* ctx, const void* y, uint32_t* bits, int64_t rows, int C, void* stream);
 /* relu_bits (or NULL): 1-bit ReLU mask of the bf16 output, u32 [N*H*W][Cout/32], bit i of word w = (y[.., 32 w + i] > 0),

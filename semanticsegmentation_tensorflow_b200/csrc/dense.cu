@@ -504,9 +504,41 @@ __global__ void __launch_bounds__(kThreads) zero_pad_kernel(const uint4* __restr
   }
 }
 
+// dst[r][j] = j < c ? bf16(src[r][j]) : 0 for j < C (C % 8 == 0): a narrow (class-count) gradient padded to a 64-channel
+// GEMM operand; thread = 8 output channels
+template <typename ST>
+__global__ void __launch_bounds__(kThreads) pad_channels_kernel(const ST* __restrict__ src, bf16* __restrict__ dst, int64_t rows, int c,
+                                                                int C8) {
+  const int64_t total = rows * C8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % C8);
+    const int64_t r = i / C8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = g * 8 + j;
+      v[j] = col < c ? (float)src[r * c + col] : 0.f;
+    }
+    reinterpret_cast<uint4*>(dst)[i] =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int segk_pad_channels(segk_ctx* ctx, const void* src, int src_is_f32, void* dst, int64_t rows, int c, int C, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, src && dst && rows > 0 && c > 0 && c <= C && C % 8 == 0, "pad_channels: bad args (0 < c <= C, C %% 8 == 0)");
+  const int64_t items = rows * (C / 8);
+  if (src_is_f32)
+    pad_channels_kernel<float><<<sgrid(ctx, items), kThreads, 0, (cudaStream_t)stream>>>((const float*)src, (bf16*)dst, rows, c, C / 8);
+  else
+    pad_channels_kernel<bf16><<<sgrid(ctx, items), kThreads, 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, rows, c, C / 8);
+  SEGK_LAUNCHED(ctx, "pad_channels");
+  return SEGK_OK;
+}
 
 int segk_global_maxpool_fwd(segk_ctx* ctx, const void* x, void* y, int* count, int N, int H, int W, int C, void* stream) {
   if (!ctx) return SEGK_EINVAL;

@@ -140,6 +140,9 @@ struct IgemmParams {
   // bf16 activation (1/16 of the bytes, one coalesced 4-byte load per thread and column group)
   uint32_t* bits_out;
   const uint32_t* mask_bits;
+  // narrow fp32 output (class-count heads: a 3x3 conv to 2 classes runs as a 64-column tile whose padded columns are
+  // zero weights): only the first out_cols columns are stored, as fp32 [pixels][out_cols]
+  int out_cols;
 };
 
 struct PipeState {
@@ -388,7 +391,15 @@ __device__ __forceinline__ void epilogue_apply_store(const P& p, float (&v)[32],
     for (int i = 0; i < 16; ++i) word |= bf16x2_pos_bits(pack_bf16x2(v[2 * i], v[2 * i + 1])) << (2 * i);
     p.bits_out[off >> 5] = word;
   }
-  if (p.out_f32) {
+  if (p.out_f32 && p.out_cols) {
+    const int col0 = (int)(off % p.ldo);
+    if (col0 < p.out_cols) {
+      float* o = reinterpret_cast<float*>(p.out) + (off / p.ldo) * p.out_cols + col0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.out_cols) o[i] = v[i];
+    }
+  } else if (p.out_f32) {
     float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off);
 #pragma unroll
     for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -791,6 +802,7 @@ struct SlabParams {
   int pool_only;
   uint32_t* bits_out;     // 1-bit ReLU masks out / in (see IgemmParams)
   const uint32_t* mask_bits;
+  int out_cols;           // narrow fp32 output (see IgemmParams)
   void* out;
   int out_f32;
   const float* bias;
@@ -1929,6 +1941,7 @@ struct PoolArgs {
   uint32_t* bits_out = nullptr;          // 1-bit ReLU mask of the output (forward)
   const uint32_t* mask_bits = nullptr;   // 1-bit ReLU mask of the producer layer (dgrad)
   bool bits_done = false;                // out: the launch wrote bits_out itself
+  int out_cols = 0;                      // narrow fp32 output: store only the first out_cols columns
 };
 
 // bits[r][c / 32] from a finished bf16 tensor [rows][C] (forward paths whose epilogue runs in a finish kernel)
@@ -1985,6 +1998,7 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
   }
   if (pool) {
     p.mask_bits = pool->mask_bits;
+    p.out_cols = out_f32 ? pool->out_cols : 0;
     if (pool->bits_out && !out_f32) { p.bits_out = pool->bits_out; pool->bits_done = true; }
   }
   const int total = N * p.tiles_h * p.tiles_w * p.n_tiles;
@@ -2082,6 +2096,8 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   p.scale = scale; p.relu = relu;
   p.ksplits = 1; p.ws = nullptr;
   if (pool) p.mask_bits = pool->mask_bits;         // (bits_out is set below, on the paths whose epilogue runs in the igemm kernel)
+  const bool narrow = pool && out_f32 && pool->out_cols > 0;
+  if (narrow) p.out_cols = pool->out_cols;
   // order the tiles so that what is larger (weights vs activations) is what concurrent CTAs share
   p.m_fastest = ((int64_t)kh * kw * Cn > (int64_t)N * H * W) ? 1 : 0;
   TapTable taps;
@@ -2099,7 +2115,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
     if (pool->bits_out) { p.bits_out = pool->bits_out; pool->bits_done = true; }
     return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
   }
-  if ((tiles * 2 <= ctx->sm_count && p.ntaps * p.kchunks >= 32 && p.kchunks >= 2) || force_ks > 0) {
+  if (!narrow && ((tiles * 2 <= ctx->sm_count && p.ntaps * p.kchunks >= 32 && p.kchunks >= 2) || force_ks > 0)) {
     // one wave of work units.  Measured (tools/time_conv6.py, conv6 dgrad: 50 tiles x 2240 k-steps): 2 splits
     // 483 us, 1: 766, 3: 596, 5: 562, 8: 692, 14: 918 -- more splits than one wave lets the m-tiles that share
     // a weight slice drift apart in K, and the 205 MB of weights stream from DRAM several times over
@@ -2194,7 +2210,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
     int ksr = rem > 0 ? sm / rem : 0;
     if (ksr > p.kchunks) ksr = p.kchunks;            // ksplits <= kchunks <= k-steps of any tile: no piece is empty
     if (ksr > 8) ksr = 8;
-    if (ctx->hybrid && waves >= 1 && waves <= 4 && ksr >= 2 && p.ntaps * p.kchunks >= 8 * ksr) {
+    if (ctx->hybrid && !narrow && waves >= 1 && waves <= 4 && ksr >= 2 && p.ntaps * p.kchunks >= 8 * ksr) {
       const size_t slice = (size_t)N * H * W * Cn;
       rc = ensure_workspace(ctx, sizeof(float) * slice * ksr);
       if (rc) return rc;
@@ -2631,6 +2647,16 @@ static int relu_bits_of(segk_ctx* ctx, const void* y, uint32_t* bits, int64_t ro
   relu_bits_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)y, bits, nwords);
   SEGK_LAUNCHED(ctx, "relu bits");
   return SEGK_OK;
+}
+
+int segk_conv2d_fwd_narrow(segk_ctx* ctx, const void* x, const void* wk, const float* bias, float* y, int out_cols, int N, int H,
+                           int W, int Cin, int Cout, int kh, int kw, unsigned flags, void* stream) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, y && out_cols > 0 && out_cols <= Cout, "conv2d_fwd_narrow: 0 < out_cols <= Cout (got %d of %d)", out_cols, Cout);
+  PoolArgs ex{nullptr, nullptr, 0, false};
+  ex.out_cols = out_cols;
+  return conv_igemm(ctx, "conv2d_fwd_narrow", x, wk, bias, nullptr, nullptr, 1.f, (flags & SEGK_EPI_RELU) ? 1 : 0, 1, y, N, H, W, Cin,
+                    Cout, kh, kw, stream, nullptr, 1, &ex);
 }
 
 int segk_relu_bits(segk_ctx* ctx, const void* y, uint32_t* bits, int64_t rows, int C, void* stream) {

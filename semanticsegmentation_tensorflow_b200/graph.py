@@ -203,7 +203,9 @@ class _Vars:
 
 
 class GraphNet(_Feeds):
-    def __init__(self, x, num_classes, nodes, variables=None, init="ref", seed=1234, world_size=1, overlap=True):
+    def __init__(self, x, num_classes, nodes, variables=None, init="ref", seed=1234, world_size=1, overlap=True,
+                 head_on_tensor_cores=True):
+        self.head_on_tensor_cores = head_on_tensor_cores      # a k x k conv to num_classes as a 64-column tcgen05 tile
         if not torch.cuda.is_available():
             raise RuntimeError("GraphNet needs a CUDA (sm_100a) device: the segmentation ops have no CPU fallback")
         x = torch.as_tensor(x)
@@ -244,6 +246,11 @@ class GraphNet(_Feeds):
             return "im2col"
         if n.k == 1 and n.cout in (2, 4, 8) and cin % 8 == 0:
             return "small"
+        if (n.k == 3 and n.cout in (2, 4, 8) and cin % 64 == 0 and n.name == self.nodes[-1].name
+                and self.H * self.W >= 4096 and getattr(self, "head_on_tensor_cores", True)):
+            # k x k head to num_classes (SegNet.py:80) on the tensor cores: weights zero-padded to 64 output channels,
+            # fp32 logits written by the narrow epilogue (segk_conv2d_fwd_narrow); 2.5 of SegNet's 15 ms on CUDA cores
+            return "head_tc"
         if (n.k in (3, 5) and n.cout in (2, 4) and cin % 8 == 0 and 256 % (cin // 8) == 0
                 and n.k * n.k * (cin // 8) * (8 * n.cout + 4) * 4 <= 48 * 1024):
             return "small"        # k x k head to num_classes (SegNet.py:80)
@@ -283,7 +290,7 @@ class GraphNet(_Feeds):
         for n in self.nodes:
             if n.kind == "conv" and n.relu and self.route[n.name] in ("tc", "first") and n.cout % 32 == 0 and n.name != last:
                 readers = [m for m in self.nodes if n.name in m.inputs]
-                if any(m.kind == "conv" and self.route[m.name] == "tc" for m in readers):
+                if any(m.kind == "conv" and self.route[m.name] in ("tc", "head_tc") for m in readers):
                     self.bits[n.name] = torch.empty(shape[n.name][:3] + (n.cout // 32,), dtype=torch.int32, device=dev)
         self.logits = self.act[last]
         assert self.logits.shape[3] == self.num_classes
@@ -299,6 +306,16 @@ class GraphNet(_Feeds):
         max_c = max([n.cout for n in self.nodes if n.kind == "conv"] + [64])
         self.unfold_ws = [self.ops.bn_unfold_workspace(max_c, dev) for _ in range(2)]
         self.labels = torch.zeros((N, self.H, self.W), dtype=torch.uint8, device=dev)
+        # class-count head on the tensor cores: weights / bias padded to 64 output channels, the logit gradient padded to a
+        # 64-channel bf16 operand, the padded weight gradient
+        self.head_pad, self.head_dz, self.head_gw = {}, {}, {}
+        for n in self.nodes:
+            if n.kind == "conv" and self.route[n.name] == "head_tc":
+                cin = shape[n.inputs[0]][3]
+                self.head_pad[n.name] = (torch.zeros((n.k, n.k, cin, 64), dtype=torch.float32, device=dev),
+                                         torch.zeros(64, dtype=torch.float32, device=dev))
+                self.head_dz[n.name] = torch.empty(shape[n.name][:3] + (64,), dtype=bf, device=dev)
+                self.head_gw[n.name] = torch.empty((n.k, n.k, cin, 64), dtype=torch.float32, device=dev)
 
     def _repack(self, ops, only=None):
         V = self.vars
@@ -318,6 +335,14 @@ class GraphNet(_Feeds):
                 V.wk[n.name], V.wd[n.name] = ops.pack_conv_weights(w, V.wk.get(n.name), V.wd.get(n.name))
             elif r in ("first", "im2col"):
                 V.wk[n.name] = ops.pack_im2col_weights(w, V.wk.get(n.name))
+            elif r == "head_tc":
+                wp, bp = self.head_pad[n.name]
+                ops.remap_weights(w, wp, amap=None, bmap=None, to_phys=True)            # [k,k,Cin,Cout] -> [k,k,Cin,64], zero columns
+                b = self._bias(n)
+                if b is not None:
+                    ops.remap_weights(b.view(1, 1, -1), bp.view(1, 1, -1), amap=None, bmap=None, to_phys=True)
+                V.wk[n.name], V.wd[n.name] = ops.pack_conv_weights(wp, V.wk.get(n.name), V.wd.get(n.name))
+                V.weff[n.name] = w
             else:
                 V.weff[n.name] = w
 
@@ -381,6 +406,9 @@ class GraphNet(_Feeds):
                     P1 = ops.im2col_k64(x, self.patch[n.name], n.k, n.k)
                     ops.conv2d_fwd(P1, V.wk[n.name], self._bias(n), out, 1, 1, relu=n.relu,
                                    flops=conv_flops(self.N, out.shape[1], out.shape[2], x.shape[3], n.cout, n.k, n.k))
+                elif r == "head_tc":
+                    ops.conv2d_fwd_narrow(x, V.wk[n.name], self.head_pad[n.name][1] if self._bias(n) is not None else None, out,
+                                          n.k, n.k, 64, relu=n.relu)
                 else:
                     ops.conv2d_small_fwd(x, V.weff[n.name], self._bias(n), out, relu=n.relu)
         self._ran_forward = True
@@ -468,6 +496,9 @@ class GraphNet(_Feeds):
             dz = G
             if r == "small" and G.dtype == torch.float32:
                 dz = ops.cast_to_bf16(G, self.dlogits_bf16)
+            dz_narrow = dz
+            if r == "head_tc":            # logit gradient [N,H,W,classes] -> bf16 [N,H,W,64] operand (zero columns)
+                dz = ops.pad_channels(G, self.head_dz[n.name])
             # d(gamma) comes out of the weight gradient (segk_bn_unfold_grads below: dgamma = mult * sum_k W dW', no pass over
             # activations); d(beta) is the BiasAddGrad of dz, off the critical path.  The fp32-logit BN of SegNet's
             # head (SegNet.py:80-81) and non-tensor-core routes keep the activation pass.
@@ -487,7 +518,7 @@ class GraphNet(_Feeds):
                                           dbeta=V.grad(f"{n.bn_scope}/beta"))
                 self.side.run(bn_grads)
             elif n.bias and r != "first":      # the fused first-layer wgrad also produces the bias gradient
-                self.side.run(lambda dz=dz, n=n: ops.bias_grad(dz, V.grad(f"{n.name}/biases")))
+                self.side.run(lambda dz=dz_narrow, n=n: ops.bias_grad(dz, V.grad(f"{n.name}/biases")))
             # weight gradient (of the folded weights; unfold the BN scale afterwards).  Tensor-core ones go to
             # the wgrad stream, ordered after this point, launched behind the layer's dgrad
             wjob, wmark = None, None
@@ -514,6 +545,12 @@ class GraphNet(_Feeds):
                     gw.view(-1).copy_(tmp.view(-1)[:gw.numel()])
                     unfold()
                 wjob = im2col_wgrad      # (every tensor-core wgrad on one stream: they share a partial-sum scratch)
+            elif r == "head_tc":
+                def head_wgrad(x=x, dz=dz, gw=gw, gwp=self.head_gw[n.name], n=n, unfold=unfold):
+                    ops.conv2d_wgrad(x, dz, gwp, n.k, n.k, flops=conv_flops(self.N, x.shape[1], x.shape[2], x.shape[3], n.cout, n.k, n.k))
+                    ops.remap_weights(gw, gwp, amap=None, bmap=None, to_phys=False)     # first Cout columns -> the variable's gradient
+                    unfold()
+                wjob = head_wgrad
             else:
                 ops.conv2d_small_wgrad(x, dz, gw)
                 unfold()
@@ -532,6 +569,11 @@ class GraphNet(_Feeds):
                     mbits = self._bits_of(t) if mask is not None else None
                     ops.conv2d_dgrad(dz, V.wd[n.name], dx, n.k, n.k, relu_mask=None if mbits is not None else mask,
                                      relu_mask_bits=mbits, residual=res, colsum=fused_bias(t))
+                elif r == "head_tc":
+                    mbits = self._bits_of(t) if mask is not None else None
+                    ops.conv2d_dgrad(dz, V.wd[n.name], dx, n.k, n.k, relu_mask=None if mbits is not None else mask,
+                                     relu_mask_bits=mbits, residual=res, colsum=fused_bias(t),
+                                     flops=conv_flops(self.N, dx.shape[1], dx.shape[2], dx.shape[3], n.cout, n.k, n.k))
                 elif r == "small":
                     if res is not None:
                         raise NotImplementedError("1x1 head input with a second consumer")

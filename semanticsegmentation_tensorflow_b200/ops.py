@@ -239,6 +239,21 @@ class Ops:
                   flags, _stream())
         return y
 
+    def conv2d_fwd_narrow(self, x, wk, bias, y, kh, kw, cout_padded, relu=False):
+        """Conv to a few output channels on the tensor cores: wk / bias zero-padded to cout_padded channels, y fp32
+        [N,H,W,out_cols] receives the first out_cols columns."""
+        n, h, w, cin = x.shape
+        self._w(conv_flops(n, h, w, cin, y.shape[3], kh, kw), "flop")
+        self.call("segk_conv2d_fwd_narrow", _p(x), _p(wk), _p(bias), _p(y), y.shape[3], n, h, w, cin, int(cout_padded), kh, kw,
+                  EPI_RELU if relu else 0, _stream())
+        return y
+
+    def pad_channels(self, src, dst):
+        """dst bf16 [..., C] = src (fp32 / bf16) [..., c] zero-padded."""
+        c, C = src.shape[-1], dst.shape[-1]
+        self.call("segk_pad_channels", _p(src), int(src.dtype == torch.float32), _p(dst), src.numel() // c, c, C, _stream())
+        return dst
+
     def relu_bits(self, y, bits):
         """bits (int32 [..., C/32]) <- [y > 0] of a finished bf16 tensor."""
         c = y.shape[-1]

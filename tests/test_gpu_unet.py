@@ -199,6 +199,34 @@ def test_segnet_forward_and_gradients(cuda_device):
         assert e <= tol_e and c >= tol_c, f"segnet grad {name}: rel {e:.3e} (tol {tol_e:.3e}) cos {c:.6f} (tol {tol_c:.6f})"
 
 
+def test_segnet_head_on_tensor_cores_matches_cuda_core_head(cuda_device):
+    """The 3x3 conv to num_classes (SegNet.py:80) as a 64-column tensor-core tile with the narrow fp32 epilogue
+    (route "head_tc", taken for maps >= 4096 pixels) against the CUDA-core head kernels on the same variables:
+    logits, loss and every gradient."""
+    from semanticsegmentation_tensorflow_b200.graph import SegNet
+    net0, variables, x0, lab0 = _build_segnet(cuda_device)
+    x, lab = synthetic_batch(1, 64, 96, seed=3, road_shaped=True)
+    x = (x // 32).astype(np.uint8)
+    xd, ld = torch.as_tensor(x).to(cuda_device), torch.as_tensor(lab).to(cuda_device)
+    outs = {}
+    for tc in (True, False):
+        net = SegNet(xd, 2, variables=variables, head_on_tensor_cores=tc)
+        last = net.nodes[-1].name
+        assert net.route[last] == ("head_tc" if tc else "small")
+        _, logits = net.create()
+        loss = net.loss(ld, with_grad=True)
+        net.backward()
+        net.side.join(); net.wside.join()
+        torch.cuda.synchronize()
+        outs[tc] = (logits.clone(), float(loss), {k: net.vars.grad(k).clone() for k in net.vars.slots})
+    # (the tensor-core head multiplies bf16-rounded weights, the CUDA-core head fp32 ones: agreement at the bf16 level)
+    assert rel_err(outs[True][0].cpu().numpy(), outs[False][0].cpu().numpy()) <= 5e-3
+    assert abs(outs[True][1] - outs[False][1]) <= 1e-3 * abs(outs[False][1])
+    for k in outs[True][2]:
+        g, r = outs[True][2][k].cpu().numpy(), outs[False][2][k].cpu().numpy()
+        assert rel_err(g, r) <= 2e-2 and cosine(g, r) >= 0.9995, (k, rel_err(g, r), cosine(g, r))
+
+
 def test_segnet_training_steps(cuda_device):
     from semanticsegmentation_tensorflow_b200.fcn import AdamOptimizer
     net, variables, x, lab = _build_segnet(cuda_device)
