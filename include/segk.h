@@ -384,7 +384,7 @@ int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const
                         const void* residual, void* dx, float* dbias, int N, int H, int W, int C, void* stream);
 
 /* tf.nn.dropout (FCN.py:165-167): y = x * keep_mask / keep_prob.  mask (u8 0/1) is used
- * when non-NULL (parity runs); otherwise Philox4x32-10(seed, element index). Same call is
+ * when non-NULL (parity runs); otherwise Philox4x32-10(seed, element index / 8), 16 bits per element. Same call is
  * the backward (pass dy as x). */
 int segk_dropout(segk_ctx* ctx, const void* x, void* y, const uint8_t* mask, int64_t n,
                  float keep_prob, uint64_t seed, void* stream);

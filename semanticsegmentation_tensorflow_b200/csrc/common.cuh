@@ -131,7 +131,9 @@ __device__ __forceinline__ uint4 segk_philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 // keep bits (bit j = element 8 i + j is kept) of the i-th 8-element group of a dropout tensor: from the injected
-// u8 mask when there is one, else from the Philox stream
+// u8 mask when there is one, else from the Philox stream -- ONE Philox4x32-10 block per group (counter = i), 16 random
+// bits per element: element j is kept iff its 16-bit uniform < keep_prob * 65536 (keep probabilities are resolved to
+// 1 / 65536; the generator, not memory, bounds the kernels that apply dropout on the fly)
 __device__ __forceinline__ uint32_t segk_dropout_keep8(const uint2* __restrict__ mask, int64_t i, float keep, uint64_t seed) {
   uint32_t kp = 0;
   if (mask) {
@@ -140,13 +142,12 @@ __device__ __forceinline__ uint32_t segk_dropout_keep8(const uint2* __restrict__
     for (int j = 0; j < 8; ++j) kp |= ((((&m.x)[j >> 2] >> (8 * (j & 3))) & 0xffu) != 0 ? 1u : 0u) << j;
   } else {
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    const int64_t q = 2 * i;
-    const uint4 r0 = segk_philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), 0u, 0u), key);
-    const uint4 r1 = segk_philox4x32_10(make_uint4((uint32_t)(q + 1), (uint32_t)((q + 1) >> 32), 0u, 0u), key);
+    const uint4 r = segk_philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0u, 0u), key);
+    const uint32_t thr = (uint32_t)(keep * 65536.0f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      kp |= (((&r0.x)[j] >> 8) * (1.0f / 16777216.0f) < keep ? 1u : 0u) << j;
-      kp |= (((&r1.x)[j] >> 8) * (1.0f / 16777216.0f) < keep ? 1u : 0u) << (4 + j);
+      kp |= (((&r.x)[j] & 0xffffu) < thr ? 1u : 0u) << (2 * j);
+      kp |= (((&r.x)[j] >> 16) < thr ? 1u : 0u) << (2 * j + 1);
     }
   }
   return kp;

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const uint4* __re
 }
 
 // ------------------------------------------------------------------------------------
-// dropout (FCN.py:165-167).  Philox4x32-10 keyed by (seed), counter = element index / 4.
+// dropout (FCN.py:165-167).  Philox4x32-10 keyed by (seed), counter = element index / 8, 16 random bits per element.
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) { return segk_philox4x32_10(ctr, key); }
 
@@ -199,27 +199,25 @@ __global__ void __launch_bounds__(kThreads) dropout_kernel(const bf16* __restric
                                                            bf16* __restrict__ y,
                                                            const uint8_t* __restrict__ mask, int64_t n,
                                                            float keep, float inv_keep, uint64_t seed) {
-  const int64_t n4 = (n + 3) >> 2;
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n4;
-       q += (int64_t)gridDim.x * blockDim.x) {
-    uint4 r = make_uint4(0, 0, 0, 0);
-    if (!mask)
-      r = philox4x32_10(make_uint4((uint32_t)q, (uint32_t)(q >> 32), 0u, 0u),
-                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t e = q * 4 + j;
+  // scalar form (any n / alignment): thread = one 8-element group, the same pattern as segk_dropout_keep8
+  const int64_t n8 = (n + 7) >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t kp = 0;
+    if (mask) {
+      for (int j = 0; j < 8 && i * 8 + j < n; ++j) kp |= (mask[i * 8 + j] != 0 ? 1u : 0u) << j;
+    } else {
+      kp = segk_dropout_keep8(nullptr, i, keep, seed);
+    }
+    for (int j = 0; j < 8; ++j) {
+      const int64_t e = i * 8 + j;
       if (e >= n) break;
-      bool kp;
-      if (mask) kp = mask[e] != 0;
-      else kp = ((&r.x)[j] >> 8) * (1.0f / 16777216.0f) < keep;
-      y[e] = kp ? f2bf(bf2f(x[e]) * inv_keep) : f2bf(0.f);
+      y[e] = (kp >> j) & 1u ? f2bf(bf2f(x[e]) * inv_keep) : f2bf(0.f);
     }
   }
 }
 
-// The same for n % 8 == 0 and 16-byte aligned buffers: 8 elements per thread (one 16-byte load / store, two
-// Philox blocks with the counters of the scalar form, so both produce the same keep pattern).
+// The same for n % 8 == 0 and 16-byte aligned buffers: 8 elements per thread (one 16-byte load / store), the same
+// keep pattern as the scalar form.
 __global__ void __launch_bounds__(kThreads) dropout_vec8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
                                                                 const uint2* __restrict__ mask, int64_t n8,
                                                                 float keep, float inv_keep, uint64_t seed) {
@@ -852,7 +850,7 @@ int segk_dropout(segk_ctx* ctx, const void* x, void* y, const uint8_t* mask, int
     SEGK_LAUNCHED(ctx, "dropout_vec8");
     return SEGK_OK;
   }
-  dropout_kernel<<<stream_grid(ctx, (n + 3) / 4), kThreads, 0, (cudaStream_t)stream>>>(
+  dropout_kernel<<<stream_grid(ctx, (n + 7) / 8), kThreads, 0, (cudaStream_t)stream>>>(
       (const bf16*)x, (bf16*)y, mask, n, keep_prob, 1.0f / keep_prob, seed);
   SEGK_LAUNCHED(ctx, "dropout");
   return SEGK_OK;
