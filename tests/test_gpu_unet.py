@@ -129,6 +129,7 @@ def test_unet_forward_and_gradients(cuda_device, init):
         g, r, f = net.vars.grad(name).cpu().numpy(), grads_ref[name].numpy(), grads_f32[name].numpy()
         e, c = rel_err(g, r), cosine(g, r)
         tol_e, tol_c = max(5e-2, 3 * rel_err(r, f)), min(0.999, 1 - 9 * (1 - cosine(r, f)))
+        tol_e, tol_c = min(tol_e, 0.15), max(tol_c, 0.99)            # hard floor, whatever the oracle's own bf16 noise
         assert e <= tol_e and c >= tol_c, f"[{init}] grad {name}: rel {e:.3e} (tol {tol_e:.3e}) cos {c:.6f} (tol {tol_c:.6f})"
         if e > worst[1]:
             worst = (name, e, c)
@@ -196,6 +197,7 @@ def test_segnet_forward_and_gradients(cuda_device):
         g, r, f = net.vars.grad(name).cpu().numpy(), grads_ref[name].numpy(), grads_f32[name].numpy()
         e, c = rel_err(g, r), cosine(g, r)
         tol_e, tol_c = max(5e-2, 3 * rel_err(r, f)), min(0.999, 1 - 9 * (1 - cosine(r, f)))
+        tol_e, tol_c = min(tol_e, 0.15), max(tol_c, 0.99)            # hard floor
         assert e <= tol_e and c >= tol_c, f"segnet grad {name}: rel {e:.3e} (tol {tol_e:.3e}) cos {c:.6f} (tol {tol_c:.6f})"
 
 
