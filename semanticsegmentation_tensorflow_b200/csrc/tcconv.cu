@@ -2744,7 +2744,8 @@ static int conv2d_wgrad_impl(segk_ctx* ctx, const void* x, const void* dy, float
   p.n_tiles = Cout / block_n;
   const int base_items = p.n_rbp * p.n_tiles;
   // measured (profiles/, sweep): one wave of items is best once there are >= 16 base items (the
-  // the partial buffers and ordered reduction of extra splits cost more than the tail); tiny item counts want two waves
+  // partial buffers and ordered reduction of extra splits cost more than the tail); tiny item
+  // counts want two waves
   int splits = base_items >= 16 ? ctx->sm_count / base_items : ceil_div(2 * ctx->sm_count, base_items);
   if (ctx->force_wsplit > 0) splits = ctx->force_wsplit;
   const int max_splits = ceil_div(n_ptiles, 8);  // at least 8 k-steps per item
