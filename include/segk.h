@@ -59,6 +59,21 @@ int segk_sm_count(segk_ctx* ctx);
  * accumulation order differs between kernels). */
 int segk_set_tuning(segk_ctx* ctx, const char* key, int value);
 
+/*
+ * Channel-strided tensor views = zero-copy Concat (utils.py:332 `tf.concat(x, axis)`; FCDenseNet.py:141-157's decoder idiom,
+ * the skip concats of the U-Net): a producer writes its [N,H,W,C] output straight into channels [c0, c0+C) of the wider
+ * concat buffer [N,H,W,P], and a consumer of the concat's gradient reads its slice of it in place.  A view is the pointer to
+ * its first element plus the pitch P (channels between consecutive pixels; a multiple of 8, first element 16-byte aligned).
+ * segk_set_pitch applies to the NEXT call on this context only (0 = dense) and is understood by:
+ *   out_pitch:  y  of segk_conv2d_fwd / segk_conv2d_fwd_pool (bf16, no residual / bits), y of segk_deconv2d_fwd (bf16, no
+ *               residual), dx (+ act, residual: the same view geometry) of segk_maxpool2x2_bwd (full-resolution mask mode)
+ *   in_pitch:   dy of segk_conv2d_dgrad / segk_conv2d_wgrad / segk_deconv2d_dgrad / segk_deconv2d_wgrad / segk_bias_grad
+ *               (bf16), x of segk_maxpool2x2_fwd and of segk_conv2d_fwd(_pool)
+ * Any other entry point fails with SEGK_EINVAL while a pitch is pending (nothing silently reads a view as dense).
+ * The tensor-core kernels address views through their TMA descriptors, so a view costs nothing over a dense tensor.
+ */
+int segk_set_pitch(segk_ctx* ctx, int in_pitch, int out_pitch);
+
 /* ---- epilogue flags for the conv family ------------------------------------------------ */
 #define SEGK_EPI_RELU 1u      /* y = max(y,0) after bias (+residual)            */
 #define SEGK_EPI_OUT_F32 2u   /* y stored as fp32 instead of bf16               */

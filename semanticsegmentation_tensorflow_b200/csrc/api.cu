@@ -75,6 +75,15 @@ int segk_set_tuning(segk_ctx* ctx, const char* key, int value) {
   return SEGK_OK;
 }
 
+int segk_set_pitch(segk_ctx* ctx, int in_pitch, int out_pitch) {
+  if (!ctx) return SEGK_EINVAL;
+  SEGK_REQUIRE(ctx, in_pitch >= 0 && out_pitch >= 0 && in_pitch % 8 == 0 && out_pitch % 8 == 0,
+               "set_pitch: pitches are channel counts, multiples of 8 (got %d, %d)", in_pitch, out_pitch);
+  ctx->pitch_in = in_pitch;
+  ctx->pitch_out = out_pitch;
+  return SEGK_OK;
+}
+
 int64_t segk_launch_count(segk_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 int segk_sm_count(segk_ctx* ctx) { return ctx ? ctx->sm_count : 0; }

@@ -30,6 +30,10 @@ struct segk_ctx {
                             //   filled.  Off by default: measured on conv5_x (B=32, 180 tiles on 148 SMs) 58 us vs 51 us for two
                             //   plain waves -- the two epilogues after the last MMA and the finish kernel (launch + 10 us) cost
                             //   more than the 54 idle k-steps they save (profiles/r2_hybrid_probe.md)
+  // one-shot channel pitches of the next conv-family call (segk_set_pitch: zero-copy Concat views); 0 = dense.  The
+  // entry points that understand them take (and clear) them before their first launch; any other launch with a pitch
+  // still pending fails (SEGK_LAUNCHED)
+  int pitch_in = 0, pitch_out = 0;
   void* ws = nullptr;       // grow-only scratch for split-K partial sums (tcconv.cu)
   size_t ws_bytes = 0;
   void* ws2 = nullptr;      // grow-only scratch for per-block BiasAddGrad partials (elementwise.cu)
@@ -62,6 +66,16 @@ inline int segk_fail(segk_ctx* ctx, int code, const char* fmt, ...) {
   return code;
 }
 
+// channel pitches set for this call by segk_set_pitch (consumed: the next call is dense again)
+struct SegkPitch {
+  int in, out;
+};
+inline SegkPitch segk_take_pitch(segk_ctx* ctx) {
+  SegkPitch p{ctx->pitch_in, ctx->pitch_out};
+  ctx->pitch_in = ctx->pitch_out = 0;
+  return p;
+}
+
 #define SEGK_REQUIRE(ctx, cond, ...)                                   \
   do {                                                                 \
     if (!(cond)) return segk_fail((ctx), SEGK_EINVAL, __VA_ARGS__);    \
@@ -71,6 +85,10 @@ inline int segk_fail(segk_ctx* ctx, int code, const char* fmt, ...) {
 #define SEGK_LAUNCHED(ctx, what)                                                        \
   do {                                                                                  \
     (ctx)->launches.fetch_add(1, std::memory_order_relaxed);                            \
+    if ((ctx)->pitch_in | (ctx)->pitch_out) {                                           \
+      (ctx)->pitch_in = (ctx)->pitch_out = 0;                                           \
+      return segk_fail((ctx), SEGK_EINVAL, "%s: a channel pitch (segk_set_pitch) is pending, but this call takes dense tensors only", (what)); \
+    }                                                                                   \
     cudaError_t e__ = cudaGetLastError();                                               \
     if (e__ != cudaSuccess)                                                             \
       return segk_fail((ctx), SEGK_ECUDA, "%s: %s", (what), cudaGetErrorString(e__));   \

@@ -22,7 +22,8 @@ inline int stream_grid(segk_ctx* ctx, int64_t work_items, int per_sm = 8) {
 __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const uint4* __restrict__ x,
                                                                uint4* __restrict__ y,
                                                                uint2* __restrict__ idx, int N, int H,
-                                                               int W, int C8) {
+                                                               int W, int C8, int P8) {
+  // P8: 8-channel groups between consecutive pixels of x (= C8 when dense; a channel slice of a wider tensor otherwise)
   const int OH = H >> 1, OW = W >> 1;
   const int64_t total = (int64_t)N * OH * OW * C8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -33,12 +34,12 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const uint4* __re
     p /= OW;
     int oy = (int)(p % OH);
     int n = (int)(p / OH);
-    const int64_t row0 = ((int64_t)(n * H + 2 * oy) * W + 2 * ox) * C8 + c8;
+    const int64_t row0 = ((int64_t)(n * H + 2 * oy) * W + 2 * ox) * P8 + c8;
     uint4 v[4];
     v[0] = __ldg(x + row0);
-    v[1] = __ldg(x + row0 + C8);
-    v[2] = __ldg(x + row0 + (int64_t)W * C8);
-    v[3] = __ldg(x + row0 + (int64_t)W * C8 + C8);
+    v[1] = __ldg(x + row0 + P8);
+    v[2] = __ldg(x + row0 + (int64_t)W * P8);
+    v[3] = __ldg(x + row0 + (int64_t)W * P8 + P8);
     uint32_t outw[4];
     uint32_t idxw[2] = {0u, 0u};
 #pragma unroll
@@ -144,7 +145,8 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const uint4* __re
                                                                const uint4* __restrict__ act,
                                                                const uint4* __restrict__ res,
                                                                uint4* __restrict__ dx, int N, int H,
-                                                               int W, int C8) {
+                                                               int W, int C8, int P8) {
+  // P8: 8-channel groups between consecutive pixels of dx / act / res (= C8 when dense)
   const int OH = H >> 1, OW = W >> 1;
   const int64_t total = (int64_t)N * OH * OW * C8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -155,8 +157,8 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const uint4* __re
     p /= OW;
     int oy = (int)(p % OH);
     int n = (int)(p / OH);
-    const int64_t row0 = ((int64_t)(n * H + 2 * oy) * W + 2 * ox) * C8 + c8;
-    const int64_t offs[4] = {row0, row0 + C8, row0 + (int64_t)W * C8, row0 + (int64_t)W * C8 + C8};
+    const int64_t row0 = ((int64_t)(n * H + 2 * oy) * W + 2 * ox) * P8 + c8;
+    const int64_t offs[4] = {row0, row0 + P8, row0 + (int64_t)W * P8, row0 + (int64_t)W * P8 + P8};
     const uint4 g = __ldg(dy + i);
     const uint2 id = __ldg(idx + i);
 #pragma unroll
@@ -544,7 +546,7 @@ __global__ void __launch_bounds__(kThreads) bias_grad_kernel(const T* __restrict
 // iteration (16-byte loads), block-level reduce over the row lanes, one atomicAdd per channel/block.
 __global__ void __launch_bounds__(kThreads) bias_grad_bf16x8_kernel(const uint4* __restrict__ dy,
                                                                      float* __restrict__ db, int64_t rows,
-                                                                     int C8) {
+                                                                     int C8, int P8) {
   __shared__ float sh[kThreads][9];
   const int cpb = C8 < kThreads ? C8 : kThreads;       // column groups handled by this block
   const int R = kThreads / cpb;                         // row lanes
@@ -560,7 +562,7 @@ __global__ void __launch_bounds__(kThreads) bias_grad_bf16x8_kernel(const uint4*
     for (; r + 3 * step < rows; r += 4 * step) {
       uint4 u[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = __ldg(dy + (r + k * step) * C8 + cg);
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(dy + (r + k * step) * P8 + cg);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -571,7 +573,7 @@ __global__ void __launch_bounds__(kThreads) bias_grad_bf16x8_kernel(const uint4*
         }
     }
     for (; r < rows; r += step) {
-      const uint4 u = __ldg(dy + r * C8 + cg);
+      const uint4 u = __ldg(dy + r * P8 + cg);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = unpack_bf16x2((&u.x)[j]);
@@ -791,12 +793,15 @@ extern "C" {
 int segk_maxpool2x2_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int N, int H, int W,
                         int C, void* stream) {
   if (!ctx) return SEGK_EINVAL;
+  const SegkPitch pitch = segk_take_pitch(ctx);
+  SEGK_REQUIRE(ctx, pitch.out == 0 && (pitch.in == 0 || pitch.in >= C), "maxpool_fwd: only x may be pitched (>= %d channels)", C);
+  const int P8 = (pitch.in > 0 ? pitch.in : C) / 8;
   SEGK_REQUIRE(ctx, x && y && idx, "maxpool_fwd: null pointer");
   SEGK_REQUIRE(ctx, N > 0 && H >= 2 && W >= 2 && (H % 2 == 0) && (W % 2 == 0) && C % 8 == 0,
                "maxpool_fwd: need even H,W and C%%8==0 (got %dx%dx%dx%d)", N, H, W, C);
   const int64_t items = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
   maxpool_fwd_kernel<<<stream_grid(ctx, items), kThreads, 0, (cudaStream_t)stream>>>(
-      (const uint4*)x, (uint4*)y, (uint2*)idx, N, H, W, C / 8);
+      (const uint4*)x, (uint4*)y, (uint2*)idx, N, H, W, C / 8, P8);
   SEGK_LAUNCHED(ctx, "maxpool_fwd");
   return SEGK_OK;
 }
@@ -804,6 +809,10 @@ int segk_maxpool2x2_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int
 int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const void* act, int act_is_pooled,
                         const void* residual, void* dx, float* dbias, int N, int H, int W, int C, void* stream) {
   if (!ctx) return SEGK_EINVAL;
+  const SegkPitch pitch = segk_take_pitch(ctx);
+  SEGK_REQUIRE(ctx, pitch.in == 0 && (pitch.out == 0 || pitch.out >= C), "maxpool_bwd: only dx (with act / residual) may be pitched");
+  const int P8 = (pitch.out > 0 ? pitch.out : C) / 8;
+  SEGK_REQUIRE(ctx, P8 == C / 8 || !(act && act_is_pooled), "maxpool_bwd: the pooled-mask mode writes a dense dx");
   SEGK_REQUIRE(ctx, dy && idx && dx, "maxpool_bwd: null pointer");
   SEGK_REQUIRE(ctx, N > 0 && H >= 2 && W >= 2 && (H % 2 == 0) && (W % 2 == 0) && C % 8 == 0,
                "maxpool_bwd: need even H,W and C%%8==0 (got %dx%dx%dx%d)", N, H, W, C);
@@ -833,7 +842,7 @@ int segk_maxpool2x2_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, const
     return SEGK_OK;
   }
   maxpool_bwd_kernel<<<stream_grid(ctx, items), kThreads, 0, st>>>(
-      (const uint4*)dy, (const uint2*)idx, (const uint4*)act, (const uint4*)residual, (uint4*)dx, N, H, W, C / 8);
+      (const uint4*)dy, (const uint2*)idx, (const uint4*)act, (const uint4*)residual, (uint4*)dx, N, H, W, C / 8, P8);
   SEGK_LAUNCHED(ctx, "maxpool_bwd");
   return SEGK_OK;
 }
@@ -970,6 +979,9 @@ int segk_cast_to_bf16(segk_ctx* ctx, const void* x, int x_dtype, void* y, int64_
 int segk_bias_grad(segk_ctx* ctx, const void* dy, int dy_is_f32, float* db, int64_t rows, int C,
                    void* stream) {
   if (!ctx) return SEGK_EINVAL;
+  const SegkPitch pitch = segk_take_pitch(ctx);
+  SEGK_REQUIRE(ctx, pitch.out == 0 && (pitch.in == 0 || pitch.in >= C), "bias_grad: only dy may be pitched (>= %d channels)", C);
+  const int ld = pitch.in > 0 ? pitch.in : C;
   SEGK_REQUIRE(ctx, dy && db && rows > 0 && C > 0, "bias_grad: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   if (!dy_is_f32 && C % 8 == 0 && (((uintptr_t)dy) & 15) == 0) {
@@ -987,13 +999,14 @@ int segk_bias_grad(segk_ctx* ctx, const void* dy, int dy_is_f32, float* db, int6
         const int rc = segk_grow(ctx, &ctx->ws2, &ctx->ws2_bytes, need < (size_t)(8 << 20) ? (size_t)(8 << 20) : need, "bias_grad");
         if (rc) return rc;
       }
-      bias_grad_bf16x8_kernel<<<dim3((unsigned)gx, gy), kThreads, 0, st>>>((const uint4*)dy, (float*)ctx->ws2, rows, C8);
+      bias_grad_bf16x8_kernel<<<dim3((unsigned)gx, gy), kThreads, 0, st>>>((const uint4*)dy, (float*)ctx->ws2, rows, C8, ld / 8);
       SEGK_LAUNCHED(ctx, "bias_grad_bf16x8");
       reduce_rows_kernel<<<ceil_div(C, 32), kThreads, 0, st>>>((const float*)ctx->ws2, db, (int)gx, C);
       SEGK_LAUNCHED(ctx, "bias_grad_reduce");
       return SEGK_OK;
     }
   }
+  SEGK_REQUIRE(ctx, ld == C, "bias_grad: a pitched dy needs bf16 with C %% 8 == 0 and C/8 dividing (or a multiple of) %d", kThreads);
   cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * C, st);
   if (e != cudaSuccess) return segk_fail(ctx, SEGK_ECUDA, "bias_grad memset: %s", cudaGetErrorString(e));
   if (dy_is_f32 && (C == 1 || C == 2 || C == 4) && (rows * C) % 4 == 0 && (((uintptr_t)dy) & 15) == 0) {

@@ -11,7 +11,8 @@ namespace tch {
 // pixel box bw x bh x bn of at most (exactly, when `exact`) max_rows rows covering [N,H,W]
 Box pick_box(int N, int H, int W, int max_rows, bool exact);
 // 4-D NHWC bf16 tensor map (C, W, H, N), box (64, bw, bh, bn), SWIZZLE_128B, zero fill outside
-int act_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn);
+// (ld = channels between consecutive pixels; 0 = dense, ld = C)
+int act_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn, int ld = 0);
 // 3-D weight map [T][Nrows][K] bf16, box (64, block_n, 1), SWIZZLE_128B
 int weight_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int K, int Nrows, int T, int block_n);
 // grow-only context scratch (ctx->ws)
@@ -27,4 +28,4 @@ int segk_first_init(segk_ctx* ctx);
 int segk_wslab_init(segk_ctx* ctx);   // wslab.cu
 // slab-formulated Conv2DBackpropFilter: 1 = handled, 0 = not applicable, < 0 = error
 int segk_wslab_try(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int kh,
-                   int kw, int accumulate, void* stream);   // firstconv.cu: shared-memory opt-in of its kernels
+                   int kw, int accumulate, void* stream, int dy_ld = 0);   // firstconv.cu: shared-memory opt-in of its kernels

@@ -1832,6 +1832,12 @@ int encode_act_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int N, int H
   return SEGK_OK;
 }
 
+// NHWC tensor whose pixels sit `ld` channels apart (ld = C: dense; ld > C: a channel slice of a wider tensor -- the
+// zero-copy Concat views of segk_set_pitch)
+int encode_nhwc_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int N, int H, int W, int C, int ld, int bw, int bh, int bn) {
+  return encode_act_map(ctx, m, base, N, H, W, C, ld, (int64_t)W * ld, (int64_t)H * W * ld, bw, bh, bn);
+}
+
 int encode_weight_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int K, int Nrows, int T, int block_n) {
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Nrows, (cuuint64_t)T};
   cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * Nrows * 2};
@@ -1960,7 +1966,9 @@ __global__ void __launch_bounds__(256) relu_bits_kernel(const uint4* __restrict_
 
 int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, const float* bias, const void* residual,
               const void* mask, float scale, int relu, int out_f32, void* y, int N, int H, int W, int Ck, int Cn,
-              void* stream, float* colsum_out, PoolArgs* pool = nullptr) {
+              void* stream, float* colsum_out, PoolArgs* pool = nullptr, int ldx = 0, int ldy = 0) {
+  if (ldx <= 0) ldx = Ck;
+  if (ldy <= 0) ldy = Cn;
   // Ck = 64: kx-fused N = 192 MMAs on resident weights (slab3_kernel), 64-channel output tiles.  Measured
   // (tools/time_n64.py, B=32 160x576): 64 -> 64 forward 228 vs 297 us, its dgrad 345 vs 372 us; with two
   // channel tiles (64 -> 128) it is a wash (116 vs 112 us), so the tap-wise slab keeps those.  slab3 = 2 forces it.
@@ -1969,7 +1977,7 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
   const int block_n = fused3 ? 64 : pick_block_n(ctx, Cn);
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));
-  int rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Ck, Ck, (int64_t)W * Ck, (int64_t)H * W * Ck, kSlabP, kSlabH + 2, 1);
+  int rc = encode_nhwc_map(ctx, &maps.a[0], x, N, H, W, Ck, ldx, kSlabP, kSlabH + 2, 1);
   if (rc) return rc;
   maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
   if (fused3) {
@@ -1987,9 +1995,11 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
   p.n_tiles = Cn / block_n; p.kchunks = Ck / 64; p.ldo = Cn;
   p.out = y; p.out_f32 = out_f32; p.bias = bias; p.residual = (const bf16*)residual; p.mask = (const bf16*)mask;
   p.scale = scale; p.relu = relu;
-  p.tma_store = (!out_f32 && ctx->tma_store) ? 1 : 0;
+  p.tma_store = (!out_f32 && (ctx->tma_store || ldy != Cn)) ? 1 : 0;
+  SEGK_REQUIRE(ctx, ldy == Cn || (p.tma_store && !colsum_out && !residual && !mask && !(pool && (pool->bits_out || pool->mask_bits))),
+               "%s: a pitched output needs the plain bf16 epilogue (no residual / mask / column sums)", what);
   if (p.tma_store) {
-    rc = encode_act_map(ctx, &maps.c, y, N, H, W, Cn, Cn, (int64_t)W * Cn, (int64_t)H * W * Cn, kSlabWV, kSlabH, 1);
+    rc = encode_nhwc_map(ctx, &maps.c, y, N, H, W, Cn, ldy, kSlabWV, kSlabH, 1);
     if (rc) return rc;
   }
   if (pool && pool->pooled && p.tma_store && !colsum_out && (W & 1) == 0) {      // 4 x 30 tiles at even origins: whole pool windows
@@ -2051,8 +2061,18 @@ void conv_taps(TapTable& t, int kh, int kw, int rate = 1) {
 // shared body of conv fwd and dgrad: y[N,H,W,Cn] = epilogue( sum_taps x[.. + tap][Ck] * wt[tap][Cn][Ck] )
 int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, const float* bias, const void* residual,
                const void* mask, float scale, int relu, int out_f32, void* y, int N, int H, int W, int Ck, int Cn,
-               int kh, int kw, void* stream, float* colsum_out = nullptr, int rate = 1, PoolArgs* pool = nullptr) {
+               int kh, int kw, void* stream, float* colsum_out = nullptr, int rate = 1, PoolArgs* pool = nullptr, int ldx = 0,
+               int ldy = 0) {
   SEGK_REQUIRE(ctx, x && wt && y, "%s: null pointer", what);
+  // ldx / ldy: channels between consecutive pixels of x / y (0 = dense).  A pitched y leaves through the TMA store only:
+  // its epilogue offsets (residual, mask, bits, finish kernels of the split schedules) all assume the dense row stride
+  if (ldx <= 0) ldx = Ck;
+  if (ldy <= 0) ldy = Cn;
+  SEGK_REQUIRE(ctx, ldx >= Ck && ldy >= Cn && ldx % 8 == 0 && ldy % 8 == 0, "%s: bad channel pitch (%d for %d, %d for %d)", what, ldx,
+               Ck, ldy, Cn);
+  const bool pitched_out = ldy != Cn;
+  SEGK_REQUIRE(ctx, !pitched_out || (!out_f32 && !colsum_out && !residual && !mask && !(pool && (pool->bits_out || pool->mask_bits))),
+               "%s: a pitched output needs the plain bf16 epilogue (no residual / mask / bits / column sums)", what);
   SEGK_REQUIRE(ctx, N > 0 && H > 0 && W > 0, "%s: empty tensor", what);
   SEGK_REQUIRE(ctx, Ck % 64 == 0 && Cn % 64 == 0 && Ck > 0 && Cn > 0,
                "%s: tensor-core path needs channel counts that are multiples of 64 (got %d -> %d); no fallback", what,
@@ -2064,7 +2084,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   SEGK_REQUIRE(ctx, !colsum_out || !out_f32, "%s: column sums need a bf16 output", what);
   SEGK_REQUIRE(ctx, rate >= 1 && (kh / 2) * rate <= 127 && (kw / 2) * rate <= 127, "%s: dilation rate %d out of range", what, rate);
   if (rate == 1 && slab_applicable(ctx, N, H, W, Ck, Cn, kh, kw))
-    return conv_slab(ctx, what, x, wt, bias, residual, mask, scale, relu, out_f32, y, N, H, W, Ck, Cn, stream, colsum_out, pool);
+    return conv_slab(ctx, what, x, wt, bias, residual, mask, scale, relu, out_f32, y, N, H, W, Ck, Cn, stream, colsum_out, pool, ldx, ldy);
   // the fused pool needs boxes of whole 2x2 windows, the TMA-store epilogue and unsplit tiles
   bool want_pool = pool && pool->pooled && !out_f32 && ctx->tma_store && !colsum_out && (H & 1) == 0 && (W & 1) == 0;
   Box b = choose_box(N, H, W, kBlockM, false, 0, 0, kh, kw, want_pool);
@@ -2076,7 +2096,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   const int block_n = pick_block_n(ctx, Cn);
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));
-  int rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Ck, Ck, (int64_t)W * Ck, (int64_t)H * W * Ck, b.bw, b.bh, b.bn);
+  int rc = encode_nhwc_map(ctx, &maps.a[0], x, N, H, W, Ck, ldx, b.bw, b.bh, b.bn);
   if (rc) return rc;
   maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
   rc = encode_weight_map_blocked(ctx, &maps.b, wt, Ck, Cn, kh * kw, block_n);
@@ -2108,14 +2128,14 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   if (want_pool) {
     // (few-tile layers are not split when the pool is fused: their tiles are small anyway)
     p.tma_store = 1;
-    rc = encode_act_map(ctx, &maps.c, y, N, H, W, Cn, Cn, (int64_t)W * Cn, (int64_t)H * W * Cn, b.bw, b.bh, b.bn);
+    rc = encode_nhwc_map(ctx, &maps.c, y, N, H, W, Cn, ldy, b.bw, b.bh, b.bn);
     if (rc) return rc;
     p.pool_out = (bf16*)pool->pooled; p.pool_idx = pool->idx; p.pool_only = pool->pool_only;
     pool->fused = true;
     if (pool->bits_out) { p.bits_out = pool->bits_out; pool->bits_done = true; }
     return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
   }
-  if (!narrow && ((tiles * 2 <= ctx->sm_count && p.ntaps * p.kchunks >= 32 && p.kchunks >= 2) || force_ks > 0)) {
+  if (!narrow && !pitched_out && ((tiles * 2 <= ctx->sm_count && p.ntaps * p.kchunks >= 32 && p.kchunks >= 2) || force_ks > 0)) {
     // one wave of work units.  Measured (tools/time_conv6.py, conv6 dgrad: 50 tiles x 2240 k-steps): 2 splits
     // 483 us, 1: 766, 3: 596, 5: 562, 8: 692, 14: 918 -- more splits than one wave lets the m-tiles that share
     // a weight slice drift apart in K, and the 205 MB of weights stream from DRAM several times over
@@ -2196,9 +2216,9 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
       return SEGK_OK;
     }
   }
-  p.tma_store = (!out_f32 && ctx->tma_store) ? 1 : 0;
+  p.tma_store = (!out_f32 && (ctx->tma_store || pitched_out)) ? 1 : 0;
   if (p.tma_store) {
-    rc = encode_act_map(ctx, &maps.c, y, N, H, W, Cn, Cn, (int64_t)W * Cn, (int64_t)H * W * Cn, b.bw, b.bh, b.bn);
+    rc = encode_nhwc_map(ctx, &maps.c, y, N, H, W, Cn, ldy, b.bw, b.bh, b.bn);
     if (rc) return rc;
   }
   if (pool && pool->bits_out && !out_f32 && !(ctx->hybrid)) { p.bits_out = pool->bits_out; pool->bits_done = true; }
@@ -2210,7 +2230,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
     int ksr = rem > 0 ? sm / rem : 0;
     if (ksr > p.kchunks) ksr = p.kchunks;            // ksplits <= kchunks <= k-steps of any tile: no piece is empty
     if (ksr > 8) ksr = 8;
-    if (ctx->hybrid && !narrow && waves >= 1 && waves <= 4 && ksr >= 2 && p.ntaps * p.kchunks >= 8 * ksr) {
+    if (ctx->hybrid && !narrow && !pitched_out && waves >= 1 && waves <= 4 && ksr >= 2 && p.ntaps * p.kchunks >= 8 * ksr) {
       const size_t slice = (size_t)N * H * W * Cn;
       rc = ensure_workspace(ctx, sizeof(float) * slice * ksr);
       if (rc) return rc;
@@ -2246,13 +2266,14 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
 
 // decimated views of a [N, s*H, s*W, C] tensor: view (py,px) holds pixels (s*i+py, s*j+px)
 int encode_decimated_maps(segk_ctx* ctx, TensorMaps& maps, const void* base, int N, int H, int W, int C, int s,
-                          const Box& b) {
+                          const Box& b, int ld = 0) {
   const int OH = H * s, OW = W * s;
+  if (ld <= 0) ld = C;
   for (int py = 0; py < s; ++py)
     for (int px = 0; px < s; ++px) {
-      const bf16* v = (const bf16*)base + ((int64_t)py * OW + px) * C;
-      int rc = encode_act_map(ctx, &maps.a[py * s + px], v, N, H, W, C, (int64_t)s * C, (int64_t)s * OW * C,
-                              (int64_t)OH * OW * C, b.bw, b.bh, b.bn);
+      const bf16* v = (const bf16*)base + ((int64_t)py * OW + px) * ld;
+      int rc = encode_act_map(ctx, &maps.a[py * s + px], v, N, H, W, C, (int64_t)s * ld, (int64_t)s * OW * ld,
+                              (int64_t)OH * OW * ld, b.bw, b.bh, b.bn);
       if (rc) return rc;
     }
   return SEGK_OK;
@@ -2277,8 +2298,9 @@ void strided_taps(TapTable& t, int k, int s) {
 
 namespace tch {
 Box pick_box(int N, int H, int W, int max_rows, bool exact) { return choose_box(N, H, W, max_rows, exact); }
-int act_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn) {
-  return encode_act_map(ctx, m, base, N, H, W, C, C, (int64_t)W * C, (int64_t)H * W * C, bw, bh, bn);
+int act_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh, int bn, int ld) {
+  if (ld <= 0) ld = C;
+  return encode_act_map(ctx, m, base, N, H, W, C, ld, (int64_t)W * ld, (int64_t)H * W * ld, bw, bh, bn);
 }
 int weight_map(segk_ctx* ctx, CUtensorMap* m, const void* base, int K, int Nrows, int T, int block_n) {
   return encode_weight_map(ctx, m, base, K, Nrows, T, block_n);
@@ -2291,7 +2313,12 @@ extern "C" {
 int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* bias, const void* residual, void* y,
                       int N, int H, int W, int Cin, int Cout, int k, int s, unsigned flags, void* stream) {
   if (!ctx) return SEGK_EINVAL;
+  const SegkPitch pitch = segk_take_pitch(ctx);
   SEGK_REQUIRE(ctx, x && wk && y && N > 0 && H > 0 && W > 0, "deconv2d_fwd: bad args");
+  SEGK_REQUIRE(ctx, pitch.in == 0 || pitch.in == Cin, "deconv2d_fwd: the input is dense");
+  const int ldy = pitch.out > 0 ? pitch.out : Cout;
+  SEGK_REQUIRE(ctx, ldy == Cout || (ldy > Cout && !residual && !(flags & SEGK_EPI_OUT_F32) && (((uintptr_t)y) & 15) == 0),
+               "deconv2d_fwd: a pitched output (%d channels apart) needs a bf16 output without residual", ldy);
   SEGK_REQUIRE(ctx, k == 2 * s && s >= 2 && s % 2 == 0 && s * s * 4 <= 32767, "deconv2d_fwd: need k == 2*stride, even stride");
   SEGK_REQUIRE(ctx, Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0,
                "deconv2d_fwd: tensor-core path needs channels %% 64 == 0 (got %d -> %d); use segk_deconv2d_small_fwd", Cin,
@@ -2315,7 +2342,7 @@ int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float*
   p.phases = s * s; p.s = s;
   p.ntaps = 4; p.kchunks = Cin / 64;
   p.in_H = H; p.in_W = W;
-  p.out_H = H * s; p.out_W = W * s; p.ldo = Cout; p.os = s; p.opad = s / 2;
+  p.out_H = H * s; p.out_W = W * s; p.ldo = ldy; p.os = s; p.opad = s / 2;      // (ldo is the row stride of `out` only here)
   p.out = y; p.out_f32 = (flags & SEGK_EPI_OUT_F32) ? 1 : 0;
   p.bias = bias; p.residual = (const bf16*)residual; p.mask = nullptr;
   p.scale = 1.f; p.relu = (flags & SEGK_EPI_RELU) ? 1 : 0;
@@ -2330,11 +2357,15 @@ int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float*
 }
 
 static int strided_conv_impl(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, const float* bias, int relu,
-                            void* dx, float* dx_colsum, int N, int H, int W, int Cin, int Cout, int k, int s, void* stream);
+                            void* dx, float* dx_colsum, int N, int H, int W, int Cin, int Cout, int k, int s, void* stream, int dy_ld);
 
 int segk_deconv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, void* dx, float* dx_colsum,
                         int N, int H, int W, int Cin, int Cout, int k, int s, void* stream) {
-  return strided_conv_impl(ctx, dy, wd, relu_mask, nullptr, 0, dx, dx_colsum, N, H, W, Cin, Cout, k, s, stream);
+  if (!ctx) return SEGK_EINVAL;
+  const SegkPitch pitch = segk_take_pitch(ctx);
+  SEGK_REQUIRE(ctx, pitch.out == 0 || pitch.out == Cin, "deconv2d_dgrad: the output is dense");
+  SEGK_REQUIRE(ctx, pitch.in == 0 || pitch.in >= Cout, "deconv2d_dgrad: dy pitch %d < %d channels", pitch.in, Cout);
+  return strided_conv_impl(ctx, dy, wd, relu_mask, nullptr, 0, dx, dx_colsum, N, H, W, Cin, Cout, k, s, stream, pitch.in);
 }
 
 // Conv2D with kernel 2s x 2s, stride s, SAME (LidCamNet.py:28-33's 4x4 stride-2 encoder convs) = the strided conv that is
@@ -2345,11 +2376,11 @@ int segk_conv2d_strided_fwd(segk_ctx* ctx, const void* x, const void* wd, const 
                             int Cin, int Cout, int k, int s, unsigned flags, void* stream) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, !(flags & SEGK_EPI_OUT_F32), "conv2d_strided_fwd: bf16 output only");
-  return strided_conv_impl(ctx, x, wd, nullptr, bias, (flags & SEGK_EPI_RELU) ? 1 : 0, y, nullptr, N, H, W, Cout, Cin, k, s, stream);
+  return strided_conv_impl(ctx, x, wd, nullptr, bias, (flags & SEGK_EPI_RELU) ? 1 : 0, y, nullptr, N, H, W, Cout, Cin, k, s, stream, 0);
 }
 
 static int strided_conv_impl(segk_ctx* ctx, const void* dy, const void* wd, const void* relu_mask, const float* bias, int relu,
-                            void* dx, float* dx_colsum, int N, int H, int W, int Cin, int Cout, int k, int s, void* stream) {
+                            void* dx, float* dx_colsum, int N, int H, int W, int Cin, int Cout, int k, int s, void* stream, int dy_ld) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, dy && wd && dx && N > 0 && H > 0 && W > 0, "deconv2d_dgrad: bad args");
   SEGK_REQUIRE(ctx, k == 4 && s == 2, "deconv2d_dgrad: tensor-core path supports k=4, stride 2 (got k=%d s=%d)", k, s);
@@ -2360,7 +2391,7 @@ static int strided_conv_impl(segk_ctx* ctx, const void* dy, const void* wd, cons
   const int block_n = pick_block_n(ctx, Cin);
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));
-  int rc = encode_decimated_maps(ctx, maps, dy, N, H, W, Cout, s, b);
+  int rc = encode_decimated_maps(ctx, maps, dy, N, H, W, Cout, s, b, dy_ld);
   if (rc) return rc;
   rc = encode_weight_map_blocked(ctx, &maps.b, wd, Cout, Cin, k * k, block_n);
   if (rc) return rc;
@@ -2401,6 +2432,8 @@ static int strided_conv_impl(segk_ctx* ctx, const void* dy, const void* wd, cons
 int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
                         int k, int s, int accumulate, void* stream) {
   if (!ctx) return SEGK_EINVAL;
+  const SegkPitch pitch = segk_take_pitch(ctx);
+  SEGK_REQUIRE(ctx, pitch.out == 0 && (pitch.in == 0 || pitch.in >= Cout), "deconv2d_wgrad: only dy may be pitched (>= %d channels)", Cout);
   SEGK_REQUIRE(ctx, x && dy && dw && N > 0 && H > 0 && W > 0, "deconv2d_wgrad: bad args");
   SEGK_REQUIRE(ctx, k == 4 && s == 2, "deconv2d_wgrad: tensor-core path supports k=4, stride 2 (got k=%d s=%d)", k, s);
   SEGK_REQUIRE(ctx, Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0,
@@ -2411,7 +2444,7 @@ int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw,
   const int block_n = pick_block_n(ctx, Cin);
   TensorMaps maps;
   memset(&maps, 0, sizeof(maps));
-  int rc = encode_decimated_maps(ctx, maps, dy, N, H, W, Cout, s, b);  // A side: dY (rows = (tap, co))
+  int rc = encode_decimated_maps(ctx, maps, dy, N, H, W, Cout, s, b, pitch.in);  // A side: dY (rows = (tap, co))
   if (rc) return rc;
   rc = encode_act_map(ctx, &maps.b, x, N, H, W, Cin, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin, b.bw, b.bh, b.bn);
   if (rc) return rc;
@@ -2668,14 +2701,15 @@ int segk_relu_bits(segk_ctx* ctx, const void* y, uint32_t* bits, int64_t rows, i
 int segk_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* bias, const void* residual, void* y,
                     uint32_t* relu_bits, int N, int H, int W, int Cin, int Cout, int kh, int kw, unsigned flags, void* stream) {
   if (!ctx) return SEGK_EINVAL;
+  const SegkPitch pitch = segk_take_pitch(ctx);
   if (!relu_bits)
     return conv_igemm(ctx, "conv2d_fwd", x, wk, bias, residual, nullptr, 1.f, (flags & SEGK_EPI_RELU) ? 1 : 0,
-                      (flags & SEGK_EPI_OUT_F32) ? 1 : 0, y, N, H, W, Cin, Cout, kh, kw, stream);
+                      (flags & SEGK_EPI_OUT_F32) ? 1 : 0, y, N, H, W, Cin, Cout, kh, kw, stream, nullptr, 1, nullptr, pitch.in, pitch.out);
   SEGK_REQUIRE(ctx, !(flags & SEGK_EPI_OUT_F32) && Cout % 32 == 0, "conv2d_fwd: relu_bits need a bf16 output with Cout %% 32 == 0");
   PoolArgs ex{nullptr, nullptr, 0, false};
   ex.bits_out = relu_bits;
   const int rc = conv_igemm(ctx, "conv2d_fwd", x, wk, bias, residual, nullptr, 1.f, (flags & SEGK_EPI_RELU) ? 1 : 0, 0, y, N, H, W,
-                            Cin, Cout, kh, kw, stream, nullptr, 1, &ex);
+                            Cin, Cout, kh, kw, stream, nullptr, 1, &ex, pitch.in, pitch.out);
   if (rc || ex.bits_done) return rc;
   return relu_bits_of(ctx, y, relu_bits, (int64_t)N * H * W, Cout, stream);
 }
@@ -2683,13 +2717,15 @@ int segk_conv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float* b
 int segk_conv2d_fwd_pool(segk_ctx* ctx, const void* x, const void* wk, const float* bias, void* y, void* pooled, uint8_t* idx,
                          int pool_only, int N, int H, int W, int Cin, int Cout, int kh, int kw, unsigned flags, void* stream) {
   if (!ctx) return SEGK_EINVAL;
+  const SegkPitch pitch = segk_take_pitch(ctx);
   SEGK_REQUIRE(ctx, y && pooled && idx, "conv2d_fwd_pool: null pointer");
   SEGK_REQUIRE(ctx, !(flags & SEGK_EPI_OUT_F32), "conv2d_fwd_pool: bf16 output only");
   SEGK_REQUIRE(ctx, (H & 1) == 0 && (W & 1) == 0, "conv2d_fwd_pool: need even H, W (got %dx%d)", H, W);
   PoolArgs pool{pooled, idx, pool_only ? 1 : 0, false};
   const int rc = conv_igemm(ctx, "conv2d_fwd_pool", x, wk, bias, nullptr, nullptr, 1.f, (flags & SEGK_EPI_RELU) ? 1 : 0, 0, y, N, H,
-                            W, Cin, Cout, kh, kw, stream, nullptr, 1, &pool);
+                            W, Cin, Cout, kh, kw, stream, nullptr, 1, &pool, pitch.in, pitch.out);
   if (rc || pool.fused) return rc;
+  ctx->pitch_in = pitch.out;                                                   // (the pool reads the tensor just written)
   return segk_maxpool2x2_fwd(ctx, y, pooled, idx, N, H, W, Cout, stream);     // (tile geometry without whole windows)
 }
 
@@ -2697,18 +2733,23 @@ int segk_conv2d_dgrad(segk_ctx* ctx, const void* dy, const void* wd, const void*
                       const void* residual, void* dx, float* dx_colsum, float scale, int N, int H, int W, int Cin, int Cout,
                       int kh, int kw, void* stream) {
   if (!ctx) return SEGK_EINVAL;
+  const SegkPitch pitch = segk_take_pitch(ctx);
+  SEGK_REQUIRE(ctx, pitch.out == 0 || pitch.out == Cin, "conv2d_dgrad: the output is dense");
   SEGK_REQUIRE(ctx, !(relu_mask && relu_mask_bits), "conv2d_dgrad: pass the ReLU mask as a tensor OR as bits");
   SEGK_REQUIRE(ctx, !relu_mask_bits || Cin % 32 == 0, "conv2d_dgrad: mask bits need Cin %% 32 == 0");
   // GEMM-K = Cout (channels of dy), GEMM-N = Cin (channels of dx); wd holds the taps reversed.
   PoolArgs ex{nullptr, nullptr, 0, false};
   ex.mask_bits = relu_mask_bits;
   return conv_igemm(ctx, "conv2d_dgrad", dy, wd, nullptr, residual, relu_mask, scale, 0, 0, dx, N, H, W, Cout, Cin, kh,
-                    kw, stream, dx_colsum, 1, relu_mask_bits ? &ex : nullptr);
+                    kw, stream, dx_colsum, 1, relu_mask_bits ? &ex : nullptr, pitch.in, 0);
 }
 
 static int conv2d_wgrad_impl(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
                              int kh, int kw, int accumulate, void* stream, int rate) {
   if (!ctx) return SEGK_EINVAL;
+  const SegkPitch pitch = segk_take_pitch(ctx);
+  SEGK_REQUIRE(ctx, pitch.out == 0 && (pitch.in == 0 || pitch.in >= Cout), "conv2d_wgrad: only dy may be pitched (>= %d channels)", Cout);
+  const int dy_ld = pitch.in > 0 ? pitch.in : Cout;
   SEGK_REQUIRE(ctx, x && dy && dw, "conv2d_wgrad: null pointer");
   SEGK_REQUIRE(ctx, rate >= 1 && (kh / 2) * rate <= 127 && (kw / 2) * rate <= 127, "conv2d_wgrad: dilation rate %d out of range", rate);
   SEGK_REQUIRE(ctx, N > 0 && H > 0 && W > 0, "conv2d_wgrad: empty tensor");
@@ -2718,7 +2759,7 @@ static int conv2d_wgrad_impl(segk_ctx* ctx, const void* x, const void* dy, float
   SEGK_REQUIRE(ctx, (kh & 1) && (kw & 1) && kh * kw <= kMaxTaps, "conv2d_wgrad: odd kernel sizes up to %d taps", kMaxTaps);
   SEGK_REQUIRE(ctx, (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) == 0, "conv2d_wgrad: 16-byte alignment");
   if (rate == 1) {
-    const int handled = segk_wslab_try(ctx, x, dy, dw, N, H, W, Cin, Cout, kh, kw, accumulate, stream);
+    const int handled = segk_wslab_try(ctx, x, dy, dw, N, H, W, Cin, Cout, kh, kw, accumulate, stream, dy_ld);
     if (handled != 0) return handled < 0 ? handled : SEGK_OK;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -2730,7 +2771,7 @@ static int conv2d_wgrad_impl(segk_ctx* ctx, const void* x, const void* dy, float
   int rc = encode_act_map(ctx, &maps.a[0], x, N, H, W, Cin, Cin, (int64_t)W * Cin, (int64_t)H * W * Cin, b.bw, b.bh, b.bn);
   if (rc) return rc;
   maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
-  rc = encode_act_map(ctx, &maps.b, dy, N, H, W, Cout, Cout, (int64_t)W * Cout, (int64_t)H * W * Cout, b.bw, b.bh, b.bn);
+  rc = encode_nhwc_map(ctx, &maps.b, dy, N, H, W, Cout, dy_ld, b.bw, b.bh, b.bn);
   if (rc) return rc;
   WgradParams p;
   memset(&p, 0, sizeof(p));

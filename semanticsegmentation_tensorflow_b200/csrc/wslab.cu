@@ -256,7 +256,7 @@ int segk_reduce_partials(segk_ctx* ctx, const float* part, float* dw, size_t n, 
 
 // -> 1 handled, 0 not applicable (caller uses the tap-wise kernel), < 0 error
 int segk_wslab_try(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout, int kh,
-                   int kw, int accumulate, void* stream) {
+                   int kw, int accumulate, void* stream, int dy_ld) {
   if (!ctx->wslab) return 0;
   if (!(kh == 3 && kw == 3 && (Cin == 64 || Cin == 128) && Cout % 64 == 0)) return 0;
   if (ctx->wslab == 1 && !((int64_t)H * W >= 4096 && W >= 64)) return 0;
@@ -307,7 +307,7 @@ int segk_wslab_try(segk_ctx* ctx, const void* x, const void* dy, float* dw, int 
   memset(&maps, 0, sizeof(maps));
   int rc = tch::act_map(ctx, &maps.x, x, N, H, W, Cin, kXP, chunks == 1 ? 6 : 4, 1);
   if (rc) return rc;
-  rc = tch::act_map(ctx, &maps.dy, dy, N, H, W, Cout, kDyP, kDyH, 1);
+  rc = tch::act_map(ctx, &maps.dy, dy, N, H, W, Cout, kDyP, kDyH, 1, dy_ld);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n = (size_t)p.rows_total * Cout;

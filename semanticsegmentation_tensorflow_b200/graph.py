@@ -204,8 +204,9 @@ class _Vars:
 
 class GraphNet(_Feeds):
     def __init__(self, x, num_classes, nodes, variables=None, init="ref", seed=1234, world_size=1, overlap=True,
-                 head_on_tensor_cores=True):
+                 head_on_tensor_cores=True, zero_copy_concat=True):
         self.head_on_tensor_cores = head_on_tensor_cores      # a k x k conv to num_classes as a 64-column tcgen05 tile
+        self.zero_copy_concat = zero_copy_concat              # Concat inputs as channel-slice views of the concat buffer
         if not torch.cuda.is_available():
             raise RuntimeError("GraphNet needs a CUDA (sm_100a) device: the segmentation ops have no CPU fallback")
         x = torch.as_tensor(x)
@@ -265,7 +266,6 @@ class GraphNet(_Feeds):
             n_, h, w, c = shape[n.inputs[0]]
             if n.kind == "pool":
                 shape[n.name] = (N, h // 2, w // 2, c)
-                self.idx[n.name] = torch.empty(shape[n.name], dtype=torch.uint8, device=dev)
             elif n.kind == "concat":
                 for i in n.inputs:
                     assert shape[i][:3] == (N, h, w), f"{n.name}: concat inputs differ in size"
@@ -276,13 +276,24 @@ class GraphNet(_Feeds):
             else:
                 self.route[n.name] = self._route(n, c)
                 shape[n.name] = (N, h, w, n.cout)
-                if self.route[n.name] == "im2col":
-                    self.patch[n.name] = torch.empty((N, h, w, 64), dtype=bf, device=dev)
-                    self.tmp[n.name] = torch.empty((1, 1, 64, n.cout), dtype=torch.float32, device=dev)
+        self.shape = shape
+        self.slot = self._concat_slots()
+        for n in self.nodes:
+            n_, h, w, c = shape[n.inputs[0]]
+            if n.kind == "pool":
+                self.idx[n.name] = torch.empty(shape[n.name], dtype=torch.uint8, device=dev)
+            elif n.kind == "conv" and self.route[n.name] == "im2col":
+                self.patch[n.name] = torch.empty((N, h, w, 64), dtype=bf, device=dev)
+                self.tmp[n.name] = torch.empty((1, 1, 64, n.cout), dtype=torch.float32, device=dev)
+            if n.name in self.slot:
+                continue                                   # a channel slice of its Concat's buffer (below)
             dt = torch.float32 if n.name == last else bf
             self.act[n.name] = torch.empty(shape[n.name], dtype=dt, device=dev)
             self.gbuf[n.name] = torch.empty(shape[n.name], dtype=dt, device=dev)
-        self.shape = shape
+        for t, (cat, off) in self.slot.items():
+            c = shape[t][3]
+            self.act[t] = self.act[cat][..., off:off + c]
+            self.gbuf[t] = self.gbuf[cat][..., off:off + c]
         # 1-bit ReLU masks of the conv outputs that a tensor-core conv reads (its dgrad epilogue applies the producer's
         # ReluGrad): written by the forward epilogue, 1/16 of the bytes of the bf16 activation
         self.bits = {}
@@ -316,6 +327,42 @@ class GraphNet(_Feeds):
                                          torch.zeros(64, dtype=torch.float32, device=dev))
                 self.head_dz[n.name] = torch.empty(shape[n.name][:3] + (64,), dtype=bf, device=dev)
                 self.head_gw[n.name] = torch.empty((n.k, n.k, cin, 64), dtype=torch.float32, device=dev)
+
+    def _concat_slots(self):
+        """Zero-copy Concat (utils.py:332): {tensor: (concat node, channel offset)} for the Concat inputs whose producer can write
+        straight into its channel slice of the concat buffer and whose gradient can be read in place from the concat's
+        gradient (channel-slice views, segk_set_pitch) -- no copy forward, none backward.  That holds for
+          * a transposed conv without ReLU that only the Concat reads (the decoder's upsampled half), and
+          * a tensor-core conv read by the Concat and by ONE earlier Max_Pooling (an encoder skip): the pool's backward adds
+            its gradient to the slice and applies the conv's ReluGrad to the sum; or, without ReLU, read by the Concat alone.
+        Everything else keeps the segk_channel_copy form."""
+        slots = {}
+        if not getattr(self, "zero_copy_concat", True):
+            return slots
+        order = {n.name: i for i, n in enumerate(self.nodes)}
+        last = self.nodes[-1].name
+        for n in self.nodes:
+            if n.kind != "concat" or n.name == last:
+                continue
+            off = 0
+            for t in n.inputs:
+                c = self.shape[t][3]
+                p = self.by_name.get(t)
+                users = [m for m in self.nodes if t in m.inputs]
+                ok = (p is not None and p.kind in ("conv", "deconv") and self.route.get(t) == "tc" and c % 64 == 0 and off % 64 == 0
+                      and t not in slots and n.inputs.count(t) == 1 and t != last)
+                if ok and p.kind == "deconv":
+                    ok = not p.relu and len(users) == 1
+                elif ok:
+                    pools = [m for m in users if m.kind == "pool"]
+                    if len(users) == 2 and len(pools) == 1:
+                        ok = order[pools[0].name] < order[n.name]
+                    else:
+                        ok = len(users) == 1 and not p.relu
+                if ok:
+                    slots[t] = (n.name, off)
+                off += c
+        return slots
 
     def _repack(self, ops, only=None):
         V = self.vars
@@ -386,7 +433,8 @@ class GraphNet(_Feeds):
                 off = 0
                 for i in n.inputs:
                     c = self.shape[i][3]
-                    ops.channel_copy(self.act[i], 0, out, off, c)
+                    if i not in self.slot:            # (slot tensors were written in place by their producers)
+                        ops.channel_copy(self.act[i], 0, out, off, c)
                     off += c
             elif n.kind == "deconv":
                 ops.deconv2d_fwd(self._in(n.inputs[0]), V.wk[n.name], self._bias(n), out, n.k, n.stride, relu=n.relu)
@@ -485,7 +533,8 @@ class GraphNet(_Feeds):
                 off = 0
                 for t in n.inputs:
                     c = self.shape[t][3]
-                    ops.channel_copy(G, off, self.gbuf[t], 0, c, mask=self._relu_mask_of(t), accumulate=has[t])
+                    if t not in self.slot:            # (a slot tensor's gradient IS its slice of G; see _concat_slots)
+                        ops.channel_copy(G, off, self.gbuf[t], 0, c, mask=self._relu_mask_of(t), accumulate=has[t])
                     has[t] = True
                     off += c
                 continue

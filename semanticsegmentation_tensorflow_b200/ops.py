@@ -26,6 +26,18 @@ def _p(t):
     return 0 if t is None else t.data_ptr()
 
 
+def _pitch(t):
+    """Channel pitch of an NHWC tensor that is a channel slice of a wider one (zero-copy Concat view, segk_set_pitch);
+    0 for a dense tensor."""
+    if t is None or t.is_contiguous():
+        return 0
+    n, h, w, c = t.shape
+    sn, sh, sw, sc = t.stride()
+    if sc != 1 or sw < c or sh != w * sw or sn != h * sh or sw % 8 or (t.data_ptr() & 15):
+        raise ValueError(f"not a channel-slice view: shape {tuple(t.shape)} strides {tuple(t.stride())}")
+    return sw
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -101,6 +113,13 @@ class Ops:
         self._work = None
         dims = tuple(a for a in args[:-1] if isinstance(a, int) and not isinstance(a, bool) and 0 <= a < (1 << 20))
         self.profile.records.append((name, work, unit, e0, e1, dims))
+
+    def _views(self, tin=None, tout=None):
+        """Announce channel-slice views (zero-copy Concat) to the next C call: `tin` its gradient / input operand, `tout`
+        its output."""
+        pi, po = _pitch(tin), _pitch(tout)
+        if pi or po:
+            self._call("segk_set_pitch", pi, po)
 
     def _w(self, work, unit):
         if self.profile is not None:
@@ -235,6 +254,7 @@ class Ops:
         cout = y.shape[3]
         flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if y.dtype == torch.float32 else 0)
         self._w(conv_flops(n, h, w, cin, cout, kh, kw) if flops is None else flops, "flop")
+        self._views(tin=x, tout=y)
         self.call("segk_conv2d_fwd", _p(x), _p(wk), _p(bias), _p(residual), _p(y), _p(relu_bits), n, h, w, cin, cout, kh, kw,
                   flags, _stream())
         return y
@@ -268,6 +288,7 @@ class Ops:
         n, h, w, cout = dy.shape
         cin = dx.shape[3]
         self._w(conv_flops(n, h, w, cin, cout, kh, kw) if flops is None else flops, "flop")
+        self._views(tin=dy)
         self.call("segk_conv2d_dgrad", _p(dy), _p(wd), _p(relu_mask), _p(relu_mask_bits), _p(residual), _p(dx), _p(colsum),
                   float(scale), n, h, w, cin, cout, kh, kw, _stream())
         return dx
@@ -276,6 +297,7 @@ class Ops:
         n, h, w, cin = x.shape
         cout = dy.shape[3]
         self._w(conv_flops(n, h, w, cin, cout, kh, kw) if flops is None else flops, "flop")
+        self._views(tin=dy)
         self.call("segk_conv2d_wgrad", _p(x), _p(dy), _p(dw), n, h, w, cin, cout, kh, kw, int(accumulate), _stream())
         return dw
 
@@ -284,6 +306,7 @@ class Ops:
         cout = y.shape[3]
         flags = (EPI_RELU if relu else 0) | (EPI_OUT_F32 if y.dtype == torch.float32 else 0)
         self._w(deconv_flops(n, h, w, cin, cout, k, s), "flop")
+        self._views(tout=y)
         self.call("segk_deconv2d_fwd", _p(x), _p(wk), _p(bias), _p(residual), _p(y), n, h, w, cin, cout, k, s, flags,
                   _stream())
         return y
@@ -292,6 +315,7 @@ class Ops:
         n, h, w, cin = dx.shape
         cout = dy.shape[3]
         self._w(deconv_flops(n, h, w, cin, cout, k, s), "flop")
+        self._views(tin=dy)
         self.call("segk_deconv2d_dgrad", _p(dy), _p(wd), _p(relu_mask), _p(dx), _p(colsum), n, h, w, cin, cout, k, s, _stream())
         return dx
 
@@ -299,6 +323,7 @@ class Ops:
         n, h, w, cin = x.shape
         cout = dy.shape[3]
         self._w(deconv_flops(n, h, w, cin, cout, k, s), "flop")
+        self._views(tin=dy)
         self.call("segk_deconv2d_wgrad", _p(x), _p(dy), _p(dw), n, h, w, cin, cout, k, s, int(accumulate), _stream())
         return dw
 
@@ -374,6 +399,7 @@ class Ops:
         n, h, w, cin = x.shape
         cout = y.shape[3]
         self._w(conv_flops(n, h, w, cin, cout, kh, kw), "flop")
+        self._views(tin=x, tout=y)
         self.call("segk_conv2d_fwd_pool", _p(x), _p(wk), _p(bias), _p(y), _p(pooled), _p(idx), int(pool_only), n, h, w, cin,
                   cout, kh, kw, EPI_RELU if relu else 0, _stream())
         return pooled, idx
@@ -381,6 +407,7 @@ class Ops:
     def maxpool_fwd(self, x, y, idx):
         n, h, w, c = x.shape
         self._w(2.0 * x.numel() + 3.0 * y.numel(), "byte")
+        self._views(tin=x)
         self.call("segk_maxpool2x2_fwd", _p(x), _p(y), _p(idx), n, h, w, c, _stream())
         return y, idx
 
@@ -397,6 +424,10 @@ class Ops:
         assert dbias is None
         extra = (2.0 * dx.numel() if act is not None else 0.0) + (2.0 * dx.numel() if residual is not None else 0.0)
         self._w(2.0 * dx.numel() + 3.0 * dy.numel() + extra, "byte")
+        pd = _pitch(dx)
+        if pd and ((act is not None and _pitch(act) != pd) or (residual is not None and _pitch(residual) != pd)):
+            raise ValueError("maxpool_bwd: dx, act and residual must be views of the same geometry")
+        self._views(tout=dx)
         self.call("segk_maxpool2x2_bwd", _p(dy), _p(idx), _p(act), 0, _p(residual), _p(dx), 0, n, h, w, c, _stream())
         return dx
 
@@ -625,5 +656,6 @@ class Ops:
     def bias_grad(self, dy, db):
         c = dy.shape[-1]
         self._w(float(dy.numel() * dy.element_size()), "byte")
+        self._views(tin=dy)
         self.call("segk_bias_grad", _p(dy), int(dy.dtype == torch.float32), _p(db), dy.numel() // c, c, _stream())
         return db

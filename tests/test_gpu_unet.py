@@ -136,6 +136,31 @@ def test_unet_forward_and_gradients(cuda_device, init):
     print(f"[{init}] unet worst grad {worst[0]}: rel {worst[1]:.3e} cos {worst[2]:.6f}")
 
 
+def test_unet_zero_copy_concat_matches_the_copy_form_bit_for_bit(cuda_device):
+    """Concat (utils.py:332) without copies: the transposed convs and the encoder skip convs write into channel slices of
+    the concat buffers and their gradients are read in place (GraphNet._concat_slots).  Same kernels, same arithmetic:
+    logits and every gradient must equal the segk_channel_copy form exactly."""
+    from semanticsegmentation_tensorflow_b200.graph import UNet
+    net, variables, x, lab = _build(cuda_device, "he")
+    assert sorted(net.slot) == sorted(["unpool%d" % i for i in range(1, 6)] + ["conv13", "conv10", "conv7", "conv4", "conv2"])
+    for t, (cat, off) in net.slot.items():
+        assert net.act[t].data_ptr() == net.act[cat].data_ptr() + 2 * off and not net.act[t].is_contiguous()
+    ref = UNet(torch.as_tensor(x).to(cuda_device), 2, variables=variables, zero_copy_concat=False)
+    ref.keep_prepool = True
+    assert not ref.slot
+    labd = torch.as_tensor(lab).to(cuda_device)
+    for m in (net, ref):
+        m.create()
+        m.loss(labd, with_grad=True)
+        m.backward()
+    torch.cuda.synchronize()
+    assert torch.equal(net.logits, ref.logits)
+    for name in net.act:
+        assert torch.equal(net.act[name], ref.act[name]), f"activation {name}"
+    for name in net.vars.slots:
+        assert torch.equal(net.vars.grad(name), ref.vars.grad(name)), f"gradient {name}"
+
+
 def test_unet_training_steps(cuda_device):
     from semanticsegmentation_tensorflow_b200.fcn import AdamOptimizer
     net, variables, x, lab = _build(cuda_device, "he")
