@@ -67,6 +67,7 @@ int segk_set_tuning(segk_ctx* ctx, const char* key, int value) {
   else if (!strcmp(key, "wslab")) ctx->wslab = value;
   else if (!strcmp(key, "teamk")) ctx->teamk = value;
   else if (!strcmp(key, "hybrid")) ctx->hybrid = value;
+  else if (!strcmp(key, "pair")) ctx->pair = value;
   else if (!strcmp(key, "tail_wide")) ctx->tail_wide = value;
   else if (!strcmp(key, "force_bn")) ctx->force_bn = value;
   else if (!strcmp(key, "force_ksplit")) ctx->force_ksplit = value;

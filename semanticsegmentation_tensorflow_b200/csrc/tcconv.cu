@@ -73,6 +73,7 @@ struct alignas(64) TensorMaps {
   CUtensorMap a[4];
   CUtensorMap b;
   CUtensorMap c;   // output tensor (TMA-store epilogue), box (64 ch, bw, bh, bn)
+  CUtensorMap b2;  // CTA-pair mode: the weights with a box of BLOCK_N / 2 rows (each CTA stages half of the B tile)
 };
 
 struct TapTable {
@@ -143,6 +144,9 @@ struct IgemmParams {
   // narrow fp32 output (class-count heads: a 3x3 conv to 2 classes runs as a 64-column tile whose padded columns are
   // zero weights): only the first out_cols columns are stored, as fp32 [pixels][out_cols]
   int out_cols;
+  // CTA-pair mode (igemm_pair_kernel, cta_group::2): CTAs 2q and 2q+1 take two consecutive pixel tiles of the same channel
+  // tile and run them as ONE M = 256 MMA -- each stages its own A box and half of the weight tile (plain schedule only)
+  int pair;
 };
 
 struct PipeState {
@@ -190,6 +194,18 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
   return t;
 }
 
+// pixel tile r (x fastest, then y, then n -- the order of decode_tile) of channel tile nt; r may be one past the last tile
+// (the odd tile's partner in CTA-pair mode): its box lies outside the batch, loads zero-fill and nothing is stored
+__device__ __forceinline__ TileCoord decode_mtile(const IgemmParams& p, int r, int nt) {
+  TileCoord t;
+  t.split = 0; t.phase = 0; t.nt = nt;
+  t.x0 = (r % p.tiles_w) * p.bw;
+  r /= p.tiles_w;
+  t.y0 = (r % p.tiles_h) * p.bh;
+  t.n0 = (r / p.tiles_h) * p.bn;
+  return t;
+}
+
 // A tap whose shifted box lies entirely outside the input contributes only zeros.
 __device__ __forceinline__ bool tap_active(const IgemmParams& p, const TileCoord& t, int dy, int dx) {
   const int ya = t.y0 + dy, xa = t.x0 + dx;
@@ -220,7 +236,7 @@ struct Work {
 struct WorkIter {
   int tile, tlo, thi, cta;
   __device__ __forceinline__ void init(const IgemmParams& p) {
-    tile = blockIdx.x;
+    tile = p.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     tlo = thi = cta = 0;
     if (p.ts) {
       cta = blockIdx.x % p.ts_G;
@@ -230,6 +246,25 @@ struct WorkIter {
     }
   }
   __device__ __forceinline__ bool next(const IgemmParams& p, const TapTable& taps, Work& w) {
+    if (p.pair) {
+      // unit = (channel tile, pair of consecutive pixel tiles); both CTAs walk the union of their tiles' active taps so
+      // that the pair issues one k-step sequence (a tap that is all padding for one of them loads zeros there)
+      const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+      const int pairs = (m_tiles + 1) >> 1;
+      if (tile >= pairs * p.n_tiles) return false;
+      const int unit = tile;
+      tile += (int)(gridDim.x >> 1);
+      int mp, nt;
+      if (p.m_fastest) { mp = unit % pairs; nt = unit / pairs; } else { nt = unit % p.n_tiles; mp = unit / p.n_tiles; }
+      const int rank = (int)(blockIdx.x & 1);
+      w.t = decode_mtile(p, 2 * mp + rank, nt);
+      const TileCoord peer = decode_mtile(p, 2 * mp + (rank ^ 1), nt);
+      w.tm = tap_mask(p, taps, w.t) | tap_mask(p, taps, peer);
+      w.partial = 0;
+      w.lo = 0;
+      w.hi = __popcll(w.tm) * p.kchunks;
+      return true;
+    }
     if (!p.ts) {
       const int tiles = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
       // units: every tile in ksplits pieces -- or, hybrid (p.hyb): the first hyb_full tiles whole (whole waves
@@ -482,37 +517,53 @@ __device__ __forceinline__ void epilogue_pool_store(const P& p, const uint8_t* s
   *reinterpret_cast<uint2*>(p.pool_idx + o) = make_uint2(idxw[0], idxw[1]);
 }
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kThreads, 1)
-igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const TapTable taps) {
+// PAIR (BLOCK_N = 256 only; launched as clusters of two CTAs, igemm_pair_kernel): the two CTAs of a cluster run two
+// consecutive pixel tiles of one channel tile as a single cta_group::2 MMA with M = 256.  Each CTA stages its own A box and
+// HALF of the weight tile (128 rows), so a stage is 32 KB instead of 48 (six stages instead of four), and per SM both the
+// operand reads from shared memory (96 -> 64 B/clk) and the weight bytes arriving by TMA halve.  The leader (rank 0)
+// owns the full barriers (both CTAs' TMA bytes complete on them), issues the MMAs and multicasts their commits to both
+// CTAs' empty / accumulator-full barriers; both CTAs' epilogue threads arrive on the leader's accumulator-empty barriers.
+// Epilogues are unchanged: each CTA's TMEM holds the 128 accumulator rows of its own pixel tile.
+template <int BLOCK_N, bool PAIR>
+__device__ __forceinline__ void igemm_body(const TensorMaps& maps, const IgemmParams& p, const TapTable& taps) {
   using C = Cfg<BLOCK_N>;
+  static_assert(!PAIR || BLOCK_N == 256, "CTA-pair mode is built for the 256-column tile");
+  constexpr int kBHalf = BLOCK_N * 64;                                      // bytes of half a weight tile
+  constexpr int STB = PAIR ? kABytes + kBHalf : C::kStageBytes;             // stage bytes
+  constexpr int NST = PAIR ? kSmemBudget / STB : C::kStages;                // stages
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_out = smem + C::kStages * C::kStageBytes;
+  uint8_t* smem_out = smem + NST * STB;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_out + kOutBytes);
-  uint64_t* empty_bar = full_bar + C::kStages;
-  uint64_t* tfull_bar = empty_bar + C::kStages;
+  uint64_t* empty_bar = full_bar + NST;
+  uint64_t* tfull_bar = empty_bar + NST;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t crank = 0;
+  if constexpr (PAIR) crank = cluster_ctarank();
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.a[i]);
-    tma_prefetch_desc(&maps.b);
-    for (int i = 0; i < C::kStages; ++i) {
+    tma_prefetch_desc(PAIR ? &maps.b2 : &maps.b);
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiThreads);
+      mbar_init(&tempty_bar[i], PAIR ? 2 * kEpiThreads : kEpiThreads);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair<C::kTmemCols>(tmem_slot);
+    else tmem_alloc<C::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();       // both CTAs' barriers exist before either one's TMA / commits reach them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -537,13 +588,13 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
             const int i = __ffsll((long long)m) - 1;
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
             if (elect_one()) {
-              uint8_t* sa = smem + ps.stage * C::kStageBytes;
+              uint8_t* sa = smem + ps.stage * STB;
               mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
               tma_load_4d(&maps.a[taps.map[i]], &full_bar[ps.stage], sa, kc * kBlockK, t.x0 + taps.dx[i], t.y0 + taps.dy[i], t.n0);
               tma_load_4d(&maps.b, &full_bar[ps.stage], sa + kABytes, 0, t.nt * BLOCK_N, kc, i);
             }
             __syncwarp();
-            ps.advance<C::kStages>();
+            ps.advance<NST>();
           }
         }
     } else
@@ -557,21 +608,29 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
           if (step < w.lo || step >= w.hi) continue;
           mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
           if (elect_one()) {
-            uint8_t* sa = smem + ps.stage * C::kStageBytes;
-            mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
-            tma_load_4d(&maps.a[mi], &full_bar[ps.stage], sa, kc * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
-            tma_load_4d(&maps.b, &full_bar[ps.stage], sa + kABytes, 0, t.nt * BLOCK_N, kc, t.phase * p.ntaps + i);
+            uint8_t* sa = smem + ps.stage * STB;
+            if constexpr (PAIR) {
+              // the leader's barrier counts the bytes of both CTAs' loads
+              const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[ps.stage]), 0);
+              if (crank == 0) mbar_arrive_expect_tx(&full_bar[ps.stage], 2u * ((uint32_t)p.rows * 128u + (uint32_t)kBHalf));
+              tma_load_4d_pair(&maps.a[mi], lead_full, sa, kc * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
+              tma_load_4d_pair(&maps.b2, lead_full, sa + kABytes, 0, t.nt * BLOCK_N + (int)crank * (BLOCK_N / 2), kc, i);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
+              tma_load_4d(&maps.a[mi], &full_bar[ps.stage], sa, kc * kBlockK, t.x0 + dx, t.y0 + dy, t.n0);
+              tma_load_4d(&maps.b, &full_bar[ps.stage], sa + kABytes, 0, t.nt * BLOCK_N, kc, t.phase * p.ntaps + i);
+            }
           }
           __syncwarp();
-          ps.advance<C::kStages>();
+          ps.advance<NST>();
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && crank == 0) {
     PipeState ps;
     int acc = 0;
     uint32_t acc_phase = 0;
-    constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 0, 0);
+    constexpr uint32_t idesc = make_idesc(PAIR ? 2 * kBlockM : kBlockM, BLOCK_N, 0, 0);
     const uint32_t smem_lo = smem_u32(smem) >> 4;          // descriptor start-address units (16 B)
     WorkIter it;
     it.init(p);
@@ -589,7 +648,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
             mbar_wait(&full_bar[ps.stage], ps.phase);
             tc_fence_after();
             if (elect_one()) {
-              const uint32_t a_lo = smem_lo + (uint32_t)ps.stage * (uint32_t)(C::kStageBytes >> 4);
+              const uint32_t a_lo = smem_lo + (uint32_t)ps.stage * (uint32_t)(STB >> 4);
               const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
 #pragma unroll
               for (int kk = 0; kk < kBlockK / 16; ++kk)
@@ -598,7 +657,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
               umma_commit(&empty_bar[ps.stage]);
             }
             __syncwarp();
-            ps.advance<C::kStages>();
+            ps.advance<NST>();
           }
         }
       if (elect_one()) {
@@ -616,22 +675,31 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
         mbar_wait(&full_bar[ps.stage], ps.phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a_lo = smem_lo + (uint32_t)ps.stage * (uint32_t)(C::kStageBytes >> 4);
+          const uint32_t a_lo = smem_lo + (uint32_t)ps.stage * (uint32_t)(STB >> 4);
           const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
+          if constexpr (PAIR) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_f16(d_addr, kDescKMajor | (uint64_t)(a_lo + 2 * k), kDescKMajor | (uint64_t)(b_lo + 2 * k), idesc,
-                     (ks | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[ps.stage]);
-          if (ks == nsteps - 1) umma_commit(&tfull_bar[acc]);
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16_pair(d_addr, kDescKMajor | (uint64_t)(a_lo + 2 * k), kDescKMajor | (uint64_t)(b_lo + 2 * k), idesc,
+                            (ks | k) != 0 ? 1u : 0u);
+            umma_commit_pair(&empty_bar[ps.stage]);
+            if (ks == nsteps - 1) umma_commit_pair(&tfull_bar[acc]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16(d_addr, kDescKMajor | (uint64_t)(a_lo + 2 * k), kDescKMajor | (uint64_t)(b_lo + 2 * k), idesc,
+                       (ks | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[ps.stage]);
+            if (ks == nsteps - 1) umma_commit(&tfull_bar[acc]);
+          }
         }
         __syncwarp();
-        ps.advance<C::kStages>();
+        ps.advance<NST>();
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-  } else {
+  } else if (warp >= 2) {
     // ---- epilogue: warps 2..9, TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 ----
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
@@ -722,7 +790,7 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
         if (do_tma) {
           fence_proxy_async();                        // generic-proxy smem writes -> visible to the TMA engine
           named_bar_sync(1, kEpiThreads);
-          if (ep_leader && !p.pool_only) {
+          if (ep_leader && !p.pool_only && t.n0 < p.N) {      // (n0 >= N: the odd tile's partner in CTA-pair mode)
             tma_store_4d(&maps.c, sbuf, t.nt * BLOCK_N + g0, t.x0, t.y0, t.n0);
             tma_store_commit();
           }
@@ -737,15 +805,19 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
+      if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));   // the leader's MMA warp waits for both epilogues
+      else mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
     if (p.tma_store && ep_leader) tma_store_wait_read<0>();
     if (p.colsum) {
-      const int nt = blockIdx.x % p.n_tiles;
+      // partial row of this CTA: all its tiles have channel tile nt; slot = its index among the CTAs of that channel tile
+      const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+      const int nt = unit0 % p.n_tiles;
+      const int slot = PAIR ? (unit0 / p.n_tiles) * 2 + (int)(blockIdx.x & 1) : unit0 / p.n_tiles;
       const int rows_per_nt = (gridDim.x / p.n_tiles) * 4;
-      float* dst = p.colsum + ((int64_t)nt * rows_per_nt + (blockIdx.x / p.n_tiles) * 4 + q) * BLOCK_N + half * 32 + lane;
+      float* dst = p.colsum + ((int64_t)nt * rows_per_nt + slot * 4 + q) * BLOCK_N + half * 32 + lane;
       dst[0] = ca0;
       if (BLOCK_N > 64) dst[64] = ca1;
       if (BLOCK_N > 128) { dst[128] = ca2; dst[192] = ca3; }
@@ -753,9 +825,24 @@ igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const
   }
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();       // the peer's shared memory and barriers stay alive until the leader's last MMA / commit
+  else __syncthreads();
   tc_fence_after();
-  if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_dealloc_pair<C::kTmemCols>(tmem_base);
+    else tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const TapTable taps) {
+  igemm_body<BLOCK_N, false>(maps, p, taps);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+igemm_pair_kernel(const __grid_constant__ TensorMaps maps, const IgemmParams p, const TapTable taps) {
+  igemm_body<256, true>(maps, p, taps);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1897,12 +1984,29 @@ int launch_igemm_t(segk_ctx* ctx, const TensorMaps& maps, const IgemmParams& p, 
   return SEGK_OK;
 }
 
+// `pair_ok`: maps.b2 is encoded and the launch may run as CTA pairs (igemm_pair_kernel); *grid_out = the grid used
 int launch_igemm(segk_ctx* ctx, int block_n, const TensorMaps& maps, const IgemmParams& p, const TapTable& taps,
-                 cudaStream_t st, int fixed_grid = 0) {
+                 cudaStream_t st, int fixed_grid = 0, bool pair_ok = false, int* grid_out = nullptr) {
   const int tiles_all = p.phases * p.tiles_n * p.tiles_h * p.tiles_w * p.n_tiles;
+  if (pair_ok && ctx->pair && block_n == 256 && fixed_grid == 0 && !p.ts && !p.hyb && p.ksplits == 1 && p.phases == 1 && !p.pack_s) {
+    const int m_tiles = p.tiles_n * p.tiles_h * p.tiles_w;
+    const int units = ((m_tiles + 1) / 2) * p.n_tiles;
+    int gp = units < ctx->sm_count / 2 ? units : ctx->sm_count / 2;
+    if (p.colsum) gp = (gp / p.n_tiles) * p.n_tiles;
+    // (a handful of tiles gains nothing from pairing, and an odd tile count would idle one SM of a pair)
+    if (gp > 0 && m_tiles >= 16) {
+      IgemmParams q = p;
+      q.pair = 1;
+      igemm_pair_kernel<<<2 * gp, kThreads, Cfg<256>::kSmemBytes, st>>>(maps, q, taps);
+      SEGK_LAUNCHED(ctx, "igemm (CTA pairs)");
+      if (grid_out) *grid_out = 2 * gp;
+      return SEGK_OK;
+    }
+  }
   const int total = p.hyb ? p.hyb_full + (tiles_all - p.hyb_full) * p.ksplits : tiles_all * p.ksplits;
   int grid = fixed_grid > 0 ? fixed_grid : (total < ctx->sm_count ? total : ctx->sm_count);
   if (p.colsum) grid = (grid / p.n_tiles) * p.n_tiles;      // every tile of a CTA has the same channel tile
+  if (grid_out) *grid_out = grid;
   switch (block_n) {
     case 256: return launch_igemm_t<256>(ctx, maps, p, taps, grid, st);
     case 128: return launch_igemm_t<128>(ctx, maps, p, taps, grid, st);
@@ -2103,6 +2207,11 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
   maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
   rc = encode_weight_map_blocked(ctx, &maps.b, wt, Ck, Cn, kh * kw, block_n);
   if (rc) return rc;
+  const bool pair_ok = block_n == 256 && ctx->pair != 0;
+  if (pair_ok) {      // CTA-pair mode: each CTA of a pair stages half of the weight tile
+    rc = encode_weight_map_blocked(ctx, &maps.b2, wt, Ck, Cn, kh * kw, block_n / 2);
+    if (rc) return rc;
+  }
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.H = H; p.W = W;
@@ -2135,7 +2244,7 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
     p.pool_out = (bf16*)pool->pooled; p.pool_idx = pool->idx; p.pool_only = pool->pool_only;
     pool->fused = true;
     if (pool->bits_out) { p.bits_out = pool->bits_out; pool->bits_done = true; }
-    return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+    return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream, 0, pair_ok);
   }
   if (!narrow && ((tiles * 2 <= ctx->sm_count && p.ntaps * p.kchunks >= 32 && p.kchunks >= 2) || force_ks > 0)) {
     // one wave of work units.  Measured (tools/time_conv6.py, conv6 dgrad: 50 tiles x 2240 k-steps): 2 splits
@@ -2258,11 +2367,12 @@ int conv_igemm(segk_ctx* ctx, const char* what, const void* x, const void* wt, c
     }
     rc = colsum_scratch(ctx, total, block_n, &p.colsum);
     if (rc) return rc;
-    rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+    int grid_used = 0;
+    rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream, 0, pair_ok, &grid_used);
     if (rc) return rc;
-    return colsum_finish(ctx, colsum_out, (total / p.n_tiles) * p.n_tiles, p.n_tiles, block_n, (cudaStream_t)stream);
+    return colsum_finish(ctx, colsum_out, grid_used, p.n_tiles, block_n, (cudaStream_t)stream);
   }
-  return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+  return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream, 0, pair_ok);
 }
 
 
@@ -2894,12 +3004,14 @@ int segk_tc_init(segk_ctx* ctx) {
   ctx->slab3 = env_int("SEGK_SLAB3", 1);
   ctx->teamk = env_int("SEGK_TEAMK", 1);
   ctx->hybrid = env_int("SEGK_HYBRID", 0);
+  ctx->pair = env_int("SEGK_PAIR", 1);
   cudaError_t e = cudaSuccess;
 #define SEGK_SMEM_ATTR(kern, bytes) \
   if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
   SEGK_SMEM_ATTR(igemm_kernel<64>, Cfg<64>::kSmemBytes);
   SEGK_SMEM_ATTR(igemm_kernel<128>, Cfg<128>::kSmemBytes);
   SEGK_SMEM_ATTR(igemm_kernel<256>, Cfg<256>::kSmemBytes);
+  SEGK_SMEM_ATTR(igemm_pair_kernel, Cfg<256>::kSmemBytes);
   SEGK_SMEM_ATTR(wgrad_kernel<64>, WCfg<64>::kSmemBytes);
   SEGK_SMEM_ATTR(wgrad_kernel<128>, WCfg<128>::kSmemBytes);
   SEGK_SMEM_ATTR(wgrad_kernel<256>, WCfg<256>::kSmemBytes);

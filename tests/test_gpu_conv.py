@@ -597,3 +597,62 @@ def test_fused_pool_and_mask_bits_stay_inside_their_outputs(ops, cuda_device, sh
     dy = dev_bf16(bf16_grid(np.random.default_rng(91).standard_normal((n, h, w, co))), cuda_device)
     ops.conv2d_dgrad(dy, wd, dx, k, k, relu_mask_bits=_pack_bits(xd))
     chk_dx("dgrad with mask bits")
+
+
+PAIR_SHAPES = [
+    # N, H, W, Cin, Cout, k            256-column tiles run as CTA pairs (cta_group::2, M = 256) when there are >= 16 pixel tiles
+    (4, 20, 72, 256, 512, 3),          # 45 pixel tiles (odd: the last pair has a partner outside the batch) x 2 channel tiles
+    (8, 10, 36, 512, 512, 3),          # border tiles whose tap sets differ inside a pair (union walk)
+    (2, 40, 144, 128, 256, 3),         # one channel tile
+    (32, 5, 18, 128, 1024, 7),         # pixel-tile-fastest order (weight-heavy), 7x7 taps mostly padding
+    (5, 24, 40, 256, 256, 1),          # 1x1
+]
+
+
+@pytest.mark.parametrize("shape", PAIR_SHAPES)
+def test_cta_pair_igemm_matches_single_cta_bit_for_bit(ops, cuda_device, shape):
+    """igemm_pair_kernel: two CTAs of a cluster run two pixel tiles as one M = 256 tcgen05.mma.cta_group::2, each staging
+    half of the weight tile.  Same k-step order per output element as the single-CTA kernel (extra all-padding taps of the
+    union walk add zeros), so forward (plain / fused pool / mask bits), dgrad (mask bits, residual, column sums) must agree
+    exactly; parity with the oracle is covered by the ordinary conv tests, which take this path by default."""
+    n, h, w, ci, co, k = shape
+    rng = np.random.default_rng(11)
+    x = dev_bf16(bf16_grid(rng.standard_normal((n, h, w, ci))), cuda_device)
+    wt = dev_f32(bf16_grid(rng.standard_normal((k, k, ci, co)) / np.sqrt(k * k * ci)), cuda_device)
+    b = dev_f32(rng.standard_normal(co) * 0.1, cuda_device)
+    dy = dev_bf16(bf16_grid(rng.standard_normal((n, h, w, co))), cuda_device)
+    res = dev_bf16(bf16_grid(rng.standard_normal((n, h, w, ci))), cuda_device)
+    wk, wd = ops.pack_conv_weights(wt)
+    out = {}
+    try:
+        for mode in (0, 1):
+            ops.ctx.set_tuning("pair", mode)
+            l0 = ops.ctx.launches
+            y = torch.empty((n, h, w, co), dtype=torch.bfloat16, device=cuda_device)
+            bits = torch.zeros((n, h, w, co // 32), dtype=torch.int32, device=cuda_device)
+            ops.conv2d_fwd(x, wk, b, y, k, k, relu=True, relu_bits=bits)
+            y2 = torch.empty_like(y)
+            pooled = torch.empty((n, h // 2, w // 2, co), dtype=torch.bfloat16, device=cuda_device)
+            idx = torch.empty((n, h // 2, w // 2, co), dtype=torch.uint8, device=cuda_device)
+            if h % 2 == 0 and w % 2 == 0:
+                ops.conv2d_fwd_pool(x, wk, b, y2, pooled, idx, k, k, relu=True)
+            xbits = torch.empty((n, h, w, ci // 32), dtype=torch.int32, device=cuda_device)
+            ops.relu_bits(x, xbits)
+            dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=cuda_device)
+            cs = torch.empty(ci, dtype=torch.float32, device=cuda_device)
+            ops.conv2d_dgrad(dy, wd, dx, k, k, relu_mask_bits=xbits, residual=res, colsum=cs)
+            dx2 = torch.empty_like(dx)
+            ops.conv2d_dgrad(dy, wd, dx2, k, k, relu_mask=x)
+            torch.cuda.synchronize()
+            out[mode] = (y, bits, y2, pooled, idx, dx, cs, dx2)
+    finally:
+        ops.ctx.set_tuning("pair", 1)
+    names = ("fwd", "relu bits", "fwd (pool call)", "pooled", "pool idx", "dgrad", "dgrad column sums", "dgrad (bf16 mask)")
+    for a, c, name in zip(out[0], out[1], names):
+        if name == "dgrad column sums":      # per-CTA partial rows: the grid (hence the fixed summation order) differs between the modes
+            np.testing.assert_allclose(a.cpu().numpy(), c.cpu().numpy(), rtol=1e-4, atol=1e-3)
+        else:
+            assert torch.equal(a, c), f"{name} {shape}: pair vs single-CTA"
+    # and against the oracle once more, explicitly in pair mode
+    ref = T.relu(T.bias_add(T.conv2d_same(x.float().cpu(), wt.cpu()), b.cpu())).numpy()
+    assert_close(host(out[1][0]), ref, TOL_BF16, f"pair conv fwd {shape}")
