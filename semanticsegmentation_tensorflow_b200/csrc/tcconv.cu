@@ -1993,8 +1993,35 @@ int launch_igemm(segk_ctx* ctx, int block_n, const TensorMaps& maps, const Igemm
     const int units = ((m_tiles + 1) / 2) * p.n_tiles;
     int gp = units < ctx->sm_count / 2 ? units : ctx->sm_count / 2;
     if (p.colsum) gp = (gp / p.n_tiles) * p.n_tiles;
-    // (a handful of tiles gains nothing from pairing, and an odd tile count would idle one SM of a pair)
-    if (gp > 0 && m_tiles >= 16) {
+    // A pair walks the UNION of its two tiles' active taps (one k-step sequence for both), and an odd tile count leaves one
+    // CTA of the last pair idle: pair only when that costs under 4 % more k-steps than single-CTA tiles.  Large maps lose
+    // nothing (tap sets differ at the image border only); conv6 (7x7 taps on a 5x18 map, every tile a different tap set)
+    // would walk 13 % more (ncu r2: 433 k vs 382 k active cycles) and stays single.
+    bool worth = gp > 0 && m_tiles >= 16;
+    if (worth && p.ntaps > 1) {
+      const int cols = p.tiles_w * p.tiles_h;
+      std::vector<uint64_t> cm((size_t)cols);
+      for (int c = 0; c < cols; ++c) {
+        const int x0 = (c % p.tiles_w) * p.bw, y0 = (c / p.tiles_w) * p.bh;
+        uint64_t m = 0;
+        for (int i = 0; i < p.ntaps; ++i) {
+          const int ya = y0 + taps.dy[i], xa = x0 + taps.dx[i];
+          if (!(ya + p.bh <= 0 || ya >= p.in_H || xa + p.bw <= 0 || xa >= p.in_W)) m |= 1ull << i;
+        }
+        if (m == 0) m = p.ntaps >= 64 ? ~0ull : ((1ull << p.ntaps) - 1);      // (mirrors tap_mask())
+        cm[c] = m;
+      }
+      int64_t single = 0, paired = 0;
+      for (int r = 0; r < m_tiles; r += 2) {
+        const uint64_t a = cm[r % cols], b = cm[(r + 1) % cols];
+        single += __builtin_popcountll(a) + (r + 1 < m_tiles ? __builtin_popcountll(b) : 0);
+        paired += 2 * __builtin_popcountll(a | b);
+      }
+      worth = paired * 100 <= single * 104;
+    } else if (worth) {
+      worth = (m_tiles & 1) == 0 || m_tiles >= 50;
+    }
+    if (worth) {
       IgemmParams q = p;
       q.pair = 1;
       igemm_pair_kernel<<<2 * gp, kThreads, Cfg<256>::kSmemBytes, st>>>(maps, q, taps);

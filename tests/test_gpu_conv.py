@@ -631,9 +631,9 @@ def test_cta_pair_igemm_matches_single_cta_bit_for_bit(ops, cuda_device, shape):
             y = torch.empty((n, h, w, co), dtype=torch.bfloat16, device=cuda_device)
             bits = torch.zeros((n, h, w, co // 32), dtype=torch.int32, device=cuda_device)
             ops.conv2d_fwd(x, wk, b, y, k, k, relu=True, relu_bits=bits)
-            y2 = torch.empty_like(y)
-            pooled = torch.empty((n, h // 2, w // 2, co), dtype=torch.bfloat16, device=cuda_device)
-            idx = torch.empty((n, h // 2, w // 2, co), dtype=torch.uint8, device=cuda_device)
+            y2 = torch.zeros_like(y)
+            pooled = torch.zeros((n, h // 2, w // 2, co), dtype=torch.bfloat16, device=cuda_device)
+            idx = torch.zeros((n, h // 2, w // 2, co), dtype=torch.uint8, device=cuda_device)
             if h % 2 == 0 and w % 2 == 0:
                 ops.conv2d_fwd_pool(x, wk, b, y2, pooled, idx, k, k, relu=True)
             xbits = torch.empty((n, h, w, ci // 32), dtype=torch.int32, device=cuda_device)
