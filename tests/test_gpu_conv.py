@@ -606,6 +606,8 @@ PAIR_SHAPES = [
     (2, 40, 144, 128, 256, 3),         # one channel tile
     (32, 5, 18, 128, 1024, 7),         # pixel-tile-fastest order (weight-heavy), 7x7 taps mostly padding
     (5, 24, 40, 256, 256, 1),          # 1x1
+    (32, 10, 36, 512, 512, 3),         # conv5_x at B=32: 90 pixel tiles, 45 pairs per channel tile
+    (32, 20, 72, 512, 256, 3),         # one 256-column channel tile, 360 pixel tiles
 ]
 
 
