@@ -170,6 +170,42 @@ def graph_init(shapes, seed=1234, init="ref"):
     return out
 
 
+def concat_slots(nodes, shape, route):
+    """Zero-copy Concat (utils.py:332): {tensor: (concat node, channel offset)} for the Concat inputs whose producer can write
+    straight into its channel slice of the concat buffer and whose gradient can be read in place from the concat's
+    gradient (channel-slice views, segk_set_pitch) -- no copy forward, none backward.  That holds for
+      * a transposed conv without ReLU that only the Concat reads (the decoder's upsampled half), and
+      * a tensor-core conv read by the Concat and by ONE earlier Max_Pooling (an encoder skip): the pool's backward adds
+        its gradient to the slice and applies the conv's ReluGrad to the sum; or, without ReLU, read by the Concat alone.
+    Everything else keeps the segk_channel_copy form.  `shape`: {tensor: (N,H,W,C)}, `route`: {conv / deconv node: route}."""
+    slots = {}
+    by_name = {n.name: n for n in nodes}
+    order = {n.name: i for i, n in enumerate(nodes)}
+    last = nodes[-1].name
+    for n in nodes:
+        if n.kind != "concat" or n.name == last:
+            continue
+        off = 0
+        for t in n.inputs:
+            c = shape[t][3]
+            p = by_name.get(t)
+            users = [m for m in nodes if t in m.inputs]
+            ok = (p is not None and p.kind in ("conv", "deconv") and route.get(t) == "tc" and c % 64 == 0 and off % 64 == 0
+                  and t not in slots and n.inputs.count(t) == 1 and t != last)
+            if ok and p.kind == "deconv":
+                ok = not p.relu and len(users) == 1
+            elif ok:
+                pools = [m for m in users if m.kind == "pool"]
+                if len(users) == 2 and len(pools) == 1:
+                    ok = order[pools[0].name] < order[n.name]
+                else:
+                    ok = len(users) == 1 and not p.relu
+            if ok:
+                slots[t] = (n.name, off)
+            off += c
+    return slots
+
+
 class _Vars:
     """Flat fp32 arenas in creation order (params, grads, optimizer slots)."""
 
@@ -329,40 +365,9 @@ class GraphNet(_Feeds):
                 self.head_gw[n.name] = torch.empty((n.k, n.k, cin, 64), dtype=torch.float32, device=dev)
 
     def _concat_slots(self):
-        """Zero-copy Concat (utils.py:332): {tensor: (concat node, channel offset)} for the Concat inputs whose producer can write
-        straight into its channel slice of the concat buffer and whose gradient can be read in place from the concat's
-        gradient (channel-slice views, segk_set_pitch) -- no copy forward, none backward.  That holds for
-          * a transposed conv without ReLU that only the Concat reads (the decoder's upsampled half), and
-          * a tensor-core conv read by the Concat and by ONE earlier Max_Pooling (an encoder skip): the pool's backward adds
-            its gradient to the slice and applies the conv's ReluGrad to the sum; or, without ReLU, read by the Concat alone.
-        Everything else keeps the segk_channel_copy form."""
-        slots = {}
         if not getattr(self, "zero_copy_concat", True):
-            return slots
-        order = {n.name: i for i, n in enumerate(self.nodes)}
-        last = self.nodes[-1].name
-        for n in self.nodes:
-            if n.kind != "concat" or n.name == last:
-                continue
-            off = 0
-            for t in n.inputs:
-                c = self.shape[t][3]
-                p = self.by_name.get(t)
-                users = [m for m in self.nodes if t in m.inputs]
-                ok = (p is not None and p.kind in ("conv", "deconv") and self.route.get(t) == "tc" and c % 64 == 0 and off % 64 == 0
-                      and t not in slots and n.inputs.count(t) == 1 and t != last)
-                if ok and p.kind == "deconv":
-                    ok = not p.relu and len(users) == 1
-                elif ok:
-                    pools = [m for m in users if m.kind == "pool"]
-                    if len(users) == 2 and len(pools) == 1:
-                        ok = order[pools[0].name] < order[n.name]
-                    else:
-                        ok = len(users) == 1 and not p.relu
-                if ok:
-                    slots[t] = (n.name, off)
-                off += c
-        return slots
+            return {}
+        return concat_slots(self.nodes, self.shape, self.route)
 
     def _repack(self, ops, only=None):
         V = self.vars

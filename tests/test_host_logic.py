@@ -290,3 +290,70 @@ def test_reference_helper_signatures():
     assert sig(layers.fuse) == [("x1", E), ("x2", E), ("name", E)]
     import semanticsegmentation_tensorflow_b200 as pkg
     assert pkg.conv_layer is layers.conv_layer and pkg.fuse is layers.fuse
+
+
+def _plan_shapes(nodes, cin=3, hw=(64, 64)):
+    """Shapes / routes of a node list as GraphNet._plan derives them (tensor-core route = both channel counts % 64 == 0)."""
+    shape, route = {"input": (2, hw[0], hw[1], cin)}, {}
+    for n in nodes:
+        N, h, w, c = shape[n.inputs[0]]
+        if n.kind == "pool":
+            shape[n.name] = (N, h // 2, w // 2, c)
+        elif n.kind == "concat":
+            shape[n.name] = (N, h, w, sum(shape[i][3] for i in n.inputs))
+        elif n.kind == "deconv":
+            shape[n.name], route[n.name] = (N, h * 2, w * 2, n.cout), "tc"
+        else:
+            shape[n.name] = (N, h, w, n.cout)
+            route[n.name] = "tc" if (c % 64 == 0 and n.cout % 64 == 0) else "other"
+    return shape, route
+
+
+def test_zero_copy_concat_planning():
+    """Which Concat inputs (utils.py:332) become channel slices of the concat buffer (graph.concat_slots)."""
+    from semanticsegmentation_tensorflow_b200.graph import GraphBuilder, concat_slots, unet_nodes
+    nodes = unet_nodes(2)
+    shape, route = _plan_shapes(nodes)
+    slots = concat_slots(nodes, shape, route)
+    # the U-Net: every upsampled half at offset 0, every encoder skip behind it
+    assert slots == {"unpool1": ("concat1", 0), "conv13": ("concat1", 512), "unpool2": ("concat2", 0), "conv10": ("concat2", 512),
+                     "unpool3": ("concat3", 0), "conv7": ("concat3", 256), "unpool4": ("concat4", 0), "conv4": ("concat4", 128),
+                     "unpool5": ("concat5", 0), "conv2": ("concat5", 64)}
+    # a ReLU conv read by the Concat and by another conv: its ReluGrad cannot be applied in place -> stays a copy;
+    # a conv without ReLU read by the Concat alone, and a pool-only skip whose pool comes AFTER the concat -> copy for the latter
+    g = GraphBuilder()
+    a = g.Conv2D_Block("input", 64, batch_normalization=True, relu=True, name="a")        # from 3 channels: not a tensor-core route
+    b = g.Conv2D_Block(a, 64, batch_normalization=True, relu=True, name="b")             # read by c and the concat
+    c = g.Conv2D_Block(b, 64, batch_normalization=True, relu=False, name="c")            # no ReLU, read by the concat only
+    d = g.Conv2D_Block(b, 64, batch_normalization=True, relu=True, name="d")             # ReLU, concat + a LATER pool
+    cat = g.Concat([a, b, c, d], "cat")
+    g.Max_Pooling(d, "late_pool")
+    g.Conv2D_Block(cat, 2, 1, 1, name="head")
+    shape, route = _plan_shapes(g.nodes)
+    assert concat_slots(g.nodes, shape, route) == {"c": ("cat", 128)}
+    # the same tensor twice in one Concat, and a concat that is the network output, never alias
+    g = GraphBuilder()
+    a = g.Conv2D_Block("input", 64, name="a")
+    b = g.Conv2D_Block(a, 64, name="b")
+    g.Concat([b, b], "cat")
+    shape, route = _plan_shapes(g.nodes)
+    assert concat_slots(g.nodes, shape, route) == {}
+
+
+def test_channel_slice_view_pitch():
+    """ops._pitch: the channel pitch handed to segk_set_pitch for a torch view, and what is rejected."""
+    import torch
+    from semanticsegmentation_tensorflow_b200.ops import _pitch
+    wide = torch.zeros((2, 4, 6, 256), dtype=torch.bfloat16)
+    assert _pitch(wide) == 0 and _pitch(None) == 0
+    assert _pitch(wide[..., 64:192]) == 256 and _pitch(wide[..., :64]) == 256
+    with pytest.raises(ValueError):
+        _pitch(wide.permute(0, 2, 1, 3))                     # not a channel slice
+    with pytest.raises(ValueError):
+        _pitch(wide[..., 4:68])                              # first element not 16-byte aligned
+    assert _pitch(wide[:, :, ::2, :64]) == 512              # every other pixel of a row is still a uniform pixel pitch
+    with pytest.raises(ValueError):
+        _pitch(wide[:, ::2, :, :64])                         # rows skipped: not one pitch
+    odd = torch.zeros((1, 2, 2, 100), dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        _pitch(odd[..., :64])                                # pitch not a multiple of 8 channels
