@@ -449,10 +449,14 @@ int segk_adam_step_ranges(segk_ctx* ctx, float* p, float* m, float* v, const flo
                           const int64_t* lengths, int nranges, float lr_t, float beta1, float beta2, float eps,
                           float grad_scale, void* stream);
 /* The same update for ONE conv_layer weight tensor [kh,kw,Cin,Cout] (Cin, Cout multiples of 64) fused with
- * segk_pack_conv_weights: the fresh parameters are written back and, from the same pass, as bf16 into wk / wd. */
+ * segk_pack_conv_weights: the fresh parameters are written back and, from the same pass, as bf16 into wk / wd.
+ * col_scale (fp32 [Cout] or NULL), col_mult: the packed copies hold p[.., co] * col_scale[co] * col_mult -- the
+ * inference-mode Batch_Normalization scale gamma / sqrt(1 + eps) of Conv2D_Block (utils.py:186-208,300-301) folded into
+ * the kernel-layout weights, i.e. segk_scale_columns + segk_pack_conv_weights in the same pass (the fp32 master
+ * weights stay unscaled; col_scale must already hold this step's updated gamma). */
 int segk_adam_pack_conv_weights(segk_ctx* ctx, float* p, float* m, float* v, const float* g, void* wk, void* wd,
-                                int kh, int kw, int Cin, int Cout, float lr_t, float beta1, float beta2, float eps,
-                                float grad_scale, void* stream);
+                                const float* col_scale, float col_mult, int kh, int kw, int Cin, int Cout, float lr_t,
+                                float beta1, float beta2, float eps, float grad_scale, void* stream);
 /* tf.train.MomentumOptimizer: a = mu a + g; p -= lr a (new) */
 int segk_momentum_step(segk_ctx* ctx, float* p, float* a, const float* g, int64_t n, float lr,
                        float mu, float grad_scale, void* stream);

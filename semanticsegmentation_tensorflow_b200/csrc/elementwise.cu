@@ -710,7 +710,8 @@ __global__ void __launch_bounds__(kThreads) pack_blocked_kernel(const float* __r
 __global__ void __launch_bounds__(kThreads) adam_pack_blocked_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                                                      const float* __restrict__ g, bf16* __restrict__ cp,
                                                                      bf16* __restrict__ tr, int A, int B, int rev_cp, float lr_t,
-                                                                     float b1, float b2, float eps, float gs) {
+                                                                     float b1, float b2, float eps, float gs,
+                                                                     const float* __restrict__ col_scale, float col_mult) {
   __shared__ float tile[64][65];
   const int t = blockIdx.z;
   const int tc = rev_cp ? (int)gridDim.z - 1 - t : t;
@@ -720,6 +721,14 @@ __global__ void __launch_bounds__(kThreads) adam_pack_blocked_kernel(float* __re
   const float c1 = 1.f - b1, c2 = 1.f - b2;
   {
     const int c4 = threadIdx.x & 15, r0 = threadIdx.x >> 4;      // A % 64 == 0 and B % 64 == 0: 16-byte accesses, no edges
+    // folded BN scale of this thread's four columns (the packed copies only; p stays the unscaled master weight)
+    // ((p * gamma) * mult, the rounding order of segk_scale_columns: the fused and the separate path agree bit for bit)
+    float4 cs = make_float4(1.f, 1.f, 1.f, 1.f);
+    float cm = 1.f;
+    if (col_scale) {
+      cs = __ldg(reinterpret_cast<const float4*>(col_scale + b0 + c4 * 4));
+      cm = col_mult;
+    }
 #pragma unroll
     for (int r = r0; r < 64; r += 16) {
       const int64_t o = base + (int64_t)(a0 + r) * B + b0 + c4 * 4;
@@ -738,7 +747,8 @@ __global__ void __launch_bounds__(kThreads) adam_pack_blocked_kernel(float* __re
       *reinterpret_cast<float4*>(p + o) = pp;
       *reinterpret_cast<float4*>(m + o) = mm;
       *reinterpret_cast<float4*>(v + o) = vv;
-      tile[r][c4 * 4] = pp.x; tile[r][c4 * 4 + 1] = pp.y; tile[r][c4 * 4 + 2] = pp.z; tile[r][c4 * 4 + 3] = pp.w;
+      tile[r][c4 * 4] = pp.x * cs.x * cm; tile[r][c4 * 4 + 1] = pp.y * cs.y * cm; tile[r][c4 * 4 + 2] = pp.z * cs.z * cm;
+      tile[r][c4 * 4 + 3] = pp.w * cs.w * cm;
     }
   }
   __syncthreads();
@@ -1069,18 +1079,18 @@ int segk_adam_step_ranges(segk_ctx* ctx, float* p, float* m, float* v, const flo
   return SEGK_OK;
 }
 
-int segk_adam_pack_conv_weights(segk_ctx* ctx, float* p, float* m, float* v, const float* g, void* wk, void* wd, int kh,
-                                int kw, int Cin, int Cout, float lr_t, float beta1, float beta2, float eps, float grad_scale,
-                                void* stream) {
+int segk_adam_pack_conv_weights(segk_ctx* ctx, float* p, float* m, float* v, const float* g, void* wk, void* wd,
+                                const float* col_scale, float col_mult, int kh, int kw, int Cin, int Cout, float lr_t,
+                                float beta1, float beta2, float eps, float grad_scale, void* stream) {
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, p && m && v && g && (wk || wd) && kh > 0 && kw > 0, "adam_pack_conv: bad args");
   SEGK_REQUIRE(ctx, Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0, "adam_pack_conv: needs Cin, Cout multiples of 64 (got %d, %d)", Cin, Cout);
-  SEGK_REQUIRE(ctx, (((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)g | (uintptr_t)wk | (uintptr_t)wd) & 15) == 0,
+  SEGK_REQUIRE(ctx, (((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)g | (uintptr_t)wk | (uintptr_t)wd | (uintptr_t)col_scale) & 15) == 0,
                "adam_pack_conv: 16-byte alignment");
   dim3 grid(Cout / 64, Cin / 64, kh * kw);
   SEGK_REQUIRE(ctx, grid.y <= 65535 && grid.z <= 65535, "adam_pack_conv: dims too large");
   adam_pack_blocked_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(p, m, v, g, (bf16*)wd, (bf16*)wk, Cin, Cout, 1, lr_t, beta1,
-                                                                       beta2, eps, grad_scale);
+                                                                       beta2, eps, grad_scale, col_scale, col_mult);
   SEGK_LAUNCHED(ctx, "adam_pack_conv_weights");
   return SEGK_OK;
 }

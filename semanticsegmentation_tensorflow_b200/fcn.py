@@ -683,20 +683,38 @@ class AdamOptimizer:
             net.vars.repack(net.ops, names)
             return
         lr_t = P.adam_lr_t(self.lr, self.t, self.beta1, self.beta2)
-        ranges, rest = [], set()
-        for name, s in V.slots.items():
-            if not (lo <= s.offset < hi):
-                continue
+        # `fused` is a set of layers (FCN) or {layer: its folded BN gamma variable or None} (GraphNet: the packed weights
+        # carry gamma / sqrt(1 + eps), Conv2D_Block of utils.py:186-208).  A folded layer is fused only when its gamma is
+        # updated in this very call (before the pack, below); otherwise it takes the separate Adam + repack path, and a
+        # gamma updated here whose weights are not packed here gets its layer repacked as well.
+        scale_of = fused if isinstance(fused, dict) else {}
+        mult = getattr(V, "fold_mult", 1.0)
+        here = {name for name, s in V.slots.items() if lo <= s.offset < hi}
+        jobs, ranges, rest = [], [], set()
+        for name in here:
             layer = name.split("/")[0]
-            if name.endswith("/weights") and layer in fused:
-                net.ops.adam_pack_conv_weights(V.view(V.p, name), V.view(V.m, name), V.view(V.v, name), V.view(V.g, name),
-                                               V.wk[layer], V.wd[layer], lr_t, self.beta1, self.beta2, self.eps, grad_scale)
-            else:
-                ranges.append((s.offset, s.size))
-                if name.endswith("/weights"):
-                    rest.add(layer)
+            if name.endswith("/weights") and layer in fused and (scale_of.get(layer) is None or scale_of[layer] in here):
+                jobs.append((name, layer))
+        packed = {layer for _, layer in jobs}
+        owner = {g: layer for layer, g in scale_of.items() if g is not None}
+        for name in here:
+            layer = name.split("/")[0]
+            if name.endswith("/weights") and layer in packed:
+                continue
+            s = V.slots[name]
+            ranges.append((s.offset, s.size))
+            if name.endswith("/weights"):
+                rest.add(layer)
+            elif name in owner and owner[name] not in packed:
+                rest.add(owner[name])
         if ranges:
+            ranges.sort()
             net.ops.adam_step_ranges(V.p, V.m, V.v, V.g, ranges, lr_t, self.beta1, self.beta2, self.eps, grad_scale)
+        for name, layer in jobs:
+            gname = scale_of.get(layer)
+            net.ops.adam_pack_conv_weights(V.view(V.p, name), V.view(V.m, name), V.view(V.v, name), V.view(V.g, name),
+                                           V.wk[layer], V.wd[layer], lr_t, self.beta1, self.beta2, self.eps, grad_scale,
+                                           col_scale=V.view(V.p, gname) if gname else None, col_mult=mult if gname else 1.0)
         if rest:
             net.vars.repack(net.ops, rest)
 

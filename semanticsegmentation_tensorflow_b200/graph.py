@@ -263,8 +263,13 @@ class GraphNet(_Feeds):
         values = variables if variables is not None else graph_init(shapes, seed, init)
         self.vars = _Vars(shapes, self.device, values)
         self.vars._repack = self._repack
+        self.vars.fold_mult = BN_SCALE
         self._plan()
         self._repack(self.ops)
+        # tensor-core conv layers whose Adam update and bf16 repack -- with the BN scale folded in -- run as one kernel
+        # (AdamOptimizer.apply_and_repack): {layer: gamma variable or None}
+        self.vars.fused_adam_layers = {n.name: (f"{n.bn_scope}/gamma" if n.bn else None) for n in self.nodes
+                                       if n.kind == "conv" and self.route[n.name] == "tc"}
         self._ran_forward = False
         self.side = SideStream(self.device, enabled=overlap)
         self.wside = SideStream(self.device, enabled=overlap)    # weight-gradient GEMMs beside the dgrad chain

@@ -638,12 +638,14 @@ class Ops:
         self.call("segk_adam_step_ranges", _p(p), _p(m), _p(v), _p(g), ctypes.addressof(offs), ctypes.addressof(lens), n,
                   float(lr_t), float(beta1), float(beta2), float(eps), float(grad_scale), _stream())
 
-    def adam_pack_conv_weights(self, p, m, v, g, wk, wd, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
-        """p, m, v, g: fp32 views [kh,kw,Cin,Cout] of one conv weight; wk / wd its bf16 kernel layouts."""
+    def adam_pack_conv_weights(self, p, m, v, g, wk, wd, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, col_scale=None,
+                               col_mult=1.0):
+        """p, m, v, g: fp32 views [kh,kw,Cin,Cout] of one conv weight; wk / wd its bf16 kernel layouts.  `col_scale` (fp32
+        [Cout]) * col_mult: the folded BN scale the packed copies carry (Conv2D_Block, utils.py:186-208)."""
         kh, kw, cin, cout = p.shape
         self._w(32.0 * p.numel(), "byte")
-        self.call("segk_adam_pack_conv_weights", _p(p), _p(m), _p(v), _p(g), _p(wk), _p(wd), kh, kw, cin, cout, float(lr_t),
-                  float(beta1), float(beta2), float(eps), float(grad_scale), _stream())
+        self.call("segk_adam_pack_conv_weights", _p(p), _p(m), _p(v), _p(g), _p(wk), _p(wd), _p(col_scale), float(col_mult), kh, kw,
+                  cin, cout, float(lr_t), float(beta1), float(beta2), float(eps), float(grad_scale), _stream())
 
     def momentum_step(self, p, a, g, lr, mu, grad_scale=1.0):
         self.call("segk_momentum_step", _p(p), _p(a), _p(g), p.numel(), float(lr), float(mu), float(grad_scale),

@@ -283,6 +283,16 @@ def test_adam_fused_with_repack_and_multi_range(ops, cuda_device):
     torch.cuda.synchronize()
     assert torch.equal(p, p2) and torch.equal(m, m2) and torch.equal(v, v2)
     assert torch.equal(wk, wk2) and torch.equal(wd, wd2)
+    # with the folded BN scale: == adam_step, scale_columns (gamma * mult), pack_conv_weights; master weights unscaled
+    gamma = 1 + 0.2 * torch.randn(shape[3], generator=g_, device=cuda_device)
+    p3, m3, v3 = p2.clone(), m2.clone(), v2.clone()
+    ops.adam_step(p2.view(-1), m2.view(-1), v2.view(-1), g.view(-1), lr_t)
+    wk, wd = ops.pack_conv_weights(ops.scale_columns(p2, gamma, 0.9995))
+    wk3, wd3 = torch.zeros_like(wk), torch.zeros_like(wd)
+    ops.adam_pack_conv_weights(p3, m3, v3, g, wk3, wd3, lr_t, col_scale=gamma, col_mult=0.9995)
+    torch.cuda.synchronize()
+    assert torch.equal(p2, p3) and torch.equal(m2, m3) and torch.equal(v2, v3)
+    assert torch.equal(wk, wk3) and torch.equal(wd, wd3)
     n = 10000
     P_, M_, V_, G_ = (torch.randn(n, generator=g_, device=cuda_device) for _ in range(4))
     V_.abs_()
