@@ -317,6 +317,41 @@ int segk_avgpool2x2_fwd(segk_ctx* ctx, const void* x, int ldx, void* y, int ldy,
                         void* stream);
 int segk_avgpool2x2_bwd(segk_ctx* ctx, const void* dy, int lddy, void* dx, int lddx, int N, int H, int W, int C,
                         void* stream);
+/*
+ * Remaining op families of Network/model, HBM-bound kernels on NHWC bf16 with C % 8 == 0 (opfam.cu).
+ * Avg_Pooling(x, kh, kw, stride_h, stride_w, padding VALID) (utils.py:309; the pyramid-pooling windows of
+ * PSPNet.py:147-165,546-567): y [N,(H-kh)/sh+1,(W-kw)/sw+1,C]; AvgPoolGrad: dx = sum over the windows containing the pixel
+ * of dy / (kh kw). */
+int segk_avgpool_fwd(segk_ctx* ctx, const void* x, void* y, int N, int H, int W, int C, int kh, int kw, int sh, int sw,
+                     void* stream);
+int segk_avgpool_bwd(segk_ctx* ctx, const void* dy, void* dx, int N, int H, int W, int C, int kh, int kw, int sh, int sw,
+                     void* stream);
+/* Max_Pooling(x, kh, kw, stride, padding) (utils.py:306; 3x3 / stride 2 VALID at PSPNet.py:34, SAME at PSPNet.py:190),
+ * same != 0: TF SAME geometry (out = ceil(in / stride), padding ignored by the max).  idx [N,OH,OW,C] u8 = position
+ * (ky * kw + kx) of the first maximum of every window; MaxPoolGrad routes dy there (overlapping windows add up). */
+int segk_maxpool_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int N, int H, int W, int C, int kh, int kw,
+                     int stride, int same, void* stream);
+int segk_maxpool_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, void* dx, int N, int H, int W, int C, int kh,
+                     int kw, int stride, int same, void* stream);
+/* tf.nn.depthwise_conv2d(x, filter [kh,kw,C,1], strides, 'SAME', rate) (DeepLabv3Plus.py:49,117; EfficientNet.py:173,453;
+ * Generative_Segmentation_net.py:53): channel multiplier 1, w fp32 [kh][kw][C], y [N,ceil(H/s),ceil(W/s),C] bf16
+ * (+ bias, ReLU by flags); rate > 1 needs stride 1 as in TF.  dgrad: dx [N,H,W,C]; wgrad: dw fp32 [kh][kw][C]
+ * (two-stage fixed-order sum, += when accumulate). */
+int segk_depthwise_conv2d_fwd(segk_ctx* ctx, const void* x, const float* w, const float* bias, void* y, int N, int H,
+                              int W, int C, int kh, int kw, int stride, int rate, unsigned flags, void* stream);
+int segk_depthwise_conv2d_dgrad(segk_ctx* ctx, const void* dy, const float* w, void* dx, int N, int H, int W, int C,
+                                int kh, int kw, int stride, int rate, void* stream);
+int segk_depthwise_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int C,
+                                int kh, int kw, int stride, int rate, int accumulate, void* stream);
+/* kind 0: tf.sigmoid, kind 1: swish x * sigmoid(x) (EfficientNet.py's activation) on n bf16 elements (n % 8 == 0);
+ * backward from the INPUT x: dx = dy * f'(x). */
+int segk_activation_fwd(segk_ctx* ctx, const void* x, void* y, int64_t n, int kind, void* stream);
+int segk_activation_bwd(segk_ctx* ctx, const void* x, const void* dy, void* dx, int64_t n, int kind, void* stream);
+/* squeeze-excite multiply (EfficientNet.py SE block: x * sigmoid(se) broadcast over H, W): y[n,p,c] = x[n,p,c] * s[n,c],
+ * x [N,HW,C], s [N,C] bf16; backward: dx = dy * s, ds[n,c] = sum_p dy x (fp32 [N,C]). */
+int segk_channel_scale_fwd(segk_ctx* ctx, const void* x, const void* s, void* y, int N, int64_t HW, int C, void* stream);
+int segk_channel_scale_bwd(segk_ctx* ctx, const void* x, const void* s, const void* dy, void* dx, float* ds, int N,
+                           int64_t HW, int C, void* stream);
 /* logical w[T][A][B] fp32 <-> physical wp[T][Ap][Bp]: to_phys != 0: wp = mapped ? w : 0; else w[mapped] = wp.
  * amap[Ap] / bmap[Bp] device int32 arrays (NULL = identity on the first A / B entries). */
 int segk_remap_weights(segk_ctx* ctx, float* w, float* wp, int T, int A, int B, int Ap, int Bp, const int* amap,

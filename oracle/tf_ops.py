@@ -208,3 +208,65 @@ def to_bf16_grid(x: torch.Tensor) -> torch.Tensor:
     """Round an fp32 tensor to the nearest bf16 value (kept as fp32).  Used to build the
     'bf16-storage' variant of the oracle that mirrors where the CUDA path rounds."""
     return x.to(torch.bfloat16).to(torch.float32)
+
+
+# ---- remaining op families (SURVEY §8f row 4) -----------------------------------------------------------------------
+def avg_pool_valid(x: torch.Tensor, kh: int, kw: int, sh: int, sw: int) -> torch.Tensor:
+    """tf.nn.avg_pool(x, [1,kh,kw,1], [1,sh,sw,1], 'VALID')  (utils.py:309; PSPNet.py:147-165 pyramid windows)."""
+    return F.avg_pool2d(x.permute(0, 3, 1, 2), (kh, kw), (sh, sw)).permute(0, 2, 3, 1).contiguous()
+
+
+def max_pool_general(x: torch.Tensor, kh: int, kw: int, stride: int, padding: str = "VALID"):
+    """tf.nn.max_pool(x, [1,kh,kw,1], [1,s,s,1], padding)  (utils.py:306; PSPNet.py:34,190).  Returns (y, idx) with idx the
+    position ky*kw + kx of the FIRST maximum of every window (the element TF's MaxPoolGrad routes the gradient to); SAME
+    padding never wins the max."""
+    n, h, w, c = x.shape
+    if padding == "SAME":
+        oh, pt, pb = _same_pad(h, kh, stride)
+        ow, pl, pr = _same_pad(w, kw, stride)
+    else:
+        oh, ow, pt, pb, pl, pr = (h - kh) // stride + 1, (w - kw) // stride + 1, 0, 0, 0, 0
+    xp = F.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb), value=float("-inf"))
+    win = xp.unfold(2, kh, stride).unfold(3, kw, stride)[:, :, :oh, :ow]            # [n, c, oh, ow, kh, kw]
+    flat = win.reshape(n, c, oh, ow, kh * kw)
+    y = flat.max(dim=4).values
+    first = (flat == y.unsqueeze(4)).to(torch.uint8).argmax(dim=4)                   # first index attaining the max
+    return y.permute(0, 2, 3, 1).contiguous(), first.permute(0, 2, 3, 1).to(torch.uint8).contiguous()
+
+
+def max_pool_general_grad(dy: torch.Tensor, idx: torch.Tensor, in_hw, kh: int, kw: int, stride: int, padding: str = "VALID"):
+    """MaxPoolGrad from the first-max positions: dx[n, oy*s - pt + ky, ox*s - pl + kx, c] += dy[n, oy, ox, c]."""
+    n, oh, ow, c = dy.shape
+    h, w = in_hw
+    pt = _same_pad(h, kh, stride)[1] if padding == "SAME" else 0
+    pl = _same_pad(w, kw, stride)[1] if padding == "SAME" else 0
+    dx = torch.zeros((n, h, w, c), dtype=dy.dtype)
+    ky, kx = (idx // kw).long(), (idx % kw).long()
+    oy = torch.arange(oh).view(1, oh, 1, 1)
+    ox = torch.arange(ow).view(1, 1, ow, 1)
+    iy, ix = oy * stride - pt + ky, ox * stride - pl + kx
+    nn_ = torch.arange(n).view(n, 1, 1, 1).expand_as(iy)
+    cc = torch.arange(c).view(1, 1, 1, c).expand_as(iy)
+    dx.index_put_((nn_.reshape(-1), iy.reshape(-1), ix.reshape(-1), cc.reshape(-1)), dy.reshape(-1), accumulate=True)
+    return dx
+
+
+def depthwise_conv2d_same(x: torch.Tensor, w: torch.Tensor, stride: int = 1, rate: int = 1) -> torch.Tensor:
+    """tf.nn.depthwise_conv2d(x, filter[kh,kw,C,1], [1,s,s,1], 'SAME', rate=[r,r])  (DeepLabv3Plus.py:49,
+    EfficientNet.py:173,453): w [kh,kw,C]; effective window (k-1) r + 1."""
+    kh, kw, c = w.shape
+    _, pt, pb = _same_pad(x.shape[1], (kh - 1) * rate + 1, stride)
+    _, pl, pr = _same_pad(x.shape[2], (kw - 1) * rate + 1, stride)
+    xn = F.pad(x.permute(0, 3, 1, 2), (pl, pr, pt, pb))
+    y = F.conv2d(xn, w.permute(2, 0, 1).unsqueeze(1), stride=stride, dilation=rate, groups=c)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def swish(x: torch.Tensor) -> torch.Tensor:
+    """x * sigmoid(x)  (EfficientNet.py's activation)."""
+    return x * torch.sigmoid(x)
+
+
+def channel_scale(x: torch.Tensor, s: torch.Tensor) -> torch.Tensor:
+    """x [N,H,W,C] * s [N,C] broadcast over H, W (the squeeze-excite multiply of EfficientNet.py's SE block)."""
+    return x * s[:, None, None, :]

@@ -7,7 +7,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "elementwise.cu", "smallconv.cu", "patch.cu", "pipeline.cu", "tcconv.cu", "firstconv.cu", "wslab.cu", "exchange.cu", "dense.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "smallconv.cu", "patch.cu", "pipeline.cu", "tcconv.cu", "firstconv.cu", "wslab.cu", "exchange.cu", "dense.cu", "opfam.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "segk.h")]
 
 

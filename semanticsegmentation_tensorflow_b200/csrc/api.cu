@@ -53,6 +53,7 @@ int segk_destroy(segk_ctx* ctx) {
   if (ctx && ctx->ws4) cudaFree(ctx->ws4);
   if (ctx && ctx->ws5) cudaFree(ctx->ws5);
   if (ctx && ctx->ws6) cudaFree(ctx->ws6);
+  if (ctx && ctx->ws7) cudaFree(ctx->ws7);
   delete ctx;
   return SEGK_OK;
 }

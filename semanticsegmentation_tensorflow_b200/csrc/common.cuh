@@ -46,6 +46,8 @@ struct segk_ctx {
   size_t ws6_bytes = 0;
   void* ws5 = nullptr;      // grow-only scratch for the pool-backward's BiasAddGrad partial rows (elementwise.cu; main stream)
   size_t ws5_bytes = 0;
+  void* ws7 = nullptr;      // grow-only scratch for the depthwise conv's filter-gradient partial rows (opfam.cu)
+  size_t ws7_bytes = 0;
   void* ws3 = nullptr;      // grow-only scratch for the full-resolution 1x1 head's wgrad partials (smallconv.cu)
   size_t ws3_bytes = 0;
   // driver entry point resolved at segk_create (no link-time libcuda dependency)

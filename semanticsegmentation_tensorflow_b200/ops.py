@@ -431,6 +431,75 @@ class Ops:
         self.call("segk_maxpool2x2_bwd", _p(dy), _p(idx), _p(act), 0, _p(residual), _p(dx), 0, n, h, w, c, _stream())
         return dx
 
+    # ---- remaining op families (csrc/opfam.cu) -----------------------------------------
+    def avgpool_window_fwd(self, x, y, kh, kw, sh, sw):
+        """Avg_Pooling(x, kh, kw, sh, sw, VALID) (utils.py:309)."""
+        n, h, w, c = x.shape
+        self._w(2.0 * x.numel() + 2.0 * y.numel(), "byte")
+        self.call("segk_avgpool_fwd", _p(x), _p(y), n, h, w, c, kh, kw, sh, sw, _stream())
+        return y
+
+    def avgpool_window_bwd(self, dy, dx, kh, kw, sh, sw):
+        n, h, w, c = dx.shape
+        self._w(2.0 * dx.numel() + 2.0 * dy.numel(), "byte")
+        self.call("segk_avgpool_bwd", _p(dy), _p(dx), n, h, w, c, kh, kw, sh, sw, _stream())
+        return dx
+
+    def maxpool_general_fwd(self, x, y, idx, kh, kw, stride, same=False):
+        """Max_Pooling(x, kh, kw, stride, VALID | SAME) (utils.py:306) with first-max indices."""
+        n, h, w, c = x.shape
+        self._w(2.0 * x.numel() + 3.0 * y.numel(), "byte")
+        self.call("segk_maxpool_fwd", _p(x), _p(y), _p(idx), n, h, w, c, kh, kw, stride, int(same), _stream())
+        return y, idx
+
+    def maxpool_general_bwd(self, dy, idx, dx, kh, kw, stride, same=False):
+        n, h, w, c = dx.shape
+        self._w(2.0 * dx.numel() + 3.0 * dy.numel(), "byte")
+        self.call("segk_maxpool_bwd", _p(dy), _p(idx), _p(dx), n, h, w, c, kh, kw, stride, int(same), _stream())
+        return dx
+
+    def depthwise_conv2d_fwd(self, x, w, bias, y, stride=1, rate=1, relu=False):
+        """tf.nn.depthwise_conv2d(x, w [kh,kw,C,1], stride, SAME, rate); w fp32 [kh,kw,C]."""
+        n, h, wd, c = x.shape
+        kh, kw = w.shape[0], w.shape[1]
+        self._w(2.0 * x.numel() + 2.0 * y.numel(), "byte")
+        self.call("segk_depthwise_conv2d_fwd", _p(x), _p(w), _p(bias), _p(y), n, h, wd, c, kh, kw, stride, rate,
+                  EPI_RELU if relu else 0, _stream())
+        return y
+
+    def depthwise_conv2d_dgrad(self, dy, w, dx, stride=1, rate=1):
+        n, h, wd, c = dx.shape
+        self._w(2.0 * dx.numel() + 2.0 * dy.numel(), "byte")
+        self.call("segk_depthwise_conv2d_dgrad", _p(dy), _p(w), _p(dx), n, h, wd, c, w.shape[0], w.shape[1], stride, rate, _stream())
+        return dx
+
+    def depthwise_conv2d_wgrad(self, x, dy, dw, stride=1, rate=1, accumulate=False):
+        n, h, wd, c = x.shape
+        self._w(2.0 * x.numel() * dw.shape[0] * dw.shape[1] + 2.0 * dy.numel(), "byte")
+        self.call("segk_depthwise_conv2d_wgrad", _p(x), _p(dy), _p(dw), n, h, wd, c, dw.shape[0], dw.shape[1], stride, rate,
+                  int(accumulate), _stream())
+        return dw
+
+    def activation_fwd(self, x, y, kind):
+        """kind: 'sigmoid' | 'swish'."""
+        self.call("segk_activation_fwd", _p(x), _p(y), x.numel(), {"sigmoid": 0, "swish": 1}[kind], _stream())
+        return y
+
+    def activation_bwd(self, x, dy, dx, kind):
+        self.call("segk_activation_bwd", _p(x), _p(dy), _p(dx), x.numel(), {"sigmoid": 0, "swish": 1}[kind], _stream())
+        return dx
+
+    def channel_scale_fwd(self, x, s, y):
+        """y[n,h,w,c] = x[n,h,w,c] * s[n,c] (squeeze-excite multiply)."""
+        n, h, w, c = x.shape
+        self.call("segk_channel_scale_fwd", _p(x), _p(s), _p(y), n, h * w, c, _stream())
+        return y
+
+    def channel_scale_bwd(self, x, s, dy, dx, ds):
+        n, h, w, c = x.shape
+        self.call("segk_channel_scale_bwd", _p(x), _p(s), _p(dy), _p(dx), _p(ds), n, h * w, c, _stream())
+        return dx, ds
+
     # ---- shared-helper layers (utils.py): BN-affine folding, concat ---------------------------------
     def scale_columns(self, w, scale, mult, out=None):
         c = w.shape[-1]

@@ -155,3 +155,111 @@ def test_conv2d_4x4_stride2_fwd_dgrad_wgrad(ops, cuda_device, shape):
     assert_close(host(y), y_ref, 1e-2, f"4x4 s2 conv fwd {shape}")
     assert_close(host(dx), xt.grad.numpy(), 1e-2, f"4x4 s2 conv dgrad {shape}")
     assert_close(host(dw), wtt.grad.numpy(), 2e-3, f"4x4 s2 conv wgrad {shape}")
+
+
+# ---- round 2, second batch: windowed pools, depthwise conv, sigmoid / swish, squeeze-excite multiply (csrc/opfam.cu) -----
+
+@pytest.mark.parametrize("case", [(2, 20, 72, 64, 20, 72, 20, 72), (2, 20, 72, 64, 10, 36, 10, 36), (1, 20, 72, 128, 7, 24, 7, 24),
+                                  (2, 20, 72, 64, 4, 12, 4, 12), (3, 9, 11, 40, 3, 3, 2, 2), (2, 8, 12, 24, 2, 2, 2, 2)])
+def test_avg_pooling_windows_fwd_bwd(ops, cuda_device, case):
+    """Avg_Pooling(kh, kw, stride_h, stride_w, VALID) (utils.py:309): PSPNet's pyramid windows at 20x72 (PSPNet.py:546-567),
+    an overlapping 3x3 / stride-2 window, and the 2x2 / stride-2 one."""
+    n, h, w, c, kh, kw, sh, sw = case
+    rng = np.random.default_rng(61)
+    x = bf16_grid(rng.standard_normal((n, h, w, c)))
+    ref = T.avg_pool_valid(torch.tensor(x), kh, kw, sh, sw)
+    y = torch.empty(tuple(ref.shape), dtype=torch.bfloat16, device=cuda_device)
+    ops.avgpool_window_fwd(dev_bf16(x, cuda_device), y, kh, kw, sh, sw)
+    dy = bf16_grid(rng.standard_normal(tuple(ref.shape)))
+    xr = torch.tensor(x, requires_grad=True)
+    T.avg_pool_valid(xr, kh, kw, sh, sw).backward(torch.tensor(dy))
+    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=cuda_device)
+    ops.avgpool_window_bwd(dev_bf16(dy, cuda_device), dx, kh, kw, sh, sw)
+    torch.cuda.synchronize()
+    assert_close(host(y), ref.numpy(), 1e-2, f"avg pool {case}")
+    assert_close(host(dx), xr.grad.numpy(), 1e-2, f"avg pool grad {case}")
+
+
+@pytest.mark.parametrize("case", [(2, 82, 290, 64, 3, 2, "VALID"), (2, 40, 144, 64, 3, 2, "SAME"), (1, 7, 9, 8, 3, 2, "SAME"),
+                                  (2, 9, 11, 16, 3, 1, "SAME"), (2, 8, 12, 32, 2, 2, "VALID")])
+def test_max_pooling_windows_fwd_bwd_bit_exact(ops, cuda_device, case):
+    """Max_Pooling(3, 3, stride 2) VALID after Zero_Padding (PSPNet.py:32-34) and SAME (PSPNet.py:190): values, first-max
+    indices and the gradient routing (overlapping windows accumulate) are exact; inputs are ReLU outputs, so ties (zeros)
+    are common and the first-max rule is what is tested."""
+    n, h, w, c, k, s, pad = case
+    rng = np.random.default_rng(62)
+    x = bf16_grid(np.maximum(rng.standard_normal((n, h, w, c)), 0))
+    y_ref, idx_ref = T.max_pool_general(torch.tensor(x), k, k, s, pad)
+    y = torch.empty(tuple(y_ref.shape), dtype=torch.bfloat16, device=cuda_device)
+    idx = torch.empty(tuple(y_ref.shape), dtype=torch.uint8, device=cuda_device)
+    ops.maxpool_general_fwd(dev_bf16(x, cuda_device), y, idx, k, k, s, same=(pad == "SAME"))
+    dy = bf16_grid(rng.integers(-4, 5, tuple(y_ref.shape)).astype(np.float32))      # small integers: sums of up to 4 are exact in bf16
+    dx_ref = T.max_pool_general_grad(torch.tensor(dy), idx_ref, (h, w), k, k, s, pad)
+    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=cuda_device)
+    ops.maxpool_general_bwd(dev_bf16(dy, cuda_device), idx, dx, k, k, s, same=(pad == "SAME"))
+    torch.cuda.synchronize()
+    assert np.array_equal(host(y), y_ref.numpy())
+    assert np.array_equal(idx.cpu().numpy(), idx_ref.numpy())
+    assert np.array_equal(host(dx), dx_ref.numpy())
+
+
+@pytest.mark.parametrize("case", [(2, 20, 36, 64, 3, 1, 1), (2, 21, 37, 32, 3, 2, 1), (1, 20, 36, 728, 3, 1, 2), (2, 12, 18, 96, 5, 2, 1),
+                                  (1, 16, 20, 2304, 3, 1, 4)])
+def test_depthwise_conv_fwd_dgrad_wgrad(ops, cuda_device, case):
+    """tf.nn.depthwise_conv2d(x, filter, stride, SAME, rate) (DeepLabv3Plus.py:49 SepConv_BN: 3x3, stride 1 / 2, atrous rates;
+    EfficientNet.py:173 MBConv: 3x3 / 5x5, stride 1 / 2): forward with bias, input gradient, filter gradient."""
+    n, h, w, c, k, s, r = case
+    rng = np.random.default_rng(63)
+    x = bf16_grid(rng.standard_normal((n, h, w, c)))
+    wt = bf16_grid(rng.standard_normal((k, k, c)) / k)
+    b = rng.standard_normal(c).astype(np.float32) * 0.1
+    xr, wr = torch.tensor(x, requires_grad=True), torch.tensor(wt, requires_grad=True)
+    ref = T.depthwise_conv2d_same(xr, wr, s, r) + torch.tensor(b)
+    dy = bf16_grid(rng.standard_normal(tuple(ref.shape)))
+    ref.backward(torch.tensor(dy))
+    xd, wd_, dyd = dev_bf16(x, cuda_device), dev_f32(wt, cuda_device), dev_bf16(dy, cuda_device)
+    y = torch.empty(tuple(ref.shape), dtype=torch.bfloat16, device=cuda_device)
+    ops.depthwise_conv2d_fwd(xd, wd_, dev_f32(b, cuda_device), y, stride=s, rate=r)
+    dx = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=cuda_device)
+    ops.depthwise_conv2d_dgrad(dyd, wd_, dx, stride=s, rate=r)
+    dw = torch.empty((k, k, c), dtype=torch.float32, device=cuda_device)
+    ops.depthwise_conv2d_wgrad(xd, dyd, dw, stride=s, rate=r)
+    dw2 = dw.clone()
+    ops.depthwise_conv2d_wgrad(xd, dyd, dw2, stride=s, rate=r, accumulate=True)
+    torch.cuda.synchronize()
+    assert_close(host(y), ref.detach().numpy(), 1e-2, f"depthwise fwd {case}")
+    assert_close(host(dx), xr.grad.numpy(), 1e-2, f"depthwise dgrad {case}")
+    assert_close(host(dw), wr.grad.numpy(), 2e-3, f"depthwise wgrad {case}")
+    assert_close(host(dw2), 2 * wr.grad.numpy(), 2e-3, f"depthwise wgrad accumulate {case}")
+
+
+def test_sigmoid_swish_and_squeeze_excite_multiply(ops, cuda_device):
+    """tf.sigmoid / swish (EfficientNet.py's activation) forward + backward and the SE multiply x * s[n, c] with ds = sum_hw dy x."""
+    rng = np.random.default_rng(64)
+    n, h, w, c = 3, 10, 18, 96
+    x = bf16_grid(rng.standard_normal((n, h, w, c)) * 2)
+    dy = bf16_grid(rng.standard_normal((n, h, w, c)))
+    xd, dyd = dev_bf16(x, cuda_device), dev_bf16(dy, cuda_device)
+    for kind, fn in (("sigmoid", torch.sigmoid), ("swish", T.swish)):
+        xr = torch.tensor(x, requires_grad=True)
+        ref = fn(xr)
+        ref.backward(torch.tensor(dy))
+        y, dx = torch.empty_like(xd), torch.empty_like(xd)
+        ops.activation_fwd(xd, y, kind)
+        ops.activation_bwd(xd, dyd, dx, kind)
+        torch.cuda.synchronize()
+        assert_close(host(y), ref.detach().numpy(), 1e-2, kind)
+        assert_close(host(dx), xr.grad.numpy(), 1e-2, kind + " grad")
+    s = bf16_grid(1 / (1 + np.exp(-rng.standard_normal((n, c)))))
+    xr, sr = torch.tensor(x, requires_grad=True), torch.tensor(s, requires_grad=True)
+    ref = T.channel_scale(xr, sr)
+    ref.backward(torch.tensor(dy))
+    sd = dev_bf16(s, cuda_device)
+    y, dx = torch.empty_like(xd), torch.empty_like(xd)
+    ds = torch.empty((n, c), dtype=torch.float32, device=cuda_device)
+    ops.channel_scale_fwd(xd, sd, y)
+    ops.channel_scale_bwd(xd, sd, dyd, dx, ds)
+    torch.cuda.synchronize()
+    assert_close(host(y), ref.detach().numpy(), 1e-2, "channel scale")
+    assert_close(host(dx), xr.grad.numpy(), 1e-2, "channel scale dx")
+    assert_close(host(ds), sr.grad.numpy(), 2e-3, "channel scale ds")

@@ -177,3 +177,53 @@ def test_resize_bilinear_align_corners_against_the_formula():
     assert np.allclose(got, ref, atol=1e-5)
     assert np.allclose(T.global_avg_pool(torch.tensor(x)).numpy(), x.mean(axis=(1, 2)), atol=1e-6)
     assert np.allclose(T.avg_pool_2x2(torch.tensor(x[:, :4, :4])).numpy()[0, 0, 0], x[0, :2, :2].mean(axis=(0, 1)), atol=1e-6)
+
+
+def test_windowed_pools_and_depthwise_conv_against_naive_loops():
+    """The op-family oracles added for SURVEY §8f row 4 (avg / max pooling windows, depthwise conv) against direct loops, and
+    the TF SAME geometry they share: out = ceil(in / s), pad_before = max((out - 1) s + k_eff - in, 0) // 2."""
+    from oracle import tf_ops as T
+    assert T._same_pad(5, 3, 2) == (3, 1, 1) and T._same_pad(6, 3, 2) == (3, 0, 1) and T._same_pad(7, 5, 1) == (7, 2, 2)
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 7, 9, 3)).astype(np.float32)
+    # average pool 3x2 windows, stride (2, 3), VALID
+    y = T.avg_pool_valid(torch.tensor(x), 3, 2, 2, 3).numpy()
+    assert y.shape == (2, 3, 3, 3)
+    for oy in range(3):
+        for ox in range(3):
+            np.testing.assert_allclose(y[:, oy, ox], x[:, 2 * oy:2 * oy + 3, 3 * ox:3 * ox + 2].mean(axis=(1, 2)), rtol=1e-5, atol=1e-6)
+    # max pool 3x3 / 2 SAME with ties: first maximum in row-major window order, padding never wins
+    xi = rng.integers(0, 3, (1, 5, 6, 2)).astype(np.float32)
+    ym, idx = T.max_pool_general(torch.tensor(xi), 3, 3, 2, "SAME")
+    oh, pt, _ = T._same_pad(5, 3, 2)
+    ow, pl, _ = T._same_pad(6, 3, 2)
+    assert tuple(ym.shape) == (1, oh, ow, 2)
+    dx = T.max_pool_general_grad(torch.ones_like(ym), idx, (5, 6), 3, 3, 2, "SAME").numpy()
+    want = np.zeros_like(xi)
+    for oy in range(oh):
+        for ox in range(ow):
+            for c in range(2):
+                best, bk = None, None
+                for ky in range(3):
+                    for kx in range(3):
+                        iy, ix = oy * 2 - pt + ky, ox * 2 - pl + kx
+                        if 0 <= iy < 5 and 0 <= ix < 6 and (best is None or xi[0, iy, ix, c] > best):
+                            best, bk = xi[0, iy, ix, c], (ky, kx, iy, ix)
+                assert float(ym[0, oy, ox, c]) == best and int(idx[0, oy, ox, c]) == bk[0] * 3 + bk[1]
+                want[0, bk[2], bk[3], c] += 1
+    assert np.array_equal(dx, want)
+    # depthwise 3x3, stride 2, and rate 2
+    w = rng.standard_normal((3, 3, 3)).astype(np.float32)
+    for s, r in ((2, 1), (1, 2)):
+        y = T.depthwise_conv2d_same(torch.tensor(x), torch.tensor(w), s, r).numpy()
+        oh, pt, _ = T._same_pad(7, 2 * r + 1, s)
+        ow, pl, _ = T._same_pad(9, 2 * r + 1, s)
+        ref = np.zeros((2, oh, ow, 3), np.float32)
+        for oy in range(oh):
+            for ox in range(ow):
+                for ky in range(3):
+                    for kx in range(3):
+                        iy, ix = oy * s - pt + ky * r, ox * s - pl + kx * r
+                        if 0 <= iy < 7 and 0 <= ix < 9:
+                            ref[:, oy, ox] += x[:, iy, ix] * w[ky, kx]
+        np.testing.assert_allclose(y, ref, rtol=1e-5, atol=1e-5)
