@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(kThreads) chscale_bwd_kernel(const uint4* __re
 
 int pool_geo(segk_ctx* ctx, const char* what, Geo& g, int N, int H, int W, int C, int kh, int kw, int sh, int sw, int same) {
   SEGK_REQUIRE(ctx, N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "%s: need C %% 8 == 0 (got %dx%dx%dx%d)", what, N, H, W, C);
-  SEGK_REQUIRE(ctx, kh >= 1 && kw >= 1 && sh >= 1 && sw >= 1 && kh * kw <= 255, "%s: bad window %dx%d / stride %dx%d", what, kh, kw, sh, sw);
+  SEGK_REQUIRE(ctx, kh >= 1 && kw >= 1 && sh >= 1 && sw >= 1, "%s: bad window %dx%d / stride %dx%d", what, kh, kw, sh, sw);
   g.N = N; g.H = H; g.W = W; g.C8 = C / 8; g.kh = kh; g.kw = kw; g.sh = sh; g.sw = sw; g.rh = g.rw = 1;
   if (same) {
     g.OH = same_out(H, sh); g.OW = same_out(W, sw);
@@ -442,6 +442,7 @@ int segk_maxpool_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int N,
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, x && y && idx, "maxpool_fwd: null pointer");
   Geo g;
+  SEGK_REQUIRE(ctx, kh * kw <= 256, "maxpool_fwd: the window position is stored in a byte (got %dx%d)", kh, kw);
   const int rc = pool_geo(ctx, "maxpool_fwd", g, N, H, W, C, kh, kw, stride, stride, same);
   if (rc) return rc;
   maxpool_gen_fwd_kernel<<<sgrid(ctx, (int64_t)N * g.OH * g.OW * g.C8), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y,
@@ -455,6 +456,7 @@ int segk_maxpool_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, void* dx
   if (!ctx) return SEGK_EINVAL;
   SEGK_REQUIRE(ctx, dy && idx && dx, "maxpool_bwd: null pointer");
   Geo g;
+  SEGK_REQUIRE(ctx, kh * kw <= 256, "maxpool_bwd: the window position is stored in a byte (got %dx%d)", kh, kw);
   const int rc = pool_geo(ctx, "maxpool_bwd", g, N, H, W, C, kh, kw, stride, stride, same);
   if (rc) return rc;
   maxpool_gen_bwd_kernel<<<sgrid(ctx, (int64_t)N * H * W * g.C8), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint2*)idx,
