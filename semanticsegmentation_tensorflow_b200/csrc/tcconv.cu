@@ -2534,6 +2534,11 @@ static int strided_conv_impl(segk_ctx* ctx, const void* dy, const void* wd, cons
   if (rc) return rc;
   rc = encode_weight_map_blocked(ctx, &maps.b, wd, Cout, Cin, k * k, block_n);
   if (rc) return rc;
+  const bool pair_ok = block_n == 256 && ctx->pair != 0;      // CTA pairs (igemm_pair_kernel): each CTA stages half of the weight tile
+  if (pair_ok) {
+    rc = encode_weight_map_blocked(ctx, &maps.b2, wd, Cout, Cin, k * k, block_n / 2);
+    if (rc) return rc;
+  }
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.H = H; p.W = W;
@@ -2561,11 +2566,12 @@ static int strided_conv_impl(segk_ctx* ctx, const void* dy, const void* wd, cons
     }
     rc = colsum_scratch(ctx, total, block_n, &p.colsum);
     if (rc) return rc;
-    rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+    int grid_used = 0;
+    rc = launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream, 0, pair_ok, &grid_used);
     if (rc) return rc;
-    return colsum_finish(ctx, dx_colsum, (total / p.n_tiles) * p.n_tiles, p.n_tiles, block_n, (cudaStream_t)stream);
+    return colsum_finish(ctx, dx_colsum, grid_used, p.n_tiles, block_n, (cudaStream_t)stream);
   }
-  return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream);
+  return launch_igemm(ctx, block_n, maps, p, taps, (cudaStream_t)stream, 0, pair_ok);
 }
 
 int segk_deconv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,

@@ -658,3 +658,31 @@ def test_cta_pair_igemm_matches_single_cta_bit_for_bit(ops, cuda_device, shape):
     # and against the oracle once more, explicitly in pair mode
     ref = T.relu(T.bias_add(T.conv2d_same(x.float().cpu(), wt.cpu()), b.cpu())).numpy()
     assert_close(host(out[1][0]), ref, TOL_BF16, f"pair conv fwd {shape}")
+
+
+@pytest.mark.parametrize("shape", [(8, 20, 36, 256, 256), (4, 40, 72, 256, 128)])
+def test_cta_pair_strided_conv_matches_single_cta(ops, cuda_device, shape):
+    """The stride-2 implicit GEMM (input gradient of the 4x4 / stride-2 transposed conv; forward of LidCamNet's 4x4 stride-2
+    conv) as CTA pairs: per-tap decimated views of dy as the A operand, same bits as single-CTA tiles, and the oracle."""
+    n, h, w, ci, co = shape          # transposed conv ci -> co, x [n,h,w,ci], dy [n,2h,2w,co]
+    rng = np.random.default_rng(12)
+    wt = bf16_grid(rng.standard_normal((4, 4, co, ci)) / np.sqrt(4 * co))
+    dy = bf16_grid(rng.standard_normal((n, 2 * h, 2 * w, co)))
+    _, wd = ops.pack_deconv_weights(dev_f32(wt, cuda_device), 2)
+    dyd = dev_bf16(dy, cuda_device)
+    out = {}
+    try:
+        for mode in (0, 1):
+            ops.ctx.set_tuning("pair", mode)
+            dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=cuda_device)
+            cs = torch.empty(ci, dtype=torch.float32, device=cuda_device)
+            ops.deconv2d_dgrad(dyd, wd, dx, 4, 2, colsum=cs)
+            torch.cuda.synchronize()
+            out[mode] = (dx, cs)
+    finally:
+        ops.ctx.set_tuning("pair", 1)
+    assert torch.equal(out[0][0], out[1][0])
+    np.testing.assert_allclose(out[0][1].cpu().numpy(), out[1][1].cpu().numpy(), rtol=1e-4, atol=1e-3)
+    # oracle: gradient of conv2d_transpose wrt its input = stride-2 conv of dy with W[k,k,Cout,Cin] read as HWIO [k,k,co,ci]
+    ref = T.conv2d_same(torch.tensor(dy), torch.tensor(wt), stride=2).numpy()
+    assert_close(host(out[1][0]), ref, TOL_BF16, f"pair strided conv {shape}")
