@@ -52,3 +52,18 @@ for name, n, h, w, ci, co, k in SHAPES:
     ops.ctx.set_tuning("pair", 1)
     s = " | ".join("pair=%d fwd %.1f dgrad %.1f" % (m, min(r[0] for r in res[m]), min(r[1] for r in res[m])) for m in (0, 1))
     print(f"{name:28s} {s}", flush=True)
+
+# the stride-2 implicit GEMM (input gradient of the 4x4 / stride-2 transposed convs of U-Net / SegNet)
+for name, n, h, w, ci, co in [("unpool1 dgrad 5x18 512", 32, 5, 18, 512, 512), ("unpool2 dgrad 10x36 512", 32, 10, 36, 512, 512),
+                              ("unpool3 dgrad 20x72 256", 32, 20, 72, 256, 256)]:
+    wt = torch.randn((4, 4, co, ci), device=dev) * 0.02
+    _, wd = ops.pack_deconv_weights(wt, 2)
+    dy = torch.randn((n, 2 * h, 2 * w, co), device=dev).to(torch.bfloat16)
+    dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=dev)
+    res = {}
+    for rep in range(2):
+        for mode in (0, 1):
+            ops.ctx.set_tuning("pair", mode)
+            res.setdefault(mode, []).append(timeit(lambda: ops.deconv2d_dgrad(dy, wd, dx, 4, 2)))
+    ops.ctx.set_tuning("pair", 1)
+    print(f"{name:28s} pair=0 {min(res[0]):.1f} | pair=1 {min(res[1]):.1f}", flush=True)
