@@ -2,6 +2,7 @@
 set -x
 python -m pytest tests -m gpu -x -q > gpurun_out/r2_final_pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/r2_final_pytest.log
 tail -2 gpurun_out/r2_final_pytest.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r2_final_smoke.log 2>&1; tail -1 gpurun_out/r2_final_smoke.log
 bash tools/ncu_round2.sh > gpurun_out/r2_final_ncu.log 2>&1
 python bench.py --layers-out gpurun_out/r2_final_layers.json > gpurun_out/r2_final_bench.json 2> gpurun_out/r2_final_bench.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_final_bench_ref.json 2>/dev/null
