@@ -899,10 +899,43 @@ struct SlabParams {
   int relu;
 };
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kThreads, 1)
-slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
+// One tile of the slab schedule: channel tile nt, output origin (x0, y0) of image n.  PAIR: CTAs 2q / 2q+1 of a cluster take two
+// consecutive pixel tiles of the same channel tile (n == p.N for the partner of an odd last tile: its slab loads zero-fill,
+// nothing is stored).
+struct SlabTile {
+  int nt, x0, y0, n;
+};
+template <bool PAIR>
+__device__ __forceinline__ bool slab_next(const SlabParams& p, int& cursor, SlabTile& t) {
+  const int m_tiles = p.N * p.tiles_h * p.tiles_w;
+  int r;
+  if (PAIR) {
+    const int pairs = (m_tiles + 1) >> 1;
+    if (cursor >= pairs * p.n_tiles) return false;
+    t.nt = cursor % p.n_tiles;
+    r = 2 * (cursor / p.n_tiles) + (int)(blockIdx.x & 1);
+    cursor += (int)(gridDim.x >> 1);
+  } else {
+    if (cursor >= m_tiles * p.n_tiles) return false;
+    t.nt = cursor % p.n_tiles;
+    r = cursor / p.n_tiles;
+    cursor += (int)gridDim.x;
+  }
+  t.x0 = (r % p.tiles_w) * kSlabWV;
+  r /= p.tiles_w;
+  t.y0 = (r % p.tiles_h) * kSlabH;
+  t.n = r / p.tiles_h;
+  return true;
+}
+
+// PAIR: the CTA-pair form of igemm_body (cta_group::2, M = 256): each CTA stages its own slab and HALF of every weight tap
+// (BLOCK_N / 2 rows, TensorMaps::b2); the leader owns the full barriers of both rings, issues the MMAs and multicasts the
+// commits.  With BLOCK_N = 128 the operand reads per SM drop from 128 B/clk -- the shared-memory limit -- to 96.
+template <int BLOCK_N, bool PAIR>
+__device__ __forceinline__ void slab_body(const TensorMaps& maps, const SlabParams& p) {
   using C = SlabCfg<BLOCK_N>;
+  constexpr int kTapHalf = C::kTapBytes / 2;
+  constexpr int kTapStride = PAIR ? kTapHalf : C::kTapBytes;       // bytes between the taps of a weight stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -917,14 +950,16 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
+  uint32_t crank = 0;
+  if constexpr (PAIR) crank = cluster_ctarank();
+  const int cursor0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.a[0]);
-    tma_prefetch_desc(&maps.b);
+    tma_prefetch_desc(PAIR ? &maps.b2 : &maps.b);
     for (int i = 0; i < C::kAStages; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < C::kBStages; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], kEpiThreads); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], PAIR ? 2 * kEpiThreads : kEpiThreads); }
     fence_barrier_init();
   }
   // the two spill rows past each slab are read (for discarded outputs only) but never written by
@@ -932,50 +967,68 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
   for (int i = threadIdx.x; i < C::kAStages * kSlabBytes / 16; i += kThreads)
     reinterpret_cast<uint4*>(smem_a)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
-  if (warp == 1) tmem_alloc<C::kTmemCols>(tmem_slot);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_alloc_pair<C::kTmemCols>(tmem_slot);
+    else tmem_alloc<C::kTmemCols>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     PipeState pa, pb;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles;
-      int r = tile / p.n_tiles;
-      const int x0 = (r % p.tiles_w) * kSlabWV;
-      r /= p.tiles_w;
-      const int y0 = (r % p.tiles_h) * kSlabH;
-      const int n = r / p.tiles_h;
+    int cursor = cursor0;
+    SlabTile t;
+    while (slab_next<PAIR>(p, cursor, t)) {
+      const int nt = t.nt, x0 = t.x0, y0 = t.y0, n = t.n;
       for (int kc = 0; kc < p.kchunks; ++kc) {
         mbar_wait(&emptyA[pa.stage], pa.phase ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&fullA[pa.stage], (uint32_t)kSlabRows * 128u);
-          tma_load_4d(&maps.a[0], &fullA[pa.stage], smem_a + pa.stage * kSlabBytes, kc * kBlockK, x0 - 1, y0 - 1, n);
+          if constexpr (PAIR) {
+            if (crank == 0) mbar_arrive_expect_tx(&fullA[pa.stage], 2u * (uint32_t)kSlabRows * 128u);
+            tma_load_4d_pair(&maps.a[0], mapa_u32(smem_u32(&fullA[pa.stage]), 0), smem_a + pa.stage * kSlabBytes, kc * kBlockK, x0 - 1,
+                             y0 - 1, n);
+          } else {
+            mbar_arrive_expect_tx(&fullA[pa.stage], (uint32_t)kSlabRows * 128u);
+            tma_load_4d(&maps.a[0], &fullA[pa.stage], smem_a + pa.stage * kSlabBytes, kc * kBlockK, x0 - 1, y0 - 1, n);
+          }
         }
         __syncwarp();
         pa.advance<C::kAStages>();
         for (int tg = 0; tg < 9; tg += C::kGroup) {
           mbar_wait(&emptyB[pb.stage], pb.phase ^ 1);
           if (elect_one()) {
-            mbar_arrive_expect_tx(&fullB[pb.stage], (uint32_t)C::kBBytes);
+            if constexpr (PAIR) {
+              const uint32_t lead = mapa_u32(smem_u32(&fullB[pb.stage]), 0);
+              if (crank == 0) mbar_arrive_expect_tx(&fullB[pb.stage], (uint32_t)C::kBBytes);        // both CTAs' halves
 #pragma unroll
-            for (int j = 0; j < C::kGroup; ++j)
-              tma_load_4d(&maps.b, &fullB[pb.stage], smem_b + pb.stage * C::kBBytes + j * C::kTapBytes, 0, nt * BLOCK_N, kc,
-                          tg + j);
+              for (int j = 0; j < C::kGroup; ++j)
+                tma_load_4d_pair(&maps.b2, lead, smem_b + pb.stage * C::kBBytes + j * kTapHalf, 0,
+                                 nt * BLOCK_N + (int)crank * (BLOCK_N / 2), kc, tg + j);
+            } else {
+              mbar_arrive_expect_tx(&fullB[pb.stage], (uint32_t)C::kBBytes);
+#pragma unroll
+              for (int j = 0; j < C::kGroup; ++j)
+                tma_load_4d(&maps.b, &fullB[pb.stage], smem_b + pb.stage * C::kBBytes + j * C::kTapBytes, 0, nt * BLOCK_N, kc,
+                            tg + j);
+            }
           }
           __syncwarp();
           pb.advance<C::kBStages>();
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && crank == 0) {
     PipeState pa, pb;
     int acc = 0;
     uint32_t acc_phase = 0;
-    constexpr uint32_t idesc = make_idesc(kBlockM, BLOCK_N, 0, 0);
+    constexpr uint32_t idesc = make_idesc(PAIR ? 2 * kBlockM : kBlockM, BLOCK_N, 0, 0);
     const uint32_t a_lo0 = smem_u32(smem_a) >> 4, b_lo0 = smem_u32(smem_b) >> 4;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int cursor = cursor0;
+    SlabTile t;
+    while (slab_next<PAIR>(p, cursor, t)) {
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -994,15 +1047,25 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
               // tap (ty,tx) = slab row offset ty*32 + tx; one row = 128 B = 8 descriptor units
               const uint32_t a_lo = slab_lo + (uint32_t)((tap / 3) * kSlabP + (tap % 3)) * 8u;
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                umma_f16(d_addr, kDescKMajor | (uint64_t)(a_lo + 2 * k),
-                         kDescKMajor | (uint64_t)(b_lo + j * (C::kTapBytes >> 4) + 2 * k), idesc,
-                         (kc | tap | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                const uint64_t da = kDescKMajor | (uint64_t)(a_lo + 2 * k);
+                const uint64_t db = kDescKMajor | (uint64_t)(b_lo + j * (kTapStride >> 4) + 2 * k);
+                if constexpr (PAIR) umma_f16_pair(d_addr, da, db, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                else umma_f16(d_addr, da, db, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              }
             }
-            umma_commit(&emptyB[pb.stage]);
-            if (tg + C::kGroup >= 9) {
-              umma_commit(&emptyA[pa.stage]);
-              if (kc == p.kchunks - 1) umma_commit(&tfull_bar[acc]);
+            if constexpr (PAIR) {
+              umma_commit_pair(&emptyB[pb.stage]);
+              if (tg + C::kGroup >= 9) {
+                umma_commit_pair(&emptyA[pa.stage]);
+                if (kc == p.kchunks - 1) umma_commit_pair(&tfull_bar[acc]);
+              }
+            } else {
+              umma_commit(&emptyB[pb.stage]);
+              if (tg + C::kGroup >= 9) {
+                umma_commit(&emptyA[pa.stage]);
+                if (kc == p.kchunks - 1) umma_commit(&tfull_bar[acc]);
+              }
             }
           }
           __syncwarp();
@@ -1013,7 +1076,7 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
-  } else {
+  } else if (warp >= 2) {
     const int q = warp & 3;       // TMEM lane quarter == image row of the tile
     const int half = (warp - 2) >> 2;   // which 32 columns of each 64-column group
     int acc = 0;
@@ -1022,15 +1085,12 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
     const int srow = q * kSlabWV + lane;            // staging row: box (64 ch, 30 w, 4 h) is packed at pitch 30
     uint32_t sg = 0;
     float ca0 = 0.f, ca1 = 0.f, ca2 = 0.f, ca3 = 0.f;      // column sums of this thread's columns (p.colsum)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int nt = tile % p.n_tiles;
-      int r = tile / p.n_tiles;
-      const int x0 = (r % p.tiles_w) * kSlabWV;
-      r /= p.tiles_w;
-      const int y0 = (r % p.tiles_h) * kSlabH;
-      const int n = r / p.tiles_h;
+    int cursor = cursor0;
+    SlabTile t;
+    while (slab_next<PAIR>(p, cursor, t)) {
+      const int nt = t.nt, x0 = t.x0, y0 = t.y0, n = t.n;
       const int ox = x0 + lane, oy = y0 + q;
-      const bool valid = lane < kSlabWV && ox < p.W && oy < p.H;
+      const bool valid = lane < kSlabWV && ox < p.W && oy < p.H && n < p.N;
       const int64_t obase = (((int64_t)n * p.H + oy) * p.W + ox) * p.ldo + (int64_t)nt * BLOCK_N;
       EpiPre pre;
       if (valid) epilogue_prefetch(p, obase + half * 32, pre);
@@ -1069,7 +1129,7 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
         if (p.tma_store) {
           fence_proxy_async();
           named_bar_sync(1, kEpiThreads);
-          if (ep_leader && !p.pool_only) {
+          if (ep_leader && !p.pool_only && n < p.N) {
             tma_store_4d(&maps.c, sbuf, nt * BLOCK_N + g0, x0, y0, n);
             tma_store_commit();
           }
@@ -1081,15 +1141,18 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[acc]);
+      if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));
+      else mbar_arrive(&tempty_bar[acc]);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
     if (p.tma_store && ep_leader) tma_store_wait_read<0>();
     if (p.colsum) {
-      const int nt = blockIdx.x % p.n_tiles;
+      const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+      const int nt = unit0 % p.n_tiles;
+      const int slot = PAIR ? (unit0 / p.n_tiles) * 2 + (int)(blockIdx.x & 1) : unit0 / p.n_tiles;
       const int rows_per_nt = (gridDim.x / p.n_tiles) * 4;
-      float* dst = p.colsum + ((int64_t)nt * rows_per_nt + (blockIdx.x / p.n_tiles) * 4 + q) * BLOCK_N + half * 32 + lane;
+      float* dst = p.colsum + ((int64_t)nt * rows_per_nt + slot * 4 + q) * BLOCK_N + half * 32 + lane;
       dst[0] = ca0;
       if (BLOCK_N > 64) dst[64] = ca1;
       if (BLOCK_N > 128) { dst[128] = ca2; dst[192] = ca3; }
@@ -1097,9 +1160,25 @@ slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
   }
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
-  if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
+  if (warp == 1) {
+    if constexpr (PAIR) tmem_dealloc_pair<C::kTmemCols>(tmem_base);
+    else tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+slab_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
+  slab_body<BLOCK_N, false>(maps, p);
+}
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+slab_pair_kernel(const __grid_constant__ TensorMaps maps, const SlabParams p) {
+  slab_body<BLOCK_N, true>(maps, p);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -2061,6 +2140,13 @@ int launch_slab_t(segk_ctx* ctx, const TensorMaps& maps, const SlabParams& p, in
   return SEGK_OK;
 }
 
+// CTA pairs for the 128-column slab tiles (slab_pair_kernel<128>; maps.b2 = weights with a 64-row box): grid of `pairs` clusters
+int launch_slab_pair128(segk_ctx* ctx, const TensorMaps& maps, const SlabParams& p, int pairs, cudaStream_t st) {
+  slab_pair_kernel<128><<<2 * pairs, kThreads, SlabCfg<128>::kSmemBytes, st>>>(maps, p);
+  SEGK_LAUNCHED(ctx, "slab (CTA pairs)");
+  return SEGK_OK;
+}
+
 // 3x3 layers on large maps whose GEMM-N is small are activation-traffic bound in the tap-wise igemm
 bool slab_applicable(const segk_ctx* ctx, int N, int H, int W, int Ck, int Cn, int kh, int kw) {
   const int mode = ctx->slab_mode;   // 0 off, 1 auto, 2 whenever legal
@@ -2121,6 +2207,14 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
     rc = encode_weight_map_blocked(ctx, &maps.b, wt, Ck, Cn, 9, block_n);
     if (rc) return rc;
   }
+  // 128-column tiles as CTA pairs: a 128 x 128 x 16 MMA reads 8 KB of operands per 64 tensor cycles = the 128 B/clk a SM's
+  // shared memory delivers; a pair's M = 256 MMA halves the weight part of it (96 B/clk)
+  const int m_tiles_all = N * (H / kSlabH) * ceil_div(W, kSlabWV);
+  const bool pair = !fused3 && block_n == 128 && ctx->pair != 0 && m_tiles_all >= 16;
+  if (pair) {
+    rc = encode_weight_map_blocked(ctx, &maps.b2, wt, Ck, Cn, 9, block_n / 2);
+    if (rc) return rc;
+  }
   SlabParams p;
   memset(&p, 0, sizeof(p));
   p.N = N; p.H = H; p.W = W;
@@ -2157,6 +2251,16 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
     }
     rc = colsum_scratch(ctx, grid, block_n, &p.colsum);
     if (rc) return rc;
+    if (pair) {
+      const int units = ((m_tiles_all + 1) / 2) * p.n_tiles;
+      int gp = units < ctx->sm_count / 2 ? units : ctx->sm_count / 2;
+      gp = (gp / p.n_tiles) * p.n_tiles;
+      if (gp > 0) {
+        rc = launch_slab_pair128(ctx, maps, p, gp, (cudaStream_t)stream);
+        if (rc) return rc;
+        return colsum_finish(ctx, colsum_out, 2 * gp, p.n_tiles, block_n, (cudaStream_t)stream);
+      }
+    }
     grid = (grid / p.n_tiles) * p.n_tiles;
     switch (block_n) {
       case 256: rc = launch_slab_t<256>(ctx, maps, p, grid, (cudaStream_t)stream); break;
@@ -2173,6 +2277,10 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
     else slab3_kernel<2><<<g3, kThreads, Slab3Cfg<2>::kSmem, (cudaStream_t)stream>>>(maps, p);
     SEGK_LAUNCHED(ctx, "slab3");
     return SEGK_OK;
+  }
+  if (pair) {
+    const int units = ((m_tiles_all + 1) / 2) * p.n_tiles;
+    return launch_slab_pair128(ctx, maps, p, units < ctx->sm_count / 2 ? units : ctx->sm_count / 2, (cudaStream_t)stream);
   }
   switch (block_n) {
     case 256: return launch_slab_t<256>(ctx, maps, p, grid, (cudaStream_t)stream);
@@ -3051,6 +3159,7 @@ int segk_tc_init(segk_ctx* ctx) {
   SEGK_SMEM_ATTR(slab_kernel<64>, SlabCfg<64>::kSmemBytes);
   SEGK_SMEM_ATTR(slab_kernel<128>, SlabCfg<128>::kSmemBytes);
   SEGK_SMEM_ATTR(slab_kernel<256>, SlabCfg<256>::kSmemBytes);
+  SEGK_SMEM_ATTR(slab_pair_kernel<128>, SlabCfg<128>::kSmemBytes);
   SEGK_SMEM_ATTR(slab3_kernel<1>, Slab3Cfg<1>::kSmem);
   SEGK_SMEM_ATTR(slab3_kernel<2>, Slab3Cfg<2>::kSmem);
 #undef SEGK_SMEM_ATTR

@@ -608,6 +608,8 @@ PAIR_SHAPES = [
     (5, 24, 40, 256, 256, 1),          # 1x1
     (32, 10, 36, 512, 512, 3),         # conv5_x at B=32: 90 pixel tiles, 45 pairs per channel tile
     (32, 20, 72, 512, 256, 3),         # one 256-column channel tile, 360 pixel tiles
+    (2, 64, 96, 128, 128, 3),          # haloed-slab kernel, 128-column tiles as pairs (slab_pair_kernel<128>): 128 tiles
+    (1, 60, 90, 64, 128, 3),           # slab pairs, 45 tiles (odd: one partner outside the batch); dgrad is the kx-fused slab3
 ]
 
 
