@@ -26,7 +26,8 @@ struct segk_ctx {
   int tail_wide = 1;        // SEGK_TAIL_WIDE: 16-byte-access forms of the few-pixel / wide-channel tail layers (conv8, conv_t1)
   int teamk = 1;            // SEGK_TEAMK: lockstep tap-split schedule instead of plain split-K for few-tile / long-K layers
                             //   (conv6 dgrad; IgemmParams::ts in tcconv.cu).  0 = plain split-K
-  int pair = 1;             // SEGK_PAIR: 256-column igemm launches as CTA pairs (cta_group::2, M = 256 MMAs; igemm_pair_kernel)
+  int pair = 1;             // SEGK_PAIR: 256-column igemm launches as CTA pairs (cta_group::2, M = 256 MMAs; igemm_pair_kernel);
+                            //   2 = also the 128-column haloed-slab tiles (slab_pair_kernel<128>; measured no faster, off by default)
   int hybrid = 0;           // SEGK_HYBRID: whole waves + K-split remainder tiles when the last wave of an igemm launch is partly
                             //   filled.  Off by default: measured on conv5_x (B=32, 180 tiles on 148 SMs) 58 us vs 51 us for two
                             //   plain waves -- the two epilogues after the last MMA and the finish kernel (launch + 10 us) cost

@@ -2207,10 +2207,13 @@ int conv_slab(segk_ctx* ctx, const char* what, const void* x, const void* wt, co
     rc = encode_weight_map_blocked(ctx, &maps.b, wt, Ck, Cn, 9, block_n);
     if (rc) return rc;
   }
-  // 128-column tiles as CTA pairs: a 128 x 128 x 16 MMA reads 8 KB of operands per 64 tensor cycles = the 128 B/clk a SM's
-  // shared memory delivers; a pair's M = 256 MMA halves the weight part of it (96 B/clk)
+  // 128-column tiles as CTA pairs (slab_pair_kernel<128>): a 128 x 128 x 16 MMA reads 8 KB of operands per 64 tensor cycles =
+  // the 128 B/clk a SM's shared memory delivers, a pair's M = 256 MMA halves the weight part of it (96 B/clk).  Measured
+  // (profiles/r2_pair_ab.md) it does not pay: conv2_2 forward 199.7 -> 195.6 us, its dgrad 197.6 -> 203.8, conv2_1 forward
+  // (one k-chunk per tile: nine MMA groups between two cross-CTA barrier round trips) 130.0 -> 162.7.  Kept behind
+  // segk_set_tuning("pair", 2) with its parity test; off by default.
   const int m_tiles_all = N * (H / kSlabH) * ceil_div(W, kSlabWV);
-  const bool pair = !fused3 && block_n == 128 && ctx->pair != 0 && m_tiles_all >= 16;
+  const bool pair = !fused3 && block_n == 128 && ctx->pair >= 2 && m_tiles_all >= 16;
   if (pair) {
     rc = encode_weight_map_blocked(ctx, &maps.b2, wt, Ck, Cn, 9, block_n / 2);
     if (rc) return rc;

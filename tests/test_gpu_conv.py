@@ -608,7 +608,7 @@ PAIR_SHAPES = [
     (5, 24, 40, 256, 256, 1),          # 1x1
     (32, 10, 36, 512, 512, 3),         # conv5_x at B=32: 90 pixel tiles, 45 pairs per channel tile
     (32, 20, 72, 512, 256, 3),         # one 256-column channel tile, 360 pixel tiles
-    (2, 64, 96, 128, 128, 3),          # haloed-slab kernel, 128-column tiles as pairs (slab_pair_kernel<128>): 128 tiles
+    (2, 64, 96, 128, 128, 3),          # haloed-slab kernel, 128-column tiles as pairs (slab_pair_kernel<128>, tuning pair = 2): 128 tiles
     (1, 60, 90, 64, 128, 3),           # slab pairs, 45 tiles (odd: one partner outside the batch); dgrad is the kx-fused slab3
 ]
 
@@ -629,7 +629,7 @@ def test_cta_pair_igemm_matches_single_cta_bit_for_bit(ops, cuda_device, shape):
     wk, wd = ops.pack_conv_weights(wt)
     out = {}
     try:
-        for mode in (0, 1):
+        for mode in (0, 2):          # 2: igemm pairs (the default, 1) plus the slab kernel's pair form
             ops.ctx.set_tuning("pair", mode)
             l0 = ops.ctx.launches
             y = torch.empty((n, h, w, co), dtype=torch.bfloat16, device=cuda_device)
@@ -652,14 +652,14 @@ def test_cta_pair_igemm_matches_single_cta_bit_for_bit(ops, cuda_device, shape):
     finally:
         ops.ctx.set_tuning("pair", 1)
     names = ("fwd", "relu bits", "fwd (pool call)", "pooled", "pool idx", "dgrad", "dgrad column sums", "dgrad (bf16 mask)")
-    for a, c, name in zip(out[0], out[1], names):
+    for a, c, name in zip(out[0], out[2], names):
         if name == "dgrad column sums":      # per-CTA partial rows: the grid (hence the fixed summation order) differs between the modes
             np.testing.assert_allclose(a.cpu().numpy(), c.cpu().numpy(), rtol=1e-4, atol=1e-3)
         else:
             assert torch.equal(a, c), f"{name} {shape}: pair vs single-CTA"
     # and against the oracle once more, explicitly in pair mode
     ref = T.relu(T.bias_add(T.conv2d_same(x.float().cpu(), wt.cpu()), b.cpu())).numpy()
-    assert_close(host(out[1][0]), ref, TOL_BF16, f"pair conv fwd {shape}")
+    assert_close(host(out[2][0]), ref, TOL_BF16, f"pair conv fwd {shape}")
 
 
 @pytest.mark.parametrize("shape", [(8, 20, 36, 256, 256), (4, 40, 72, 256, 128)])

@@ -8,6 +8,9 @@ from semanticsegmentation_tensorflow_b200.ops import Ops
 dev = torch.device("cuda", 0)
 ops = Ops(dev)
 SHAPES = [  # name, N, H, W, Cin, Cout, k
+    ("conv2_1 80x288 64->128 (slab)", 32, 80, 288, 64, 128, 3),
+    ("conv2_2 80x288 128->128 (slab)", 32, 80, 288, 128, 128, 3),
+    ("conv3_1 40x144 128->256", 32, 40, 144, 128, 256, 3),
     ("conv3_2 40x144 256->256", 32, 40, 144, 256, 256, 3),
     ("conv4_1 20x72 256->512", 32, 20, 72, 256, 512, 3),
     ("conv4_2 20x72 512->512", 32, 20, 72, 512, 512, 3),
