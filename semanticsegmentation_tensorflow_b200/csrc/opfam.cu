@@ -417,7 +417,7 @@ extern "C" {
 
 int segk_avgpool_fwd(segk_ctx* ctx, const void* x, void* y, int N, int H, int W, int C, int kh, int kw, int sh, int sw, void* stream) {
   if (!ctx) return SEGK_EINVAL;
-  SEGK_REQUIRE(ctx, x && y, "avgpool_fwd: null pointer");
+  SEGK_REQUIRE(ctx, x && y && (((uintptr_t)x | (uintptr_t)y) & 15) == 0, "avgpool_fwd: null or unaligned (16 B) pointer");
   Geo g;
   const int rc = pool_geo(ctx, "avgpool_fwd", g, N, H, W, C, kh, kw, sh, sw, 0);
   if (rc) return rc;
@@ -428,7 +428,7 @@ int segk_avgpool_fwd(segk_ctx* ctx, const void* x, void* y, int N, int H, int W,
 
 int segk_avgpool_bwd(segk_ctx* ctx, const void* dy, void* dx, int N, int H, int W, int C, int kh, int kw, int sh, int sw, void* stream) {
   if (!ctx) return SEGK_EINVAL;
-  SEGK_REQUIRE(ctx, dy && dx, "avgpool_bwd: null pointer");
+  SEGK_REQUIRE(ctx, dy && dx && (((uintptr_t)dy | (uintptr_t)dx) & 15) == 0, "avgpool_bwd: null or unaligned (16 B) pointer");
   Geo g;
   const int rc = pool_geo(ctx, "avgpool_bwd", g, N, H, W, C, kh, kw, sh, sw, 0);
   if (rc) return rc;
@@ -440,7 +440,7 @@ int segk_avgpool_bwd(segk_ctx* ctx, const void* dy, void* dx, int N, int H, int 
 int segk_maxpool_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int N, int H, int W, int C, int kh, int kw, int stride,
                      int same, void* stream) {
   if (!ctx) return SEGK_EINVAL;
-  SEGK_REQUIRE(ctx, x && y && idx, "maxpool_fwd: null pointer");
+  SEGK_REQUIRE(ctx, x && y && idx && (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && (((uintptr_t)idx) & 7) == 0, "maxpool_fwd: null or unaligned pointer");
   Geo g;
   SEGK_REQUIRE(ctx, kh * kw <= 256, "maxpool_fwd: the window position is stored in a byte (got %dx%d)", kh, kw);
   const int rc = pool_geo(ctx, "maxpool_fwd", g, N, H, W, C, kh, kw, stride, stride, same);
@@ -454,7 +454,7 @@ int segk_maxpool_fwd(segk_ctx* ctx, const void* x, void* y, uint8_t* idx, int N,
 int segk_maxpool_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, void* dx, int N, int H, int W, int C, int kh, int kw, int stride,
                      int same, void* stream) {
   if (!ctx) return SEGK_EINVAL;
-  SEGK_REQUIRE(ctx, dy && idx && dx, "maxpool_bwd: null pointer");
+  SEGK_REQUIRE(ctx, dy && idx && dx && (((uintptr_t)dy | (uintptr_t)dx) & 15) == 0 && (((uintptr_t)idx) & 7) == 0, "maxpool_bwd: null or unaligned pointer");
   Geo g;
   SEGK_REQUIRE(ctx, kh * kw <= 256, "maxpool_bwd: the window position is stored in a byte (got %dx%d)", kh, kw);
   const int rc = pool_geo(ctx, "maxpool_bwd", g, N, H, W, C, kh, kw, stride, stride, same);
@@ -468,7 +468,8 @@ int segk_maxpool_bwd(segk_ctx* ctx, const void* dy, const uint8_t* idx, void* dx
 int segk_depthwise_conv2d_fwd(segk_ctx* ctx, const void* x, const float* w, const float* bias, void* y, int N, int H, int W, int C,
                               int kh, int kw, int stride, int rate, unsigned flags, void* stream) {
   if (!ctx) return SEGK_EINVAL;
-  SEGK_REQUIRE(ctx, x && w && y && !(flags & SEGK_EPI_OUT_F32) && (((uintptr_t)w | (uintptr_t)bias) & 15) == 0, "depthwise_conv2d_fwd: bad args");
+  SEGK_REQUIRE(ctx, x && w && y && !(flags & SEGK_EPI_OUT_F32) && (((uintptr_t)w | (uintptr_t)bias | (uintptr_t)x | (uintptr_t)y) & 15) == 0,
+               "depthwise_conv2d_fwd: null / unaligned (16 B) pointer, or fp32 output requested (bf16 only)");
   Geo g;
   const int rc = dw_geo(ctx, "depthwise_conv2d_fwd", g, N, H, W, C, kh, kw, stride, rate);
   if (rc) return rc;
@@ -481,7 +482,7 @@ int segk_depthwise_conv2d_fwd(segk_ctx* ctx, const void* x, const float* w, cons
 int segk_depthwise_conv2d_dgrad(segk_ctx* ctx, const void* dy, const float* w, void* dx, int N, int H, int W, int C, int kh, int kw,
                                 int stride, int rate, void* stream) {
   if (!ctx) return SEGK_EINVAL;
-  SEGK_REQUIRE(ctx, dy && w && dx && (((uintptr_t)w) & 15) == 0, "depthwise_conv2d_dgrad: bad args");
+  SEGK_REQUIRE(ctx, dy && w && dx && (((uintptr_t)w | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0, "depthwise_conv2d_dgrad: null or unaligned (16 B) pointer");
   Geo g;
   const int rc = dw_geo(ctx, "depthwise_conv2d_dgrad", g, N, H, W, C, kh, kw, stride, rate);
   if (rc) return rc;
@@ -493,7 +494,7 @@ int segk_depthwise_conv2d_dgrad(segk_ctx* ctx, const void* dy, const float* w, v
 int segk_depthwise_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, float* dw, int N, int H, int W, int C, int kh, int kw,
                                 int stride, int rate, int accumulate, void* stream) {
   if (!ctx) return SEGK_EINVAL;
-  SEGK_REQUIRE(ctx, x && dy && dw && (((uintptr_t)dw) & 15) == 0, "depthwise_conv2d_wgrad: bad args");
+  SEGK_REQUIRE(ctx, x && dy && dw && (((uintptr_t)dw | (uintptr_t)x | (uintptr_t)dy) & 15) == 0, "depthwise_conv2d_wgrad: null or unaligned (16 B) pointer");
   Geo g;
   int rc = dw_geo(ctx, "depthwise_conv2d_wgrad", g, N, H, W, C, kh, kw, stride, rate);
   if (rc) return rc;
@@ -519,7 +520,8 @@ int segk_depthwise_conv2d_wgrad(segk_ctx* ctx, const void* x, const void* dy, fl
 
 int segk_activation_fwd(segk_ctx* ctx, const void* x, void* y, int64_t n, int kind, void* stream) {
   if (!ctx) return SEGK_EINVAL;
-  SEGK_REQUIRE(ctx, x && y && n > 0 && n % 8 == 0 && (kind == 0 || kind == 1), "activation_fwd: n %% 8 == 0, kind 0 (sigmoid) or 1 (swish)");
+  SEGK_REQUIRE(ctx, x && y && n > 0 && n % 8 == 0 && (kind == 0 || kind == 1) && (((uintptr_t)x | (uintptr_t)y) & 15) == 0,
+               "activation_fwd: 16-byte aligned tensors, n %% 8 == 0, kind 0 (sigmoid) or 1 (swish)");
   act_fwd_kernel<<<sgrid(ctx, n / 8), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, n / 8, kind);
   SEGK_LAUNCHED(ctx, "activation_fwd");
   return SEGK_OK;
@@ -527,7 +529,8 @@ int segk_activation_fwd(segk_ctx* ctx, const void* x, void* y, int64_t n, int ki
 
 int segk_activation_bwd(segk_ctx* ctx, const void* x, const void* dy, void* dx, int64_t n, int kind, void* stream) {
   if (!ctx) return SEGK_EINVAL;
-  SEGK_REQUIRE(ctx, x && dy && dx && n > 0 && n % 8 == 0 && (kind == 0 || kind == 1), "activation_bwd: n %% 8 == 0, kind 0 (sigmoid) or 1 (swish)");
+  SEGK_REQUIRE(ctx, x && dy && dx && n > 0 && n % 8 == 0 && (kind == 0 || kind == 1) && (((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0,
+               "activation_bwd: 16-byte aligned tensors, n %% 8 == 0, kind 0 (sigmoid) or 1 (swish)");
   act_bwd_kernel<<<sgrid(ctx, n / 8), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)dy, (uint4*)dx, n / 8, kind);
   SEGK_LAUNCHED(ctx, "activation_bwd");
   return SEGK_OK;
@@ -535,7 +538,8 @@ int segk_activation_bwd(segk_ctx* ctx, const void* x, const void* dy, void* dx, 
 
 int segk_channel_scale_fwd(segk_ctx* ctx, const void* x, const void* s, void* y, int N, int64_t HW, int C, void* stream) {
   if (!ctx) return SEGK_EINVAL;
-  SEGK_REQUIRE(ctx, x && s && y && N > 0 && HW > 0 && C > 0 && C % 8 == 0, "channel_scale_fwd: need C %% 8 == 0");
+  SEGK_REQUIRE(ctx, x && s && y && N > 0 && HW > 0 && C > 0 && C % 8 == 0 && (((uintptr_t)x | (uintptr_t)s | (uintptr_t)y) & 15) == 0,
+               "channel_scale_fwd: need C %% 8 == 0 and 16-byte aligned tensors");
   const int64_t total = (int64_t)N * HW * (C / 8);
   chscale_fwd_kernel<<<sgrid(ctx, total), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)s, (uint4*)y, total, HW, C / 8);
   SEGK_LAUNCHED(ctx, "channel_scale_fwd");
@@ -545,8 +549,9 @@ int segk_channel_scale_fwd(segk_ctx* ctx, const void* x, const void* s, void* y,
 int segk_channel_scale_bwd(segk_ctx* ctx, const void* x, const void* s, const void* dy, void* dx, float* ds, int N, int64_t HW, int C,
                            void* stream) {
   if (!ctx) return SEGK_EINVAL;
-  SEGK_REQUIRE(ctx, x && s && dy && dx && ds && N > 0 && HW > 0 && C > 0 && C % 8 == 0 && (((uintptr_t)ds) & 15) == 0,
-               "channel_scale_bwd: need C %% 8 == 0");
+  SEGK_REQUIRE(ctx, x && s && dy && dx && ds && N > 0 && HW > 0 && C > 0 && C % 8 == 0 &&
+                        (((uintptr_t)ds | (uintptr_t)x | (uintptr_t)s | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0,
+               "channel_scale_bwd: need C %% 8 == 0 and 16-byte aligned tensors");
   const int C8 = C / 8, groups = C8 < kThreads ? C8 : kThreads;
   chscale_bwd_kernel<<<dim3(ceil_div(C8, groups), N), kThreads, 0, (cudaStream_t)stream>>>((const uint4*)x, (const uint4*)s, (const uint4*)dy,
                                                                                             (uint4*)dx, ds, HW, C8);

@@ -263,3 +263,24 @@ def test_sigmoid_swish_and_squeeze_excite_multiply(ops, cuda_device):
     assert_close(host(y), ref.detach().numpy(), 1e-2, "channel scale")
     assert_close(host(dx), xr.grad.numpy(), 1e-2, "channel scale dx")
     assert_close(host(ds), sr.grad.numpy(), 2e-3, "channel scale ds")
+
+
+def test_op_family_argument_errors(ops, cuda_device):
+    """Unsupported shapes are errors with a message, never a silent fallback."""
+    from semanticsegmentation_tensorflow_b200._lib import SegkError
+    x = torch.zeros((1, 8, 8, 16), dtype=torch.bfloat16, device=cuda_device)
+    y = torch.zeros_like(x)
+    w = torch.zeros((3, 3, 16), dtype=torch.float32, device=cuda_device)
+    with pytest.raises(SegkError, match="rate > 1 needs stride 1"):
+        ops.depthwise_conv2d_fwd(x, w, None, y[:, :4, :4], stride=2, rate=2)
+    with pytest.raises(SegkError, match="C %% 8|C % 8"):
+        ops.avgpool_window_fwd(x[..., :12].contiguous(), y[..., :12].contiguous(), 2, 2, 2, 2)
+    with pytest.raises(SegkError, match="larger than"):
+        ops.avgpool_window_fwd(x, y, 9, 9, 1, 1)
+    with pytest.raises(SegkError, match="byte"):
+        ops.maxpool_general_fwd(torch.zeros((1, 20, 20, 8), dtype=torch.bfloat16, device=cuda_device),
+                                torch.zeros((1, 1, 1, 8), dtype=torch.bfloat16, device=cuda_device),
+                                torch.zeros((1, 1, 1, 8), dtype=torch.uint8, device=cuda_device), 17, 17, 1)
+    with pytest.raises(KeyError):
+        ops.activation_fwd(x, y, "gelu")
+    torch.cuda.synchronize()
