@@ -1631,6 +1631,183 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ Wg
   if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
+// wgrad_pair_kernel: the 256-column weight-gradient GEMM as CTA pairs (cta_group::2, M = 256).  CTAs 2q / 2q+1 of a cluster take
+// two CONSECUTIVE row-block pairs (different taps / input-channel chunks: 2 x 128 dW rows) of the same channel tile and pixel
+// split; both need the same dy boxes as their B operand, so each CTA stages its own two 8 KB x boxes and HALF of the dy box
+// (128 of the 256 columns): a stage is 32 KB instead of 48 (six stages), and per SM the operand reads from shared memory
+// fall from 96 to 64 B/clk.  Barrier protocol as in igemm_body<.., PAIR>.  Launched only when every pixel box contributes
+// to every item (!skip_oob: the large-map layers) and n_rbp is even; each CTA's epilogue stores its own 128 rows.
+constexpr int kWPairStageBytes = kABytes + 2 * 8192;                 // A (2 x 8 KB) + half of B (2 x 8 KB)
+constexpr int kWPairStages = kSmemBudget / kWPairStageBytes;         // 6
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgradThreads, 1)
+wgrad_pair_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ WgradParams p, const TapTable taps) {
+  constexpr int BLOCK_N = 256;
+  using C = WCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kWPairStages * kWPairStageBytes);
+  uint64_t* empty_bar = full_bar + kWPairStages;
+  uint64_t* tfull_bar = empty_bar + kWPairStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const int n_ptiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int half_rbp = p.n_rbp >> 1;
+  const int total_units = p.splits * half_rbp * p.n_tiles;
+  const int per_split = (n_ptiles + p.splits - 1) / p.splits;
+  const int ustride = (int)(gridDim.x >> 1);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&maps.a[i]);
+    tma_prefetch_desc(&maps.b);
+    for (int i = 0; i < kWPairStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 2 * (kWgradThreads - 64));
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair<C::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    PipeState ps;
+    for (int u = (int)(blockIdx.x >> 1); u < total_units; u += ustride) {
+      const int nt = u % p.n_tiles;
+      const int rbp = 2 * ((u / p.n_tiles) % half_rbp) + (int)crank;
+      const int split = u / (p.n_tiles * half_rbp);
+      const int rb0 = 2 * rbp, rb1 = (2 * rbp + 1 < p.n_rb) ? 2 * rbp + 1 : 2 * rbp;
+      const int tap0 = rb0 / p.kchunks_in, c0 = (rb0 % p.kchunks_in) * 64;
+      const int tap1 = rb1 / p.kchunks_in, c1 = (rb1 % p.kchunks_in) * 64;
+      const int dy0 = taps.dy[tap0], dx0 = taps.dx[tap0], dy1 = taps.dy[tap1], dx1 = taps.dx[tap1];
+      const int m0 = taps.map[tap0], m1 = taps.map[tap1];
+      const int pt0 = split * per_split;
+      const int pt1 = min(pt0 + per_split, n_ptiles);
+      int x0 = (pt0 % p.tiles_w) * p.bw;
+      int y0 = ((pt0 / p.tiles_w) % p.tiles_h) * p.bh;
+      int n0 = (pt0 / (p.tiles_w * p.tiles_h)) * p.bn;
+      for (int pt = pt0; pt < pt1; ++pt) {
+        mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + ps.stage * kWPairStageBytes;
+          const uint32_t lead = mapa_u32(smem_u32(&full_bar[ps.stage]), 0);
+          if (crank == 0) mbar_arrive_expect_tx(&full_bar[ps.stage], 2u * (uint32_t)kWPairStageBytes);
+          tma_load_4d_pair(&maps.a[m0], lead, sa, c0, x0 + dx0, y0 + dy0, n0);
+          tma_load_4d_pair(&maps.a[m1], lead, sa + 8192, c1, x0 + dx1, y0 + dy1, n0);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_4d_pair(&maps.b, lead, sa + kABytes + j * 8192, nt * BLOCK_N + (int)crank * 128 + j * 64, x0, y0, n0);
+        }
+        __syncwarp();
+        ps.advance<kWPairStages>();
+        x0 += p.bw;
+        if (x0 >= p.tiles_w * p.bw) {
+          x0 = 0;
+          y0 += p.bh;
+          if (y0 >= p.tiles_h * p.bh) { y0 = 0; n0 += p.bn; }
+        }
+      }
+    }
+  } else if (warp == 1 && crank == 0) {
+    PipeState ps;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    constexpr uint32_t idesc = make_idesc(2 * kBlockM, BLOCK_N, 1, 1);
+    const uint32_t smem_lo = smem_u32(smem) >> 4;
+    for (int u = (int)(blockIdx.x >> 1); u < total_units; u += ustride) {
+      const int split = u / (p.n_tiles * half_rbp);
+      const int pt0 = split * per_split;
+      const int pt1 = min(pt0 + per_split, n_ptiles);
+      if (pt1 - pt0 <= 0) continue;
+      const int nboxes = pt1 - pt0;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int b0 = 0; b0 < nboxes; ++b0) {
+        mbar_wait(&full_bar[ps.stage], ps.phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_lo = smem_lo + (uint32_t)(ps.stage * kWPairStageBytes) / 16u;
+          const uint32_t b_lo = a_lo + (uint32_t)(kABytes >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 16 pixels (2048 B = 128 units) per MMA
+            umma_f16_pair(d_addr, kDescMNMajor | (uint64_t)(a_lo + 128 * k), kDescMNMajor | (uint64_t)(b_lo + 128 * k), idesc,
+                          (b0 | k) != 0 ? 1u : 0u);
+          umma_commit_pair(&empty_bar[ps.stage]);
+          if (b0 + 1 >= nboxes) umma_commit_pair(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        ps.advance<kWPairStages>();
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else if (warp >= 2) {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t lead_tempty0 = mapa_u32(smem_u32(&tempty_bar[0]), 0), lead_tempty1 = mapa_u32(smem_u32(&tempty_bar[1]), 0);
+    for (int u = (int)(blockIdx.x >> 1); u < total_units; u += ustride) {
+      const int nt = u % p.n_tiles;
+      const int rbp = 2 * ((u / p.n_tiles) % half_rbp) + (int)crank;
+      const int split = u / (p.n_tiles * half_rbp);
+      const int pt0 = split * per_split;
+      const int pt1 = min(pt0 + per_split, n_ptiles);
+      if (pt1 - pt0 <= 0) continue;
+      const int rb = 2 * rbp + (row >> 6);
+      const bool valid = rb < p.n_rb;
+      const int tap = rb / p.kchunks_in;
+      const int ci = (rb % p.kchunks_in) * 64 + (row & 63);
+      float* dst = p.dw + (int64_t)split * p.part_stride + (int64_t)tap * p.dw_tap_stride + (int64_t)ci * p.dw_row_stride +
+                   (int64_t)(nt * BLOCK_N) * p.dw_col_stride;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c0 = half * 32; c0 < BLOCK_N; c0 += 64) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        tmem_ld_wait();
+        if (valid) {
+          if (p.wide_store) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + c0 + 8 * i), "r"(r[8 * i]),
+                           "r"(r[8 * i + 1]), "r"(r[8 * i + 2]), "r"(r[8 * i + 3]), "r"(r[8 * i + 4]), "r"(r[8 * i + 5]),
+                           "r"(r[8 * i + 6]), "r"(r[8 * i + 7])
+                           : "memory");
+          } else {
+            float4* d4 = reinterpret_cast<float4*>(dst + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              d4[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                  __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(acc ? lead_tempty1 : lead_tempty0);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc_pair<C::kTmemCols>(tmem_base);
+}
+
 // Finishes a split-K igemm: out = epilogue(sum of the ksplits slices of ws) over [rows][C], 8 channels per thread.
 __global__ void __launch_bounds__(256) epilogue_finish_kernel(const float* __restrict__ ws, int ksplits, int64_t slice,
                                                               const float* __restrict__ bias,
@@ -2127,6 +2304,14 @@ int launch_wgrad_t(segk_ctx* ctx, const TensorMaps& maps, const WgradParams& p, 
   WgradParams q = p;
   q.wide_store = (((uintptr_t)p.dw & 31) == 0 && p.dw_col_stride == 1 && p.dw_row_stride % 8 == 0 && p.dw_tap_stride % 8 == 0 &&
                   p.part_stride % 8 == 0) ? 1 : 0;
+  if (BLOCK_N == 256 && ctx->pair && !q.skip_oob && !q.use_perm && (q.n_rbp & 1) == 0 && q.n_rb == 2 * q.n_rbp) {
+    // CTA pairs: two consecutive row-block pairs share the dy boxes (wgrad_pair_kernel)
+    const int units = q.splits * (q.n_rbp / 2) * q.n_tiles;
+    const int gp = units < ctx->sm_count / 2 ? units : ctx->sm_count / 2;
+    wgrad_pair_kernel<<<2 * gp, kWgradThreads, WCfg<256>::kSmemBytes, st>>>(maps, q, taps);
+    SEGK_LAUNCHED(ctx, "wgrad (CTA pairs)");
+    return SEGK_OK;
+  }
   wgrad_kernel<BLOCK_N><<<grid, kWgradThreads, C::kSmemBytes, st>>>(maps, q, taps);
   SEGK_LAUNCHED(ctx, "wgrad");
   return SEGK_OK;
@@ -3159,6 +3344,7 @@ int segk_tc_init(segk_ctx* ctx) {
   SEGK_SMEM_ATTR(wgrad_kernel<64>, WCfg<64>::kSmemBytes);
   SEGK_SMEM_ATTR(wgrad_kernel<128>, WCfg<128>::kSmemBytes);
   SEGK_SMEM_ATTR(wgrad_kernel<256>, WCfg<256>::kSmemBytes);
+  SEGK_SMEM_ATTR(wgrad_pair_kernel, WCfg<256>::kSmemBytes);
   SEGK_SMEM_ATTR(slab_kernel<64>, SlabCfg<64>::kSmemBytes);
   SEGK_SMEM_ATTR(slab_kernel<128>, SlabCfg<128>::kSmemBytes);
   SEGK_SMEM_ATTR(slab_kernel<256>, SlabCfg<256>::kSmemBytes);

@@ -647,11 +647,13 @@ def test_cta_pair_igemm_matches_single_cta_bit_for_bit(ops, cuda_device, shape):
             ops.conv2d_dgrad(dy, wd, dx, k, k, relu_mask_bits=xbits, residual=res, colsum=cs)
             dx2 = torch.empty_like(dx)
             ops.conv2d_dgrad(dy, wd, dx2, k, k, relu_mask=x)
+            dw = torch.empty((k, k, ci, co), dtype=torch.float32, device=cuda_device)
+            ops.conv2d_wgrad(x, dy, dw, k, k)            # (wgrad_pair_kernel for the 256-column layers whose boxes all contribute)
             torch.cuda.synchronize()
-            out[mode] = (y, bits, y2, pooled, idx, dx, cs, dx2)
+            out[mode] = (y, bits, y2, pooled, idx, dx, cs, dx2, dw)
     finally:
         ops.ctx.set_tuning("pair", 1)
-    names = ("fwd", "relu bits", "fwd (pool call)", "pooled", "pool idx", "dgrad", "dgrad column sums", "dgrad (bf16 mask)")
+    names = ("fwd", "relu bits", "fwd (pool call)", "pooled", "pool idx", "dgrad", "dgrad column sums", "dgrad (bf16 mask)", "wgrad")
     for a, c, name in zip(out[0], out[2], names):
         if name == "dgrad column sums":      # per-CTA partial rows: the grid (hence the fixed summation order) differs between the modes
             np.testing.assert_allclose(a.cpu().numpy(), c.cpu().numpy(), rtol=1e-4, atol=1e-3)
