@@ -674,6 +674,7 @@ def test_cta_pair_strided_conv_matches_single_cta(ops, cuda_device, shape):
     dy = bf16_grid(rng.standard_normal((n, 2 * h, 2 * w, co)))
     _, wd = ops.pack_deconv_weights(dev_f32(wt, cuda_device), 2)
     dyd = dev_bf16(dy, cuda_device)
+    xd = dev_bf16(bf16_grid(rng.standard_normal((n, h, w, ci))), cuda_device)
     out = {}
     try:
         for mode in (0, 1):
@@ -681,11 +682,18 @@ def test_cta_pair_strided_conv_matches_single_cta(ops, cuda_device, shape):
             dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=cuda_device)
             cs = torch.empty(ci, dtype=torch.float32, device=cuda_device)
             ops.deconv2d_dgrad(dyd, wd, dx, 4, 2, colsum=cs)
+            dw = torch.empty((4, 4, co, ci), dtype=torch.float32, device=cuda_device)
+            ops.deconv2d_wgrad(xd, dyd, dw, 4, 2)          # wgrad_pair_kernel when Cin % 256 == 0: decimated dy views as A, x boxes as B
             torch.cuda.synchronize()
-            out[mode] = (dx, cs)
+            out[mode] = (dx, cs, dw)
     finally:
         ops.ctx.set_tuning("pair", 1)
     assert torch.equal(out[0][0], out[1][0])
+    assert torch.equal(out[0][2], out[1][2]), "deconv wgrad: pair vs single-CTA"
+    xt = torch.tensor(host(xd), requires_grad=True)
+    wtt = torch.tensor(wt, requires_grad=True)
+    T.conv2d_transpose_same(xt, wtt, (2 * h, 2 * w), 2).backward(torch.tensor(dy))
+    assert_close(host(out[1][2]), wtt.grad.numpy(), TOL_F32, f"pair deconv wgrad {shape}")
     np.testing.assert_allclose(out[0][1].cpu().numpy(), out[1][1].cpu().numpy(), rtol=1e-4, atol=1e-3)
     # oracle: gradient of conv2d_transpose wrt its input = stride-2 conv of dy with W[k,k,Cout,Cin] read as HWIO [k,k,co,ci]
     ref = T.conv2d_same(torch.tensor(dy), torch.tensor(wt), stride=2).numpy()

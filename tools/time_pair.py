@@ -44,6 +44,7 @@ for name, n, h, w, ci, co, k in SHAPES:
     y = torch.empty((n, h, w, co), dtype=torch.bfloat16, device=dev)
     dx = torch.empty((n, h, w, ci), dtype=torch.bfloat16, device=dev)
     xb = torch.empty((n, h, w, ci // 32), dtype=torch.int32, device=dev)
+    dw = torch.empty((k, k, ci, co), dtype=torch.float32, device=dev)
     ops.relu_bits(x, xb)
     res = {}
     for rep in range(2):
@@ -51,9 +52,11 @@ for name, n, h, w, ci, co, k in SHAPES:
             ops.ctx.set_tuning("pair", mode)
             f = timeit(lambda: ops.conv2d_fwd(x, wk, b, y, k, k, relu=True))
             d = timeit(lambda: ops.conv2d_dgrad(dy, wd, dx, k, k, relu_mask_bits=xb))
-            res.setdefault(mode, []).append((f, d))
+            g = timeit(lambda: ops.conv2d_wgrad(x, dy, dw, k, k))
+            res.setdefault(mode, []).append((f, d, g))
     ops.ctx.set_tuning("pair", 1)
-    s = " | ".join("pair=%d fwd %.1f dgrad %.1f" % (m, min(r[0] for r in res[m]), min(r[1] for r in res[m])) for m in (0, 1))
+    s = " | ".join("pair=%d fwd %.1f dgrad %.1f wgrad %.1f" % (m, min(r[0] for r in res[m]), min(r[1] for r in res[m]), min(r[2] for r in res[m]))
+                   for m in (0, 1))
     print(f"{name:28s} {s}", flush=True)
 
 # the stride-2 implicit GEMM (input gradient of the 4x4 / stride-2 transposed convs of U-Net / SegNet)
