@@ -1631,6 +1631,44 @@ wgrad_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ Wg
   if (warp == 1) tmem_dealloc<C::kTmemCols>(tmem_base);
 }
 
+// wgrad_pair_kernel: the (dx, dy) of the four row blocks of a CTA pair (row-block pairs 2 rp and 2 rp + 1) and which pixel boxes
+// the pair walks: those at least one of the four shifted x boxes of which touches the image (all of them without skip_oob,
+// or when none does: the item still has to produce its zeros)
+struct PairTaps {
+  int dx[4], dy[4];
+};
+__device__ __forceinline__ PairTaps pair_taps(const WgradParams& p, const TapTable& taps, int rp) {
+  PairTaps t;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int rb = 4 * rp + i;
+    if (rb >= p.n_rb) rb = p.n_rb - 1;
+    const int tap = rb / p.kchunks_in;
+    t.dx[i] = taps.dx[tap];
+    t.dy[i] = taps.dy[tap];
+  }
+  return t;
+}
+__device__ __forceinline__ bool pair_box_active(const WgradParams& p, const PairTaps& t, int x0, int y0) {
+  bool any = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int xa = x0 + t.dx[i], ya = y0 + t.dy[i];
+    any |= !(ya + p.bh <= 0 || ya >= p.H || xa + p.bw <= 0 || xa >= p.W);
+  }
+  return any;
+}
+// active boxes among pixel tiles [pt0, pt1), counted by the whole warp
+__device__ __forceinline__ int pair_count_active(const WgradParams& p, const PairTaps& t, int pt0, int pt1, int lane) {
+  if (!p.skip_oob) return pt1 - pt0;
+  int n = 0;
+  for (int pt = pt0 + lane; pt < pt1; pt += 32) {
+    const int x0 = (pt % p.tiles_w) * p.bw, y0 = ((pt / p.tiles_w) % p.tiles_h) * p.bh;
+    n += pair_box_active(p, t, x0, y0) ? 1 : 0;
+  }
+  return __reduce_add_sync(0xffffffffu, n);
+}
+
 // wgrad_pair_kernel: the 256-column weight-gradient GEMM as CTA pairs (cta_group::2, M = 256).  CTAs 2q / 2q+1 of a cluster take
 // two CONSECUTIVE row-block pairs (different taps / input-channel chunks: 2 x 128 dW rows) of the same channel tile and pixel
 // split; both need the same dy boxes as their B operand, so each CTA stages its own two 8 KB x boxes and HALF of the dy box
@@ -1694,7 +1732,10 @@ wgrad_pair_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
       int x0 = (pt0 % p.tiles_w) * p.bw;
       int y0 = ((pt0 / p.tiles_w) % p.tiles_h) * p.bh;
       int n0 = (pt0 / (p.tiles_w * p.tiles_h)) * p.bn;
+      const PairTaps pt4 = pair_taps(p, taps, (u / p.n_tiles) % half_rbp);
+      const bool all = !p.skip_oob || pair_count_active(p, pt4, pt0, pt1, lane) == 0;
       for (int pt = pt0; pt < pt1; ++pt) {
+        if (all || pair_box_active(p, pt4, x0, y0)) {
         mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + ps.stage * kWPairStageBytes;
@@ -1708,6 +1749,7 @@ wgrad_pair_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
         }
         __syncwarp();
         ps.advance<kWPairStages>();
+        }
         x0 += p.bw;
         if (x0 >= p.tiles_w * p.bw) {
           x0 = 0;
@@ -1727,7 +1769,11 @@ wgrad_pair_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant
       const int pt0 = split * per_split;
       const int pt1 = min(pt0 + per_split, n_ptiles);
       if (pt1 - pt0 <= 0) continue;
-      const int nboxes = pt1 - pt0;
+      int nboxes = pt1 - pt0;
+      if (p.skip_oob) {
+        const int na = pair_count_active(p, pair_taps(p, taps, (u / p.n_tiles) % half_rbp), pt0, pt1, lane);
+        if (na > 0) nboxes = na;
+      }
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_addr = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -2304,7 +2350,7 @@ int launch_wgrad_t(segk_ctx* ctx, const TensorMaps& maps, const WgradParams& p, 
   WgradParams q = p;
   q.wide_store = (((uintptr_t)p.dw & 31) == 0 && p.dw_col_stride == 1 && p.dw_row_stride % 8 == 0 && p.dw_tap_stride % 8 == 0 &&
                   p.part_stride % 8 == 0) ? 1 : 0;
-  if (BLOCK_N == 256 && ctx->pair && !q.skip_oob && !q.use_perm && (q.n_rbp & 1) == 0 && q.n_rb == 2 * q.n_rbp) {
+  if (BLOCK_N == 256 && ctx->pair && !q.use_perm && (q.n_rbp & 1) == 0 && q.n_rb == 2 * q.n_rbp) {
     // CTA pairs: two consecutive row-block pairs share the dy boxes (wgrad_pair_kernel)
     const int units = q.splits * (q.n_rbp / 2) * q.n_tiles;
     const int gp = units < ctx->sm_count / 2 ? units : ctx->sm_count / 2;
