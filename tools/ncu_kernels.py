@@ -1,5 +1,5 @@
 """One launch of every tensor-core kernel variant at its FCN-8s training shape (B=32, 160x576), three
-rounds, for `ncu --set full --import-source on -k regex:'^(igemm_kernel|igemm_pair_kernel|wgrad_kernel|slab_kernel|
+rounds, for `ncu --set full --import-source on -k regex:'^(igemm_kernel|igemm_pair_kernel|wgrad_kernel|wgrad_pair_kernel|slab_kernel|
 slab3_kernel|wslab_kernel|first_fwd_kernel|first_wgrad_kernel)$' -s 26 -c 13` (13 matching launches per
 round; the first two rounds are warm-up).  Prints the launch order."""
 import os, sys

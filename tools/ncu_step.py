@@ -1,6 +1,6 @@
 """One FCN-8s training step (B=32, 160x576) for an ncu capture of every tensor-core launch in it.
 Plain run: writes the ordered list of tensor-core calls of step 3 to gpurun_out/step_calls.json and
-their count K to gpurun_out/step_k.txt.  Under ncu use  -k regex:'^(igemm_kernel|igemm_pair_kernel|wgrad_kernel|slab_kernel|slab3_kernel|wslab_kernel|first_fwd_kernel|first_wgrad_kernel)$'
+their count K to gpurun_out/step_k.txt.  Under ncu use  -k regex:'^(igemm_kernel|igemm_pair_kernel|wgrad_kernel|wgrad_pair_kernel|slab_kernel|slab3_kernel|wslab_kernel|first_fwd_kernel|first_wgrad_kernel)$'
 -s $((2*K)) -c K  (the two warm-up steps launch 2K matching kernels).  Use --metrics + --csv (a
 --set full report of ~60 launches exceeds gpurun's 64 MiB return limit)."""
 import json, os, sys
