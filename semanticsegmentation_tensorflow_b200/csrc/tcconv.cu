@@ -74,6 +74,7 @@ struct alignas(64) TensorMaps {
   CUtensorMap b;
   CUtensorMap c;   // output tensor (TMA-store epilogue), box (64 ch, bw, bh, bn)
   CUtensorMap b2;  // CTA-pair mode: the weights with a box of BLOCK_N / 2 rows (each CTA stages half of the B tile)
+  CUtensorMap cph[4];  // stride-2 transposed conv: the output pixels of phase (ay, ax) as a decimated view (TMA-store epilogue)
 };
 
 struct TapTable {
@@ -791,7 +792,13 @@ __device__ __forceinline__ void igemm_body(const TensorMaps& maps, const IgemmPa
           fence_proxy_async();                        // generic-proxy smem writes -> visible to the TMA engine
           named_bar_sync(1, kEpiThreads);
           if (ep_leader && !p.pool_only && t.n0 < p.N) {      // (n0 >= N: the odd tile's partner in CTA-pair mode)
-            tma_store_4d(&maps.c, sbuf, t.nt * BLOCK_N + g0, t.x0, t.y0, t.n0);
+            if (p.phases > 1) {
+              // transposed conv: out pixel = q * s + a - opad; phase (ay, ax)'s pixels are a decimated view of y whose
+              // index is q (a >= opad) or q - 1 (a < opad: q = 0 falls outside the view and is clipped by the store)
+              tma_store_4d(&maps.cph[t.phase], sbuf, t.nt * BLOCK_N + g0, t.x0 - (ax < p.opad ? 1 : 0), t.y0 - (ay < p.opad ? 1 : 0), t.n0);
+            } else {
+              tma_store_4d(&maps.c, sbuf, t.nt * BLOCK_N + g0, t.x0, t.y0, t.n0);
+            }
             tma_store_commit();
           }
           ++sg;
@@ -2828,6 +2835,20 @@ int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float*
   p.bias = bias; p.residual = (const bf16*)residual; p.mask = nullptr;
   p.scale = 1.f; p.relu = (flags & SEGK_EPI_RELU) ? 1 : 0;
   p.ksplits = 1; p.ws = nullptr;
+  if (s == 2 && !p.out_f32 && ctx->tma_store) {
+    // bf16 output through shared memory + TMA store, one decimated view of y per phase: phase (ay, ax) owns the pixels
+    // (2 j + (ay + 1) % 2, 2 i + (ax + 1) % 2) -- coalesced 128-byte rows instead of 64-byte pieces at every other pixel
+    const int OH = H * s, OW = W * s;
+    for (int ay = 0; ay < s; ++ay)
+      for (int ax = 0; ax < s; ++ax) {
+        const int oy0 = (ay - s / 2 + s) % s, ox0 = (ax - s / 2 + s) % s;
+        const bf16* v = (const bf16*)y + ((int64_t)oy0 * OW + ox0) * ldy;
+        rc = encode_act_map(ctx, &maps.cph[ay * s + ax], v, N, H, W, Cout, (int64_t)s * ldy, (int64_t)s * OW * ldy, (int64_t)OH * OW * ldy,
+                            b.bw, b.bh, b.bn);
+        if (rc) return rc;
+      }
+    p.tma_store = 1;
+  }
   TapTable taps;
   memset(&taps, 0, sizeof(taps));
   for (int u = 0; u < 4; ++u) {
