@@ -166,6 +166,16 @@ struct TileCoord {
   int nt, x0, y0, n0, phase, split;
 };
 
+// Transposed conv (phases > 1): out pixel = q * s + a - opad.  A phase with a < opad produces nothing at q = 0 and its last
+// pixel at q = H (W), one with a >= opad covers q = 0 .. H - 1: every phase has exactly H x W rows, starting at q = 1 or 0.
+// The tiles are laid over that H x W range and shifted here (no (H+1) x (W+1) grid with an empty border row per phase).
+__device__ __forceinline__ void phase_origin(const IgemmParams& p, TileCoord& t) {
+  if (p.phases > 1) {
+    t.x0 += (t.phase % p.s) < p.opad ? 1 : 0;
+    t.y0 += (t.phase / p.s) < p.opad ? 1 : 0;
+  }
+}
+
 __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile) {
   TileCoord t;
   t.split = 0;
@@ -182,6 +192,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
     r /= p.tiles_w;
     t.y0 = (r % p.tiles_h) * p.bh;
     t.n0 = (r / p.tiles_h) * p.bn;
+    phase_origin(p, t);
     return t;
   }
   t.nt = tile % p.n_tiles;
@@ -192,6 +203,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmParams& p, int tile)
   r /= p.tiles_h;
   t.n0 = (r % p.tiles_n) * p.bn;
   t.phase = r / p.tiles_n;
+  phase_origin(p, t);
   return t;
 }
 
@@ -2811,7 +2823,7 @@ int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float*
   SEGK_REQUIRE(ctx, Cin % 64 == 0 && Cout % 64 == 0 && Cin > 0 && Cout > 0,
                "deconv2d_fwd: tensor-core path needs channels %% 64 == 0 (got %d -> %d); use segk_deconv2d_small_fwd", Cin,
                Cout);
-  const Box b = choose_box(N, H + 1, W + 1, kBlockM, false, H, W);
+  const Box b = choose_box(N, H, W, kBlockM, false);
   SEGK_REQUIRE(ctx, b.rows > 0, "deconv2d_fwd: no pixel box");
   const int block_n = pick_block_n(ctx, Cout);
   TensorMaps maps;
@@ -2823,9 +2835,9 @@ int segk_deconv2d_fwd(segk_ctx* ctx, const void* x, const void* wk, const float*
   if (rc) return rc;
   IgemmParams p;
   memset(&p, 0, sizeof(p));
-  p.N = N; p.H = H + 1; p.W = W + 1;
+  p.N = N; p.H = H + 1; p.W = W + 1;                 // bounds of q; the tiles cover H x W of it per phase (phase_origin)
   p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.rows;
-  p.tiles_w = ceil_div(W + 1, b.bw); p.tiles_h = ceil_div(H + 1, b.bh); p.tiles_n = ceil_div(N, b.bn);
+  p.tiles_w = ceil_div(W, b.bw); p.tiles_h = ceil_div(H, b.bh); p.tiles_n = ceil_div(N, b.bn);
   p.n_tiles = Cout / block_n;
   p.phases = s * s; p.s = s;
   p.ntaps = 4; p.kchunks = Cin / 64;
