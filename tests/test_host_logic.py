@@ -357,3 +357,66 @@ def test_channel_slice_view_pitch():
     odd = torch.zeros((1, 2, 2, 100), dtype=torch.bfloat16)
     with pytest.raises(ValueError):
         _pitch(odd[..., :64])                                # pitch not a multiple of 8 channels
+
+
+def test_adam_apply_and_repack_planning_for_folded_bn_layers():
+    """AdamOptimizer.apply_and_repack on a graph model (BN scale folded into the packed weights): which variables take the
+    fused Adam + fold + repack kernel, in which order, and what happens when a gradient bucket separates a layer's weights
+    from its gamma.  Pure host logic: the ops are recorded, nothing runs."""
+    import torch
+    from collections import OrderedDict
+    from semanticsegmentation_tensorflow_b200.fcn import AdamOptimizer
+    from semanticsegmentation_tensorflow_b200.graph import _Vars, BN_SCALE
+
+    shapes = OrderedDict([("conv1/weights", (3, 3, 3, 64)), ("bn0/gamma", (64,)), ("bn0/beta", (64,)),
+                          ("conv2/weights", (3, 3, 64, 64)), ("bn1/gamma", (64,)), ("bn1/beta", (64,)),
+                          ("up/weights", (4, 4, 64, 64)),
+                          ("conv3/weights", (3, 3, 64, 128)), ("bn2/gamma", (128,)), ("bn2/beta", (128,)),
+                          ("head/weights", (1, 1, 128, 2))])
+    V = _Vars(shapes, "cpu", {})
+    V.m, V.v = torch.zeros_like(V.p), torch.zeros_like(V.p)
+    V.fold_mult = BN_SCALE
+    V.fused_adam_layers = {"conv2": "bn1/gamma", "conv3": "bn2/gamma"}      # tensor-core routes; conv1 (first layer), up, head are not
+    V.wk = {"conv2": "wk2", "conv3": "wk3"}
+    V.wd = {"conv2": "wd2", "conv3": "wd3"}
+    calls = []
+
+    class Rec:
+        def adam_step_ranges(self, p, m, v, g, ranges, *a):
+            calls.append(("ranges", list(ranges)))
+
+        def adam_pack_conv_weights(self, p, m, v, g, wk, wd, *a, col_scale=None, col_mult=1.0):
+            calls.append(("pack", wk, None if col_scale is None else col_scale.data_ptr(), col_mult))
+
+    V._repack = lambda ops, only: calls.append(("repack", set(only)))
+
+    class Net:
+        vars, ops = V, Rec()
+
+    opt = AdamOptimizer(1e-4)
+    opt.t = 1                      # (TrainStep increments the step count before the update)
+    off = {k: (s.offset, s.size) for k, s in V.slots.items()}
+
+    # the whole arena: small variables first (gamma is updated before its weights are packed with it), then the fused layers
+    opt.apply_and_repack(Net)
+    assert calls[0][0] == "ranges"
+    assert sorted(calls[0][1]) == sorted(off[k] for k in shapes if k not in ("conv2/weights", "conv3/weights"))
+    packs = [c for c in calls if c[0] == "pack"]
+    assert {c[1] for c in packs} == {"wk2", "wk3"} and all(c[3] == BN_SCALE for c in packs)
+    assert {c[2] for c in packs} == {V.view(V.p, "bn1/gamma").data_ptr(), V.view(V.p, "bn2/gamma").data_ptr()}
+    assert calls.index(packs[0]) > 0 and calls[-1] == ("repack", {"conv1", "up", "head"})
+
+    # a bucket that ends between conv2's weights and its gamma: the layer takes the separate path and is repacked now...
+    calls.clear()
+    lo, hi = off["conv1/weights"][0], off["bn1/gamma"][0]
+    opt.apply_and_repack(Net, lo, hi)
+    assert [c[0] for c in calls] == ["ranges", "repack"]
+    assert off["conv2/weights"] in calls[0][1] and calls[1][1] == {"conv1", "conv2"}
+    # ... and again when the bucket with its gamma is applied (the packed copy must carry the new gamma)
+    calls.clear()
+    opt.apply_and_repack(Net, off["bn1/gamma"][0], off["conv3/weights"][0])
+    assert [c[0] for c in calls] == ["ranges", "repack"] and calls[1][1] == {"conv2", "up"}
+    # a bucket holding conv3's weights AND gamma fuses it
+    calls.clear()
+    opt.apply_and_repack(Net, off["conv3/weights"][0], V.total)
+    assert [c[0] for c in calls] == ["ranges", "pack", "repack"] and calls[1][1] == "wk3" and calls[2][1] == {"head"}
