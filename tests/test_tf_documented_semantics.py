@@ -116,3 +116,30 @@ def test_reduce_max_gradient_shares_ties_and_bilinear_align_corners_and_dropout(
     np.testing.assert_allclose(r2[0, 0, :, 0].numpy(), [0.0, 1.5, 3.0, 4.5, 6.0], rtol=1e-6)
     d = T.dropout(torch.tensor([1.0, 2.0, 3.0, 4.0]), 0.8, torch.tensor([1.0, 0.0, 1.0, 1.0]))
     np.testing.assert_allclose(d.numpy(), [1.25, 0.0, 3.75, 5.0], rtol=1e-6)
+
+
+def test_depthwise_conv_avg_pool_and_same_max_pool_known_answers():
+    """tf.nn.depthwise_conv2d (documented: output[b,i,j,k] = sum_{di,dj} filter[di,dj,k,0] * input[b, s i + r di, s j + r dj, k],
+    SAME padding by the padding rule above with the EFFECTIVE filter size (k - 1) r + 1), tf.nn.avg_pool VALID (windows that
+    do not fit are dropped) and tf.nn.max_pool SAME (padding never wins), each by hand."""
+    # depthwise 1x3 filter [1, 10, 100] per channel, two channels scaled 1 and 2, stride 1, rate 1: y[j] = x[j-1] + 10 x[j] + 100 x[j+1]
+    x = torch.tensor([1., 2., 3., 4.]).reshape(1, 1, 4, 1).repeat(1, 1, 1, 2)
+    w = torch.tensor([1., 10., 100.]).reshape(1, 3, 1) * torch.tensor([1., 2.])
+    y = T.depthwise_conv2d_same(x, w, 1, 1)
+    assert y[0, 0, :, 0].tolist() == [210., 321., 432., 43.] and y[0, 0, :, 1].tolist() == [420., 642., 864., 86.]
+    # rate 2: taps at j-2, j, j+2 (effective size 5, SAME pads 2 + 2)
+    y = T.depthwise_conv2d_same(x[..., :1], w[..., :1], 1, 2)
+    assert y[0, 0, :, 0].tolist() == [310., 420., 31., 42.]
+    # stride 2, in = 4, k = 3: out = 2, pad_total = (2 - 1) 2 + 3 - 4 = 1 -> before 0, after 1: windows start at 0 and 2
+    y = T.depthwise_conv2d_same(x[..., :1], w[..., :1], 2, 1)
+    assert y[0, 0, :, 0].tolist() == [321., 43.]                      # x0 + 10 x1 + 100 x2, x2 + 10 x3 + 100 * pad
+    # avg_pool 2x2 / stride 2 VALID on 3x5: the last row / column do not fit and are dropped
+    a = torch.arange(15, dtype=torch.float32).reshape(1, 3, 5, 1)
+    assert T.avg_pool_valid(a, 2, 2, 2, 2)[0, :, :, 0].tolist() == [[3.0, 5.0]]
+    # PSPNet's 1x3 window with stride (1, 3) on one 1x6 row (PSPNet.py:165)
+    assert T.avg_pool_valid(a[:, :1, :, :].repeat(1, 1, 1, 1)[:, :, :3, :], 1, 3, 1, 3)[0, 0, :, 0].tolist() == [1.0]
+    # max_pool 3x3 / stride 2 SAME on all-negative values: the zero-valued padding of a naive implementation would win; TF's does not
+    m = -torch.arange(1, 17, dtype=torch.float32).reshape(1, 4, 4, 1)
+    ym, idx = T.max_pool_general(m, 3, 3, 2, "SAME")                    # in 4, k 3, s 2: out 2, pad_total 1 -> before 0, after 1
+    assert ym[0, :, :, 0].tolist() == [[-1., -3.], [-9., -11.]]
+    assert idx[0, :, :, 0].tolist() == [[0, 0], [0, 0]]                 # the window's first element is its maximum here
