@@ -420,3 +420,11 @@ def test_adam_apply_and_repack_planning_for_folded_bn_layers():
     calls.clear()
     opt.apply_and_repack(Net, off["conv3/weights"][0], V.total)
     assert [c[0] for c in calls] == ["ranges", "pack", "repack"] and calls[1][1] == "wk3" and calls[2][1] == {"head"}
+
+
+def test_measurement_scripts_compile():
+    """bench.py, __graft_entry__.py and every script under tools/ at least parse (they only run on a GPU box)."""
+    import glob
+    import py_compile
+    for path in [os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")] + sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))):
+        py_compile.compile(path, doraise=True)
